@@ -1,0 +1,220 @@
+// a1 -- spherical range projection + min-depth z-buffer for a CSR batch of scans.
+//
+// Replaces RangeProjection.doProjection (reference
+// pc_processor/dataset/preprocess/projection.py:43-115).  Compiled with
+// -fmad=false: every float32 operation after the transcendentals must round
+// exactly like the reference's separate numpy ufuncs.
+//
+// Two kernels, both HBM-bound:
+//   project_points : 1 thread / point.  128-bit load of (x,y,z,i); depth, yaw,
+//                    pitch, pixel; writes uproj_x/y/depth; 64-bit atomicMin of
+//                    (depth_key << 32 | point_index) into the z-buffer.
+//   resolve_pixels : 1 thread / pixel.  Decodes the winner, gathers its point,
+//                    writes range / pointcloud / idx / mask with coalesced
+//                    (128-bit for the pointcloud) stores.
+//
+// Transcendentals.  The oracle's rule is the correctly rounded float32
+// arctan2 / arcsin.  Evaluating both in fp64 for every point costs ~150 DFMA
+// per point and would make the kernel FP64-pipe bound (B200: 64 DFMA/clk/SM),
+// so the kernel first evaluates atan2f/asinf (<= 2 ulp) and only re-evaluates
+// in fp64 when the scaled coordinate lies within a proven error bound of a
+// pixel boundary (the only case where the floor could differ): ~0.5 % of
+// points.  C3D_PROJECT_F64_ONLY=1 forces the fp64 path for every point.
+#include <stdlib.h>
+
+#include "common.cuh"
+
+namespace c3d {
+
+__device__ __forceinline__ uint32_t depth_key(float d) {
+  uint32_t b = __float_as_uint(d);
+  return (b >> 31) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float key_depth(uint32_t k) {
+  return __uint_as_float((k >> 31) ? (k & 0x7fffffffu) : ~k);
+}
+
+struct ProjParams {
+  float abs_left, fov_hori, abs_down, fov_vert;  // float32-rounded Python floats
+  float wf, hf, wmax, hmax;
+  float tol_x, tol_y;  // hybrid guard bands, in pixels
+  int H, W;
+};
+
+template <bool kHybrid>
+__device__ __forceinline__ void pixel_of(float x, float y, float q, const ProjParams& p,
+                                         int& px, int& py, bool& nan) {
+  float yaw, pitch, fx, fy;
+  if (kHybrid) {
+    yaw = -atan2f(y, x);
+    pitch = asinf(q);
+    fx = ((yaw + p.abs_left) / p.fov_hori) * p.wf;
+    fy = (1.0f - (pitch + p.abs_down) / p.fov_vert) * p.hf;
+    // !(a > b) also catches NaN
+    bool near_x = !(fabsf(fx - rintf(fx)) > p.tol_x);
+    bool near_y = !(fabsf(fy - rintf(fy)) > p.tol_y);
+    if (near_x) {
+      yaw = -(float)atan2((double)y, (double)x);
+      fx = ((yaw + p.abs_left) / p.fov_hori) * p.wf;
+    }
+    if (near_y) {
+      pitch = (float)asin((double)q);
+      fy = (1.0f - (pitch + p.abs_down) / p.fov_vert) * p.hf;
+    }
+  } else {
+    yaw = -(float)atan2((double)y, (double)x);
+    pitch = (float)asin((double)q);
+    fx = ((yaw + p.abs_left) / p.fov_hori) * p.wf;
+    fy = (1.0f - (pitch + p.abs_down) / p.fov_vert) * p.hf;
+  }
+  nan = (fx != fx) || (fy != fy);
+  px = (int)fmaxf(fminf(p.wmax, floorf(fx)), 0.0f);
+  py = (int)fmaxf(fminf(p.hmax, floorf(fy)), 0.0f);
+}
+
+template <bool kHybrid, bool kC4>
+__global__ void __launch_bounds__(256)
+project_points_kernel(const float* __restrict__ points, int c_in,
+                      const int32_t* __restrict__ offsets, int batch, int total,
+                      const float* __restrict__ depth_override, ProjParams p,
+                      int32_t* __restrict__ upx, int32_t* __restrict__ upy,
+                      float* __restrict__ udepth, unsigned long long* __restrict__ zbuf,
+                      int32_t* __restrict__ flags) {
+  extern __shared__ int32_t s_off[];
+  for (int i = threadIdx.x; i <= batch; i += blockDim.x) s_off[i] = offsets[i];
+  __syncthreads();
+  const int HW = p.H * p.W;
+  bool any_nan = false;
+  for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < total; g += gridDim.x * blockDim.x) {
+    float x, y, z;
+    if (kC4) {
+      float4 v = __ldg(reinterpret_cast<const float4*>(points) + g);  // keep in L2 for resolve
+      x = v.x; y = v.y; z = v.z;
+    } else {
+      const float* r = points + (size_t)g * c_in;
+      x = r[0]; y = r[1]; z = r[2];
+    }
+    float depth = depth_override ? depth_override[g] : sqrtf((x * x + y * y) + z * z);
+    float q = z / depth;
+    int px, py; bool nan;
+    pixel_of<kHybrid>(x, y, q, p, px, py, nan);
+    any_nan |= nan;
+    upx[g] = px; upy[g] = py; udepth[g] = depth;
+    int b = scan_of(s_off, batch, g);
+    unsigned long long key =
+        ((unsigned long long)depth_key(depth) << 32) | (uint32_t)(g - s_off[b]);
+    atomicMin(zbuf + (size_t)b * HW + py * p.W + px, key);
+  }
+  if (any_nan) atomicOr(flags, 1);
+}
+
+template <bool kC4>
+__global__ void __launch_bounds__(256)
+resolve_pixels_kernel(const float* __restrict__ points, int c_in,
+                      const int32_t* __restrict__ offsets, int HW, long long total_px,
+                      const unsigned long long* __restrict__ zbuf,
+                      float* __restrict__ proj_range, float* __restrict__ proj_pc,
+                      int32_t* __restrict__ proj_idx, int32_t* __restrict__ proj_mask) {
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < total_px;
+       q += (long long)gridDim.x * blockDim.x) {
+    unsigned long long key = __ldcs(zbuf + q);
+    if (key == ~0ull) {
+      proj_range[q] = -1.0f; proj_idx[q] = -1; proj_mask[q] = 0;
+      if (kC4) {
+        st_stream(reinterpret_cast<float4*>(proj_pc) + q, make_float4(-1.f, -1.f, -1.f, -1.f));
+      } else {
+        for (int c = 0; c < c_in; ++c) proj_pc[q * c_in + c] = -1.0f;
+      }
+    } else {
+      int idx = (int)(uint32_t)key;
+      int b = (int)(q / HW);
+      size_t row = (size_t)offsets[b] + idx;
+      proj_range[q] = key_depth((uint32_t)(key >> 32));
+      proj_idx[q] = idx;
+      proj_mask[q] = idx > 0;  // projection.py:113
+      if (kC4) {
+        float4 v = __ldg(reinterpret_cast<const float4*>(points) + row);
+        st_stream(reinterpret_cast<float4*>(proj_pc) + q, v);
+      } else {
+        for (int c = 0; c < c_in; ++c) proj_pc[q * c_in + c] = points[row * c_in + c];
+      }
+    }
+  }
+}
+
+}  // namespace c3d
+
+using namespace c3d;
+
+extern "C" size_t c3d_project_workspace_bytes(int batch, int proj_h, int proj_w) {
+  if (batch <= 0 || proj_h <= 0 || proj_w <= 0) return 0;
+  return (size_t)batch * proj_h * proj_w * sizeof(unsigned long long);
+}
+
+extern "C" int c3d_project_batch(
+    const float* points, int c_in, const int32_t* offsets, int batch, int64_t total_points,
+    const float* depth_override, double abs_fov_left, double fov_hori, double abs_fov_down,
+    double fov_vert, int proj_h, int proj_w, float* proj_range, float* proj_pointcloud,
+    int32_t* proj_idx, int32_t* proj_mask, int32_t* uproj_x_idx, int32_t* uproj_y_idx,
+    float* uproj_depth, void* workspace, int32_t* status_flags, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  C3D_REQUIRE(batch > 0 && batch <= kMaxBatch, "batch must be in [1, %d], got %d", kMaxBatch, batch);
+  C3D_REQUIRE(c_in >= 3, "c_in must be >= 3, got %d", c_in);
+  C3D_REQUIRE(proj_h > 0 && proj_w > 0, "bad image size %dx%d", proj_h, proj_w);
+  C3D_REQUIRE(total_points >= 0 && total_points < (1ll << 31), "total_points out of range");
+  C3D_REQUIRE((long long)batch * proj_h * proj_w < (1ll << 31), "batch*H*W must be < 2^31");
+  C3D_REQUIRE(fov_hori > 0 && fov_vert > 0, "field of view must be positive");
+  C3D_REQUIRE(offsets && proj_range && proj_pointcloud && proj_idx && proj_mask && workspace &&
+              status_flags, "null pointer argument");
+  C3D_REQUIRE(total_points == 0 || (points && uproj_x_idx && uproj_y_idx && uproj_depth),
+              "null per-point pointer");
+
+  ProjParams p;
+  p.abs_left = (float)abs_fov_left; p.fov_hori = (float)fov_hori;
+  p.abs_down = (float)abs_fov_down; p.fov_vert = (float)fov_vert;
+  p.wf = (float)proj_w; p.hf = (float)proj_h;
+  p.wmax = (float)(proj_w - 1); p.hmax = (float)(proj_h - 1);
+  p.H = proj_h; p.W = proj_w;
+  // Guard bands: |fast - exact| chain error bounds (projection),
+  // with a 2.5x margin.  atan2f/asinf <= 2 ulp (CUDA math API), |yaw| <= pi,
+  // |pitch| <= pi/2, then add / divide / multiply roundings.
+  p.tol_x = p.wf * 1.0e-6f;
+  p.tol_y = p.hf * (2.0e-6f / p.fov_vert + 1.0e-6f);
+
+  const long long total_px = (long long)batch * proj_h * proj_w;
+  auto* zbuf = reinterpret_cast<unsigned long long*>(workspace);
+  C3D_CUDA(cudaMemsetAsync(zbuf, 0xFF, (size_t)total_px * sizeof(unsigned long long), stream));
+
+  const bool c4 = (c_in == 4) && ((reinterpret_cast<uintptr_t>(points) & 15) == 0) &&
+                  ((reinterpret_cast<uintptr_t>(proj_pointcloud) & 15) == 0);
+  const char* env = getenv("C3D_PROJECT_F64_ONLY");
+  const bool hybrid = !(env && env[0] == '1');
+  const int threads = 256;
+  if (total_points > 0) {
+    int grid = wave_grid(total_points, threads, 8);
+    size_t smem = (size_t)(batch + 1) * sizeof(int32_t);
+#define LAUNCH_PP(HY, C4)                                                                   \
+  project_points_kernel<HY, C4><<<grid, threads, smem, stream>>>(                           \
+      points, c_in, offsets, batch, (int)total_points, depth_override, p, uproj_x_idx,      \
+      uproj_y_idx, uproj_depth, zbuf, status_flags)
+    if (hybrid) { if (c4) LAUNCH_PP(true, true); else LAUNCH_PP(true, false); }
+    else        { if (c4) LAUNCH_PP(false, true); else LAUNCH_PP(false, false); }
+#undef LAUNCH_PP
+    int rc = check_launch("project_points_kernel");
+    if (rc) return rc;
+  }
+  {
+    int grid = wave_grid(total_px, threads, 8);
+    if (c4)
+      resolve_pixels_kernel<true><<<grid, threads, 0, stream>>>(
+          points, c_in, offsets, proj_h * proj_w, total_px, zbuf, proj_range, proj_pointcloud,
+          proj_idx, proj_mask);
+    else
+      resolve_pixels_kernel<false><<<grid, threads, 0, stream>>>(
+          points, c_in, offsets, proj_h * proj_w, total_px, zbuf, proj_range, proj_pointcloud,
+          proj_idx, proj_mask);
+    int rc = check_launch("resolve_pixels_kernel");
+    if (rc) return rc;
+  }
+  return C3D_OK;
+}

@@ -1,0 +1,165 @@
+"""Tensor-level batched API over the C ABI (device tensors in, device tensors out).
+
+These are the throughput entry points: a CSR batch of scans per call, all work
+enqueued on torch's current CUDA stream, no host synchronisation.  The
+reference-shaped classes in `coarse3d_b200.pc_processor` are thin adapters over
+these functions.
+"""
+import ctypes
+import math
+from typing import NamedTuple, Optional
+
+import torch
+
+from . import _lib
+from ._lib import check, lib
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _need_cuda(**tensors):
+    for name, t in tensors.items():
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("coarse3d_b200: `%s` must be a CUDA tensor (no CPU path)" % name)
+        if not t.is_contiguous():
+            raise ValueError("coarse3d_b200: `%s` must be contiguous" % name)
+
+
+# --------------------------------------------------------------------- a1 --
+class Fov(NamedTuple):
+    """The angles RangeProjection.__init__ stores (projection.py:29-35), radians."""
+    abs_fov_left: float
+    fov_hori: float
+    abs_fov_down: float
+    fov_vert: float
+
+    @staticmethod
+    def from_degrees(fov_up=3, fov_down=-25, fov_left=-180, fov_right=180):
+        up = fov_up / 180.0 * math.pi
+        down = fov_down / 180.0 * math.pi
+        left = fov_left / 180.0 * math.pi
+        right = fov_right / 180.0 * math.pi
+        return Fov(abs(left), abs(left) + abs(right), abs(down), abs(up) + abs(down))
+
+
+class Projection(NamedTuple):
+    proj_pointcloud: torch.Tensor  # (B,H,W,C) f32
+    proj_range: torch.Tensor       # (B,H,W) f32
+    proj_idx: torch.Tensor         # (B,H,W) i32, index within the scan
+    proj_mask: torch.Tensor        # (B,H,W) i32
+    uproj_x_idx: torch.Tensor      # (sum N,) i32
+    uproj_y_idx: torch.Tensor      # (sum N,) i32
+    uproj_depth: torch.Tensor      # (sum N,) f32
+    flags: torch.Tensor            # (1,) i32; bit 0: NaN pixel coordinate
+
+
+class ProjectionBuffers:
+    """Pre-allocated outputs + z-buffer scratch, reusable across calls (and
+    stable addresses for CUDA-graph capture)."""
+
+    def __init__(self, batch, total_points, c_in, proj_h, proj_w, device):
+        f32, i32 = torch.float32, torch.int32
+        self.batch, self.total, self.c_in, self.H, self.W = batch, total_points, c_in, proj_h, proj_w
+        self.proj_pointcloud = torch.empty((batch, proj_h, proj_w, c_in), dtype=f32, device=device)
+        self.proj_range = torch.empty((batch, proj_h, proj_w), dtype=f32, device=device)
+        self.proj_idx = torch.empty((batch, proj_h, proj_w), dtype=i32, device=device)
+        self.proj_mask = torch.empty((batch, proj_h, proj_w), dtype=i32, device=device)
+        self.uproj_x_idx = torch.empty((total_points,), dtype=i32, device=device)
+        self.uproj_y_idx = torch.empty((total_points,), dtype=i32, device=device)
+        self.uproj_depth = torch.empty((total_points,), dtype=f32, device=device)
+        self.flags = torch.zeros((1,), dtype=i32, device=device)
+        nbytes = lib.c3d_project_workspace_bytes(batch, proj_h, proj_w)
+        self.workspace = torch.empty((nbytes,), dtype=torch.uint8, device=device)
+
+
+def project_batch(points, offsets, fov: Fov, proj_h, proj_w, depth=None,
+                  buffers: ProjectionBuffers = None) -> Projection:
+    """RangeProjection.doProjection for a CSR batch (projection.py:43-115).
+
+    points (sum N, C>=3) f32, offsets (B+1,) i32, optional depth (sum N,) f32;
+    all CUDA.  proj_idx holds indices local to each scan.
+    """
+    _need_cuda(points=points, offsets=offsets, depth=depth)
+    if points.dtype != torch.float32 or points.dim() != 2:
+        raise ValueError("points must be (N, C) float32")
+    if offsets.dtype != torch.int32:
+        raise ValueError("offsets must be int32")
+    if depth is not None and (depth.dtype != torch.float32 or depth.numel() != points.shape[0]):
+        raise ValueError("depth must be (N,) float32")
+    batch = offsets.numel() - 1
+    total, c_in = points.shape
+    b = buffers
+    if b is None:
+        b = ProjectionBuffers(batch, total, c_in, proj_h, proj_w, points.device)
+    elif (b.batch, b.total, b.c_in, b.H, b.W) != (batch, total, c_in, proj_h, proj_w):
+        raise ValueError("ProjectionBuffers shape mismatch")
+    check(lib.c3d_project_batch(
+        _p(points), c_in, _p(offsets), batch, total, _p(depth),
+        fov.abs_fov_left, fov.fov_hori, fov.abs_fov_down, fov.fov_vert, proj_h, proj_w,
+        _p(b.proj_range), _p(b.proj_pointcloud), _p(b.proj_idx), _p(b.proj_mask),
+        _p(b.uproj_x_idx), _p(b.uproj_y_idx), _p(b.uproj_depth), _p(b.workspace), _p(b.flags),
+        _stream()))
+    return Projection(b.proj_pointcloud, b.proj_range, b.proj_idx, b.proj_mask,
+                      b.uproj_x_idx, b.uproj_y_idx, b.uproj_depth, b.flags)
+
+
+# --------------------------------------------------------------------- a4 --
+def gaussian_kernel(kernel_size=3, sigma=2):
+    """get_gaussian_kernel (knn.py:11-33): same torch ops, CPU, float32."""
+    x_coord = torch.arange(kernel_size)
+    x_grid = x_coord.repeat(kernel_size).view(kernel_size, kernel_size)
+    y_grid = x_grid.t()
+    xy_grid = torch.stack([x_grid, y_grid], dim=-1).float()
+    mean = (kernel_size - 1) / 2.
+    variance = sigma ** 2.
+    g = (1. / (2. * math.pi * variance)) * \
+        torch.exp(-torch.sum((xy_grid - mean) ** 2., dim=-1) / (2 * variance))
+    g = g / torch.sum(g)
+    return g.view(kernel_size, kernel_size)
+
+
+def knn_batch(proj_range, proj_argmax, unproj_range, px, py, offsets, knn, search, sigma,
+              cutoff, nclasses, inv_gauss=None, out=None):
+    """KNN.forward for a CSR batch (knn.py:54-142).
+
+    proj_range (B,H,W) f32; proj_argmax (B,H,W), px, py (sum N,) all int64 (the
+    reference's dtypes) or all int32; offsets (B+1,) i32.  Returns (sum N,)
+    labels of the index dtype.
+    """
+    if search % 2 == 0:
+        raise ValueError("Nearest neighbor kernel must be odd number")  # knn.py:72-73
+    _need_cuda(proj_range=proj_range, proj_argmax=proj_argmax, unproj_range=unproj_range,
+               px=px, py=py, offsets=offsets)
+    idt = px.dtype
+    if idt not in (torch.int64, torch.int32) or py.dtype != idt or proj_argmax.dtype != idt:
+        raise ValueError("px, py, proj_argmax must share dtype int64 or int32")
+    if proj_range.dtype != torch.float32 or unproj_range.dtype != torch.float32:
+        raise ValueError("ranges must be float32")
+    if proj_range.dim() != 3 or proj_argmax.shape != proj_range.shape:
+        raise ValueError("proj_range / proj_argmax must be (B,H,W)")
+    B, H, W = proj_range.shape
+    if offsets.numel() != B + 1 or offsets.dtype != torch.int32:
+        raise ValueError("offsets must be (B+1,) int32")
+    total = unproj_range.numel()
+    if inv_gauss is None:
+        inv_gauss = (1 - gaussian_kernel(search, sigma)).reshape(-1).to(proj_range.device)
+    if out is None:
+        out = torch.empty((total,), dtype=idt, device=proj_range.device)
+    check(lib.c3d_knn_batch(
+        _p(proj_range), _p(proj_argmax), _p(unproj_range), _p(px), _p(py), _p(offsets), B, total,
+        H, W, int(knn), int(search), float(cutoff), int(nclasses), _p(inv_gauss),
+        1 if idt == torch.int64 else 0, _p(out), _stream()))
+    return out
+
+
+def launch_count():
+    """Kernel launches enqueued by the library since load."""
+    return _lib.launch_count()

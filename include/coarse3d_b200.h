@@ -1,0 +1,102 @@
+/*
+ * coarse3d_b200 -- C ABI of the B200-native COARSE3D per-scan hot path.
+ *
+ * The reference (astra-vision/COARSE3D) is pure Python: it has no FFI layer.
+ * The boundary it offers is the `pc_processor` operator surface; each entry
+ * point below is what a binding for one of those operators calls, and cites
+ * the reference code it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - every pointer is a caller-owned DEVICE pointer unless marked "host";
+ *   - no hidden allocation: scratch is passed in, sized by *_workspace_bytes;
+ *   - `stream` is a cudaStream_t (CUstream) passed as void*; all work is
+ *     enqueued on it and nothing synchronises;
+ *   - every function returns a c3d_status; on failure c3d_last_error() gives a
+ *     thread-local message; nothing throws across the ABI;
+ *   - a scan batch is CSR: `offsets[b] .. offsets[b+1]` are scan b's points.
+ */
+#ifndef COARSE3D_B200_H_
+#define COARSE3D_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  C3D_OK = 0,
+  C3D_INVALID_ARGUMENT = 1,
+  C3D_CUDA_ERROR = 2,
+  C3D_UNSUPPORTED = 3
+} c3d_status;
+
+/* ABI version (major*100 + minor). */
+int c3d_version(void);
+/* Message of the last failure on this thread ("" if none). */
+const char* c3d_last_error(void);
+/* Number of kernel launches enqueued by this library since load (all threads). */
+long long c3d_launch_count(void);
+
+/* ---------------------------------------------------------------- a1 ----
+ * RangeProjection.doProjection, pc_processor/dataset/preprocess/projection.py:43-115,
+ * for a CSR batch of scans.
+ *
+ * fov arguments are the Python floats RangeProjection.__init__ stores
+ * (projection.py:29-35): abs(fov_left), fov_hori, abs(fov_down), fov_vert in
+ * radians; they are rounded to float32 exactly where numpy does.
+ * z-buffer rule: minimum depth, then minimum point index (projection.py:94 is
+ * an unstable sort, so ties are otherwise undefined).
+ * status_flags[0] bit 0 is set when a pixel coordinate is NaN (depth == 0), the
+ * case in which the reference crashes.
+ */
+size_t c3d_project_workspace_bytes(int batch, int proj_h, int proj_w);
+
+int c3d_project_batch(
+    const float* points,          /* [total_points, c_in] x,y,z,(intensity,...)  */
+    int c_in,                     /* >= 3; 4 is the fast path                    */
+    const int32_t* offsets,       /* [batch+1]                                   */
+    int batch,
+    int64_t total_points,
+    const float* depth_override,  /* [total_points] or NULL (projection.py:46)   */
+    double abs_fov_left, double fov_hori, double abs_fov_down, double fov_vert,
+    int proj_h, int proj_w,
+    float* proj_range,            /* [batch, H, W]        -1 where empty         */
+    float* proj_pointcloud,       /* [batch, H, W, c_in]  -1 where empty         */
+    int32_t* proj_idx,            /* [batch, H, W]        -1 where empty         */
+    int32_t* proj_mask,           /* [batch, H, W]        proj_idx > 0 (:113)    */
+    int32_t* uproj_x_idx,         /* [total_points]  cached_data (:87-89)        */
+    int32_t* uproj_y_idx,         /* [total_points]                              */
+    float* uproj_depth,           /* [total_points]                              */
+    void* workspace,              /* c3d_project_workspace_bytes                 */
+    int32_t* status_flags,        /* [1], caller-zeroed                          */
+    void* stream);
+
+/* ---------------------------------------------------------------- a4 ----
+ * KNN.forward, pc_processor/postproc/knn.py:54-142, for a CSR batch of scans.
+ *
+ * inv_gauss is (1 - get_gaussian_kernel(search, sigma)) flattened row-major
+ * (knn.py:11-33,102-104), computed by the host with the reference's formula.
+ * Tie rule: k smallest by (distance, window slot); vote argmax = first maximum.
+ * index_is_i64 selects the dtype of px / py / proj_argmax / out
+ * (int64 = the reference's dtypes, int32 = this library's projection outputs).
+ */
+int c3d_knn_batch(
+    const float* proj_range,      /* [batch, H, W]                               */
+    const void* proj_argmax,      /* [batch, H, W] i64 or i32                    */
+    const float* unproj_range,    /* [total_points]                              */
+    const void* px, const void* py, /* [total_points] i64 or i32                 */
+    const int32_t* offsets,       /* [batch+1]                                   */
+    int batch, int64_t total_points,
+    int proj_h, int proj_w,
+    int knn, int search, float cutoff, int nclasses,
+    const float* inv_gauss,       /* [search*search]                             */
+    int index_is_i64,
+    void* out_labels,             /* [total_points] i64 or i32, in [1, C-1]      */
+    void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COARSE3D_B200_H_ */

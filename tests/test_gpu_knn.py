@@ -1,0 +1,96 @@
+"""GPU parity: c3d_knn_batch against the CPU oracle and the reference golden vectors."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import knn as oknn
+from oracle import projection as oproj
+
+pytestmark = pytest.mark.gpu
+
+KNN = load_golden("knn")
+
+
+@pytest.mark.parametrize("case", sorted(KNN))
+def test_dropin_matches_golden(cuda_device, case):
+    from coarse3d_b200.pc_processor.postproc import KNN as KNNModule
+    g = KNN[case]
+    params = dict(knn=int(g["knn"]), search=int(g["search"]), sigma=float(g["sigma"]),
+                  cutoff=float(g["cutoff"]))
+    mod = KNNModule(params, int(g["nclasses"]))
+    out = mod(torch.from_numpy(g["proj_range"]).cuda(), torch.from_numpy(g["unproj_range"]).cuda(),
+              torch.from_numpy(g["proj_argmax"]).cuda(), torch.from_numpy(g["px"]).cuda(),
+              torch.from_numpy(g["py"]).cuda())
+    assert out.dtype == torch.int64 and out.is_cuda
+    assert np.array_equal(out.cpu().numpy(), g["out"])
+
+
+def test_even_window_raises(cuda_device):
+    from coarse3d_b200.pc_processor.postproc import KNN as KNNModule
+    mod = KNNModule(dict(knn=3, search=4, sigma=1.0, cutoff=1.0), 5)
+    z = torch.zeros((4, 4), device="cuda")
+    with pytest.raises(ValueError):
+        mod(z, torch.zeros(1, device="cuda"), z.long(), torch.zeros(1, device="cuda").long(),
+            torch.zeros(1, device="cuda").long())
+
+
+def _make_batch(shape_name, batch, seed0, quantize=None):
+    from coarse3d_b200 import synth
+    shp = synth.SHAPES[shape_name]
+    pts, offs, _, _ = synth.make_batch(shp, batch, seed0=seed0, ragged=True)
+    fov = oproj.Fov(fov_up=shp.fov_up, fov_down=shp.fov_down, proj_h=shp.proj_h, proj_w=shp.proj_w)
+    rng = np.random.default_rng(seed0)
+    per = []
+    for b in range(batch):
+        p = pts[offs[b]:offs[b + 1]]
+        d = None
+        if quantize:  # coarse depths => many exactly equal distances (tie rule)
+            d = (np.round(oproj.depth_of(p) / quantize) * quantize + quantize).astype(np.float32)
+        o = oproj.project(p, fov, d)
+        argmax = rng.integers(0, shp.n_classes, (shp.proj_h, shp.proj_w))
+        per.append((o, argmax))
+    return shp, offs, per
+
+
+@pytest.mark.parametrize("idt", [torch.int64, torch.int32])
+@pytest.mark.parametrize("shape_name,batch,k,s,sigma,cutoff,quant", [
+    ("kitti", 2, 5, 5, 1.0, 1.0, None),
+    ("poss", 3, 5, 5, 1.0, 1.0, None),     # BASELINE config 4: 40x1800, 5x5
+    ("nuscenes", 4, 3, 3, 2.0, 0.0, None),  # cutoff disabled: inf slots vote
+    ("nuscenes", 2, 7, 7, 1.5, 2.0, 0.5),  # quantised depths: distance ties
+    ("kitti", 1, 9, 5, 1.0, 0.7, 0.25),
+])
+def test_batched_matches_oracle(cuda_device, shape_name, batch, k, s, sigma, cutoff, quant, idt):
+    from coarse3d_b200 import ops
+    shp, offs, per = _make_batch(shape_name, batch, 300, quant)
+    cat = lambda key, dt: torch.from_numpy(np.concatenate([o[key] for o, _ in per]).astype(dt)).cuda()
+    npdt = np.int64 if idt == torch.int64 else np.int32
+    proj_range = torch.from_numpy(np.stack([o["proj_range"] for o, _ in per])).cuda()
+    proj_argmax = torch.from_numpy(np.stack([a for _, a in per]).astype(npdt)).cuda()
+    out = ops.knn_batch(proj_range, proj_argmax, cat("uproj_depth", np.float32),
+                        cat("uproj_x_idx", npdt), cat("uproj_y_idx", npdt),
+                        torch.from_numpy(offs).cuda(), k, s, sigma, cutoff, shp.n_classes)
+    assert out.dtype == idt
+    out = out.cpu().numpy()
+    for b, (o, argmax) in enumerate(per):
+        want = oknn.knn_vote(o["proj_range"], o["uproj_depth"], argmax, o["uproj_x_idx"],
+                             o["uproj_y_idx"], k, s, sigma, cutoff, shp.n_classes)
+        got = out[offs[b]:offs[b + 1]]
+        assert np.array_equal(got, want), (b, int((got != want).sum()))
+        assert got.min() >= 1 and got.max() <= shp.n_classes - 1
+
+
+def test_uniform_labels_are_a_fixed_point(cuda_device):
+    """Size-independent property at full KITTI size: if every pixel predicts class c,
+    every point is labelled c (the centre slot always votes with distance 0)."""
+    from coarse3d_b200 import ops, synth
+    shp = synth.KITTI
+    pts, offs, _, _ = synth.make_batch(shp, 4, seed0=2000)
+    P, O = torch.from_numpy(pts).cuda(), torch.from_numpy(offs).cuda()
+    pr = ops.project_batch(P, O, ops.Fov.from_degrees(shp.fov_up, shp.fov_down), shp.proj_h, shp.proj_w)
+    for c in (1, 7, shp.n_classes - 1):
+        am = torch.full(pr.proj_idx.shape, c, dtype=torch.int32, device="cuda")
+        out = ops.knn_batch(pr.proj_range, am, pr.uproj_depth, pr.uproj_x_idx, pr.uproj_y_idx, O,
+                            5, 5, 1.0, 1.0, shp.n_classes)
+        assert (out == c).all()

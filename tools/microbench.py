@@ -1,0 +1,74 @@
+#!/usr/bin/env python
+"""Developer micro-benchmark: per-op device time and algorithmic GB/s (CUDA events).
+Not the contract benchmark (that is bench.py); used while tuning kernels."""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from coarse3d_b200 import ops, synth  # noqa: E402
+
+
+def timeit(fn, iters=20, warmup=5, flush=None):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        if flush is not None:
+            flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        fn()
+        e.record()
+        torch.cuda.synchronize()
+        ts.append(s.elapsed_time(e))
+    return float(np.median(ts)), float(np.min(ts))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=8)
+    ap.add_argument("--shape", default="kitti")
+    ap.add_argument("--ops", default="project,knn")
+    args = ap.parse_args()
+    shp = synth.SHAPES[args.shape]
+    B = args.batch
+    one, offs1, _, _ = synth.make_batch(shp, min(B, 8), seed0=1000)
+    reps = (B + 7) // 8
+    pts = np.concatenate([one] * reps, 0)
+    sizes = np.tile(np.diff(offs1), reps)[:B]
+    pts = pts[:sizes.sum()]
+    offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    P, O = torch.from_numpy(pts).cuda(), torch.from_numpy(offs).cuda()
+    N, HW = pts.shape[0], shp.proj_h * shp.proj_w
+    fov = ops.Fov.from_degrees(shp.fov_up, shp.fov_down)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    res = {}
+    bufs = ops.ProjectionBuffers(B, N, 4, shp.proj_h, shp.proj_w, "cuda")
+    if "project" in args.ops:
+        for mode in ("0", "1"):
+            os.environ["C3D_PROJECT_F64_ONLY"] = mode
+            med, mn = timeit(lambda: ops.project_batch(P, O, fov, shp.proj_h, shp.proj_w, buffers=bufs), flush=flush)
+            by = 28 * N + 28 * B * HW
+            res["project_f64only=" + mode] = dict(ms=med, ms_min=mn, GBs=by / med / 1e6, scans_s=B / med * 1e3)
+        os.environ["C3D_PROJECT_F64_ONLY"] = "0"
+    pr = ops.project_batch(P, O, fov, shp.proj_h, shp.proj_w, buffers=bufs)
+    if "knn" in args.ops:
+        for idt, name in ((torch.int64, "i64"), (torch.int32, "i32")):
+            am = torch.randint(0, shp.n_classes, pr.proj_idx.shape, device="cuda").to(idt)
+            px, py = pr.uproj_x_idx.to(idt), pr.uproj_y_idx.to(idt)
+            out = torch.empty(N, dtype=idt, device="cuda")
+            med, mn = timeit(lambda: ops.knn_batch(pr.proj_range, am, pr.uproj_depth, px, py, O, 5, 5, 1.0, 1.0,
+                                                   shp.n_classes, out=out), flush=flush)
+            by = 12 * B * HW + 28 * N
+            res["knn_" + name] = dict(ms=med, ms_min=mn, GBs_ref_dtypes=by / med / 1e6, scans_s=B / med * 1e3)
+    print(json.dumps(dict(batch=B, shape=args.shape, results=res), indent=1))
+
+
+if __name__ == "__main__":
+    main()
