@@ -5,7 +5,7 @@ operator raises -- there is no CPU or PyTorch fallback.
 """
 import ctypes
 import os
-from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_longlong, c_size_t, c_void_p
+from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_longlong, c_size_t, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcoarse3d_b200.so")
@@ -33,6 +33,13 @@ def _load():
                                       c_double, c_int, c_int, P, P, P, P, P, P, P, P, P, P]),
         "c3d_knn_batch": (c_int, [P, P, P, P, P, P, c_int, c_int64, c_int, c_int, c_int, c_int,
                                   c_float, c_int, P, c_int, P, P]),
+        "c3d_proto_loss_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
+        "c3d_proto_loss_forward": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int,
+                                           c_int, c_float, c_float, c_int, P, c_int, c_uint64, P, P, P]),
+        "c3d_proto_loss_backward": (c_int, [P, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
+                                            c_float, c_int, P, P, P, P]),
+        "c3d_proto_loss_info": (c_int, [P, P, P]),
+        "c3d_proto_loss_rows": (c_int, [P, c_int, c_int, c_int, c_int, c_int, c_int64, P, P, P, P]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported

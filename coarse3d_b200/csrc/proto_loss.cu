@@ -1,0 +1,704 @@
+// a2 -- class-prototype contrastive loss (ContrastMEMLoss), forward + backward.
+//
+// Replaces reference pc_processor/loss/contrast_pixel_loss.py:27-195 and its
+// autograd.  What the reference does with a full NCHW->NHWC copy, a B x C Python
+// loop of unique / multinomial / gather launches, a 380 x D GEMM over A*T
+// duplicated rows and an index_put backward is restated as:
+//
+//   K1 loss_count    labels + keep_mask (9 B/px, coalesced) -> per-tile per-class counts
+//   K2 loss_scan     per-scan prefix over tiles; last CTA builds the (scan, class)
+//                    segment table in the reference's X_ptr order (b asc, class asc)
+//   K3 loss_scatter  stable multi-split: labelled pixels -> slots sorted by
+//                    (scan, class, pixel); entropy weight exp(-H^2) per slot
+//                    (:46-49); extra CTAs L2-normalise the bank rows (:167)
+//   K4 loss_sample   one CTA per segment: CDF, A draws with replacement
+//                    (Philox) or the injected `keep` indices -> multiplicity per slot
+//   K5 loss_rows     one warp per labelled slot with multiplicity > 0: strided NCHW
+//                    gather, L2 normalise, similarity against the bank staged in
+//                    shared memory, temperature, max-shift, masked sums (:166-193);
+//                    rows are weighted by multiplicity instead of being duplicated
+//   K6 fill_zero     dense (B,D,H,W) gradient zero-fill, 128-bit streaming stores
+//   K7 loss_rows<bwd> recompute logits, closed-form gradient, scatter D values/slot
+//
+// All reductions are order-deterministic (no float atomics).
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace c3d {
+
+constexpr int kTile = 1024;        // pixels per count/scatter CTA (4 rounds x 256 threads)
+constexpr int kMaxClasses = 64;
+constexpr int kRowWarps = 8;       // rows processed concurrently per loss_rows CTA
+
+enum LossFlag { kFlagNoAnchor = 1, kFlagBadKeep = 2, kFlagKeepRows = 4, kFlagBadLabel = 8 };
+enum LossInfo { kInfoT = 0, kInfoPl = 1, kInfoFlags = 2, kInfoDone = 3, kInfoDone2 = 4 };
+
+struct LossWs {
+  int32_t* info;       // [8]
+  int32_t* blk_cnt;    // [nblk * C] counts, then exclusive prefix inside (scan, class)
+  int32_t* seg_cnt;    // [B * C]
+  int32_t* seg_start;  // [B * C]
+  int32_t* seg_tidx;   // [B * C] index among non-empty segments, or -1
+  int32_t* pix_list;   // [cap] b*HW + pixel
+  int32_t* cls_list;   // [cap]
+  float* w_list;       // [cap] weights, then in-place CDF
+  int32_t* cnt_list;   // [cap] sampling multiplicity
+  float* loss_part;    // [cap]
+  float* bank_n;       // [(C-1)*M*D] normalised prototypes, classes 1..C-1
+  size_t bytes;
+};
+
+static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static LossWs carve(void* base, int B, int C, int HW, int D, int M) {
+  LossWs w;
+  const size_t cap = (size_t)B * HW;
+  const size_t nblk = (size_t)B * ((HW + kTile - 1) / kTile);
+  size_t off = 0;
+  auto take = [&](size_t n) { size_t o = off; off += align_up(n); return (char*)base + o; };
+  w.info = (int32_t*)take(8 * 4);
+  w.blk_cnt = (int32_t*)take(nblk * C * 4);
+  w.seg_cnt = (int32_t*)take((size_t)B * C * 4);
+  w.seg_start = (int32_t*)take((size_t)B * C * 4);
+  w.seg_tidx = (int32_t*)take((size_t)B * C * 4);
+  w.pix_list = (int32_t*)take(cap * 4);
+  w.cls_list = (int32_t*)take(cap * 4);
+  w.w_list = (float*)take(cap * 4);
+  w.cnt_list = (int32_t*)take(cap * 4);
+  w.loss_part = (float*)take(cap * 4);
+  w.bank_n = (float*)take((size_t)(C - 1) * M * D * 4);
+  w.bytes = off;
+  return w;
+}
+
+// ---------------------------------------------------------------- K1 -------
+__device__ __forceinline__ int masked_class(const long long* __restrict__ labels,
+                                            const uint8_t* __restrict__ keep, size_t i,
+                                            int ignore_label) {
+  long long l = labels[i];
+  if (keep && keep[i] == 0) l = ignore_label;  // contrast_pixel_loss.py:36-38
+  return (int)l;
+}
+
+__global__ void __launch_bounds__(256)
+loss_count_kernel(const long long* __restrict__ labels, const uint8_t* __restrict__ keep, int HW,
+                  int nbps, int C, int ignore_label, int32_t* __restrict__ blk_cnt,
+                  int32_t* __restrict__ info) {
+  __shared__ int s_cnt[kMaxClasses];
+  if (threadIdx.x < C) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const int b = blockIdx.x / nbps, tile = blockIdx.x % nbps;
+  bool bad = false;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int pix = tile * kTile + r * 256 + threadIdx.x;
+    if (pix < HW) {
+      const int c = masked_class(labels, keep, (size_t)b * HW + pix, ignore_label);
+      if (c != ignore_label) {
+        if (c < 0 || c >= C) bad = true; else atomicAdd(&s_cnt[c], 1);
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < C) blk_cnt[(size_t)blockIdx.x * C + threadIdx.x] = s_cnt[threadIdx.x];
+  if (bad) atomicOr(&info[kInfoFlags], kFlagBadLabel);
+}
+
+// ---------------------------------------------------------------- K2 -------
+// CTA b: warp per class, exclusive prefix of the tile counts of scan b.  The
+// last CTA to finish turns the B*C totals into the segment table.
+__global__ void __launch_bounds__(1024)
+loss_scan_kernel(int32_t* __restrict__ blk_cnt, int nbps, int B, int C,
+                 int32_t* __restrict__ seg_cnt, int32_t* __restrict__ seg_start,
+                 int32_t* __restrict__ seg_tidx, int32_t* __restrict__ info) {
+  const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nwarps = blockDim.x >> 5;
+  for (int c = warp; c < C; c += nwarps) {
+    int carry = 0;
+    for (int base = 0; base < nbps; base += 32) {
+      const int i = base + lane;
+      int32_t* p = blk_cnt + ((size_t)(b * nbps + i)) * C + c;
+      const int v = (i < nbps) ? *p : 0;
+      int incl = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      if (i < nbps) *p = carry + incl - v;
+      carry += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) seg_cnt[b * C + c] = carry;
+  }
+  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(&info[kInfoDone], 1) == B - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (warp == 0) {
+    int carry = 0, tcarry = 0;
+    const int n = B * C;
+    for (int base = 0; base < n; base += 32) {
+      const int i = base + lane;
+      const int v = (i < n) ? __ldcg(seg_cnt + i) : 0;
+      const int ne = v > 0;
+      int incl = v, tincl = ne;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, incl, o);
+        int u = __shfl_up_sync(0xffffffffu, tincl, o);
+        if (lane >= o) { incl += t; tincl += u; }
+      }
+      if (i < n) {
+        seg_start[i] = carry + incl - v;
+        seg_tidx[i] = ne ? (tcarry + tincl - 1) : -1;
+      }
+      carry += __shfl_sync(0xffffffffu, incl, 31);
+      tcarry += __shfl_sync(0xffffffffu, tincl, 31);
+    }
+    if (lane == 0) {
+      info[kInfoT] = tcarry;
+      info[kInfoPl] = carry;
+      if (tcarry == 0) atomicOr(&info[kInfoFlags], kFlagNoAnchor);
+      info[kInfoDone] = 0;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- K3 -------
+__global__ void __launch_bounds__(256)
+loss_scatter_kernel(const long long* __restrict__ labels, const uint8_t* __restrict__ keep,
+                    const float* __restrict__ probs, int HW, int nbps, int nblk, int C,
+                    int ignore_label, const int32_t* __restrict__ blk_prefix,
+                    const int32_t* __restrict__ seg_start, int32_t* __restrict__ pix_list,
+                    int32_t* __restrict__ cls_list, float* __restrict__ w_list,
+                    int32_t* __restrict__ cnt_list, const float* __restrict__ queue, int M, int D,
+                    float* __restrict__ bank_n) {
+  if ((int)blockIdx.x >= nblk) {
+    // bank rows: F.normalize(contrast_feature) (:167); classes 1..C-1 (:139-140)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rows = (C - 1) * M;
+    for (int k = (blockIdx.x - nblk) * 8 + warp; k < rows; k += (gridDim.x - nblk) * 8) {
+      const float* src = queue + (size_t)(k + M) * D;  // skip class 0
+      float s = 0.f;
+      for (int d = lane; d < D; d += 32) { float v = src[d]; s += v * v; }
+      s = warp_sum(s);
+      const float inv = 1.0f / fmaxf(sqrtf(s), 1e-12f);
+      for (int d = lane; d < D; d += 32) bank_n[(size_t)k * D + d] = src[d] * inv;
+    }
+    return;
+  }
+  __shared__ int s_cnt[4][8][kMaxClasses];  // [round][warp][class] -> exclusive prefix
+  const int b = blockIdx.x / nbps, tile = blockIdx.x % nbps;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 4 * 8 * kMaxClasses; i += 256) (&s_cnt[0][0][0])[i] = 0;
+  __syncthreads();
+  int cls[4], rank[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int pix = tile * kTile + r * 256 + threadIdx.x;
+    int c = -1;
+    if (pix < HW) {
+      c = masked_class(labels, keep, (size_t)b * HW + pix, ignore_label);
+      if (c == ignore_label || c < 0 || c >= C) c = -1;
+    }
+    const unsigned peers = __match_any_sync(0xffffffffu, c);
+    rank[r] = __popc(peers & ((1u << lane) - 1));
+    cls[r] = c;
+    if (c >= 0 && rank[r] == 0) s_cnt[r][warp][c] = __popc(peers);
+  }
+  __syncthreads();
+  if (threadIdx.x < C) {  // exclusive prefix over (round, warp) for class threadIdx.x
+    int run = 0;
+    for (int i = 0; i < 32; ++i) {
+      int* p = &s_cnt[i >> 3][i & 7][threadIdx.x];
+      const int v = *p; *p = run; run += v;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int c = cls[r];
+    if (c < 0) continue;
+    const int pix = tile * kTile + r * 256 + threadIdx.x;
+    const int slot = seg_start[b * C + c] + blk_prefix[(size_t)blockIdx.x * C + c] +
+                     s_cnt[r][warp][c] + rank[r];
+    // entropy weight (contrast_pixel_loss.py:46-49)
+    const float* p = probs + (size_t)b * C * HW + pix;
+    float ent = 0.f;
+    for (int k = 0; k < C; ++k) {
+      const float v = __ldg(p + (size_t)k * HW);
+      ent += v * logf(v + 1e-10f);
+    }
+    ent = -ent;
+    pix_list[slot] = b * HW + pix;
+    cls_list[slot] = c;
+    w_list[slot] = expf(-(ent * ent));
+    cnt_list[slot] = 0;
+  }
+}
+
+// ---------------------------------------------------------------- K4 -------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += 0x9E3779B9u; key.y += 0xBB67AE85u;
+  }
+  return ctr;
+}
+
+__global__ void __launch_bounds__(256)
+loss_sample_kernel(const int32_t* __restrict__ seg_cnt, const int32_t* __restrict__ seg_start,
+                   const int32_t* __restrict__ seg_tidx, const int32_t* __restrict__ pix_list,
+                   float* __restrict__ w_list, int32_t* __restrict__ cnt_list, int HW, int C, int A,
+                   const long long* __restrict__ keep, int keep_rows, unsigned long long seed,
+                   int32_t* __restrict__ info) {
+  const int seg = blockIdx.x;
+  const int n = seg_cnt[seg];
+  if (keep && seg == 0 && threadIdx.x == 0 && info[kInfoT] != keep_rows)
+    atomicOr(&info[kInfoFlags], kFlagKeepRows);
+  if (n == 0) return;
+  const int start = seg_start[seg], t = seg_tidx[seg], b = seg / C;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (keep) {
+    if (t >= keep_rows) return;
+    bool bad = false;
+    for (int a = threadIdx.x; a < A; a += 256) {
+      const long long pix = keep[(size_t)t * A + a];
+      const long long key = (long long)b * HW + pix;
+      int lo = 0, hi = n;  // first slot with pix_list >= key
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (pix_list[start + mid] < key) lo = mid + 1; else hi = mid;
+      }
+      if (pix < 0 || pix >= HW || lo >= n || pix_list[start + lo] != key) bad = true;
+      else atomicAdd(&cnt_list[start + lo], 1);
+    }
+    if (bad) atomicOr(&info[kInfoFlags], kFlagBadKeep);
+    return;
+  }
+  // inclusive scan of the weights -> CDF (in place), 256 elements per step
+  __shared__ float s_warp[8];
+  __shared__ float s_carry;
+  if (threadIdx.x == 0) s_carry = 0.f;
+  __syncthreads();
+  for (int base = 0; base < n; base += 256) {
+    const int i = base + threadIdx.x;
+    float v = (i < n) ? w_list[start + i] : 0.f;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      float u = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += u;
+    }
+    if (lane == 31) s_warp[warp] = v;
+    __syncthreads();
+    float pre = s_carry;
+    for (int w = 0; w < warp; ++w) pre += s_warp[w];
+    if (i < n) w_list[start + i] = pre + v;
+    __syncthreads();
+    if (threadIdx.x == 255) s_carry = pre + v;
+    __syncthreads();
+  }
+  const float total = s_carry;
+  for (int a = threadIdx.x; a < A; a += 256) {
+    const unsigned long long ctr = (unsigned long long)t * A + a;
+    const uint4 r = philox4x32_10(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u),
+                                  make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    const float x = (float)(r.x >> 8) * (1.0f / 16777216.0f) * total;
+    int lo = 0, hi = n - 1;  // first slot with cdf > x (clamped)
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (w_list[start + mid] > x) hi = mid; else lo = mid + 1;
+    }
+    atomicAdd(&cnt_list[start + lo], 1);
+  }
+}
+
+// ---------------------------------------------------------------- K5 / K7 --
+struct RowsParams {
+  const float* feats;      // (B, D, HW)
+  const float* bank_n;     // (Kc, D)
+  const int32_t* pix_list;
+  const int32_t* cls_list;
+  const int32_t* cnt_list;
+  int32_t* info;
+  float* loss_part;        // fwd: [cap]
+  float* loss_out;         // fwd: [1]
+  const float* grad_out;   // bwd: [1]
+  float* grad_feats;       // bwd: (B, D, HW)
+  int HW, D, M, Kc, A, tile_rows, n_tiles;
+  float temperature, base_temperature;
+};
+
+template <bool kBackward>
+__global__ void __launch_bounds__(kRowWarps * 32, 1)
+loss_rows_kernel(RowsParams p) {
+  extern __shared__ __align__(16) float smem[];
+  const int D = p.D, Kc = p.Kc, ld = D + 4;
+  const int KcPad = (Kc + 31) & ~31;
+  float* s_bank = smem;                                    // [tile_rows][D+4]
+  float* s_a = s_bank + (size_t)p.tile_rows * ld;          // [warps][D]
+  float* s_l = s_a + kRowWarps * D;                        // [warps][KcPad]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_slots = p.info[kInfoPl];
+  const int n_groups = (n_slots + kRowWarps - 1) / kRowWarps;
+  float* my_a = s_a + warp * D;
+  float* my_l = s_l + warp * KcPad;
+  const float scale_row = p.temperature / p.base_temperature;
+
+  auto load_tile = [&](int tile) {
+    const int r0 = tile * p.tile_rows;
+    const int rows = min(p.tile_rows, Kc - r0);
+    const int d4 = D >> 2;
+    for (int i = threadIdx.x; i < rows * d4; i += blockDim.x) {
+      const int r = i / d4, c = i - r * d4;
+      const float4 v = __ldg(reinterpret_cast<const float4*>(p.bank_n + (size_t)(r0 + r) * D) + c);
+      *reinterpret_cast<float4*>(s_bank + (size_t)r * ld + c * 4) = v;
+    }
+  };
+
+  if (p.n_tiles == 1 && (int)blockIdx.x < n_groups) { load_tile(0); }
+  __syncthreads();
+
+  for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+    const int slot = grp * kRowWarps + warp;
+    const int cnt = (slot < n_slots) ? p.cnt_list[slot] : 0;
+    const bool active = cnt > 0;
+    int gpix = 0, cls = 0;
+    float inv_norm = 0.f;
+    if (active) {
+      gpix = p.pix_list[slot];
+      cls = p.cls_list[slot];
+      const int b = gpix / p.HW, pix = gpix - b * p.HW;
+      const float* src = p.feats + (size_t)b * D * p.HW + pix;
+      float n2 = 0.f;
+      for (int d = lane; d < D; d += 32) {
+        const float v = __ldg(src + (size_t)d * p.HW);
+        my_a[d] = v;
+        n2 += v * v;
+      }
+      n2 = warp_sum(n2);
+      inv_norm = 1.0f / fmaxf(sqrtf(n2), 1e-12f);  // F.normalize eps (:166)
+      for (int d = lane; d < D; d += 32) my_a[d] *= inv_norm;
+    }
+    __syncwarp();
+
+    // ---- logits z_k = (a_hat . c_hat_k) / temperature  (:168-172)
+    for (int tile = 0; tile < p.n_tiles; ++tile) {
+      if (p.n_tiles > 1) { __syncthreads(); load_tile(tile); __syncthreads(); }
+      if (active) {
+        const int r0 = tile * p.tile_rows;
+        const int rows = min(p.tile_rows, Kc - r0);
+        for (int kk = lane; kk < rows; kk += 32) {
+          const float4* c4 = reinterpret_cast<const float4*>(s_bank + (size_t)kk * ld);
+          const float4* a4 = reinterpret_cast<const float4*>(my_a);
+          float acc = 0.f;
+#pragma unroll 8
+          for (int j = 0; j < (D >> 2); ++j) {
+            const float4 c = c4[j], a = a4[j];
+            acc += a.x * c.x; acc += a.y * c.y; acc += a.z * c.z; acc += a.w * c.w;
+          }
+          my_l[r0 + kk] = acc / p.temperature;
+        }
+      }
+    }
+    __syncwarp();
+
+    if (active) {
+      // ---- softmax statistics (:175-188)
+      float mx = -CUDART_INF_F;
+      for (int k = lane; k < Kc; k += 32) mx = fmaxf(mx, my_l[k]);
+      mx = warp_max(mx);
+      const int pos_lo = (cls - 1) * p.M, pos_hi = cls * p.M;  // bank rows of class `cls`
+      float neg = 0.f;
+      for (int k = lane; k < Kc; k += 32) {
+        const float e = expf(my_l[k] - mx);
+        if (k < pos_lo || k >= pos_hi) neg += e;
+      }
+      neg = warp_sum(neg);
+      if (!kBackward) {
+        float s = 0.f; int npos = 0;
+        for (int k = pos_lo + lane; k < pos_hi; k += 32) {
+          if (k >= 0 && k < Kc) {
+            const float l = my_l[k] - mx;
+            s += l - logf(expf(l) + neg + 1e-6f);
+            ++npos;
+          }
+        }
+        s = warp_sum(s);
+        npos = __reduce_add_sync(0xffffffffu, npos);
+        if (lane == 0)  // (:191-192), weighted by the row's multiplicity
+          p.loss_part[slot] = (float)cnt * (-scale_row * (s / (float)npos));
+      } else {
+        // ---- dL/dz_k
+        float inv_den = 0.f; int npos = 0;
+        for (int k = pos_lo + lane; k < pos_hi; k += 32) {
+          if (k >= 0 && k < Kc) {
+            inv_den += 1.0f / (expf(my_l[k] - mx) + neg + 1e-6f);
+            ++npos;
+          }
+        }
+        inv_den = warp_sum(inv_den);
+        npos = __reduce_add_sync(0xffffffffu, npos);
+        const float s = scale_row / (float)npos;
+        for (int k = lane; k < Kc; k += 32) {
+          const float e = expf(my_l[k] - mx);
+          float g;
+          if (k >= pos_lo && k < pos_hi) g = -s * (1.0f - e / (e + neg + 1e-6f));
+          else g = s * e * inv_den;
+          my_l[k] = g / p.temperature;  // dL/d(a_hat . c_hat_k)
+        }
+      }
+    }
+    __syncwarp();
+
+    if (kBackward) {
+      // ---- d a_hat = sum_k g_k c_hat_k ; lane owns 4-wide chunks of D
+      constexpr int kMaxChunks = 8;  // D <= 1024
+      float4 acc[kMaxChunks];
+#pragma unroll
+      for (int i = 0; i < kMaxChunks; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int d4 = D >> 2;
+      for (int tile = 0; tile < p.n_tiles; ++tile) {
+        if (p.n_tiles > 1) { __syncthreads(); load_tile(tile); __syncthreads(); }
+        if (active) {
+          const int r0 = tile * p.tile_rows;
+          const int rows = min(p.tile_rows, Kc - r0);
+          for (int kk = 0; kk < rows; ++kk) {
+            const float g = my_l[r0 + kk];
+            const float4* c4 = reinterpret_cast<const float4*>(s_bank + (size_t)kk * ld);
+#pragma unroll
+            for (int i = 0; i < kMaxChunks; ++i) {
+              const int ch = lane + 32 * i;
+              if (ch < d4) {
+                const float4 c = c4[ch];
+                acc[i].x += g * c.x; acc[i].y += g * c.y; acc[i].z += g * c.z; acc[i].w += g * c.w;
+              }
+            }
+          }
+        }
+      }
+      if (active) {
+        // normalize backward: da = (dhat - a_hat (a_hat . dhat)) / max(|a|, eps)
+        float dot = 0.f;
+#pragma unroll
+        for (int i = 0; i < kMaxChunks; ++i) {
+          const int ch = lane + 32 * i;
+          if (ch < d4) {
+            const float4 a = reinterpret_cast<const float4*>(my_a)[ch];
+            dot += a.x * acc[i].x + a.y * acc[i].y + a.z * acc[i].z + a.w * acc[i].w;
+          }
+        }
+        dot = warp_sum(dot);
+        const int T = p.info[kInfoT];
+        // mean over R = A*T rows (:193) times the upstream gradient
+        const float w = (float)cnt / ((float)p.A * (float)T) * __ldg(p.grad_out) * inv_norm;
+        const int b = gpix / p.HW, pix = gpix - b * p.HW;
+        float* dst = p.grad_feats + (size_t)b * D * p.HW + pix;
+        const bool clamped = inv_norm >= 1e12f;  // |a| < eps: y = x / eps, dy/dx = 1/eps
+#pragma unroll
+        for (int i = 0; i < kMaxChunks; ++i) {
+          const int ch = lane + 32 * i;
+          if (ch < d4) {
+            const float4 a = reinterpret_cast<const float4*>(my_a)[ch];
+            const float sub = clamped ? 0.f : dot;
+            dst[(size_t)(ch * 4 + 0) * p.HW] = (acc[i].x - a.x * sub) * w;
+            dst[(size_t)(ch * 4 + 1) * p.HW] = (acc[i].y - a.y * sub) * w;
+            dst[(size_t)(ch * 4 + 2) * p.HW] = (acc[i].z - a.z * sub) * w;
+            dst[(size_t)(ch * 4 + 3) * p.HW] = (acc[i].w - a.w * sub) * w;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+
+  if (!kBackward) {
+    // ---- deterministic final reduction by the last CTA: loss = sum / (A*T)
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&p.info[kInfoDone2], 1) == (int)gridDim.x - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    float s = 0.f;
+    for (int i = threadIdx.x; i < n_slots; i += blockDim.x)
+      if (__ldcg(p.cnt_list + i) > 0) s += __ldcg(p.loss_part + i);
+    s = warp_sum(s);
+    __shared__ float s_red[kRowWarps];
+    if (lane == 0) s_red[warp] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float tot = 0.f;
+      for (int w = 0; w < kRowWarps; ++w) tot += s_red[w];
+      const int T = p.info[kInfoT];
+      p.loss_out[0] = tot / ((float)p.A * (float)T);  // T == 0 -> NaN (reference crashes)
+      p.info[kInfoDone2] = 0;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- K6 -------
+__global__ void __launch_bounds__(512)
+fill_zero_kernel(float4* __restrict__ dst, size_t n4, float* __restrict__ tail, int ntail) {
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i + 3 * stride < n4; i += 4 * stride) {
+    __stcs(dst + i, z); __stcs(dst + i + stride, z);
+    __stcs(dst + i + 2 * stride, z); __stcs(dst + i + 3 * stride, z);
+  }
+  for (; i < n4; i += stride) __stcs(dst + i, z);
+  if (blockIdx.x == 0 && (int)threadIdx.x < ntail) tail[threadIdx.x] = 0.f;
+}
+
+static int rows_config(int D, int Kc, int* tile_rows, int* n_tiles, size_t* smem) {
+  const size_t budget = 227 * 1024;
+  const size_t fixed = ((size_t)kRowWarps * D + (size_t)kRowWarps * ((Kc + 31) & ~31)) * 4;
+  const size_t row = (size_t)(D + 4) * 4;
+  if (fixed + 32 * row > budget) return -1;
+  int tr = (int)((budget - fixed) / row);
+  if (tr >= Kc) tr = Kc; else tr &= ~31;
+  *tile_rows = tr;
+  *n_tiles = (Kc + tr - 1) / tr;
+  *smem = fixed + (size_t)tr * row;
+  return 0;
+}
+
+}  // namespace c3d
+
+using namespace c3d;
+
+extern "C" size_t c3d_proto_loss_workspace_bytes(int batch, int n_classes, int hw, int dim,
+                                                 int sub_protos) {
+  if (batch <= 0 || n_classes < 2 || hw <= 0 || dim <= 0 || sub_protos <= 0) return 0;
+  return carve(nullptr, batch, n_classes, hw, dim, sub_protos).bytes;
+}
+
+extern "C" int c3d_proto_loss_forward(
+    const float* feats, const float* probs, const int64_t* labels, const uint8_t* keep_mask,
+    const float* proto_queue, int batch, int dim, int proj_h, int proj_w, int n_classes,
+    int sub_protos, int ignore_label, float temperature, float base_temperature, int num_anchor,
+    const int64_t* keep, int keep_rows, uint64_t seed, void* workspace, float* loss_out,
+    void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int B = batch, D = dim, C = n_classes, M = sub_protos;
+  const long long HWll = (long long)proj_h * proj_w;
+  C3D_REQUIRE(B > 0 && B <= kMaxBatch, "batch must be in [1, %d]", kMaxBatch);
+  C3D_REQUIRE(C >= 2 && C <= kMaxClasses, "n_classes must be in [2, %d]", kMaxClasses);
+  C3D_REQUIRE(D > 0 && D % 4 == 0 && D <= 1024, "feature dim must be a multiple of 4, <= 1024");
+  C3D_REQUIRE(M > 0 && num_anchor > 0, "sub_protos and num_anchor must be positive");
+  C3D_REQUIRE(HWll > 0 && B * HWll < (1ll << 31), "batch*H*W must be < 2^31");
+  C3D_REQUIRE(feats && probs && labels && proto_queue && workspace && loss_out,
+              "null pointer argument");
+  C3D_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "workspace must be 256 B aligned");
+  C3D_REQUIRE(temperature > 0 && base_temperature > 0, "temperatures must be positive");
+  const int HW = (int)HWll;
+  LossWs w = carve(workspace, B, C, HW, D, M);
+  const int nbps = (HW + kTile - 1) / kTile, nblk = B * nbps;
+  const int Kc = (C - 1) * M;
+  int tile_rows, n_tiles; size_t smem;
+  C3D_REQUIRE(rows_config(D, Kc, &tile_rows, &n_tiles, &smem) == 0,
+              "bank does not fit shared memory tiling (D=%d, Kc=%d)", D, Kc);
+
+  C3D_CUDA(cudaMemsetAsync(w.info, 0, 8 * 4, stream));
+  loss_count_kernel<<<nblk, 256, 0, stream>>>((const long long*)labels, keep_mask, HW, nbps, C,
+                                              ignore_label, w.blk_cnt, w.info);
+  int rc = check_launch("loss_count_kernel");
+  if (rc) return rc;
+  loss_scan_kernel<<<B, 1024, 0, stream>>>(w.blk_cnt, nbps, B, C, w.seg_cnt, w.seg_start,
+                                           w.seg_tidx, w.info);
+  if ((rc = check_launch("loss_scan_kernel"))) return rc;
+  const int bank_blocks = 16;
+  loss_scatter_kernel<<<nblk + bank_blocks, 256, 0, stream>>>(
+      (const long long*)labels, keep_mask, probs, HW, nbps, nblk, C, ignore_label, w.blk_cnt,
+      w.seg_start, w.pix_list, w.cls_list, w.w_list, w.cnt_list, proto_queue, M, D, w.bank_n);
+  if ((rc = check_launch("loss_scatter_kernel"))) return rc;
+  loss_sample_kernel<<<B * C, 256, 0, stream>>>(w.seg_cnt, w.seg_start, w.seg_tidx, w.pix_list,
+                                                w.w_list, w.cnt_list, HW, C, num_anchor,
+                                                (const long long*)keep, keep_rows, seed, w.info);
+  if ((rc = check_launch("loss_sample_kernel"))) return rc;
+
+  RowsParams p{};
+  p.feats = feats; p.bank_n = w.bank_n; p.pix_list = w.pix_list; p.cls_list = w.cls_list;
+  p.cnt_list = w.cnt_list; p.info = w.info; p.loss_part = w.loss_part; p.loss_out = loss_out;
+  p.HW = HW; p.D = D; p.M = M; p.Kc = Kc; p.A = num_anchor; p.tile_rows = tile_rows;
+  p.n_tiles = n_tiles; p.temperature = temperature; p.base_temperature = base_temperature;
+  C3D_CUDA(cudaFuncSetAttribute(loss_rows_kernel<false>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  loss_rows_kernel<false><<<kNumSMs, kRowWarps * 32, smem, stream>>>(p);
+  return check_launch("loss_rows_kernel<fwd>");
+}
+
+extern "C" int c3d_proto_loss_backward(
+    const float* feats, int batch, int dim, int proj_h, int proj_w, int n_classes, int sub_protos,
+    float temperature, float base_temperature, int num_anchor, void* workspace,
+    const float* grad_out, float* grad_feats, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int B = batch, D = dim, C = n_classes, M = sub_protos;
+  const long long HWll = (long long)proj_h * proj_w;
+  C3D_REQUIRE(B > 0 && B <= kMaxBatch && C >= 2 && C <= kMaxClasses, "bad batch / n_classes");
+  C3D_REQUIRE(D > 0 && D % 4 == 0 && D <= 1024, "feature dim must be a multiple of 4, <= 1024");
+  C3D_REQUIRE(HWll > 0 && B * HWll < (1ll << 31), "batch*H*W must be < 2^31");
+  C3D_REQUIRE(feats && workspace && grad_out && grad_feats, "null pointer argument");
+  C3D_REQUIRE((reinterpret_cast<uintptr_t>(grad_feats) & 15) == 0, "grad_feats must be 16 B aligned");
+  const int HW = (int)HWll;
+  LossWs w = carve(workspace, B, C, HW, D, M);
+  const int Kc = (C - 1) * M;
+  int tile_rows, n_tiles; size_t smem;
+  C3D_REQUIRE(rows_config(D, Kc, &tile_rows, &n_tiles, &smem) == 0,
+              "bank does not fit shared memory tiling (D=%d, Kc=%d)", D, Kc);
+
+  const size_t n = (size_t)B * D * HW, n4 = n / 4;
+  {
+    const int threads = 512;
+    long long blocks = (long long)((n4 + threads - 1) / threads);
+    const int wave = kNumSMs * 4;
+    const int grid = (int)(blocks < wave ? (blocks > 0 ? blocks : 1) : wave);
+    fill_zero_kernel<<<grid, threads, 0, stream>>>(reinterpret_cast<float4*>(grad_feats), n4,
+                                                   grad_feats + n4 * 4, (int)(n - n4 * 4));
+    int rc = check_launch("fill_zero_kernel");
+    if (rc) return rc;
+  }
+  RowsParams p{};
+  p.feats = feats; p.bank_n = w.bank_n; p.pix_list = w.pix_list; p.cls_list = w.cls_list;
+  p.cnt_list = w.cnt_list; p.info = w.info; p.grad_out = grad_out; p.grad_feats = grad_feats;
+  p.HW = HW; p.D = D; p.M = M; p.Kc = Kc; p.A = num_anchor; p.tile_rows = tile_rows;
+  p.n_tiles = n_tiles; p.temperature = temperature; p.base_temperature = base_temperature;
+  C3D_CUDA(cudaFuncSetAttribute(loss_rows_kernel<true>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  loss_rows_kernel<true><<<kNumSMs, kRowWarps * 32, smem, stream>>>(p);
+  return check_launch("loss_rows_kernel<bwd>");
+}
+
+extern "C" int c3d_proto_loss_info(const void* workspace, int32_t* host_info4, void* stream_) {
+  // Synchronous debug/strict helper: copies {T, labelled slots, flags, 0} to the host.
+  cudaStream_t stream = (cudaStream_t)stream_;
+  C3D_REQUIRE(workspace && host_info4, "null pointer argument");
+  C3D_CUDA(cudaMemcpyAsync(host_info4, workspace, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+  C3D_CUDA(cudaStreamSynchronize(stream));
+  return C3D_OK;
+}
+
+extern "C" int c3d_proto_loss_rows(const void* workspace, int batch, int dim, int hw, int n_classes,
+                                   int sub_protos, int64_t capacity, int32_t* pix, int32_t* cls,
+                                   int32_t* cnt, void* stream_) {
+  // Exports the labelled-pixel slots of the last forward (device to device):
+  // pix = scan*HW + pixel, cls = class, cnt = how many anchors hit the slot.
+  cudaStream_t stream = (cudaStream_t)stream_;
+  C3D_REQUIRE(workspace && pix && cls && cnt, "null pointer argument");
+  C3D_REQUIRE(capacity > 0 && capacity <= (int64_t)batch * hw, "bad capacity");
+  LossWs w = carve(const_cast<void*>(workspace), batch, n_classes, hw, dim, sub_protos);
+  const size_t n = (size_t)capacity * 4;
+  C3D_CUDA(cudaMemcpyAsync(pix, w.pix_list, n, cudaMemcpyDeviceToDevice, stream));
+  C3D_CUDA(cudaMemcpyAsync(cls, w.cls_list, n, cudaMemcpyDeviceToDevice, stream));
+  C3D_CUDA(cudaMemcpyAsync(cnt, w.cnt_list, n, cudaMemcpyDeviceToDevice, stream));
+  return C3D_OK;
+}

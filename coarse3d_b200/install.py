@@ -19,9 +19,12 @@ def install(pc_processor=None):
         pc_processor = sys.modules.get("pc_processor") or importlib.import_module("pc_processor")
     from .pc_processor.dataset.preprocess.projection import RangeProjection
     from .pc_processor.postproc.knn import KNN
+    from .pc_processor.loss.contrast_pixel_loss import ContrastMEMLoss
 
     pc_processor.dataset.preprocess.projection.RangeProjection = RangeProjection
     pc_processor.dataset.preprocess.RangeProjection = RangeProjection
     pc_processor.postproc.knn.KNN = KNN
     pc_processor.postproc.KNN = KNN
+    pc_processor.loss.contrast_pixel_loss.ContrastMEMLoss = ContrastMEMLoss
+    pc_processor.loss.ContrastMEMLoss = ContrastMEMLoss
     return pc_processor

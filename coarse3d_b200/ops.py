@@ -160,6 +160,105 @@ def knn_batch(proj_range, proj_argmax, unproj_range, px, py, offsets, knn, searc
     return out
 
 
+# --------------------------------------------------------------------- a2 --
+class ProtoLossConfig(NamedTuple):
+    ignore_label: int = 0
+    temperature: float = 0.1
+    base_temperature: float = 0.07
+    num_anchor: int = 50
+
+
+FLAG_NO_ANCHOR, FLAG_BAD_KEEP, FLAG_KEEP_ROWS, FLAG_BAD_LABEL = 1, 2, 4, 8
+
+
+def proto_loss_workspace(batch, n_classes, hw, dim, sub_protos, device):
+    n = lib.c3d_proto_loss_workspace_bytes(batch, n_classes, hw, dim, sub_protos)
+    if n == 0:
+        raise ValueError("bad prototype-loss shape")
+    return torch.empty((n,), dtype=torch.uint8, device=device)
+
+
+def proto_loss_info(workspace):
+    """(T segments, labelled pixels, flags) of the last forward.  Synchronises."""
+    host = (ctypes.c_int32 * 4)()
+    check(lib.c3d_proto_loss_info(_p(workspace), ctypes.cast(host, ctypes.c_void_p), _stream()))
+    return int(host[0]), int(host[1]), int(host[2])
+
+
+def proto_loss_rows(workspace, batch, dim, hw, n_classes, sub_protos):
+    """Labelled-pixel slots of the last forward: (pix, cls, cnt) int32 tensors,
+    sorted by (scan, class, pixel).  Synchronises (reads the slot count)."""
+    _, n_lab, _ = proto_loss_info(workspace)
+    dev = workspace.device
+    pix, cls, cnt = (torch.empty((max(n_lab, 1),), dtype=torch.int32, device=dev) for _ in range(3))
+    if n_lab:
+        check(lib.c3d_proto_loss_rows(_p(workspace), batch, dim, hw, n_classes, sub_protos, n_lab,
+                                      _p(pix), _p(cls), _p(cnt), _stream()))
+    return pix[:n_lab], cls[:n_lab], cnt[:n_lab]
+
+
+class _ProtoLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feats, probs, labels, keep_mask, queue, cfg, keep, seed, workspace):
+        B, D, H, W = feats.shape
+        C, M, _ = queue.shape
+        loss = torch.empty((), dtype=torch.float32, device=feats.device)
+        check(lib.c3d_proto_loss_forward(
+            _p(feats), _p(probs), _p(labels), _p(keep_mask), _p(queue), B, D, H, W, C, M,
+            int(cfg.ignore_label), float(cfg.temperature), float(cfg.base_temperature),
+            int(cfg.num_anchor), _p(keep), 0 if keep is None else keep.shape[0], int(seed),
+            _p(workspace), _p(loss), _stream()))
+        ctx.save_for_backward(feats)
+        ctx.workspace, ctx.cfg, ctx.cm = workspace, cfg, (C, M)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (feats,) = ctx.saved_tensors
+        B, D, H, W = feats.shape
+        C, M = ctx.cm
+        cfg = ctx.cfg
+        grad_out = grad_out.contiguous().float()
+        grad = torch.empty_like(feats)
+        check(lib.c3d_proto_loss_backward(
+            _p(feats), B, D, H, W, C, M, float(cfg.temperature), float(cfg.base_temperature),
+            int(cfg.num_anchor), _p(ctx.workspace), _p(grad_out), _p(grad), _stream()))
+        return grad, None, None, None, None, None, None, None, None
+
+
+def proto_loss(feats, probs, labels, keep_mask, proto_queue, cfg: ProtoLossConfig, keep=None,
+               seed=None, workspace=None):
+    """ContrastMEMLoss.forward (contrast_pixel_loss.py:27-75) on device tensors.
+
+    feats (B,D,H,W) f32 [grad], probs (B,C,H,W) f32, labels (B,H,W) i64,
+    keep_mask (B,H,W) bool or None, proto_queue (C,M,D) f32.  `keep` (T,A) i64
+    injects the sampled anchors; otherwise they are drawn on the device from
+    `seed` (default: drawn from torch's global CPU generator).
+    Returns (loss 0-dim tensor, workspace).
+    """
+    _need_cuda(feats=feats, probs=probs, labels=labels, keep_mask=keep_mask,
+               proto_queue=proto_queue, keep=keep)
+    if feats.dtype != torch.float32 or probs.dtype != torch.float32 or proto_queue.dtype != torch.float32:
+        raise ValueError("feats / probs / proto_queue must be float32")
+    if labels.dtype != torch.int64:
+        raise ValueError("labels must be int64")
+    if keep_mask is not None and keep_mask.dtype not in (torch.bool, torch.uint8):
+        raise ValueError("keep_mask must be bool")
+    if keep is not None and (keep.dtype != torch.int64 or keep.dim() != 2
+                             or keep.shape[1] != cfg.num_anchor):
+        raise ValueError("keep must be (T, num_anchor) int64")
+    B, D, H, W = feats.shape
+    C, M, D2 = proto_queue.shape
+    if D2 != D or probs.shape != (B, C, H, W) or labels.shape != (B, H, W):
+        raise ValueError("shape mismatch between feats / probs / labels / proto_queue")
+    if workspace is None:
+        workspace = proto_loss_workspace(B, C, H * W, D, M, feats.device)
+    if seed is None:
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+    loss = _ProtoLossFn.apply(feats, probs, labels, keep_mask, proto_queue, cfg, keep, seed, workspace)
+    return loss, workspace
+
+
 def launch_count():
     """Kernel launches enqueued by the library since load."""
     return _lib.launch_count()

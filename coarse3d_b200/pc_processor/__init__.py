@@ -11,4 +11,4 @@ the same names, signatures and error behaviour as the reference:
 `coarse3d_b200.install()` swaps them into the real `pc_processor` package so
 that tasks/weak_segmentation runs unchanged.
 """
-from . import dataset, postproc  # noqa: F401
+from . import dataset, loss, postproc  # noqa: F401

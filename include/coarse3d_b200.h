@@ -96,6 +96,59 @@ int c3d_knn_batch(
     void* out_labels,             /* [total_points] i64 or i32, in [1, C-1]      */
     void* stream);
 
+/* ---------------------------------------------------------------- a2 ----
+ * ContrastMEMLoss.forward, pc_processor/loss/contrast_pixel_loss.py:27-195,
+ * and its autograd (gradient w.r.t. feats only; the bank is detached at
+ * tasks/weak_segmentation/trainer.py:675-678).
+ *
+ * Anchors: with keep == NULL the A anchors per (scan, class) segment are drawn
+ * on the device (entropy-weighted, with replacement, Philox keyed by `seed`),
+ * the statistical equivalent of torch.multinomial (:114-116).  With keep != NULL
+ * the caller injects the sampled pixel indices, shape [keep_rows, num_anchor],
+ * rows in the reference's X_ptr order (scan ascending, class ascending); every
+ * index must be a kept pixel of that segment's class (what multinomial returns).
+ * Duplicate anchors are evaluated once and weighted by their multiplicity.
+ * The sub-prototype randperm (:142-143) is not applied (it only reorders sums).
+ *
+ * The workspace carries the sampled rows from forward to backward; it must
+ * stay untouched in between.  ws[0..2] (int32) = {T segments, labelled pixels,
+ * flags}; flags: 1 no anchor (loss is NaN; the reference crashes), 2 injected
+ * index not in its segment, 4 keep_rows != T, 8 label outside [0, C).
+ */
+size_t c3d_proto_loss_workspace_bytes(int batch, int n_classes, int hw, int dim, int sub_protos);
+
+int c3d_proto_loss_forward(
+    const float* feats,           /* [B, D, H, W]                                */
+    const float* probs,           /* [B, C, H, W] softmax output (:46-49)        */
+    const int64_t* labels,        /* [B, H, W]                                   */
+    const uint8_t* keep_mask,     /* [B, H, W] bool, or NULL (:36-38)            */
+    const float* proto_queue,     /* [C, M, D]                                   */
+    int batch, int dim, int proj_h, int proj_w, int n_classes, int sub_protos,
+    int ignore_label, float temperature, float base_temperature, int num_anchor,
+    const int64_t* keep,          /* [keep_rows, num_anchor] or NULL             */
+    int keep_rows, uint64_t seed,
+    void* workspace,              /* c3d_proto_loss_workspace_bytes, 256 B aligned */
+    float* loss_out,              /* [1]                                         */
+    void* stream);
+
+int c3d_proto_loss_backward(
+    const float* feats, int batch, int dim, int proj_h, int proj_w, int n_classes,
+    int sub_protos, float temperature, float base_temperature, int num_anchor,
+    void* workspace,              /* as left by c3d_proto_loss_forward           */
+    const float* grad_out,        /* [1] upstream gradient of the scalar loss    */
+    float* grad_feats,            /* [B, D, H, W] dense, fully written           */
+    void* stream);
+
+/* Synchronous: copies {T, labelled pixels, flags, 0} to host_info4 (host). */
+int c3d_proto_loss_info(const void* workspace, int32_t* host_info4, void* stream);
+
+/* Exports the first `capacity` labelled-pixel slots of the last forward, sorted
+ * by (scan, class, pixel): pix = scan*H*W + pixel, cls = class, cnt = number of
+ * anchors that hit the slot (sums to num_anchor per segment). */
+int c3d_proto_loss_rows(const void* workspace, int batch, int dim, int hw, int n_classes,
+                        int sub_protos, int64_t capacity, int32_t* pix, int32_t* cls,
+                        int32_t* cnt, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

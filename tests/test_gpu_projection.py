@@ -101,7 +101,7 @@ def test_depth_ties_follow_the_rule(cuda_device):
 
 
 def test_point_zero_mask_quirk_and_empty_scan(cuda_device):
-    pts = np.array([[5, 0, 0, 1], [5, 0.01, 0, 2]], np.float32)
+    pts = np.array([[5, 1, 0, 1], [5, 1, 0, 2]], np.float32)  # same pixel, same depth
     out = _run_dropin(pts, None, 3.0, -25.0, 4, 8)
     assert out["proj_idx"].max() == 0 and out["proj_mask"].sum() == 0  # projection.py:113
     empty = _run_dropin(np.zeros((0, 4), np.float32), None, 3.0, -25.0, 4, 8)

@@ -13,7 +13,12 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from coarse3d_b200 import ops, synth  # noqa: E402
 
 
-def timeit(fn, iters=20, warmup=5, flush=None):
+ITERS, WARMUP = [20], [5]
+
+
+def timeit(fn, iters=None, warmup=None, flush=None):
+    iters = ITERS[0] if iters is None else iters
+    warmup = WARMUP[0] if warmup is None else warmup
     for _ in range(warmup):
         fn()
     torch.cuda.synchronize()
@@ -35,8 +40,11 @@ def main():
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--shape", default="kitti")
     ap.add_argument("--ops", default="project,knn")
+    ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     args = ap.parse_args()
     shp = synth.SHAPES[args.shape]
+    ITERS[0], WARMUP[0] = args.iters, args.warmup
     B = args.batch
     one, offs1, _, _ = synth.make_batch(shp, min(B, 8), seed0=1000)
     reps = (B + 7) // 8
