@@ -20,7 +20,7 @@ class C3DError(RuntimeError):
 def _load():
     if not os.path.exists(LIB_PATH):
         raise ImportError(
-            "coarse3d_b200: %s is missing. Build it with `python -m coarse3d_b200.build` "
+            "coarse3d_b200: %s is missing. Build it with `python coarse3d_b200/build.py` "
             "(needs nvcc; sm_100a). There is no CPU fallback." % LIB_PATH)
     lib = ctypes.CDLL(LIB_PATH)
     P = c_void_p

@@ -1,6 +1,7 @@
 """Build libcoarse3d_b200.so (the C-ABI CUDA library) in-tree with nvcc for sm_100a.
 
-    python -m coarse3d_b200.build [--force] [--verbose]
+    python coarse3d_b200/build.py [--force] [--verbose]     (run as a script: importing
+    the package needs the library to exist already)
 
 No torch headers are involved: the library is plain CUDA behind `extern "C"`
 (include/coarse3d_b200.h).  nvcc cross-compiles without a GPU.
