@@ -1,0 +1,201 @@
+// Stable multi-split of labelled pixels (shared by the prototype loss and the
+// EMA prototype update).
+//
+//   split_count    labels (+ keep_mask) -> per-tile per-class counts (9 B/px, coalesced)
+//   split_scan     per-scan exclusive prefix over tiles; the last CTA turns the
+//                  B*C totals into the segment table (start, index among non-empty)
+//   split_scatter  labelled pixels -> slots sorted by (segment, pixel); optional
+//                  entropy weight per slot; extra CTAs L2-normalise bank rows
+//
+// Segment order: kClassMajor = false -> (scan, class)  [ContrastMEMLoss X_ptr order,
+// contrast_pixel_loss.py:82-109]; true -> (class, scan), i.e. per class all
+// labelled pixels of the batch in global pixel order [prototype_learning's
+// `label == id_c` row order, salsanext_proto.py:350-365].
+// No atomics decide positions: the order is deterministic.
+#pragma once
+#include "common.cuh"
+
+namespace c3d {
+
+constexpr int kTile = 1024;  // pixels per count/scatter CTA (4 rounds x 256 threads)
+constexpr int kMaxClasses = 64;
+constexpr int kFlagBadLabel = 8;
+enum SplitInfo { kInfoT = 0, kInfoPl = 1, kInfoFlags = 2, kInfoDone = 3, kInfoDone2 = 4 };
+
+template <bool kClassMajor>
+__device__ __forceinline__ int seg_index(int b, int c, int B, int C) {
+  return kClassMajor ? c * B + b : b * C + c;
+}
+
+__device__ __forceinline__ int masked_class(const long long* __restrict__ labels,
+                                            const uint8_t* __restrict__ keep, size_t i,
+                                            int ignore_label) {
+  long long l = labels[i];
+  if (keep && keep[i] == 0) l = ignore_label;  // contrast_pixel_loss.py:36-38
+  return (int)l;
+}
+
+static __global__ void __launch_bounds__(256)
+split_count_kernel(const long long* __restrict__ labels, const uint8_t* __restrict__ keep, int HW,
+                  int nbps, int C, int ignore_label, int32_t* __restrict__ blk_cnt,
+                  int32_t* __restrict__ info) {
+  __shared__ int s_cnt[kMaxClasses];
+  if (threadIdx.x < C) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const int b = blockIdx.x / nbps, tile = blockIdx.x % nbps;
+  bool bad = false;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int pix = tile * kTile + r * 256 + threadIdx.x;
+    if (pix < HW) {
+      const int c = masked_class(labels, keep, (size_t)b * HW + pix, ignore_label);
+      if (c != ignore_label) {
+        if (c < 0 || c >= C) bad = true; else atomicAdd(&s_cnt[c], 1);
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < C) blk_cnt[(size_t)blockIdx.x * C + threadIdx.x] = s_cnt[threadIdx.x];
+  if (bad) atomicOr(&info[kInfoFlags], kFlagBadLabel);
+}
+
+// CTA b: warp per class, exclusive prefix of the tile counts of scan b.  The
+// last CTA to finish turns the B*C totals into the segment table.
+template <bool kClassMajor>
+__global__ void __launch_bounds__(1024)
+split_scan_kernel(int32_t* __restrict__ blk_cnt, int nbps, int B, int C,
+                 int32_t* __restrict__ seg_cnt, int32_t* __restrict__ seg_start,
+                 int32_t* __restrict__ seg_tidx, int32_t* __restrict__ info) {
+  const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nwarps = blockDim.x >> 5;
+  for (int c = warp; c < C; c += nwarps) {
+    int carry = 0;
+    for (int base = 0; base < nbps; base += 32) {
+      const int i = base + lane;
+      int32_t* p = blk_cnt + ((size_t)(b * nbps + i)) * C + c;
+      const int v = (i < nbps) ? *p : 0;
+      int incl = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      if (i < nbps) *p = carry + incl - v;
+      carry += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) seg_cnt[seg_index<kClassMajor>(b, c, B, C)] = carry;
+  }
+  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(&info[kInfoDone], 1) == B - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (warp == 0) {
+    int carry = 0, tcarry = 0;
+    const int n = B * C;
+    for (int base = 0; base < n; base += 32) {
+      const int i = base + lane;
+      const int v = (i < n) ? __ldcg(seg_cnt + i) : 0;
+      const int ne = v > 0;
+      int incl = v, tincl = ne;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, incl, o);
+        int u = __shfl_up_sync(0xffffffffu, tincl, o);
+        if (lane >= o) { incl += t; tincl += u; }
+      }
+      if (i < n) {
+        seg_start[i] = carry + incl - v;
+        seg_tidx[i] = ne ? (tcarry + tincl - 1) : -1;
+      }
+      carry += __shfl_sync(0xffffffffu, incl, 31);
+      tcarry += __shfl_sync(0xffffffffu, tincl, 31);
+    }
+    if (lane == 0) {
+      info[kInfoT] = tcarry;
+      info[kInfoPl] = carry;
+      if (tcarry == 0) atomicOr(&info[kInfoFlags], 1);  // no labelled pixel
+      info[kInfoDone] = 0;
+    }
+  }
+}
+
+template <bool kClassMajor, bool kEntropy>
+__global__ void __launch_bounds__(256)
+split_scatter_kernel(const long long* __restrict__ labels, const uint8_t* __restrict__ keep,
+                     const float* __restrict__ probs, int HW, int nbps, int nblk, int B, int C,
+                     int ignore_label, const int32_t* __restrict__ blk_prefix,
+                     const int32_t* __restrict__ seg_start, int32_t* __restrict__ pix_list,
+                     int32_t* __restrict__ cls_list, float* __restrict__ w_list,
+                     int32_t* __restrict__ cnt_list, const float* __restrict__ bank_src,
+                     int bank_rows, int D, float* __restrict__ bank_n) {
+  if ((int)blockIdx.x >= nblk) {
+    // bank rows: F.normalize(x, p=2, dim=-1), eps 1e-12
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rows = bank_rows;
+    for (int k = (blockIdx.x - nblk) * 8 + warp; k < rows; k += (gridDim.x - nblk) * 8) {
+      const float* src = bank_src + (size_t)k * D;
+      float s = 0.f;
+      for (int d = lane; d < D; d += 32) { float v = src[d]; s += v * v; }
+      s = warp_sum(s);
+      const float inv = 1.0f / fmaxf(sqrtf(s), 1e-12f);
+      for (int d = lane; d < D; d += 32) bank_n[(size_t)k * D + d] = src[d] * inv;
+    }
+    return;
+  }
+  __shared__ int s_cnt[4][8][kMaxClasses];  // [round][warp][class] -> exclusive prefix
+  const int b = blockIdx.x / nbps, tile = blockIdx.x % nbps;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 4 * 8 * kMaxClasses; i += 256) (&s_cnt[0][0][0])[i] = 0;
+  __syncthreads();
+  int cls[4], rank[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int pix = tile * kTile + r * 256 + threadIdx.x;
+    int c = -1;
+    if (pix < HW) {
+      c = masked_class(labels, keep, (size_t)b * HW + pix, ignore_label);
+      if (c == ignore_label || c < 0 || c >= C) c = -1;
+    }
+    const unsigned peers = __match_any_sync(0xffffffffu, c);
+    rank[r] = __popc(peers & ((1u << lane) - 1));
+    cls[r] = c;
+    if (c >= 0 && rank[r] == 0) s_cnt[r][warp][c] = __popc(peers);
+  }
+  __syncthreads();
+  if (threadIdx.x < C) {  // exclusive prefix over (round, warp) for class threadIdx.x
+    int run = 0;
+    for (int i = 0; i < 32; ++i) {
+      int* p = &s_cnt[i >> 3][i & 7][threadIdx.x];
+      const int v = *p; *p = run; run += v;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int c = cls[r];
+    if (c < 0) continue;
+    const int pix = tile * kTile + r * 256 + threadIdx.x;
+    const int slot = seg_start[seg_index<kClassMajor>(b, c, B, C)] +
+                     blk_prefix[(size_t)blockIdx.x * C + c] + s_cnt[r][warp][c] + rank[r];
+    pix_list[slot] = b * HW + pix;
+    cls_list[slot] = c;
+    if (kEntropy) {
+      // entropy weight (contrast_pixel_loss.py:46-49)
+      const float* p = probs + (size_t)b * C * HW + pix;
+      float ent = 0.f;
+      for (int k = 0; k < C; ++k) {
+        const float v = __ldg(p + (size_t)k * HW);
+        ent += v * logf(v + 1e-10f);
+      }
+      ent = -ent;
+      w_list[slot] = expf(-(ent * ent));
+      cnt_list[slot] = 0;
+    }
+  }
+}
+
+
+}  // namespace c3d

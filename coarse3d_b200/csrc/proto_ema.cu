@@ -1,0 +1,494 @@
+// a3 -- EMA prototype update (prototype_learning + momentum_update + Sinkhorn).
+//
+// Replaces reference pc_processor/models/salsanext_proto.py:337-402 with its
+// pre-step :497-510 and pc_processor/models/sinkhorn.py:5-33.  The reference
+// evaluates LayerNorm, the (n x C*M) similarity and LayerNorm_C on all
+// n = B*H*W pixels (838 MB of similarities at B=4) and then loops over classes
+// in Python; only labelled pixels influence the update, so everything here runs
+// on the labelled rows only:
+//
+//   E1 split_count/scan/scatter (labelsplit.cuh, class-major): labelled pixels ->
+//      rows sorted by (class, global pixel) = the reference's `label == id_c` order
+//   E2 ema_rows      one warp per row: strided NCHW gather, LayerNorm_D, L2 norm,
+//                    similarity against all C*M normalised prototypes (bank in
+//                    shared memory), amax over M, LayerNorm_C, argmax -> mask;
+//                    keeps the row's feature and its M similarities to its own class
+//   E3 ema_sinkhorn  one CTA per class: 3 Sinkhorn iterations in the reference's
+//                    operation order, argmax / Gumbel-hard assignment
+//   E4 ema_segsum    one CTA per class: per-(class, sub-prototype) feature sums and
+//                    counts, rows accumulated in order (no atomics) -> packed
+//                    [K*D sums | K counts] buffer, the all-reduce payload
+//   E5 ema_apply     normalise sums, EMA where count != 0, renormalise (:379-394)
+#include <math_constants.h>
+
+#include "common.cuh"
+#include "labelsplit.cuh"
+
+namespace c3d {
+
+constexpr int kEmaWarps = 8;
+constexpr int kMaxSub = 32;  // sub-prototypes per class handled in registers
+enum EmaFlag { kEmaNoRows = 1, kEmaBadLabel = 8, kEmaOverflow = 16 };
+
+struct EmaWs {
+  int32_t* info;
+  int32_t* blk_cnt;
+  int32_t* seg_cnt;
+  int32_t* seg_start;
+  int32_t* seg_tidx;
+  int32_t* pix_list;   // [B*HW]
+  int32_t* cls_list;   // [B*HW]
+  float* bank_n;       // [C*M*D]
+  float* feat;         // [max_rows * D]
+  float* simq;         // [max_rows * M]
+  int32_t* maskv;      // [max_rows]
+  int32_t* sub;        // [max_rows] assigned sub-prototype
+  size_t bytes;
+};
+
+static size_t align_up_e(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static EmaWs carve_ema(void* base, int B, int C, int HW, int D, int M, long long max_rows) {
+  EmaWs w;
+  const size_t cap = (size_t)B * HW;
+  const size_t nblk = (size_t)B * ((HW + kTile - 1) / kTile);
+  size_t off = 0;
+  auto take = [&](size_t n) { size_t o = off; off += align_up_e(n); return (char*)base + o; };
+  w.info = (int32_t*)take(8 * 4);
+  w.blk_cnt = (int32_t*)take(nblk * C * 4);
+  w.seg_cnt = (int32_t*)take((size_t)B * C * 4);
+  w.seg_start = (int32_t*)take((size_t)B * C * 4);
+  w.seg_tidx = (int32_t*)take((size_t)B * C * 4);
+  w.pix_list = (int32_t*)take(cap * 4);
+  w.cls_list = (int32_t*)take(cap * 4);
+  w.bank_n = (float*)take((size_t)C * M * D * 4);
+  w.feat = (float*)take((size_t)max_rows * D * 4);
+  w.simq = (float*)take((size_t)max_rows * M * 4);
+  w.maskv = (int32_t*)take((size_t)max_rows * 4);
+  w.sub = (int32_t*)take((size_t)max_rows * 4);
+  w.bytes = off;
+  return w;
+}
+
+// ---------------------------------------------------------------- E2 -------
+struct EmaRowsParams {
+  const float* emb;      // (B, D, HW)
+  const float* bank_n;   // (K, D)
+  const float* ln_d_w; const float* ln_d_b; const float* ln_c_w; const float* ln_c_b;
+  const int32_t* pix_list; const int32_t* cls_list;
+  int32_t* info;
+  float* feat; float* simq; int32_t* maskv;
+  int HW, D, M, C, K, tile_rows, n_tiles, max_rows;
+  float eps;
+};
+
+__global__ void __launch_bounds__(kEmaWarps * 32, 1)
+ema_rows_kernel(EmaRowsParams p) {
+  extern __shared__ __align__(16) float smem[];
+  const int D = p.D, K = p.K, ld = D + 4, KPad = (K + 31) & ~31;
+  float* s_bank = smem;
+  float* s_a = s_bank + (size_t)p.tile_rows * ld;
+  float* s_l = s_a + kEmaWarps * D;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int n_rows = p.info[kInfoPl];
+  if (n_rows > p.max_rows) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&p.info[kInfoFlags], kEmaOverflow);
+    return;
+  }
+  const int n_groups = (n_rows + kEmaWarps - 1) / kEmaWarps;
+  float* my_a = s_a + warp * D;
+  float* my_l = s_l + warp * KPad;
+
+  auto load_tile = [&](int tile) {
+    const int r0 = tile * p.tile_rows;
+    const int rows = min(p.tile_rows, K - r0);
+    const int d4 = D >> 2;
+    for (int i = threadIdx.x; i < rows * d4; i += blockDim.x) {
+      const int r = i / d4, c = i - r * d4;
+      const float4 v = __ldg(reinterpret_cast<const float4*>(p.bank_n + (size_t)(r0 + r) * D) + c);
+      *reinterpret_cast<float4*>(s_bank + (size_t)r * ld + c * 4) = v;
+    }
+  };
+  if (p.n_tiles == 1 && (int)blockIdx.x < n_groups) load_tile(0);
+  __syncthreads();
+
+  for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+    const int slot = grp * kEmaWarps + warp;
+    const bool active = slot < n_rows;
+    int cls = 0;
+    if (active) {
+      const int gpix = p.pix_list[slot];
+      cls = p.cls_list[slot];
+      const int b = gpix / p.HW, pix = gpix - b * p.HW;
+      const float* src = p.emb + (size_t)b * D * p.HW + pix;
+      // LayerNorm over D (salsanext_proto.py:498), biased variance
+      float s = 0.f;
+      for (int d = lane; d < D; d += 32) { const float v = __ldg(src + (size_t)d * p.HW); my_a[d] = v; s += v; }
+      const float mean = warp_sum(s) / (float)D;
+      float v2 = 0.f;
+      for (int d = lane; d < D; d += 32) { const float t = my_a[d] - mean; v2 += t * t; }
+      const float rstd = 1.0f / sqrtf(warp_sum(v2) / (float)D + p.eps);
+      float n2 = 0.f;
+      for (int d = lane; d < D; d += 32) {
+        const float y = (my_a[d] - mean) * rstd * p.ln_d_w[d] + p.ln_d_b[d];
+        my_a[d] = y; n2 += y * y;
+      }
+      const float inv = 1.0f / fmaxf(sqrtf(warp_sum(n2)), 1e-12f);  // l2_normalize (:501)
+      for (int d = lane; d < D; d += 32) {
+        const float y = my_a[d] * inv;
+        my_a[d] = y;
+        p.feat[(size_t)slot * D + d] = y;
+      }
+    }
+    __syncwarp();
+    // similarities against every (class, sub-prototype) (:504)
+    for (int tile = 0; tile < p.n_tiles; ++tile) {
+      if (p.n_tiles > 1) { __syncthreads(); load_tile(tile); __syncthreads(); }
+      if (active) {
+        const int r0 = tile * p.tile_rows;
+        const int rows = min(p.tile_rows, K - r0);
+        for (int kk = lane; kk < rows; kk += 32) {
+          const float4* c4 = reinterpret_cast<const float4*>(s_bank + (size_t)kk * ld);
+          const float4* a4 = reinterpret_cast<const float4*>(my_a);
+          float acc = 0.f;
+#pragma unroll 8
+          for (int j = 0; j < (D >> 2); ++j) {
+            const float4 c = c4[j], a = a4[j];
+            acc += a.x * c.x; acc += a.y * c.y; acc += a.z * c.z; acc += a.w * c.w;
+          }
+          my_l[r0 + kk] = acc;
+        }
+      }
+    }
+    __syncwarp();
+    if (active) {
+      // nearest = amax over M (:506), LayerNorm over C (:507), argmax (:340)
+      float nv[2]; float s = 0.f;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int c = lane + 32 * h;
+        float m = -CUDART_INF_F;
+        if (c < p.C) for (int j = 0; j < p.M; ++j) m = fmaxf(m, my_l[c * p.M + j]);
+        nv[h] = m;
+        if (c < p.C) s += m;
+      }
+      const float mean = warp_sum(s) / (float)p.C;
+      float v2 = 0.f;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) if (lane + 32 * h < p.C) { const float t = nv[h] - mean; v2 += t * t; }
+      const float rstd = 1.0f / sqrtf(warp_sum(v2) / (float)p.C + p.eps);
+      float best = -CUDART_INF_F; int best_c = 0x7fffffff;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int c = lane + 32 * h;
+        if (c < p.C) {
+          const float y = (nv[h] - mean) * rstd * p.ln_c_w[c] + p.ln_c_b[c];
+          if (y > best) { best = y; best_c = c; }  // h ascending keeps the first maximum
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oc = __shfl_xor_sync(0xffffffffu, best_c, o);
+        if (ob > best || (ob == best && oc < best_c)) { best = ob; best_c = oc; }
+      }
+      if (lane == 0) p.maskv[slot] = (best_c == cls);  // mask = label == pred (:341)
+      if (lane < p.M) p.simq[(size_t)slot * p.M + lane] = my_l[cls * p.M + lane];  // sim[..., id_c]
+    }
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------- E3 -------
+__device__ __forceinline__ uint4 philox_e(uint4 ctr, uint2 key) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += 0x9E3779B9u; key.y += 0xBB67AE85u;
+  }
+  return ctr;
+}
+
+// Block-wide sum of an M-vector held per thread in acc[]; result in s_out[0..M).
+__device__ __forceinline__ void block_vec_sum(float (&acc)[kMaxSub], int M, float* s_part /*[8][32]*/,
+                                              float* s_out /*[32]*/) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int m = 0; m < kMaxSub; ++m) {
+    if (m < M) {
+      const float v = warp_sum(acc[m]);
+      if (lane == 0) s_part[warp * kMaxSub + m] = v;
+    }
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < M) {
+    float t = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_part[w * kMaxSub + threadIdx.x];
+    s_out[threadIdx.x] = t;
+  }
+  __syncthreads();
+}
+
+// mode: 0 = one_hot(argmax) (sinkhorn.py:30), 1 = injected Gumbel noise, 2 = device noise
+__global__ void __launch_bounds__(256)
+ema_sinkhorn_kernel(const int32_t* __restrict__ seg_cnt, const int32_t* __restrict__ seg_start,
+                    const int32_t* __restrict__ pix_list, int32_t* __restrict__ info, int B, int M,
+                    int ignore_label, int max_rows, float* __restrict__ simq,
+                    int32_t* __restrict__ sub, const float* __restrict__ gumbel, int mode,
+                    unsigned long long seed, float* __restrict__ proto_target) {
+  const int c = blockIdx.x;
+  if (c == ignore_label || info[kInfoPl] > max_rows) return;
+  const int start = seg_start[c * B];
+  int n = 0;
+  for (int b = 0; b < B; ++b) n += seg_cnt[c * B + b];
+  if (n == 0) return;  // no such class (:356-357)
+  __shared__ float s_part[8 * kMaxSub];
+  __shared__ float s_vec[kMaxSub];
+  __shared__ float s_red[8];
+  float* Q = simq + (size_t)start * M;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float fM = (float)M, fn = (float)n;
+
+  // Q = exp(out / eps); sum_Q (sinkhorn.py:8,13)
+  float tot = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x)
+    for (int m = 0; m < M; ++m) {
+      const float q = expf(Q[(size_t)i * M + m] / 0.05f);
+      Q[(size_t)i * M + m] = q; tot += q;
+    }
+  tot = warp_sum(tot);
+  if (lane == 0) s_red[warp] = tot;
+  __syncthreads();
+  float sum_q = 0.f;
+  for (int w = 0; w < 8; ++w) sum_q += s_red[w];
+
+  // Q /= sum_Q (:14) and the first row sums (:18)
+  float acc[kMaxSub];
+#pragma unroll
+  for (int m = 0; m < kMaxSub; ++m) acc[m] = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+#pragma unroll
+    for (int m = 0; m < kMaxSub; ++m)
+      if (m < M) { const float q = Q[(size_t)i * M + m] / sum_q; Q[(size_t)i * M + m] = q; acc[m] += q; }
+  }
+  block_vec_sum(acc, M, s_part, s_vec);
+
+  for (int it = 0; it < 3; ++it) {  // sinkhorn.py:16-24
+    float rs[kMaxSub];
+#pragma unroll
+    for (int m = 0; m < kMaxSub; ++m) { rs[m] = (m < M) ? s_vec[m] : 1.f; acc[m] = 0.f; }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      float q[kMaxSub]; float cs = 0.f;
+#pragma unroll
+      for (int m = 0; m < kMaxSub; ++m)
+        if (m < M) { q[m] = Q[(size_t)i * M + m] / rs[m]; q[m] = q[m] / fM; cs += q[m]; }
+#pragma unroll
+      for (int m = 0; m < kMaxSub; ++m)
+        if (m < M) { q[m] = q[m] / cs; q[m] = q[m] / fn; Q[(size_t)i * M + m] = q[m]; acc[m] += q[m]; }
+    }
+    if (it < 2) block_vec_sum(acc, M, s_part, s_vec);
+  }
+
+  // Q *= B; argmax; assignment (sinkhorn.py:26-31)
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int slot = start + i;
+    float best = -CUDART_INF_F, bestg = -CUDART_INF_F; int idx = 0, hard = 0;
+    for (int m = 0; m < M; ++m) {
+      const float q = Q[(size_t)i * M + m] * fn;
+      if (q > best) { best = q; idx = m; }
+      float g = 0.f;
+      if (mode == 1) g = gumbel[(size_t)slot * M + m];
+      else if (mode == 2) {
+        const unsigned long long ctr = (unsigned long long)slot * M + m;
+        const uint4 r = philox_e(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), 1u, 0u),
+                                 make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+        const float u = ((float)(r.x >> 8) + 0.5f) * (1.0f / 16777216.0f);
+        g = -logf(-logf(u));
+      }
+      const float y = (q + g) / 0.5f;  // F.gumbel_softmax(tau=0.5); softmax is monotone
+      if (y > bestg) { bestg = y; hard = m; }
+    }
+    sub[slot] = (mode == 0) ? idx : hard;
+    if (proto_target) proto_target[pix_list[slot]] = (float)idx + (float)(M * c);  // :390-392
+  }
+}
+
+// ---------------------------------------------------------------- E4 -------
+// packed = [K*D sums | K counts]; one CTA per class, thread owns feature columns,
+// rows accumulated in order => bitwise reproducible.
+__global__ void __launch_bounds__(256)
+ema_segsum_kernel(const int32_t* __restrict__ seg_cnt, const int32_t* __restrict__ seg_start,
+                  const int32_t* __restrict__ info, int B, int M, int D, int K, int ignore_label,
+                  int max_rows, const float* __restrict__ feat, const int32_t* __restrict__ maskv,
+                  const int32_t* __restrict__ sub, float* __restrict__ packed) {
+  extern __shared__ float s_sum[];  // [M][D] then [M] counts
+  float* s_cnt = s_sum + (size_t)M * D;
+  const int c = blockIdx.x;
+  for (int i = threadIdx.x; i < M * D + M; i += blockDim.x) s_sum[i] = 0.f;
+  __syncthreads();
+  int n = 0, start = 0;
+  if (c != ignore_label && info[kInfoPl] <= max_rows) {
+    start = seg_start[c * B];
+    for (int b = 0; b < B; ++b) n += seg_cnt[c * B + b];
+  }
+  for (int i = 0; i < n; ++i) {
+    const int slot = start + i;
+    if (!maskv[slot]) continue;  // m_q = q * mask, c_q = feat * mask (:363-375)
+    const int m = sub[slot];
+    for (int d = threadIdx.x; d < D; d += blockDim.x) s_sum[m * D + d] += feat[(size_t)slot * D + d];
+    if (threadIdx.x == 0) s_cnt[m] += 1.0f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < M * D; i += blockDim.x) packed[(size_t)c * M * D + i] = s_sum[i];
+  if ((int)threadIdx.x < M) packed[(size_t)K * D + c * M + threadIdx.x] = s_cnt[threadIdx.x];
+}
+
+// ---------------------------------------------------------------- E5 -------
+__global__ void __launch_bounds__(256)
+ema_apply_kernel(const float* __restrict__ protos_in, const float* __restrict__ packed, int C, int M,
+                 int D, int ignore_label, float mom, float one_minus_mom,
+                 float* __restrict__ protos_out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int K = C * M;
+  const int k = blockIdx.x * 8 + warp;
+  if (k >= K) return;
+  const int c = k / M;
+  const float* cnt = packed + (size_t)K * D;
+  float csum = 0.f;
+  for (int m = lane; m < M; m += 32) csum += cnt[c * M + m];
+  csum = warp_sum(csum);
+  const bool update = (c != ignore_label) && (csum > 0.f) && (cnt[k] != 0.f);  // :379,383
+  const float* old = protos_in + (size_t)k * D;
+  const float* f = packed + (size_t)k * D;
+  float o2 = 0.f, f2 = 0.f;
+  for (int d = lane; d < D; d += 32) { o2 += old[d] * old[d]; f2 += f[d] * f[d]; }
+  const float oinv = 1.0f / fmaxf(sqrtf(warp_sum(o2)), 1e-12f);  // prototypes <- l2norm (:502)
+  const float finv = 1.0f / fmaxf(sqrtf(warp_sum(f2)), 1e-12f);  // f = normalize(f) (:380)
+  float n2 = 0.f;
+  for (int d = lane; d < D; d += 32) {
+    float v = old[d] * oinv;
+    if (update) v = mom * v + one_minus_mom * (f[d] * finv);       // momentum_update (:19-31)
+    n2 += v * v;
+  }
+  const float ninv = 1.0f / fmaxf(sqrtf(warp_sum(n2)), 1e-12f);    // l2_normalize(protos) (:394)
+  for (int d = lane; d < D; d += 32) {
+    float v = old[d] * oinv;
+    if (update) v = mom * v + one_minus_mom * (f[d] * finv);
+    protos_out[(size_t)k * D + d] = v * ninv;
+  }
+}
+
+static int ema_rows_config(int D, int K, int* tile_rows, int* n_tiles, size_t* smem) {
+  const size_t budget = 227 * 1024;
+  const size_t fixed = ((size_t)kEmaWarps * D + (size_t)kEmaWarps * ((K + 31) & ~31)) * 4;
+  const size_t row = (size_t)(D + 4) * 4;
+  if (fixed + 32 * row > budget) return -1;
+  int tr = (int)((budget - fixed) / row);
+  if (tr >= K) tr = K; else tr &= ~31;
+  *tile_rows = tr;
+  *n_tiles = (K + tr - 1) / tr;
+  *smem = fixed + (size_t)tr * row;
+  return 0;
+}
+
+}  // namespace c3d
+
+using namespace c3d;
+
+extern "C" size_t c3d_proto_ema_workspace_bytes(int batch, int n_classes, int hw, int dim,
+                                                int sub_protos, int64_t max_rows) {
+  if (batch <= 0 || n_classes < 2 || hw <= 0 || dim <= 0 || sub_protos <= 0 || max_rows <= 0) return 0;
+  return carve_ema(nullptr, batch, n_classes, hw, dim, sub_protos, max_rows).bytes;
+}
+
+extern "C" int c3d_proto_ema_accumulate(
+    const float* embedding, const int64_t* label, const float* prototypes, const float* ln_d_w,
+    const float* ln_d_b, const float* ln_c_w, const float* ln_c_b, float ln_eps, int batch, int dim,
+    int proj_h, int proj_w, int n_classes, int sub_protos, int ignore_label, int64_t max_rows,
+    const float* gumbel, int assign_mode, uint64_t seed, void* workspace, float* packed,
+    float* proto_target, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int B = batch, D = dim, C = n_classes, M = sub_protos;
+  const long long HWll = (long long)proj_h * proj_w;
+  C3D_REQUIRE(B > 0 && B <= kMaxBatch, "batch must be in [1, %d]", kMaxBatch);
+  C3D_REQUIRE(C >= 2 && C <= kMaxClasses, "n_classes must be in [2, %d]", kMaxClasses);
+  C3D_REQUIRE(M > 0 && M <= kMaxSub, "sub_protos must be in [1, %d]", kMaxSub);
+  C3D_REQUIRE(D > 0 && D % 4 == 0 && D <= 1024, "feature dim must be a multiple of 4, <= 1024");
+  C3D_REQUIRE(HWll > 0 && B * HWll < (1ll << 31), "batch*H*W must be < 2^31");
+  C3D_REQUIRE(max_rows > 0 && max_rows <= B * HWll, "max_rows must be in [1, B*H*W]");
+  C3D_REQUIRE(assign_mode >= 0 && assign_mode <= 2, "assign_mode must be 0, 1 or 2");
+  C3D_REQUIRE(assign_mode != 1 || gumbel, "assign_mode 1 needs the gumbel noise");
+  C3D_REQUIRE(embedding && label && prototypes && ln_d_w && ln_d_b && ln_c_w && ln_c_b &&
+              workspace && packed, "null pointer argument");
+  C3D_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "workspace must be 256 B aligned");
+  const int HW = (int)HWll, K = C * M;
+  EmaWs w = carve_ema(workspace, B, C, HW, D, M, max_rows);
+  const int nbps = (HW + kTile - 1) / kTile, nblk = B * nbps;
+  int tile_rows, n_tiles; size_t smem;
+  C3D_REQUIRE(ema_rows_config(D, K, &tile_rows, &n_tiles, &smem) == 0,
+              "bank does not fit shared memory tiling (D=%d, K=%d)", D, K);
+  const size_t seg_smem = ((size_t)M * D + M) * sizeof(float);
+  C3D_REQUIRE(seg_smem <= 227 * 1024, "M*D too large for the segmented-sum kernel");
+
+  C3D_CUDA(cudaMemsetAsync(w.info, 0, 8 * 4, stream));
+  if (proto_target) C3D_CUDA(cudaMemsetAsync(proto_target, 0, (size_t)B * HW * 4, stream));
+  int rc;
+  split_count_kernel<<<nblk, 256, 0, stream>>>((const long long*)label, nullptr, HW, nbps, C,
+                                               ignore_label, w.blk_cnt, w.info);
+  if ((rc = check_launch("split_count_kernel"))) return rc;
+  split_scan_kernel<true><<<B, 1024, 0, stream>>>(w.blk_cnt, nbps, B, C, w.seg_cnt, w.seg_start,
+                                                  w.seg_tidx, w.info);
+  if ((rc = check_launch("split_scan_kernel"))) return rc;
+  split_scatter_kernel<true, false><<<nblk + 16, 256, 0, stream>>>(
+      (const long long*)label, nullptr, nullptr, HW, nbps, nblk, B, C, ignore_label, w.blk_cnt,
+      w.seg_start, w.pix_list, w.cls_list, nullptr, nullptr, prototypes, K, D, w.bank_n);
+  if ((rc = check_launch("split_scatter_kernel"))) return rc;
+
+  EmaRowsParams p{};
+  p.emb = embedding; p.bank_n = w.bank_n; p.ln_d_w = ln_d_w; p.ln_d_b = ln_d_b;
+  p.ln_c_w = ln_c_w; p.ln_c_b = ln_c_b; p.pix_list = w.pix_list; p.cls_list = w.cls_list;
+  p.info = w.info; p.feat = w.feat; p.simq = w.simq; p.maskv = w.maskv;
+  p.HW = HW; p.D = D; p.M = M; p.C = C; p.K = K; p.tile_rows = tile_rows; p.n_tiles = n_tiles;
+  p.max_rows = (int)max_rows; p.eps = ln_eps;
+  C3D_CUDA(cudaFuncSetAttribute(ema_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)smem));
+  ema_rows_kernel<<<kNumSMs, kEmaWarps * 32, smem, stream>>>(p);
+  if ((rc = check_launch("ema_rows_kernel"))) return rc;
+  ema_sinkhorn_kernel<<<C, 256, 0, stream>>>(w.seg_cnt, w.seg_start, w.pix_list, w.info, B, M,
+                                             ignore_label, (int)max_rows, w.simq, w.sub, gumbel,
+                                             assign_mode, seed, proto_target);
+  if ((rc = check_launch("ema_sinkhorn_kernel"))) return rc;
+  if (seg_smem > 48 * 1024)
+    C3D_CUDA(cudaFuncSetAttribute(ema_segsum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)seg_smem));
+  ema_segsum_kernel<<<C, 256, seg_smem, stream>>>(w.seg_cnt, w.seg_start, w.info, B, M, D, K,
+                                                  ignore_label, (int)max_rows, w.feat, w.maskv,
+                                                  w.sub, packed);
+  return check_launch("ema_segsum_kernel");
+}
+
+extern "C" int c3d_proto_ema_apply(const float* prototypes_in, const float* packed, int n_classes,
+                                   int sub_protos, int dim, int ignore_label, double momentum,
+                                   float* prototypes_out, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  C3D_REQUIRE(prototypes_in && packed && prototypes_out, "null pointer argument");
+  C3D_REQUIRE(n_classes >= 2 && sub_protos > 0 && dim > 0, "bad prototype shape");
+  const int K = n_classes * sub_protos;
+  // weak-scalar rounding of the reference: momentum and (1 - momentum) are Python
+  // floats multiplied into float32 tensors (salsanext_proto.py:20)
+  ema_apply_kernel<<<(K + 7) / 8, 256, 0, stream>>>(prototypes_in, packed, n_classes, sub_protos,
+                                                    dim, ignore_label, (float)momentum,
+                                                    (float)(1.0 - momentum), prototypes_out);
+  return check_launch("ema_apply_kernel");
+}
+
+extern "C" int c3d_proto_ema_info(const void* workspace, int32_t* host_info4, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  C3D_REQUIRE(workspace && host_info4, "null pointer argument");
+  C3D_CUDA(cudaMemcpyAsync(host_info4, workspace, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+  C3D_CUDA(cudaStreamSynchronize(stream));
+  return C3D_OK;
+}

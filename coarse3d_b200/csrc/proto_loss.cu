@@ -24,15 +24,13 @@
 #include <math_constants.h>
 
 #include "common.cuh"
+#include "labelsplit.cuh"
 
 namespace c3d {
 
-constexpr int kTile = 1024;        // pixels per count/scatter CTA (4 rounds x 256 threads)
-constexpr int kMaxClasses = 64;
 constexpr int kRowWarps = 8;       // rows processed concurrently per loss_rows CTA
 
-enum LossFlag { kFlagNoAnchor = 1, kFlagBadKeep = 2, kFlagKeepRows = 4, kFlagBadLabel = 8 };
-enum LossInfo { kInfoT = 0, kInfoPl = 1, kInfoFlags = 2, kInfoDone = 3, kInfoDone2 = 4 };
+enum LossFlag { kFlagNoAnchor = 1, kFlagBadKeep = 2, kFlagKeepRows = 4 };  // 8 = kFlagBadLabel
 
 struct LossWs {
   int32_t* info;       // [8]
@@ -70,175 +68,6 @@ static LossWs carve(void* base, int B, int C, int HW, int D, int M) {
   w.bank_n = (float*)take((size_t)(C - 1) * M * D * 4);
   w.bytes = off;
   return w;
-}
-
-// ---------------------------------------------------------------- K1 -------
-__device__ __forceinline__ int masked_class(const long long* __restrict__ labels,
-                                            const uint8_t* __restrict__ keep, size_t i,
-                                            int ignore_label) {
-  long long l = labels[i];
-  if (keep && keep[i] == 0) l = ignore_label;  // contrast_pixel_loss.py:36-38
-  return (int)l;
-}
-
-__global__ void __launch_bounds__(256)
-loss_count_kernel(const long long* __restrict__ labels, const uint8_t* __restrict__ keep, int HW,
-                  int nbps, int C, int ignore_label, int32_t* __restrict__ blk_cnt,
-                  int32_t* __restrict__ info) {
-  __shared__ int s_cnt[kMaxClasses];
-  if (threadIdx.x < C) s_cnt[threadIdx.x] = 0;
-  __syncthreads();
-  const int b = blockIdx.x / nbps, tile = blockIdx.x % nbps;
-  bool bad = false;
-#pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    const int pix = tile * kTile + r * 256 + threadIdx.x;
-    if (pix < HW) {
-      const int c = masked_class(labels, keep, (size_t)b * HW + pix, ignore_label);
-      if (c != ignore_label) {
-        if (c < 0 || c >= C) bad = true; else atomicAdd(&s_cnt[c], 1);
-      }
-    }
-  }
-  __syncthreads();
-  if (threadIdx.x < C) blk_cnt[(size_t)blockIdx.x * C + threadIdx.x] = s_cnt[threadIdx.x];
-  if (bad) atomicOr(&info[kInfoFlags], kFlagBadLabel);
-}
-
-// ---------------------------------------------------------------- K2 -------
-// CTA b: warp per class, exclusive prefix of the tile counts of scan b.  The
-// last CTA to finish turns the B*C totals into the segment table.
-__global__ void __launch_bounds__(1024)
-loss_scan_kernel(int32_t* __restrict__ blk_cnt, int nbps, int B, int C,
-                 int32_t* __restrict__ seg_cnt, int32_t* __restrict__ seg_start,
-                 int32_t* __restrict__ seg_tidx, int32_t* __restrict__ info) {
-  const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nwarps = blockDim.x >> 5;
-  for (int c = warp; c < C; c += nwarps) {
-    int carry = 0;
-    for (int base = 0; base < nbps; base += 32) {
-      const int i = base + lane;
-      int32_t* p = blk_cnt + ((size_t)(b * nbps + i)) * C + c;
-      const int v = (i < nbps) ? *p : 0;
-      int incl = v;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        int t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
-      }
-      if (i < nbps) *p = carry + incl - v;
-      carry += __shfl_sync(0xffffffffu, incl, 31);
-    }
-    if (lane == 0) seg_cnt[b * C + c] = carry;
-  }
-  __shared__ int s_last;
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) s_last = (atomicAdd(&info[kInfoDone], 1) == B - 1);
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  if (warp == 0) {
-    int carry = 0, tcarry = 0;
-    const int n = B * C;
-    for (int base = 0; base < n; base += 32) {
-      const int i = base + lane;
-      const int v = (i < n) ? __ldcg(seg_cnt + i) : 0;
-      const int ne = v > 0;
-      int incl = v, tincl = ne;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        int t = __shfl_up_sync(0xffffffffu, incl, o);
-        int u = __shfl_up_sync(0xffffffffu, tincl, o);
-        if (lane >= o) { incl += t; tincl += u; }
-      }
-      if (i < n) {
-        seg_start[i] = carry + incl - v;
-        seg_tidx[i] = ne ? (tcarry + tincl - 1) : -1;
-      }
-      carry += __shfl_sync(0xffffffffu, incl, 31);
-      tcarry += __shfl_sync(0xffffffffu, tincl, 31);
-    }
-    if (lane == 0) {
-      info[kInfoT] = tcarry;
-      info[kInfoPl] = carry;
-      if (tcarry == 0) atomicOr(&info[kInfoFlags], kFlagNoAnchor);
-      info[kInfoDone] = 0;
-    }
-  }
-}
-
-// ---------------------------------------------------------------- K3 -------
-__global__ void __launch_bounds__(256)
-loss_scatter_kernel(const long long* __restrict__ labels, const uint8_t* __restrict__ keep,
-                    const float* __restrict__ probs, int HW, int nbps, int nblk, int C,
-                    int ignore_label, const int32_t* __restrict__ blk_prefix,
-                    const int32_t* __restrict__ seg_start, int32_t* __restrict__ pix_list,
-                    int32_t* __restrict__ cls_list, float* __restrict__ w_list,
-                    int32_t* __restrict__ cnt_list, const float* __restrict__ queue, int M, int D,
-                    float* __restrict__ bank_n) {
-  if ((int)blockIdx.x >= nblk) {
-    // bank rows: F.normalize(contrast_feature) (:167); classes 1..C-1 (:139-140)
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int rows = (C - 1) * M;
-    for (int k = (blockIdx.x - nblk) * 8 + warp; k < rows; k += (gridDim.x - nblk) * 8) {
-      const float* src = queue + (size_t)(k + M) * D;  // skip class 0
-      float s = 0.f;
-      for (int d = lane; d < D; d += 32) { float v = src[d]; s += v * v; }
-      s = warp_sum(s);
-      const float inv = 1.0f / fmaxf(sqrtf(s), 1e-12f);
-      for (int d = lane; d < D; d += 32) bank_n[(size_t)k * D + d] = src[d] * inv;
-    }
-    return;
-  }
-  __shared__ int s_cnt[4][8][kMaxClasses];  // [round][warp][class] -> exclusive prefix
-  const int b = blockIdx.x / nbps, tile = blockIdx.x % nbps;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int i = threadIdx.x; i < 4 * 8 * kMaxClasses; i += 256) (&s_cnt[0][0][0])[i] = 0;
-  __syncthreads();
-  int cls[4], rank[4];
-#pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    const int pix = tile * kTile + r * 256 + threadIdx.x;
-    int c = -1;
-    if (pix < HW) {
-      c = masked_class(labels, keep, (size_t)b * HW + pix, ignore_label);
-      if (c == ignore_label || c < 0 || c >= C) c = -1;
-    }
-    const unsigned peers = __match_any_sync(0xffffffffu, c);
-    rank[r] = __popc(peers & ((1u << lane) - 1));
-    cls[r] = c;
-    if (c >= 0 && rank[r] == 0) s_cnt[r][warp][c] = __popc(peers);
-  }
-  __syncthreads();
-  if (threadIdx.x < C) {  // exclusive prefix over (round, warp) for class threadIdx.x
-    int run = 0;
-    for (int i = 0; i < 32; ++i) {
-      int* p = &s_cnt[i >> 3][i & 7][threadIdx.x];
-      const int v = *p; *p = run; run += v;
-    }
-  }
-  __syncthreads();
-#pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    const int c = cls[r];
-    if (c < 0) continue;
-    const int pix = tile * kTile + r * 256 + threadIdx.x;
-    const int slot = seg_start[b * C + c] + blk_prefix[(size_t)blockIdx.x * C + c] +
-                     s_cnt[r][warp][c] + rank[r];
-    // entropy weight (contrast_pixel_loss.py:46-49)
-    const float* p = probs + (size_t)b * C * HW + pix;
-    float ent = 0.f;
-    for (int k = 0; k < C; ++k) {
-      const float v = __ldg(p + (size_t)k * HW);
-      ent += v * logf(v + 1e-10f);
-    }
-    ent = -ent;
-    pix_list[slot] = b * HW + pix;
-    cls_list[slot] = c;
-    w_list[slot] = expf(-(ent * ent));
-    cnt_list[slot] = 0;
-  }
 }
 
 // ---------------------------------------------------------------- K4 -------
@@ -609,18 +438,19 @@ extern "C" int c3d_proto_loss_forward(
               "bank does not fit shared memory tiling (D=%d, Kc=%d)", D, Kc);
 
   C3D_CUDA(cudaMemsetAsync(w.info, 0, 8 * 4, stream));
-  loss_count_kernel<<<nblk, 256, 0, stream>>>((const long long*)labels, keep_mask, HW, nbps, C,
+  split_count_kernel<<<nblk, 256, 0, stream>>>((const long long*)labels, keep_mask, HW, nbps, C,
                                               ignore_label, w.blk_cnt, w.info);
-  int rc = check_launch("loss_count_kernel");
+  int rc = check_launch("split_count_kernel");
   if (rc) return rc;
-  loss_scan_kernel<<<B, 1024, 0, stream>>>(w.blk_cnt, nbps, B, C, w.seg_cnt, w.seg_start,
+  split_scan_kernel<false><<<B, 1024, 0, stream>>>(w.blk_cnt, nbps, B, C, w.seg_cnt, w.seg_start,
                                            w.seg_tidx, w.info);
-  if ((rc = check_launch("loss_scan_kernel"))) return rc;
+  if ((rc = check_launch("split_scan_kernel"))) return rc;
   const int bank_blocks = 16;
-  loss_scatter_kernel<<<nblk + bank_blocks, 256, 0, stream>>>(
-      (const long long*)labels, keep_mask, probs, HW, nbps, nblk, C, ignore_label, w.blk_cnt,
-      w.seg_start, w.pix_list, w.cls_list, w.w_list, w.cnt_list, proto_queue, M, D, w.bank_n);
-  if ((rc = check_launch("loss_scatter_kernel"))) return rc;
+  split_scatter_kernel<false, true><<<nblk + bank_blocks, 256, 0, stream>>>(
+      (const long long*)labels, keep_mask, probs, HW, nbps, nblk, B, C, ignore_label, w.blk_cnt,
+      w.seg_start, w.pix_list, w.cls_list, w.w_list, w.cnt_list, proto_queue + (size_t)M * D,
+      (C - 1) * M, D, w.bank_n);
+  if ((rc = check_launch("split_scatter_kernel"))) return rc;
   loss_sample_kernel<<<B * C, 256, 0, stream>>>(w.seg_cnt, w.seg_start, w.seg_tidx, w.pix_list,
                                                 w.w_list, w.cnt_list, HW, C, num_anchor,
                                                 (const long long*)keep, keep_rows, seed, w.info);

@@ -259,6 +259,75 @@ def proto_loss(feats, probs, labels, keep_mask, proto_queue, cfg: ProtoLossConfi
     return loss, workspace
 
 
+# --------------------------------------------------------------------- a3 --
+EMA_FLAG_NO_ROWS, EMA_FLAG_BAD_LABEL, EMA_FLAG_OVERFLOW = 1, 8, 16
+ASSIGN_ARGMAX, ASSIGN_GUMBEL_INJECTED, ASSIGN_GUMBEL_DEVICE = 0, 1, 2
+
+
+class EmaAccum(NamedTuple):
+    packed: torch.Tensor        # (C*M*D + C*M,) f32: feature sums then counts
+    proto_target: Optional[torch.Tensor]  # (B*H*W,) f32 or None
+    workspace: torch.Tensor
+
+
+def proto_ema_info(workspace):
+    """(non-empty segments, labelled rows, flags) of the last accumulate.  Synchronises."""
+    host = (ctypes.c_int32 * 4)()
+    check(lib.c3d_proto_ema_info(_p(workspace), ctypes.cast(host, ctypes.c_void_p), _stream()))
+    return int(host[0]), int(host[1]), int(host[2])
+
+
+def proto_ema_accumulate(embedding, label, prototypes, ln_d_w, ln_d_b, ln_c_w, ln_c_b,
+                         ignore_label=0, ln_eps=1e-5, gumbel=None, assign_mode=None, seed=None,
+                         max_rows=None, want_target=False, workspace=None, packed=None) -> EmaAccum:
+    """Per-(class, sub-prototype) feature sums and counts of this rank's scans
+    (salsanext_proto.py:497-510 + :340-377), as the all-reduce payload."""
+    _need_cuda(embedding=embedding, label=label, prototypes=prototypes, ln_d_w=ln_d_w,
+               ln_d_b=ln_d_b, ln_c_w=ln_c_w, ln_c_b=ln_c_b, gumbel=gumbel)
+    if embedding.dtype != torch.float32 or prototypes.dtype != torch.float32:
+        raise ValueError("embedding / prototypes must be float32")
+    if label.dtype != torch.int64:
+        raise ValueError("label must be int64")
+    B, D, H, W = embedding.shape
+    C, M, D2 = prototypes.shape
+    if D2 != D or label.numel() != B * H * W:
+        raise ValueError("shape mismatch between embedding / label / prototypes")
+    if assign_mode is None:
+        assign_mode = ASSIGN_GUMBEL_INJECTED if gumbel is not None else ASSIGN_GUMBEL_DEVICE
+    if max_rows is None:
+        max_rows = min(B * H * W, 1 << 17)
+    if gumbel is not None and (gumbel.dtype != torch.float32 or gumbel.dim() != 2 or gumbel.shape[1] != M):
+        raise ValueError("gumbel must be (rows, M) float32 in (class, pixel) row order")
+    if workspace is None:
+        n = lib.c3d_proto_ema_workspace_bytes(B, C, H * W, D, M, max_rows)
+        if n == 0:
+            raise ValueError("bad EMA shape")
+        workspace = torch.empty((n,), dtype=torch.uint8, device=embedding.device)
+    if packed is None:
+        packed = torch.empty((C * M * D + C * M,), dtype=torch.float32, device=embedding.device)
+    target = torch.empty((B * H * W,), dtype=torch.float32, device=embedding.device) if want_target else None
+    if seed is None:
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if assign_mode == ASSIGN_GUMBEL_DEVICE else 0
+    check(lib.c3d_proto_ema_accumulate(
+        _p(embedding), _p(label), _p(prototypes), _p(ln_d_w), _p(ln_d_b), _p(ln_c_w), _p(ln_c_b),
+        float(ln_eps), B, D, H, W, C, M, int(ignore_label), int(max_rows), _p(gumbel),
+        int(assign_mode), int(seed), _p(workspace), _p(packed), _p(target), _stream()))
+    return EmaAccum(packed, target, workspace)
+
+
+def proto_ema_apply(prototypes, packed, momentum, ignore_label=0, out=None):
+    """normalise sums -> EMA where count != 0 -> renormalise (salsanext_proto.py:379-394)."""
+    _need_cuda(prototypes=prototypes, packed=packed)
+    C, M, D = prototypes.shape
+    if packed.numel() != C * M * D + C * M or packed.dtype != torch.float32:
+        raise ValueError("packed must be (C*M*D + C*M,) float32")
+    if out is None:
+        out = torch.empty_like(prototypes)
+    check(lib.c3d_proto_ema_apply(_p(prototypes), _p(packed), C, M, D, int(ignore_label),
+                                  float(momentum), _p(out), _stream()))
+    return out
+
+
 def launch_count():
     """Kernel launches enqueued by the library since load."""
     return _lib.launch_count()

@@ -149,6 +149,58 @@ int c3d_proto_loss_rows(const void* workspace, int batch, int dim, int hw, int n
                         int sub_protos, int64_t capacity, int32_t* pix, int32_t* cls,
                         int32_t* cnt, void* stream);
 
+/* ---------------------------------------------------------------- a3 ----
+ * EMA prototype update: the pre-step of SalsaNextProto.forward,
+ * pc_processor/models/salsanext_proto.py:497-510, prototype_learning :337-402
+ * (same logic in rangenet_proto.py:460-567, squeezesegv3_Proto.py:253-351),
+ * momentum_update :19-31 and distributed_sinkhorn, models/sinkhorn.py:5-33 --
+ * restricted to the pixels with label != ignore_label, the only rows that
+ * influence the update.
+ *
+ * c3d_proto_ema_accumulate produces the all-reduce payload
+ *     packed = [ C*M*D feature sums | C*M counts ]   (float32)
+ * i.e. per (class, sub-prototype) the sum of the LayerNorm+L2-normalised
+ * features of correctly predicted pixels assigned to it, and how many.  Ranks
+ * sum `packed` (one NCCL all-reduce) and then each calls c3d_proto_ema_apply,
+ * which normalises the sums, applies the EMA where count != 0 and renormalises
+ * every prototype (:379-394).  On one rank this equals the reference.
+ *
+ * assign_mode: 0 = one_hot(argmax Q) (sinkhorn.py:30, deterministic),
+ *              1 = F.gumbel_softmax(hard) with the caller's noise `gumbel`
+ *                  [rows, M], rows in (class, global pixel) order (sinkhorn.py:31),
+ *              2 = the same with Philox noise drawn on the device from `seed`.
+ * ws[0..2] (int32) = {non-empty (class, scan) segments, labelled rows, flags};
+ * flags: 1 no labelled pixel, 8 label outside [0, C), 16 rows > max_rows (the
+ * update is then skipped entirely: packed is all zero).
+ */
+size_t c3d_proto_ema_workspace_bytes(int batch, int n_classes, int hw, int dim, int sub_protos,
+                                     int64_t max_rows);
+
+int c3d_proto_ema_accumulate(
+    const float* embedding,       /* [B, D, H, W] (feat_2d)                      */
+    const int64_t* label,         /* [B, H, W]                                   */
+    const float* prototypes,      /* [C, M, D] current bank (any norm)           */
+    const float* ln_d_w, const float* ln_d_b, /* feat_norm = LayerNorm(D) (:327) */
+    const float* ln_c_w, const float* ln_c_b, /* mask_norm = LayerNorm(C) (:328) */
+    float ln_eps,
+    int batch, int dim, int proj_h, int proj_w, int n_classes, int sub_protos,
+    int ignore_label, int64_t max_rows,
+    const float* gumbel, int assign_mode, uint64_t seed,
+    void* workspace,              /* c3d_proto_ema_workspace_bytes, 256 B aligned */
+    float* packed,                /* [C*M*D + C*M]                               */
+    float* proto_target,          /* [B*H*W] or NULL (:346,390-392)              */
+    void* stream);
+
+int c3d_proto_ema_apply(
+    const float* prototypes_in,   /* [C, M, D]                                   */
+    const float* packed,          /* [C*M*D + C*M], summed over ranks            */
+    int n_classes, int sub_protos, int dim, int ignore_label, double momentum,
+    float* prototypes_out,        /* [C, M, D] (may alias prototypes_in)         */
+    void* stream);
+
+/* Synchronous: copies {segments, labelled rows, flags, 0} to host_info4 (host). */
+int c3d_proto_ema_info(const void* workspace, int32_t* host_info4, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
