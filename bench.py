@@ -1,0 +1,391 @@
+#!/usr/bin/env python
+"""Benchmark of the COARSE3D per-scan hot path on B200 (contract: see DESIGN.md section 6).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A step = one pass of the hot path over one batch of synthetic scans per GPU:
+projection -> prototype loss fwd+bwd -> EMA prototype update (+ all-reduce of the
+packed prototype sums when N > 1) -> KNN vote.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "scans/s (project+proto-loss fwd/bwd+KNN)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--shape", default="kitti")
+    ap.add_argument("--batch-per-gpu", type=int, default=8)   # BASELINE config 2; config 5 uses 64
+    ap.add_argument("--dim", type=int, default=128)
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-scans", type=int, default=2)
+    return ap.parse_args()
+
+
+def workload_config(args, world):
+    from coarse3d_b200 import synth
+    shp = synth.SHAPES[args.shape]
+    return {
+        "workload": "BASELINE.json configs[1]: batch %d %s-shaped scans per GPU (%d points, %dx%d, "
+                    "%d classes, %.2g%% weak labels), D=%d, M=20, A=512; project + proto-loss fwd/bwd "
+                    "+ EMA update + KNN 5x5 k=5" % (args.batch_per_gpu, shp.name, shp.n_points,
+                                                    shp.proj_h, shp.proj_w, shp.n_classes,
+                                                    100 * shp.label_ratio, args.dim),
+        "batch_per_gpu": args.batch_per_gpu, "global_batch": args.batch_per_gpu * world,
+        "points_per_scan": shp.n_points, "proj": [shp.proj_h, shp.proj_w], "feature_dim": args.dim,
+        "parallelism": "scan-sharded x%d, one all-reduce of [K*D|K] prototype sums" % world,
+    }
+
+
+# ------------------------------------------------------------------ clocks --
+class ClockSampler:
+    """Samples SM clock and throttle reasons of one GPU through NVML while the
+    timed region runs (B200_PROFILING.md 'clocks DURING the timed region')."""
+
+    BAD = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown"}
+    NOTE = {0x4: "sw_power_cap", 0x80: "hw_power_brake"}
+
+    def __init__(self, index, period=0.02):
+        self.samples, self.reasons, self.stop_flag, self.ok = [], set(), False, False
+        self.period, self.marks = period, []
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:  # noqa: BLE001
+            self.max = None
+        self.t = threading.Thread(target=self._loop, daemon=True)
+
+    def _loop(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                clk = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                util = nv.nvmlDeviceGetUtilizationRates(self.h).gpu
+                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                self.samples.append((time.perf_counter(), clk, util, rs))
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(self.period)
+
+    def start(self):
+        if self.ok:
+            self.t.start()
+
+    def stop(self):
+        self.stop_flag = True
+        if self.ok:
+            self.t.join(timeout=1)
+
+    def summary(self, t0, t1):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max, "reasons": [], "samples": 0}
+        inside = [s for s in self.samples if t0 <= s[0] <= t1] or \
+                 [s for s in self.samples if s[2] > 0] or self.samples
+        reasons = set()
+        for _, _, _, rs in inside:
+            for bit, name in {**self.BAD, **self.NOTE}.items():
+                if rs & bit:
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median([s[1] for s in inside])), "sm_max_mhz": self.max,
+                "reasons": sorted(reasons), "samples": len(inside),
+                "samples_in_timed_region": len([s for s in self.samples if t0 <= s[0] <= t1])}
+
+
+# ------------------------------------------------------------ CPU baseline --
+def cpu_reference_step(n_scans, shape_name, dim, seed0=1000):
+    """The oracle (CPU restatement of the reference) over `n_scans` scans of the
+    workload: projection, loss fwd+bwd, EMA update, KNN.  Returns seconds."""
+    from coarse3d_b200 import synth
+    from oracle import knn as oknn, projection as oproj, proto_ema as oema, proto_loss as oloss
+    shp = synth.SHAPES[shape_name]
+    H, W, C, M = shp.proj_h, shp.proj_w, shp.n_classes, 20
+    fov = oproj.Fov(fov_up=shp.fov_up, fov_down=shp.fov_down, proj_h=H, proj_w=W)
+    g = torch.Generator().manual_seed(seed0)
+    scans = [synth.make_scan(shp, seed0 + i) for i in range(n_scans)]
+    feats = torch.randn(n_scans, dim, H, W, generator=g)
+    probs = torch.softmax(torch.randn(n_scans, C, H, W, generator=g), 1)
+    argmax = torch.randint(0, C, (n_scans, H, W), generator=g).numpy()
+    queue = torch.nn.functional.normalize(torch.randn(1, C, M, dim, generator=g), dim=-1)
+    ln = [torch.ones(dim), torch.zeros(dim), torch.ones(C), torch.zeros(C)]
+    t0 = time.perf_counter()
+    projs, labels = [], []
+    for pts, _, weak in scans:
+        o = oproj.project(pts, fov)
+        lab = np.zeros((H, W), np.int64)
+        v = o["proj_idx"] >= 0
+        lab[v] = weak[o["proj_idx"][v]]
+        projs.append(o), labels.append(lab)
+    labels = torch.from_numpy(np.stack(labels))
+    f = feats.clone().requires_grad_(True)
+    loss, _, _ = oloss.contrast_mem_loss(f, probs, labels, labels > 0, queue, temperature=0.07,
+                                         num_anchor=512)
+    loss.backward()
+    oema.prototype_learning(feats, labels, queue[0], *ln, C, 0, 0.999, gumbel=None, labelled_only=True)
+    for o, am in zip(projs, argmax):
+        oknn.knn_vote(o["proj_range"], o["uproj_depth"], am, o["uproj_x_idx"], o["uproj_y_idx"],
+                      5, 5, 1.0, 1.0, C)
+    return time.perf_counter() - t0
+
+
+def cpu_baseline(args):
+    torch.set_num_threads(os.cpu_count() or 1)
+    cpu_reference_step(1, args.shape, args.dim)  # warm-up (imports, allocator)
+    n = max(1, args.cpu_scans)
+    dt = cpu_reference_step(n, args.shape, args.dim)
+    return {"value": n / dt, "unit": "scans/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": "%d scans of the same workload through oracle/ (numpy projection 1 thread, torch-CPU "
+                      "loss fwd+bwd / EMA / KNN), %.2f s" % (n, dt)}
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    torch.set_num_threads(os.cpu_count() or 1)
+    n = 1 if args.steps > 20 else 2
+    for _ in range(min(args.warmup, 1)):
+        cpu_reference_step(1, args.shape, args.dim)
+    t_all, done, t_start = 0.0, 0, time.perf_counter()
+    for _ in range(args.steps):
+        t_all += cpu_reference_step(n, args.shape, args.dim)
+        done += 1
+        if time.perf_counter() - t_start > 150:
+            break
+    val = done * n / t_all
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "scans/s", "n_gpus": args.gpus,
+        "steps": done, "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * t_all / done,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": workload_config(args, world),
+        "cpu_baseline": {"value": val, "unit": "scans/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": "%d scan(s) per step through oracle/ on the host cores" % n},
+        "e2e": {"value": val, "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------- main --
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch.distributed as dist
+    from coarse3d_b200 import ops, synth
+    from coarse3d_b200.pipeline import HotPathStep
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: coarse3d_b200 has no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    shp = synth.SHAPES[args.shape]
+    B, K, Wu = args.batch_per_gpu, args.steps, max(args.warmup, 3)
+
+    step = HotPathStep(shp, B, dim=args.dim, seed0=1000 + 10000 * rank, device=dev)
+    sampler = ClockSampler(local)
+    sampler.start()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- warm-up (eager), then graph capture
+    for i in range(Wu):
+        step.run(i, seed=i)
+    barrier()
+    graphed = (not args.no_graph) and step.capture()
+    for i in range(Wu):
+        step.step(i)
+    barrier()
+
+    # ---- timed region: exactly K steps, CUDA events, max over ranks
+    l0 = ops.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    for i in range(K):
+        step.step(i)
+    e1.record()
+    barrier()
+    t1 = time.perf_counter()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    eager_launches_per_step = None
+    if graphed:
+        la = ops.launch_count(); step.run(0); torch.cuda.synchronize(dev)
+        eager_launches_per_step = ops.launch_count() - la
+        launches = eager_launches_per_step * K  # kernels inside the replayed graphs
+    else:
+        launches = ops.launch_count() - l0
+    clocks = sampler.summary(t0, t1)
+
+    # ---- per-kernel device times (eager, events inside the library around each launch)
+    n_prof = min(max(K, 20), 100)
+    with ops.profile("") as prof:
+        for i in range(n_prof):
+            step.run(i, seed=i)
+        torch.cuda.synchronize(dev)
+        per_kernel = {k: {"us": 1e3 * v[0] / max(v[1], 1), "launches_per_step": v[1] / n_prof}
+                      for k, v in prof.all().items()}
+    sampler.stop()
+
+    alg = step.algorithmic_bytes()
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:  # noqa: BLE001
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    dom = "fill_zero_kernel"
+    dom_us = per_kernel.get(dom, {}).get("us")
+    achieved = alg["loss_grad_fill"] / (dom_us * 1e-6) / 1e9 if dom_us else None
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            tj = json.load(open(tpath))
+            if tj.get("batch") == B and tj.get("dim") == args.dim and tj.get("shape") == args.shape:
+                traffic = tj.get("dram_bytes_per_launch")
+        except Exception:  # noqa: BLE001
+            pass
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+                "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650",
+                "algorithmic_bytes_per_launch": alg["loss_grad_fill"],
+                "step_algorithmic_bytes": alg["project"] + alg["knn"] + alg["loss"],
+                "step_frac_of_peak": (alg["project"] + alg["knn"] + alg["loss"]) /
+                                     (ms_total / K * 1e-3) / 1e9 / peak}
+
+    # ---- end to end through the public, reference-shaped API with host buffers
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(args, step, dev, world, min(K, 50))
+
+    value = world * B * K / (ms_total * 1e-3)
+    line = {
+        "metric": METRIC, "value": value, "unit": "scans/s", "n_gpus": world, "steps": K, "warmup": Wu,
+        "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": dict(
+            workload_config(args, world), cuda_graph=bool(graphed),
+            l2="3 rotating input sets (~120 MB re-read inputs each) + a %d MB gradient streamed per "
+               "step; both exceed the 126 MB L2" % (alg["loss_grad_fill"] >> 20)),
+        "roofline": roofline, "clocks": clocks, "gpu_launches": int(launches),
+        "kernels_us": {k: round(v["us"], 2) for k, v in sorted(per_kernel.items())},
+        "e2e": e2e,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(args)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_e2e(args, step, dev, world, K):
+    """Same step through the reference-shaped classes, inputs starting in pinned
+    host memory every step (raw points, CSR offsets, projected weak labels) and
+    results read back to the host (loss scalar, per-point KNN labels).  The CNN
+    activations (features / probabilities / argmax) are produced on the device in
+    the reference too (trainer.py:625-638), so they stay resident."""
+    import torch.distributed as dist
+    from coarse3d_b200.pc_processor.dataset.preprocess import RangeProjection
+    from coarse3d_b200.pc_processor.loss import ContrastMEMLoss
+    from coarse3d_b200.pc_processor.models import PrototypeBank
+    from coarse3d_b200.pc_processor.postproc import KNN
+    shp, B = step.shape, step.batch
+    H, W, C = shp.proj_h, shp.proj_w, shp.n_classes
+    rp = RangeProjection(fov_up=shp.fov_up, fov_down=shp.fov_down, proj_h=H, proj_w=W, device=dev)
+    crit = ContrastMEMLoss(ignore_label=0, temperature=0.07, num_anchor=512)
+    bank = PrototypeBank(C, step.M, step.dim, proto_mom=0.999).to(dev)
+    knn = KNN(dict(knn=5, search=5, sigma=1.0, cutoff=1.0), C)
+    host = []
+    for s in step.sets:
+        host.append(dict(points=torch.from_numpy(s.host_points).pin_memory(),
+                         offsets=torch.from_numpy(s.host_offsets).pin_memory(),
+                         labels=s.labels.cpu().pin_memory(), keep=s.keep_mask.cpu().pin_memory()))
+    d_points = torch.empty_like(step.sets[0].points)
+    d_offsets = torch.empty_like(step.sets[0].offsets)
+    d_labels = torch.empty_like(step.sets[0].labels)
+    d_keep = torch.empty_like(step.sets[0].keep_mask)
+    h_loss = torch.zeros((), dtype=torch.float32).pin_memory()
+    h_knn = torch.zeros((step.n_points,), dtype=torch.int64).pin_memory()
+    h2d = sum(host[0][k].numel() * host[0][k].element_size() for k in host[0])
+    d2h = h_loss.numel() * 4 + h_knn.numel() * 8
+
+    def one(i):
+        s, h = step.sets[i % len(step.sets)], host[i % len(host)]
+        d_points.copy_(h["points"], non_blocking=True)
+        d_offsets.copy_(h["offsets"], non_blocking=True)
+        d_labels.copy_(h["labels"], non_blocking=True)
+        d_keep.copy_(h["keep"], non_blocking=True)
+        pr = rp.doProjectionBatch(d_points, d_offsets, buffers=step.proj_bufs[0])
+        feats = s.feats.requires_grad_(True)
+        feats.grad = None
+        loss = crit(feats=feats, output=s.probs, labels=d_labels, keep_mask=d_keep,
+                    proto_queue=bank.prototypes.detach().unsqueeze(0))
+        loss.backward()
+        bank.update(s.feats.detach(), d_labels)
+        lab = knn.forward_batch(pr.proj_range, pr.uproj_depth, s.argmax, pr.uproj_x_idx,
+                                pr.uproj_y_idx, d_offsets)
+        h_loss.copy_(loss.detach(), non_blocking=True)
+        h_knn.copy_(lab, non_blocking=True)
+
+    for i in range(3):
+        one(i)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        one(i)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    for s in step.sets:
+        s.feats.requires_grad_(False)
+    return {"value": world * B * K / (float(ms.item()) * 1e-3), "unit": "scans/s",
+            "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": K,
+            "ms_per_step": float(ms.item()) / K,
+            "api": "RangeProjection.doProjectionBatch + ContrastMEMLoss()(..).backward() + "
+                   "PrototypeBank.update + KNN.forward_batch",
+            "host_inputs": "points, offsets, projected weak labels, keep mask (pinned); "
+                           "CNN activations resident on device as in the reference"}
+
+
+if __name__ == "__main__":
+    main()

@@ -16,6 +16,17 @@ constexpr int kMaxBatch = 4096;
 void set_error(const char* fmt, ...);
 extern std::atomic<long long> g_launches;
 
+// RAII device timer around one kernel launch; a no-op unless c3d_profile_enable.
+class KernelTimer {
+ public:
+  KernelTimer(const char* name, cudaStream_t stream);
+  ~KernelTimer();
+ private:
+  const char* name_;
+  cudaStream_t stream_;
+  cudaEvent_t a_, b_;
+};
+
 inline int check_launch(const char* what) {
   g_launches.fetch_add(1, std::memory_order_relaxed);
   cudaError_t e = cudaGetLastError();

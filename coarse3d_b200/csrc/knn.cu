@@ -16,13 +16,13 @@
 
 namespace c3d {
 
-template <typename IdxT, int S, int KMAX>
+template <typename IdxT, typename LabT, int S, int KMAX>
 __global__ void __launch_bounds__(256)
-knn_vote_kernel(const float* __restrict__ proj_range, const IdxT* __restrict__ proj_argmax,
+knn_vote_kernel(const float* __restrict__ proj_range, const LabT* __restrict__ proj_argmax,
                 const float* __restrict__ unproj_range, const IdxT* __restrict__ px_,
                 const IdxT* __restrict__ py_, const int32_t* __restrict__ offsets, int batch,
                 int total, int H, int W, int knn, float cutoff, int nclasses,
-                const float* __restrict__ inv_gauss, IdxT* __restrict__ out) {
+                const float* __restrict__ inv_gauss, LabT* __restrict__ out) {
   constexpr int S2 = S * S;
   constexpr int PAD = (S - 1) / 2;
   extern __shared__ int32_t s_off[];
@@ -57,7 +57,7 @@ knn_vote_kernel(const float* __restrict__ proj_range, const IdxT* __restrict__ p
     int sel_cls[KMAX];
     float prev_d = -CUDART_INF_F;
     int prev_s = -1;
-    const IdxT* cimg = proj_argmax + (size_t)b * HW;
+    const LabT* cimg = proj_argmax + (size_t)b * HW;
 #pragma unroll
     for (int j = 0; j < KMAX; ++j) {
       sel_cls[j] = 0;
@@ -93,11 +93,11 @@ knn_vote_kernel(const float* __restrict__ proj_range, const IdxT* __restrict__ p
         if (n > best_n || (n == best_n && c < best_c)) { best_n = n; best_c = c; }
       }
     }
-    out[g] = (IdxT)best_c;
+    out[g] = (LabT)best_c;
   }
 }
 
-template <typename IdxT>
+template <typename IdxT, typename LabT>
 int launch_knn(const float* proj_range, const void* proj_argmax, const float* unproj_range,
                const void* px, const void* py, const int32_t* offsets, int batch, int total,
                int H, int W, int knn, int search, float cutoff, int nclasses,
@@ -105,10 +105,11 @@ int launch_knn(const float* proj_range, const void* proj_argmax, const float* un
   const int threads = 256;
   const int grid = wave_grid(total, threads, 8);
   const size_t smem = (size_t)(batch + 1) * sizeof(int32_t);
+  KernelTimer timer("knn_vote_kernel", stream);
 #define LAUNCH_KNN(S_, K_)                                                                  \
-  knn_vote_kernel<IdxT, S_, K_><<<grid, threads, smem, stream>>>(                           \
-      proj_range, (const IdxT*)proj_argmax, unproj_range, (const IdxT*)px, (const IdxT*)py, \
-      offsets, batch, total, H, W, knn, cutoff, nclasses, inv_gauss, (IdxT*)out)
+  knn_vote_kernel<IdxT, LabT, S_, K_><<<grid, threads, smem, stream>>>(                     \
+      proj_range, (const LabT*)proj_argmax, unproj_range, (const IdxT*)px, (const IdxT*)py, \
+      offsets, batch, total, H, W, knn, cutoff, nclasses, inv_gauss, (LabT*)out)
   if (search == 3) { LAUNCH_KNN(3, 9); }
   else if (search == 5 && knn <= 8) { LAUNCH_KNN(5, 8); }
   else if (search == 5) { LAUNCH_KNN(5, 25); }
@@ -131,8 +132,8 @@ extern "C" int c3d_knn_batch(const float* proj_range, const void* proj_argmax,
                              const float* unproj_range, const void* px, const void* py,
                              const int32_t* offsets, int batch, int64_t total_points, int proj_h,
                              int proj_w, int knn, int search, float cutoff, int nclasses,
-                             const float* inv_gauss, int index_is_i64, void* out_labels,
-                             void* stream_) {
+                             const float* inv_gauss, int pxy_is_i64, int label_is_i64,
+                             void* out_labels, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   C3D_REQUIRE(search % 2 == 1, "Nearest neighbor kernel must be odd number");  // knn.py:72-73
   C3D_REQUIRE(batch > 0 && batch <= kMaxBatch, "batch must be in [1, %d]", kMaxBatch);
@@ -143,11 +144,11 @@ extern "C" int c3d_knn_batch(const float* proj_range, const void* proj_argmax,
   C3D_REQUIRE(proj_range && proj_argmax && offsets && inv_gauss, "null pointer argument");
   if (total_points == 0) return C3D_OK;
   C3D_REQUIRE(unproj_range && px && py && out_labels, "null per-point pointer");
-  if (index_is_i64)
-    return launch_knn<long long>(proj_range, proj_argmax, unproj_range, px, py, offsets, batch,
-                                 (int)total_points, proj_h, proj_w, knn, search, cutoff, nclasses,
-                                 inv_gauss, out_labels, stream);
-  return launch_knn<int>(proj_range, proj_argmax, unproj_range, px, py, offsets, batch,
-                         (int)total_points, proj_h, proj_w, knn, search, cutoff, nclasses,
-                         inv_gauss, out_labels, stream);
+#define KNN_ARGS proj_range, proj_argmax, unproj_range, px, py, offsets, batch, (int)total_points, \
+                 proj_h, proj_w, knn, search, cutoff, nclasses, inv_gauss, out_labels, stream
+  if (pxy_is_i64 && label_is_i64) return launch_knn<long long, long long>(KNN_ARGS);
+  if (pxy_is_i64) return launch_knn<long long, int>(KNN_ARGS);
+  if (label_is_i64) return launch_knn<int, long long>(KNN_ARGS);
+  return launch_knn<int, int>(KNN_ARGS);
+#undef KNN_ARGS
 }

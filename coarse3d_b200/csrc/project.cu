@@ -183,7 +183,10 @@ extern "C" int c3d_project_batch(
 
   const long long total_px = (long long)batch * proj_h * proj_w;
   auto* zbuf = reinterpret_cast<unsigned long long*>(workspace);
-  C3D_CUDA(cudaMemsetAsync(zbuf, 0xFF, (size_t)total_px * sizeof(unsigned long long), stream));
+  {
+    KernelTimer kt__("zbuf_memset", stream);
+    C3D_CUDA(cudaMemsetAsync(zbuf, 0xFF, (size_t)total_px * sizeof(unsigned long long), stream));
+  }
 
   const bool c4 = (c_in == 4) && ((reinterpret_cast<uintptr_t>(points) & 15) == 0) &&
                   ((reinterpret_cast<uintptr_t>(proj_pointcloud) & 15) == 0);
@@ -197,14 +200,18 @@ extern "C" int c3d_project_batch(
   project_points_kernel<HY, C4><<<grid, threads, smem, stream>>>(                           \
       points, c_in, offsets, batch, (int)total_points, depth_override, p, uproj_x_idx,      \
       uproj_y_idx, uproj_depth, zbuf, status_flags)
-    if (hybrid) { if (c4) LAUNCH_PP(true, true); else LAUNCH_PP(true, false); }
-    else        { if (c4) LAUNCH_PP(false, true); else LAUNCH_PP(false, false); }
+    {
+      KernelTimer kt__("project_points_kernel", stream);
+      if (hybrid) { if (c4) LAUNCH_PP(true, true); else LAUNCH_PP(true, false); }
+      else        { if (c4) LAUNCH_PP(false, true); else LAUNCH_PP(false, false); }
+    }
 #undef LAUNCH_PP
     int rc = check_launch("project_points_kernel");
     if (rc) return rc;
   }
   {
     int grid = wave_grid(total_px, threads, 8);
+    KernelTimer kt__("resolve_pixels_kernel", stream);
     if (c4)
       resolve_pixels_kernel<true><<<grid, threads, 0, stream>>>(
           points, c_in, offsets, proj_h * proj_w, total_px, zbuf, proj_range, proj_pointcloud,

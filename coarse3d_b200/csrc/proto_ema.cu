@@ -436,15 +436,15 @@ extern "C" int c3d_proto_ema_accumulate(
   C3D_CUDA(cudaMemsetAsync(w.info, 0, 8 * 4, stream));
   if (proto_target) C3D_CUDA(cudaMemsetAsync(proto_target, 0, (size_t)B * HW * 4, stream));
   int rc;
-  split_count_kernel<<<nblk, 256, 0, stream>>>((const long long*)label, nullptr, HW, nbps, C,
-                                               ignore_label, w.blk_cnt, w.info);
+  { KernelTimer kt__("split_count_kernel", stream); split_count_kernel<<<nblk, 256, 0, stream>>>((const long long*)label, nullptr, HW, nbps, C,
+                                               ignore_label, w.blk_cnt, w.info); }
   if ((rc = check_launch("split_count_kernel"))) return rc;
-  split_scan_kernel<true><<<B, 1024, 0, stream>>>(w.blk_cnt, nbps, B, C, w.seg_cnt, w.seg_start,
-                                                  w.seg_tidx, w.info);
+  { KernelTimer kt__("split_scan_kernel", stream); split_scan_kernel<true><<<B, 1024, 0, stream>>>(w.blk_cnt, nbps, B, C, w.seg_cnt, w.seg_start,
+                                                  w.seg_tidx, w.info); }
   if ((rc = check_launch("split_scan_kernel"))) return rc;
-  split_scatter_kernel<true, false><<<nblk + 16, 256, 0, stream>>>(
+  { KernelTimer kt__("split_scatter_kernel", stream); split_scatter_kernel<true, false><<<nblk + 16, 256, 0, stream>>>(
       (const long long*)label, nullptr, nullptr, HW, nbps, nblk, B, C, ignore_label, w.blk_cnt,
-      w.seg_start, w.pix_list, w.cls_list, nullptr, nullptr, prototypes, K, D, w.bank_n);
+      w.seg_start, w.pix_list, w.cls_list, nullptr, nullptr, prototypes, K, D, w.bank_n); }
   if ((rc = check_launch("split_scatter_kernel"))) return rc;
 
   EmaRowsParams p{};
@@ -455,18 +455,18 @@ extern "C" int c3d_proto_ema_accumulate(
   p.max_rows = (int)max_rows; p.eps = ln_eps;
   C3D_CUDA(cudaFuncSetAttribute(ema_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)smem));
-  ema_rows_kernel<<<kNumSMs, kEmaWarps * 32, smem, stream>>>(p);
+  { KernelTimer kt__("ema_rows_kernel", stream); ema_rows_kernel<<<kNumSMs, kEmaWarps * 32, smem, stream>>>(p); }
   if ((rc = check_launch("ema_rows_kernel"))) return rc;
-  ema_sinkhorn_kernel<<<C, 256, 0, stream>>>(w.seg_cnt, w.seg_start, w.pix_list, w.info, B, M,
+  { KernelTimer kt__("ema_sinkhorn_kernel", stream); ema_sinkhorn_kernel<<<C, 256, 0, stream>>>(w.seg_cnt, w.seg_start, w.pix_list, w.info, B, M,
                                              ignore_label, (int)max_rows, w.simq, w.sub, gumbel,
-                                             assign_mode, seed, proto_target);
+                                             assign_mode, seed, proto_target); }
   if ((rc = check_launch("ema_sinkhorn_kernel"))) return rc;
   if (seg_smem > 48 * 1024)
     C3D_CUDA(cudaFuncSetAttribute(ema_segsum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)seg_smem));
-  ema_segsum_kernel<<<C, 256, seg_smem, stream>>>(w.seg_cnt, w.seg_start, w.info, B, M, D, K,
+  { KernelTimer kt__("ema_segsum_kernel", stream); ema_segsum_kernel<<<C, 256, seg_smem, stream>>>(w.seg_cnt, w.seg_start, w.info, B, M, D, K,
                                                   ignore_label, (int)max_rows, w.feat, w.maskv,
-                                                  w.sub, packed);
+                                                  w.sub, packed); }
   return check_launch("ema_segsum_kernel");
 }
 
@@ -479,9 +479,9 @@ extern "C" int c3d_proto_ema_apply(const float* prototypes_in, const float* pack
   const int K = n_classes * sub_protos;
   // weak-scalar rounding of the reference: momentum and (1 - momentum) are Python
   // floats multiplied into float32 tensors (salsanext_proto.py:20)
-  ema_apply_kernel<<<(K + 7) / 8, 256, 0, stream>>>(prototypes_in, packed, n_classes, sub_protos,
+  { KernelTimer kt__("ema_apply_kernel", stream); ema_apply_kernel<<<(K + 7) / 8, 256, 0, stream>>>(prototypes_in, packed, n_classes, sub_protos,
                                                     dim, ignore_label, (float)momentum,
-                                                    (float)(1.0 - momentum), prototypes_out);
+                                                    (float)(1.0 - momentum), prototypes_out); }
   return check_launch("ema_apply_kernel");
 }
 

@@ -438,22 +438,22 @@ extern "C" int c3d_proto_loss_forward(
               "bank does not fit shared memory tiling (D=%d, Kc=%d)", D, Kc);
 
   C3D_CUDA(cudaMemsetAsync(w.info, 0, 8 * 4, stream));
-  split_count_kernel<<<nblk, 256, 0, stream>>>((const long long*)labels, keep_mask, HW, nbps, C,
-                                              ignore_label, w.blk_cnt, w.info);
+  { KernelTimer kt__("split_count_kernel", stream); split_count_kernel<<<nblk, 256, 0, stream>>>((const long long*)labels, keep_mask, HW, nbps, C,
+                                              ignore_label, w.blk_cnt, w.info); }
   int rc = check_launch("split_count_kernel");
   if (rc) return rc;
-  split_scan_kernel<false><<<B, 1024, 0, stream>>>(w.blk_cnt, nbps, B, C, w.seg_cnt, w.seg_start,
-                                           w.seg_tidx, w.info);
+  { KernelTimer kt__("split_scan_kernel", stream); split_scan_kernel<false><<<B, 1024, 0, stream>>>(w.blk_cnt, nbps, B, C, w.seg_cnt, w.seg_start,
+                                           w.seg_tidx, w.info); }
   if ((rc = check_launch("split_scan_kernel"))) return rc;
   const int bank_blocks = 16;
-  split_scatter_kernel<false, true><<<nblk + bank_blocks, 256, 0, stream>>>(
+  { KernelTimer kt__("split_scatter_kernel", stream); split_scatter_kernel<false, true><<<nblk + bank_blocks, 256, 0, stream>>>(
       (const long long*)labels, keep_mask, probs, HW, nbps, nblk, B, C, ignore_label, w.blk_cnt,
       w.seg_start, w.pix_list, w.cls_list, w.w_list, w.cnt_list, proto_queue + (size_t)M * D,
-      (C - 1) * M, D, w.bank_n);
+      (C - 1) * M, D, w.bank_n); }
   if ((rc = check_launch("split_scatter_kernel"))) return rc;
-  loss_sample_kernel<<<B * C, 256, 0, stream>>>(w.seg_cnt, w.seg_start, w.seg_tidx, w.pix_list,
+  { KernelTimer kt__("loss_sample_kernel", stream); loss_sample_kernel<<<B * C, 256, 0, stream>>>(w.seg_cnt, w.seg_start, w.seg_tidx, w.pix_list,
                                                 w.w_list, w.cnt_list, HW, C, num_anchor,
-                                                (const long long*)keep, keep_rows, seed, w.info);
+                                                (const long long*)keep, keep_rows, seed, w.info); }
   if ((rc = check_launch("loss_sample_kernel"))) return rc;
 
   RowsParams p{};
@@ -463,7 +463,7 @@ extern "C" int c3d_proto_loss_forward(
   p.n_tiles = n_tiles; p.temperature = temperature; p.base_temperature = base_temperature;
   C3D_CUDA(cudaFuncSetAttribute(loss_rows_kernel<false>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  loss_rows_kernel<false><<<kNumSMs, kRowWarps * 32, smem, stream>>>(p);
+  { KernelTimer kt__("loss_rows_fwd_kernel", stream); loss_rows_kernel<false><<<kNumSMs, kRowWarps * 32, smem, stream>>>(p); }
   return check_launch("loss_rows_kernel<fwd>");
 }
 
@@ -492,8 +492,8 @@ extern "C" int c3d_proto_loss_backward(
     long long blocks = (long long)((n4 + threads - 1) / threads);
     const int wave = kNumSMs * 4;
     const int grid = (int)(blocks < wave ? (blocks > 0 ? blocks : 1) : wave);
-    fill_zero_kernel<<<grid, threads, 0, stream>>>(reinterpret_cast<float4*>(grad_feats), n4,
-                                                   grad_feats + n4 * 4, (int)(n - n4 * 4));
+    { KernelTimer kt__("fill_zero_kernel", stream); fill_zero_kernel<<<grid, threads, 0, stream>>>(reinterpret_cast<float4*>(grad_feats), n4,
+                                                   grad_feats + n4 * 4, (int)(n - n4 * 4)); }
     int rc = check_launch("fill_zero_kernel");
     if (rc) return rc;
   }
@@ -504,7 +504,7 @@ extern "C" int c3d_proto_loss_backward(
   p.n_tiles = n_tiles; p.temperature = temperature; p.base_temperature = base_temperature;
   C3D_CUDA(cudaFuncSetAttribute(loss_rows_kernel<true>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  loss_rows_kernel<true><<<kNumSMs, kRowWarps * 32, smem, stream>>>(p);
+  { KernelTimer kt__("loss_rows_bwd_kernel", stream); loss_rows_kernel<true><<<kNumSMs, kRowWarps * 32, smem, stream>>>(p); }
   return check_launch("loss_rows_kernel<bwd>");
 }
 

@@ -130,17 +130,19 @@ def knn_batch(proj_range, proj_argmax, unproj_range, px, py, offsets, knn, searc
               cutoff, nclasses, inv_gauss=None, out=None):
     """KNN.forward for a CSR batch (knn.py:54-142).
 
-    proj_range (B,H,W) f32; proj_argmax (B,H,W), px, py (sum N,) all int64 (the
-    reference's dtypes) or all int32; offsets (B+1,) i32.  Returns (sum N,)
-    labels of the index dtype.
+    proj_range (B,H,W) f32; px, py (sum N,) int64 (the reference's dtype) or
+    int32 (project_batch's output); proj_argmax (B,H,W) int64 or int32; offsets
+    (B+1,) i32.  Returns (sum N,) labels with proj_argmax's dtype.
     """
     if search % 2 == 0:
         raise ValueError("Nearest neighbor kernel must be odd number")  # knn.py:72-73
     _need_cuda(proj_range=proj_range, proj_argmax=proj_argmax, unproj_range=unproj_range,
                px=px, py=py, offsets=offsets)
-    idt = px.dtype
-    if idt not in (torch.int64, torch.int32) or py.dtype != idt or proj_argmax.dtype != idt:
-        raise ValueError("px, py, proj_argmax must share dtype int64 or int32")
+    idt, ldt = px.dtype, proj_argmax.dtype
+    if idt not in (torch.int64, torch.int32) or py.dtype != idt:
+        raise ValueError("px, py must share dtype int64 or int32")
+    if ldt not in (torch.int64, torch.int32):
+        raise ValueError("proj_argmax must be int64 or int32")
     if proj_range.dtype != torch.float32 or unproj_range.dtype != torch.float32:
         raise ValueError("ranges must be float32")
     if proj_range.dim() != 3 or proj_argmax.shape != proj_range.shape:
@@ -152,11 +154,11 @@ def knn_batch(proj_range, proj_argmax, unproj_range, px, py, offsets, knn, searc
     if inv_gauss is None:
         inv_gauss = (1 - gaussian_kernel(search, sigma)).reshape(-1).to(proj_range.device)
     if out is None:
-        out = torch.empty((total,), dtype=idt, device=proj_range.device)
+        out = torch.empty((total,), dtype=ldt, device=proj_range.device)
     check(lib.c3d_knn_batch(
         _p(proj_range), _p(proj_argmax), _p(unproj_range), _p(px), _p(py), _p(offsets), B, total,
         H, W, int(knn), int(search), float(cutoff), int(nclasses), _p(inv_gauss),
-        1 if idt == torch.int64 else 0, _p(out), _stream()))
+        1 if idt == torch.int64 else 0, 1 if ldt == torch.int64 else 0, _p(out), _stream()))
     return out
 
 
@@ -197,32 +199,43 @@ def proto_loss_rows(workspace, batch, dim, hw, n_classes, sub_protos):
     return pix[:n_lab], cls[:n_lab], cnt[:n_lab]
 
 
+def proto_loss_forward_raw(feats, probs, labels, keep_mask, queue, cfg, keep, seed, workspace, loss_out):
+    """c3d_proto_loss_forward on pre-validated device tensors (no autograd, no allocation)."""
+    B, D, H, W = feats.shape
+    C, M, _ = queue.shape
+    check(lib.c3d_proto_loss_forward(
+        _p(feats), _p(probs), _p(labels), _p(keep_mask), _p(queue), B, D, H, W, C, M,
+        int(cfg.ignore_label), float(cfg.temperature), float(cfg.base_temperature),
+        int(cfg.num_anchor), _p(keep), 0 if keep is None else keep.shape[0], int(seed),
+        _p(workspace), _p(loss_out), _stream()))
+    return loss_out
+
+
+def proto_loss_backward_raw(feats, cfg, n_classes, sub_protos, workspace, grad_out, grad_feats):
+    """c3d_proto_loss_backward: writes the dense (B,D,H,W) gradient into grad_feats."""
+    B, D, H, W = feats.shape
+    check(lib.c3d_proto_loss_backward(
+        _p(feats), B, D, H, W, n_classes, sub_protos, float(cfg.temperature),
+        float(cfg.base_temperature), int(cfg.num_anchor), _p(workspace), _p(grad_out),
+        _p(grad_feats), _stream()))
+    return grad_feats
+
+
 class _ProtoLossFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, feats, probs, labels, keep_mask, queue, cfg, keep, seed, workspace):
-        B, D, H, W = feats.shape
-        C, M, _ = queue.shape
         loss = torch.empty((), dtype=torch.float32, device=feats.device)
-        check(lib.c3d_proto_loss_forward(
-            _p(feats), _p(probs), _p(labels), _p(keep_mask), _p(queue), B, D, H, W, C, M,
-            int(cfg.ignore_label), float(cfg.temperature), float(cfg.base_temperature),
-            int(cfg.num_anchor), _p(keep), 0 if keep is None else keep.shape[0], int(seed),
-            _p(workspace), _p(loss), _stream()))
+        proto_loss_forward_raw(feats, probs, labels, keep_mask, queue, cfg, keep, seed, workspace, loss)
         ctx.save_for_backward(feats)
-        ctx.workspace, ctx.cfg, ctx.cm = workspace, cfg, (C, M)
+        ctx.workspace, ctx.cfg, ctx.cm = workspace, cfg, (queue.shape[0], queue.shape[1])
         return loss
 
     @staticmethod
     def backward(ctx, grad_out):
         (feats,) = ctx.saved_tensors
-        B, D, H, W = feats.shape
         C, M = ctx.cm
-        cfg = ctx.cfg
-        grad_out = grad_out.contiguous().float()
         grad = torch.empty_like(feats)
-        check(lib.c3d_proto_loss_backward(
-            _p(feats), B, D, H, W, C, M, float(cfg.temperature), float(cfg.base_temperature),
-            int(cfg.num_anchor), _p(ctx.workspace), _p(grad_out), _p(grad), _stream()))
+        proto_loss_backward_raw(feats, ctx.cfg, C, M, ctx.workspace, grad_out.contiguous().float(), grad)
         return grad, None, None, None, None, None, None, None, None
 
 
@@ -331,3 +344,40 @@ def proto_ema_apply(prototypes, packed, momentum, ignore_label=0, out=None):
 def launch_count():
     """Kernel launches enqueued by the library since load."""
     return _lib.launch_count()
+
+
+class profile:
+    """Per-kernel device timing (CUDA events around each launch inside the library).
+
+        with ops.profile("fill_zero_kernel") as prof: ...steps...
+        ms, n = prof.read("fill_zero_kernel")
+    """
+
+    def __init__(self, kernel_name=""):
+        self.kernel_name = kernel_name
+
+    def __enter__(self):
+        check(lib.c3d_profile_reset())
+        check(lib.c3d_profile_enable(self.kernel_name.encode()))
+        return self
+
+    def __exit__(self, *exc):
+        check(lib.c3d_profile_enable(None))
+        return False
+
+    @staticmethod
+    def read(kernel_name=""):
+        ms, n = ctypes.c_double(0), ctypes.c_longlong(0)
+        check(lib.c3d_profile_read(kernel_name.encode(), ctypes.cast(ctypes.byref(ms), ctypes.c_void_p),
+                                   ctypes.cast(ctypes.byref(n), ctypes.c_void_p)))
+        return ms.value, n.value
+
+    @staticmethod
+    def names():
+        buf = ctypes.create_string_buffer(4096)
+        check(lib.c3d_profile_names(ctypes.cast(buf, ctypes.c_void_p), 4096))
+        return [s for s in buf.value.decode().split(",") if s]
+
+    @staticmethod
+    def all():
+        return {n: profile.read(n) for n in profile.names()}

@@ -1,0 +1,151 @@
+"""The per-scan hot path as one device-resident step, eager or CUDA-graph captured.
+
+A step is what BASELINE.json's metric counts: for one batch of scans,
+  projection  ->  prototype loss forward + backward  ->  EMA prototype update
+  (one all-reduce of the packed sums when world_size > 1)  ->  KNN vote.
+The range-image CNN between projection and loss is out of scope (SURVEY.md 2,
+row 9), so its outputs (features, softmax probabilities, argmax image) are
+synthetic resident tensors, exactly as BASELINE.json's configs prescribe.
+"""
+import numpy as np
+import torch
+
+from . import distributed, ops, synth
+
+
+class StepInputs:
+    """One set of resident inputs for a batch of `batch` scans of `shape`."""
+
+    def __init__(self, shape: synth.ScanShape, batch, dim, sub_protos, seed0, device,
+                 feats=None, share_probs=None):
+        self.shape, self.batch, self.dim = shape, batch, dim
+        pts, offs, _full, weak = synth.make_batch(shape, batch, seed0)
+        H, W, C = shape.proj_h, shape.proj_w, shape.n_classes
+        self.host_points, self.host_offsets, self.host_weak = pts, offs, weak
+        self.points = torch.from_numpy(pts).to(device)
+        self.offsets = torch.from_numpy(offs).to(device)
+        self.weak = torch.from_numpy(weak).to(device)
+        self.n_points = int(pts.shape[0])
+        g = torch.Generator(device=device).manual_seed(seed0)
+        self.feats = feats if feats is not None else \
+            torch.randn((batch, dim, H, W), device=device, generator=g)
+        if share_probs is not None:
+            self.probs = share_probs
+        else:
+            self.probs = torch.softmax(torch.randn((batch, C, H, W), device=device, generator=g), 1)
+        self.argmax = torch.randint(0, C, (batch, H, W), device=device, generator=g)  # int64
+        self.labels = None      # (B,H,W) int64: weak labels of the winning points
+        self.keep_mask = None   # (B,H,W) bool
+
+    def derive_labels(self, proj):
+        """Projected weak-label image, like the reference's loader builds it
+        (wss_sem_kitti_loader.py:124-132): label of the point that won the pixel."""
+        B = self.batch
+        gidx = proj.proj_idx.long() + self.offsets[:-1].long().view(B, 1, 1)
+        lab = torch.zeros_like(gidx)
+        valid = proj.proj_idx >= 0
+        lab[valid] = self.weak[gidx[valid]]
+        self.labels = lab.contiguous()
+        self.keep_mask = (lab > 0).contiguous()
+
+
+class HotPathStep:
+    """Pre-allocated, allocation-free step over rotating input sets."""
+
+    def __init__(self, shape, batch, dim=128, sub_protos=20, num_anchor=512, temperature=0.07,
+                 momentum=0.999, n_sets=3, seed0=1000, device="cuda", group=None,
+                 knn=(5, 5, 1.0, 1.0)):
+        self.shape, self.batch, self.dim, self.M = shape, batch, dim, sub_protos
+        self.device, self.group = torch.device(device), group
+        self.knn_k, self.knn_s, self.knn_sigma, self.knn_cutoff = knn
+        H, W, C = shape.proj_h, shape.proj_w, shape.n_classes
+        self.fov = ops.Fov.from_degrees(shape.fov_up, shape.fov_down)
+        self.cfg = ops.ProtoLossConfig(0, temperature, 0.07, num_anchor)
+        self.momentum = momentum
+        self.sets = []
+        for i in range(n_sets):
+            self.sets.append(StepInputs(shape, batch, dim, sub_protos, seed0 + 100 * i, self.device))
+        n = self.sets[0].n_points
+        assert all(s.n_points == n for s in self.sets)
+        self.n_points = n
+        self.proj_bufs = [ops.ProjectionBuffers(batch, n, 4, H, W, self.device) for _ in self.sets]
+        for s, b in zip(self.sets, self.proj_bufs):
+            s.derive_labels(ops.project_batch(s.points, s.offsets, self.fov, H, W, buffers=b))
+        g = torch.Generator(device=self.device).manual_seed(seed0 + 7)
+        self.protos = torch.nn.functional.normalize(
+            torch.randn((C, sub_protos, dim), device=self.device, generator=g), dim=-1)
+        self.protos_next = torch.empty_like(self.protos)
+        self.ln_d = (torch.ones(dim, device=self.device), torch.zeros(dim, device=self.device))
+        self.ln_c = (torch.ones(C, device=self.device), torch.zeros(C, device=self.device))
+        self.loss_ws = ops.proto_loss_workspace(batch, C, H * W, dim, sub_protos, self.device)
+        self.loss = torch.zeros((), device=self.device)
+        self.grad_out = torch.ones((), device=self.device)
+        self.grad = torch.empty((batch, dim, H, W), device=self.device)
+        self.max_rows = min(batch * H * W, 1 << 17)
+        nws = ops.lib.c3d_proto_ema_workspace_bytes(batch, C, H * W, dim, sub_protos, self.max_rows)
+        self.ema_ws = torch.empty((nws,), dtype=torch.uint8, device=self.device)
+        K = C * sub_protos
+        self.packed = torch.empty((K * dim + K,), device=self.device)
+        self.knn_out = torch.empty((n,), dtype=torch.int64, device=self.device)
+        self.inv_gauss = (1 - ops.gaussian_kernel(self.knn_s, self.knn_sigma)).reshape(-1).to(self.device)
+        self.graphs = None
+        torch.cuda.synchronize(self.device)
+
+    # bytes the reference dtypes move per step
+    def algorithmic_bytes(self):
+        HW = self.shape.proj_h * self.shape.proj_w
+        B, N, D = self.batch, self.n_points, self.dim
+        return {
+            "project": 28 * N + 28 * B * HW,
+            "knn": 12 * B * HW + 28 * N,
+            "loss": (4 * D + 9) * B * HW,
+            "loss_grad_fill": 4 * D * B * HW,
+        }
+
+    def run(self, i, seed=0):
+        """Enqueue one step on the current stream (no allocation, no sync)."""
+        s, b = self.sets[i % len(self.sets)], self.proj_bufs[i % len(self.sets)]
+        H, W, C = self.shape.proj_h, self.shape.proj_w, self.shape.n_classes
+        pr = ops.project_batch(s.points, s.offsets, self.fov, H, W, buffers=b)
+        ops.proto_loss_forward_raw(s.feats, s.probs, s.labels, s.keep_mask, self.protos, self.cfg,
+                                   None, seed, self.loss_ws, self.loss)
+        ops.proto_loss_backward_raw(s.feats, self.cfg, C, self.M, self.loss_ws, self.grad_out, self.grad)
+        distributed.prototype_update(
+            s.feats, s.labels, self.protos, *self.ln_d, *self.ln_c, self.momentum,
+            assign_mode=ops.ASSIGN_GUMBEL_DEVICE, seed=seed, max_rows=self.max_rows, group=self.group,
+            workspace=self.ema_ws, packed=self.packed, out=self.protos_next)
+        ops.knn_batch(pr.proj_range, s.argmax, pr.uproj_depth, pr.uproj_x_idx, pr.uproj_y_idx,
+                      s.offsets, self.knn_k, self.knn_s, self.knn_sigma, self.knn_cutoff, C,
+                      inv_gauss=self.inv_gauss, out=self.knn_out)
+        return pr
+
+    def capture(self):
+        """Capture one CUDA graph per input set.  Returns False if capture fails
+        (e.g. a collective that cannot be captured); the step then stays eager."""
+        try:
+            graphs = []
+            side = torch.cuda.Stream(self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):
+                for i in range(len(self.sets)):
+                    self.run(i)  # warm-up on the capture stream
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            torch.cuda.synchronize(self.device)
+            for i in range(len(self.sets)):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self.run(i)
+                graphs.append(g)
+            self.graphs = graphs
+            return True
+        except Exception as e:  # noqa: BLE001
+            self.graphs = None
+            self.capture_error = repr(e)
+            torch.cuda.synchronize(self.device)
+            return False
+
+    def step(self, i):
+        if self.graphs is not None:
+            self.graphs[i % len(self.graphs)].replay()
+        else:
+            self.run(i, seed=i)

@@ -39,6 +39,18 @@ const char* c3d_last_error(void);
 /* Number of kernel launches enqueued by this library since load (all threads). */
 long long c3d_launch_count(void);
 
+/* Optional per-kernel device timing: CUDA events recorded on the launching
+ * stream right before and after each kernel launch.  kernel_name "" = every
+ * kernel, a kernel's name = only that kernel, NULL = off (default).  Not
+ * usable during CUDA-graph capture.  c3d_profile_read waits for the recorded
+ * events and returns the summed elapsed ms and the number of launches of
+ * `kernel_name` ("" = all); c3d_profile_names lists the recorded names,
+ * comma separated; c3d_profile_reset drops the records. */
+int c3d_profile_enable(const char* kernel_name);
+int c3d_profile_read(const char* kernel_name, double* total_ms, long long* count);
+int c3d_profile_names(char* buf, int buf_len);
+int c3d_profile_reset(void);
+
 /* ---------------------------------------------------------------- a1 ----
  * RangeProjection.doProjection, pc_processor/dataset/preprocess/projection.py:43-115,
  * for a CSR batch of scans.
@@ -79,8 +91,9 @@ int c3d_project_batch(
  * inv_gauss is (1 - get_gaussian_kernel(search, sigma)) flattened row-major
  * (knn.py:11-33,102-104), computed by the host with the reference's formula.
  * Tie rule: k smallest by (distance, window slot); vote argmax = first maximum.
- * index_is_i64 selects the dtype of px / py / proj_argmax / out
- * (int64 = the reference's dtypes, int32 = this library's projection outputs).
+ * pxy_is_i64 selects the dtype of px / py, label_is_i64 that of proj_argmax /
+ * out_labels (int64 = the reference's dtypes, int32 = this library's
+ * projection outputs).
  */
 int c3d_knn_batch(
     const float* proj_range,      /* [batch, H, W]                               */
@@ -92,7 +105,7 @@ int c3d_knn_batch(
     int proj_h, int proj_w,
     int knn, int search, float cutoff, int nclasses,
     const float* inv_gauss,       /* [search*search]                             */
-    int index_is_i64,
+    int pxy_is_i64, int label_is_i64,
     void* out_labels,             /* [total_points] i64 or i32, in [1, C-1]      */
     void* stream);
 
