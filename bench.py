@@ -34,6 +34,7 @@ def parse():
     ap.add_argument("--batch-per-gpu", type=int, default=8)   # BASELINE config 2; config 5 uses 64
     ap.add_argument("--dim", type=int, default=128)
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--serial", action="store_true", help="one stream, no overlap of the four chains")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-scans", type=int, default=2)
@@ -208,7 +209,8 @@ def main():
     shp = synth.SHAPES[args.shape]
     B, K, Wu = args.batch_per_gpu, args.steps, max(args.warmup, 3)
 
-    step = HotPathStep(shp, B, dim=args.dim, seed0=1000 + 10000 * rank, device=dev)
+    step = HotPathStep(shp, B, dim=args.dim, seed0=1000 + 10000 * rank, device=dev,
+                       concurrent=not args.serial)
     sampler = ClockSampler(local)
     sampler.start()
 
@@ -252,6 +254,7 @@ def main():
 
     # ---- per-kernel device times (eager, events inside the library around each launch)
     n_prof = min(max(K, 20), 100)
+    step.concurrent = False  # one stream, so each kernel's events bracket only itself
     with ops.profile("") as prof:
         for i in range(n_prof):
             step.run(i, seed=i)
@@ -297,7 +300,7 @@ def main():
         "metric": METRIC, "value": value, "unit": "scans/s", "n_gpus": world, "steps": K, "warmup": Wu,
         "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": dict(
-            workload_config(args, world), cuda_graph=bool(graphed),
+            workload_config(args, world), cuda_graph=bool(graphed), concurrent_chains=not args.serial,
             l2="3 rotating input sets (~120 MB re-read inputs each) + a %d MB gradient streamed per "
                "step; both exceed the 126 MB L2" % (alg["loss_grad_fill"] >> 20)),
         "roofline": roofline, "clocks": clocks, "gpu_launches": int(launches),

@@ -83,6 +83,15 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// 16-byte asynchronous global -> shared copy (LDGSTS), bypassing registers and L1.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
+
 // Streaming 128-bit store (data written once, never re-read by this kernel).
 __device__ __forceinline__ void st_stream(float4* p, float4 v) { __stcs(p, v); }
 

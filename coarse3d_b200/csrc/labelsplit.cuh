@@ -186,9 +186,12 @@ split_scatter_kernel(const long long* __restrict__ labels, const uint8_t* __rest
       // entropy weight (contrast_pixel_loss.py:46-49)
       const float* p = probs + (size_t)b * C * HW + pix;
       float ent = 0.f;
-      for (int k = 0; k < C; ++k) {
-        const float v = __ldg(p + (size_t)k * HW);
-        ent += v * logf(v + 1e-10f);
+      for (int k0 = 0; k0 < C; k0 += 8) {  // 8 strided loads in flight per pass
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = (k0 + j < C) ? __ldg(p + (size_t)(k0 + j) * HW) : 1.0f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) if (k0 + j < C) ent += v[j] * logf(v[j] + 1e-10f);
       }
       ent = -ent;
       w_list[slot] = expf(-(ent * ent));

@@ -105,9 +105,9 @@ ema_rows_kernel(EmaRowsParams p) {
     const int d4 = D >> 2;
     for (int i = threadIdx.x; i < rows * d4; i += blockDim.x) {
       const int r = i / d4, c = i - r * d4;
-      const float4 v = __ldg(reinterpret_cast<const float4*>(p.bank_n + (size_t)(r0 + r) * D) + c);
-      *reinterpret_cast<float4*>(s_bank + (size_t)r * ld + c * 4) = v;
+      cp_async16(s_bank + (size_t)r * ld + c * 4, p.bank_n + (size_t)(r0 + r) * D + c * 4);
     }
+    cp_async_wait_all();
   };
   if (p.n_tiles == 1 && (int)blockIdx.x < n_groups) load_tile(0);
   __syncthreads();
@@ -334,12 +334,27 @@ ema_segsum_kernel(const int32_t* __restrict__ seg_cnt, const int32_t* __restrict
     start = seg_start[c * B];
     for (int b = 0; b < B; ++b) n += seg_cnt[c * B + b];
   }
-  for (int i = 0; i < n; ++i) {
-    const int slot = start + i;
-    if (!maskv[slot]) continue;  // m_q = q * mask, c_q = feat * mask (:363-375)
-    const int m = sub[slot];
-    for (int d = threadIdx.x; d < D; d += blockDim.x) s_sum[m * D + d] += feat[(size_t)slot * D + d];
-    if (threadIdx.x == 0) s_cnt[m] += 1.0f;
+  // rows in order, 4 at a time so that the loads of a group are all in flight
+  for (int i0 = 0; i0 < n; i0 += 4) {
+    int mk[4], sb[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int slot = start + i0 + j;
+      const bool in = (i0 + j) < n;
+      mk[j] = in ? maskv[slot] : 0;  // m_q = q * mask, c_q = feat * mask (:363-375)
+      sb[j] = in ? sub[slot] : 0;
+    }
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+      float v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = mk[j] ? feat[(size_t)(start + i0 + j) * D + d] : 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) if (mk[j]) s_sum[sb[j] * D + d] += v[j];
+    }
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) if (mk[j]) s_cnt[sb[j]] += 1.0f;
+    }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < M * D; i += blockDim.x) packed[(size_t)c * M * D + i] = s_sum[i];

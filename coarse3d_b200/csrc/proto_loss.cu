@@ -165,7 +165,7 @@ struct RowsParams {
   float temperature, base_temperature;
 };
 
-template <bool kBackward>
+template <bool kBackward, int kChunks>
 __global__ void __launch_bounds__(kRowWarps * 32, 1)
 loss_rows_kernel(RowsParams p) {
   extern __shared__ __align__(16) float smem[];
@@ -181,15 +181,17 @@ loss_rows_kernel(RowsParams p) {
   float* my_l = s_l + warp * KcPad;
   const float scale_row = p.temperature / p.base_temperature;
 
+  // bank tile -> shared memory with cp.async (LDGSTS): every 16 B chunk is in
+  // flight at once instead of one L2 round trip per loop iteration
   auto load_tile = [&](int tile) {
     const int r0 = tile * p.tile_rows;
     const int rows = min(p.tile_rows, Kc - r0);
     const int d4 = D >> 2;
     for (int i = threadIdx.x; i < rows * d4; i += blockDim.x) {
       const int r = i / d4, c = i - r * d4;
-      const float4 v = __ldg(reinterpret_cast<const float4*>(p.bank_n + (size_t)(r0 + r) * D) + c);
-      *reinterpret_cast<float4*>(s_bank + (size_t)r * ld + c * 4) = v;
+      cp_async16(s_bank + (size_t)r * ld + c * 4, p.bank_n + (size_t)(r0 + r) * D + c * 4);
     }
+    cp_async_wait_all();
   };
 
   if (p.n_tiles == 1 && (int)blockIdx.x < n_groups) { load_tile(0); }
@@ -289,7 +291,7 @@ loss_rows_kernel(RowsParams p) {
 
     if (kBackward) {
       // ---- d a_hat = sum_k g_k c_hat_k ; lane owns 4-wide chunks of D
-      constexpr int kMaxChunks = 8;  // D <= 1024
+      constexpr int kMaxChunks = kChunks;  // D <= 128 * kChunks
       float4 acc[kMaxChunks];
 #pragma unroll
       for (int i = 0; i < kMaxChunks; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -461,16 +463,16 @@ extern "C" int c3d_proto_loss_forward(
   p.cnt_list = w.cnt_list; p.info = w.info; p.loss_part = w.loss_part; p.loss_out = loss_out;
   p.HW = HW; p.D = D; p.M = M; p.Kc = Kc; p.A = num_anchor; p.tile_rows = tile_rows;
   p.n_tiles = n_tiles; p.temperature = temperature; p.base_temperature = base_temperature;
-  C3D_CUDA(cudaFuncSetAttribute(loss_rows_kernel<false>,
+  C3D_CUDA(cudaFuncSetAttribute(loss_rows_kernel<false, 1>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  { KernelTimer kt__("loss_rows_fwd_kernel", stream); loss_rows_kernel<false><<<kNumSMs, kRowWarps * 32, smem, stream>>>(p); }
+  { KernelTimer kt__("loss_rows_fwd_kernel", stream); loss_rows_kernel<false, 1><<<kNumSMs, kRowWarps * 32, smem, stream>>>(p); }
   return check_launch("loss_rows_kernel<fwd>");
 }
 
 extern "C" int c3d_proto_loss_backward(
     const float* feats, int batch, int dim, int proj_h, int proj_w, int n_classes, int sub_protos,
     float temperature, float base_temperature, int num_anchor, void* workspace,
-    const float* grad_out, float* grad_feats, void* stream_) {
+    const float* grad_out, float* grad_feats, int grad_is_zeroed, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   const int B = batch, D = dim, C = n_classes, M = sub_protos;
   const long long HWll = (long long)proj_h * proj_w;
@@ -487,7 +489,7 @@ extern "C" int c3d_proto_loss_backward(
               "bank does not fit shared memory tiling (D=%d, Kc=%d)", D, Kc);
 
   const size_t n = (size_t)B * D * HW, n4 = n / 4;
-  {
+  if (!grad_is_zeroed) {
     const int threads = 512;
     long long blocks = (long long)((n4 + threads - 1) / threads);
     const int wave = kNumSMs * 4;
@@ -502,10 +504,34 @@ extern "C" int c3d_proto_loss_backward(
   p.cnt_list = w.cnt_list; p.info = w.info; p.grad_out = grad_out; p.grad_feats = grad_feats;
   p.HW = HW; p.D = D; p.M = M; p.Kc = Kc; p.A = num_anchor; p.tile_rows = tile_rows;
   p.n_tiles = n_tiles; p.temperature = temperature; p.base_temperature = base_temperature;
-  C3D_CUDA(cudaFuncSetAttribute(loss_rows_kernel<true>,
-                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  { KernelTimer kt__("loss_rows_bwd_kernel", stream); loss_rows_kernel<true><<<kNumSMs, kRowWarps * 32, smem, stream>>>(p); }
+#define LAUNCH_BWD(CH)                                                                          \
+  do {                                                                                          \
+    C3D_CUDA(cudaFuncSetAttribute(loss_rows_kernel<true, CH>,                                   \
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
+    KernelTimer kt__("loss_rows_bwd_kernel", stream);                                           \
+    loss_rows_kernel<true, CH><<<kNumSMs, kRowWarps * 32, smem, stream>>>(p);                   \
+  } while (0)
+  if (D <= 128) LAUNCH_BWD(1); else if (D <= 256) LAUNCH_BWD(2); else if (D <= 512) LAUNCH_BWD(4);
+  else LAUNCH_BWD(8);
+#undef LAUNCH_BWD
   return check_launch("loss_rows_kernel<bwd>");
+}
+
+extern "C" int c3d_zero_fill(void* dst, size_t nbytes, void* stream_) {
+  // The dense-gradient zero fill as its own entry point, so a caller can run it on
+  // a side stream concurrently with the forward pass (then pass grad_is_zeroed=1).
+  cudaStream_t stream = (cudaStream_t)stream_;
+  C3D_REQUIRE(dst && (reinterpret_cast<uintptr_t>(dst) & 15) == 0, "dst must be 16 B aligned");
+  C3D_REQUIRE(nbytes % 4 == 0, "nbytes must be a multiple of 4");
+  const size_t n = nbytes / 4, n4 = n / 4;
+  const int threads = 512;
+  long long blocks = (long long)((n4 + threads - 1) / threads);
+  const int wave = kNumSMs * 4;
+  const int grid = (int)(blocks < wave ? (blocks > 0 ? blocks : 1) : wave);
+  KernelTimer kt__("fill_zero_kernel", stream);
+  fill_zero_kernel<<<grid, threads, 0, stream>>>(reinterpret_cast<float4*>(dst), n4,
+                                                 reinterpret_cast<float*>(dst) + n4 * 4, (int)(n - n4 * 4));
+  return check_launch("fill_zero_kernel");
 }
 
 extern "C" int c3d_proto_loss_info(const void* workspace, int32_t* host_info4, void* stream_) {

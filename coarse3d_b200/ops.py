@@ -211,13 +211,22 @@ def proto_loss_forward_raw(feats, probs, labels, keep_mask, queue, cfg, keep, se
     return loss_out
 
 
-def proto_loss_backward_raw(feats, cfg, n_classes, sub_protos, workspace, grad_out, grad_feats):
-    """c3d_proto_loss_backward: writes the dense (B,D,H,W) gradient into grad_feats."""
+def zero_fill(t):
+    """Zero a contiguous float32 CUDA tensor with the library's streaming fill kernel."""
+    _need_cuda(t=t)
+    check(lib.c3d_zero_fill(_p(t), t.numel() * t.element_size(), _stream()))
+    return t
+
+
+def proto_loss_backward_raw(feats, cfg, n_classes, sub_protos, workspace, grad_out, grad_feats,
+                            grad_is_zeroed=False):
+    """c3d_proto_loss_backward: writes the dense (B,D,H,W) gradient into grad_feats.
+    grad_is_zeroed=True skips the zero fill (the caller ran `zero_fill(grad_feats)`)."""
     B, D, H, W = feats.shape
     check(lib.c3d_proto_loss_backward(
         _p(feats), B, D, H, W, n_classes, sub_protos, float(cfg.temperature),
         float(cfg.base_temperature), int(cfg.num_anchor), _p(workspace), _p(grad_out),
-        _p(grad_feats), _stream()))
+        _p(grad_feats), 1 if grad_is_zeroed else 0, _stream()))
     return grad_feats
 
 

@@ -54,7 +54,7 @@ class HotPathStep:
 
     def __init__(self, shape, batch, dim=128, sub_protos=20, num_anchor=512, temperature=0.07,
                  momentum=0.999, n_sets=3, seed0=1000, device="cuda", group=None,
-                 knn=(5, 5, 1.0, 1.0)):
+                 knn=(5, 5, 1.0, 1.0), concurrent=True):
         self.shape, self.batch, self.dim, self.M = shape, batch, dim, sub_protos
         self.device, self.group = torch.device(device), group
         self.knn_k, self.knn_s, self.knn_sigma, self.knn_cutoff = knn
@@ -89,6 +89,9 @@ class HotPathStep:
         self.knn_out = torch.empty((n,), dtype=torch.int64, device=self.device)
         self.inv_gauss = (1 - ops.gaussian_kernel(self.knn_s, self.knn_sigma)).reshape(-1).to(self.device)
         self.graphs = None
+        self.concurrent = concurrent
+        self.side = [torch.cuda.Stream(self.device) for _ in range(3)]
+        self.ev_fork, self.ev_fill, self.ev_proj, self.ev_ema = (torch.cuda.Event() for _ in range(4))
         torch.cuda.synchronize(self.device)
 
     # bytes the reference dtypes move per step
@@ -103,21 +106,57 @@ class HotPathStep:
         }
 
     def run(self, i, seed=0):
-        """Enqueue one step on the current stream (no allocation, no sync)."""
+        """Enqueue one step (no allocation, no sync).  The four independent chains
+        -- projection -> KNN, the dense-gradient zero fill, loss forward -> backward,
+        EMA update -- are forked onto side streams and joined before returning, so
+        the latency-bound small kernels overlap the bandwidth-bound fill; under
+        CUDA-graph capture they become parallel branches of the graph."""
         s, b = self.sets[i % len(self.sets)], self.proj_bufs[i % len(self.sets)]
         H, W, C = self.shape.proj_h, self.shape.proj_w, self.shape.n_classes
-        pr = ops.project_batch(s.points, s.offsets, self.fov, H, W, buffers=b)
+        cur = torch.cuda.current_stream(self.device)
+        if not self.concurrent:
+            pr = ops.project_batch(s.points, s.offsets, self.fov, H, W, buffers=b)
+            self._loss_fwd(s, seed)
+            ops.proto_loss_backward_raw(s.feats, self.cfg, C, self.M, self.loss_ws, self.grad_out, self.grad)
+            self._ema(s, seed)
+            self._knn(s, pr, C)
+            return pr
+        st_fill, st_proj, st_ema = self.side
+        self.ev_fork.record(cur)
+        for st in self.side:
+            st.wait_event(self.ev_fork)
+        with torch.cuda.stream(st_fill):
+            ops.zero_fill(self.grad)
+            self.ev_fill.record(st_fill)
+        with torch.cuda.stream(st_proj):
+            pr = ops.project_batch(s.points, s.offsets, self.fov, H, W, buffers=b)
+            self._knn(s, pr, C)
+            self.ev_proj.record(st_proj)
+        with torch.cuda.stream(st_ema):
+            self._ema(s, seed)
+            self.ev_ema.record(st_ema)
+        self._loss_fwd(s, seed)
+        cur.wait_event(self.ev_fill)
+        ops.proto_loss_backward_raw(s.feats, self.cfg, C, self.M, self.loss_ws, self.grad_out,
+                                    self.grad, grad_is_zeroed=True)
+        cur.wait_event(self.ev_proj)
+        cur.wait_event(self.ev_ema)
+        return pr
+
+    def _loss_fwd(self, s, seed):
         ops.proto_loss_forward_raw(s.feats, s.probs, s.labels, s.keep_mask, self.protos, self.cfg,
                                    None, seed, self.loss_ws, self.loss)
-        ops.proto_loss_backward_raw(s.feats, self.cfg, C, self.M, self.loss_ws, self.grad_out, self.grad)
+
+    def _ema(self, s, seed):
         distributed.prototype_update(
             s.feats, s.labels, self.protos, *self.ln_d, *self.ln_c, self.momentum,
             assign_mode=ops.ASSIGN_GUMBEL_DEVICE, seed=seed, max_rows=self.max_rows, group=self.group,
             workspace=self.ema_ws, packed=self.packed, out=self.protos_next)
+
+    def _knn(self, s, pr, C):
         ops.knn_batch(pr.proj_range, s.argmax, pr.uproj_depth, pr.uproj_x_idx, pr.uproj_y_idx,
                       s.offsets, self.knn_k, self.knn_s, self.knn_sigma, self.knn_cutoff, C,
                       inv_gauss=self.inv_gauss, out=self.knn_out)
-        return pr
 
     def capture(self):
         """Capture one CUDA graph per input set.  Returns False if capture fails

@@ -150,7 +150,12 @@ int c3d_proto_loss_backward(
     void* workspace,              /* as left by c3d_proto_loss_forward           */
     const float* grad_out,        /* [1] upstream gradient of the scalar loss    */
     float* grad_feats,            /* [B, D, H, W] dense, fully written           */
+    int grad_is_zeroed,           /* 1: caller already zero-filled grad_feats
+                                     (c3d_zero_fill, e.g. on a side stream)      */
     void* stream);
+
+/* The dense-gradient zero fill (128-bit streaming stores) as its own entry point. */
+int c3d_zero_fill(void* dst, size_t nbytes, void* stream);
 
 /* Synchronous: copies {T, labelled pixels, flags, 0} to host_info4 (host). */
 int c3d_proto_loss_info(const void* workspace, int32_t* host_info4, void* stream);
