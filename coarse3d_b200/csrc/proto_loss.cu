@@ -5,20 +5,23 @@
 // loop of unique / multinomial / gather launches, a 380 x D GEMM over A*T
 // duplicated rows and an index_put backward is restated as:
 //
-//   K1 loss_count    labels + keep_mask (9 B/px, coalesced) -> per-tile per-class counts
-//   K2 loss_scan     per-scan prefix over tiles; last CTA builds the (scan, class)
-//                    segment table in the reference's X_ptr order (b asc, class asc)
-//   K3 loss_scatter  stable multi-split: labelled pixels -> slots sorted by
-//                    (scan, class, pixel); entropy weight exp(-H^2) per slot
-//                    (:46-49); extra CTAs L2-normalise the bank rows (:167)
-//   K4 loss_sample   one CTA per segment: CDF, A draws with replacement
-//                    (Philox) or the injected `keep` indices -> multiplicity per slot
-//   K5 loss_rows     one warp per labelled slot with multiplicity > 0: strided NCHW
-//                    gather, L2 normalise, similarity against the bank staged in
-//                    shared memory, temperature, max-shift, masked sums (:166-193);
-//                    rows are weighted by multiplicity instead of being duplicated
-//   K6 fill_zero     dense (B,D,H,W) gradient zero-fill, 128-bit streaming stores
-//   K7 loss_rows<bwd> recompute logits, closed-form gradient, scatter D values/slot
+//   K1-K3 split_count / split_scan / split_scatter  (labelsplit.cuh) labelled pixels
+//         -> slots sorted by (scan, class, pixel) + entropy weight exp(-H^2) per slot
+//         (:46-49); extra CTAs L2-normalise the bank rows (:167)
+//   K4 loss_sample   one CTA per (scan, class) segment: CDF, A draws with replacement
+//         (Philox) or the injected `keep` indices -> multiplicity per slot; the
+//         distinct sampled slots are compacted into ROWS (<= A per segment)
+//   K5 loss_rows     one warp per distinct row: strided NCHW gather, L2 normalise,
+//         similarity against the bank staged in shared memory (cp.async),
+//         temperature, max-shift, masked sums (:166-193); rows are weighted by their
+//         multiplicity instead of being duplicated.  With need_grad the same kernel
+//         also evaluates the closed-form gradient row d loss / d feats[:, pixel]
+//         (per unit upstream gradient) into a compact (rows x D) buffer, so the
+//         backward pass has no arithmetic left on its critical path.
+//   K6 fill_zero     dense (B,D,H,W) gradient zero fill, 128-bit streaming stores --
+//         98 % of the path's compulsory bytes; deliberately low-occupancy so that it
+//         can share the SMs with the latency-bound kernels of the other chains.
+//   K7 loss_grad_scatter  D strided stores per distinct row, scaled by grad_out.
 //
 // All reductions are order-deterministic (no float atomics).
 #include <math_constants.h>
@@ -30,7 +33,9 @@ namespace c3d {
 
 constexpr int kRowWarps = 8;       // rows processed concurrently per loss_rows CTA
 
-enum LossFlag { kFlagNoAnchor = 1, kFlagBadKeep = 2, kFlagKeepRows = 4 };  // 8 = kFlagBadLabel
+enum LossFlag { kFlagNoAnchor = 1, kFlagBadKeep = 2, kFlagKeepRows = 4, kFlagNoGradRows = 32 };
+// info[] slots beyond SplitInfo
+enum LossInfo { kInfoU = 5, kInfoDone3 = 6, kInfoHasGrad = 7 };
 
 struct LossWs {
   int32_t* info;       // [8]
@@ -38,21 +43,28 @@ struct LossWs {
   int32_t* seg_cnt;    // [B * C]
   int32_t* seg_start;  // [B * C]
   int32_t* seg_tidx;   // [B * C] index among non-empty segments, or -1
+  int32_t* seg_nd;     // [B * C] distinct sampled slots of the segment
+  int32_t* row_base;   // [B * C + 1] exclusive prefix of seg_nd over non-empty segments
+  int32_t* seg_of_t;   // [B * C] segment index of the t-th non-empty segment
   int32_t* pix_list;   // [cap] b*HW + pixel
   int32_t* cls_list;   // [cap]
-  float* w_list;       // [cap] weights, then in-place CDF
+  float* w_list;       // [cap] weights -> in-place CDF -> (int) distinct-slot list
   int32_t* cnt_list;   // [cap] sampling multiplicity
-  float* loss_part;    // [cap]
+  float* loss_part;    // [max_rows]
+  float* grad_rows;    // [max_rows * D]
   float* bank_n;       // [(C-1)*M*D] normalised prototypes, classes 1..C-1
+  size_t max_rows;
   size_t bytes;
 };
 
 static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
-static LossWs carve(void* base, int B, int C, int HW, int D, int M) {
+static LossWs carve(void* base, int B, int C, int HW, int D, int M, int A) {
   LossWs w;
   const size_t cap = (size_t)B * HW;
   const size_t nblk = (size_t)B * ((HW + kTile - 1) / kTile);
+  size_t max_rows = (size_t)A * B * (C - 1);  // <= A distinct rows per segment
+  if (max_rows > cap) max_rows = cap;
   size_t off = 0;
   auto take = [&](size_t n) { size_t o = off; off += align_up(n); return (char*)base + o; };
   w.info = (int32_t*)take(8 * 4);
@@ -60,12 +72,17 @@ static LossWs carve(void* base, int B, int C, int HW, int D, int M) {
   w.seg_cnt = (int32_t*)take((size_t)B * C * 4);
   w.seg_start = (int32_t*)take((size_t)B * C * 4);
   w.seg_tidx = (int32_t*)take((size_t)B * C * 4);
+  w.seg_nd = (int32_t*)take((size_t)B * C * 4);
+  w.row_base = (int32_t*)take(((size_t)B * C + 1) * 4);
+  w.seg_of_t = (int32_t*)take((size_t)B * C * 4);
   w.pix_list = (int32_t*)take(cap * 4);
   w.cls_list = (int32_t*)take(cap * 4);
   w.w_list = (float*)take(cap * 4);
   w.cnt_list = (int32_t*)take(cap * 4);
-  w.loss_part = (float*)take(cap * 4);
+  w.loss_part = (float*)take(max_rows * 4);
+  w.grad_rows = (float*)take(max_rows * D * 4);
   w.bank_n = (float*)take((size_t)(C - 1) * M * D * 4);
+  w.max_rows = max_rows;
   w.bytes = off;
   return w;
 }
@@ -87,85 +104,153 @@ loss_sample_kernel(const int32_t* __restrict__ seg_cnt, const int32_t* __restric
                    const int32_t* __restrict__ seg_tidx, const int32_t* __restrict__ pix_list,
                    float* __restrict__ w_list, int32_t* __restrict__ cnt_list, int HW, int C, int A,
                    const long long* __restrict__ keep, int keep_rows, unsigned long long seed,
-                   int32_t* __restrict__ info) {
-  const int seg = blockIdx.x;
+                   int32_t* __restrict__ seg_nd, int32_t* __restrict__ row_base,
+                   int32_t* __restrict__ seg_of_t, int32_t* __restrict__ info) {
+  const int seg = blockIdx.x, nseg = gridDim.x;
   const int n = seg_cnt[seg];
-  if (keep && seg == 0 && threadIdx.x == 0 && info[kInfoT] != keep_rows)
-    atomicOr(&info[kInfoFlags], kFlagKeepRows);
-  if (n == 0) return;
-  const int start = seg_start[seg], t = seg_tidx[seg], b = seg / C;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (keep) {
-    if (t >= keep_rows) return;
-    bool bad = false;
-    for (int a = threadIdx.x; a < A; a += 256) {
-      const long long pix = keep[(size_t)t * A + a];
-      const long long key = (long long)b * HW + pix;
-      int lo = 0, hi = n;  // first slot with pix_list >= key
-      while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (pix_list[start + mid] < key) lo = mid + 1; else hi = mid;
-      }
-      if (pix < 0 || pix >= HW || lo >= n || pix_list[start + lo] != key) bad = true;
-      else atomicAdd(&cnt_list[start + lo], 1);
-    }
-    if (bad) atomicOr(&info[kInfoFlags], kFlagBadKeep);
-    return;
-  }
-  // inclusive scan of the weights -> CDF (in place), 256 elements per step
   __shared__ float s_warp[8];
   __shared__ float s_carry;
-  if (threadIdx.x == 0) s_carry = 0.f;
-  __syncthreads();
-  for (int base = 0; base < n; base += 256) {
-    const int i = base + threadIdx.x;
-    float v = (i < n) ? w_list[start + i] : 0.f;
+  __shared__ int s_iw[8];
+  __shared__ int s_last;
+  if (keep && seg == 0 && threadIdx.x == 0 && info[kInfoT] != keep_rows)
+    atomicOr(&info[kInfoFlags], kFlagKeepRows);
+  if (n > 0) {
+    const int start = seg_start[seg], t = seg_tidx[seg], b = seg / C;
+    if (keep) {
+      bool bad = false;
+      for (int a = threadIdx.x; a < A && t < keep_rows; a += 256) {
+        const long long pix = keep[(size_t)t * A + a];
+        const long long key = (long long)b * HW + pix;
+        int lo = 0, hi = n;  // first slot with pix_list >= key
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (pix_list[start + mid] < key) lo = mid + 1; else hi = mid;
+        }
+        if (pix < 0 || pix >= HW || lo >= n || pix_list[start + lo] != key) bad = true;
+        else atomicAdd(&cnt_list[start + lo], 1);
+      }
+      if (bad) atomicOr(&info[kInfoFlags], kFlagBadKeep);
+    } else {
+      // inclusive scan of the weights -> CDF (in place), 256 elements per step
+      if (threadIdx.x == 0) s_carry = 0.f;
+      __syncthreads();
+      for (int base = 0; base < n; base += 256) {
+        const int i = base + threadIdx.x;
+        float v = (i < n) ? w_list[start + i] : 0.f;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      float u = __shfl_up_sync(0xffffffffu, v, o);
-      if (lane >= o) v += u;
+        for (int o = 1; o < 32; o <<= 1) {
+          float u = __shfl_up_sync(0xffffffffu, v, o);
+          if (lane >= o) v += u;
+        }
+        if (lane == 31) s_warp[warp] = v;
+        __syncthreads();
+        float pre = s_carry;
+        for (int w = 0; w < warp; ++w) pre += s_warp[w];
+        if (i < n) w_list[start + i] = pre + v;
+        __syncthreads();
+        if (threadIdx.x == 255) s_carry = pre + v;
+        __syncthreads();
+      }
+      const float total = s_carry;
+      for (int a = threadIdx.x; a < A; a += 256) {
+        const unsigned long long ctr = (unsigned long long)t * A + a;
+        const uint4 r = philox4x32_10(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u),
+                                      make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+        const float x = (float)(r.x >> 8) * (1.0f / 16777216.0f) * total;
+        int lo = 0, hi = n - 1;  // first slot with cdf > x (clamped)
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (w_list[start + mid] > x) hi = mid; else lo = mid + 1;
+        }
+        atomicAdd(&cnt_list[start + lo], 1);
+      }
     }
-    if (lane == 31) s_warp[warp] = v;
+    // ---- compact the distinct sampled slots of this segment, in slot order,
+    //      into the (now dead) w_list storage of the segment
     __syncthreads();
-    float pre = s_carry;
-    for (int w = 0; w < warp; ++w) pre += s_warp[w];
-    if (i < n) w_list[start + i] = pre + v;
-    __syncthreads();
-    if (threadIdx.x == 255) s_carry = pre + v;
-    __syncthreads();
+    int32_t* dist = reinterpret_cast<int32_t*>(w_list) + start;
+    int carry = 0;
+    for (int base = 0; base < n; base += 256) {
+      const int i = base + threadIdx.x;
+      const bool f = (i < n) && (__ldcg(cnt_list + start + i) > 0);
+      const unsigned bal = __ballot_sync(0xffffffffu, f);
+      if (lane == 0) s_iw[warp] = __popc(bal);
+      __syncthreads();
+      int pre = carry, tot = 0;
+      for (int w = 0; w < 8; ++w) { if (w < warp) pre += s_iw[w]; tot += s_iw[w]; }
+      __syncthreads();
+      if (f) dist[pre + __popc(bal & ((1u << lane) - 1))] = start + i;
+      carry += tot;
+    }
+    if (threadIdx.x == 0) seg_nd[seg] = carry;
+  } else if (threadIdx.x == 0) {
+    seg_nd[seg] = 0;
   }
-  const float total = s_carry;
-  for (int a = threadIdx.x; a < A; a += 256) {
-    const unsigned long long ctr = (unsigned long long)t * A + a;
-    const uint4 r = philox4x32_10(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u),
-                                  make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
-    const float x = (float)(r.x >> 8) * (1.0f / 16777216.0f) * total;
-    int lo = 0, hi = n - 1;  // first slot with cdf > x (clamped)
-    while (lo < hi) {
-      const int mid = (lo + hi) >> 1;
-      if (w_list[start + mid] > x) hi = mid; else lo = mid + 1;
+  // ---- last CTA: exclusive prefix of the row counts over non-empty segments
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(&info[kInfoDone3], 1) == nseg - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (warp == 0) {
+    int carry = 0;
+    for (int base = 0; base < nseg; base += 32) {
+      const int i = base + lane;
+      const int t = (i < nseg) ? seg_tidx[i] : -1;
+      const int v = (t >= 0) ? __ldcg(seg_nd + i) : 0;
+      int incl = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int u = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += u;
+      }
+      if (t >= 0) { row_base[t] = carry + incl - v; seg_of_t[t] = i; }
+      carry += __shfl_sync(0xffffffffu, incl, 31);
     }
-    atomicAdd(&cnt_list[start + lo], 1);
+    if (lane == 0) {
+      row_base[info[kInfoT]] = carry;
+      info[kInfoU] = carry;
+      info[kInfoDone3] = 0;
+    }
   }
 }
 
-// ---------------------------------------------------------------- K5 / K7 --
+// ---------------------------------------------------------------- K5 -------
 struct RowsParams {
   const float* feats;      // (B, D, HW)
   const float* bank_n;     // (Kc, D)
   const int32_t* pix_list;
   const int32_t* cls_list;
   const int32_t* cnt_list;
+  const int32_t* dist_list;  // distinct slots, per segment at seg_start
+  const int32_t* seg_start;
+  const int32_t* row_base;
+  const int32_t* seg_of_t;
   int32_t* info;
-  float* loss_part;        // fwd: [cap]
-  float* loss_out;         // fwd: [1]
-  const float* grad_out;   // bwd: [1]
-  float* grad_feats;       // bwd: (B, D, HW)
+  float* loss_part;        // [rows]
+  float* grad_rows;        // [rows * D]
+  float* loss_out;         // [1]
   int HW, D, M, Kc, A, tile_rows, n_tiles;
   float temperature, base_temperature;
 };
 
-template <bool kBackward, int kChunks>
+// row index -> labelled-pixel slot, through the per-segment distinct lists
+__device__ __forceinline__ int slot_of_row(int row, int T, const int32_t* __restrict__ row_base,
+                                           const int32_t* __restrict__ seg_of_t,
+                                           const int32_t* __restrict__ seg_start,
+                                           const int32_t* __restrict__ dist_list) {
+  int lo = 0, hi = T;  // row_base[lo] <= row < row_base[hi]
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(row_base + mid) <= row) lo = mid; else hi = mid;
+  }
+  const int seg = __ldg(seg_of_t + lo);
+  return __ldcg(dist_list + __ldg(seg_start + seg) + (row - __ldg(row_base + lo)));
+}
+
+template <bool kWithGrad, int kChunks>
 __global__ void __launch_bounds__(kRowWarps * 32, 1)
 loss_rows_kernel(RowsParams p) {
   extern __shared__ __align__(16) float smem[];
@@ -175,11 +260,13 @@ loss_rows_kernel(RowsParams p) {
   float* s_a = s_bank + (size_t)p.tile_rows * ld;          // [warps][D]
   float* s_l = s_a + kRowWarps * D;                        // [warps][KcPad]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_slots = p.info[kInfoPl];
-  const int n_groups = (n_slots + kRowWarps - 1) / kRowWarps;
+  const int n_rows = p.info[kInfoU];
+  const int T = p.info[kInfoT];
+  const int n_groups = (n_rows + kRowWarps - 1) / kRowWarps;
   float* my_a = s_a + warp * D;
   float* my_l = s_l + warp * KcPad;
   const float scale_row = p.temperature / p.base_temperature;
+  const float inv_R = 1.0f / ((float)p.A * (float)T);  // mean over R = A*T rows (:193)
 
   // bank tile -> shared memory with cp.async (LDGSTS): every 16 B chunk is in
   // flight at once instead of one L2 round trip per loop iteration
@@ -198,13 +285,14 @@ loss_rows_kernel(RowsParams p) {
   __syncthreads();
 
   for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
-    const int slot = grp * kRowWarps + warp;
-    const int cnt = (slot < n_slots) ? p.cnt_list[slot] : 0;
-    const bool active = cnt > 0;
-    int gpix = 0, cls = 0;
+    const int row = grp * kRowWarps + warp;
+    const bool active = row < n_rows;
+    int cls = 0, cnt = 0;
     float inv_norm = 0.f;
     if (active) {
-      gpix = p.pix_list[slot];
+      const int slot = slot_of_row(row, T, p.row_base, p.seg_of_t, p.seg_start, p.dist_list);
+      cnt = __ldcg(p.cnt_list + slot);
+      const int gpix = p.pix_list[slot];
       cls = p.cls_list[slot];
       const int b = gpix / p.HW, pix = gpix - b * p.HW;
       const float* src = p.feats + (size_t)b * D * p.HW + pix;
@@ -229,13 +317,13 @@ loss_rows_kernel(RowsParams p) {
         for (int kk = lane; kk < rows; kk += 32) {
           const float4* c4 = reinterpret_cast<const float4*>(s_bank + (size_t)kk * ld);
           const float4* a4 = reinterpret_cast<const float4*>(my_a);
-          float acc = 0.f;
+          float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
 #pragma unroll 8
           for (int j = 0; j < (D >> 2); ++j) {
             const float4 c = c4[j], a = a4[j];
-            acc += a.x * c.x; acc += a.y * c.y; acc += a.z * c.z; acc += a.w * c.w;
+            acc0 += a.x * c.x; acc1 += a.y * c.y; acc2 += a.z * c.z; acc3 += a.w * c.w;
           }
-          my_l[r0 + kk] = acc / p.temperature;
+          my_l[r0 + kk] = ((acc0 + acc1) + (acc2 + acc3)) / p.temperature;
         }
       }
     }
@@ -253,59 +341,52 @@ loss_rows_kernel(RowsParams p) {
         if (k < pos_lo || k >= pos_hi) neg += e;
       }
       neg = warp_sum(neg);
-      if (!kBackward) {
-        float s = 0.f; int npos = 0;
-        for (int k = pos_lo + lane; k < pos_hi; k += 32) {
-          if (k >= 0 && k < Kc) {
-            const float l = my_l[k] - mx;
-            s += l - logf(expf(l) + neg + 1e-6f);
-            ++npos;
-          }
+      float s = 0.f, inv_den = 0.f; int npos = 0;
+      for (int k = pos_lo + lane; k < pos_hi; k += 32) {
+        if (k >= 0 && k < Kc) {
+          const float l = my_l[k] - mx;
+          const float den = expf(l) + neg + 1e-6f;
+          s += l - logf(den);
+          inv_den += 1.0f / den;
+          ++npos;
         }
-        s = warp_sum(s);
-        npos = __reduce_add_sync(0xffffffffu, npos);
-        if (lane == 0)  // (:191-192), weighted by the row's multiplicity
-          p.loss_part[slot] = (float)cnt * (-scale_row * (s / (float)npos));
-      } else {
-        // ---- dL/dz_k
-        float inv_den = 0.f; int npos = 0;
-        for (int k = pos_lo + lane; k < pos_hi; k += 32) {
-          if (k >= 0 && k < Kc) {
-            inv_den += 1.0f / (expf(my_l[k] - mx) + neg + 1e-6f);
-            ++npos;
-          }
-        }
-        inv_den = warp_sum(inv_den);
-        npos = __reduce_add_sync(0xffffffffu, npos);
-        const float s = scale_row / (float)npos;
+      }
+      s = warp_sum(s);
+      inv_den = warp_sum(inv_den);
+      npos = __reduce_add_sync(0xffffffffu, npos);
+      if (lane == 0)  // (:191-192), weighted by the row's multiplicity
+        p.loss_part[row] = (float)cnt * (-scale_row * (s / (float)npos));
+      if (kWithGrad) {
+        // dL/dz_k: positives -s (1 - e_k/den_k); negatives s e_k sum_{j in pos} 1/den_j
+        const float sg = scale_row / (float)npos;
         for (int k = lane; k < Kc; k += 32) {
           const float e = expf(my_l[k] - mx);
           float g;
-          if (k >= pos_lo && k < pos_hi) g = -s * (1.0f - e / (e + neg + 1e-6f));
-          else g = s * e * inv_den;
+          if (k >= pos_lo && k < pos_hi) g = -sg * (1.0f - e / (e + neg + 1e-6f));
+          else g = sg * e * inv_den;
           my_l[k] = g / p.temperature;  // dL/d(a_hat . c_hat_k)
         }
       }
     }
     __syncwarp();
 
-    if (kBackward) {
+    if (kWithGrad) {
       // ---- d a_hat = sum_k g_k c_hat_k ; lane owns 4-wide chunks of D
-      constexpr int kMaxChunks = kChunks;  // D <= 128 * kChunks
-      float4 acc[kMaxChunks];
+      float4 acc[kChunks];
 #pragma unroll
-      for (int i = 0; i < kMaxChunks; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = 0; i < kChunks; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       const int d4 = D >> 2;
       for (int tile = 0; tile < p.n_tiles; ++tile) {
         if (p.n_tiles > 1) { __syncthreads(); load_tile(tile); __syncthreads(); }
         if (active) {
           const int r0 = tile * p.tile_rows;
           const int rows = min(p.tile_rows, Kc - r0);
+#pragma unroll 4
           for (int kk = 0; kk < rows; ++kk) {
             const float g = my_l[r0 + kk];
             const float4* c4 = reinterpret_cast<const float4*>(s_bank + (size_t)kk * ld);
 #pragma unroll
-            for (int i = 0; i < kMaxChunks; ++i) {
+            for (int i = 0; i < kChunks; ++i) {
               const int ch = lane + 32 * i;
               if (ch < d4) {
                 const float4 c = c4[ch];
@@ -319,7 +400,7 @@ loss_rows_kernel(RowsParams p) {
         // normalize backward: da = (dhat - a_hat (a_hat . dhat)) / max(|a|, eps)
         float dot = 0.f;
 #pragma unroll
-        for (int i = 0; i < kMaxChunks; ++i) {
+        for (int i = 0; i < kChunks; ++i) {
           const int ch = lane + 32 * i;
           if (ch < d4) {
             const float4 a = reinterpret_cast<const float4*>(my_a)[ch];
@@ -327,22 +408,16 @@ loss_rows_kernel(RowsParams p) {
           }
         }
         dot = warp_sum(dot);
-        const int T = p.info[kInfoT];
-        // mean over R = A*T rows (:193) times the upstream gradient
-        const float w = (float)cnt / ((float)p.A * (float)T) * __ldg(p.grad_out) * inv_norm;
-        const int b = gpix / p.HW, pix = gpix - b * p.HW;
-        float* dst = p.grad_feats + (size_t)b * D * p.HW + pix;
-        const bool clamped = inv_norm >= 1e12f;  // |a| < eps: y = x / eps, dy/dx = 1/eps
+        const float w = (float)cnt * inv_R * inv_norm;
+        const float sub = (inv_norm >= 1e12f) ? 0.f : dot;  // |a| < eps: y = x / eps
+        float4* dst = reinterpret_cast<float4*>(p.grad_rows + (size_t)row * D);
 #pragma unroll
-        for (int i = 0; i < kMaxChunks; ++i) {
+        for (int i = 0; i < kChunks; ++i) {
           const int ch = lane + 32 * i;
           if (ch < d4) {
             const float4 a = reinterpret_cast<const float4*>(my_a)[ch];
-            const float sub = clamped ? 0.f : dot;
-            dst[(size_t)(ch * 4 + 0) * p.HW] = (acc[i].x - a.x * sub) * w;
-            dst[(size_t)(ch * 4 + 1) * p.HW] = (acc[i].y - a.y * sub) * w;
-            dst[(size_t)(ch * 4 + 2) * p.HW] = (acc[i].z - a.z * sub) * w;
-            dst[(size_t)(ch * 4 + 3) * p.HW] = (acc[i].w - a.w * sub) * w;
+            dst[ch] = make_float4((acc[i].x - a.x * sub) * w, (acc[i].y - a.y * sub) * w,
+                                  (acc[i].z - a.z * sub) * w, (acc[i].w - a.w * sub) * w);
           }
         }
       }
@@ -350,44 +425,81 @@ loss_rows_kernel(RowsParams p) {
     __syncwarp();
   }
 
-  if (!kBackward) {
-    // ---- deterministic final reduction by the last CTA: loss = sum / (A*T)
-    __shared__ int s_last;
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) s_last = (atomicAdd(&p.info[kInfoDone2], 1) == (int)gridDim.x - 1);
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    float s = 0.f;
-    for (int i = threadIdx.x; i < n_slots; i += blockDim.x)
-      if (__ldcg(p.cnt_list + i) > 0) s += __ldcg(p.loss_part + i);
-    s = warp_sum(s);
-    __shared__ float s_red[kRowWarps];
-    if (lane == 0) s_red[warp] = s;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      float tot = 0.f;
-      for (int w = 0; w < kRowWarps; ++w) tot += s_red[w];
-      const int T = p.info[kInfoT];
-      p.loss_out[0] = tot / ((float)p.A * (float)T);  // T == 0 -> NaN (reference crashes)
-      p.info[kInfoDone2] = 0;
-    }
+  // ---- deterministic final reduction by the last CTA: loss = sum / (A*T)
+  __shared__ int s_last;
+  __shared__ float s_red[kRowWarps];
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(&p.info[kInfoDone2], 1) == (int)gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n_rows; i += blockDim.x) s += __ldcg(p.loss_part + i);
+  s = warp_sum(s);
+  if (lane == 0) s_red[warp] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot = 0.f;
+    for (int w = 0; w < kRowWarps; ++w) tot += s_red[w];
+    p.loss_out[0] = tot * inv_R;  // T == 0 -> NaN (the reference crashes)
+    p.info[kInfoDone2] = 0;
+    p.info[kInfoHasGrad] = kWithGrad ? 1 : 0;
   }
 }
 
 // ---------------------------------------------------------------- K6 -------
-__global__ void __launch_bounds__(512)
+// Low-occupancy streaming fill: 2 CTAs x 256 threads per SM, 8 independent 128-bit
+// stores per thread per iteration.  Stores are fire-and-forget, so this already
+// saturates HBM while leaving most warp slots to concurrently running kernels.
+__global__ void __launch_bounds__(256)
 fill_zero_kernel(float4* __restrict__ dst, size_t n4, float* __restrict__ tail, int ntail) {
   const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (; i + 3 * stride < n4; i += 4 * stride) {
-    __stcs(dst + i, z); __stcs(dst + i + stride, z);
-    __stcs(dst + i + 2 * stride, z); __stcs(dst + i + 3 * stride, z);
+  for (; i + 7 * stride < n4; i += 8 * stride) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) __stcs(dst + i + j * stride, z);
   }
   for (; i < n4; i += stride) __stcs(dst + i, z);
   if (blockIdx.x == 0 && (int)threadIdx.x < ntail) tail[threadIdx.x] = 0.f;
+}
+
+static int launch_fill(void* dst, size_t nbytes, cudaStream_t stream) {
+  const size_t n = nbytes / 4, n4 = n / 4;
+  const int threads = 256;
+  long long blocks = (long long)((n4 + threads - 1) / threads);
+  const int wave = kNumSMs * 2;
+  const int grid = (int)(blocks < wave ? (blocks > 0 ? blocks : 1) : wave);
+  KernelTimer kt__("fill_zero_kernel", stream);
+  fill_zero_kernel<<<grid, threads, 0, stream>>>(reinterpret_cast<float4*>(dst), n4,
+                                                 reinterpret_cast<float*>(dst) + n4 * 4,
+                                                 (int)(n - n4 * 4));
+  return check_launch("fill_zero_kernel");
+}
+
+// ---------------------------------------------------------------- K7 -------
+__global__ void __launch_bounds__(256)
+loss_grad_scatter_kernel(const float* __restrict__ grad_rows, const int32_t* __restrict__ pix_list,
+                         const int32_t* __restrict__ dist_list, const int32_t* __restrict__ seg_start,
+                         const int32_t* __restrict__ row_base, const int32_t* __restrict__ seg_of_t,
+                         int32_t* __restrict__ info, const float* __restrict__ grad_out, int HW, int D,
+                         float* __restrict__ grad_feats) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_rows = info[kInfoU], T = info[kInfoT];
+  if (!info[kInfoHasGrad]) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&info[kInfoFlags], kFlagNoGradRows);
+    return;
+  }
+  const float go = __ldg(grad_out);
+  for (int row = blockIdx.x * 8 + warp; row < n_rows; row += gridDim.x * 8) {
+    const int slot = slot_of_row(row, T, row_base, seg_of_t, seg_start, dist_list);
+    const int gpix = __ldg(pix_list + slot);
+    const int b = gpix / HW, pix = gpix - b * HW;
+    float* dst = grad_feats + (size_t)b * D * HW + pix;
+    const float* src = grad_rows + (size_t)row * D;
+    for (int d = lane; d < D; d += 32) dst[(size_t)d * HW] = __ldcg(src + d) * go;
+  }
 }
 
 static int rows_config(int D, int Kc, int* tile_rows, int* n_tiles, size_t* smem) {
@@ -403,22 +515,32 @@ static int rows_config(int D, int Kc, int* tile_rows, int* n_tiles, size_t* smem
   return 0;
 }
 
+template <bool kWithGrad, int kChunks>
+static int launch_rows(const RowsParams& p, size_t smem, cudaStream_t stream) {
+  C3D_CUDA(cudaFuncSetAttribute(loss_rows_kernel<kWithGrad, kChunks>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  KernelTimer kt__("loss_rows_kernel", stream);
+  loss_rows_kernel<kWithGrad, kChunks><<<kNumSMs, kRowWarps * 32, smem, stream>>>(p);
+  return check_launch("loss_rows_kernel");
+}
+
 }  // namespace c3d
 
 using namespace c3d;
 
 extern "C" size_t c3d_proto_loss_workspace_bytes(int batch, int n_classes, int hw, int dim,
-                                                 int sub_protos) {
-  if (batch <= 0 || n_classes < 2 || hw <= 0 || dim <= 0 || sub_protos <= 0) return 0;
-  return carve(nullptr, batch, n_classes, hw, dim, sub_protos).bytes;
+                                                 int sub_protos, int num_anchor) {
+  if (batch <= 0 || n_classes < 2 || hw <= 0 || dim <= 0 || sub_protos <= 0 || num_anchor <= 0)
+    return 0;
+  return carve(nullptr, batch, n_classes, hw, dim, sub_protos, num_anchor).bytes;
 }
 
 extern "C" int c3d_proto_loss_forward(
     const float* feats, const float* probs, const int64_t* labels, const uint8_t* keep_mask,
     const float* proto_queue, int batch, int dim, int proj_h, int proj_w, int n_classes,
     int sub_protos, int ignore_label, float temperature, float base_temperature, int num_anchor,
-    const int64_t* keep, int keep_rows, uint64_t seed, void* workspace, float* loss_out,
-    void* stream_) {
+    const int64_t* keep, int keep_rows, uint64_t seed, int need_grad, void* workspace,
+    float* loss_out, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   const int B = batch, D = dim, C = n_classes, M = sub_protos;
   const long long HWll = (long long)proj_h * proj_w;
@@ -432,7 +554,7 @@ extern "C" int c3d_proto_loss_forward(
   C3D_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "workspace must be 256 B aligned");
   C3D_REQUIRE(temperature > 0 && base_temperature > 0, "temperatures must be positive");
   const int HW = (int)HWll;
-  LossWs w = carve(workspace, B, C, HW, D, M);
+  LossWs w = carve(workspace, B, C, HW, D, M, num_anchor);
   const int nbps = (HW + kTile - 1) / kTile, nblk = B * nbps;
   const int Kc = (C - 1) * M;
   int tile_rows, n_tiles; size_t smem;
@@ -440,81 +562,64 @@ extern "C" int c3d_proto_loss_forward(
               "bank does not fit shared memory tiling (D=%d, Kc=%d)", D, Kc);
 
   C3D_CUDA(cudaMemsetAsync(w.info, 0, 8 * 4, stream));
-  { KernelTimer kt__("split_count_kernel", stream); split_count_kernel<<<nblk, 256, 0, stream>>>((const long long*)labels, keep_mask, HW, nbps, C,
-                                              ignore_label, w.blk_cnt, w.info); }
-  int rc = check_launch("split_count_kernel");
-  if (rc) return rc;
-  { KernelTimer kt__("split_scan_kernel", stream); split_scan_kernel<false><<<B, 1024, 0, stream>>>(w.blk_cnt, nbps, B, C, w.seg_cnt, w.seg_start,
-                                           w.seg_tidx, w.info); }
+  int rc;
+  { KernelTimer kt__("split_count_kernel", stream);
+    split_count_kernel<<<nblk, 256, 0, stream>>>((const long long*)labels, keep_mask, HW, nbps, C,
+                                                 ignore_label, w.blk_cnt, w.info); }
+  if ((rc = check_launch("split_count_kernel"))) return rc;
+  { KernelTimer kt__("split_scan_kernel", stream);
+    split_scan_kernel<false><<<B, 1024, 0, stream>>>(w.blk_cnt, nbps, B, C, w.seg_cnt, w.seg_start,
+                                                     w.seg_tidx, w.info); }
   if ((rc = check_launch("split_scan_kernel"))) return rc;
   const int bank_blocks = 16;
-  { KernelTimer kt__("split_scatter_kernel", stream); split_scatter_kernel<false, true><<<nblk + bank_blocks, 256, 0, stream>>>(
-      (const long long*)labels, keep_mask, probs, HW, nbps, nblk, B, C, ignore_label, w.blk_cnt,
-      w.seg_start, w.pix_list, w.cls_list, w.w_list, w.cnt_list, proto_queue + (size_t)M * D,
-      (C - 1) * M, D, w.bank_n); }
+  { KernelTimer kt__("split_scatter_kernel", stream);
+    split_scatter_kernel<false, true><<<nblk + bank_blocks, 256, 0, stream>>>(
+        (const long long*)labels, keep_mask, probs, HW, nbps, nblk, B, C, ignore_label, w.blk_cnt,
+        w.seg_start, w.pix_list, w.cls_list, w.w_list, w.cnt_list, proto_queue + (size_t)M * D,
+        (C - 1) * M, D, w.bank_n); }
   if ((rc = check_launch("split_scatter_kernel"))) return rc;
-  { KernelTimer kt__("loss_sample_kernel", stream); loss_sample_kernel<<<B * C, 256, 0, stream>>>(w.seg_cnt, w.seg_start, w.seg_tidx, w.pix_list,
-                                                w.w_list, w.cnt_list, HW, C, num_anchor,
-                                                (const long long*)keep, keep_rows, seed, w.info); }
+  { KernelTimer kt__("loss_sample_kernel", stream);
+    loss_sample_kernel<<<B * C, 256, 0, stream>>>(w.seg_cnt, w.seg_start, w.seg_tidx, w.pix_list,
+                                                  w.w_list, w.cnt_list, HW, C, num_anchor,
+                                                  (const long long*)keep, keep_rows, seed, w.seg_nd,
+                                                  w.row_base, w.seg_of_t, w.info); }
   if ((rc = check_launch("loss_sample_kernel"))) return rc;
 
   RowsParams p{};
   p.feats = feats; p.bank_n = w.bank_n; p.pix_list = w.pix_list; p.cls_list = w.cls_list;
-  p.cnt_list = w.cnt_list; p.info = w.info; p.loss_part = w.loss_part; p.loss_out = loss_out;
+  p.cnt_list = w.cnt_list; p.dist_list = reinterpret_cast<const int32_t*>(w.w_list);
+  p.seg_start = w.seg_start; p.row_base = w.row_base; p.seg_of_t = w.seg_of_t; p.info = w.info;
+  p.loss_part = w.loss_part; p.grad_rows = w.grad_rows; p.loss_out = loss_out;
   p.HW = HW; p.D = D; p.M = M; p.Kc = Kc; p.A = num_anchor; p.tile_rows = tile_rows;
   p.n_tiles = n_tiles; p.temperature = temperature; p.base_temperature = base_temperature;
-  C3D_CUDA(cudaFuncSetAttribute(loss_rows_kernel<false, 1>,
-                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  { KernelTimer kt__("loss_rows_fwd_kernel", stream); loss_rows_kernel<false, 1><<<kNumSMs, kRowWarps * 32, smem, stream>>>(p); }
-  return check_launch("loss_rows_kernel<fwd>");
+  if (!need_grad) return launch_rows<false, 1>(p, smem, stream);
+  if (D <= 128) return launch_rows<true, 1>(p, smem, stream);
+  if (D <= 256) return launch_rows<true, 2>(p, smem, stream);
+  if (D <= 512) return launch_rows<true, 4>(p, smem, stream);
+  return launch_rows<true, 8>(p, smem, stream);
 }
 
-extern "C" int c3d_proto_loss_backward(
-    const float* feats, int batch, int dim, int proj_h, int proj_w, int n_classes, int sub_protos,
-    float temperature, float base_temperature, int num_anchor, void* workspace,
-    const float* grad_out, float* grad_feats, int grad_is_zeroed, void* stream_) {
+extern "C" int c3d_proto_loss_backward(int batch, int dim, int proj_h, int proj_w, int n_classes,
+                                       int sub_protos, int num_anchor, void* workspace,
+                                       const float* grad_out, float* grad_feats, int grad_is_zeroed,
+                                       void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   const int B = batch, D = dim, C = n_classes, M = sub_protos;
   const long long HWll = (long long)proj_h * proj_w;
   C3D_REQUIRE(B > 0 && B <= kMaxBatch && C >= 2 && C <= kMaxClasses, "bad batch / n_classes");
   C3D_REQUIRE(D > 0 && D % 4 == 0 && D <= 1024, "feature dim must be a multiple of 4, <= 1024");
   C3D_REQUIRE(HWll > 0 && B * HWll < (1ll << 31), "batch*H*W must be < 2^31");
-  C3D_REQUIRE(feats && workspace && grad_out && grad_feats, "null pointer argument");
+  C3D_REQUIRE(workspace && grad_out && grad_feats, "null pointer argument");
   C3D_REQUIRE((reinterpret_cast<uintptr_t>(grad_feats) & 15) == 0, "grad_feats must be 16 B aligned");
   const int HW = (int)HWll;
-  LossWs w = carve(workspace, B, C, HW, D, M);
-  const int Kc = (C - 1) * M;
-  int tile_rows, n_tiles; size_t smem;
-  C3D_REQUIRE(rows_config(D, Kc, &tile_rows, &n_tiles, &smem) == 0,
-              "bank does not fit shared memory tiling (D=%d, Kc=%d)", D, Kc);
-
-  const size_t n = (size_t)B * D * HW, n4 = n / 4;
-  if (!grad_is_zeroed) {
-    const int threads = 512;
-    long long blocks = (long long)((n4 + threads - 1) / threads);
-    const int wave = kNumSMs * 4;
-    const int grid = (int)(blocks < wave ? (blocks > 0 ? blocks : 1) : wave);
-    { KernelTimer kt__("fill_zero_kernel", stream); fill_zero_kernel<<<grid, threads, 0, stream>>>(reinterpret_cast<float4*>(grad_feats), n4,
-                                                   grad_feats + n4 * 4, (int)(n - n4 * 4)); }
-    int rc = check_launch("fill_zero_kernel");
-    if (rc) return rc;
-  }
-  RowsParams p{};
-  p.feats = feats; p.bank_n = w.bank_n; p.pix_list = w.pix_list; p.cls_list = w.cls_list;
-  p.cnt_list = w.cnt_list; p.info = w.info; p.grad_out = grad_out; p.grad_feats = grad_feats;
-  p.HW = HW; p.D = D; p.M = M; p.Kc = Kc; p.A = num_anchor; p.tile_rows = tile_rows;
-  p.n_tiles = n_tiles; p.temperature = temperature; p.base_temperature = base_temperature;
-#define LAUNCH_BWD(CH)                                                                          \
-  do {                                                                                          \
-    C3D_CUDA(cudaFuncSetAttribute(loss_rows_kernel<true, CH>,                                   \
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
-    KernelTimer kt__("loss_rows_bwd_kernel", stream);                                           \
-    loss_rows_kernel<true, CH><<<kNumSMs, kRowWarps * 32, smem, stream>>>(p);                   \
-  } while (0)
-  if (D <= 128) LAUNCH_BWD(1); else if (D <= 256) LAUNCH_BWD(2); else if (D <= 512) LAUNCH_BWD(4);
-  else LAUNCH_BWD(8);
-#undef LAUNCH_BWD
-  return check_launch("loss_rows_kernel<bwd>");
+  LossWs w = carve(workspace, B, C, HW, D, M, num_anchor);
+  int rc;
+  if (!grad_is_zeroed && (rc = launch_fill(grad_feats, (size_t)B * D * HW * 4, stream))) return rc;
+  { KernelTimer kt__("loss_grad_scatter_kernel", stream);
+    loss_grad_scatter_kernel<<<kNumSMs * 2, 256, 0, stream>>>(
+        w.grad_rows, w.pix_list, reinterpret_cast<const int32_t*>(w.w_list), w.seg_start,
+        w.row_base, w.seg_of_t, w.info, grad_out, HW, D, grad_feats); }
+  return check_launch("loss_grad_scatter_kernel");
 }
 
 extern "C" int c3d_zero_fill(void* dst, size_t nbytes, void* stream_) {
@@ -523,15 +628,7 @@ extern "C" int c3d_zero_fill(void* dst, size_t nbytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   C3D_REQUIRE(dst && (reinterpret_cast<uintptr_t>(dst) & 15) == 0, "dst must be 16 B aligned");
   C3D_REQUIRE(nbytes % 4 == 0, "nbytes must be a multiple of 4");
-  const size_t n = nbytes / 4, n4 = n / 4;
-  const int threads = 512;
-  long long blocks = (long long)((n4 + threads - 1) / threads);
-  const int wave = kNumSMs * 4;
-  const int grid = (int)(blocks < wave ? (blocks > 0 ? blocks : 1) : wave);
-  KernelTimer kt__("fill_zero_kernel", stream);
-  fill_zero_kernel<<<grid, threads, 0, stream>>>(reinterpret_cast<float4*>(dst), n4,
-                                                 reinterpret_cast<float*>(dst) + n4 * 4, (int)(n - n4 * 4));
-  return check_launch("fill_zero_kernel");
+  return launch_fill(dst, nbytes, stream);
 }
 
 extern "C" int c3d_proto_loss_info(const void* workspace, int32_t* host_info4, void* stream_) {
@@ -544,14 +641,14 @@ extern "C" int c3d_proto_loss_info(const void* workspace, int32_t* host_info4, v
 }
 
 extern "C" int c3d_proto_loss_rows(const void* workspace, int batch, int dim, int hw, int n_classes,
-                                   int sub_protos, int64_t capacity, int32_t* pix, int32_t* cls,
-                                   int32_t* cnt, void* stream_) {
+                                   int sub_protos, int num_anchor, int64_t capacity, int32_t* pix,
+                                   int32_t* cls, int32_t* cnt, void* stream_) {
   // Exports the labelled-pixel slots of the last forward (device to device):
   // pix = scan*HW + pixel, cls = class, cnt = how many anchors hit the slot.
   cudaStream_t stream = (cudaStream_t)stream_;
   C3D_REQUIRE(workspace && pix && cls && cnt, "null pointer argument");
   C3D_REQUIRE(capacity > 0 && capacity <= (int64_t)batch * hw, "bad capacity");
-  LossWs w = carve(const_cast<void*>(workspace), batch, n_classes, hw, dim, sub_protos);
+  LossWs w = carve(const_cast<void*>(workspace), batch, n_classes, hw, dim, sub_protos, num_anchor);
   const size_t n = (size_t)capacity * 4;
   C3D_CUDA(cudaMemcpyAsync(pix, w.pix_list, n, cudaMemcpyDeviceToDevice, stream));
   C3D_CUDA(cudaMemcpyAsync(cls, w.cls_list, n, cudaMemcpyDeviceToDevice, stream));

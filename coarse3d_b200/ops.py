@@ -173,8 +173,8 @@ class ProtoLossConfig(NamedTuple):
 FLAG_NO_ANCHOR, FLAG_BAD_KEEP, FLAG_KEEP_ROWS, FLAG_BAD_LABEL = 1, 2, 4, 8
 
 
-def proto_loss_workspace(batch, n_classes, hw, dim, sub_protos, device):
-    n = lib.c3d_proto_loss_workspace_bytes(batch, n_classes, hw, dim, sub_protos)
+def proto_loss_workspace(batch, n_classes, hw, dim, sub_protos, num_anchor, device):
+    n = lib.c3d_proto_loss_workspace_bytes(batch, n_classes, hw, dim, sub_protos, num_anchor)
     if n == 0:
         raise ValueError("bad prototype-loss shape")
     return torch.empty((n,), dtype=torch.uint8, device=device)
@@ -187,19 +187,20 @@ def proto_loss_info(workspace):
     return int(host[0]), int(host[1]), int(host[2])
 
 
-def proto_loss_rows(workspace, batch, dim, hw, n_classes, sub_protos):
+def proto_loss_rows(workspace, batch, dim, hw, n_classes, sub_protos, num_anchor):
     """Labelled-pixel slots of the last forward: (pix, cls, cnt) int32 tensors,
     sorted by (scan, class, pixel).  Synchronises (reads the slot count)."""
     _, n_lab, _ = proto_loss_info(workspace)
     dev = workspace.device
     pix, cls, cnt = (torch.empty((max(n_lab, 1),), dtype=torch.int32, device=dev) for _ in range(3))
     if n_lab:
-        check(lib.c3d_proto_loss_rows(_p(workspace), batch, dim, hw, n_classes, sub_protos, n_lab,
+        check(lib.c3d_proto_loss_rows(_p(workspace), batch, dim, hw, n_classes, sub_protos, num_anchor, n_lab,
                                       _p(pix), _p(cls), _p(cnt), _stream()))
     return pix[:n_lab], cls[:n_lab], cnt[:n_lab]
 
 
-def proto_loss_forward_raw(feats, probs, labels, keep_mask, queue, cfg, keep, seed, workspace, loss_out):
+def proto_loss_forward_raw(feats, probs, labels, keep_mask, queue, cfg, keep, seed, workspace, loss_out,
+                           need_grad=True):
     """c3d_proto_loss_forward on pre-validated device tensors (no autograd, no allocation)."""
     B, D, H, W = feats.shape
     C, M, _ = queue.shape
@@ -207,7 +208,7 @@ def proto_loss_forward_raw(feats, probs, labels, keep_mask, queue, cfg, keep, se
         _p(feats), _p(probs), _p(labels), _p(keep_mask), _p(queue), B, D, H, W, C, M,
         int(cfg.ignore_label), float(cfg.temperature), float(cfg.base_temperature),
         int(cfg.num_anchor), _p(keep), 0 if keep is None else keep.shape[0], int(seed),
-        _p(workspace), _p(loss_out), _stream()))
+        1 if need_grad else 0, _p(workspace), _p(loss_out), _stream()))
     return loss_out
 
 
@@ -218,14 +219,13 @@ def zero_fill(t):
     return t
 
 
-def proto_loss_backward_raw(feats, cfg, n_classes, sub_protos, workspace, grad_out, grad_feats,
+def proto_loss_backward_raw(shape, cfg, n_classes, sub_protos, workspace, grad_out, grad_feats,
                             grad_is_zeroed=False):
     """c3d_proto_loss_backward: writes the dense (B,D,H,W) gradient into grad_feats.
     grad_is_zeroed=True skips the zero fill (the caller ran `zero_fill(grad_feats)`)."""
-    B, D, H, W = feats.shape
+    B, D, H, W = shape
     check(lib.c3d_proto_loss_backward(
-        _p(feats), B, D, H, W, n_classes, sub_protos, float(cfg.temperature),
-        float(cfg.base_temperature), int(cfg.num_anchor), _p(workspace), _p(grad_out),
+        B, D, H, W, n_classes, sub_protos, int(cfg.num_anchor), _p(workspace), _p(grad_out),
         _p(grad_feats), 1 if grad_is_zeroed else 0, _stream()))
     return grad_feats
 
@@ -234,18 +234,49 @@ class _ProtoLossFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, feats, probs, labels, keep_mask, queue, cfg, keep, seed, workspace):
         loss = torch.empty((), dtype=torch.float32, device=feats.device)
-        proto_loss_forward_raw(feats, probs, labels, keep_mask, queue, cfg, keep, seed, workspace, loss)
-        ctx.save_for_backward(feats)
-        ctx.workspace, ctx.cfg, ctx.cm = workspace, cfg, (queue.shape[0], queue.shape[1])
+        need_grad = feats.requires_grad
+        proto_loss_forward_raw(feats, probs, labels, keep_mask, queue, cfg, keep, seed, workspace, loss,
+                               need_grad=need_grad)
+        ctx.workspace, ctx.cfg, ctx.cm, ctx.shape = workspace, cfg, (queue.shape[0], queue.shape[1]), feats.shape
+        ctx.prefill = None
+        if need_grad and PREFILL_GRAD:
+            # start the dense zero fill now, on a side stream, so that it overlaps
+            # whatever runs between this forward and the backward pass
+            grad = torch.empty_like(feats)
+            side = _side_stream(feats.device)
+            side.wait_stream(torch.cuda.current_stream(feats.device))
+            grad.record_stream(side)
+            with torch.cuda.stream(side):
+                zero_fill(grad)
+                ev = torch.cuda.Event()
+                ev.record(side)
+            ctx.prefill = (grad, ev)
         return loss
 
     @staticmethod
     def backward(ctx, grad_out):
-        (feats,) = ctx.saved_tensors
         C, M = ctx.cm
-        grad = torch.empty_like(feats)
-        proto_loss_backward_raw(feats, ctx.cfg, C, M, ctx.workspace, grad_out.contiguous().float(), grad)
+        grad_out = grad_out.contiguous().float()
+        if ctx.prefill is not None:
+            grad, ev = ctx.prefill
+            torch.cuda.current_stream(grad.device).wait_event(ev)
+            proto_loss_backward_raw(ctx.shape, ctx.cfg, C, M, ctx.workspace, grad_out, grad,
+                                    grad_is_zeroed=True)
+        else:
+            grad = torch.empty(ctx.shape, dtype=torch.float32, device=grad_out.device)
+            proto_loss_backward_raw(ctx.shape, ctx.cfg, C, M, ctx.workspace, grad_out, grad)
         return grad, None, None, None, None, None, None, None, None
+
+
+PREFILL_GRAD = True
+_SIDE = {}
+
+
+def _side_stream(device):
+    key = torch.device(device).index
+    if key not in _SIDE:
+        _SIDE[key] = torch.cuda.Stream(device)
+    return _SIDE[key]
 
 
 def proto_loss(feats, probs, labels, keep_mask, proto_queue, cfg: ProtoLossConfig, keep=None,
@@ -274,7 +305,7 @@ def proto_loss(feats, probs, labels, keep_mask, proto_queue, cfg: ProtoLossConfi
     if D2 != D or probs.shape != (B, C, H, W) or labels.shape != (B, H, W):
         raise ValueError("shape mismatch between feats / probs / labels / proto_queue")
     if workspace is None:
-        workspace = proto_loss_workspace(B, C, H * W, D, M, feats.device)
+        workspace = proto_loss_workspace(B, C, H * W, D, M, cfg.num_anchor, feats.device)
     if seed is None:
         seed = int(torch.randint(0, 2 ** 62, (1,)).item())
     loss = _ProtoLossFn.apply(feats, probs, labels, keep_mask, proto_queue, cfg, keep, seed, workspace)

@@ -77,7 +77,7 @@ class HotPathStep:
         self.protos_next = torch.empty_like(self.protos)
         self.ln_d = (torch.ones(dim, device=self.device), torch.zeros(dim, device=self.device))
         self.ln_c = (torch.ones(C, device=self.device), torch.zeros(C, device=self.device))
-        self.loss_ws = ops.proto_loss_workspace(batch, C, H * W, dim, sub_protos, self.device)
+        self.loss_ws = ops.proto_loss_workspace(batch, C, H * W, dim, sub_protos, num_anchor, self.device)
         self.loss = torch.zeros((), device=self.device)
         self.grad_out = torch.ones((), device=self.device)
         self.grad = torch.empty((batch, dim, H, W), device=self.device)
@@ -117,7 +117,7 @@ class HotPathStep:
         if not self.concurrent:
             pr = ops.project_batch(s.points, s.offsets, self.fov, H, W, buffers=b)
             self._loss_fwd(s, seed)
-            ops.proto_loss_backward_raw(s.feats, self.cfg, C, self.M, self.loss_ws, self.grad_out, self.grad)
+            ops.proto_loss_backward_raw(s.feats.shape, self.cfg, C, self.M, self.loss_ws, self.grad_out, self.grad)
             self._ema(s, seed)
             self._knn(s, pr, C)
             return pr
@@ -137,7 +137,7 @@ class HotPathStep:
             self.ev_ema.record(st_ema)
         self._loss_fwd(s, seed)
         cur.wait_event(self.ev_fill)
-        ops.proto_loss_backward_raw(s.feats, self.cfg, C, self.M, self.loss_ws, self.grad_out,
+        ops.proto_loss_backward_raw(s.feats.shape, self.cfg, C, self.M, self.loss_ws, self.grad_out,
                                     self.grad, grad_is_zeroed=True)
         cur.wait_event(self.ev_proj)
         cur.wait_event(self.ev_ema)

@@ -123,12 +123,17 @@ int c3d_knn_batch(
  * Duplicate anchors are evaluated once and weighted by their multiplicity.
  * The sub-prototype randperm (:142-143) is not applied (it only reorders sums).
  *
- * The workspace carries the sampled rows from forward to backward; it must
- * stay untouched in between.  ws[0..2] (int32) = {T segments, labelled pixels,
+ * With need_grad the forward also evaluates, per distinct sampled pixel, the
+ * gradient row d loss / d feats[:, pixel] for a unit upstream gradient; backward
+ * is then the dense zero fill plus D strided stores per row, scaled by grad_out.
+ * The workspace carries those rows from forward to backward; it must stay
+ * untouched in between.  ws[0..2] (int32) = {T segments, labelled pixels,
  * flags}; flags: 1 no anchor (loss is NaN; the reference crashes), 2 injected
- * index not in its segment, 4 keep_rows != T, 8 label outside [0, C).
+ * index not in its segment, 4 keep_rows != T, 8 label outside [0, C), 32 backward
+ * called after a forward without need_grad.
  */
-size_t c3d_proto_loss_workspace_bytes(int batch, int n_classes, int hw, int dim, int sub_protos);
+size_t c3d_proto_loss_workspace_bytes(int batch, int n_classes, int hw, int dim, int sub_protos,
+                                      int num_anchor);
 
 int c3d_proto_loss_forward(
     const float* feats,           /* [B, D, H, W]                                */
@@ -140,14 +145,14 @@ int c3d_proto_loss_forward(
     int ignore_label, float temperature, float base_temperature, int num_anchor,
     const int64_t* keep,          /* [keep_rows, num_anchor] or NULL             */
     int keep_rows, uint64_t seed,
+    int need_grad,                /* 1: also evaluate the gradient rows (training) */
     void* workspace,              /* c3d_proto_loss_workspace_bytes, 256 B aligned */
     float* loss_out,              /* [1]                                         */
     void* stream);
 
 int c3d_proto_loss_backward(
-    const float* feats, int batch, int dim, int proj_h, int proj_w, int n_classes,
-    int sub_protos, float temperature, float base_temperature, int num_anchor,
-    void* workspace,              /* as left by c3d_proto_loss_forward           */
+    int batch, int dim, int proj_h, int proj_w, int n_classes, int sub_protos, int num_anchor,
+    void* workspace,              /* as left by c3d_proto_loss_forward(need_grad=1) */
     const float* grad_out,        /* [1] upstream gradient of the scalar loss    */
     float* grad_feats,            /* [B, D, H, W] dense, fully written           */
     int grad_is_zeroed,           /* 1: caller already zero-filled grad_feats
@@ -164,8 +169,8 @@ int c3d_proto_loss_info(const void* workspace, int32_t* host_info4, void* stream
  * by (scan, class, pixel): pix = scan*H*W + pixel, cls = class, cnt = number of
  * anchors that hit the slot (sums to num_anchor per segment). */
 int c3d_proto_loss_rows(const void* workspace, int batch, int dim, int hw, int n_classes,
-                        int sub_protos, int64_t capacity, int32_t* pix, int32_t* cls,
-                        int32_t* cnt, void* stream);
+                        int sub_protos, int num_anchor, int64_t capacity, int32_t* pix,
+                        int32_t* cls, int32_t* cnt, void* stream);
 
 /* ---------------------------------------------------------------- a3 ----
  * EMA prototype update: the pre-step of SalsaNextProto.forward,

@@ -91,7 +91,7 @@ def test_device_sampler_is_consistent_and_reproducible(cuda_device):
     args = (output.cuda(), labels.cuda(), keep_mask.cuda(), queue[0].cuda(), cfg)
     loss, ws = ops.proto_loss(f_gpu, *args, seed=1234)
     loss.backward()
-    pix, cls, cnt = (t.cpu().long() for t in ops.proto_loss_rows(ws, B, D, H * W, C, M))
+    pix, cls, cnt = (t.cpu().long() for t in ops.proto_loss_rows(ws, B, D, H * W, C, M, A))
     lab = oloss.masked_labels(labels, keep_mask, 0).view(-1)
     assert torch.equal(lab[pix], cls) and (cls != 0).all()
     assert pix.numel() == int((lab != 0).sum())
@@ -111,9 +111,9 @@ def test_device_sampler_is_consistent_and_reproducible(cuda_device):
     assert _rel(f_gpu.grad.cpu(), f_cpu.grad) <= GRAD_RTOL
     loss2, ws2 = ops.proto_loss(feats.cuda(), *args, seed=1234)
     assert loss2.item() == loss.item()  # bitwise reproducible
-    assert torch.equal(ops.proto_loss_rows(ws2, B, D, H * W, C, M)[2].cpu().long(), cnt)
+    assert torch.equal(ops.proto_loss_rows(ws2, B, D, H * W, C, M, A)[2].cpu().long(), cnt)
     loss3, ws3 = ops.proto_loss(feats.cuda(), *args, seed=99)
-    assert not torch.equal(ops.proto_loss_rows(ws3, B, D, H * W, C, M)[2].cpu().long(), cnt)
+    assert not torch.equal(ops.proto_loss_rows(ws3, B, D, H * W, C, M, A)[2].cpu().long(), cnt)
 
 
 def test_device_sampler_follows_entropy_weights(cuda_device):
@@ -129,7 +129,7 @@ def test_device_sampler_follows_entropy_weights(cuda_device):
     cfg = ops.ProtoLossConfig(0, 0.07, 0.07, A)
     _, ws = ops.proto_loss(feats.cuda(), output.cuda(), labels.cuda(), keep_mask.cuda(), queue.cuda(),
                            cfg, seed=42)
-    pix, _, cnt = (t.cpu().long() for t in ops.proto_loss_rows(ws, B, D, H * W, C, M))
+    pix, _, cnt = (t.cpu().long() for t in ops.proto_loss_rows(ws, B, D, H * W, C, M, A))
     w = oloss.entropy_weights(output).view(-1)[pix]
     p = (w / w.sum()).double()
     freq = cnt.double() / A
@@ -184,7 +184,7 @@ def test_full_size_config2_properties(cuda_device):
         loss.backward()
         outs.append((loss.detach().clone(), f.grad))
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
-    pix, cls, cnt = ops.proto_loss_rows(ws, B, D, H * W, C, M)
+    pix, cls, cnt = ops.proto_loss_rows(ws, B, D, H * W, C, M, A)
     support = torch.zeros(B * H * W, dtype=torch.bool, device="cuda")
     support[pix[cnt > 0].long()] = True
     gsup = (outs[0][1] != 0).any(dim=1).view(-1)
