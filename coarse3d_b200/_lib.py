@@ -36,6 +36,7 @@ def _load():
         "c3d_profile_enable": (c_int, [c_char_p]),
         "c3d_profile_read": (c_int, [c_char_p, P, P]),
         "c3d_profile_names": (c_int, [P, c_int]),
+        "c3d_profile_timeline": (c_int, [P, c_int]),
         "c3d_profile_reset": (c_int, []),
         "c3d_proto_loss_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int]),
         "c3d_proto_loss_forward": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int,

@@ -87,6 +87,27 @@ extern "C" int c3d_profile_names(char* buf, int buf_len) {
   return C3D_OK;
 }
 
+extern "C" int c3d_profile_timeline(char* buf, int buf_len) {
+  // "name,start_us,end_us\n" per recorded launch, relative to the first record.
+  std::lock_guard<std::mutex> lk(c3d::g_mu);
+  if (!buf || buf_len <= 0) return C3D_INVALID_ARGUMENT;
+  std::string out;
+  if (!c3d::g_recs.empty()) {
+    cudaEvent_t base = c3d::g_recs[0].a;
+    for (auto& r : c3d::g_recs) {
+      if (cudaEventSynchronize(r.b) != cudaSuccess) continue;
+      float t0 = 0, t1 = 0;
+      if (cudaEventElapsedTime(&t0, base, r.a) != cudaSuccess) continue;
+      if (cudaEventElapsedTime(&t1, base, r.b) != cudaSuccess) continue;
+      char line[160];
+      snprintf(line, sizeof(line), "%s,%.2f,%.2f\n", r.name, t0 * 1e3f, t1 * 1e3f);
+      out += line;
+    }
+  }
+  snprintf(buf, buf_len, "%s", out.c_str());
+  return C3D_OK;
+}
+
 extern "C" int c3d_profile_reset(void) {
   std::lock_guard<std::mutex> lk(c3d::g_mu);
   for (auto& r : c3d::g_recs) { c3d::g_pool.push_back(r.a); c3d::g_pool.push_back(r.b); }

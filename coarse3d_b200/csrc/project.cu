@@ -194,7 +194,7 @@ extern "C" int c3d_project_batch(
   const bool hybrid = !(env && env[0] == '1');
   const int threads = 256;
   if (total_points > 0) {
-    int grid = wave_grid(total_points, threads, 8);
+    int grid = (int)((total_points + threads - 1) / threads);  // short CTAs (overlap)
     size_t smem = (size_t)(batch + 1) * sizeof(int32_t);
 #define LAUNCH_PP(HY, C4)                                                                   \
   project_points_kernel<HY, C4><<<grid, threads, smem, stream>>>(                           \
@@ -210,7 +210,7 @@ extern "C" int c3d_project_batch(
     if (rc) return rc;
   }
   {
-    int grid = wave_grid(total_px, threads, 8);
+    int grid = (int)((total_px + threads - 1) / threads);
     KernelTimer kt__("resolve_pixels_kernel", stream);
     if (c4)
       resolve_pixels_kernel<true><<<grid, threads, 0, stream>>>(

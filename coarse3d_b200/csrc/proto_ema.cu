@@ -211,85 +211,81 @@ __device__ __forceinline__ uint4 philox_e(uint4 ctr, uint2 key) {
   return ctr;
 }
 
-// Block-wide sum of an M-vector held per thread in acc[]; result in s_out[0..M).
-__device__ __forceinline__ void block_vec_sum(float (&acc)[kMaxSub], int M, float* s_part /*[8][32]*/,
-                                              float* s_out /*[32]*/) {
+// One CTA per class.  Q (n_c x M) lives in shared memory when it fits (the
+// weak-label regime: tens of rows per class) and in the global scratch otherwise;
+// every element-wise step is element-parallel, row sums are (sub-prototype x 8
+// partial) trees, column sums are one thread per row.  All sums have a fixed
+// order, so the assignment is bitwise reproducible.
+// mode: 0 = one_hot(argmax) (sinkhorn.py:30), 1 = injected Gumbel noise, 2 = device noise
+constexpr int kSinkSmemFloats = 24 * 1024;  // 96 KB of dynamic shared memory
+
+__device__ __forceinline__ void sink_row_sums(const float* Q, int n, int M, float* s_part, float* s_R) {
+  // s_R[m] = sum_i Q[i*M + m]; thread (p = warp, m = lane) sums rows p, p+8, ...
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-#pragma unroll
-  for (int m = 0; m < kMaxSub; ++m) {
-    if (m < M) {
-      const float v = warp_sum(acc[m]);
-      if (lane == 0) s_part[warp * kMaxSub + m] = v;
-    }
-  }
+  float a = 0.f;
+  if (lane < M) for (int i = warp; i < n; i += 8) a += Q[(size_t)i * M + lane];
+  s_part[warp * 32 + lane] = a;
   __syncthreads();
   if ((int)threadIdx.x < M) {
     float t = 0.f;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_part[w * kMaxSub + threadIdx.x];
-    s_out[threadIdx.x] = t;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += s_part[w * 32 + threadIdx.x];
+    s_R[threadIdx.x] = t;
   }
   __syncthreads();
 }
 
-// mode: 0 = one_hot(argmax) (sinkhorn.py:30), 1 = injected Gumbel noise, 2 = device noise
 __global__ void __launch_bounds__(256)
 ema_sinkhorn_kernel(const int32_t* __restrict__ seg_cnt, const int32_t* __restrict__ seg_start,
                     const int32_t* __restrict__ pix_list, int32_t* __restrict__ info, int B, int M,
                     int ignore_label, int max_rows, float* __restrict__ simq,
                     int32_t* __restrict__ sub, const float* __restrict__ gumbel, int mode,
                     unsigned long long seed, float* __restrict__ proto_target) {
+  extern __shared__ float s_dyn[];
+  __shared__ float s_part[8 * 32];
+  __shared__ float s_R[32];
+  __shared__ float s_tot;
   const int c = blockIdx.x;
   if (c == ignore_label || info[kInfoPl] > max_rows) return;
   const int start = seg_start[c * B];
   int n = 0;
   for (int b = 0; b < B; ++b) n += seg_cnt[c * B + b];
   if (n == 0) return;  // no such class (:356-357)
-  __shared__ float s_part[8 * kMaxSub];
-  __shared__ float s_vec[kMaxSub];
-  __shared__ float s_red[8];
-  float* Q = simq + (size_t)start * M;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ne = n * M;
+  const bool fits = ne + n <= kSinkSmemFloats;
+  float* G = simq + (size_t)start * M;
+  float* Q = fits ? s_dyn : G;
+  float* csum = fits ? s_dyn + ne : reinterpret_cast<float*>(sub + start);  // n floats of scratch
   const float fM = (float)M, fn = (float)n;
 
-  // Q = exp(out / eps); sum_Q (sinkhorn.py:8,13)
-  float tot = 0.f;
-  for (int i = threadIdx.x; i < n; i += blockDim.x)
-    for (int m = 0; m < M; ++m) {
-      const float q = expf(Q[(size_t)i * M + m] / 0.05f);
-      Q[(size_t)i * M + m] = q; tot += q;
-    }
-  tot = warp_sum(tot);
-  if (lane == 0) s_red[warp] = tot;
+  // Q = exp(out / eps) (sinkhorn.py:8)
+  for (int e = threadIdx.x; e < ne; e += blockDim.x) Q[e] = expf(G[e] / 0.05f);
   __syncthreads();
-  float sum_q = 0.f;
-  for (int w = 0; w < 8; ++w) sum_q += s_red[w];
-
-  // Q /= sum_Q (:14) and the first row sums (:18)
-  float acc[kMaxSub];
-#pragma unroll
-  for (int m = 0; m < kMaxSub; ++m) acc[m] = 0.f;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-#pragma unroll
-    for (int m = 0; m < kMaxSub; ++m)
-      if (m < M) { const float q = Q[(size_t)i * M + m] / sum_q; Q[(size_t)i * M + m] = q; acc[m] += q; }
-  }
-  block_vec_sum(acc, M, s_part, s_vec);
-
+  // sum_Q (:13): per-sub-prototype sums, then their sum
+  sink_row_sums(Q, n, M, s_part, s_R);
+  if (threadIdx.x == 0) { float t = 0.f; for (int m = 0; m < M; ++m) t += s_R[m]; s_tot = t; }
+  __syncthreads();
+  const float sum_q = s_tot;
+  for (int e = threadIdx.x; e < ne; e += blockDim.x) Q[e] = Q[e] / sum_q;  // (:14)
+  __syncthreads();
   for (int it = 0; it < 3; ++it) {  // sinkhorn.py:16-24
-    float rs[kMaxSub];
-#pragma unroll
-    for (int m = 0; m < kMaxSub; ++m) { rs[m] = (m < M) ? s_vec[m] : 1.f; acc[m] = 0.f; }
-    __syncthreads();
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      float q[kMaxSub]; float cs = 0.f;
-#pragma unroll
-      for (int m = 0; m < kMaxSub; ++m)
-        if (m < M) { q[m] = Q[(size_t)i * M + m] / rs[m]; q[m] = q[m] / fM; cs += q[m]; }
-#pragma unroll
-      for (int m = 0; m < kMaxSub; ++m)
-        if (m < M) { q[m] = q[m] / cs; q[m] = q[m] / fn; Q[(size_t)i * M + m] = q[m]; acc[m] += q[m]; }
+    sink_row_sums(Q, n, M, s_part, s_R);                                    // sum over rows (:18)
+    for (int e = threadIdx.x; e < ne; e += blockDim.x) {
+      float q = Q[e] / s_R[e % M];                                          // (:19)
+      Q[e] = q / fM;                                                        // (:20)
     }
-    if (it < 2) block_vec_sum(acc, M, s_part, s_vec);
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {                     // column sums (:23)
+      float t = 0.f;
+      for (int m = 0; m < M; ++m) t += Q[(size_t)i * M + m];
+      csum[i] = t;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < ne; e += blockDim.x) {
+      float q = Q[e] / csum[e / M];                                         // (:23)
+      Q[e] = q / fn;                                                        // (:24)
+    }
+    __syncthreads();
   }
 
   // Q *= B; argmax; assignment (sinkhorn.py:26-31)
@@ -472,7 +468,9 @@ extern "C" int c3d_proto_ema_accumulate(
                                 (int)smem));
   { KernelTimer kt__("ema_rows_kernel", stream); ema_rows_kernel<<<kNumSMs, kEmaWarps * 32, smem, stream>>>(p); }
   if ((rc = check_launch("ema_rows_kernel"))) return rc;
-  { KernelTimer kt__("ema_sinkhorn_kernel", stream); ema_sinkhorn_kernel<<<C, 256, 0, stream>>>(w.seg_cnt, w.seg_start, w.pix_list, w.info, B, M,
+  C3D_CUDA(cudaFuncSetAttribute(ema_sinkhorn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                kSinkSmemFloats * 4));
+  { KernelTimer kt__("ema_sinkhorn_kernel", stream); ema_sinkhorn_kernel<<<C, 256, kSinkSmemFloats * 4, stream>>>(w.seg_cnt, w.seg_start, w.pix_list, w.info, B, M,
                                              ignore_label, (int)max_rows, w.simq, w.sub, gumbel,
                                              assign_mode, seed, proto_target); }
   if ((rc = check_launch("ema_sinkhorn_kernel"))) return rc;

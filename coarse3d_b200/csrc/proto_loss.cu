@@ -449,32 +449,35 @@ loss_rows_kernel(RowsParams p) {
 }
 
 // ---------------------------------------------------------------- K6 -------
-// Low-occupancy streaming fill: 2 CTAs x 256 threads per SM, 8 independent 128-bit
-// stores per thread per iteration.  Stores are fire-and-forget, so this already
-// saturates HBM while leaving most warp slots to concurrently running kernels.
+// Streaming zero fill.  Each CTA writes one contiguous 32 KB block (256 threads x
+// 8 independent 128-bit stores) and retires: CTAs are short, so when this kernel
+// shares the GPU with the latency-bound kernels of the other chains (which run on
+// higher-priority streams) SM slots turn over within a microsecond.
+constexpr int kFillPerThread = 8;
 __global__ void __launch_bounds__(256)
 fill_zero_kernel(float4* __restrict__ dst, size_t n4, float* __restrict__ tail, int ntail) {
   const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (; i + 7 * stride < n4; i += 8 * stride) {
+  const size_t base = (size_t)blockIdx.x * (256 * kFillPerThread) + threadIdx.x;
+  if (base + (kFillPerThread - 1) * 256 < n4) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) __stcs(dst + i + j * stride, z);
+    for (int j = 0; j < kFillPerThread; ++j) __stcs(dst + base + j * 256, z);
+  } else {
+    for (int j = 0; j < kFillPerThread; ++j)
+      if (base + j * 256 < n4) __stcs(dst + base + j * 256, z);
   }
-  for (; i < n4; i += stride) __stcs(dst + i, z);
   if (blockIdx.x == 0 && (int)threadIdx.x < ntail) tail[threadIdx.x] = 0.f;
 }
 
 static int launch_fill(void* dst, size_t nbytes, cudaStream_t stream) {
   const size_t n = nbytes / 4, n4 = n / 4;
-  const int threads = 256;
-  long long blocks = (long long)((n4 + threads - 1) / threads);
-  const int wave = kNumSMs * 2;
-  const int grid = (int)(blocks < wave ? (blocks > 0 ? blocks : 1) : wave);
+  const size_t per_cta = 256 * kFillPerThread;
+  size_t grid = (n4 + per_cta - 1) / per_cta;
+  if (grid == 0) grid = 1;
+  if (grid > 0x7fffffffull) { set_error("fill too large"); return C3D_INVALID_ARGUMENT; }
   KernelTimer kt__("fill_zero_kernel", stream);
-  fill_zero_kernel<<<grid, threads, 0, stream>>>(reinterpret_cast<float4*>(dst), n4,
-                                                 reinterpret_cast<float*>(dst) + n4 * 4,
-                                                 (int)(n - n4 * 4));
+  fill_zero_kernel<<<(unsigned)grid, 256, 0, stream>>>(reinterpret_cast<float4*>(dst), n4,
+                                                       reinterpret_cast<float*>(dst) + n4 * 4,
+                                                       (int)(n - n4 * 4));
   return check_launch("fill_zero_kernel");
 }
 

@@ -419,5 +419,15 @@ class profile:
         return [s for s in buf.value.decode().split(",") if s]
 
     @staticmethod
+    def timeline():
+        buf = ctypes.create_string_buffer(1 << 20)
+        check(lib.c3d_profile_timeline(ctypes.cast(buf, ctypes.c_void_p), 1 << 20))
+        rows = []
+        for line in buf.value.decode().splitlines():
+            name, a, b = line.split(",")
+            rows.append((name, float(a), float(b)))
+        return rows
+
+    @staticmethod
     def all():
         return {n: profile.read(n) for n in profile.names()}

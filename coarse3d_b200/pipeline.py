@@ -90,7 +90,12 @@ class HotPathStep:
         self.inv_gauss = (1 - ops.gaussian_kernel(self.knn_s, self.knn_sigma)).reshape(-1).to(self.device)
         self.graphs = None
         self.concurrent = concurrent
-        self.side = [torch.cuda.Stream(self.device) for _ in range(3)]
+        # fill: lowest priority (bandwidth hog with short CTAs); projection -> KNN:
+        # normal; the latency-bound EMA chain: high.  The loss chain runs on the
+        # caller's stream.
+        self.side = [torch.cuda.Stream(self.device, priority=0),
+                     torch.cuda.Stream(self.device, priority=0),
+                     torch.cuda.Stream(self.device, priority=-1)]
         self.ev_fork, self.ev_fill, self.ev_proj, self.ev_ema = (torch.cuda.Event() for _ in range(4))
         torch.cuda.synchronize(self.device)
 

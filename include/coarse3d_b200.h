@@ -49,6 +49,8 @@ long long c3d_launch_count(void);
 int c3d_profile_enable(const char* kernel_name);
 int c3d_profile_read(const char* kernel_name, double* total_ms, long long* count);
 int c3d_profile_names(char* buf, int buf_len);
+/* "name,start_us,end_us\n" per recorded launch, relative to the first record. */
+int c3d_profile_timeline(char* buf, int buf_len);
 int c3d_profile_reset(void);
 
 /* ---------------------------------------------------------------- a1 ----

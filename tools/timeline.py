@@ -1,0 +1,20 @@
+#!/usr/bin/env python
+"""Developer tool: event timeline of one concurrent step (which kernels overlap)."""
+import os, sys
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from coarse3d_b200 import ops, synth
+from coarse3d_b200.pipeline import HotPathStep
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+step = HotPathStep(synth.KITTI, B)
+for i in range(5):
+    step.run(i, seed=i)
+torch.cuda.synchronize()
+with ops.profile("") as prof:
+    step.run(0); step.run(1)
+    torch.cuda.synchronize()
+    tl = prof.timeline()
+t0 = [r for r in tl if r[0] == "fill_zero_kernel"][1][1]
+for name, a, b in tl[len(tl) // 2:]:
+    print("%-28s %8.1f -> %8.1f  (%6.1f us)" % (name, a - t0, b - t0, b - a))
