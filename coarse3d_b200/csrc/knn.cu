@@ -30,7 +30,8 @@ knn_vote_kernel(const float* __restrict__ proj_range, const void* __restrict__ p
                 const float* __restrict__ unproj_range, const void* __restrict__ px_,
                 const void* __restrict__ py_, const int32_t* __restrict__ offsets, int batch,
                 int total, int H, int W, int knn, float cutoff, int nclasses,
-                const float* __restrict__ inv_gauss, void* __restrict__ out, int pxy64, int lab64) {
+                const float* __restrict__ inv_gauss, void* __restrict__ out, int pxy64, int lab64,
+                int vec_ok) {
   constexpr int S2 = S * S;
   constexpr int PAD = (S - 1) / 2;
   extern __shared__ int32_t s_off[];
@@ -57,22 +58,60 @@ knn_vote_kernel(const float* __restrict__ proj_range, const void* __restrict__ p
   }
   const float* img = proj_range + (size_t)b * HW;
 
-  bool colok[S];
-#pragma unroll
-  for (int dx = 0; dx < S; ++dx) { const int x = x0 + dx - PAD; colok[dx] = (x >= 0) && (x < W); }
   float d[S2];
+  if (vec_ok) {
+    // Row segments as aligned 128-bit loads: NQ quads starting at xa = (x0-PAD) & ~3
+    // cover the S wanted columns at offset o = (x0-PAD) & 3.  One warp instruction
+    // then touches <= 32 sectors for 4 columns instead of 32 sectors per column
+    // (the kernel is L2-sector bound with scalar gathers; W % 4 == 0 makes every
+    // quad lie fully inside or fully outside the row).
+    constexpr int NQ = (S + 3 + 3) / 4;
+    const int xs = x0 - PAD;
+    const int xa = xs & ~3, o = xs & 3;
 #pragma unroll
-  for (int dy = 0; dy < S; ++dy) {
-    const int y = y0 + dy - PAD;
-    const bool rowok = (y >= 0) && (y < H);
-    const float* rowp = img + y * W + (x0 - PAD);
+    for (int dy = 0; dy < S; ++dy) {
+      const int y = y0 + dy - PAD;
+      const bool rowok = (y >= 0) && (y < H);
+      const float* rowp = img + y * W + xa;
+      float w[NQ * 4 + 4];
 #pragma unroll
-    for (int dx = 0; dx < S; ++dx) {
-      float v = 0.0f;  // F.unfold zero padding (knn.py:79-81)
-      if (rowok && colok[dx]) v = __ldg(rowp + dx);
-      if (v < 0.0f) v = CUDART_INF_F;              // knn.py:90
-      if (dy == PAD && dx == PAD) v = r;           // knn.py:93-94
-      d[dy * S + dx] = fabsf(v - r) * s_w[dy * S + dx];  // knn.py:97,107
+      for (int q = 0; q < NQ; ++q) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);  // F.unfold zero padding (knn.py:79-81)
+        const int xq = xa + 4 * q;
+        if (rowok && xq >= 0 && xq < W) v = __ldg(reinterpret_cast<const float4*>(rowp + 4 * q));
+        w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
+      }
+#pragma unroll
+      for (int i = NQ * 4; i < NQ * 4 + 4; ++i) w[i] = 0.f;
+      // v[dx] = w[o + dx], o in 0..3: two-level select
+      float a[NQ * 4 + 2];
+#pragma unroll
+      for (int i = 0; i < NQ * 4 + 2; ++i) a[i] = (o & 1) ? w[i + 1] : w[i];
+#pragma unroll
+      for (int dx = 0; dx < S; ++dx) {
+        float v = (o & 2) ? a[dx + 2] : a[dx];
+        if (v < 0.0f) v = CUDART_INF_F;              // knn.py:90
+        if (dy == PAD && dx == PAD) v = r;           // knn.py:93-94
+        d[dy * S + dx] = fabsf(v - r) * s_w[dy * S + dx];  // knn.py:97,107
+      }
+    }
+  } else {
+    bool colok[S];
+#pragma unroll
+    for (int dx = 0; dx < S; ++dx) { const int x = x0 + dx - PAD; colok[dx] = (x >= 0) && (x < W); }
+#pragma unroll
+    for (int dy = 0; dy < S; ++dy) {
+      const int y = y0 + dy - PAD;
+      const bool rowok = (y >= 0) && (y < H);
+      const float* rowp = img + y * W + (x0 - PAD);
+#pragma unroll
+      for (int dx = 0; dx < S; ++dx) {
+        float v = 0.0f;  // F.unfold zero padding (knn.py:79-81)
+        if (rowok && colok[dx]) v = __ldg(rowp + dx);
+        if (v < 0.0f) v = CUDART_INF_F;              // knn.py:90
+        if (dy == PAD && dx == PAD) v = r;           // knn.py:93-94
+        d[dy * S + dx] = fabsf(v - r) * s_w[dy * S + dx];  // knn.py:97,107
+      }
     }
   }
 
@@ -179,7 +218,8 @@ static int launch_knn_sk(const float* proj_range, const void* proj_argmax, const
   KernelTimer timer("knn_vote_kernel", stream);
   knn_vote_kernel<S, KT><<<grid, threads, smem, stream>>>(
       proj_range, proj_argmax, unproj_range, px, py, offsets, batch, total, H, W, knn, cutoff,
-      nclasses, inv_gauss, out, pxy64, lab64);
+      nclasses, inv_gauss, out, pxy64, lab64,
+      (W % 4 == 0 && (reinterpret_cast<uintptr_t>(proj_range) & 15) == 0) ? 1 : 0);
   return check_launch("knn_vote_kernel");
 }
 

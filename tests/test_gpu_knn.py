@@ -94,3 +94,26 @@ def test_uniform_labels_are_a_fixed_point(cuda_device):
         out = ops.knn_batch(pr.proj_range, am, pr.uproj_depth, pr.uproj_x_idx, pr.uproj_y_idx, O,
                             5, 5, 1.0, 1.0, shp.n_classes)
         assert (out == c).all()
+
+
+@pytest.mark.parametrize("W", [101, 64, 7])
+@pytest.mark.parametrize("k,s", [(5, 5), (3, 3), (12, 5), (9, 3), (20, 7), (5, 9)])
+def test_random_images_any_width(cuda_device, W, k, s):
+    """Widths that are not a multiple of 4 take the scalar-gather path; tiny images put
+    every window across the border; large k exercises the generic top-k capacity."""
+    from coarse3d_b200 import ops
+    rng = np.random.default_rng(W * 100 + k)
+    H, P, C = 9, 3000, 11
+    proj_range = rng.uniform(1, 30, (H, W)).astype(np.float32)
+    proj_range = (np.round(proj_range * 2) / 2).astype(np.float32)      # ties
+    proj_range[rng.random((H, W)) < 0.3] = -1.0                          # empty pixels
+    argmax = rng.integers(0, C, (H, W))
+    px, py = rng.integers(0, W, P), rng.integers(0, H, P)
+    ur = (np.round(rng.uniform(1, 30, P) * 2) / 2).astype(np.float32)
+    for cutoff in (1.0, 0.0):
+        want = oknn.knn_vote(proj_range, ur, argmax, px, py, k, s, 1.0, cutoff, C)
+        out = ops.knn_batch(torch.from_numpy(proj_range[None]).cuda(), torch.from_numpy(argmax[None]).cuda(),
+                            torch.from_numpy(ur).cuda(), torch.from_numpy(px).cuda(),
+                            torch.from_numpy(py).cuda(), torch.tensor([0, P], dtype=torch.int32).cuda(),
+                            k, s, 1.0, cutoff, C)
+        assert np.array_equal(out.cpu().numpy(), want), int((out.cpu().numpy() != want).sum())
