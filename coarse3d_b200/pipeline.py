@@ -90,13 +90,15 @@ class HotPathStep:
         self.inv_gauss = (1 - ops.gaussian_kernel(self.knn_s, self.knn_sigma)).reshape(-1).to(self.device)
         self.graphs = None
         self.concurrent = concurrent
-        # fill: lowest priority (bandwidth hog with short CTAs); projection -> KNN:
-        # normal; the latency-bound EMA chain: high.  The loss chain runs on the
-        # caller's stream.
-        self.side = [torch.cuda.Stream(self.device, priority=0),
-                     torch.cuda.Stream(self.device, priority=0),
-                     torch.cuda.Stream(self.device, priority=-1)]
-        self.ev_fork, self.ev_fill, self.ev_proj, self.ev_ema = (torch.cuda.Event() for _ in range(4))
+        # Priorities: the latency-bound chains (loss, EMA) high, so their small CTAs
+        # are placed first whenever the short CTAs of the fill / KNN retire.
+        lo, hi = 0, -1
+        self.side = [torch.cuda.Stream(self.device, priority=lo),   # fill
+                     torch.cuda.Stream(self.device, priority=lo),   # projection -> KNN
+                     torch.cuda.Stream(self.device, priority=hi),   # EMA chain
+                     torch.cuda.Stream(self.device, priority=hi)]   # loss chain
+        (self.ev_fork, self.ev_fill, self.ev_proj, self.ev_ema, self.ev_loss,
+         self.ev_resolved) = (torch.cuda.Event() for _ in range(6))
         torch.cuda.synchronize(self.device)
 
     # bytes the reference dtypes move per step
@@ -126,26 +128,32 @@ class HotPathStep:
             self._ema(s, seed)
             self._knn(s, pr, C)
             return pr
-        st_fill, st_proj, st_ema = self.side
+        st_fill, st_proj, st_ema, st_loss = self.side
         self.ev_fork.record(cur)
         for st in self.side:
             st.wait_event(self.ev_fork)
-        with torch.cuda.stream(st_fill):
-            ops.zero_fill(self.grad)
-            self.ev_fill.record(st_fill)
         with torch.cuda.stream(st_proj):
             pr = ops.project_batch(s.points, s.offsets, self.fov, H, W, buffers=b)
-            self._knn(s, pr, C)
+            self.ev_resolved.record(st_proj)
+            self._knn(s, pr, C)          # ALU-bound: pairs with the bandwidth-bound fill
             self.ev_proj.record(st_proj)
+        with torch.cuda.stream(st_fill):
+            # the fill saturates HBM; start it once the projection's atomics and
+            # scatter/gather traffic are through, then it overlaps the KNN vote
+            st_fill.wait_event(self.ev_resolved)
+            ops.zero_fill(self.grad)
+            self.ev_fill.record(st_fill)
         with torch.cuda.stream(st_ema):
             self._ema(s, seed)
             self.ev_ema.record(st_ema)
-        self._loss_fwd(s, seed)
-        cur.wait_event(self.ev_fill)
-        ops.proto_loss_backward_raw(s.feats.shape, self.cfg, C, self.M, self.loss_ws, self.grad_out,
-                                    self.grad, grad_is_zeroed=True)
-        cur.wait_event(self.ev_proj)
-        cur.wait_event(self.ev_ema)
+        with torch.cuda.stream(st_loss):
+            self._loss_fwd(s, seed)
+            st_loss.wait_event(self.ev_fill)
+            ops.proto_loss_backward_raw(s.feats.shape, self.cfg, C, self.M, self.loss_ws, self.grad_out,
+                                        self.grad, grad_is_zeroed=True)
+            self.ev_loss.record(st_loss)
+        for ev in (self.ev_proj, self.ev_ema, self.ev_loss):
+            cur.wait_event(ev)
         return pr
 
     def _loss_fwd(self, s, seed):
