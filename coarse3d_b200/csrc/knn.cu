@@ -24,12 +24,8 @@
 namespace c3d {
 
 // KT >= knn is the compile-time capacity of the top-k network (KT == knn for knn <= 8).
-// 768-thread CTAs: at ~58 registers per thread exactly one CTA fits per SM, which
-// caps the kernel at 24 warps / 44 k registers per SM and leaves room for the
-// concurrently running fill (bandwidth-bound) and loss / EMA kernels.
-constexpr int kKnnThreads = 768;
 template <int S, int KT>
-__global__ void __launch_bounds__(kKnnThreads)
+__global__ void __launch_bounds__(256)
 knn_vote_kernel(const float* __restrict__ proj_range, const void* __restrict__ proj_argmax,
                 const float* __restrict__ unproj_range, const void* __restrict__ px_,
                 const void* __restrict__ py_, const int32_t* __restrict__ offsets, int batch,
@@ -216,8 +212,8 @@ static int launch_knn_sk(const float* proj_range, const void* proj_argmax, const
                          const void* px, const void* py, const int32_t* offsets, int batch, int total,
                          int H, int W, int knn, float cutoff, int nclasses, const float* inv_gauss,
                          void* out, int pxy64, int lab64, cudaStream_t stream) {
-  const int threads = kKnnThreads;
-  const int grid = (total + threads - 1) / threads;
+  const int threads = 256;
+  const int grid = (total + threads - 1) / threads;  // short CTAs: SM slots free up quickly
   const size_t smem = (size_t)(batch + 1) * sizeof(int32_t);
   KernelTimer timer("knn_vote_kernel", stream);
   knn_vote_kernel<S, KT><<<grid, threads, smem, stream>>>(

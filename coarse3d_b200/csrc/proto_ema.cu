@@ -26,7 +26,7 @@
 
 namespace c3d {
 
-constexpr int kEmaWarps = 4;
+constexpr int kEmaWarps = 8;
 constexpr int kMaxSub = 32;  // sub-prototypes per class handled in registers
 enum EmaFlag { kEmaNoRows = 1, kEmaBadLabel = 8, kEmaOverflow = 16 };
 

@@ -31,7 +31,7 @@
 
 namespace c3d {
 
-constexpr int kRowWarps = 4;       // rows processed concurrently per loss_rows CTA
+constexpr int kRowWarps = 8;       // rows processed concurrently per loss_rows CTA
 
 enum LossFlag { kFlagNoAnchor = 1, kFlagBadKeep = 2, kFlagKeepRows = 4, kFlagNoGradRows = 32 };
 // info[] slots beyond SplitInfo
@@ -449,40 +449,35 @@ loss_rows_kernel(RowsParams p) {
 }
 
 // ---------------------------------------------------------------- K6 -------
-// Streaming zero fill.  One persistent 128-thread CTA per SM, 16 independent 128-bit
-// stores per thread per iteration: stores are fire-and-forget, so four warps per SM
-// already saturate HBM (measured 6.6 TB/s), and the tiny footprint (2 k registers,
-// no shared memory) lets the fill co-reside with the ALU-bound KNN vote and the
-// latency-bound loss / EMA kernels instead of evicting them from the SMs.
-constexpr int kFillThreads = 128;
-constexpr int kFillUnroll = 16;
-__global__ void __launch_bounds__(kFillThreads)
+// Streaming zero fill.  Each CTA writes one contiguous 32 KB block (256 threads x
+// 8 independent 128-bit stores) and retires: CTAs are short, so when this kernel
+// shares the GPU with the latency-bound kernels of the other chains (which run on
+// higher-priority streams) SM slots turn over within a microsecond.
+constexpr int kFillPerThread = 8;
+__global__ void __launch_bounds__(256)
 fill_zero_kernel(float4* __restrict__ dst, size_t n4, float* __restrict__ tail, int ntail) {
   const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-  const size_t chunk = (size_t)kFillThreads * kFillUnroll;  // float4 per CTA iteration
-  for (size_t base = (size_t)blockIdx.x * chunk; base < n4; base += (size_t)gridDim.x * chunk) {
-    const size_t i = base + threadIdx.x;
-    if (base + chunk <= n4) {
+  const size_t base = (size_t)blockIdx.x * (256 * kFillPerThread) + threadIdx.x;
+  if (base + (kFillPerThread - 1) * 256 < n4) {
 #pragma unroll
-      for (int j = 0; j < kFillUnroll; ++j) __stcs(dst + i + j * kFillThreads, z);
-    } else {
-      for (int j = 0; j < kFillUnroll; ++j)
-        if (i + j * kFillThreads < n4) __stcs(dst + i + j * kFillThreads, z);
-    }
+    for (int j = 0; j < kFillPerThread; ++j) __stcs(dst + base + j * 256, z);
+  } else {
+    for (int j = 0; j < kFillPerThread; ++j)
+      if (base + j * 256 < n4) __stcs(dst + base + j * 256, z);
   }
   if (blockIdx.x == 0 && (int)threadIdx.x < ntail) tail[threadIdx.x] = 0.f;
 }
 
 static int launch_fill(void* dst, size_t nbytes, cudaStream_t stream) {
   const size_t n = nbytes / 4, n4 = n / 4;
-  const size_t chunk = (size_t)kFillThreads * kFillUnroll;
-  size_t blocks = (n4 + chunk - 1) / chunk;
-  if (blocks == 0) blocks = 1;
-  const int grid = (int)(blocks < (size_t)kNumSMs ? blocks : (size_t)kNumSMs);
+  const size_t per_cta = 256 * kFillPerThread;
+  size_t grid = (n4 + per_cta - 1) / per_cta;
+  if (grid == 0) grid = 1;
+  if (grid > 0x7fffffffull) { set_error("fill too large"); return C3D_INVALID_ARGUMENT; }
   KernelTimer kt__("fill_zero_kernel", stream);
-  fill_zero_kernel<<<grid, kFillThreads, 0, stream>>>(reinterpret_cast<float4*>(dst), n4,
-                                                      reinterpret_cast<float*>(dst) + n4 * 4,
-                                                      (int)(n - n4 * 4));
+  fill_zero_kernel<<<(unsigned)grid, 256, 0, stream>>>(reinterpret_cast<float4*>(dst), n4,
+                                                       reinterpret_cast<float*>(dst) + n4 * 4,
+                                                       (int)(n - n4 * 4));
   return check_launch("fill_zero_kernel");
 }
 

@@ -93,7 +93,7 @@ class HotPathStep:
         # Priorities: the latency-bound chains (loss, EMA) high, so their small CTAs
         # are placed first whenever the short CTAs of the fill / KNN retire.
         lo, hi = 0, -1
-        self.side = [torch.cuda.Stream(self.device, priority=hi),   # fill: 1 small CTA per SM, placed first
+        self.side = [torch.cuda.Stream(self.device, priority=lo),   # fill
                      torch.cuda.Stream(self.device, priority=lo),   # projection -> KNN
                      torch.cuda.Stream(self.device, priority=hi),   # EMA chain
                      torch.cuda.Stream(self.device, priority=hi)]   # loss chain
