@@ -134,13 +134,15 @@ class HotPathStep:
             st.wait_event(self.ev_fork)
         with torch.cuda.stream(st_proj):
             pr = ops.project_batch(s.points, s.offsets, self.fov, H, W, buffers=b)
-            self.ev_resolved.record(st_proj)
-            self._knn(s, pr, C)          # ALU-bound: pairs with the bandwidth-bound fill
+            self._knn(s, pr, C)
             self.ev_proj.record(st_proj)
         with torch.cuda.stream(st_fill):
-            # the fill saturates HBM; start it once the projection's atomics and
-            # scatter/gather traffic are through, then it overlaps the KNN vote
-            st_fill.wait_event(self.ev_resolved)
+            # The fill saturates HBM and streams 512 MB through L2; anything that
+            # depends on L2-resident data (the z-buffer atomics, the KNN window
+            # gathers) slows down more than the overlap gains (profiles/
+            # timeline_r1.txt), so it starts after the projection -> KNN chain and
+            # overlaps the latency-bound loss / EMA kernels instead.
+            st_fill.wait_event(self.ev_proj)
             ops.zero_fill(self.grad)
             self.ev_fill.record(st_fill)
         with torch.cuda.stream(st_ema):
