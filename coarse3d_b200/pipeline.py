@@ -134,15 +134,15 @@ class HotPathStep:
             st.wait_event(self.ev_fork)
         with torch.cuda.stream(st_proj):
             pr = ops.project_batch(s.points, s.offsets, self.fov, H, W, buffers=b)
-            self._knn(s, pr, C)
+            self.ev_resolved.record(st_proj)
+            self._knn(s, pr, C)          # ALU-bound: pairs with the bandwidth-bound fill
             self.ev_proj.record(st_proj)
         with torch.cuda.stream(st_fill):
-            # The fill saturates HBM and streams 512 MB through L2; anything that
-            # depends on L2-resident data (the z-buffer atomics, the KNN window
-            # gathers) slows down more than the overlap gains (profiles/
-            # timeline_r1.txt), so it starts after the projection -> KNN chain and
-            # overlaps the latency-bound loss / EMA kernels instead.
-            st_fill.wait_event(self.ev_proj)
+            # The fill saturates HBM and streams 512 MB through L2, which slows the
+            # z-buffer atomics and scatter/gather of the projection far more than the
+            # overlap gains (profiles/timeline_r1.txt); it therefore starts after the
+            # projection and overlaps the ALU-bound KNN vote and the loss / EMA chains.
+            st_fill.wait_event(self.ev_resolved)
             ops.zero_fill(self.grad)
             self.ev_fill.record(st_fill)
         with torch.cuda.stream(st_ema):
