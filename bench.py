@@ -312,8 +312,15 @@ def main():
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
+        # Tear-down: NCCL communicators referenced by captured CUDA graphs can make
+        # destroy_process_group() block; all results are out, so drop the graphs,
+        # synchronise with the peers and leave without the collective tear-down.
+        step.graphs = None
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize(dev)
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def run_e2e(args, step, dev, world, K):
