@@ -135,21 +135,42 @@ knn_vote_kernel(const float* __restrict__ proj_range, const void* __restrict__ p
     for (int i = 0; i < KT; ++i) if (i == knn - 1) t = top[i];
   }
 
-  // 2. selected = (d < t) or the first `need` slots with d == t; 3. voters within cut-off
-  int n_lt = 0;
-#pragma unroll
-  for (int s = 0; s < S2; ++s) n_lt += (d[s] < t) ? 1 : 0;
-  int need = knn - n_lt;
+  // 2./3. voters = selected slots within the cut-off.
+  // selected = {d < t} plus the first (k - #{d < t}) slots with d == t.  If the cut-off
+  // is below t, every voter has d <= cutoff < t and is selected; otherwise, when exactly k
+  // slots have d <= t (no tie reaches past the k-th), selected = {d <= t}.  Both cases
+  // are a single compare per slot; only a real tie at the threshold takes the slow path.
+  const bool has_cut = cutoff > 0.0f;                       // knn.py:124-127
+  const float tv = (has_cut && cutoff < t) ? cutoff : t;
+  int n_le = 0;
   unsigned voters = 0;
 #pragma unroll
   for (int s = 0; s < S2; ++s) {
-    const bool lt = d[s] < t;
-    const bool eq = d[s] == t;
-    const bool take = lt || (eq && need > 0);
-    if (eq) --need;
-    const bool in_cut = !(cutoff > 0.0f) || !(d[s] > cutoff);  // knn.py:124-127
-    if (take && in_cut) voters |= (S2 <= 32) ? (1u << s) : 0u;
-    if (S2 > 32 && take && in_cut) d[s] = -1.0f;  // large windows: mark in place
+    const bool le = d[s] <= tv;
+    n_le += le ? 1 : 0;
+    if (S2 <= 32) voters |= le ? (1u << s) : 0u;
+  }
+  const bool simple = (has_cut && cutoff < t) || (n_le == knn);
+  if (S2 > 32 && simple) {
+#pragma unroll
+    for (int s = 0; s < S2; ++s) if (d[s] <= tv) d[s] = -1.0f;  // large windows: mark in place
+  }
+  if (!simple) {
+    int n_lt = 0;
+#pragma unroll
+    for (int s = 0; s < S2; ++s) n_lt += (d[s] < t) ? 1 : 0;
+    int need = knn - n_lt;
+    voters = 0;
+#pragma unroll
+    for (int s = 0; s < S2; ++s) {
+      const bool lt = d[s] < t;
+      const bool eq = d[s] == t;
+      const bool take = lt || (eq && need > 0);
+      if (eq) --need;
+      const bool in_cut = !has_cut || !(d[s] > cutoff);
+      if (take && in_cut) voters |= (S2 <= 32) ? (1u << s) : 0u;
+      if (S2 > 32 && take && in_cut) d[s] = -1.0f;
+    }
   }
 
   // class of each voter (zero padding => class 0, which can never win)

@@ -38,6 +38,7 @@ struct ProjParams {
   float abs_left, fov_hori, abs_down, fov_vert;  // float32-rounded Python floats
   float wf, hf, wmax, hmax;
   float tol_x, tol_y;  // hybrid guard bands, in pixels
+  float sx, sy;        // fast path: W / fov_hori, H / fov_vert
   int H, W;
 };
 
@@ -46,18 +47,20 @@ __device__ __forceinline__ void pixel_of(float x, float y, float q, const ProjPa
                                          int& px, int& py, bool& nan) {
   float yaw, pitch, fx, fy;
   if (kHybrid) {
+    // fast estimate: <= 2 ulp transcendentals and one multiply by a pre-divided
+    // scale instead of the reference's divide-then-multiply (error inside the guard band)
     yaw = -atan2f(y, x);
     pitch = asinf(q);
-    fx = ((yaw + p.abs_left) / p.fov_hori) * p.wf;
-    fy = (1.0f - (pitch + p.abs_down) / p.fov_vert) * p.hf;
+    fx = (yaw + p.abs_left) * p.sx;
+    fy = p.hf - (pitch + p.abs_down) * p.sy;
     // !(a > b) also catches NaN
     bool near_x = !(fabsf(fx - rintf(fx)) > p.tol_x);
     bool near_y = !(fabsf(fy - rintf(fy)) > p.tol_y);
-    if (near_x) {
+    if (near_x) {  // exact chain (projection.py:62-64,73): correctly rounded angle, IEEE ops
       yaw = -(float)atan2((double)y, (double)x);
       fx = ((yaw + p.abs_left) / p.fov_hori) * p.wf;
     }
-    if (near_y) {
+    if (near_y) {  // projection.py:66-68,74
       pitch = (float)asin((double)q);
       fy = (1.0f - (pitch + p.abs_down) / p.fov_vert) * p.hf;
     }
@@ -81,64 +84,82 @@ project_points_kernel(const float* __restrict__ points, int c_in,
                       float* __restrict__ udepth, unsigned long long* __restrict__ zbuf,
                       int32_t* __restrict__ flags) {
   extern __shared__ int32_t s_off[];
+  __shared__ int s_b0;
   for (int i = threadIdx.x; i <= batch; i += blockDim.x) s_off[i] = offsets[i];
   __syncthreads();
+  if (threadIdx.x == 0) s_b0 = scan_of(s_off, batch, min((int)(blockIdx.x * blockDim.x), total - 1));
+  __syncthreads();
   const int HW = p.H * p.W;
-  bool any_nan = false;
-  for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < total; g += gridDim.x * blockDim.x) {
-    float x, y, z;
-    if (kC4) {
-      float4 v = __ldg(reinterpret_cast<const float4*>(points) + g);  // keep in L2 for resolve
-      x = v.x; y = v.y; z = v.z;
-    } else {
-      const float* r = points + (size_t)g * c_in;
-      x = r[0]; y = r[1]; z = r[2];
-    }
-    float depth = depth_override ? depth_override[g] : sqrtf((x * x + y * y) + z * z);
-    float q = z / depth;
-    int px, py; bool nan;
-    pixel_of<kHybrid>(x, y, q, p, px, py, nan);
-    any_nan |= nan;
-    upx[g] = px; upy[g] = py; udepth[g] = depth;
-    int b = scan_of(s_off, batch, g);
-    unsigned long long key =
-        ((unsigned long long)depth_key(depth) << 32) | (uint32_t)(g - s_off[b]);
-    atomicMin(zbuf + (size_t)b * HW + py * p.W + px, key);
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= total) return;
+  int b = s_b0;
+  while (g >= s_off[b + 1]) ++b;  // a CTA spans at most a few scans
+  float x, y, z;
+  if (kC4) {
+    float4 v = __ldg(reinterpret_cast<const float4*>(points) + g);  // keep in L2 for resolve
+    x = v.x; y = v.y; z = v.z;
+  } else {
+    const float* r = points + (size_t)g * c_in;
+    x = r[0]; y = r[1]; z = r[2];
   }
-  if (any_nan) atomicOr(flags, 1);
+  float depth = depth_override ? depth_override[g] : sqrtf((x * x + y * y) + z * z);
+  float q = z / depth;
+  int px, py; bool nan;
+  pixel_of<kHybrid>(x, y, q, p, px, py, nan);
+  upx[g] = px; upy[g] = py; udepth[g] = depth;
+  unsigned long long key =
+      ((unsigned long long)depth_key(depth) << 32) | (uint32_t)(g - s_off[b]);
+  atomicMin(zbuf + (size_t)b * HW + py * p.W + px, key);
+  if (nan) atomicOr(flags, 1);
 }
 
+// Two pixels per thread (two independent key -> gather -> store chains in flight).
+// Every z-buffer entry is reset to "empty" after it is read, so the workspace is
+// left clean for the next call and needs no memset.
 template <bool kC4>
 __global__ void __launch_bounds__(256)
 resolve_pixels_kernel(const float* __restrict__ points, int c_in,
                       const int32_t* __restrict__ offsets, int HW, long long total_px,
-                      const unsigned long long* __restrict__ zbuf,
+                      unsigned long long* __restrict__ zbuf,
                       float* __restrict__ proj_range, float* __restrict__ proj_pc,
                       int32_t* __restrict__ proj_idx, int32_t* __restrict__ proj_mask) {
-  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < total_px;
-       q += (long long)gridDim.x * blockDim.x) {
-    unsigned long long key = __ldcs(zbuf + q);
-    if (key == ~0ull) {
-      proj_range[q] = -1.0f; proj_idx[q] = -1; proj_mask[q] = 0;
-      if (kC4) {
-        st_stream(reinterpret_cast<float4*>(proj_pc) + q, make_float4(-1.f, -1.f, -1.f, -1.f));
-      } else {
-        for (int c = 0; c < c_in; ++c) proj_pc[q * c_in + c] = -1.0f;
-      }
-    } else {
-      int idx = (int)(uint32_t)key;
-      int b = (int)(q / HW);
-      size_t row = (size_t)offsets[b] + idx;
-      proj_range[q] = key_depth((uint32_t)(key >> 32));
-      proj_idx[q] = idx;
-      proj_mask[q] = idx > 0;  // projection.py:113
-      if (kC4) {
-        float4 v = __ldg(reinterpret_cast<const float4*>(points) + row);
-        st_stream(reinterpret_cast<float4*>(proj_pc) + q, v);
-      } else {
-        for (int c = 0; c < c_in; ++c) proj_pc[q * c_in + c] = points[row * c_in + c];
-      }
+  const long long q0 = ((long long)blockIdx.x * blockDim.x) * 2 + threadIdx.x;
+  unsigned long long key[2];
+  bool in[2];
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const long long q = q0 + j * 256;
+    in[j] = q < total_px;
+    key[j] = in[j] ? __ldcs(zbuf + q) : ~0ull;
+  }
+  float4 pt[2];
+  size_t row[2];
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    pt[j] = make_float4(-1.f, -1.f, -1.f, -1.f);
+    row[j] = 0;
+    if (key[j] != ~0ull) {
+      const long long q = q0 + j * 256;
+      row[j] = (size_t)__ldg(offsets + (int)(q / HW)) + (uint32_t)key[j];
+      if (kC4) pt[j] = __ldg(reinterpret_cast<const float4*>(points) + row[j]);
     }
+  }
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    if (!in[j]) continue;
+    const long long q = q0 + j * 256;
+    const bool valid = key[j] != ~0ull;
+    const int idx = valid ? (int)(uint32_t)key[j] : -1;
+    proj_range[q] = valid ? key_depth((uint32_t)(key[j] >> 32)) : -1.0f;
+    proj_idx[q] = idx;
+    proj_mask[q] = idx > 0;  // projection.py:113
+    if (kC4) {
+      st_stream(reinterpret_cast<float4*>(proj_pc) + q, pt[j]);
+    } else {
+      for (int c = 0; c < c_in; ++c)
+        proj_pc[q * c_in + c] = valid ? points[row[j] * c_in + c] : -1.0f;
+    }
+    if (valid) zbuf[q] = ~0ull;
   }
 }
 
@@ -156,7 +177,8 @@ extern "C" int c3d_project_batch(
     const float* depth_override, double abs_fov_left, double fov_hori, double abs_fov_down,
     double fov_vert, int proj_h, int proj_w, float* proj_range, float* proj_pointcloud,
     int32_t* proj_idx, int32_t* proj_mask, int32_t* uproj_x_idx, int32_t* uproj_y_idx,
-    float* uproj_depth, void* workspace, int32_t* status_flags, void* stream_) {
+    float* uproj_depth, void* workspace, int workspace_is_clean, int32_t* status_flags,
+    void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   C3D_REQUIRE(batch > 0 && batch <= kMaxBatch, "batch must be in [1, %d], got %d", kMaxBatch, batch);
   C3D_REQUIRE(c_in >= 3, "c_in must be >= 3, got %d", c_in);
@@ -180,10 +202,12 @@ extern "C" int c3d_project_batch(
   // |pitch| <= pi/2, then add / divide / multiply roundings.
   p.tol_x = p.wf * 1.0e-6f;
   p.tol_y = p.hf * (2.0e-6f / p.fov_vert + 1.0e-6f);
+  p.sx = p.wf / p.fov_hori;
+  p.sy = p.hf / p.fov_vert;
 
   const long long total_px = (long long)batch * proj_h * proj_w;
   auto* zbuf = reinterpret_cast<unsigned long long*>(workspace);
-  {
+  if (!workspace_is_clean) {
     KernelTimer kt__("zbuf_memset", stream);
     C3D_CUDA(cudaMemsetAsync(zbuf, 0xFF, (size_t)total_px * sizeof(unsigned long long), stream));
   }
@@ -210,7 +234,7 @@ extern "C" int c3d_project_batch(
     if (rc) return rc;
   }
   {
-    int grid = (int)((total_px + threads - 1) / threads);
+    int grid = (int)((total_px + 2 * threads - 1) / (2 * threads));
     KernelTimer kt__("resolve_pixels_kernel", stream);
     if (c4)
       resolve_pixels_kernel<true><<<grid, threads, 0, stream>>>(

@@ -78,6 +78,7 @@ class ProjectionBuffers:
         self.flags = torch.zeros((1,), dtype=i32, device=device)
         nbytes = lib.c3d_project_workspace_bytes(batch, proj_h, proj_w)
         self.workspace = torch.empty((nbytes,), dtype=torch.uint8, device=device)
+        self.clean = False  # True once a call has left the z-buffer reset
 
 
 def project_batch(points, offsets, fov: Fov, proj_h, proj_w, depth=None,
@@ -105,8 +106,9 @@ def project_batch(points, offsets, fov: Fov, proj_h, proj_w, depth=None,
         _p(points), c_in, _p(offsets), batch, total, _p(depth),
         fov.abs_fov_left, fov.fov_hori, fov.abs_fov_down, fov.fov_vert, proj_h, proj_w,
         _p(b.proj_range), _p(b.proj_pointcloud), _p(b.proj_idx), _p(b.proj_mask),
-        _p(b.uproj_x_idx), _p(b.uproj_y_idx), _p(b.uproj_depth), _p(b.workspace), _p(b.flags),
-        _stream()))
+        _p(b.uproj_x_idx), _p(b.uproj_y_idx), _p(b.uproj_depth), _p(b.workspace),
+        1 if b.clean else 0, _p(b.flags), _stream()))
+    b.clean = True
     return Projection(b.proj_pointcloud, b.proj_range, b.proj_idx, b.proj_mask,
                       b.uproj_x_idx, b.uproj_y_idx, b.uproj_depth, b.flags)
 

@@ -84,6 +84,9 @@ int c3d_project_batch(
     int32_t* uproj_y_idx,         /* [total_points]                              */
     float* uproj_depth,           /* [total_points]                              */
     void* workspace,              /* c3d_project_workspace_bytes                 */
+    int workspace_is_clean,       /* 1: workspace is as a previous call left it
+                                     (all 0xFF), so the 8 B/pixel memset is
+                                     skipped; 0: fresh memory                    */
     int32_t* status_flags,        /* [1], caller-zeroed                          */
     void* stream);
 
