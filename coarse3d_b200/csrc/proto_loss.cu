@@ -25,6 +25,7 @@
 //
 // All reductions are order-deterministic (no float atomics).
 #include <math_constants.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "labelsplit.cuh"
@@ -449,21 +450,26 @@ loss_rows_kernel(RowsParams p) {
 }
 
 // ---------------------------------------------------------------- K6 -------
-// Streaming zero fill.  Each CTA writes one contiguous 32 KB block (256 threads x
-// 8 independent 128-bit stores) and retires: CTAs are short, so when this kernel
-// shares the GPU with the latency-bound kernels of the other chains (which run on
-// higher-priority streams) SM slots turn over within a microsecond.
+// Streaming zero fill, two launch shapes (C3D_FILL_PERSISTENT=1 selects the second):
+//  * short CTAs: each CTA writes one contiguous 32 KB block (256 threads x 8
+//    independent 128-bit stores) and retires, so SM slots turn over within a
+//    microsecond when higher-priority kernels are waiting;
+//  * persistent: one 256-thread CTA per SM looping over 32 KB blocks -- a fixed small
+//    footprint (4 k registers, no shared memory) that can co-reside with other kernels.
 constexpr int kFillPerThread = 8;
 __global__ void __launch_bounds__(256)
 fill_zero_kernel(float4* __restrict__ dst, size_t n4, float* __restrict__ tail, int ntail) {
   const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-  const size_t base = (size_t)blockIdx.x * (256 * kFillPerThread) + threadIdx.x;
-  if (base + (kFillPerThread - 1) * 256 < n4) {
+  const size_t chunk = 256 * kFillPerThread;
+  for (size_t blk = blockIdx.x; blk * chunk < n4; blk += gridDim.x) {
+    const size_t base = blk * chunk + threadIdx.x;
+    if (blk * chunk + chunk <= n4) {
 #pragma unroll
-    for (int j = 0; j < kFillPerThread; ++j) __stcs(dst + base + j * 256, z);
-  } else {
-    for (int j = 0; j < kFillPerThread; ++j)
-      if (base + j * 256 < n4) __stcs(dst + base + j * 256, z);
+      for (int j = 0; j < kFillPerThread; ++j) __stcs(dst + base + j * 256, z);
+    } else {
+      for (int j = 0; j < kFillPerThread; ++j)
+        if (base + j * 256 < n4) __stcs(dst + base + j * 256, z);
+    }
   }
   if (blockIdx.x == 0 && (int)threadIdx.x < ntail) tail[threadIdx.x] = 0.f;
 }
@@ -474,6 +480,11 @@ static int launch_fill(void* dst, size_t nbytes, cudaStream_t stream) {
   size_t grid = (n4 + per_cta - 1) / per_cta;
   if (grid == 0) grid = 1;
   if (grid > 0x7fffffffull) { set_error("fill too large"); return C3D_INVALID_ARGUMENT; }
+  const char* env = getenv("C3D_FILL_PERSISTENT");
+  if (env && env[0] != '0') {
+    const size_t cap = (size_t)kNumSMs * (size_t)(env[0] - '0');
+    if (grid > cap) grid = cap;
+  }
   KernelTimer kt__("fill_zero_kernel", stream);
   fill_zero_kernel<<<(unsigned)grid, 256, 0, stream>>>(reinterpret_cast<float4*>(dst), n4,
                                                        reinterpret_cast<float*>(dst) + n4 * 4,

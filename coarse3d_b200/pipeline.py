@@ -54,7 +54,7 @@ class HotPathStep:
 
     def __init__(self, shape, batch, dim=128, sub_protos=20, num_anchor=512, temperature=0.07,
                  momentum=0.999, n_sets=3, seed0=1000, device="cuda", group=None,
-                 knn=(5, 5, 1.0, 1.0), concurrent=True):
+                 knn=(5, 5, 1.0, 1.0), concurrent=True, parts=None):
         self.shape, self.batch, self.dim, self.M = shape, batch, dim, sub_protos
         self.device, self.group = torch.device(device), group
         self.knn_k, self.knn_s, self.knn_sigma, self.knn_cutoff = knn
@@ -90,6 +90,8 @@ class HotPathStep:
         self.inv_gauss = (1 - ops.gaussian_kernel(self.knn_s, self.knn_sigma)).reshape(-1).to(self.device)
         self.graphs = None
         self.concurrent = concurrent
+        # ablation switch for tools/ablate.py: which chains run (default: all)
+        self.parts = set(parts) if parts else {"proj", "knn", "fill", "loss", "ema"}
         # Priorities: the latency-bound chains (loss, EMA) high, so their small CTAs
         # are placed first whenever the short CTAs of the fill / KNN retire.
         lo, hi = 0, -1
@@ -132,10 +134,14 @@ class HotPathStep:
         self.ev_fork.record(cur)
         for st in self.side:
             st.wait_event(self.ev_fork)
+        P = self.parts
+        pr = None
         with torch.cuda.stream(st_proj):
-            pr = ops.project_batch(s.points, s.offsets, self.fov, H, W, buffers=b)
+            if "proj" in P:
+                pr = ops.project_batch(s.points, s.offsets, self.fov, H, W, buffers=b)
             self.ev_resolved.record(st_proj)
-            self._knn(s, pr, C)          # ALU-bound: pairs with the bandwidth-bound fill
+            if "knn" in P:
+                self._knn(s, pr if pr is not None else self._last_proj(b), C)  # ALU-bound
             self.ev_proj.record(st_proj)
         with torch.cuda.stream(st_fill):
             # The fill saturates HBM and streams 512 MB through L2, which slows the
@@ -143,20 +149,28 @@ class HotPathStep:
             # overlap gains (profiles/timeline_r1.txt); it therefore starts after the
             # projection and overlaps the ALU-bound KNN vote and the loss / EMA chains.
             st_fill.wait_event(self.ev_resolved)
-            ops.zero_fill(self.grad)
+            if "fill" in P:
+                ops.zero_fill(self.grad)
             self.ev_fill.record(st_fill)
         with torch.cuda.stream(st_ema):
-            self._ema(s, seed)
+            if "ema" in P:
+                self._ema(s, seed)
             self.ev_ema.record(st_ema)
         with torch.cuda.stream(st_loss):
-            self._loss_fwd(s, seed)
+            if "loss" in P:
+                self._loss_fwd(s, seed)
             st_loss.wait_event(self.ev_fill)
-            ops.proto_loss_backward_raw(s.feats.shape, self.cfg, C, self.M, self.loss_ws, self.grad_out,
-                                        self.grad, grad_is_zeroed=True)
+            if "loss" in P:
+                ops.proto_loss_backward_raw(s.feats.shape, self.cfg, C, self.M, self.loss_ws,
+                                            self.grad_out, self.grad, grad_is_zeroed=True)
             self.ev_loss.record(st_loss)
         for ev in (self.ev_proj, self.ev_ema, self.ev_loss):
             cur.wait_event(ev)
         return pr
+
+    def _last_proj(self, b):
+        return ops.Projection(b.proj_pointcloud, b.proj_range, b.proj_idx, b.proj_mask,
+                              b.uproj_x_idx, b.uproj_y_idx, b.uproj_depth, b.flags)
 
     def _loss_fwd(self, s, seed):
         ops.proto_loss_forward_raw(s.feats, s.probs, s.labels, s.keep_mask, self.protos, self.cfg,
