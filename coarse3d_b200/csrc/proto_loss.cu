@@ -29,6 +29,7 @@
 
 #include "common.cuh"
 #include "labelsplit.cuh"
+#include "rowgemm.cuh"
 
 namespace c3d {
 
@@ -233,7 +234,7 @@ struct RowsParams {
   float* loss_part;        // [rows]
   float* grad_rows;        // [rows * D]
   float* loss_out;         // [1]
-  int HW, D, M, Kc, A, tile_rows, n_tiles;
+  int HW, D, M, Kc, A, tile_rows, n_tiles, ldl;
   float temperature, base_temperature;
 };
 
@@ -449,6 +450,210 @@ loss_rows_kernel(RowsParams p) {
   }
 }
 
+// ---------------------------------------------------------------- K5b ------
+// loss_rows16: the same math as loss_rows_kernel, organised as register-tiled products
+// over groups of 16 rows (rowgemm.cuh).  Default; C3D_LOSS_ROWS_V1=1 selects the
+// warp-per-row kernel above (kept for A/B measurements).
+template <bool kWithGrad, int kDch, int kDJ>
+__global__ void __launch_bounds__(256, 1)
+loss_rows16_kernel(RowsParams p) {
+  extern __shared__ __align__(16) float smem[];
+  const int D = p.D, Kc = p.Kc, ldl = p.ldl;
+  const BankLayout BL = BankLayout::make(D);
+  float* s_bank = smem;                                   // [tile_rows] rows, layout BL
+  float* s_A = s_bank + (size_t)p.tile_rows * BL.ld;      // [16][D]   a_hat, later d a_hat
+  float* s_L = s_A + kGroupRows * D;                      // [16][ldl] logits, later dL/dlogit
+  __shared__ int s_cnt[kGroupRows], s_cls[kGroupRows];
+  __shared__ float s_inv[kGroupRows];
+  __shared__ int s_last;
+  __shared__ float s_red[8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cg = threadIdx.x & 63, rg = threadIdx.x >> 6;
+  const int n_rows = p.info[kInfoU];
+  const int T = p.info[kInfoT];
+  const int n_groups = (n_rows + kGroupRows - 1) / kGroupRows;
+  const float scale_row = p.temperature / p.base_temperature;
+  const float inv_R = 1.0f / ((float)p.A * (float)T);  // mean over R = A*T rows (:193)
+
+  if (p.n_tiles == 1 && (int)blockIdx.x < n_groups) stage_bank_tile(s_bank, p.bank_n, 0, Kc, BL);
+  __syncthreads();
+
+  for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+    // ---- P0: gather + L2-normalise two rows per warp (:166)
+    float areg[2][kDJ];
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      const int rl = warp * 2 + rr, row = grp * kGroupRows + rl;
+      int cnt = 0, cls = 0; float inv_norm = 0.f;
+#pragma unroll
+      for (int j = 0; j < kDJ; ++j) areg[rr][j] = 0.f;
+      if (row < n_rows) {
+        const int slot = slot_of_row(row, T, p.row_base, p.seg_of_t, p.seg_start, p.dist_list);
+        cnt = __ldcg(p.cnt_list + slot);
+        const int gpix = p.pix_list[slot];
+        cls = p.cls_list[slot];
+        const int b = gpix / p.HW, pix = gpix - b * p.HW;
+        const float* src = p.feats + (size_t)b * D * p.HW + pix;
+        float n2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < kDJ; ++j) {
+          const int d = lane + 32 * j;
+          if (d < D) { const float v = __ldg(src + (size_t)d * p.HW); areg[rr][j] = v; n2 += v * v; }
+        }
+        n2 = warp_sum(n2);
+        inv_norm = 1.0f / fmaxf(sqrtf(n2), 1e-12f);
+#pragma unroll
+        for (int j = 0; j < kDJ; ++j) areg[rr][j] *= inv_norm;
+      }
+#pragma unroll
+      for (int j = 0; j < kDJ; ++j) { const int d = lane + 32 * j; if (d < D) s_A[rl * D + d] = areg[rr][j]; }
+      if (lane == 0) { s_cnt[rl] = cnt; s_cls[rl] = cls; s_inv[rl] = inv_norm; }
+    }
+    __syncthreads();
+
+    // ---- P1: logits z = (a_hat . c_hat) / temperature (:168-172)
+    for (int tile = 0; tile < p.n_tiles; ++tile) {
+      const int r0 = tile * p.tile_rows, rows = min(p.tile_rows, Kc - r0);
+      if (p.n_tiles > 1) { __syncthreads(); stage_bank_tile(s_bank, p.bank_n, r0, rows, BL); __syncthreads(); }
+      float acc[4][kColsPerThread];
+      tile_logits(s_A, s_bank, rows, BL, acc);
+#pragma unroll
+      for (int i = 0; i < kColsPerThread; ++i) {
+        const int c = cg + 64 * i;
+        if (c < rows) {
+#pragma unroll
+          for (int r = 0; r < 4; ++r) s_L[(rg * 4 + r) * ldl + r0 + c] = acc[r][i] / p.temperature;
+        }
+      }
+    }
+    __syncthreads();
+
+    // ---- P2: softmax statistics, loss term, dL/dlogit (:175-193)
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      const int rl = warp * 2 + rr, row = grp * kGroupRows + rl;
+      float* my_l = s_L + rl * ldl;
+      const int cnt = s_cnt[rl], cls = s_cls[rl];
+      if (row < n_rows) {
+        float mx = -CUDART_INF_F;
+        for (int k = lane; k < Kc; k += 32) mx = fmaxf(mx, my_l[k]);
+        mx = warp_max(mx);
+        const int pos_lo = (cls - 1) * p.M, pos_hi = cls * p.M;
+        float neg = 0.f;
+        for (int k = lane; k < Kc; k += 32) {
+          const float e = expf(my_l[k] - mx);
+          if (k < pos_lo || k >= pos_hi) neg += e;
+        }
+        neg = warp_sum(neg);
+        float s = 0.f, inv_den = 0.f; int npos = 0;
+        for (int k = pos_lo + lane; k < pos_hi; k += 32) {
+          if (k >= 0 && k < Kc) {
+            const float l = my_l[k] - mx;
+            const float den = expf(l) + neg + 1e-6f;
+            s += l - logf(den);
+            inv_den += 1.0f / den;
+            ++npos;
+          }
+        }
+        s = warp_sum(s);
+        inv_den = warp_sum(inv_den);
+        npos = __reduce_add_sync(0xffffffffu, npos);
+        if (lane == 0) p.loss_part[row] = (float)cnt * (-scale_row * (s / (float)npos));
+        if (kWithGrad) {
+          const float sg = scale_row / (float)npos;
+          for (int k = lane; k < Kc; k += 32) {
+            const float e = expf(my_l[k] - mx);
+            float g;
+            if (k >= pos_lo && k < pos_hi) g = -sg * (1.0f - e / (e + neg + 1e-6f));
+            else g = sg * e * inv_den;
+            my_l[k] = g / p.temperature;
+          }
+        }
+      } else if (kWithGrad) {
+        for (int k = lane; k < Kc; k += 32) my_l[k] = 0.f;
+      }
+    }
+    __syncthreads();
+
+    if (kWithGrad) {
+      // ---- P3: d a_hat = G . bank
+      float4 acc4[4][kDch];
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int q = 0; q < kDch; ++q) acc4[r][q] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int tile = 0; tile < p.n_tiles; ++tile) {
+        const int r0 = tile * p.tile_rows, rows = min(p.tile_rows, Kc - r0);
+        if (p.n_tiles > 1) { __syncthreads(); stage_bank_tile(s_bank, p.bank_n, r0, rows, BL); __syncthreads(); }
+        tile_gradT<kDch>(s_L, ldl, r0, s_bank, rows, BL, acc4);
+      }
+      const int d4 = D >> 2;
+#pragma unroll
+      for (int q = 0; q < kDch; ++q) {
+        const int ch = cg + 64 * q;
+        if (ch < d4) {
+#pragma unroll
+          for (int r = 0; r < 4; ++r)
+            *reinterpret_cast<float4*>(s_A + (rg * 4 + r) * D + ch * 4) = acc4[r][q];
+        }
+      }
+      __syncthreads();
+      // ---- P4: normalize backward, weighted gradient row
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+        const int rl = warp * 2 + rr, row = grp * kGroupRows + rl;
+        if (row < n_rows) {
+          float dot = 0.f;
+#pragma unroll
+          for (int j = 0; j < kDJ; ++j) {
+            const int d = lane + 32 * j;
+            if (d < D) dot += areg[rr][j] * s_A[rl * D + d];
+          }
+          dot = warp_sum(dot);
+          const float inv_norm = s_inv[rl];
+          const float w = (float)s_cnt[rl] * inv_R * inv_norm;
+          const float sub = (inv_norm >= 1e12f) ? 0.f : dot;  // |a| < eps: y = x / eps
+#pragma unroll
+          for (int j = 0; j < kDJ; ++j) {
+            const int d = lane + 32 * j;
+            if (d < D) p.grad_rows[(size_t)row * D + d] = (s_A[rl * D + d] - areg[rr][j] * sub) * w;
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- deterministic final reduction by the last CTA: loss = sum / (A*T)
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(&p.info[kInfoDone2], 1) == (int)gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n_rows; i += blockDim.x) s += __ldcg(p.loss_part + i);
+  s = warp_sum(s);
+  if (lane == 0) s_red[warp] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot = 0.f;
+    for (int w = 0; w < 8; ++w) tot += s_red[w];
+    p.loss_out[0] = tot * inv_R;  // T == 0 -> NaN (the reference crashes)
+    p.info[kInfoDone2] = 0;
+    p.info[kInfoHasGrad] = kWithGrad ? 1 : 0;
+  }
+}
+
+template <bool kWithGrad, int kDch, int kDJ>
+static int launch_rows16(const RowsParams& p, size_t smem, cudaStream_t stream) {
+  C3D_CUDA(cudaFuncSetAttribute(loss_rows16_kernel<kWithGrad, kDch, kDJ>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  KernelTimer kt__("loss_rows_kernel", stream);
+  loss_rows16_kernel<kWithGrad, kDch, kDJ><<<kNumSMs, 256, smem, stream>>>(p);
+  return check_launch("loss_rows16_kernel");
+}
+
 // ---------------------------------------------------------------- K6 -------
 // Streaming zero fill, two launch shapes (C3D_FILL_PERSISTENT=1 selects the second):
 //  * short CTAs: each CTA writes one contiguous 32 KB block (256 threads x 8
@@ -606,6 +811,19 @@ extern "C" int c3d_proto_loss_forward(
   p.loss_part = w.loss_part; p.grad_rows = w.grad_rows; p.loss_out = loss_out;
   p.HW = HW; p.D = D; p.M = M; p.Kc = Kc; p.A = num_anchor; p.tile_rows = tile_rows;
   p.n_tiles = n_tiles; p.temperature = temperature; p.base_temperature = base_temperature;
+  const char* v1 = getenv("C3D_LOSS_ROWS_V1");
+  RowsPlan plan;
+  if (!(v1 && v1[0] == '1') && plan_rows16(D, Kc, &plan) == 0) {
+    p.tile_rows = plan.tile_rows; p.n_tiles = plan.n_tiles; p.ldl = plan.ldl;
+    if (need_grad) {
+      if (D <= 128) return launch_rows16<true, 1, 4>(p, plan.smem, stream);
+      if (D <= 256) return launch_rows16<true, 1, 8>(p, plan.smem, stream);
+      return launch_rows16<true, 4, 32>(p, plan.smem, stream);
+    }
+    if (D <= 128) return launch_rows16<false, 1, 4>(p, plan.smem, stream);
+    if (D <= 256) return launch_rows16<false, 1, 8>(p, plan.smem, stream);
+    return launch_rows16<false, 4, 32>(p, plan.smem, stream);
+  }
   if (!need_grad) return launch_rows<false, 1>(p, smem, stream);
   if (D <= 128) return launch_rows<true, 1>(p, smem, stream);
   if (D <= 256) return launch_rows<true, 2>(p, smem, stream);
