@@ -454,7 +454,7 @@ loss_rows_kernel(RowsParams p) {
 // loss_rows16: the same math as loss_rows_kernel, organised as register-tiled products
 // over groups of 16 rows (rowgemm.cuh).  Default; C3D_LOSS_ROWS_V1=1 selects the
 // warp-per-row kernel above (kept for A/B measurements).
-template <bool kWithGrad, int kDch, int kDJ>
+template <bool kWithGrad, int kRP, int kDch, int kDJ>
 __global__ void __launch_bounds__(256, 1)
 loss_rows16_kernel(RowsParams p) {
   extern __shared__ __align__(16) float smem[];
@@ -475,40 +475,55 @@ loss_rows16_kernel(RowsParams p) {
   const float scale_row = p.temperature / p.base_temperature;
   const float inv_R = 1.0f / ((float)p.A * (float)T);  // mean over R = A*T rows (:193)
 
-  if (p.n_tiles == 1 && (int)blockIdx.x < n_groups) stage_bank_tile(s_bank, p.bank_n, 0, Kc, BL);
-  __syncthreads();
+  // single-tile case: start the bank copies now, complete them after the first gather
+  bool staged = !(p.n_tiles == 1 && (int)blockIdx.x < n_groups);
+  if (!staged) stage_bank_tile_issue(s_bank, p.bank_n, 0, Kc, BL);
 
   for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
-    // ---- P0: gather + L2-normalise two rows per warp (:166)
+    // ---- P0: gather + L2-normalise two rows per warp (:166); the two rows' dependent
+    //      load chains (row -> slot -> pixel -> features) are issued interleaved
     float areg[2][kDJ];
+    int slot[2], cnt2[2], cls2[2], gpix2[2];
+    bool act[2];
 #pragma unroll
     for (int rr = 0; rr < 2; ++rr) {
-      const int rl = warp * 2 + rr, row = grp * kGroupRows + rl;
-      int cnt = 0, cls = 0; float inv_norm = 0.f;
-#pragma unroll
-      for (int j = 0; j < kDJ; ++j) areg[rr][j] = 0.f;
-      if (row < n_rows) {
-        const int slot = slot_of_row(row, T, p.row_base, p.seg_of_t, p.seg_start, p.dist_list);
-        cnt = __ldcg(p.cnt_list + slot);
-        const int gpix = p.pix_list[slot];
-        cls = p.cls_list[slot];
-        const int b = gpix / p.HW, pix = gpix - b * p.HW;
-        const float* src = p.feats + (size_t)b * D * p.HW + pix;
-        float n2 = 0.f;
-#pragma unroll
-        for (int j = 0; j < kDJ; ++j) {
-          const int d = lane + 32 * j;
-          if (d < D) { const float v = __ldg(src + (size_t)d * p.HW); areg[rr][j] = v; n2 += v * v; }
-        }
-        n2 = warp_sum(n2);
-        inv_norm = 1.0f / fmaxf(sqrtf(n2), 1e-12f);
-#pragma unroll
-        for (int j = 0; j < kDJ; ++j) areg[rr][j] *= inv_norm;
-      }
-#pragma unroll
-      for (int j = 0; j < kDJ; ++j) { const int d = lane + 32 * j; if (d < D) s_A[rl * D + d] = areg[rr][j]; }
-      if (lane == 0) { s_cnt[rl] = cnt; s_cls[rl] = cls; s_inv[rl] = inv_norm; }
+      const int row = grp * kGroupRows + warp * 2 + rr;
+      act[rr] = row < n_rows;
+      slot[rr] = act[rr] ? slot_of_row(row, T, p.row_base, p.seg_of_t, p.seg_start, p.dist_list) : 0;
     }
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      cnt2[rr] = act[rr] ? __ldcg(p.cnt_list + slot[rr]) : 0;
+      gpix2[rr] = act[rr] ? p.pix_list[slot[rr]] : 0;
+      cls2[rr] = act[rr] ? p.cls_list[slot[rr]] : 0;
+    }
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      const int b = gpix2[rr] / p.HW, pix = gpix2[rr] - b * p.HW;
+      const float* src = p.feats + (size_t)b * D * p.HW + pix;
+#pragma unroll
+      for (int j = 0; j < kDJ; ++j) {
+        const int d = lane + 32 * j;
+        areg[rr][j] = (act[rr] && d < D) ? __ldg(src + (size_t)d * p.HW) : 0.f;
+      }
+    }
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      const int rl = warp * 2 + rr;
+      float n2 = 0.f;
+#pragma unroll
+      for (int j = 0; j < kDJ; ++j) n2 += areg[rr][j] * areg[rr][j];
+      n2 = warp_sum(n2);
+      const float inv_norm = act[rr] ? 1.0f / fmaxf(sqrtf(n2), 1e-12f) : 0.f;
+#pragma unroll
+      for (int j = 0; j < kDJ; ++j) {
+        areg[rr][j] *= inv_norm;
+        const int d = lane + 32 * j;
+        if (d < D) s_A[rl * D + d] = areg[rr][j];
+      }
+      if (lane == 0) { s_cnt[rl] = cnt2[rr]; s_cls[rl] = cls2[rr]; s_inv[rl] = inv_norm; }
+    }
+    if (!staged) { cp_async_wait_all(); staged = true; }
     __syncthreads();
 
     // ---- P1: logits z = (a_hat . c_hat) / temperature (:168-172)
@@ -577,24 +592,27 @@ loss_rows16_kernel(RowsParams p) {
 
     if (kWithGrad) {
       // ---- P3: d a_hat = G . bank
-      float4 acc4[4][kDch];
+      float4 acc4[kRP][kDch];
 #pragma unroll
-      for (int r = 0; r < 4; ++r)
+      for (int r = 0; r < kRP; ++r)
 #pragma unroll
         for (int q = 0; q < kDch; ++q) acc4[r][q] = make_float4(0.f, 0.f, 0.f, 0.f);
       for (int tile = 0; tile < p.n_tiles; ++tile) {
         const int r0 = tile * p.tile_rows, rows = min(p.tile_rows, Kc - r0);
         if (p.n_tiles > 1) { __syncthreads(); stage_bank_tile(s_bank, p.bank_n, r0, rows, BL); __syncthreads(); }
-        tile_gradT<kDch>(s_L, ldl, r0, s_bank, rows, BL, acc4);
+        tile_gradT<kRP, kDch>(s_L, ldl, r0, s_bank, rows, BL, acc4);
       }
-      const int d4 = D >> 2;
+      {
+        constexpr int CT = 16 * kRP;
+        const int ct = threadIdx.x % CT, rgp = threadIdx.x / CT, d4 = D >> 2;
 #pragma unroll
-      for (int q = 0; q < kDch; ++q) {
-        const int ch = cg + 64 * q;
-        if (ch < d4) {
+        for (int q = 0; q < kDch; ++q) {
+          const int ch = ct + CT * q;
+          if (ch < d4) {
 #pragma unroll
-          for (int r = 0; r < 4; ++r)
-            *reinterpret_cast<float4*>(s_A + (rg * 4 + r) * D + ch * 4) = acc4[r][q];
+            for (int r = 0; r < kRP; ++r)
+              *reinterpret_cast<float4*>(s_A + (rgp * kRP + r) * D + ch * 4) = acc4[r][q];
+          }
         }
       }
       __syncthreads();
@@ -645,12 +663,12 @@ loss_rows16_kernel(RowsParams p) {
   }
 }
 
-template <bool kWithGrad, int kDch, int kDJ>
+template <bool kWithGrad, int kRP, int kDch, int kDJ>
 static int launch_rows16(const RowsParams& p, size_t smem, cudaStream_t stream) {
-  C3D_CUDA(cudaFuncSetAttribute(loss_rows16_kernel<kWithGrad, kDch, kDJ>,
+  C3D_CUDA(cudaFuncSetAttribute(loss_rows16_kernel<kWithGrad, kRP, kDch, kDJ>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   KernelTimer kt__("loss_rows_kernel", stream);
-  loss_rows16_kernel<kWithGrad, kDch, kDJ><<<kNumSMs, 256, smem, stream>>>(p);
+  loss_rows16_kernel<kWithGrad, kRP, kDch, kDJ><<<kNumSMs, 256, smem, stream>>>(p);
   return check_launch("loss_rows16_kernel");
 }
 
@@ -815,14 +833,17 @@ extern "C" int c3d_proto_loss_forward(
   RowsPlan plan;
   if (!(v1 && v1[0] == '1') && plan_rows16(D, Kc, &plan) == 0) {
     p.tile_rows = plan.tile_rows; p.n_tiles = plan.n_tiles; p.ldl = plan.ldl;
+    // <grad, rows per thread in P3 (chunk-threads = 16*kRP), chunks per thread, D/32>
     if (need_grad) {
-      if (D <= 128) return launch_rows16<true, 1, 4>(p, plan.smem, stream);
-      if (D <= 256) return launch_rows16<true, 1, 8>(p, plan.smem, stream);
-      return launch_rows16<true, 4, 32>(p, plan.smem, stream);
+      if (D <= 64) return launch_rows16<true, 1, 1, 2>(p, plan.smem, stream);
+      if (D <= 128) return launch_rows16<true, 2, 1, 4>(p, plan.smem, stream);
+      if (D <= 256) return launch_rows16<true, 4, 1, 8>(p, plan.smem, stream);
+      return launch_rows16<true, 4, 4, 32>(p, plan.smem, stream);
     }
-    if (D <= 128) return launch_rows16<false, 1, 4>(p, plan.smem, stream);
-    if (D <= 256) return launch_rows16<false, 1, 8>(p, plan.smem, stream);
-    return launch_rows16<false, 4, 32>(p, plan.smem, stream);
+    if (D <= 64) return launch_rows16<false, 1, 1, 2>(p, plan.smem, stream);
+    if (D <= 128) return launch_rows16<false, 2, 1, 4>(p, plan.smem, stream);
+    if (D <= 256) return launch_rows16<false, 4, 1, 8>(p, plan.smem, stream);
+    return launch_rows16<false, 4, 4, 32>(p, plan.smem, stream);
   }
   if (!need_grad) return launch_rows<false, 1>(p, smem, stream);
   if (D <= 128) return launch_rows<true, 1>(p, smem, stream);

@@ -5,7 +5,7 @@
 // multiplies it with a tile of bank rows staged in shared memory:
 //
 //   tile_logits : C[16][rows] = A . bank_tile^T      thread (rg, cg) -> 4 rows x 6 cols
-//   tile_gradT  : dA[16][D]  += G[16][rows] . bank_tile   thread (rg, ch) -> 4 rows x 4 d
+//   tile_gradT  : dA[16][D]  += G[16][rows] . bank_tile   thread (rgp, ct) -> kRP rows x 4 d
 //
 // The first version of these kernels gave each warp ONE row and re-read every bank
 // element from shared memory once per row: ncu showed them shared-memory-bandwidth
@@ -39,14 +39,20 @@ struct BankLayout {
   }
 };
 
-// bank_n rows [r0, r0 + rows) -> shared memory, all 16 B chunks in flight (cp.async)
-__device__ __forceinline__ void stage_bank_tile(float* s_bank, const float* __restrict__ bank_n, int r0,
-                                                int rows, const BankLayout& L) {
+// bank_n rows [r0, r0 + rows) -> shared memory, all 16 B chunks in flight (cp.async).
+// `issue` only starts the copies; cp_async_wait_all() (+ a barrier) completes them, so
+// the caller can overlap the staging with its own global loads.
+__device__ __forceinline__ void stage_bank_tile_issue(float* s_bank, const float* __restrict__ bank_n,
+                                                      int r0, int rows, const BankLayout& L) {
   const int d4 = L.D >> 2;
   for (int i = threadIdx.x; i < rows * d4; i += blockDim.x) {
     const int r = i / d4, c = i - r * d4;
     cp_async16(s_bank + L.off(r, c), bank_n + (size_t)(r0 + r) * L.D + c * 4);
   }
+}
+__device__ __forceinline__ void stage_bank_tile(float* s_bank, const float* __restrict__ bank_n, int r0,
+                                                int rows, const BankLayout& L) {
+  stage_bank_tile_issue(s_bank, bank_n, r0, rows, L);
   cp_async_wait_all();
 }
 
@@ -79,28 +85,51 @@ __device__ __forceinline__ void tile_logits(const float* s_A, const float* s_ban
   }
 }
 
-// acc[r][q] += sum_k G[rg*4 + r][k0 + k] * bank[k][chunk ch + 64 q]; G row stride ldg floats.
-template <int kDch>
+// dA[16][D] += G[16][k0 .. k0+rows) . bank_tile.  Thread (rgp, ct): kRP rows
+// rgp*kRP.., chunks ct + CT*q (CT = 16*kRP chunk-threads per row group, so all 256
+// threads work for D = 64*kRP/... see launch table).  G is read 4 k at a time as
+// warp-wide broadcasts; requires k0 % 4 == 0 and ldg % 4 == 0.
+template <int kRP, int kDch>
 __device__ __forceinline__ void tile_gradT(const float* s_G, int ldg, int k0, const float* s_bank,
-                                           int rows, const BankLayout& L, float4 (&acc)[4][kDch]) {
-  const int ch0 = threadIdx.x & 63, rg = threadIdx.x >> 6;
+                                           int rows, const BankLayout& L, float4 (&acc)[kRP][kDch]) {
+  constexpr int CT = 16 * kRP;
+  const int ct = threadIdx.x % CT, rgp = threadIdx.x / CT;
   const int d4 = L.D >> 2;
-  const float* g_base = s_G + (size_t)(rg * 4) * ldg + k0;
-  if (ch0 >= d4) return;
-#pragma unroll 2
-  for (int k = 0; k < rows; ++k) {
-    float g[4];
+  if (ct >= d4) return;
+  const float* g_base = s_G + (size_t)(rgp * kRP) * ldg + k0;
+  const int rows4 = rows & ~3;
+  for (int k = 0; k < rows4; k += 4) {
+    float4 g[kRP];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) g[r] = g_base[r * ldg + k];  // broadcast
+    for (int r = 0; r < kRP; ++r) g[r] = *reinterpret_cast<const float4*>(g_base + r * ldg + k);
 #pragma unroll
     for (int q = 0; q < kDch; ++q) {
-      const int ch = ch0 + 64 * q;
+      const int ch = ct + CT * q;
+      if (ch < d4) {
+        const float4 b0 = *reinterpret_cast<const float4*>(s_bank + L.off(k, ch));
+        const float4 b1 = *reinterpret_cast<const float4*>(s_bank + L.off(k + 1, ch));
+        const float4 b2 = *reinterpret_cast<const float4*>(s_bank + L.off(k + 2, ch));
+        const float4 b3 = *reinterpret_cast<const float4*>(s_bank + L.off(k + 3, ch));
+#pragma unroll
+        for (int r = 0; r < kRP; ++r) {
+          acc[r][q].x += g[r].x * b0.x; acc[r][q].y += g[r].x * b0.y; acc[r][q].z += g[r].x * b0.z; acc[r][q].w += g[r].x * b0.w;
+          acc[r][q].x += g[r].y * b1.x; acc[r][q].y += g[r].y * b1.y; acc[r][q].z += g[r].y * b1.z; acc[r][q].w += g[r].y * b1.w;
+          acc[r][q].x += g[r].z * b2.x; acc[r][q].y += g[r].z * b2.y; acc[r][q].z += g[r].z * b2.z; acc[r][q].w += g[r].z * b2.w;
+          acc[r][q].x += g[r].w * b3.x; acc[r][q].y += g[r].w * b3.y; acc[r][q].z += g[r].w * b3.z; acc[r][q].w += g[r].w * b3.w;
+        }
+      }
+    }
+  }
+  for (int k = rows4; k < rows; ++k) {
+#pragma unroll
+    for (int q = 0; q < kDch; ++q) {
+      const int ch = ct + CT * q;
       if (ch < d4) {
         const float4 b = *reinterpret_cast<const float4*>(s_bank + L.off(k, ch));
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          acc[r][q].x += g[r] * b.x; acc[r][q].y += g[r] * b.y;
-          acc[r][q].z += g[r] * b.z; acc[r][q].w += g[r] * b.w;
+        for (int r = 0; r < kRP; ++r) {
+          const float g = g_base[r * ldg + k];
+          acc[r][q].x += g * b.x; acc[r][q].y += g * b.y; acc[r][q].z += g * b.z; acc[r][q].w += g * b.w;
         }
       }
     }

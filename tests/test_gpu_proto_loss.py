@@ -61,6 +61,8 @@ def _random_problem(B, D, H, W, C, M, frac, seed, normalized_bank=True):
     (1, 256, 8, 256, 20, 20, 128, 0.01),     # D=256: bank streamed in two smem tiles
     (3, 64, 8, 128, 17, 20, 64, 0.3),        # dense labels (pseudo-label regime)
     (2, 32, 4, 100, 14, 7, 33, 0.05),        # odd sizes, W not a multiple of 4
+    (1, 512, 4, 64, 6, 4, 16, 0.1),          # wide features: 4 chunks per thread
+    (1, 24, 4, 64, 20, 20, 16, 0.2),         # D not a multiple of 32: padded (unswizzled) bank
 ])
 def test_matches_oracle_with_injected_anchors(cuda_device, B, D, H, W, C, M, A, frac):
     feats, output, labels, keep_mask, queue = _random_problem(B, D, H, W, C, M, frac, 7)
