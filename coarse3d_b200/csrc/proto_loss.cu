@@ -242,11 +242,19 @@ struct RowsParams {
 __device__ __forceinline__ int slot_of_row(int row, int T, const int32_t* __restrict__ row_base,
                                            const int32_t* __restrict__ seg_of_t,
                                            const int32_t* __restrict__ seg_start,
-                                           const int32_t* __restrict__ dist_list) {
+                                           const int32_t* __restrict__ dist_list,
+                                           const int32_t* s_row_base = nullptr) {
   int lo = 0, hi = T;  // row_base[lo] <= row < row_base[hi]
-  while (hi - lo > 1) {
-    const int mid = (lo + hi) >> 1;
-    if (__ldg(row_base + mid) <= row) lo = mid; else hi = mid;
+  if (s_row_base) {    // copy in shared memory: 8 steps of ~30 cycles instead of L2 round trips
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (s_row_base[mid] <= row) lo = mid; else hi = mid;
+    }
+  } else {
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (__ldg(row_base + mid) <= row) lo = mid; else hi = mid;
+    }
   }
   const int seg = __ldg(seg_of_t + lo);
   return __ldcg(dist_list + __ldg(seg_start + seg) + (row - __ldg(row_base + lo)));
@@ -450,11 +458,20 @@ loss_rows_kernel(RowsParams p) {
   }
 }
 
+// Developer aid (compile with -DC3D_DEBUG_STAMPS): SM-clock stamps of CTA 0 at the phase
+// boundaries of loss_rows16, read back by tools/rows_stamps.py.
+#ifdef C3D_DEBUG_STAMPS
+__device__ long long g_rows_dbg[16];
+#define DBG_STAMP(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_rows_dbg[i] = clock64(); } while (0)
+#else
+#define DBG_STAMP(i) do { } while (0)
+#endif
+
 // ---------------------------------------------------------------- K5b ------
 // loss_rows16: the same math as loss_rows_kernel, organised as register-tiled products
 // over groups of 16 rows (rowgemm.cuh).  Default; C3D_LOSS_ROWS_V1=1 selects the
 // warp-per-row kernel above (kept for A/B measurements).
-template <bool kWithGrad, int kRP, int kDch, int kDJ>
+template <bool kWithGrad, int kKS, int kRP, int kDch, int kDJ>
 __global__ void __launch_bounds__(256, 1)
 loss_rows16_kernel(RowsParams p) {
   extern __shared__ __align__(16) float smem[];
@@ -467,17 +484,23 @@ loss_rows16_kernel(RowsParams p) {
   __shared__ float s_inv[kGroupRows];
   __shared__ int s_last;
   __shared__ float s_red[8];
+  constexpr int kRbCap = 192;
+  __shared__ int32_t s_rb[kRbCap];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cg = threadIdx.x & 63, rg = threadIdx.x >> 6;
   const int n_rows = p.info[kInfoU];
   const int T = p.info[kInfoT];
+  const int32_t* rb_s = (T + 1 <= kRbCap) ? s_rb : nullptr;
+  if (rb_s && (int)threadIdx.x <= T) s_rb[threadIdx.x] = __ldg(p.row_base + threadIdx.x);
   const int n_groups = (n_rows + kGroupRows - 1) / kGroupRows;
   const float scale_row = p.temperature / p.base_temperature;
   const float inv_R = 1.0f / ((float)p.A * (float)T);  // mean over R = A*T rows (:193)
 
+  DBG_STAMP(0);
   // single-tile case: start the bank copies now, complete them after the first gather
   bool staged = !(p.n_tiles == 1 && (int)blockIdx.x < n_groups);
   if (!staged) stage_bank_tile_issue(s_bank, p.bank_n, 0, Kc, BL);
+  __syncthreads();  // s_rb visible
 
   for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
     // ---- P0: gather + L2-normalise two rows per warp (:166); the two rows' dependent
@@ -489,7 +512,7 @@ loss_rows16_kernel(RowsParams p) {
     for (int rr = 0; rr < 2; ++rr) {
       const int row = grp * kGroupRows + warp * 2 + rr;
       act[rr] = row < n_rows;
-      slot[rr] = act[rr] ? slot_of_row(row, T, p.row_base, p.seg_of_t, p.seg_start, p.dist_list) : 0;
+      slot[rr] = act[rr] ? slot_of_row(row, T, p.row_base, p.seg_of_t, p.seg_start, p.dist_list, rb_s) : 0;
     }
 #pragma unroll
     for (int rr = 0; rr < 2; ++rr) {
@@ -523,8 +546,10 @@ loss_rows16_kernel(RowsParams p) {
       }
       if (lane == 0) { s_cnt[rl] = cnt2[rr]; s_cls[rl] = cls2[rr]; s_inv[rl] = inv_norm; }
     }
+    DBG_STAMP(1);
     if (!staged) { cp_async_wait_all(); staged = true; }
     __syncthreads();
+    DBG_STAMP(2);
 
     // ---- P1: logits z = (a_hat . c_hat) / temperature (:168-172)
     for (int tile = 0; tile < p.n_tiles; ++tile) {
@@ -543,53 +568,94 @@ loss_rows16_kernel(RowsParams p) {
     }
     __syncthreads();
 
-    // ---- P2: softmax statistics, loss term, dL/dlogit (:175-193)
-#pragma unroll
-    for (int rr = 0; rr < 2; ++rr) {
-      const int rl = warp * 2 + rr, row = grp * kGroupRows + rl;
+    DBG_STAMP(3);
+    // ---- P2: softmax statistics, loss term, dL/dlogit (:175-193); one half-warp per
+    //      row, so the two rows of a warp advance together
+    {
+      const int l16 = lane & 15, rl = warp * 2 + (lane >> 4), row = grp * kGroupRows + rl;
       float* my_l = s_L + rl * ldl;
       const int cnt = s_cnt[rl], cls = s_cls[rl];
-      if (row < n_rows) {
-        float mx = -CUDART_INF_F;
-        for (int k = lane; k < Kc; k += 32) mx = fmaxf(mx, my_l[k]);
-        mx = warp_max(mx);
-        const int pos_lo = (cls - 1) * p.M, pos_hi = cls * p.M;
-        float neg = 0.f;
-        for (int k = lane; k < Kc; k += 32) {
+      const bool live = row < n_rows;
+      auto sum16 = [](float v) {
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        return v;
+      };
+      float mx = -CUDART_INF_F;
+      if (live) {
+#pragma unroll 4
+        for (int k = l16; k < Kc; k += 16) mx = fmaxf(mx, my_l[k]);
+      }
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      const int pos_lo = (cls - 1) * p.M, pos_hi = cls * p.M;
+      // shifted logits of this lane's (<= 2) positives stay in registers; every logit is
+      // then replaced by exp(l), so exp is evaluated once per element
+      const bool one_pass = p.M <= 32;
+      float l_pos[2]; bool is_pos[2]; int kp[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        kp[u] = pos_lo + l16 + 16 * u;
+        is_pos[u] = live && one_pass && (l16 + 16 * u) < p.M && kp[u] >= 0 && kp[u] < Kc;
+        l_pos[u] = is_pos[u] ? my_l[kp[u]] - mx : 0.f;
+      }
+      __syncwarp();
+      float neg = 0.f;
+      if (live) {
+#pragma unroll 4
+        for (int k = l16; k < Kc; k += 16) {
           const float e = expf(my_l[k] - mx);
+          if (one_pass) my_l[k] = e;
           if (k < pos_lo || k >= pos_hi) neg += e;
         }
-        neg = warp_sum(neg);
-        float s = 0.f, inv_den = 0.f; int npos = 0;
-        for (int k = pos_lo + lane; k < pos_hi; k += 32) {
-          if (k >= 0 && k < Kc) {
-            const float l = my_l[k] - mx;
-            const float den = expf(l) + neg + 1e-6f;
-            s += l - logf(den);
-            inv_den += 1.0f / den;
-            ++npos;
+      }
+      neg = sum16(neg);
+      __syncwarp();
+      float s = 0.f, inv_den = 0.f; float npos = 0.f;
+      if (live) {
+        if (one_pass) {
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            if (is_pos[u]) {
+              const float den = my_l[kp[u]] + neg + 1e-6f;
+              s += l_pos[u] - logf(den);
+              inv_den += 1.0f / den;
+              npos += 1.f;
+            }
+          }
+        } else {
+          for (int k = pos_lo + l16; k < pos_hi; k += 16) {
+            if (k >= 0 && k < Kc) {
+              const float l = my_l[k] - mx;
+              const float den = expf(l) + neg + 1e-6f;
+              s += l - logf(den);
+              inv_den += 1.0f / den;
+              npos += 1.f;
+            }
           }
         }
-        s = warp_sum(s);
-        inv_den = warp_sum(inv_den);
-        npos = __reduce_add_sync(0xffffffffu, npos);
-        if (lane == 0) p.loss_part[row] = (float)cnt * (-scale_row * (s / (float)npos));
-        if (kWithGrad) {
-          const float sg = scale_row / (float)npos;
-          for (int k = lane; k < Kc; k += 32) {
-            const float e = expf(my_l[k] - mx);
+      }
+      s = sum16(s); inv_den = sum16(inv_den); npos = sum16(npos);
+      if (live && l16 == 0) p.loss_part[row] = (float)cnt * (-scale_row * (s / npos));
+      if (kWithGrad) {
+        if (live) {
+          const float sg = scale_row / npos;
+#pragma unroll 4
+          for (int k = l16; k < Kc; k += 16) {
+            const float e = one_pass ? my_l[k] : expf(my_l[k] - mx);
             float g;
             if (k >= pos_lo && k < pos_hi) g = -sg * (1.0f - e / (e + neg + 1e-6f));
             else g = sg * e * inv_den;
             my_l[k] = g / p.temperature;
           }
+        } else {
+          for (int k = l16; k < Kc; k += 16) my_l[k] = 0.f;
         }
-      } else if (kWithGrad) {
-        for (int k = lane; k < Kc; k += 32) my_l[k] = 0.f;
       }
     }
     __syncthreads();
 
+    DBG_STAMP(4);
     if (kWithGrad) {
       // ---- P3: d a_hat = G . bank
       float4 acc4[kRP][kDch];
@@ -600,18 +666,54 @@ loss_rows16_kernel(RowsParams p) {
       for (int tile = 0; tile < p.n_tiles; ++tile) {
         const int r0 = tile * p.tile_rows, rows = min(p.tile_rows, Kc - r0);
         if (p.n_tiles > 1) { __syncthreads(); stage_bank_tile(s_bank, p.bank_n, r0, rows, BL); __syncthreads(); }
-        tile_gradT<kRP, kDch>(s_L, ldl, r0, s_bank, rows, BL, acc4);
+        tile_gradT<kKS, kRP, kDch>(s_L, ldl, r0, s_bank, rows, BL, acc4);
       }
       {
-        constexpr int CT = 16 * kRP;
-        const int ct = threadIdx.x % CT, rgp = threadIdx.x / CT, d4 = D >> 2;
+        constexpr int kRowGroups = kGroupRows / kRP;
+        constexpr int CT = 256 / (kKS * kRowGroups);
+        const int ct = threadIdx.x % CT, rgp = (threadIdx.x / CT) % kRowGroups;
+        const int kh = threadIdx.x / (CT * kRowGroups), d4 = D >> 2;
+        if (kKS > 1) {
+          // add the k-split partials through shared memory (G in s_L is dead now)
+          __syncthreads();
+          float4* s_part = reinterpret_cast<float4*>(s_L);  // [kKS-1][16 rows][d4]
+          if (kh > 0) {
 #pragma unroll
-        for (int q = 0; q < kDch; ++q) {
-          const int ch = ct + CT * q;
-          if (ch < d4) {
+            for (int q = 0; q < kDch; ++q) {
+              const int ch = ct + CT * q;
+              if (ch < d4) {
 #pragma unroll
-            for (int r = 0; r < kRP; ++r)
-              *reinterpret_cast<float4*>(s_A + (rgp * kRP + r) * D + ch * 4) = acc4[r][q];
+                for (int r = 0; r < kRP; ++r)
+                  s_part[((kh - 1) * kGroupRows + rgp * kRP + r) * d4 + ch] = acc4[r][q];
+              }
+            }
+          }
+          __syncthreads();
+          if (kh == 0) {
+#pragma unroll
+            for (int q = 0; q < kDch; ++q) {
+              const int ch = ct + CT * q;
+              if (ch < d4) {
+#pragma unroll
+                for (int r = 0; r < kRP; ++r) {
+                  for (int h = 1; h < kKS; ++h) {
+                    const float4 v = s_part[((h - 1) * kGroupRows + rgp * kRP + r) * d4 + ch];
+                    acc4[r][q].x += v.x; acc4[r][q].y += v.y; acc4[r][q].z += v.z; acc4[r][q].w += v.w;
+                  }
+                }
+              }
+            }
+          }
+        }
+        if (kh == 0) {
+#pragma unroll
+          for (int q = 0; q < kDch; ++q) {
+            const int ch = ct + CT * q;
+            if (ch < d4) {
+#pragma unroll
+              for (int r = 0; r < kRP; ++r)
+                *reinterpret_cast<float4*>(s_A + (rgp * kRP + r) * D + ch * 4) = acc4[r][q];
+            }
           }
         }
       }
@@ -642,11 +744,13 @@ loss_rows16_kernel(RowsParams p) {
     __syncthreads();
   }
 
+  DBG_STAMP(6);
   // ---- deterministic final reduction by the last CTA: loss = sum / (A*T)
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) s_last = (atomicAdd(&p.info[kInfoDone2], 1) == (int)gridDim.x - 1);
   __syncthreads();
+  DBG_STAMP(7);
   if (!s_last) return;
   __threadfence();
   float s = 0.f;
@@ -663,12 +767,12 @@ loss_rows16_kernel(RowsParams p) {
   }
 }
 
-template <bool kWithGrad, int kRP, int kDch, int kDJ>
+template <bool kWithGrad, int kKS, int kRP, int kDch, int kDJ>
 static int launch_rows16(const RowsParams& p, size_t smem, cudaStream_t stream) {
-  C3D_CUDA(cudaFuncSetAttribute(loss_rows16_kernel<kWithGrad, kRP, kDch, kDJ>,
+  C3D_CUDA(cudaFuncSetAttribute(loss_rows16_kernel<kWithGrad, kKS, kRP, kDch, kDJ>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   KernelTimer kt__("loss_rows_kernel", stream);
-  loss_rows16_kernel<kWithGrad, kRP, kDch, kDJ><<<kNumSMs, 256, smem, stream>>>(p);
+  loss_rows16_kernel<kWithGrad, kKS, kRP, kDch, kDJ><<<kNumSMs, 256, smem, stream>>>(p);
   return check_launch("loss_rows16_kernel");
 }
 
@@ -833,17 +937,18 @@ extern "C" int c3d_proto_loss_forward(
   RowsPlan plan;
   if (!(v1 && v1[0] == '1') && plan_rows16(D, Kc, &plan) == 0) {
     p.tile_rows = plan.tile_rows; p.n_tiles = plan.n_tiles; p.ldl = plan.ldl;
-    // <grad, rows per thread in P3 (chunk-threads = 16*kRP), chunks per thread, D/32>
+    // <grad, k-splits, rows per thread in P3, chunks per thread, D/32>; chunk-threads
+    // CT = 256 / (kKS * 16 / kRP) must cover D/4 chunks (times kDch)
     if (need_grad) {
-      if (D <= 64) return launch_rows16<true, 1, 1, 2>(p, plan.smem, stream);
-      if (D <= 128) return launch_rows16<true, 2, 1, 4>(p, plan.smem, stream);
-      if (D <= 256) return launch_rows16<true, 4, 1, 8>(p, plan.smem, stream);
-      return launch_rows16<true, 4, 4, 32>(p, plan.smem, stream);
+      if (D <= 64) return launch_rows16<true, 4, 4, 1, 2>(p, plan.smem, stream);     // CT = 16
+      if (D <= 128) return launch_rows16<true, 2, 4, 1, 4>(p, plan.smem, stream);    // CT = 32
+      if (D <= 256) return launch_rows16<true, 1, 4, 1, 8>(p, plan.smem, stream);    // CT = 64
+      return launch_rows16<true, 1, 4, 4, 32>(p, plan.smem, stream);
     }
-    if (D <= 64) return launch_rows16<false, 1, 1, 2>(p, plan.smem, stream);
-    if (D <= 128) return launch_rows16<false, 2, 1, 4>(p, plan.smem, stream);
-    if (D <= 256) return launch_rows16<false, 4, 1, 8>(p, plan.smem, stream);
-    return launch_rows16<false, 4, 4, 32>(p, plan.smem, stream);
+    if (D <= 64) return launch_rows16<false, 4, 4, 1, 2>(p, plan.smem, stream);
+    if (D <= 128) return launch_rows16<false, 2, 4, 1, 4>(p, plan.smem, stream);
+    if (D <= 256) return launch_rows16<false, 1, 4, 1, 8>(p, plan.smem, stream);
+    return launch_rows16<false, 1, 4, 4, 32>(p, plan.smem, stream);
   }
   if (!need_grad) return launch_rows<false, 1>(p, smem, stream);
   if (D <= 128) return launch_rows<true, 1>(p, smem, stream);
@@ -908,3 +1013,11 @@ extern "C" int c3d_proto_loss_rows(const void* workspace, int batch, int dim, in
   C3D_CUDA(cudaMemcpyAsync(cnt, w.cnt_list, n, cudaMemcpyDeviceToDevice, stream));
   return C3D_OK;
 }
+
+#ifdef C3D_DEBUG_STAMPS
+extern "C" int c3d_debug_rows_stamps(long long* host16) {
+  C3D_CUDA(cudaDeviceSynchronize());
+  C3D_CUDA(cudaMemcpyFromSymbol(host16, g_rows_dbg, sizeof(long long) * 16));
+  return C3D_OK;
+}
+#endif

@@ -45,9 +45,16 @@ struct BankLayout {
 __device__ __forceinline__ void stage_bank_tile_issue(float* s_bank, const float* __restrict__ bank_n,
                                                       int r0, int rows, const BankLayout& L) {
   const int d4 = L.D >> 2;
-  for (int i = threadIdx.x; i < rows * d4; i += blockDim.x) {
-    const int r = i / d4, c = i - r * d4;
-    cp_async16(s_bank + L.off(r, c), bank_n + (size_t)(r0 + r) * L.D + c * 4);
+  const int nt = blockDim.x;
+  if (d4 <= nt && nt % d4 == 0) {  // fixed chunk per thread: no division in the loop
+    const int c = threadIdx.x % d4, rstep = nt / d4;
+    for (int r = threadIdx.x / d4; r < rows; r += rstep)
+      cp_async16(s_bank + L.off(r, c), bank_n + (size_t)(r0 + r) * L.D + c * 4);
+  } else {
+    for (int i = threadIdx.x; i < rows * d4; i += nt) {
+      const int r = i / d4, c = i - r * d4;
+      cp_async16(s_bank + L.off(r, c), bank_n + (size_t)(r0 + r) * L.D + c * 4);
+    }
   }
 }
 __device__ __forceinline__ void stage_bank_tile(float* s_bank, const float* __restrict__ bank_n, int r0,
@@ -56,49 +63,65 @@ __device__ __forceinline__ void stage_bank_tile(float* s_bank, const float* __re
   cp_async_wait_all();
 }
 
-// acc[r][i] = sum_d A[rg*4 + r][d] * bank[cg + 64 i][d]   (rows >= `rows` give 0)
+// acc[r][i] = sum_d A[rg*4 + r][d] * bank[cg + 64 i][d].  Columns >= `rows` are
+// computed on a clamped (valid) row and must be discarded by the caller: keeping the
+// inner loop branch-free lets the compiler batch the ten 128-bit loads of an iteration
+// (with per-column guards it serialised load -> use, 4x slower).
 __device__ __forceinline__ void tile_logits(const float* s_A, const float* s_bank, int rows,
                                             const BankLayout& L, float (&acc)[4][kColsPerThread]) {
   const int cg = threadIdx.x & 63, rg = threadIdx.x >> 6;
+  int rowoff[kColsPerThread], sw[kColsPerThread];
+#pragma unroll
+  for (int i = 0; i < kColsPerThread; ++i) {
+    const int c = min(cg + 64 * i, rows - 1);
+    rowoff[i] = c * L.ld;
+    sw[i] = L.swz ? (c & 7) : 0;
+  }
 #pragma unroll
   for (int r = 0; r < 4; ++r)
 #pragma unroll
     for (int i = 0; i < kColsPerThread; ++i) acc[r][i] = 0.f;
   const int d4 = L.D >> 2;
   const float4* a_base = reinterpret_cast<const float4*>(s_A) + (size_t)(rg * 4) * d4;
+#pragma unroll 2
   for (int j = 0; j < d4; ++j) {
-    float4 a[4];
+    float4 a[4], b[kColsPerThread];
 #pragma unroll
     for (int r = 0; r < 4; ++r) a[r] = a_base[r * d4 + j];  // warp-wide broadcast
 #pragma unroll
-    for (int i = 0; i < kColsPerThread; ++i) {
-      const int c = cg + 64 * i;
-      if (c < rows) {
-        const float4 b = *reinterpret_cast<const float4*>(s_bank + L.off(c, j));
+    for (int i = 0; i < kColsPerThread; ++i)
+      b[i] = *reinterpret_cast<const float4*>(s_bank + rowoff[i] + ((j ^ sw[i]) << 2));
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          acc[r][i] += a[r].x * b.x; acc[r][i] += a[r].y * b.y;
-          acc[r][i] += a[r].z * b.z; acc[r][i] += a[r].w * b.w;
-        }
+    for (int i = 0; i < kColsPerThread; ++i) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        acc[r][i] += a[r].x * b[i].x; acc[r][i] += a[r].y * b[i].y;
+        acc[r][i] += a[r].z * b[i].z; acc[r][i] += a[r].w * b[i].w;
       }
     }
   }
 }
 
-// dA[16][D] += G[16][k0 .. k0+rows) . bank_tile.  Thread (rgp, ct): kRP rows
-// rgp*kRP.., chunks ct + CT*q (CT = 16*kRP chunk-threads per row group, so all 256
-// threads work for D = 64*kRP/... see launch table).  G is read 4 k at a time as
-// warp-wide broadcasts; requires k0 % 4 == 0 and ldg % 4 == 0.
-template <int kRP, int kDch>
+// Partial dA[16][D] += G[16][ks .. ke) . bank_tile for this thread's k range.
+// Thread (kh, rgp, ct): k-split kh of kKS, rows rgp*kRP .. +kRP-1, chunks ct + CT*q with
+// CT = 256 / (kKS * 16 / kRP) chunk-threads.  kKS > 1 keeps all eight warps busy when
+// D/4 < 64 (D = 128: kKS = 2, kRP = 4, CT = 32); the caller adds the kKS partials.
+// G is read 4 k at a time as warp-wide broadcasts (k0, ldg multiples of 4).
+template <int kKS, int kRP, int kDch>
 __device__ __forceinline__ void tile_gradT(const float* s_G, int ldg, int k0, const float* s_bank,
                                            int rows, const BankLayout& L, float4 (&acc)[kRP][kDch]) {
-  constexpr int CT = 16 * kRP;
-  const int ct = threadIdx.x % CT, rgp = threadIdx.x / CT;
+  constexpr int kRowGroups = kGroupRows / kRP;
+  constexpr int CT = 256 / (kKS * kRowGroups);
+  const int ct = threadIdx.x % CT;
+  const int rgp = (threadIdx.x / CT) % kRowGroups;
+  const int kh = threadIdx.x / (CT * kRowGroups);
   const int d4 = L.D >> 2;
   if (ct >= d4) return;
+  const int per = (((rows + kKS - 1) / kKS) + 3) & ~3;   // k per split, multiple of 4
+  const int ks = min(kh * per, rows), ke = min(ks + per, rows);
   const float* g_base = s_G + (size_t)(rgp * kRP) * ldg + k0;
-  const int rows4 = rows & ~3;
-  for (int k = 0; k < rows4; k += 4) {
+  const int ke4 = ks + ((ke - ks) & ~3);
+  for (int k = ks; k < ke4; k += 4) {
     float4 g[kRP];
 #pragma unroll
     for (int r = 0; r < kRP; ++r) g[r] = *reinterpret_cast<const float4*>(g_base + r * ldg + k);
@@ -106,10 +129,12 @@ __device__ __forceinline__ void tile_gradT(const float* s_G, int ldg, int k0, co
     for (int q = 0; q < kDch; ++q) {
       const int ch = ct + CT * q;
       if (ch < d4) {
-        const float4 b0 = *reinterpret_cast<const float4*>(s_bank + L.off(k, ch));
-        const float4 b1 = *reinterpret_cast<const float4*>(s_bank + L.off(k + 1, ch));
-        const float4 b2 = *reinterpret_cast<const float4*>(s_bank + L.off(k + 2, ch));
-        const float4 b3 = *reinterpret_cast<const float4*>(s_bank + L.off(k + 3, ch));
+        const float* bp = s_bank + (size_t)k * L.ld;
+        const int m = L.swz ? (k & 7) : 0;   // k % 4 == 0: rows k..k+3 swizzle with m..m+3
+        const float4 b0 = *reinterpret_cast<const float4*>(bp + ((L.swz ? (ch ^ m) : ch) << 2));
+        const float4 b1 = *reinterpret_cast<const float4*>(bp + L.ld + ((L.swz ? (ch ^ (m + 1)) : ch) << 2));
+        const float4 b2 = *reinterpret_cast<const float4*>(bp + 2 * L.ld + ((L.swz ? (ch ^ (m + 2)) : ch) << 2));
+        const float4 b3 = *reinterpret_cast<const float4*>(bp + 3 * L.ld + ((L.swz ? (ch ^ (m + 3)) : ch) << 2));
 #pragma unroll
         for (int r = 0; r < kRP; ++r) {
           acc[r][q].x += g[r].x * b0.x; acc[r][q].y += g[r].x * b0.y; acc[r][q].z += g[r].x * b0.z; acc[r][q].w += g[r].x * b0.w;
@@ -120,7 +145,7 @@ __device__ __forceinline__ void tile_gradT(const float* s_G, int ldg, int k0, co
       }
     }
   }
-  for (int k = rows4; k < rows; ++k) {
+  for (int k = ke4; k < ke; ++k) {
 #pragma unroll
     for (int q = 0; q < kDch; ++q) {
       const int ch = ct + CT * q;
@@ -143,7 +168,12 @@ inline int plan_rows16(int D, int K, RowsPlan* out) {
   const size_t budget = 227 * 1024 - 1024;  // 1 KB for the kernel's static shared memory
   const BankLayout L = BankLayout::make(D);
   const int ldl = (K + 3) & ~3;
-  const size_t fixed = ((size_t)kGroupRows * D + (size_t)kGroupRows * ldl) * 4;
+  // the L region also holds the k-split partial sums of the gradient product
+  // ((kKS-1) x 16 x D floats; kKS = 4 for D <= 64, 2 for D <= 128, see the launch table)
+  const size_t part = (D <= 64) ? (size_t)3 * kGroupRows * D : (D <= 128 ? (size_t)kGroupRows * D : 0);
+  size_t lfloats = (size_t)kGroupRows * ldl;
+  if (lfloats < part) lfloats = part;
+  const size_t fixed = ((size_t)kGroupRows * D + lfloats) * 4;
   const size_t row = (size_t)L.ld * 4;
   if (fixed + 64 * row > budget) return -1;
   long long tr = (long long)((budget - fixed) / row);
