@@ -1,9 +1,10 @@
 // Stable multi-split of labelled pixels (shared by the prototype loss and the
 // EMA prototype update).
 //
-//   split_count    labels (+ keep_mask) -> per-tile per-class counts (9 B/px, coalesced)
-//   split_scan     per-scan exclusive prefix over tiles; the last CTA turns the
-//                  B*C totals into the segment table (start, index among non-empty)
+//   split_count_scan  labels (+ keep_mask) -> per-tile per-class counts (9 B/px,
+//                  coalesced); the last CTA of each scan turns them into exclusive
+//                  prefixes, the last scan's CTA builds the segment table (start, index
+//                  among non-empty) from the B*C totals -- one launch
 //   split_scatter  labelled pixels -> slots sorted by (segment, pixel); optional
 //                  entropy weight per slot; extra CTAs L2-normalise bank rows
 //
@@ -35,14 +36,23 @@ __device__ __forceinline__ int masked_class(const long long* __restrict__ labels
   return (int)l;
 }
 
-static __global__ void __launch_bounds__(256)
-split_count_kernel(const long long* __restrict__ labels, const uint8_t* __restrict__ keep, int HW,
-                  int nbps, int C, int ignore_label, int32_t* __restrict__ blk_cnt,
-                  int32_t* __restrict__ info) {
+// Count + scan in one launch.  Every CTA counts its tile; the last CTA of a scan
+// (atomic ticket per scan) turns the scan's tile counts into exclusive prefixes per
+// class, and the last scan's CTA turns the B*C totals into the segment table.
+// `info` is [8 + B] ints: info[8 + b] is scan b's ticket counter (zeroed by the caller).
+template <bool kClassMajor>
+__global__ void __launch_bounds__(256)
+split_count_scan_kernel(const long long* __restrict__ labels, const uint8_t* __restrict__ keep,
+                        int HW, int nbps, int B, int C, int ignore_label,
+                        int32_t* __restrict__ blk_cnt, int32_t* __restrict__ seg_cnt,
+                        int32_t* __restrict__ seg_start, int32_t* __restrict__ seg_tidx,
+                        int32_t* __restrict__ info) {
   __shared__ int s_cnt[kMaxClasses];
+  __shared__ int s_flag;
   if (threadIdx.x < C) s_cnt[threadIdx.x] = 0;
   __syncthreads();
   const int b = blockIdx.x / nbps, tile = blockIdx.x % nbps;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   bool bad = false;
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
@@ -57,23 +67,20 @@ split_count_kernel(const long long* __restrict__ labels, const uint8_t* __restri
   __syncthreads();
   if (threadIdx.x < C) blk_cnt[(size_t)blockIdx.x * C + threadIdx.x] = s_cnt[threadIdx.x];
   if (bad) atomicOr(&info[kInfoFlags], kFlagBadLabel);
-}
 
-// CTA b: warp per class, exclusive prefix of the tile counts of scan b.  The
-// last CTA to finish turns the B*C totals into the segment table.
-template <bool kClassMajor>
-__global__ void __launch_bounds__(1024)
-split_scan_kernel(int32_t* __restrict__ blk_cnt, int nbps, int B, int C,
-                 int32_t* __restrict__ seg_cnt, int32_t* __restrict__ seg_start,
-                 int32_t* __restrict__ seg_tidx, int32_t* __restrict__ info) {
-  const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nwarps = blockDim.x >> 5;
-  for (int c = warp; c < C; c += nwarps) {
+  // ---- last CTA of scan b: exclusive prefix of the tile counts, per class
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_flag = (atomicAdd(&info[8 + b], 1) == nbps - 1);
+  __syncthreads();
+  if (!s_flag) return;
+  __threadfence();
+  for (int c = warp; c < C; c += 8) {
     int carry = 0;
     for (int base = 0; base < nbps; base += 32) {
       const int i = base + lane;
       int32_t* p = blk_cnt + ((size_t)(b * nbps + i)) * C + c;
-      const int v = (i < nbps) ? *p : 0;
+      const int v = (i < nbps) ? __ldcg(p) : 0;
       int incl = v;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
@@ -85,12 +92,12 @@ split_scan_kernel(int32_t* __restrict__ blk_cnt, int nbps, int B, int C,
     }
     if (lane == 0) seg_cnt[seg_index<kClassMajor>(b, c, B, C)] = carry;
   }
-  __shared__ int s_last;
+  // ---- last scan: segment table over the B*C totals
   __threadfence();
   __syncthreads();
-  if (threadIdx.x == 0) s_last = (atomicAdd(&info[kInfoDone], 1) == B - 1);
+  if (threadIdx.x == 0) { info[8 + b] = 0; s_flag = (atomicAdd(&info[kInfoDone], 1) == B - 1); }
   __syncthreads();
-  if (!s_last) return;
+  if (!s_flag) return;
   __threadfence();
   if (warp == 0) {
     int carry = 0, tcarry = 0;

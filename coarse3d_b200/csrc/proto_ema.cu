@@ -54,7 +54,7 @@ static EmaWs carve_ema(void* base, int B, int C, int HW, int D, int M, long long
   const size_t nblk = (size_t)B * ((HW + kTile - 1) / kTile);
   size_t off = 0;
   auto take = [&](size_t n) { size_t o = off; off += align_up_e(n); return (char*)base + o; };
-  w.info = (int32_t*)take(8 * 4);
+  w.info = (int32_t*)take((size_t)(8 + B) * 4);  // [8 + B]: counters/flags + per-scan tickets
   w.blk_cnt = (int32_t*)take(nblk * C * 4);
   w.seg_cnt = (int32_t*)take((size_t)B * C * 4);
   w.seg_start = (int32_t*)take((size_t)B * C * 4);
@@ -313,48 +313,44 @@ ema_sinkhorn_kernel(const int32_t* __restrict__ seg_cnt, const int32_t* __restri
 }
 
 // ---------------------------------------------------------------- E4 -------
-// packed = [K*D sums | K counts]; one CTA per class, thread owns feature columns,
-// rows accumulated in order => bitwise reproducible.
+// packed = [K*D sums | K counts]; one CTA per class.  The class's rows are dealt
+// round-robin to `nsplit` warps, each accumulating its rows in order into a private
+// shared-memory copy (lane owns feature columns); the copies are then added in warp
+// order.  Fixed assignment + fixed order => atomics-free and bitwise reproducible.
 __global__ void __launch_bounds__(256)
 ema_segsum_kernel(const int32_t* __restrict__ seg_cnt, const int32_t* __restrict__ seg_start,
                   const int32_t* __restrict__ info, int B, int M, int D, int K, int ignore_label,
-                  int max_rows, const float* __restrict__ feat, const int32_t* __restrict__ maskv,
-                  const int32_t* __restrict__ sub, float* __restrict__ packed) {
-  extern __shared__ float s_sum[];  // [M][D] then [M] counts
-  float* s_cnt = s_sum + (size_t)M * D;
+                  int max_rows, int nsplit, const float* __restrict__ feat,
+                  const int32_t* __restrict__ maskv, const int32_t* __restrict__ sub,
+                  float* __restrict__ packed) {
+  extern __shared__ float s_sum[];  // [nsplit][M*D + M]
+  const int stride = M * D + M;
   const int c = blockIdx.x;
-  for (int i = threadIdx.x; i < M * D + M; i += blockDim.x) s_sum[i] = 0.f;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < nsplit * stride; i += blockDim.x) s_sum[i] = 0.f;
   __syncthreads();
   int n = 0, start = 0;
   if (c != ignore_label && info[kInfoPl] <= max_rows) {
     start = seg_start[c * B];
     for (int b = 0; b < B; ++b) n += seg_cnt[c * B + b];
   }
-  // rows in order, 4 at a time so that the loads of a group are all in flight
-  for (int i0 = 0; i0 < n; i0 += 4) {
-    int mk[4], sb[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int slot = start + i0 + j;
-      const bool in = (i0 + j) < n;
-      mk[j] = in ? maskv[slot] : 0;  // m_q = q * mask, c_q = feat * mask (:363-375)
-      sb[j] = in ? sub[slot] : 0;
-    }
-    for (int d = threadIdx.x; d < D; d += blockDim.x) {
-      float v[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) v[j] = mk[j] ? feat[(size_t)(start + i0 + j) * D + d] : 0.f;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) if (mk[j]) s_sum[sb[j] * D + d] += v[j];
-    }
-    if (threadIdx.x == 0) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) if (mk[j]) s_cnt[sb[j]] += 1.0f;
+  if (warp < nsplit) {
+    float* acc = s_sum + (size_t)warp * stride;
+    for (int i = warp; i < n; i += nsplit) {
+      const int slot = start + i;
+      if (!maskv[slot]) continue;  // m_q = q * mask, c_q = feat * mask (:363-375)
+      const int m = sub[slot];
+      for (int d = lane; d < D; d += 32) acc[m * D + d] += feat[(size_t)slot * D + d];
+      if (lane == 0) acc[M * D + m] += 1.0f;
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < M * D; i += blockDim.x) packed[(size_t)c * M * D + i] = s_sum[i];
-  if ((int)threadIdx.x < M) packed[(size_t)K * D + c * M + threadIdx.x] = s_cnt[threadIdx.x];
+  for (int i = threadIdx.x; i < stride; i += blockDim.x) {
+    float t = 0.f;
+    for (int w = 0; w < nsplit; ++w) t += s_sum[(size_t)w * stride + i];
+    if (i < M * D) packed[(size_t)c * M * D + i] = t;
+    else packed[(size_t)K * D + c * M + (i - M * D)] = t;
+  }
 }
 
 // ---------------------------------------------------------------- E5 -------
@@ -441,18 +437,19 @@ extern "C" int c3d_proto_ema_accumulate(
   int tile_rows, n_tiles; size_t smem;
   C3D_REQUIRE(ema_rows_config(D, K, &tile_rows, &n_tiles, &smem) == 0,
               "bank does not fit shared memory tiling (D=%d, K=%d)", D, K);
-  const size_t seg_smem = ((size_t)M * D + M) * sizeof(float);
+  int seg_split = 8;
+  while (seg_split > 1 && (size_t)seg_split * ((size_t)M * D + M) * sizeof(float) > 200 * 1024) seg_split >>= 1;
+  const size_t seg_smem = (size_t)seg_split * ((size_t)M * D + M) * sizeof(float);
   C3D_REQUIRE(seg_smem <= 227 * 1024, "M*D too large for the segmented-sum kernel");
 
-  C3D_CUDA(cudaMemsetAsync(w.info, 0, 8 * 4, stream));
+  C3D_CUDA(cudaMemsetAsync(w.info, 0, (size_t)(8 + B) * 4, stream));
   if (proto_target) C3D_CUDA(cudaMemsetAsync(proto_target, 0, (size_t)B * HW * 4, stream));
   int rc;
-  { KernelTimer kt__("split_count_kernel", stream); split_count_kernel<<<nblk, 256, 0, stream>>>((const long long*)label, nullptr, HW, nbps, C,
-                                               ignore_label, w.blk_cnt, w.info); }
-  if ((rc = check_launch("split_count_kernel"))) return rc;
-  { KernelTimer kt__("split_scan_kernel", stream); split_scan_kernel<true><<<B, 1024, 0, stream>>>(w.blk_cnt, nbps, B, C, w.seg_cnt, w.seg_start,
-                                                  w.seg_tidx, w.info); }
-  if ((rc = check_launch("split_scan_kernel"))) return rc;
+  { KernelTimer kt__("split_count_scan_kernel", stream);
+    split_count_scan_kernel<true><<<nblk, 256, 0, stream>>>(
+        (const long long*)label, nullptr, HW, nbps, B, C, ignore_label, w.blk_cnt, w.seg_cnt, w.seg_start,
+        w.seg_tidx, w.info); }
+  if ((rc = check_launch("split_count_scan_kernel"))) return rc;
   { KernelTimer kt__("split_scatter_kernel", stream); split_scatter_kernel<true, false><<<nblk + 16, 256, 0, stream>>>(
       (const long long*)label, nullptr, nullptr, HW, nbps, nblk, B, C, ignore_label, w.blk_cnt,
       w.seg_start, w.pix_list, w.cls_list, nullptr, nullptr, prototypes, K, D, w.bank_n); }
@@ -478,7 +475,7 @@ extern "C" int c3d_proto_ema_accumulate(
     C3D_CUDA(cudaFuncSetAttribute(ema_segsum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)seg_smem));
   { KernelTimer kt__("ema_segsum_kernel", stream); ema_segsum_kernel<<<C, 256, seg_smem, stream>>>(w.seg_cnt, w.seg_start, w.info, B, M, D, K,
-                                                  ignore_label, (int)max_rows, w.feat, w.maskv,
+                                                  ignore_label, (int)max_rows, seg_split, w.feat, w.maskv,
                                                   w.sub, packed); }
   return check_launch("ema_segsum_kernel");
 }

@@ -53,6 +53,7 @@ struct LossWs {
   float* w_list;       // [cap] weights -> in-place CDF -> (int) distinct-slot list
   int32_t* cnt_list;   // [cap] sampling multiplicity
   float* loss_part;    // [max_rows]
+  int32_t* row_pix;    // [max_rows] b*HW + pixel of each distinct row
   float* grad_rows;    // [max_rows * D]
   float* bank_n;       // [(C-1)*M*D] normalised prototypes, classes 1..C-1
   size_t max_rows;
@@ -69,7 +70,7 @@ static LossWs carve(void* base, int B, int C, int HW, int D, int M, int A) {
   if (max_rows > cap) max_rows = cap;
   size_t off = 0;
   auto take = [&](size_t n) { size_t o = off; off += align_up(n); return (char*)base + o; };
-  w.info = (int32_t*)take(8 * 4);
+  w.info = (int32_t*)take((size_t)(8 + B) * 4);  // [8 + B]: counters/flags + per-scan tickets
   w.blk_cnt = (int32_t*)take(nblk * C * 4);
   w.seg_cnt = (int32_t*)take((size_t)B * C * 4);
   w.seg_start = (int32_t*)take((size_t)B * C * 4);
@@ -82,6 +83,7 @@ static LossWs carve(void* base, int B, int C, int HW, int D, int M, int A) {
   w.w_list = (float*)take(cap * 4);
   w.cnt_list = (int32_t*)take(cap * 4);
   w.loss_part = (float*)take(max_rows * 4);
+  w.row_pix = (int32_t*)take(max_rows * 4);
   w.grad_rows = (float*)take(max_rows * D * 4);
   w.bank_n = (float*)take((size_t)(C - 1) * M * D * 4);
   w.max_rows = max_rows;
@@ -111,6 +113,8 @@ loss_sample_kernel(const int32_t* __restrict__ seg_cnt, const int32_t* __restric
   const int seg = blockIdx.x, nseg = gridDim.x;
   const int n = seg_cnt[seg];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int kCdfSmem = 2048;
+  __shared__ float s_cdf[kCdfSmem];
   __shared__ float s_warp[8];
   __shared__ float s_carry;
   __shared__ int s_iw[8];
@@ -134,12 +138,18 @@ loss_sample_kernel(const int32_t* __restrict__ seg_cnt, const int32_t* __restric
       }
       if (bad) atomicOr(&info[kInfoFlags], kFlagBadKeep);
     } else {
-      // inclusive scan of the weights -> CDF (in place), 256 elements per step
+      // inclusive scan of the weights -> CDF, 256 elements per step; small segments
+      // (the weak-label regime) keep the CDF in shared memory for the binary searches
+      float* cdf = w_list + start;
+      if (n <= kCdfSmem) {
+        for (int i = threadIdx.x; i < n; i += 256) s_cdf[i] = w_list[start + i];
+        cdf = s_cdf;
+      }
       if (threadIdx.x == 0) s_carry = 0.f;
       __syncthreads();
       for (int base = 0; base < n; base += 256) {
         const int i = base + threadIdx.x;
-        float v = (i < n) ? w_list[start + i] : 0.f;
+        float v = (i < n) ? cdf[i] : 0.f;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
           float u = __shfl_up_sync(0xffffffffu, v, o);
@@ -149,7 +159,7 @@ loss_sample_kernel(const int32_t* __restrict__ seg_cnt, const int32_t* __restric
         __syncthreads();
         float pre = s_carry;
         for (int w = 0; w < warp; ++w) pre += s_warp[w];
-        if (i < n) w_list[start + i] = pre + v;
+        if (i < n) cdf[i] = pre + v;
         __syncthreads();
         if (threadIdx.x == 255) s_carry = pre + v;
         __syncthreads();
@@ -163,7 +173,7 @@ loss_sample_kernel(const int32_t* __restrict__ seg_cnt, const int32_t* __restric
         int lo = 0, hi = n - 1;  // first slot with cdf > x (clamped)
         while (lo < hi) {
           const int mid = (lo + hi) >> 1;
-          if (w_list[start + mid] > x) hi = mid; else lo = mid + 1;
+          if (cdf[mid] > x) hi = mid; else lo = mid + 1;
         }
         atomicAdd(&cnt_list[start + lo], 1);
       }
@@ -232,6 +242,7 @@ struct RowsParams {
   const int32_t* seg_of_t;
   int32_t* info;
   float* loss_part;        // [rows]
+  int32_t* row_pix;        // [rows]
   float* grad_rows;        // [rows * D]
   float* loss_out;         // [1]
   int HW, D, M, Kc, A, tile_rows, n_tiles, ldl;
@@ -304,6 +315,7 @@ loss_rows_kernel(RowsParams p) {
       cnt = __ldcg(p.cnt_list + slot);
       const int gpix = p.pix_list[slot];
       cls = p.cls_list[slot];
+      if (lane == 0) p.row_pix[row] = gpix;
       const int b = gpix / p.HW, pix = gpix - b * p.HW;
       const float* src = p.feats + (size_t)b * D * p.HW + pix;
       float n2 = 0.f;
@@ -544,7 +556,10 @@ loss_rows16_kernel(RowsParams p) {
         const int d = lane + 32 * j;
         if (d < D) s_A[rl * D + d] = areg[rr][j];
       }
-      if (lane == 0) { s_cnt[rl] = cnt2[rr]; s_cls[rl] = cls2[rr]; s_inv[rl] = inv_norm; }
+      if (lane == 0) {
+        s_cnt[rl] = cnt2[rr]; s_cls[rl] = cls2[rr]; s_inv[rl] = inv_norm;
+        if (act[rr]) p.row_pix[grp * kGroupRows + rl] = gpix2[rr];
+      }
     }
     DBG_STAMP(1);
     if (!staged) { cp_async_wait_all(); staged = true; }
@@ -821,21 +836,18 @@ static int launch_fill(void* dst, size_t nbytes, cudaStream_t stream) {
 
 // ---------------------------------------------------------------- K7 -------
 __global__ void __launch_bounds__(256)
-loss_grad_scatter_kernel(const float* __restrict__ grad_rows, const int32_t* __restrict__ pix_list,
-                         const int32_t* __restrict__ dist_list, const int32_t* __restrict__ seg_start,
-                         const int32_t* __restrict__ row_base, const int32_t* __restrict__ seg_of_t,
+loss_grad_scatter_kernel(const float* __restrict__ grad_rows, const int32_t* __restrict__ row_pix,
                          int32_t* __restrict__ info, const float* __restrict__ grad_out, int HW, int D,
                          float* __restrict__ grad_feats) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_rows = info[kInfoU], T = info[kInfoT];
+  const int n_rows = info[kInfoU];
   if (!info[kInfoHasGrad]) {
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&info[kInfoFlags], kFlagNoGradRows);
     return;
   }
   const float go = __ldg(grad_out);
   for (int row = blockIdx.x * 8 + warp; row < n_rows; row += gridDim.x * 8) {
-    const int slot = slot_of_row(row, T, row_base, seg_of_t, seg_start, dist_list);
-    const int gpix = __ldg(pix_list + slot);
+    const int gpix = __ldcg(row_pix + row);
     const int b = gpix / HW, pix = gpix - b * HW;
     float* dst = grad_feats + (size_t)b * D * HW + pix;
     const float* src = grad_rows + (size_t)row * D;
@@ -902,16 +914,13 @@ extern "C" int c3d_proto_loss_forward(
   C3D_REQUIRE(rows_config(D, Kc, &tile_rows, &n_tiles, &smem) == 0,
               "bank does not fit shared memory tiling (D=%d, Kc=%d)", D, Kc);
 
-  C3D_CUDA(cudaMemsetAsync(w.info, 0, 8 * 4, stream));
+  C3D_CUDA(cudaMemsetAsync(w.info, 0, (size_t)(8 + B) * 4, stream));
   int rc;
-  { KernelTimer kt__("split_count_kernel", stream);
-    split_count_kernel<<<nblk, 256, 0, stream>>>((const long long*)labels, keep_mask, HW, nbps, C,
-                                                 ignore_label, w.blk_cnt, w.info); }
-  if ((rc = check_launch("split_count_kernel"))) return rc;
-  { KernelTimer kt__("split_scan_kernel", stream);
-    split_scan_kernel<false><<<B, 1024, 0, stream>>>(w.blk_cnt, nbps, B, C, w.seg_cnt, w.seg_start,
-                                                     w.seg_tidx, w.info); }
-  if ((rc = check_launch("split_scan_kernel"))) return rc;
+  { KernelTimer kt__("split_count_scan_kernel", stream);
+    split_count_scan_kernel<false><<<nblk, 256, 0, stream>>>(
+        (const long long*)labels, keep_mask, HW, nbps, B, C, ignore_label, w.blk_cnt, w.seg_cnt, w.seg_start,
+        w.seg_tidx, w.info); }
+  if ((rc = check_launch("split_count_scan_kernel"))) return rc;
   const int bank_blocks = 16;
   { KernelTimer kt__("split_scatter_kernel", stream);
     split_scatter_kernel<false, true><<<nblk + bank_blocks, 256, 0, stream>>>(
@@ -930,7 +939,7 @@ extern "C" int c3d_proto_loss_forward(
   p.feats = feats; p.bank_n = w.bank_n; p.pix_list = w.pix_list; p.cls_list = w.cls_list;
   p.cnt_list = w.cnt_list; p.dist_list = reinterpret_cast<const int32_t*>(w.w_list);
   p.seg_start = w.seg_start; p.row_base = w.row_base; p.seg_of_t = w.seg_of_t; p.info = w.info;
-  p.loss_part = w.loss_part; p.grad_rows = w.grad_rows; p.loss_out = loss_out;
+  p.loss_part = w.loss_part; p.row_pix = w.row_pix; p.grad_rows = w.grad_rows; p.loss_out = loss_out;
   p.HW = HW; p.D = D; p.M = M; p.Kc = Kc; p.A = num_anchor; p.tile_rows = tile_rows;
   p.n_tiles = n_tiles; p.temperature = temperature; p.base_temperature = base_temperature;
   const char* v1 = getenv("C3D_LOSS_ROWS_V1");
@@ -975,8 +984,7 @@ extern "C" int c3d_proto_loss_backward(int batch, int dim, int proj_h, int proj_
   if (!grad_is_zeroed && (rc = launch_fill(grad_feats, (size_t)B * D * HW * 4, stream))) return rc;
   { KernelTimer kt__("loss_grad_scatter_kernel", stream);
     loss_grad_scatter_kernel<<<kNumSMs * 2, 256, 0, stream>>>(
-        w.grad_rows, w.pix_list, reinterpret_cast<const int32_t*>(w.w_list), w.seg_start,
-        w.row_base, w.seg_of_t, w.info, grad_out, HW, D, grad_feats); }
+        w.grad_rows, w.row_pix, w.info, grad_out, HW, D, grad_feats); }
   return check_launch("loss_grad_scatter_kernel");
 }
 
