@@ -325,10 +325,12 @@ def main():
 
 def run_e2e(args, step, dev, world, K):
     """Same step through the reference-shaped classes, inputs starting in pinned
-    host memory every step (raw points, CSR offsets, projected weak labels) and
+    host memory every step (raw points, CSR offsets, per-point weak labels) and
     results read back to the host (loss scalar, per-point KNN labels).  The CNN
     activations (features / probabilities / argmax) are produced on the device in
-    the reference too (trainer.py:625-638), so they stay resident."""
+    the reference too (trainer.py:625-638), so they stay resident.  The projected weak
+    label image is built on the device by the fused projection (8f-1), so the labels
+    travel per point."""
     import torch.distributed as dist
     from coarse3d_b200.pc_processor.dataset.preprocess import RangeProjection
     from coarse3d_b200.pc_processor.loss import ContrastMEMLoss
@@ -344,12 +346,12 @@ def run_e2e(args, step, dev, world, K):
     for s in step.sets:
         host.append(dict(points=torch.from_numpy(s.host_points).pin_memory(),
                          offsets=torch.from_numpy(s.host_offsets).pin_memory(),
-                         labels=s.labels.cpu().pin_memory(), keep=s.keep_mask.cpu().pin_memory()))
+                         weak=torch.from_numpy(s.host_weak.astype(np.int32)).pin_memory()))
     # double-buffered device inputs / pinned outputs: the H2D copies of step i+1 (copy-in
     # stream) and the D2H of step i-1 (copy-out stream) overlap the compute of step i
     NB = 2
     d_in = [dict(points=torch.empty_like(step.sets[0].points), offsets=torch.empty_like(step.sets[0].offsets),
-                 labels=torch.empty_like(step.sets[0].labels), keep=torch.empty_like(step.sets[0].keep_mask))
+                 weak=torch.empty((step.n_points,), dtype=torch.int32, device=dev))
             for _ in range(NB)]
     h_out = [dict(loss=torch.zeros((), dtype=torch.float32).pin_memory(),
                   knn=torch.zeros((step.n_points,), dtype=torch.int64).pin_memory()) for _ in range(NB)]
@@ -368,17 +370,20 @@ def run_e2e(args, step, dev, world, K):
         di, ho = d_in[j], h_out[j]
         s_in.wait_event(ev_done[j])          # buffer j free again (compute of step i-NB done)
         with torch.cuda.stream(s_in):
-            for k in ("points", "offsets", "labels", "keep"):
+            for k in ("points", "offsets", "weak"):
                 di[k].copy_(h[k], non_blocking=True)
             ev_in[j].record(s_in)
         main.wait_event(ev_in[j])
-        pr = rp.doProjectionBatch(di["points"], di["offsets"], buffers=step.proj_bufs[j])
+        # projection fused with label-image assembly: the weak labels travel per point
+        pr = rp.doProjectionAssembleBatch(di["points"], di["offsets"], weak_label=di["weak"],
+                                          buffers=step.proj_bufs[j])
+        labels = pr.train_label
         feats = s.feats.requires_grad_(True)
         feats.grad = None
-        loss = crit(feats=feats, output=s.probs, labels=di["labels"], keep_mask=di["keep"],
+        loss = crit(feats=feats, output=s.probs, labels=labels, keep_mask=None,
                     proto_queue=bank.prototypes.detach().unsqueeze(0))
         loss.backward()
-        bank.update(s.feats.detach(), di["labels"])
+        bank.update(s.feats.detach(), labels)
         lab = knn.forward_batch(pr.proj_range, pr.uproj_depth, s.argmax, pr.uproj_x_idx,
                                 pr.uproj_y_idx, di["offsets"])
         loss_d = loss.detach()
@@ -412,9 +417,9 @@ def run_e2e(args, step, dev, world, K):
     return {"value": world * B * K / (float(ms.item()) * 1e-3), "unit": "scans/s",
             "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": K,
             "ms_per_step": float(ms.item()) / K,
-            "api": "RangeProjection.doProjectionBatch + ContrastMEMLoss()(..).backward() + "
+            "api": "RangeProjection.doProjectionAssembleBatch + ContrastMEMLoss()(..).backward() + "
                    "PrototypeBank.update + KNN.forward_batch",
-            "host_inputs": "points, offsets, projected weak labels, keep mask (pinned); "
+            "host_inputs": "points, offsets, per-point weak labels int32 (pinned); "
                            "CNN activations resident on device as in the reference",
             "pipelining": "double-buffered: H2D / compute / D2H of consecutive steps on three streams"}
 

@@ -163,6 +163,67 @@ resolve_pixels_kernel(const float* __restrict__ points, int c_in,
   }
 }
 
+// ---------------------------------------------------------------- f1 -------
+// Resolve pass fused with the projection's caller: the label images and the 5-channel
+// network input are written straight from the z-buffer winners
+// (wss_sem_kitti_loader.py:124-132,159-172; trainer.py:600-608), so neither the
+// (H,W,4) projected point cloud nor a CPU-side gather is needed.
+__global__ void __launch_bounds__(256)
+resolve_assemble_kernel(const float* __restrict__ points, const int32_t* __restrict__ offsets,
+                        int HW, long long total_px, unsigned long long* __restrict__ zbuf,
+                        const int32_t* __restrict__ sem_label, const int32_t* __restrict__ weak_label,
+                        const float* __restrict__ mean, const float* __restrict__ stdv,
+                        float* __restrict__ proj_range, int32_t* __restrict__ proj_idx,
+                        float* __restrict__ feature, long long* __restrict__ train_label,
+                        long long* __restrict__ eval_label) {
+  const long long q0 = ((long long)blockIdx.x * blockDim.x) * 2 + threadIdx.x;
+  unsigned long long key[2]; bool in[2];
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const long long q = q0 + j * 256;
+    in[j] = q < total_px;
+    key[j] = in[j] ? __ldcs(zbuf + q) : ~0ull;
+  }
+  float4 pt[2]; int sl[2], wl[2];
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    pt[j] = make_float4(-1.f, -1.f, -1.f, -1.f); sl[j] = 0; wl[j] = 0;
+    if (key[j] != ~0ull) {
+      const long long q = q0 + j * 256;
+      const size_t row = (size_t)__ldg(offsets + (int)(q / HW)) + (uint32_t)key[j];
+      pt[j] = __ldg(reinterpret_cast<const float4*>(points) + row);
+      if (sem_label) sl[j] = __ldg(sem_label + row);
+      if (weak_label) wl[j] = __ldg(weak_label + row);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    if (!in[j]) continue;
+    const long long q = q0 + j * 256;
+    const bool valid = key[j] != ~0ull;
+    const float rng = valid ? key_depth((uint32_t)(key[j] >> 32)) : -1.0f;
+    if (proj_range) proj_range[q] = rng;
+    if (proj_idx) proj_idx[q] = valid ? (int)(uint32_t)key[j] : -1;
+    // loader :124-132 builds float32 label images, trainer :600-601 casts them to int64
+    if (eval_label) eval_label[q] = (long long)(float)sl[j];
+    if (train_label) train_label[q] = (long long)(float)wl[j];
+    float f[5];
+    f[0] = rng; f[1] = pt[j].x; f[2] = pt[j].y; f[3] = pt[j].z;
+    f[4] = ((pt[j].w != -1.0f) ? 1.0f : 0.0f) * pt[j].w;          // loader :161-164
+    const int b = (int)(q / HW);
+    const long long pix = q - (long long)b * HW;
+    float* dst = feature + (size_t)b * 5 * HW + pix;
+    if (mean) {
+      const float m = (sl[j] > 0) ? 1.0f : 0.0f;                    // eval_mask, trainer :603
+#pragma unroll
+      for (int c = 0; c < 5; ++c) f[c] = (f[c] - mean[c]) / stdv[c] * m;  // trainer :604-608
+    }
+#pragma unroll
+    for (int c = 0; c < 5; ++c) dst[(size_t)c * HW] = f[c];
+    if (valid) zbuf[q] = ~0ull;
+  }
+}
+
 }  // namespace c3d
 
 using namespace c3d;
@@ -248,4 +309,71 @@ extern "C" int c3d_project_batch(
     if (rc) return rc;
   }
   return C3D_OK;
+}
+
+extern "C" int c3d_project_assemble_batch(
+    const float* points, const int32_t* offsets, int batch, int64_t total_points,
+    const float* depth_override, const int32_t* sem_label, const int32_t* weak_label,
+    const float* img_mean, const float* img_std, double abs_fov_left, double fov_hori,
+    double abs_fov_down, double fov_vert, int proj_h, int proj_w, float* feature,
+    int64_t* train_label, int64_t* eval_label, float* proj_range, int32_t* proj_idx,
+    int32_t* uproj_x_idx, int32_t* uproj_y_idx, float* uproj_depth, void* workspace,
+    int workspace_is_clean, int32_t* status_flags, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  C3D_REQUIRE(batch > 0 && batch <= kMaxBatch, "batch must be in [1, %d], got %d", kMaxBatch, batch);
+  C3D_REQUIRE(proj_h > 0 && proj_w > 0, "bad image size %dx%d", proj_h, proj_w);
+  C3D_REQUIRE(total_points >= 0 && total_points < (1ll << 31), "total_points out of range");
+  C3D_REQUIRE((long long)batch * proj_h * proj_w < (1ll << 31), "batch*H*W must be < 2^31");
+  C3D_REQUIRE(fov_hori > 0 && fov_vert > 0, "field of view must be positive");
+  C3D_REQUIRE(offsets && feature && workspace && status_flags, "null pointer argument");
+  C3D_REQUIRE(total_points == 0 || (points && uproj_x_idx && uproj_y_idx && uproj_depth),
+              "null per-point pointer");
+  C3D_REQUIRE((reinterpret_cast<uintptr_t>(points) & 15) == 0, "points must be 16 B aligned (x,y,z,i rows)");
+  C3D_REQUIRE((img_mean == nullptr) == (img_std == nullptr), "img_mean and img_std go together");
+  C3D_REQUIRE(!img_mean || sem_label, "normalisation needs sem_label (eval_mask = eval_label > 0)");
+  C3D_REQUIRE(!eval_label || sem_label, "eval_label output needs sem_label");
+  C3D_REQUIRE(!train_label || weak_label, "train_label output needs weak_label");
+
+  ProjParams p;
+  p.abs_left = (float)abs_fov_left; p.fov_hori = (float)fov_hori;
+  p.abs_down = (float)abs_fov_down; p.fov_vert = (float)fov_vert;
+  p.wf = (float)proj_w; p.hf = (float)proj_h;
+  p.wmax = (float)(proj_w - 1); p.hmax = (float)(proj_h - 1);
+  p.H = proj_h; p.W = proj_w;
+  p.tol_x = p.wf * 1.0e-6f;
+  p.tol_y = p.hf * (2.0e-6f / p.fov_vert + 1.0e-6f);
+  p.sx = p.wf / p.fov_hori;
+  p.sy = p.hf / p.fov_vert;
+  const long long total_px = (long long)batch * proj_h * proj_w;
+  auto* zbuf = reinterpret_cast<unsigned long long*>(workspace);
+  if (!workspace_is_clean) {
+    KernelTimer kt__("zbuf_memset", stream);
+    C3D_CUDA(cudaMemsetAsync(zbuf, 0xFF, (size_t)total_px * sizeof(unsigned long long), stream));
+  }
+  const char* env = getenv("C3D_PROJECT_F64_ONLY");
+  const bool hybrid = !(env && env[0] == '1');
+  const int threads = 256;
+  if (total_points > 0) {
+    int grid = (int)((total_points + threads - 1) / threads);
+    size_t smem = (size_t)(batch + 1) * sizeof(int32_t);
+    KernelTimer kt__("project_points_kernel", stream);
+    if (hybrid)
+      project_points_kernel<true, true><<<grid, threads, smem, stream>>>(
+          points, 4, offsets, batch, (int)total_points, depth_override, p, uproj_x_idx, uproj_y_idx,
+          uproj_depth, zbuf, status_flags);
+    else
+      project_points_kernel<false, true><<<grid, threads, smem, stream>>>(
+          points, 4, offsets, batch, (int)total_points, depth_override, p, uproj_x_idx, uproj_y_idx,
+          uproj_depth, zbuf, status_flags);
+    int rc = check_launch("project_points_kernel");
+    if (rc) return rc;
+  }
+  {
+    int grid = (int)((total_px + 2 * threads - 1) / (2 * threads));
+    KernelTimer kt__("resolve_assemble_kernel", stream);
+    resolve_assemble_kernel<<<grid, threads, 0, stream>>>(
+        points, offsets, proj_h * proj_w, total_px, zbuf, sem_label, weak_label, img_mean, img_std,
+        proj_range, proj_idx, feature, (long long*)train_label, (long long*)eval_label);
+    return check_launch("resolve_assemble_kernel");
+  }
 }

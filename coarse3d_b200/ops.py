@@ -113,6 +113,53 @@ def project_batch(points, offsets, fov: Fov, proj_h, proj_w, depth=None,
                       b.uproj_x_idx, b.uproj_y_idx, b.uproj_depth, b.flags)
 
 
+# --------------------------------------------------------------------- f1 --
+class Assembled(NamedTuple):
+    feature: torch.Tensor      # (B,5,H,W) f32 [range,x,y,z,intensity], normalised if mean/std given
+    train_label: Optional[torch.Tensor]  # (B,H,W) i64
+    eval_label: Optional[torch.Tensor]   # (B,H,W) i64
+    proj_range: torch.Tensor   # (B,H,W) f32
+    proj_idx: torch.Tensor     # (B,H,W) i32
+    uproj_x_idx: torch.Tensor  # (sum N,) i32
+    uproj_y_idx: torch.Tensor
+    uproj_depth: torch.Tensor
+    flags: torch.Tensor
+
+
+def project_assemble_batch(points, offsets, fov: Fov, proj_h, proj_w, sem_label=None,
+                           weak_label=None, img_mean=None, img_std=None, depth=None,
+                           buffers: ProjectionBuffers = None) -> Assembled:
+    """Projection fused with its caller (loader :124-172, trainer :600-608): label images
+    and the 5-channel network input straight from the z-buffer winners.
+
+    points (sum N, 4) f32; sem_label / weak_label (sum N,) int32; img_mean / img_std (5,) f32.
+    """
+    _need_cuda(points=points, offsets=offsets, depth=depth, sem_label=sem_label,
+               weak_label=weak_label, img_mean=img_mean, img_std=img_std)
+    if points.dtype != torch.float32 or points.dim() != 2 or points.shape[1] != 4:
+        raise ValueError("points must be (N, 4) float32")
+    for name, t in (("sem_label", sem_label), ("weak_label", weak_label)):
+        if t is not None and (t.dtype != torch.int32 or t.numel() != points.shape[0]):
+            raise ValueError("%s must be (N,) int32" % name)
+    batch, total = offsets.numel() - 1, points.shape[0]
+    b = buffers
+    if b is None:
+        b = ProjectionBuffers(batch, total, 4, proj_h, proj_w, points.device)
+    dev = points.device
+    feature = torch.empty((batch, 5, proj_h, proj_w), dtype=torch.float32, device=dev)
+    train = torch.empty((batch, proj_h, proj_w), dtype=torch.int64, device=dev) if weak_label is not None else None
+    evall = torch.empty((batch, proj_h, proj_w), dtype=torch.int64, device=dev) if sem_label is not None else None
+    check(lib.c3d_project_assemble_batch(
+        _p(points), _p(offsets), batch, total, _p(depth), _p(sem_label), _p(weak_label),
+        _p(img_mean), _p(img_std), fov.abs_fov_left, fov.fov_hori, fov.abs_fov_down, fov.fov_vert,
+        proj_h, proj_w, _p(feature), _p(train), _p(evall), _p(b.proj_range), _p(b.proj_idx),
+        _p(b.uproj_x_idx), _p(b.uproj_y_idx), _p(b.uproj_depth), _p(b.workspace),
+        1 if b.clean else 0, _p(b.flags), _stream()))
+    b.clean = True
+    return Assembled(feature, train, evall, b.proj_range, b.proj_idx, b.uproj_x_idx, b.uproj_y_idx,
+                     b.uproj_depth, b.flags)
+
+
 # --------------------------------------------------------------------- a4 --
 def gaussian_kernel(kernel_size=3, sigma=2):
     """get_gaussian_kernel (knn.py:11-33): same torch ops, CPU, float32."""

@@ -48,6 +48,15 @@ class RangeProjection(object):
         return ops.project_batch(points, offsets, self.fov, self.proj_h, self.proj_w, depth,
                                  buffers)
 
+    def doProjectionAssembleBatch(self, points, offsets, sem_label=None, weak_label=None,
+                                  img_mean=None, img_std=None, depth=None, buffers=None):
+        """CSR batch on the device, fused with what the loaders / trainer build from the
+        projection (wss_sem_kitti_loader.py:124-172, trainer.py:600-608): the 5-channel
+        input (optionally normalised) and the int64 train / eval label images.  See
+        ops.project_assemble_batch."""
+        return ops.project_assemble_batch(points, offsets, self.fov, self.proj_h, self.proj_w,
+                                          sem_label, weak_label, img_mean, img_std, depth, buffers)
+
     def doProjection(self, pointcloud: np.ndarray, depth: np.ndarray = None):
         self.cached_data = {}
         pts = torch.from_numpy(np.ascontiguousarray(pointcloud, dtype=np.float32))

@@ -90,6 +90,8 @@ class HotPathStep:
         self.inv_gauss = (1 - ops.gaussian_kernel(self.knn_s, self.knn_sigma)).reshape(-1).to(self.device)
         self.graphs = None
         self.concurrent = concurrent
+        import os as _os
+        self.schedule = _os.environ.get("C3D_SCHEDULE", "fill_after_projection")
         # ablation switch for tools/ablate.py: which chains run (default: all)
         self.parts = set(parts) if parts else {"proj", "knn", "fill", "loss", "ema"}
         # Priorities: the latency-bound chains (loss, EMA) high, so their small CTAs
@@ -136,22 +138,38 @@ class HotPathStep:
             st.wait_event(self.ev_fork)
         P = self.parts
         pr = None
-        with torch.cuda.stream(st_proj):
-            if "proj" in P:
-                pr = ops.project_batch(s.points, s.offsets, self.fov, H, W, buffers=b)
-            self.ev_resolved.record(st_proj)
-            if "knn" in P:
-                self._knn(s, pr if pr is not None else self._last_proj(b), C)  # ALU-bound
-            self.ev_proj.record(st_proj)
-        with torch.cuda.stream(st_fill):
-            # The fill saturates HBM and streams 512 MB through L2, which slows the
-            # z-buffer atomics and scatter/gather of the projection far more than the
-            # overlap gains (profiles/timeline_r1.txt); it therefore starts after the
-            # projection and overlaps the ALU-bound KNN vote and the loss / EMA chains.
-            st_fill.wait_event(self.ev_resolved)
-            if "fill" in P:
-                ops.zero_fill(self.grad)
-            self.ev_fill.record(st_fill)
+        sched = self.schedule
+        if sched == "fill_first":
+            # fill (optionally throttled, C3D_FILL_PERSISTENT) together with the latency-bound
+            # loss / EMA chains from t = 0; projection -> KNN afterwards
+            with torch.cuda.stream(st_fill):
+                if "fill" in P:
+                    ops.zero_fill(self.grad)
+                self.ev_fill.record(st_fill)
+            with torch.cuda.stream(st_proj):
+                st_proj.wait_event(self.ev_fill)
+                if "proj" in P:
+                    pr = ops.project_batch(s.points, s.offsets, self.fov, H, W, buffers=b)
+                if "knn" in P:
+                    self._knn(s, pr if pr is not None else self._last_proj(b), C)
+                self.ev_proj.record(st_proj)
+        else:
+            with torch.cuda.stream(st_proj):
+                if "proj" in P:
+                    pr = ops.project_batch(s.points, s.offsets, self.fov, H, W, buffers=b)
+                self.ev_resolved.record(st_proj)
+                if "knn" in P:
+                    self._knn(s, pr if pr is not None else self._last_proj(b), C)  # ALU-bound
+                self.ev_proj.record(st_proj)
+            with torch.cuda.stream(st_fill):
+                # The fill saturates HBM and streams 512 MB through L2, which slows the
+                # z-buffer atomics and scatter/gather of the projection far more than the
+                # overlap gains (profiles/timeline_r1.txt); it therefore starts after the
+                # projection (default) or after the KNN vote ("fill_last").
+                st_fill.wait_event(self.ev_proj if sched == "fill_last" else self.ev_resolved)
+                if "fill" in P:
+                    ops.zero_fill(self.grad)
+                self.ev_fill.record(st_fill)
         with torch.cuda.stream(st_ema):
             if "ema" in P:
                 self._ema(s, seed)

@@ -90,6 +90,33 @@ int c3d_project_batch(
     int32_t* status_flags,        /* [1], caller-zeroed                          */
     void* stream);
 
+/* ---------------------------------------------------------------- f1 ----
+ * Projection fused with its caller: instead of the (H,W,4) projected
+ * point cloud, the resolve pass writes what the data path builds from it --
+ * pc_processor/dataset/semantic_kitti/wss_sem_kitti_loader.py:124-132 (eval / train label
+ * images = per-point labels of the winning points), :159-172 (input
+ * [range, x, y, z, intensity*(intensity != -1)], channel-major) and
+ * tasks/weak_segmentation/trainer.py:600-608 (int64 labels; with img_mean/img_std:
+ * (feature - mean) / std * (eval_label > 0)).  Points are [total, 4] x,y,z,intensity.
+ * Nullable: depth_override, sem_label, weak_label, img_mean+img_std, train_label,
+ * eval_label, proj_range, proj_idx.
+ */
+int c3d_project_assemble_batch(
+    const float* points, const int32_t* offsets, int batch, int64_t total_points,
+    const float* depth_override,
+    const int32_t* sem_label,     /* [total_points] full labels (mapped to [0, C))        */
+    const int32_t* weak_label,    /* [total_points] weak labels, 0 = unlabelled            */
+    const float* img_mean, const float* img_std,   /* [5] each (config sensor.img_mean)   */
+    double abs_fov_left, double fov_hori, double abs_fov_down, double fov_vert,
+    int proj_h, int proj_w,
+    float* feature,               /* [batch, 5, H, W]                                      */
+    int64_t* train_label,         /* [batch, H, W]                                         */
+    int64_t* eval_label,          /* [batch, H, W]                                         */
+    float* proj_range,            /* [batch, H, W]                                         */
+    int32_t* proj_idx,            /* [batch, H, W]                                         */
+    int32_t* uproj_x_idx, int32_t* uproj_y_idx, float* uproj_depth,   /* [total_points]   */
+    void* workspace, int workspace_is_clean, int32_t* status_flags, void* stream);
+
 /* ---------------------------------------------------------------- a4 ----
  * KNN.forward, pc_processor/postproc/knn.py:54-142, for a CSR batch of scans.
  *

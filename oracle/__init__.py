@@ -9,6 +9,8 @@ with hand-written CUDA:
     oracle.proto_loss   <- pc_processor/loss/contrast_pixel_loss.py:8-195
     oracle.proto_ema    <- pc_processor/models/salsanext_proto.py:19-35,337-402,497-510
                            pc_processor/models/sinkhorn.py:5-33
+    oracle.assemble     <- pc_processor/dataset/semantic_kitti/wss_sem_kitti_loader.py:124-172
+                           tasks/weak_segmentation/trainer.py:600-608   (the projection's caller)
 
 Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline /
 `--impl reference` legs may import it, and only as the checker or the timed CPU

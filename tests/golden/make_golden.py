@@ -255,9 +255,58 @@ def gold_ema(pcp):
     print("ema: ok")
 
 
+def gold_assemble(pcp):
+    """Caller side of the projection: the statements of wss_sem_kitti_loader.py:124-132,
+    159-172 and trainer.py:600-608 executed on the reference RangeProjection's output."""
+    from coarse3d_b200 import synth
+    RP = pcp.dataset.preprocess.projection.RangeProjection
+    cases = {}
+    mean = [12.12, 10.88, 0.23, -1.04, 0.21]   # config_semantic_kitti.yaml:142-153
+    stds = [12.32, 11.47, 6.91, 0.86, 0.16]
+    for name, shp, n, H, W, seed, normalise in [
+            ("kitti_norm", synth.KITTI, 9000, 32, 512, 51, True),
+            ("nusc_raw", synth.NUSCENES, 5000, 32, 256, 52, False)]:
+        pts, sem, weak = synth.make_scan(shp, seed, n)
+        pts[::97, 3] = -1.0   # exercise the intensity != -1 mask on real points too
+        sem_label, weak_label = sem.astype(np.int32), weak.astype(np.int32)
+        rp = RP(fov_up=shp.fov_up, fov_down=shp.fov_down, proj_h=H, proj_w=W)
+        proj_pointcloud, proj_range, proj_idx, proj_eval_mask = rp.doProjection(pts)
+        # --- wss_sem_kitti_loader.py:124-132
+        proj_eval_label = np.zeros((proj_eval_mask.shape[0], proj_eval_mask.shape[1]), dtype=np.float32)
+        proj_eval_label[proj_idx > -1] = sem_label[proj_idx[proj_idx > -1]]
+        proj_train_label = np.zeros((proj_eval_mask.shape[0], proj_eval_mask.shape[1]), dtype=np.float32)
+        proj_train_label[proj_idx > -1] = weak_label[proj_idx[proj_idx > -1]]
+        # --- wss_sem_kitti_loader.py:159-172
+        proj_range_tensor = torch.from_numpy(proj_range)
+        proj_xyz_tensor = torch.from_numpy(proj_pointcloud[..., :3])
+        proj_intensity_tensor = torch.from_numpy(proj_pointcloud[..., 3])
+        proj_intensity_tensor = proj_intensity_tensor.ne(-1).float() * proj_intensity_tensor
+        proj_feature_tensor = torch.cat([proj_range_tensor.unsqueeze(0), proj_xyz_tensor.permute(2, 0, 1),
+                                         proj_intensity_tensor.unsqueeze(0)], 0)
+        # --- trainer.py:555-567,599-608 (batch of one)
+        input_feature = proj_feature_tensor.unsqueeze(0).clone()
+        train_label = torch.from_numpy(proj_train_label).unsqueeze(0).long()
+        eval_label = torch.from_numpy(proj_eval_label).unsqueeze(0).long()
+        eval_mask = eval_label.gt(0)
+        if normalise:
+            feature_mean = torch.Tensor(mean).unsqueeze(0).unsqueeze(2).unsqueeze(2)
+            feature_std = torch.Tensor(stds).unsqueeze(0).unsqueeze(2).unsqueeze(2)
+            input_feature[:, 0:5] = ((input_feature[:, 0:5] - feature_mean) / feature_std
+                                     * eval_mask.unsqueeze(1).expand_as(input_feature[:, 0:5]))
+        cases[name] = dict(points=pts, sem_label=sem_label, weak_label=weak_label, H=H, W=W,
+                           fov_up=shp.fov_up, fov_down=shp.fov_down, normalise=normalise,
+                           img_mean=np.asarray(mean, np.float32), img_std=np.asarray(stds, np.float32),
+                           feature=input_feature[0].numpy(), train_label=train_label[0].numpy(),
+                           eval_label=eval_label[0].numpy(), proj_range=proj_range, proj_idx=proj_idx)
+    flat = {f"{k}/{f}": np.asarray(v) for k, c in cases.items() for f, v in c.items()}
+    np.savez_compressed(os.path.join(OUT, "assemble.npz"), **flat)
+    print("assemble: ok")
+
+
 if __name__ == "__main__":
     pcp = import_reference()
     gold_projection(pcp)
     gold_knn(pcp)
     gold_loss(pcp)
     gold_ema(pcp)
+    gold_assemble(pcp)

@@ -140,3 +140,24 @@ def test_ema_matches_reference(case, labelled_only):
     assert counts.sum() > 0, "fixture must exercise the update"
     assert torch.allclose(new, torch.from_numpy(g["prototypes1"]), rtol=1e-5, atol=1e-6)
     assert np.array_equal(target.numpy(), g["proto_target"])
+
+
+ASM = load_golden("assemble")
+
+
+@pytest.mark.parametrize("case", sorted(ASM))
+def test_assemble_matches_reference(case):
+    from oracle import assemble as oasm
+    g = ASM[case]
+    fov = oproj.Fov(fov_up=float(g["fov_up"]), fov_down=float(g["fov_down"]),
+                    proj_h=int(g["H"]), proj_w=int(g["W"]))
+    norm = bool(g["normalise"])
+    o = oasm.assemble(g["points"], fov, g["sem_label"], g["weak_label"],
+                      g["img_mean"] if norm else None, g["img_std"] if norm else None)
+    assert np.array_equal(o["proj_idx"], g["proj_idx"])
+    assert np.array_equal(o["train_label"], g["train_label"]) and o["train_label"].dtype == np.int64
+    assert np.array_equal(o["eval_label"], g["eval_label"])
+    assert o["feature"].dtype == np.float32 and o["feature"].shape == g["feature"].shape
+    # bit-exact, including the -0.0 of empty pixels' intensity channel
+    assert np.array_equal(o["feature"].view(np.uint32), g["feature"].view(np.uint32))
+    assert (g["train_label"] > 0).sum() > 0 and (g["points"][:, 3] == -1).sum() > 0
