@@ -365,8 +365,57 @@ def run_e2e(args, step, dev, world, K):
     h2d = sum(host[0][k].numel() * host[0][k].element_size() for k in host[0])
     d2h = 4 + step.n_points * 8
 
+    s0 = step.sets[0]
+    d_loss = [torch.zeros((), device=dev) for _ in range(NB)]
+    d_knn = [torch.zeros((step.n_points,), dtype=torch.int64, device=dev) for _ in range(NB)]
+
+    def compute(j):
+        """The user-level calls of one step on the device inputs of buffer j."""
+        di = d_in[j]
+        # projection fused with label-image assembly: the weak labels travel per point
+        pr = rp.doProjectionAssembleBatch(di["points"], di["offsets"], weak_label=di["weak"],
+                                          buffers=step.proj_bufs[j])
+        labels = pr.train_label
+        feats = s0.feats.requires_grad_(True)
+        feats.grad = None
+        loss = crit(feats=feats, output=s0.probs, labels=labels, keep_mask=None,
+                    proto_queue=bank.prototypes.detach().unsqueeze(0))
+        loss.backward()
+        bank.update(s0.feats.detach(), labels)
+        lab = knn.forward_batch(pr.proj_range, pr.uproj_depth, s0.argmax, pr.uproj_x_idx,
+                                pr.uproj_y_idx, di["offsets"])
+        d_loss[j].copy_(loss.detach())
+        d_knn[j].copy_(lab)
+
+    # The compute part (the same public-API calls) is captured in one CUDA graph per
+    # buffer, as a user would do for a fixed-shape training step; falls back to eager.
+    graphs = None
+    for j in range(NB):                      # valid inputs before any warm-up / capture
+        for k in ("points", "offsets", "weak"):
+            d_in[j][k].copy_(host[0][k])
+    torch.cuda.synchronize(dev)
+    if not args.no_graph and world == 1:
+        try:
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                for j in range(NB):
+                    compute(j)
+            main.wait_stream(side)
+            torch.cuda.synchronize(dev)
+            graphs = []
+            for j in range(NB):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    compute(j)
+                graphs.append(g)
+        except Exception as e:  # noqa: BLE001
+            graphs = None
+            torch.cuda.synchronize(dev)
+            sys.stderr.write("e2e graph capture failed, running eager: %r\n" % (e,))
+
     def one(i):
-        s, h, j = step.sets[i % len(step.sets)], host[i % len(host)], i % NB
+        h, j = host[i % len(host)], i % NB
         di, ho = d_in[j], h_out[j]
         s_in.wait_event(ev_done[j])          # buffer j free again (compute of step i-NB done)
         with torch.cuda.stream(s_in):
@@ -374,27 +423,16 @@ def run_e2e(args, step, dev, world, K):
                 di[k].copy_(h[k], non_blocking=True)
             ev_in[j].record(s_in)
         main.wait_event(ev_in[j])
-        # projection fused with label-image assembly: the weak labels travel per point
-        pr = rp.doProjectionAssembleBatch(di["points"], di["offsets"], weak_label=di["weak"],
-                                          buffers=step.proj_bufs[j])
-        labels = pr.train_label
-        feats = s.feats.requires_grad_(True)
-        feats.grad = None
-        loss = crit(feats=feats, output=s.probs, labels=labels, keep_mask=None,
-                    proto_queue=bank.prototypes.detach().unsqueeze(0))
-        loss.backward()
-        bank.update(s.feats.detach(), labels)
-        lab = knn.forward_batch(pr.proj_range, pr.uproj_depth, s.argmax, pr.uproj_x_idx,
-                                pr.uproj_y_idx, di["offsets"])
-        loss_d = loss.detach()
+        main.wait_event(ev_out[j])           # outputs of step i-NB have left the device
+        if graphs is not None:
+            graphs[j].replay()
+        else:
+            compute(j)
         ev_done[j].record(main)
         s_out.wait_event(ev_done[j])
-        s_out.wait_event(ev_out[j])
-        lab.record_stream(s_out)
-        loss_d.record_stream(s_out)
         with torch.cuda.stream(s_out):
-            ho["loss"].copy_(loss_d, non_blocking=True)
-            ho["knn"].copy_(lab, non_blocking=True)
+            ho["loss"].copy_(d_loss[j], non_blocking=True)
+            ho["knn"].copy_(d_knn[j], non_blocking=True)
             ev_out[j].record(s_out)
 
     for i in range(3):
@@ -421,7 +459,8 @@ def run_e2e(args, step, dev, world, K):
                    "PrototypeBank.update + KNN.forward_batch",
             "host_inputs": "points, offsets, per-point weak labels int32 (pinned); "
                            "CNN activations resident on device as in the reference",
-            "pipelining": "double-buffered: H2D / compute / D2H of consecutive steps on three streams"}
+            "pipelining": "double-buffered: H2D / compute / D2H of consecutive steps on three streams",
+            "compute_graph": graphs is not None}
 
 
 if __name__ == "__main__":

@@ -34,6 +34,8 @@ def _load():
         "c3d_project_assemble_batch": (c_int, [P, P, c_int, c_int64, P, P, P, P, P, c_double, c_double,
                                                c_double, c_double, c_int, c_int, P, P, P, P, P, P, P, P,
                                                P, c_int, P, P]),
+        "c3d_unproject_confusion_batch": (c_int, [P, P, P, P, P, c_int, c_int64, c_int, c_int, c_int, c_int,
+                                                  c_int, c_int, P, P, P, P]),
         "c3d_knn_batch": (c_int, [P, P, P, P, P, P, c_int, c_int64, c_int, c_int, c_int, c_int,
                                   c_float, c_int, P, c_int, c_int, P, P]),
         "c3d_profile_enable": (c_int, [c_char_p]),

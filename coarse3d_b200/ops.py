@@ -211,6 +211,37 @@ def knn_batch(proj_range, proj_argmax, unproj_range, px, py, offsets, knn, searc
     return out
 
 
+# --------------------------------------------------------------------- f2 --
+def unproject_confusion_batch(proj_argmax, px, py, offsets, nclasses, labels=None, conf_matrix=None,
+                              want_unproj=True, flags=None):
+    """Per-point prediction `argmax_2d[b, py, px]` (trainer.py:714-724) and, with `labels`,
+    IOUEval.addBatch (iou_eval.py:35-58) accumulated into `conf_matrix` (C,C) int64
+    (rows = prediction, columns = ground truth).  Returns (unproj_argmax or None, conf_matrix)."""
+    _need_cuda(proj_argmax=proj_argmax, px=px, py=py, offsets=offsets, labels=labels,
+               conf_matrix=conf_matrix)
+    def is64(t, name):
+        if t.dtype not in (torch.int64, torch.int32):
+            raise ValueError("%s must be int64 or int32" % name)
+        return 1 if t.dtype == torch.int64 else 0
+    if py.dtype != px.dtype:
+        raise ValueError("px and py must share a dtype")
+    B, H, W = proj_argmax.shape
+    total = px.numel()
+    dev = proj_argmax.device
+    if labels is not None and conf_matrix is None:
+        conf_matrix = torch.zeros((nclasses, nclasses), dtype=torch.int64, device=dev)
+    if conf_matrix is not None and (conf_matrix.dtype != torch.int64 or conf_matrix.shape != (nclasses, nclasses)):
+        raise ValueError("conf_matrix must be (C, C) int64")
+    out = torch.empty((total,), dtype=proj_argmax.dtype, device=dev) if want_unproj else None
+    if flags is None:
+        flags = torch.zeros((1,), dtype=torch.int32, device=dev)
+    check(lib.c3d_unproject_confusion_batch(
+        _p(proj_argmax), _p(px), _p(py), _p(labels), _p(offsets), B, total, H, W, int(nclasses),
+        is64(proj_argmax, "proj_argmax"), is64(px, "px"), 0 if labels is None else is64(labels, "labels"),
+        _p(out), _p(conf_matrix if labels is not None else None), _p(flags), _stream()))
+    return out, conf_matrix
+
+
 # --------------------------------------------------------------------- a2 --
 class ProtoLossConfig(NamedTuple):
     ignore_label: int = 0

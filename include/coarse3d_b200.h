@@ -141,6 +141,25 @@ int c3d_knn_batch(
     void* out_labels,             /* [total_points] i64 or i32, in [1, C-1]      */
     void* stream);
 
+/* ---------------------------------------------------------------- f2 ----
+ * Un-projection gather + confusion matrix:
+ * `argmax_2d[ii, uproj_y_idx[ii], uproj_x_idx[ii]]` per scan,
+ * tasks/weak_segmentation/trainer.py:714-724, and IOUEval.addBatch,
+ * pc_processor/metrics/iou_eval.py:35-58 (conf[pred, gt] += 1; rows = prediction,
+ * columns = ground truth).  conf_matrix is ACCUMULATED into (int64, caller-zeroed at
+ * reset); either output may be NULL.  status_flags bit 0: pixel index outside the
+ * image, bit 1: class outside [0, C).
+ */
+int c3d_unproject_confusion_batch(
+    const void* proj_argmax,      /* [batch, H, W] i64 or i32                    */
+    const void* px, const void* py, /* [total_points] i64 or i32                 */
+    const void* labels,           /* [total_points] i64 or i32, or NULL          */
+    const int32_t* offsets, int batch, int64_t total_points, int proj_h, int proj_w,
+    int nclasses, int argmax_is_i64, int pxy_is_i64, int label_is_i64,
+    void* unproj_argmax,          /* [total_points], dtype of proj_argmax, or NULL */
+    int64_t* conf_matrix,         /* [C, C] accumulated, or NULL                 */
+    int32_t* status_flags, void* stream);
+
 /* ---------------------------------------------------------------- a2 ----
  * ContrastMEMLoss.forward, pc_processor/loss/contrast_pixel_loss.py:27-195,
  * and its autograd (gradient w.r.t. feats only; the bank is detached at
