@@ -11,6 +11,8 @@ with hand-written CUDA:
                            pc_processor/models/sinkhorn.py:5-33
     oracle.assemble     <- pc_processor/dataset/semantic_kitti/wss_sem_kitti_loader.py:124-172
                            tasks/weak_segmentation/trainer.py:600-608   (the projection's caller)
+    oracle.unproject    <- tasks/weak_segmentation/trainer.py:714-724,
+                           pc_processor/metrics/iou_eval.py:35-58
 
 Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline /
 `--impl reference` legs may import it, and only as the checker or the timed CPU

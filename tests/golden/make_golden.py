@@ -303,6 +303,35 @@ def gold_assemble(pcp):
     print("assemble: ok")
 
 
+def gold_unproject(pcp):
+    """trainer.py:714-728 with the reference's IOUEval (metrics/iou_eval.py) on two scans."""
+    from coarse3d_b200 import synth
+    RP = pcp.dataset.preprocess.projection.RangeProjection
+    shp, H, W, C = synth.KITTI, 32, 256, 20
+    evaluator = pcp.metrics.IOUEval(n_classes=C, device=torch.device("cpu"), ignore=[0])
+    g = torch.Generator().manual_seed(61)
+    argmax_2d = torch.randint(0, C, (2, H, W), generator=g)
+    px, py, lab, un, offs = [], [], [], [], [0]
+    for ii in range(2):
+        pts, full, _ = synth.make_scan(shp, 61 + ii, 4000 + 500 * ii)
+        rp = RP(fov_up=shp.fov_up, fov_down=shp.fov_down, proj_h=H, proj_w=W)
+        rp.doProjection(pts)
+        uproj_x_idx = torch.from_numpy(rp.cached_data["uproj_x_idx"]).long()   # trainer.py:618-619
+        uproj_y_idx = torch.from_numpy(rp.cached_data["uproj_y_idx"]).long()
+        unproj_full_labels = torch.from_numpy(full).long()
+        unproj_argmax = argmax_2d[ii, uproj_y_idx, uproj_x_idx]                # trainer.py:719
+        evaluator.addBatch(unproj_argmax, unproj_full_labels)                  # trainer.py:728
+        px.append(uproj_x_idx), py.append(uproj_y_idx), lab.append(unproj_full_labels)
+        un.append(unproj_argmax), offs.append(offs[-1] + len(pts))
+    np.savez_compressed(os.path.join(OUT, "unproject.npz"), **{
+        "two_scans/argmax_2d": argmax_2d.numpy(), "two_scans/px": torch.cat(px).numpy(),
+        "two_scans/py": torch.cat(py).numpy(), "two_scans/labels": torch.cat(lab).numpy(),
+        "two_scans/offsets": np.asarray(offs, np.int32), "two_scans/nclasses": np.asarray(C),
+        "two_scans/unproj_argmax": torch.cat(un).numpy(),
+        "two_scans/conf_matrix": evaluator.conf_matrix.numpy()})
+    print("unproject: ok")
+
+
 if __name__ == "__main__":
     pcp = import_reference()
     gold_projection(pcp)
@@ -310,3 +339,4 @@ if __name__ == "__main__":
     gold_loss(pcp)
     gold_ema(pcp)
     gold_assemble(pcp)
+    gold_unproject(pcp)

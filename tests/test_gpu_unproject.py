@@ -1,6 +1,6 @@
-"""GPU parity: c3d_unproject_confusion_batch against the reference's own
-statements -- trainer.py:714-724 (per-scan fancy-index gather) and IOUEval.addBatch
-(iou_eval.py:35-58), restated with torch-CPU ops in the test.  Integer work: exact."""
+"""GPU parity: c3d_unproject_confusion_batch against the oracle
+(trainer.py:714-724 + IOUEval.addBatch, iou_eval.py:35-58) and the golden vectors produced
+by the reference's IOUEval.  Integer work: exact."""
 import numpy as np
 import pytest
 import torch
@@ -8,17 +8,24 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
+from conftest import load_golden
+from oracle import unproject as ounp
+
+
 def _reference(argmax_2d, px, py, offs, labels, C):
-    conf = torch.zeros((C, C)).long()                        # iou_eval.py:29-31
-    unproj = []
-    for ii in range(argmax_2d.shape[0]):
-        lo, hi = int(offs[ii]), int(offs[ii + 1])
-        u = argmax_2d[ii, py[lo:hi].long(), px[lo:hi].long()]  # trainer.py:719
-        unproj.append(u)
-        x_row, y_row = u.reshape(-1).long(), labels[lo:hi].reshape(-1).long()   # iou_eval.py:44-45
-        idxs = torch.stack([x_row, y_row], dim=0)
-        conf = conf.index_put_(tuple(idxs), torch.ones(idxs.shape[-1]).long(), accumulate=True)  # :56-58
-    return torch.cat(unproj), conf
+    return ounp.unproject_confusion(argmax_2d, px, py, offs, labels, C)
+
+
+def test_matches_reference_golden(cuda_device):
+    from coarse3d_b200 import ops
+    g = load_golden("unproject")["two_scans"]
+    C = int(g["nclasses"])
+    u, conf = ops.unproject_confusion_batch(
+        torch.from_numpy(g["argmax_2d"]).cuda(), torch.from_numpy(g["px"]).cuda(),
+        torch.from_numpy(g["py"]).cuda(), torch.from_numpy(g["offsets"]).cuda(), C,
+        labels=torch.from_numpy(g["labels"]).cuda())
+    assert np.array_equal(u.cpu().numpy(), g["unproj_argmax"])
+    assert np.array_equal(conf.cpu().numpy(), g["conf_matrix"])
 
 
 @pytest.mark.parametrize("adt,pdt,ldt", [(torch.int64, torch.int32, torch.int32),

@@ -161,3 +161,13 @@ def test_assemble_matches_reference(case):
     # bit-exact, including the -0.0 of empty pixels' intensity channel
     assert np.array_equal(o["feature"].view(np.uint32), g["feature"].view(np.uint32))
     assert (g["train_label"] > 0).sum() > 0 and (g["points"][:, 3] == -1).sum() > 0
+
+
+def test_unproject_confusion_matches_reference():
+    from oracle import unproject as ounp
+    g = load_golden("unproject")["two_scans"]
+    u, conf = ounp.unproject_confusion(torch.from_numpy(g["argmax_2d"]), torch.from_numpy(g["px"]),
+                                       torch.from_numpy(g["py"]), g["offsets"],
+                                       torch.from_numpy(g["labels"]), int(g["nclasses"]))
+    assert np.array_equal(u.numpy(), g["unproj_argmax"])
+    assert np.array_equal(conf.numpy(), g["conf_matrix"]) and conf.sum() == len(g["px"])
