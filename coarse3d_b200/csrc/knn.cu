@@ -25,7 +25,7 @@ namespace c3d {
 
 // KT >= knn is the compile-time capacity of the top-k network (KT == knn for knn <= 8).
 template <int S, int KT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, (S <= 5 && KT <= 8) ? 5 : 1)
 knn_vote_kernel(const float* __restrict__ proj_range, const void* __restrict__ proj_argmax,
                 const float* __restrict__ unproj_range, const void* __restrict__ px_,
                 const void* __restrict__ py_, const int32_t* __restrict__ offsets, int batch,

@@ -24,11 +24,14 @@ unproject_confusion_kernel(const void* __restrict__ proj_argmax, const void* __r
   for (int i = threadIdx.x; i <= batch; i += blockDim.x) s_off[i] = offsets[i];
   if (conf) for (int i = threadIdx.x; i < C * C; i += blockDim.x) s_hist[i] = 0;
   __syncthreads();
-  if (threadIdx.x == 0) s_b0 = scan_of(s_off, batch, min((int)(blockIdx.x * blockDim.x), total - 1));
+  // each CTA owns one contiguous chunk of points and keeps its histogram in shared
+  // memory for the whole chunk: C*C global atomics per CTA, not per 256 points
+  const int chunk = (((total + gridDim.x - 1) / gridDim.x) + 255) & ~255;
+  const int g_begin = blockIdx.x * chunk, g_end = min(g_begin + chunk, total);
+  if (threadIdx.x == 0) s_b0 = scan_of(s_off, batch, min(g_begin, total - 1));
   __syncthreads();
-  const int g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g < total) {
-    int b = s_b0;
+  int b = s_b0;
+  for (int g = g_begin + threadIdx.x; g < g_end; g += blockDim.x) {
     while (g >= s_off[b + 1]) ++b;
     const int x = pxy64 ? (int)reinterpret_cast<const long long*>(px_)[g] : reinterpret_cast<const int*>(px_)[g];
     const int y = pxy64 ? (int)reinterpret_cast<const long long*>(py_)[g] : reinterpret_cast<const int*>(py_)[g];
@@ -80,7 +83,8 @@ extern "C" int c3d_unproject_confusion_batch(
   if (total_points == 0) return C3D_OK;
   C3D_REQUIRE(px && py, "null per-point pointer");
   const int threads = 256;
-  const int grid = (int)((total_points + threads - 1) / threads);
+  long long blocks = (total_points + threads - 1) / threads;
+  const int grid = (int)(blocks < kNumSMs * 8 ? blocks : kNumSMs * 8);
   const size_t smem = ((size_t)(batch + 1) + (conf_matrix ? (size_t)nclasses * nclasses : 0)) * 4;
   KernelTimer kt__("unproject_confusion_kernel", stream);
   unproject_confusion_kernel<<<grid, threads, smem, stream>>>(

@@ -39,7 +39,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--shape", default="kitti")
-    ap.add_argument("--ops", default="project,knn")
+    ap.add_argument("--ops", default="project,knn,assemble,unproject")
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     args = ap.parse_args()
@@ -75,6 +75,23 @@ def main():
                                                    shp.n_classes, out=out), flush=flush)
             by = 12 * B * HW + 28 * N
             res["knn_" + name] = dict(ms=med, ms_min=mn, GBs_ref_dtypes=by / med / 1e6, scans_s=B / med * 1e3)
+    if "assemble" in args.ops:
+        weak = torch.randint(0, shp.n_classes, (N,), device="cuda", dtype=torch.int32)
+        sem = torch.randint(1, shp.n_classes, (N,), device="cuda", dtype=torch.int32)
+        mean = torch.tensor([12.12, 10.88, 0.23, -1.04, 0.21], device="cuda")
+        std = torch.tensor([12.32, 11.47, 6.91, 0.86, 0.16], device="cuda")
+        med, mn = timeit(lambda: ops.project_assemble_batch(P, O, fov, shp.proj_h, shp.proj_w, sem, weak, mean, std,
+                                                             buffers=bufs), flush=flush)
+        by = 28 * N + 44 * B * HW  # points 16 + upx/upy/udepth 12 per point; feature 20 + labels 16 + range 4 + idx 4 per pixel
+        res["project_assemble"] = dict(ms=med, ms_min=mn, GBs=by / med / 1e6, scans_s=B / med * 1e3)
+    if "unproject" in args.ops:
+        am = torch.randint(0, shp.n_classes, pr.proj_idx.shape, device="cuda")
+        lab = torch.randint(0, shp.n_classes, (N,), device="cuda")
+        conf = torch.zeros((shp.n_classes, shp.n_classes), dtype=torch.int64, device="cuda")
+        med, mn = timeit(lambda: ops.unproject_confusion_batch(am, pr.uproj_x_idx, pr.uproj_y_idx, O, shp.n_classes,
+                                                               labels=lab, conf_matrix=conf), flush=flush)
+        by = (4 + 4 + 8 + 8 + 8) * N  # px, py i32; label i64; gathered class i64; output i64
+        res["unproject_confusion"] = dict(ms=med, ms_min=mn, GBs=by / med / 1e6, scans_s=B / med * 1e3)
     print(json.dumps(dict(batch=B, shape=args.shape, results=res), indent=1))
 
 
