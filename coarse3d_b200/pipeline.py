@@ -97,7 +97,8 @@ class HotPathStep:
         # Priorities: the latency-bound chains (loss, EMA) high, so their small CTAs
         # are placed first whenever the short CTAs of the fill / KNN retire.
         lo, hi = 0, -1
-        self.side = [torch.cuda.Stream(self.device, priority=lo),   # fill
+        fill_prio = hi if _os.environ.get("C3D_FILL_PRIO", "0") == "1" else lo
+        self.side = [torch.cuda.Stream(self.device, priority=fill_prio),   # fill
                      torch.cuda.Stream(self.device, priority=lo),   # projection -> KNN
                      torch.cuda.Stream(self.device, priority=hi),   # EMA chain
                      torch.cuda.Stream(self.device, priority=hi)]   # loss chain
