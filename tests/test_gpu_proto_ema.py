@@ -81,6 +81,8 @@ def _oracle(emb, label, protos0, ln, C, mom, gumbel_rows=None):
     (3, 128, 16, 256, 20, 20, 0.01, True),
     (2, 256, 8, 128, 17, 20, 0.02, True),     # D=256: bank streamed in smem tiles
     (2, 64, 8, 100, 14, 7, 0.2, False),       # denser labels, odd sizes
+    (2, 32, 16, 128, 6, 4, 0.5, True),        # ~400 rows per class: block Sinkhorn, Q in shared memory
+    (1, 16, 32, 256, 3, 20, 0.9, False),      # ~3700 rows per class: Q in the global scratch
 ])
 def test_matches_oracle(cuda_device, B, D, H, W, C, M, frac, use_gumbel):
     from coarse3d_b200 import ops
