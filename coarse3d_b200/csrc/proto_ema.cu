@@ -218,7 +218,6 @@ __device__ __forceinline__ uint4 philox_e(uint4 ctr, uint2 key) {
 // order, so the assignment is bitwise reproducible.
 // mode: 0 = one_hot(argmax) (sinkhorn.py:30), 1 = injected Gumbel noise, 2 = device noise
 constexpr int kSinkSmemFloats = 24 * 1024;  // 96 KB of dynamic shared memory
-constexpr int kSinkRows = 2;                // rows per lane in the one-warp fast path (n <= 64)
 
 __device__ __forceinline__ void sink_row_sums(const float* Q, int n, int M, float* s_part, float* s_R) {
   // s_R[m] = sum_i Q[i*M + m]; thread (p = warp, m = lane) sums rows p, p+8, ...
@@ -253,87 +252,8 @@ ema_sinkhorn_kernel(const int32_t* __restrict__ seg_cnt, const int32_t* __restri
   for (int b = 0; b < B; ++b) n += seg_cnt[c * B + b];
   if (n == 0) return;  // no such class (:356-357)
   const int ne = n * M;
-  float* G = simq + (size_t)start * M;
-  if (n <= 32 * kSinkRows) {
-    // ---- small class (the weak-label regime: tens of rows): one warp, Q in registers
-    // (lane owns rows lane, lane+32, ...), row sums by warp shuffles, column sums local;
-    // no shared memory, no block barriers -- the block version below spends its time in
-    // ~40 barriers around a few hundred cycles of work each.
-    if (threadIdx.x >= 32) return;
-    const int lane = threadIdx.x;
-    const float fM = (float)M, fn = (float)n;
-    float q[kSinkRows][kMaxSub];
-#pragma unroll
-    for (int r = 0; r < kSinkRows; ++r) {
-      const int i = lane + 32 * r;
-#pragma unroll
-      for (int m = 0; m < kMaxSub; ++m)
-        q[r][m] = (i < n && m < M) ? expf(G[(size_t)i * M + m] / 0.05f) : 0.f;   // (:8)
-    }
-    float rs[kMaxSub];
-    auto row_sums = [&]() {
-#pragma unroll
-      for (int m = 0; m < kMaxSub; ++m) {
-        if (m < M) {
-          float a = 0.f;
-#pragma unroll
-          for (int r = 0; r < kSinkRows; ++r) a += q[r][m];
-          rs[m] = warp_sum(a);
-        }
-      }
-    };
-    row_sums();
-    float sum_q = 0.f;
-#pragma unroll
-    for (int m = 0; m < kMaxSub; ++m) if (m < M) sum_q += rs[m];               // (:13)
-#pragma unroll
-    for (int r = 0; r < kSinkRows; ++r)
-#pragma unroll
-      for (int m = 0; m < kMaxSub; ++m) if (m < M) q[r][m] = q[r][m] / sum_q;  // (:14)
-    for (int it = 0; it < 3; ++it) {                                           // (:16-24)
-      row_sums();
-#pragma unroll
-      for (int r = 0; r < kSinkRows; ++r) {
-        float cs = 0.f;
-#pragma unroll
-        for (int m = 0; m < kMaxSub; ++m)
-          if (m < M) { float v = q[r][m] / rs[m]; v = v / fM; q[r][m] = v; cs += v; }
-        const bool live = (lane + 32 * r) < n;
-#pragma unroll
-        for (int m = 0; m < kMaxSub; ++m)
-          if (m < M) { float v = live ? q[r][m] / cs : 0.f; q[r][m] = v / fn; }
-      }
-    }
-#pragma unroll
-    for (int r = 0; r < kSinkRows; ++r) {
-      const int i = lane + 32 * r;
-      if (i >= n) continue;
-      const int slot = start + i;
-      float best = -CUDART_INF_F, bestg = -CUDART_INF_F; int idx = 0, hard = 0;
-#pragma unroll
-      for (int m = 0; m < kMaxSub; ++m) {
-        if (m < M) {
-          const float v = q[r][m] * fn;                                        // (:26)
-          if (v > best) { best = v; idx = m; }
-          float g = 0.f;
-          if (mode == 1) g = gumbel[(size_t)slot * M + m];
-          else if (mode == 2) {
-            const unsigned long long ctr = (unsigned long long)slot * M + m;
-            const uint4 rr = philox_e(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), 1u, 0u),
-                                      make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
-            const float u = ((float)(rr.x >> 8) + 0.5f) * (1.0f / 16777216.0f);
-            g = -logf(-logf(u));
-          }
-          const float y = (v + g) / 0.5f;
-          if (y > bestg) { bestg = y; hard = m; }
-        }
-      }
-      sub[slot] = (mode == 0) ? idx : hard;
-      if (proto_target) proto_target[pix_list[slot]] = (float)idx + (float)(M * c);
-    }
-    return;
-  }
   const bool fits = ne + n <= kSinkSmemFloats;
+  float* G = simq + (size_t)start * M;
   float* Q = fits ? s_dyn : G;
   float* csum = fits ? s_dyn + ne : reinterpret_cast<float*>(sub + start);  // n floats of scratch
   const float fM = (float)M, fn = (float)n;
