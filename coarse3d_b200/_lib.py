@@ -36,6 +36,9 @@ def _load():
                                                P, c_int, P, P]),
         "c3d_unproject_confusion_batch": (c_int, [P, P, P, P, P, c_int, c_int64, c_int, c_int, c_int, c_int,
                                                   c_int, c_int, P, P, P, P]),
+        "c3d_entropy_select_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+        "c3d_entropy_select_batch": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_float, P,
+                                             c_uint64, P, P, P, P]),
         "c3d_knn_batch": (c_int, [P, P, P, P, P, P, c_int, c_int64, c_int, c_int, c_int, c_int,
                                   c_float, c_int, P, c_int, c_int, P, P]),
         "c3d_profile_enable": (c_int, [c_char_p]),

@@ -3,7 +3,7 @@ import importlib
 import sys
 
 
-def install(pc_processor=None):
+def install(pc_processor=None, trainer_cls=None):
     """Replace the reference's hot-path operators with the B200 ones.
 
     Call once, after `import pc_processor` (the reference package) and before
@@ -13,7 +13,9 @@ def install(pc_processor=None):
         import pc_processor, coarse3d_b200
         coarse3d_b200.install(pc_processor)
 
-    Everything else in `pc_processor` is left untouched.
+    Everything else in `pc_processor` is left untouched.  Pass the task's `Trainer` class
+    (tasks/weak_segmentation/trainer.py:17) as `trainer_cls` to also replace its
+    `entropy_based_selection` method (trainer.py:447-518) with the batched kernel.
     """
     if pc_processor is None:
         pc_processor = sys.modules.get("pc_processor") or importlib.import_module("pc_processor")
@@ -27,4 +29,7 @@ def install(pc_processor=None):
     pc_processor.postproc.KNN = KNN
     pc_processor.loss.contrast_pixel_loss.ContrastMEMLoss = ContrastMEMLoss
     pc_processor.loss.ContrastMEMLoss = ContrastMEMLoss
+    if trainer_cls is not None:
+        from .trainer_ops import entropy_based_selection
+        trainer_cls.entropy_based_selection = entropy_based_selection
     return pc_processor

@@ -242,6 +242,35 @@ def unproject_confusion_batch(proj_argmax, px, py, offsets, nclasses, labels=Non
     return out, conf_matrix
 
 
+# --------------------------------------------------------------------- f3 --
+def entropy_select_batch(output, wss_mask, eval_mask, train_label, select_ratio, ignore_cls=0,
+                         noise=None, seed=None, workspace=None):
+    """Trainer.entropy_based_selection (trainer.py:447-518) for the whole batch in three
+    launches.  output (B,C,H,W) f32 probs; wss_mask / eval_mask (B,H,W) bool; train_label
+    (B,H,W) int64.  noise (B,C,H*W) f32 injects the Exp(1) draws of the reference's
+    multinomial calls; otherwise Philox draws from `seed`.
+    Returns (pseudo_label (B,H,W) int64, new_wss_mask (B,H,W) bool)."""
+    _need_cuda(output=output, wss_mask=wss_mask, eval_mask=eval_mask, train_label=train_label, noise=noise)
+    if output.dtype != torch.float32 or train_label.dtype != torch.int64:
+        raise ValueError("output must be float32 and train_label int64")
+    if wss_mask.dtype != torch.bool or eval_mask.dtype != torch.bool:
+        raise ValueError("wss_mask / eval_mask must be bool")
+    B, C, H, W = output.shape
+    if noise is not None and (noise.dtype != torch.float32 or noise.shape != (B, C, H * W)):
+        raise ValueError("noise must be (B, C, H*W) float32")
+    if workspace is None:
+        n = lib.c3d_entropy_select_workspace_bytes(B, C, H * W)
+        workspace = torch.empty((n,), dtype=torch.uint8, device=output.device)
+    if seed is None:
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if noise is None else 0
+    label = torch.empty((B, H, W), dtype=torch.int64, device=output.device)
+    mask = torch.empty((B, H, W), dtype=torch.bool, device=output.device)
+    check(lib.c3d_entropy_select_batch(
+        _p(output), _p(train_label), _p(wss_mask), _p(eval_mask), B, C, H, W, int(ignore_cls),
+        float(select_ratio), _p(noise), int(seed), _p(workspace), _p(label), _p(mask), _stream()))
+    return label, mask
+
+
 # --------------------------------------------------------------------- a2 --
 class ProtoLossConfig(NamedTuple):
     ignore_label: int = 0

@@ -160,6 +160,28 @@ int c3d_unproject_confusion_batch(
     int64_t* conf_matrix,         /* [C, C] accumulated, or NULL                 */
     int32_t* status_flags, void* stream);
 
+/* ---------------------------------------------------------------- f3 ----
+ * Trainer.entropy_based_selection, tasks/weak_segmentation/trainer.py:447-518 (SURVEY.md
+ * 8f-3): per (scan, class present in train_label) int(count * select_ratio) of the pixels
+ * predicted as that class are drawn without replacement with weights exp(-entropy); the
+ * result is the pseudo-label image (weak ground truth kept) and its mask.
+ * `noise` [B, C, H*W] injects the Exp(1) draws torch.multinomial would make in iteration
+ * (scan, class) -- selection is topk(weight / noise) -- or NULL for Philox draws from `seed`.
+ */
+size_t c3d_entropy_select_workspace_bytes(int batch, int n_classes, int hw);
+
+int c3d_entropy_select_batch(
+    const float* probs,           /* [B, C, H, W] softmax output                 */
+    const int64_t* train_label,   /* [B, H, W]                                   */
+    const uint8_t* wss_mask,      /* [B, H, W] bool: weak label present          */
+    const uint8_t* eval_mask,     /* [B, H, W] bool                              */
+    int batch, int n_classes, int proj_h, int proj_w, int ignore_cls, float select_ratio,
+    const float* noise, uint64_t seed,
+    void* workspace,              /* c3d_entropy_select_workspace_bytes, 256 B aligned */
+    int64_t* out_label,           /* [B, H, W] pseudo label (:512-515)           */
+    uint8_t* out_mask,            /* [B, H, W] bool: label != ignore_cls (:516)  */
+    void* stream);
+
 /* ---------------------------------------------------------------- a2 ----
  * ContrastMEMLoss.forward, pc_processor/loss/contrast_pixel_loss.py:27-195,
  * and its autograd (gradient w.r.t. feats only; the bank is detached at

@@ -13,6 +13,7 @@ with hand-written CUDA:
                            tasks/weak_segmentation/trainer.py:600-608   (the projection's caller)
     oracle.unproject    <- tasks/weak_segmentation/trainer.py:714-724,
                            pc_processor/metrics/iou_eval.py:35-58
+    oracle.entropy_select <- tasks/weak_segmentation/trainer.py:447-518
 
 Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline /
 `--impl reference` legs may import it, and only as the checker or the timed CPU

@@ -332,6 +332,69 @@ def gold_unproject(pcp):
     print("unproject: ok")
 
 
+def gold_entropy_select(pcp):
+    """Trainer.entropy_based_selection (trainer.py:447-518) executed from the reference's
+    trainer module; the Exp(1) draws of its torch.multinomial calls are replayed from the
+    seed (multinomial without replacement == topk(w / q), verified below)."""
+    sys.path.insert(0, os.path.join(REF, "tasks", "weak_segmentation"))
+    import importlib
+    trainer = importlib.import_module("trainer")
+    w = torch.rand(3000)
+    torch.manual_seed(5); a = torch.multinomial(w, 400, replacement=False)
+    torch.manual_seed(5); b = torch.topk(w / torch.empty_like(w).exponential_(1), 400)[1]
+    assert torch.equal(a, b), "torch.multinomial(replacement=False) is no longer topk(w / Exp(1))"
+    cases = {}
+    for name, B, C, H, W, ratio, seed in [("small", 2, 6, 8, 64, 0.37, 71), ("kitti_like", 2, 20, 16, 256, 0.21, 72)]:
+        g = torch.Generator().manual_seed(seed)
+        output = torch.softmax(torch.randn(B, C, H, W, generator=g) * 1.5, 1)
+        eval_mask = torch.rand(B, H, W, generator=g) < 0.8
+        full = torch.randint(1, C, (B, H, W), generator=g)
+        wss_mask = (torch.rand(B, H, W, generator=g) < 0.02) & eval_mask
+        train_label = full * wss_mask
+        train_label[1][train_label[1] == 2] = 0          # a class absent from scan 1's weak labels
+        wss_mask = train_label.gt(0)                     # trainer.py:602
+        fake = types.SimpleNamespace(settings=types.SimpleNamespace(ignore_cls=0, n_classes=C))
+        draws = []
+        real = torch.multinomial
+
+        def rec(wt, n, replacement=False):
+            state = torch.get_rng_state()
+            r = real(wt, n, replacement=replacement)
+            after = torch.get_rng_state()
+            torch.set_rng_state(state)
+            draws.append(torch.empty_like(wt).exponential_(1))   # the same draws multinomial made
+            torch.set_rng_state(after)
+            return r
+
+        torch.multinomial = rec
+        try:
+            torch.manual_seed(seed)
+            label, mask = trainer.Trainer.entropy_based_selection(
+                fake, output.clone(), wss_mask, eval_mask, train_label, ratio)
+        finally:
+            torch.multinomial = real
+        # place the recorded draws at [b, cls] in the loop's order (trainer.py:473-496)
+        noise = torch.ones(B, C, H * W)
+        it = iter(draws)
+        pseudo = torch.max(output, dim=1)[1]
+        pseudo[eval_mask == False] = 0                                           # noqa: E712
+        for b_ in range(B):
+            for cls in torch.unique(train_label[b_]):
+                if cls == 0:
+                    continue
+                cm = (pseudo[b_] == cls) * (eval_mask[b_] > 0)
+                if cm.sum() == 0 or int(cm.sum() * ratio) < 1:
+                    continue
+                noise[b_, int(cls)] = next(it)
+        assert next(it, None) is None
+        cases[name] = dict(output=output.numpy(), wss_mask=wss_mask.numpy(), eval_mask=eval_mask.numpy(),
+                           train_label=train_label.numpy(), select_ratio=np.float64(ratio),
+                           noise=noise.numpy(), pseudo_label=label.numpy(), new_wss_mask=mask.numpy())
+    flat = {f"{k}/{f}": np.asarray(v) for k, c in cases.items() for f, v in c.items()}
+    np.savez_compressed(os.path.join(OUT, "entropy_select.npz"), **flat)
+    print("entropy_select: ok", {k: int(c["new_wss_mask"].sum()) for k, c in cases.items()})
+
+
 if __name__ == "__main__":
     pcp = import_reference()
     gold_projection(pcp)
@@ -340,3 +403,4 @@ if __name__ == "__main__":
     gold_ema(pcp)
     gold_assemble(pcp)
     gold_unproject(pcp)
+    gold_entropy_select(pcp)

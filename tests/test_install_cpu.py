@@ -74,3 +74,17 @@ def test_constructor_behaviour_without_a_gpu():
     assert abs(rp.fov_vert - 0.4886921905584123) < 1e-12 and rp.cached_data == {}
     k = KNN(dict(knn=5, search=5, sigma=1.0, cutoff=1.0), 20)
     assert (k.knn, k.search, k.sigma, k.cutoff, k.nclasses) == (5, 5, 1.0, 1.0, 20)
+
+
+def test_install_rebinds_trainer_selection():
+    import coarse3d_b200
+    from coarse3d_b200.trainer_ops import entropy_based_selection
+
+    class Trainer:
+        def entropy_based_selection(self, output, wss_mask, eval_mask, train_label, select_ratio):
+            raise AssertionError("reference path")
+
+    coarse3d_b200.install(_fake_pc_processor(), trainer_cls=Trainer)
+    assert Trainer.entropy_based_selection is entropy_based_selection
+    assert list(inspect.signature(entropy_based_selection).parameters) == [
+        "self", "output", "wss_mask", "eval_mask", "train_label", "select_ratio"]      # trainer.py:447-454

@@ -171,3 +171,21 @@ def test_unproject_confusion_matches_reference():
                                        torch.from_numpy(g["labels"]), int(g["nclasses"]))
     assert np.array_equal(u.numpy(), g["unproj_argmax"])
     assert np.array_equal(conf.numpy(), g["conf_matrix"]) and conf.sum() == len(g["px"])
+
+
+@pytest.mark.parametrize("case", ["small", "kitti_like"])
+def test_entropy_select_matches_reference(case):
+    """trainer.py:447-518 executed from the reference's Trainer with its multinomial draws
+    recorded; the oracle consumes the same draws and must give the same images."""
+    from oracle import entropy_select as osel
+    g = load_golden("entropy_select")[case]
+    label, mask, keys, thr = osel.entropy_based_selection(
+        torch.from_numpy(g["output"]), torch.from_numpy(g["wss_mask"]), torch.from_numpy(g["eval_mask"]),
+        torch.from_numpy(g["train_label"]), float(g["select_ratio"]), 0, torch.from_numpy(g["noise"]))
+    assert label.dtype == torch.int64 and mask.dtype == torch.bool
+    assert np.array_equal(label.numpy(), g["pseudo_label"])
+    assert np.array_equal(mask.numpy(), g["new_wss_mask"])
+    # the fixture exercises the selection: more pixels than the weak labels alone
+    assert g["new_wss_mask"].sum() > g["wss_mask"].sum() and len(thr) > 0
+    # ground truth kept (:515)
+    assert np.array_equal(g["pseudo_label"][g["wss_mask"]], g["train_label"][g["wss_mask"]])

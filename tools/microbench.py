@@ -39,7 +39,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--shape", default="kitti")
-    ap.add_argument("--ops", default="project,knn,assemble,unproject")
+    ap.add_argument("--ops", default="project,knn,assemble,unproject,select")
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     args = ap.parse_args()
@@ -92,6 +92,19 @@ def main():
                                                                labels=lab, conf_matrix=conf), flush=flush)
         by = (4 + 4 + 8 + 8 + 8) * N  # px, py i32; label i64; gathered class i64; output i64
         res["unproject_confusion"] = dict(ms=med, ms_min=mn, GBs=by / med / 1e6, scans_s=B / med * 1e3)
+    if "select" in args.ops:
+        C = shp.n_classes
+        g = torch.Generator(device="cuda").manual_seed(3)
+        probs = torch.softmax(2 * torch.randn(B, C, shp.proj_h, shp.proj_w, device="cuda", generator=g), 1)
+        ev = torch.rand(B, shp.proj_h, shp.proj_w, device="cuda", generator=g) < 0.7
+        tl = torch.randint(1, C, ev.shape, device="cuda", generator=g) * (torch.rand(ev.shape, device="cuda", generator=g) < 1e-3) * ev
+        wss = tl.gt(0)
+        ws = torch.empty(ops.lib.c3d_entropy_select_workspace_bytes(B, C, HW), dtype=torch.uint8, device="cuda")
+        with ops.profile("") as prof:
+            med, mn = timeit(lambda: ops.entropy_select_batch(probs, wss, ev, tl, 0.5, seed=5, workspace=ws), flush=flush)
+            kern = {n: round(1e3 * v[0] / v[1], 1) for n, v in prof.all().items()}
+        by = (4 * C + 1 + 8 + 1 + 8 + 1) * B * HW  # probs, eval mask, train label, weak mask; label i64 + mask out
+        res["entropy_select"] = dict(ms=med, ms_min=mn, GBs=by / med / 1e6, scans_s=B / med * 1e3, kernels_us=kern)
     print(json.dumps(dict(batch=B, shape=args.shape, results=res), indent=1))
 
 
