@@ -40,7 +40,7 @@ def _load():
         "c3d_entropy_select_batch": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_float, P,
                                              c_uint64, P, P, P, P]),
         "c3d_knn_batch": (c_int, [P, P, P, P, P, P, c_int, c_int64, c_int, c_int, c_int, c_int,
-                                  c_float, c_int, P, c_int, c_int, P, P]),
+                                  c_float, c_int, P, c_int, c_int, P, P, c_size_t, P]),
         "c3d_profile_enable": (c_int, [c_char_p]),
         "c3d_profile_read": (c_int, [c_char_p, P, P]),
         "c3d_profile_names": (c_int, [P, c_int]),

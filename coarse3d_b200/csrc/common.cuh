@@ -54,6 +54,9 @@ inline int check_launch(const char* what) {
     }                                                                    \
   } while (0)
 
+// Zero fill with 128-bit streaming stores (proto_loss.cu); shared with the KNN entry point.
+int launch_fill(void* dst, size_t nbytes, cudaStream_t stream);
+
 // Grid for a grid-stride kernel: whole waves of the 148 SMs.
 inline int wave_grid(long long work_items, int threads, int ctas_per_sm) {
   long long blocks = (work_items + threads - 1) / threads;

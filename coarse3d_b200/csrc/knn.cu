@@ -17,33 +17,102 @@
 // ALU-pipe bound, not memory bound (profiles/).
 //
 // Compiled with -fmad=false (|a-b| * w must round like torch's separate ops).
+//
+// Co-scheduled zero fill (kFill).  The vote is ALU-pipe bound and leaves HBM idle; the
+// dense-gradient zero fill of the loss backward (98 % of the step's bytes) is the opposite.
+// Run as two kernels they do not overlap (the fill's CTAs occupy every SM slot first), so
+// the caller may hand the fill to this kernel.  Two forms (kFill):
+//   1  every thread issues 128-bit streaming stores between the window rows.  Measured: no
+//      gain (132 us fused vs 62 + 81 us apart at B=8) -- the vote's gathers and the fill's
+//      stores share the LSU / L1TEX path, which is what both kernels are really bound by.
+//   2  TMA: each CTA keeps an 8 KB zero page in shared memory and ONE thread issues
+//      cp.async.bulk shared->global copies of it (UBLKCP) over the CTA's share of the buffer.
+//      The copy engine streams the page to L2 without LSU wavefronts or issue slots, so the
+//      vote keeps the LSU and the ALU while the fill keeps HBM busy.
 #include <math_constants.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
 namespace c3d {
 
+constexpr int kZeroPage = 8192;  // bytes of the shared-memory zero page (TMA fill source)
+
+__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n"
+               :: "l"(gdst), "r"((unsigned)__cvta_generic_to_shared(ssrc)), "r"(bytes) : "memory");
+}
+// Same copy with an L2 evict-first policy: the zero lines should not displace the range /
+// class images the vote gathers from.
+__device__ __forceinline__ void bulk_store_evict_first(void* gdst, const void* ssrc, unsigned bytes) {
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(pol));
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;\n"
+               :: "l"(gdst), "r"((unsigned)__cvta_generic_to_shared(ssrc)), "r"(bytes), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_all() {
+  asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+}
+
 // KT >= knn is the compile-time capacity of the top-k network (KT == knn for knn <= 8).
-template <int S, int KT>
+template <int S, int KT, int kFill>
 __global__ void __launch_bounds__(256, (S <= 5 && KT <= 8) ? 5 : 1)
 knn_vote_kernel(const float* __restrict__ proj_range, const void* __restrict__ proj_argmax,
                 const float* __restrict__ unproj_range, const void* __restrict__ px_,
                 const void* __restrict__ py_, const int32_t* __restrict__ offsets, int batch,
                 int total, int H, int W, int knn, float cutoff, int nclasses,
                 const float* __restrict__ inv_gauss, void* __restrict__ out, int pxy64, int lab64,
-                int vec_ok) {
+                int vec_ok, float4* __restrict__ cofill, unsigned long long cofill_n4,
+                unsigned long long cofill_per_cta) {
   constexpr int S2 = S * S;
   constexpr int PAD = (S - 1) / 2;
   extern __shared__ int32_t s_off[];
   __shared__ float s_w[S2];
   __shared__ int s_b0;
+  __shared__ __align__(128) float4 s_zero[kFill >= 2 ? kZeroPage / 16 : 1];
   for (int i = threadIdx.x; i <= batch; i += blockDim.x) s_off[i] = offsets[i];
   for (int i = threadIdx.x; i < S2; i += blockDim.x) s_w[i] = inv_gauss[i];
+  if (kFill >= 2) {
+    for (int i = threadIdx.x; i < kZeroPage / 16; i += blockDim.x) s_zero[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // page visible to the copy engine
+  }
   __syncthreads();
   if (threadIdx.x == 0) s_b0 = scan_of(s_off, batch, min(blockIdx.x * blockDim.x, total - 1));
   __syncthreads();
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= total) return;
+  // this CTA's share of the co-scheduled fill, in 16-byte units
+  float4* fbase = nullptr;
+  int f_cnt = 0;        // kFill 1: stores left to this thread; kFill 2: pages of this CTA
+  unsigned f_last = 0;  // kFill 2: bytes of the CTA's last page
+  if (kFill) {
+    const unsigned long long lo = blockIdx.x * cofill_per_cta;
+    const unsigned long long hi = min(lo + cofill_per_cta, cofill_n4);
+    if (kFill == 1) {
+      fbase = cofill + lo + threadIdx.x;
+      f_cnt = lo + threadIdx.x < hi ? (int)((hi - lo - threadIdx.x + 255) / 256) : 0;
+    } else if (lo < hi) {  // kFill 2, 3
+      fbase = cofill + lo;
+      f_cnt = (int)((hi - lo + kZeroPage / 16 - 1) / (kZeroPage / 16));
+      f_last = (unsigned)((hi - lo - (unsigned long long)(f_cnt - 1) * (kZeroPage / 16)) * 16);
+    }
+  }
+  auto fill_part = [&](int part, int nparts) {
+    if (kFill == 1) {
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int j = part; j < f_cnt; j += nparts) __stcs(fbase + (size_t)j * 256, z);
+    } else if (kFill >= 2) {
+      if (threadIdx.x == 0) {
+        for (int j = part; j < f_cnt; j += nparts) {
+          const unsigned nb = j == f_cnt - 1 ? f_last : (unsigned)kZeroPage;
+          if (kFill == 3) bulk_store_evict_first(fbase + (size_t)j * (kZeroPage / 16), s_zero, nb);
+          else bulk_store(fbase + (size_t)j * (kZeroPage / 16), s_zero, nb);
+        }
+        bulk_commit();
+      }
+    }
+  };
+  if (g >= total) { fill_part(0, 1); return; }
   int b = s_b0;
   while (g >= s_off[b + 1]) ++b;
   const int HW = H * W;
@@ -81,6 +150,7 @@ knn_vote_kernel(const float* __restrict__ proj_range, const void* __restrict__ p
         if (rowok && xq >= 0 && xq < W) v = __ldg(reinterpret_cast<const float4*>(rowp + 4 * q));
         w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
       }
+      fill_part(dy, S);
 #pragma unroll
       for (int i = NQ * 4; i < NQ * 4 + 4; ++i) w[i] = 0.f;
       // v[dx] = w[o + dx], o in 0..3: two-level select
@@ -104,6 +174,7 @@ knn_vote_kernel(const float* __restrict__ proj_range, const void* __restrict__ p
       const int y = y0 + dy - PAD;
       const bool rowok = (y >= 0) && (y < H);
       const float* rowp = img + y * W + (x0 - PAD);
+      fill_part(dy, S);
 #pragma unroll
       for (int dx = 0; dx < S; ++dx) {
         float v = 0.0f;  // F.unfold zero padding (knn.py:79-81)
@@ -226,21 +297,45 @@ knn_vote_kernel(const float* __restrict__ proj_range, const void* __restrict__ p
   }
   if (lab64) reinterpret_cast<long long*>(out)[g] = best_c;
   else reinterpret_cast<int*>(out)[g] = best_c;
+  // the zero page must outlive the copies that read it (thread 0 is always a valid point)
+  if (kFill >= 2 && threadIdx.x == 0) bulk_wait_read_all();
 }
 
 template <int S, int KT>
 static int launch_knn_sk(const float* proj_range, const void* proj_argmax, const float* unproj_range,
                          const void* px, const void* py, const int32_t* offsets, int batch, int total,
                          int H, int W, int knn, float cutoff, int nclasses, const float* inv_gauss,
-                         void* out, int pxy64, int lab64, cudaStream_t stream) {
+                         void* out, int pxy64, int lab64, void* cofill, size_t cofill_bytes,
+                         cudaStream_t stream) {
   const int threads = 256;
   const int grid = (total + threads - 1) / threads;  // short CTAs: SM slots free up quickly
   const size_t smem = (size_t)(batch + 1) * sizeof(int32_t);
+  const int vec_ok = (W % 4 == 0 && (reinterpret_cast<uintptr_t>(proj_range) & 15) == 0) ? 1 : 0;
+  if (cofill && cofill_bytes) {
+    const unsigned long long n4 = cofill_bytes / 16;
+    unsigned long long per_cta = (n4 + grid - 1) / grid;
+    per_cta = (per_cta + 511) / 512 * 512;  // whole 8 KB pages (and 4 KB CTA-wide store rounds)
+    const char* env = getenv("C3D_KNN_COFILL_MODE");
+    const int mode = (env && env[0] >= '1' && env[0] <= '3') ? env[0] - '0' : 2;
+    KernelTimer timer("knn_vote_fill_kernel", stream);
+    if (mode == 3)
+      knn_vote_kernel<S, KT, 3><<<grid, threads, smem, stream>>>(
+          proj_range, proj_argmax, unproj_range, px, py, offsets, batch, total, H, W, knn, cutoff,
+          nclasses, inv_gauss, out, pxy64, lab64, vec_ok, reinterpret_cast<float4*>(cofill), n4, per_cta);
+    else if (mode == 2)
+      knn_vote_kernel<S, KT, 2><<<grid, threads, smem, stream>>>(
+          proj_range, proj_argmax, unproj_range, px, py, offsets, batch, total, H, W, knn, cutoff,
+          nclasses, inv_gauss, out, pxy64, lab64, vec_ok, reinterpret_cast<float4*>(cofill), n4, per_cta);
+    else
+      knn_vote_kernel<S, KT, 1><<<grid, threads, smem, stream>>>(
+          proj_range, proj_argmax, unproj_range, px, py, offsets, batch, total, H, W, knn, cutoff,
+          nclasses, inv_gauss, out, pxy64, lab64, vec_ok, reinterpret_cast<float4*>(cofill), n4, per_cta);
+    return check_launch("knn_vote_fill_kernel");
+  }
   KernelTimer timer("knn_vote_kernel", stream);
-  knn_vote_kernel<S, KT><<<grid, threads, smem, stream>>>(
+  knn_vote_kernel<S, KT, 0><<<grid, threads, smem, stream>>>(
       proj_range, proj_argmax, unproj_range, px, py, offsets, batch, total, H, W, knn, cutoff,
-      nclasses, inv_gauss, out, pxy64, lab64,
-      (W % 4 == 0 && (reinterpret_cast<uintptr_t>(proj_range) & 15) == 0) ? 1 : 0);
+      nclasses, inv_gauss, out, pxy64, lab64, vec_ok, nullptr, 0, 0);
   return check_launch("knn_vote_kernel");
 }
 
@@ -249,11 +344,11 @@ static int launch_knn_s(int knn, const float* proj_range, const void* proj_argma
                         const float* unproj_range, const void* px, const void* py,
                         const int32_t* offsets, int batch, int total, int H, int W, float cutoff,
                         int nclasses, const float* inv_gauss, void* out, int pxy64, int lab64,
-                        cudaStream_t stream) {
+                        void* cofill, size_t cofill_bytes, cudaStream_t stream) {
 #define KNN_CALL(KT_)                                                                          \
   return launch_knn_sk<S, KT_>(proj_range, proj_argmax, unproj_range, px, py, offsets, batch,  \
                                total, H, W, knn, cutoff, nclasses, inv_gauss, out, pxy64, lab64, \
-                               stream)
+                               cofill, cofill_bytes, stream)
   switch (knn) {
     case 1: KNN_CALL(1);
     case 2: KNN_CALL(2);
@@ -282,7 +377,8 @@ extern "C" int c3d_knn_batch(const float* proj_range, const void* proj_argmax,
                              const int32_t* offsets, int batch, int64_t total_points, int proj_h,
                              int proj_w, int knn, int search, float cutoff, int nclasses,
                              const float* inv_gauss, int pxy_is_i64, int label_is_i64,
-                             void* out_labels, void* stream_) {
+                             void* out_labels, void* cofill_ptr, size_t cofill_bytes,
+                             void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   C3D_REQUIRE(search % 2 == 1, "Nearest neighbor kernel must be odd number");  // knn.py:72-73
   C3D_REQUIRE(batch > 0 && batch <= kMaxBatch, "batch must be in [1, %d]", kMaxBatch);
@@ -291,11 +387,14 @@ extern "C" int c3d_knn_batch(const float* proj_range, const void* proj_argmax,
   C3D_REQUIRE(total_points >= 0 && total_points < (1ll << 31), "total_points out of range");
   C3D_REQUIRE(proj_h > 0 && proj_w > 0, "bad image size");
   C3D_REQUIRE(proj_range && proj_argmax && offsets && inv_gauss, "null pointer argument");
-  if (total_points == 0) return C3D_OK;
+  C3D_REQUIRE((cofill_ptr == nullptr) == (cofill_bytes == 0), "cofill_ptr and cofill_bytes go together");
+  C3D_REQUIRE((reinterpret_cast<uintptr_t>(cofill_ptr) & 15) == 0 && cofill_bytes % 16 == 0,
+              "co-scheduled fill must be 16 B aligned and a multiple of 16 B");
+  if (total_points == 0) return cofill_ptr ? launch_fill(cofill_ptr, cofill_bytes, stream) : C3D_OK;
   C3D_REQUIRE(unproj_range && px && py && out_labels, "null per-point pointer");
 #define KNN_ARGS knn, proj_range, proj_argmax, unproj_range, px, py, offsets, batch,            \
                  (int)total_points, proj_h, proj_w, cutoff, nclasses, inv_gauss, out_labels,     \
-                 pxy_is_i64, label_is_i64, stream
+                 pxy_is_i64, label_is_i64, cofill_ptr, cofill_bytes, stream
   switch (search) {
     case 3: return launch_knn_s<3>(KNN_ARGS);
     case 5: return launch_knn_s<5>(KNN_ARGS);

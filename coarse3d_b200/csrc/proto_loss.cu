@@ -816,7 +816,7 @@ fill_zero_kernel(float4* __restrict__ dst, size_t n4, float* __restrict__ tail, 
   if (blockIdx.x == 0 && (int)threadIdx.x < ntail) tail[threadIdx.x] = 0.f;
 }
 
-static int launch_fill(void* dst, size_t nbytes, cudaStream_t stream) {
+int launch_fill(void* dst, size_t nbytes, cudaStream_t stream) {
   const size_t n = nbytes / 4, n4 = n / 4;
   const size_t per_cta = 256 * kFillPerThread;
   size_t grid = (n4 + per_cta - 1) / per_cta;

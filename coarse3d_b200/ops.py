@@ -176,12 +176,15 @@ def gaussian_kernel(kernel_size=3, sigma=2):
 
 
 def knn_batch(proj_range, proj_argmax, unproj_range, px, py, offsets, knn, search, sigma,
-              cutoff, nclasses, inv_gauss=None, out=None):
+              cutoff, nclasses, inv_gauss=None, out=None, cofill=None):
     """KNN.forward for a CSR batch (knn.py:54-142).
 
     proj_range (B,H,W) f32; px, py (sum N,) int64 (the reference's dtype) or
     int32 (project_batch's output); proj_argmax (B,H,W) int64 or int32; offsets
     (B+1,) i32.  Returns (sum N,) labels with proj_argmax's dtype.
+    `cofill`: a contiguous CUDA tensor zeroed by the same kernel (TMA bulk stores from a
+    shared-memory zero page while the vote keeps the ALU busy; the step pipeline passes the
+    loss's dense gradient buffer).
     """
     if search % 2 == 0:
         raise ValueError("Nearest neighbor kernel must be odd number")  # knn.py:72-73
@@ -204,10 +207,17 @@ def knn_batch(proj_range, proj_argmax, unproj_range, px, py, offsets, knn, searc
         inv_gauss = (1 - gaussian_kernel(search, sigma)).reshape(-1).to(proj_range.device)
     if out is None:
         out = torch.empty((total,), dtype=ldt, device=proj_range.device)
+    nfill = 0
+    if cofill is not None:
+        _need_cuda(cofill=cofill)
+        nfill = cofill.numel() * cofill.element_size()
+        if not cofill.is_contiguous() or nfill % 16 or cofill.data_ptr() % 16:
+            raise ValueError("cofill must be contiguous, 16 B aligned and a multiple of 16 B")
     check(lib.c3d_knn_batch(
         _p(proj_range), _p(proj_argmax), _p(unproj_range), _p(px), _p(py), _p(offsets), B, total,
         H, W, int(knn), int(search), float(cutoff), int(nclasses), _p(inv_gauss),
-        1 if idt == torch.int64 else 0, 1 if ldt == torch.int64 else 0, _p(out), _stream()))
+        1 if idt == torch.int64 else 0, 1 if ldt == torch.int64 else 0, _p(out),
+        _p(cofill) if nfill else None, nfill, _stream()))
     return out
 
 

@@ -91,7 +91,7 @@ class HotPathStep:
         self.graphs = None
         self.concurrent = concurrent
         import os as _os
-        self.schedule = _os.environ.get("C3D_SCHEDULE", "fill_after_projection")
+        self.schedule = _os.environ.get("C3D_SCHEDULE", "fill_in_knn")
         # ablation switch for tools/ablate.py: which chains run (default: all)
         self.parts = set(parts) if parts else {"proj", "knn", "fill", "loss", "ema"}
         # Priorities: the latency-bound chains (loss, EMA) high, so their small CTAs
@@ -126,12 +126,17 @@ class HotPathStep:
         s, b = self.sets[i % len(self.sets)], self.proj_bufs[i % len(self.sets)]
         H, W, C = self.shape.proj_h, self.shape.proj_w, self.shape.n_classes
         cur = torch.cuda.current_stream(self.device)
+        fused = self.schedule == "fill_in_knn" and {"knn", "fill"} <= self.parts
         if not self.concurrent:
             pr = ops.project_batch(s.points, s.offsets, self.fov, H, W, buffers=b)
             self._loss_fwd(s, seed)
-            ops.proto_loss_backward_raw(s.feats.shape, self.cfg, C, self.M, self.loss_ws, self.grad_out, self.grad)
+            if fused:
+                self._knn(s, pr, C, cofill=self.grad)
+            ops.proto_loss_backward_raw(s.feats.shape, self.cfg, C, self.M, self.loss_ws, self.grad_out,
+                                        self.grad, grad_is_zeroed=fused)
             self._ema(s, seed)
-            self._knn(s, pr, C)
+            if not fused:
+                self._knn(s, pr, C)
             return pr
         st_fill, st_proj, st_ema, st_loss = self.side
         self.ev_fork.record(cur)
@@ -140,7 +145,17 @@ class HotPathStep:
         P = self.parts
         pr = None
         sched = self.schedule
-        if sched == "fill_first":
+        if fused:
+            # The KNN vote (ALU bound) carries the zero fill (HBM bound): one kernel, both
+            # pipes busy.  As two kernels they serialise: the fill's CTAs occupy every SM slot.
+            with torch.cuda.stream(st_proj):
+                if "proj" in P:
+                    pr = ops.project_batch(s.points, s.offsets, self.fov, H, W, buffers=b)
+                self._knn(s, pr if pr is not None else self._last_proj(b), C, cofill=self.grad)
+                self.ev_proj.record(st_proj)
+            st_fill.wait_event(self.ev_proj)
+            self.ev_fill.record(st_fill)
+        elif sched == "fill_first":
             # fill (optionally throttled, C3D_FILL_PERSISTENT) together with the latency-bound
             # loss / EMA chains from t = 0; projection -> KNN afterwards
             with torch.cuda.stream(st_fill):
@@ -201,10 +216,10 @@ class HotPathStep:
             assign_mode=ops.ASSIGN_GUMBEL_DEVICE, seed=seed, max_rows=self.max_rows, group=self.group,
             workspace=self.ema_ws, packed=self.packed, out=self.protos_next)
 
-    def _knn(self, s, pr, C):
+    def _knn(self, s, pr, C, cofill=None):
         ops.knn_batch(pr.proj_range, s.argmax, pr.uproj_depth, pr.uproj_x_idx, pr.uproj_y_idx,
                       s.offsets, self.knn_k, self.knn_s, self.knn_sigma, self.knn_cutoff, C,
-                      inv_gauss=self.inv_gauss, out=self.knn_out)
+                      inv_gauss=self.inv_gauss, out=self.knn_out, cofill=cofill)
 
     def capture(self):
         """Capture one CUDA graph per input set.  Returns False if capture fails

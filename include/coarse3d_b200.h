@@ -126,6 +126,11 @@ int c3d_project_assemble_batch(
  * pxy_is_i64 selects the dtype of px / py, label_is_i64 that of proj_argmax /
  * out_labels (int64 = the reference's dtypes, int32 = this library's
  * projection outputs).
+ *
+ * Co-scheduled fill: the vote is ALU bound and leaves HBM idle, so the caller may hand it
+ * an unrelated zero fill -- in the hot-path step the dense gradient buffer of
+ * c3d_proto_loss_backward (then called with grad_is_zeroed=1).  [cofill_ptr, +cofill_bytes)
+ * is zeroed by the time the kernel completes; pass NULL / 0 for the plain vote.
  */
 int c3d_knn_batch(
     const float* proj_range,      /* [batch, H, W]                               */
@@ -139,6 +144,8 @@ int c3d_knn_batch(
     const float* inv_gauss,       /* [search*search]                             */
     int pxy_is_i64, int label_is_i64,
     void* out_labels,             /* [total_points] i64 or i32, in [1, C-1]      */
+    void* cofill_ptr,             /* 16 B aligned buffer to zero meanwhile, or NULL */
+    size_t cofill_bytes,          /* multiple of 16                              */
     void* stream);
 
 /* ---------------------------------------------------------------- f2 ----

@@ -117,3 +117,42 @@ def test_random_images_any_width(cuda_device, W, k, s):
                             torch.from_numpy(py).cuda(), torch.tensor([0, P], dtype=torch.int32).cuda(),
                             k, s, 1.0, cutoff, C)
         assert np.array_equal(out.cpu().numpy(), want), int((out.cpu().numpy() != want).sum())
+
+
+@pytest.mark.parametrize("mode", ["2", "1"])     # TMA bulk stores (default) / per-thread stores
+@pytest.mark.parametrize("nfill,W", [(16, 64), (4096 * 7 + 16, 64), (1 << 22, 101), (999 * 16, 7),
+                                     (8192 * 10, 64), (8192 * 10 + 48, 64)])
+def test_co_scheduled_fill_zeroes_exactly_its_buffer(cuda_device, monkeypatch, nfill, W, mode):
+    """The vote kernel can carry a zero fill (the loss's dense gradient in the step
+    pipeline): labels are unchanged, every byte of the buffer is zero, guards untouched."""
+    from coarse3d_b200 import ops
+    monkeypatch.setenv("C3D_KNN_COFILL_MODE", mode)
+    rng = np.random.default_rng(nfill % 1000 + W)
+    H, P, C = 9, 2500, 11
+    proj_range = rng.uniform(1, 30, (H, W)).astype(np.float32)
+    proj_range[rng.random((H, W)) < 0.3] = -1.0
+    argmax = rng.integers(0, C, (H, W))
+    px, py = rng.integers(0, W, P), rng.integers(0, H, P)
+    ur = rng.uniform(1, 30, P).astype(np.float32)
+    args = (torch.from_numpy(proj_range[None]).cuda(), torch.from_numpy(argmax[None]).cuda(),
+            torch.from_numpy(ur).cuda(), torch.from_numpy(px).cuda(), torch.from_numpy(py).cuda(),
+            torch.tensor([0, P], dtype=torch.int32).cuda(), 5, 5, 1.0, 1.0, C)
+    plain = ops.knn_batch(*args)
+    guard = 64
+    buf = torch.full((nfill + 2 * guard,), 0xAB, dtype=torch.uint8, device="cuda")
+    out = ops.knn_batch(*args, cofill=buf[guard:guard + nfill])
+    assert torch.equal(out, plain)
+    assert int(buf[guard:guard + nfill].max()) == 0
+    assert bool((buf[:guard] == 0xAB).all()) and bool((buf[guard + nfill:] == 0xAB).all())
+    with pytest.raises(ValueError):
+        ops.knn_batch(*args, cofill=buf[guard + 4:guard + 4 + 32])       # not 16 B aligned
+
+
+def test_co_scheduled_fill_without_points(cuda_device):
+    from coarse3d_b200 import ops
+    z = torch.zeros((1, 4, 8), device="cuda")
+    e = torch.zeros((0,), device="cuda")
+    buf = torch.ones(4096, device="cuda")
+    ops.knn_batch(z, z.long(), e, e.long(), e.long(), torch.zeros(2, dtype=torch.int32, device="cuda"),
+                  5, 5, 1.0, 1.0, 5, cofill=buf)
+    assert float(buf.abs().max()) == 0.0

@@ -154,3 +154,47 @@ def test_full_size_properties_and_hybrid_equals_f64(cuda_device, monkeypatch):
     assert torch.equal(P[gidx], out.proj_pointcloud[valid])
     assert torch.equal(out.proj_mask, (out.proj_idx > 0).int())
     assert (out.proj_pointcloud[~valid] == -1).all()
+
+
+def test_estimate_guard_band_on_adversarial_points(cuda_device, monkeypatch):
+    """Points constructed to sit on / next to pixel boundaries, on the axes, at extreme
+    magnitudes and outside the vertical field of view: the fast-transcendental + guard band
+    path must give exactly the exact-chain pixels (C3D_PROJECT_F64_ONLY=1) and the oracle's."""
+    from coarse3d_b200 import ops
+    rng = np.random.default_rng(11)
+    H, W, up, down = 64, 2048, 3.0, -25.0
+    fov_v = np.deg2rad(up - down)
+    n = 200_000
+    # yaw exactly on column boundaries (+- a few ulp), pitch exactly on row boundaries
+    col = rng.integers(0, W, n)
+    yaw = (col / W) * 2 * np.pi - np.pi
+    row = rng.integers(0, H, n)
+    pitch = (1.0 - row / H) * fov_v - abs(np.deg2rad(down))
+    on_row = rng.random(n) < 0.5
+    pitch = np.where(on_row, pitch, np.deg2rad(rng.uniform(down - 20, up + 60, n)))
+    r = np.exp(rng.uniform(np.log(0.3), np.log(200), n))
+    x = r * np.cos(pitch) * np.cos(-yaw)
+    y = r * np.cos(pitch) * np.sin(-yaw)
+    z = r * np.sin(pitch)
+    pts = np.stack([x, y, z, rng.random(n)], 1).astype(np.float32)
+    for k in range(1, 4):   # nudge by a few ulp either way
+        sel = slice(k, n, 7)
+        pts[sel, :3] = np.nextafter(pts[sel, :3], np.float32(np.inf if k % 2 else -np.inf))
+    special = np.array([[1, 0, 0, 0], [-1, 0, 0, 0], [0, 1, 0, 0], [0, -1, 0, 0], [-1, -0.0, 0, 0],
+                        [1e-15, 1e-16, 1e-17, 0], [1e-15, -1e-15, 1e-16, 0], [3e18, 1e18, -1e18, 0],
+                        [1e25, -1e25, 1e24, 0], [0, 0, 1, 0], [0, 0, -1, 0], [1e-3, 1e-3, 5, 0],
+                        [5, 5, -5, 0], [1, 1, 1.4, 0], [1, -1, -1.39, 0]], np.float32)
+    pts = np.concatenate([special, pts], 0)
+    P = torch.from_numpy(pts).cuda()
+    O = torch.tensor([0, pts.shape[0]], dtype=torch.int32, device="cuda")
+    fov = ops.Fov.from_degrees(up, down)
+    monkeypatch.setenv("C3D_PROJECT_F64_ONLY", "1")
+    ref = [t.clone() for t in ops.project_batch(P, O, fov, H, W)]
+    monkeypatch.setenv("C3D_PROJECT_F64_ONLY", "0")
+    out = ops.project_batch(P, O, fov, H, W)
+    for a, b in zip(out, ref):
+        assert torch.equal(a, b)
+    o = oproj.project(pts, oproj.Fov(fov_up=up, fov_down=down, proj_h=H, proj_w=W))
+    assert np.array_equal(out.uproj_x_idx.cpu().numpy(), o["uproj_x_idx"])
+    assert np.array_equal(out.uproj_y_idx.cpu().numpy(), o["uproj_y_idx"])
+    assert np.array_equal(out.proj_idx[0].cpu().numpy(), o["proj_idx"])
