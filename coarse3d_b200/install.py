@@ -22,6 +22,7 @@ def install(pc_processor=None, trainer_cls=None):
     from .pc_processor.dataset.preprocess.projection import RangeProjection
     from .pc_processor.postproc.knn import KNN
     from .pc_processor.loss.contrast_pixel_loss import ContrastMEMLoss
+    from .pc_processor.loss.lovasz_softmax import Lovasz_softmax, lovasz_softmax
 
     pc_processor.dataset.preprocess.projection.RangeProjection = RangeProjection
     pc_processor.dataset.preprocess.RangeProjection = RangeProjection
@@ -29,6 +30,10 @@ def install(pc_processor=None, trainer_cls=None):
     pc_processor.postproc.KNN = KNN
     pc_processor.loss.contrast_pixel_loss.ContrastMEMLoss = ContrastMEMLoss
     pc_processor.loss.ContrastMEMLoss = ContrastMEMLoss
+    if hasattr(pc_processor.loss, "lovasz_softmax"):   # pc_processor/loss/__init__.py:2
+        pc_processor.loss.lovasz_softmax.Lovasz_softmax = Lovasz_softmax
+        pc_processor.loss.lovasz_softmax.lovasz_softmax = lovasz_softmax
+    pc_processor.loss.Lovasz_softmax = Lovasz_softmax
     if trainer_cls is not None:
         from .trainer_ops import entropy_based_selection
         trainer_cls.entropy_based_selection = entropy_based_selection

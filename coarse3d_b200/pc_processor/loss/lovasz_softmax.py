@@ -1,0 +1,64 @@
+"""Lovasz_softmax with the reference's interface, running on the B200.
+
+Mirrors pc_processor/loss/lovasz_softmax.py:160-179 (`Lovasz_softmax`) and :67-98
+(`lovasz_softmax`): same constructor arguments, `forward(probas, labels)` returning a 0-dim
+loss with autograd to `probas`, the same NaN assertion.  The arithmetic runs in
+`c3d_lovasz_forward` / `c3d_lovasz_backward`.
+
+Differences a caller can observe:
+  * ties between equal errors rank by ascending pixel index (torch.sort is unstable);
+  * the rank pass is quadratic in the number of valid pixels, so at most 32768 pixels may
+    carry a label (weak labels: ~1e3 per batch) -- more raises ValueError in strict mode;
+  * with no valid pixel the reference returns an empty tensor (and the trainer skips such
+    batches, trainer.py:586-589); here the loss is 0 with zero gradient;
+  * `classes` may be "present" (default) or "all", not a list.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from coarse3d_b200 import ops
+
+
+def lovasz_softmax(probas, labels, classes="present", per_image=False, ignore=None, softmax=False,
+                   strict=False):
+    if softmax:
+        probas = F.softmax(probas, 1)                              # lovasz_softmax.py:80-81
+    if probas.dim() == 3:                                          # (B,C,N) form, :143-147
+        probas = probas.unsqueeze(-1)
+        labels = labels.unsqueeze(-1)
+    labels = labels.long()
+    if per_image:                                                  # :82-89: mean over images
+        losses = [_one(p.unsqueeze(0), l.unsqueeze(0), classes, ignore, strict)
+                  for p, l in zip(probas, labels)]
+        acc = losses[0]
+        for v in losses[1:]:
+            acc = acc + v
+        return acc if len(losses) == 1 else acc / len(losses)
+    return _one(probas, labels, classes, ignore, strict)
+
+
+def _one(probas, labels, classes, ignore, strict):
+    loss, ws = ops.lovasz_softmax(probas.float(), labels, ignore=ignore, classes=classes)
+    if strict:
+        n_valid, _, flags = ops.lovasz_info(ws)
+        if flags & 1:
+            raise ValueError("Lovasz_softmax: %d labelled pixels exceed the supported %d"
+                             % (n_valid, ops.LOVASZ_MAX_VALID))
+    return loss
+
+
+class Lovasz_softmax(nn.Module):
+    def __init__(self, classes="present", per_image=False, ignore=None, softmax=False, strict=False):
+        super(Lovasz_softmax, self).__init__()
+        self.classes = classes
+        self.per_image = per_image
+        self.ignore = ignore
+        self.softmax = softmax
+        self.strict = strict
+
+    def forward(self, probas, labels):
+        loss = lovasz_softmax(probas, labels, self.classes, self.per_image, self.ignore, self.softmax,
+                              self.strict)
+        assert not torch.any(torch.isnan(loss)), "lov loss is none"   # lovasz_softmax.py:178
+        return loss

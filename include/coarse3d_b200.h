@@ -189,6 +189,40 @@ int c3d_entropy_select_batch(
     uint8_t* out_mask,            /* [B, H, W] bool: label != ignore_cls (:516)  */
     void* stream);
 
+/* ---------------------------------------------------------------- f4 ----
+ * Lovasz-softmax loss, pc_processor/loss/lovasz_softmax.py:51-157 (lovasz_grad,
+ * lovasz_softmax_flat, flatten_probas), as the trainer calls it
+ * (tasks/weak_segmentation/trainer.py:362-364,650): class probabilities, weak labels,
+ * `ignore`, classes = "present" (classes_all = 0) or "all" (1), per_image = False.
+ * Forward keeps per-element gradient entries in the workspace; backward zero-fills the
+ * dense (B,C,H,W) gradient (unless grad_is_zeroed) and scatters P x C entries scaled by
+ * grad_out.  The rank pass is quadratic in the number of valid pixels P, so max_valid is
+ * capped at 32768 (weak labels: ~1e3 per batch); more valid pixels set flag bit 0 and are
+ * dropped, max_valid above the cap returns C3D_UNSUPPORTED.  Ties in the errors rank by
+ * ascending pixel index (torch.sort is unstable).  ignore < 0: no ignored label.
+ */
+size_t c3d_lovasz_workspace_bytes(int n_classes, int64_t max_valid);
+
+int c3d_lovasz_forward(
+    const float* probs,           /* [B, C, H, W] class probabilities            */
+    const int64_t* labels,        /* [B, H, W]                                   */
+    int batch, int n_classes, int proj_h, int proj_w, int ignore, int classes_all,
+    int64_t max_valid,
+    void* workspace,              /* c3d_lovasz_workspace_bytes, 256 B aligned   */
+    float* loss_out,              /* [1]                                         */
+    void* stream);
+
+int c3d_lovasz_backward(
+    int batch, int n_classes, int proj_h, int proj_w, int classes_all, int64_t max_valid,
+    void* workspace,              /* as left by c3d_lovasz_forward               */
+    const float* grad_out,        /* [1] upstream gradient                       */
+    float* grad_probs,            /* [B, C, H, W], 16 B aligned                  */
+    int grad_is_zeroed, void* stream);
+
+/* Synchronous: host_info4 = {valid pixels, classes averaged, flags (1: more than max_valid
+ * valid pixels, 2: none), 0}. */
+int c3d_lovasz_info(const void* workspace, int32_t* host_info4, void* stream);
+
 /* ---------------------------------------------------------------- a2 ----
  * ContrastMEMLoss.forward, pc_processor/loss/contrast_pixel_loss.py:27-195,
  * and its autograd (gradient w.r.t. feats only; the bank is detached at

@@ -14,6 +14,7 @@ with hand-written CUDA:
     oracle.unproject    <- tasks/weak_segmentation/trainer.py:714-724,
                            pc_processor/metrics/iou_eval.py:35-58
     oracle.entropy_select <- tasks/weak_segmentation/trainer.py:447-518
+    oracle.lovasz       <- pc_processor/loss/lovasz_softmax.py:51-157
 
 Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline /
 `--impl reference` legs may import it, and only as the checker or the timed CPU

@@ -395,6 +395,35 @@ def gold_entropy_select(pcp):
     print("entropy_select: ok", {k: int(c["new_wss_mask"].sum()) for k, c in cases.items()})
 
 
+def gold_lovasz(pcp):
+    """Lovasz_softmax (pc_processor/loss/lovasz_softmax.py:160-179) executed from the
+    reference, as the trainer builds it (trainer.py:362-364: ignore=ignore_cls,
+    per_image=False, softmax=False); loss and autograd gradient.  Random probabilities have
+    no equal errors, so the unstable torch.sort leaves nothing undefined."""
+    Lov = pcp.loss.Lovasz_softmax
+    cases = {}
+    for name, B, C, H, W, frac, classes, seed in [("weak", 2, 20, 16, 256, 0.02, "present", 81),
+                                                  ("all_classes", 1, 6, 8, 64, 0.3, "all", 82),
+                                                  ("one_class", 2, 5, 8, 32, 0.05, "present", 83)]:
+        g = torch.Generator().manual_seed(seed)
+        probs = torch.softmax(torch.randn(B, C, H, W, generator=g) * 1.5, 1).requires_grad_(True)
+        labels = torch.randint(1, C, (B, H, W), generator=g) * (torch.rand(B, H, W, generator=g) < frac)
+        if name == "one_class":
+            labels = (labels > 0).long() * 3
+        crit = Lov(classes=classes, ignore=0, per_image=False, softmax=False)
+        loss = crit(probs, labels)
+        loss.backward()
+        e = (torch.nn.functional.one_hot(labels, C).permute(0, 3, 1, 2).float() - probs.detach()).abs()
+        v = e.permute(0, 2, 3, 1)[labels != 0]
+        assert all(len(torch.unique(v[:, c])) == v.shape[0] for c in range(C)), "tied errors in fixture"
+        cases[name] = dict(probs=probs.detach().numpy(), labels=labels.numpy(), ignore=np.int64(0),
+                           classes_all=np.int64(classes == "all"), loss=loss.detach().numpy(),
+                           grad=probs.grad.numpy())
+    flat = {f"{k}/{f}": np.asarray(v) for k, c in cases.items() for f, v in c.items()}
+    np.savez_compressed(os.path.join(OUT, "lovasz.npz"), **flat)
+    print("lovasz: ok", {k: float(c["loss"]) for k, c in cases.items()})
+
+
 if __name__ == "__main__":
     pcp = import_reference()
     gold_projection(pcp)
@@ -404,3 +433,4 @@ if __name__ == "__main__":
     gold_assemble(pcp)
     gold_unproject(pcp)
     gold_entropy_select(pcp)
+    gold_lovasz(pcp)

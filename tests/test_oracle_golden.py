@@ -189,3 +189,17 @@ def test_entropy_select_matches_reference(case):
     assert g["new_wss_mask"].sum() > g["wss_mask"].sum() and len(thr) > 0
     # ground truth kept (:515)
     assert np.array_equal(g["pseudo_label"][g["wss_mask"]], g["train_label"][g["wss_mask"]])
+
+
+@pytest.mark.parametrize("case", ["weak", "all_classes", "one_class"])
+def test_lovasz_matches_reference(case):
+    """Lovasz_softmax executed from the reference (loss and autograd gradient) vs the oracle."""
+    from oracle import lovasz as olov
+    g = load_golden("lovasz")[case]
+    probs = torch.from_numpy(g["probs"]).requires_grad_(True)
+    loss = olov.lovasz_softmax(probs, torch.from_numpy(g["labels"]), ignore=int(g["ignore"]),
+                               classes="all" if int(g["classes_all"]) else "present")
+    loss.backward()
+    assert abs(float(loss) - float(g["loss"])) <= 1e-6 * abs(float(g["loss"]))
+    assert np.array_equal(probs.grad.numpy() != 0, g["grad"] != 0)
+    assert np.abs(probs.grad.numpy() - g["grad"]).max() <= 1e-6 * np.abs(g["grad"]).max()

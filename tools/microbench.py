@@ -39,7 +39,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--shape", default="kitti")
-    ap.add_argument("--ops", default="project,knn,assemble,unproject,select")
+    ap.add_argument("--ops", default="project,knn,assemble,unproject,select,lovasz")
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     args = ap.parse_args()
@@ -111,6 +111,24 @@ def main():
             kern = {n: round(1e3 * v[0] / v[1], 1) for n, v in prof.all().items()}
         by = (4 * C + 1 + 8 + 1 + 8 + 1) * B * HW  # probs, eval mask, train label, weak mask; label i64 + mask out
         res["entropy_select"] = dict(ms=med, ms_min=mn, GBs=by / med / 1e6, scans_s=B / med * 1e3, kernels_us=kern)
+    if "lovasz" in args.ops:
+        C = shp.n_classes
+        g = torch.Generator(device="cuda").manual_seed(4)
+        probs = torch.softmax(torch.randn(B, C, shp.proj_h, shp.proj_w, device="cuda", generator=g), 1).requires_grad_(True)
+        lab = torch.randint(1, C, (B, shp.proj_h, shp.proj_w), device="cuda", generator=g) * \
+            (torch.rand(B, shp.proj_h, shp.proj_w, device="cuda", generator=g) < shp.label_ratio)
+        ws = torch.empty(ops.lib.c3d_lovasz_workspace_bytes(C, ops.LOVASZ_MAX_VALID), dtype=torch.uint8, device="cuda")
+
+        def lov():
+            probs.grad = None
+            loss, _ = ops.lovasz_softmax(probs, lab, ignore=0, workspace=ws)
+            loss.backward()
+        with ops.profile("") as prof:
+            med, mn = timeit(lov, flush=flush)
+            kern = {n: round(1e3 * v[0] / v[1], 1) for n, v in prof.all().items()}
+        by = (8 + 4 * C) * B * HW   # labels read + dense gradient written
+        res["lovasz_fwd_bwd"] = dict(ms=med, ms_min=mn, GBs=by / med / 1e6, scans_s=B / med * 1e3,
+                                     valid=ops.lovasz_info(ws)[0], kernels_us=kern)
     print(json.dumps(dict(batch=B, shape=args.shape, results=res), indent=1))
 
 
