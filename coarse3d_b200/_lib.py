@@ -54,6 +54,9 @@ def _load():
         "c3d_proto_loss_forward": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int,
                                            c_int, c_float, c_float, c_int, P, c_int, c_uint64, c_int, P,
                                            P, P]),
+        "c3d_proto_loss_forward_phase": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int,
+                                                 c_int, c_float, c_float, c_int, P, c_int, c_uint64, c_int,
+                                                 c_int, P, P, P]),
         "c3d_proto_loss_backward": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P,
                                             c_int, P]),
         "c3d_zero_fill": (c_int, [P, c_size_t, P]),

@@ -28,7 +28,9 @@
 //   2  TMA: each CTA keeps an 8 KB zero page in shared memory and ONE thread issues
 //      cp.async.bulk shared->global copies of it (UBLKCP) over the CTA's share of the buffer.
 //      The copy engine streams the page to L2 without LSU wavefronts or issue slots, so the
-//      vote keeps the LSU and the ALU while the fill keeps HBM busy.
+//      vote keeps the LSU and the ALU while the fill keeps HBM busy (117 us).
+//   3  (default) the same with an L2 evict-first policy on the copies, so the zero lines do
+//      not displace the range / class images the vote gathers from (113 us; step -2 %).
 #include <math_constants.h>
 #include <stdlib.h>
 
@@ -316,18 +318,22 @@ static int launch_knn_sk(const float* proj_range, const void* proj_argmax, const
     unsigned long long per_cta = (n4 + grid - 1) / grid;
     per_cta = (per_cta + 511) / 512 * 512;  // whole 8 KB pages (and 4 KB CTA-wide store rounds)
     const char* env = getenv("C3D_KNN_COFILL_MODE");
-    const int mode = (env && env[0] >= '1' && env[0] <= '3') ? env[0] - '0' : 2;
+    const int mode = (env && env[0] >= '1' && env[0] <= '3') ? env[0] - '0' : 3;
+    // C3D_KNN_FILL_CTAS=4: pad the dynamic shared memory to 48 KB so that only 4 (not 5) CTAs
+    // are resident per SM, leaving registers for the small kernels of the other chains.
+    const char* env4 = getenv("C3D_KNN_FILL_CTAS");
+    const size_t smem_fill = (env4 && env4[0] == '4' && smem < 48 * 1024) ? 48 * 1024 : smem;
     KernelTimer timer("knn_vote_fill_kernel", stream);
     if (mode == 3)
-      knn_vote_kernel<S, KT, 3><<<grid, threads, smem, stream>>>(
+      knn_vote_kernel<S, KT, 3><<<grid, threads, smem_fill, stream>>>(
           proj_range, proj_argmax, unproj_range, px, py, offsets, batch, total, H, W, knn, cutoff,
           nclasses, inv_gauss, out, pxy64, lab64, vec_ok, reinterpret_cast<float4*>(cofill), n4, per_cta);
     else if (mode == 2)
-      knn_vote_kernel<S, KT, 2><<<grid, threads, smem, stream>>>(
+      knn_vote_kernel<S, KT, 2><<<grid, threads, smem_fill, stream>>>(
           proj_range, proj_argmax, unproj_range, px, py, offsets, batch, total, H, W, knn, cutoff,
           nclasses, inv_gauss, out, pxy64, lab64, vec_ok, reinterpret_cast<float4*>(cofill), n4, per_cta);
     else
-      knn_vote_kernel<S, KT, 1><<<grid, threads, smem, stream>>>(
+      knn_vote_kernel<S, KT, 1><<<grid, threads, smem_fill, stream>>>(
           proj_range, proj_argmax, unproj_range, px, py, offsets, batch, total, H, W, knn, cutoff,
           nclasses, inv_gauss, out, pxy64, lab64, vec_ok, reinterpret_cast<float4*>(cofill), n4, per_cta);
     return check_launch("knn_vote_fill_kernel");

@@ -888,11 +888,12 @@ extern "C" size_t c3d_proto_loss_workspace_bytes(int batch, int n_classes, int h
   return carve(nullptr, batch, n_classes, hw, dim, sub_protos, num_anchor).bytes;
 }
 
-extern "C" int c3d_proto_loss_forward(
+// phases: 1 = select (label split + anchor sampling), 2 = rows (loss and gradient rows).
+static int proto_loss_forward_impl(
     const float* feats, const float* probs, const int64_t* labels, const uint8_t* keep_mask,
     const float* proto_queue, int batch, int dim, int proj_h, int proj_w, int n_classes,
     int sub_protos, int ignore_label, float temperature, float base_temperature, int num_anchor,
-    const int64_t* keep, int keep_rows, uint64_t seed, int need_grad, void* workspace,
+    const int64_t* keep, int keep_rows, uint64_t seed, int need_grad, int phases, void* workspace,
     float* loss_out, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   const int B = batch, D = dim, C = n_classes, M = sub_protos;
@@ -914,8 +915,9 @@ extern "C" int c3d_proto_loss_forward(
   C3D_REQUIRE(rows_config(D, Kc, &tile_rows, &n_tiles, &smem) == 0,
               "bank does not fit shared memory tiling (D=%d, Kc=%d)", D, Kc);
 
-  C3D_CUDA(cudaMemsetAsync(w.info, 0, (size_t)(8 + B) * 4, stream));
   int rc;
+  if (phases & 1) {
+  C3D_CUDA(cudaMemsetAsync(w.info, 0, (size_t)(8 + B) * 4, stream));
   { KernelTimer kt__("split_count_scan_kernel", stream);
     split_count_scan_kernel<false><<<nblk, 256, 0, stream>>>(
         (const long long*)labels, keep_mask, HW, nbps, B, C, ignore_label, w.blk_cnt, w.seg_cnt, w.seg_start,
@@ -934,6 +936,8 @@ extern "C" int c3d_proto_loss_forward(
                                                   (const long long*)keep, keep_rows, seed, w.seg_nd,
                                                   w.row_base, w.seg_of_t, w.info); }
   if ((rc = check_launch("loss_sample_kernel"))) return rc;
+  }
+  if (!(phases & 2)) return C3D_OK;
 
   RowsParams p{};
   p.feats = feats; p.bank_n = w.bank_n; p.pix_list = w.pix_list; p.cls_list = w.cls_list;
@@ -964,6 +968,31 @@ extern "C" int c3d_proto_loss_forward(
   if (D <= 256) return launch_rows<true, 2>(p, smem, stream);
   if (D <= 512) return launch_rows<true, 4>(p, smem, stream);
   return launch_rows<true, 8>(p, smem, stream);
+}
+
+extern "C" int c3d_proto_loss_forward(
+    const float* feats, const float* probs, const int64_t* labels, const uint8_t* keep_mask,
+    const float* proto_queue, int batch, int dim, int proj_h, int proj_w, int n_classes,
+    int sub_protos, int ignore_label, float temperature, float base_temperature, int num_anchor,
+    const int64_t* keep, int keep_rows, uint64_t seed, int need_grad, void* workspace,
+    float* loss_out, void* stream) {
+  return proto_loss_forward_impl(feats, probs, labels, keep_mask, proto_queue, batch, dim, proj_h, proj_w,
+                                 n_classes, sub_protos, ignore_label, temperature, base_temperature,
+                                 num_anchor, keep, keep_rows, seed, need_grad, 3, workspace, loss_out,
+                                 stream);
+}
+
+extern "C" int c3d_proto_loss_forward_phase(
+    const float* feats, const float* probs, const int64_t* labels, const uint8_t* keep_mask,
+    const float* proto_queue, int batch, int dim, int proj_h, int proj_w, int n_classes,
+    int sub_protos, int ignore_label, float temperature, float base_temperature, int num_anchor,
+    const int64_t* keep, int keep_rows, uint64_t seed, int need_grad, int phases, void* workspace,
+    float* loss_out, void* stream) {
+  C3D_REQUIRE(phases >= 1 && phases <= 3, "phases must be 1 (select), 2 (rows) or 3 (both)");
+  return proto_loss_forward_impl(feats, probs, labels, keep_mask, proto_queue, batch, dim, proj_h, proj_w,
+                                 n_classes, sub_protos, ignore_label, temperature, base_temperature,
+                                 num_anchor, keep, keep_rows, seed, need_grad, phases, workspace, loss_out,
+                                 stream);
 }
 
 extern "C" int c3d_proto_loss_backward(int batch, int dim, int proj_h, int proj_w, int n_classes,

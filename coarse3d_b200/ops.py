@@ -372,15 +372,16 @@ def proto_loss_rows(workspace, batch, dim, hw, n_classes, sub_protos, num_anchor
 
 
 def proto_loss_forward_raw(feats, probs, labels, keep_mask, queue, cfg, keep, seed, workspace, loss_out,
-                           need_grad=True):
-    """c3d_proto_loss_forward on pre-validated device tensors (no autograd, no allocation)."""
+                           need_grad=True, phases=3):
+    """c3d_proto_loss_forward on pre-validated device tensors (no autograd, no allocation).
+    phases: 1 = selection only, 2 = rows only (after a phase 1), 3 = both."""
     B, D, H, W = feats.shape
     C, M, _ = queue.shape
-    check(lib.c3d_proto_loss_forward(
+    check(lib.c3d_proto_loss_forward_phase(
         _p(feats), _p(probs), _p(labels), _p(keep_mask), _p(queue), B, D, H, W, C, M,
         int(cfg.ignore_label), float(cfg.temperature), float(cfg.base_temperature),
         int(cfg.num_anchor), _p(keep), 0 if keep is None else keep.shape[0], int(seed),
-        1 if need_grad else 0, _p(workspace), _p(loss_out), _stream()))
+        1 if need_grad else 0, int(phases), _p(workspace), _p(loss_out), _stream()))
     return loss_out
 
 

@@ -103,7 +103,8 @@ class HotPathStep:
                      torch.cuda.Stream(self.device, priority=hi),   # EMA chain
                      torch.cuda.Stream(self.device, priority=hi)]   # loss chain
         (self.ev_fork, self.ev_fill, self.ev_proj, self.ev_ema, self.ev_loss,
-         self.ev_resolved) = (torch.cuda.Event() for _ in range(6))
+         self.ev_resolved, self.ev_selected) = (torch.cuda.Event() for _ in range(7))
+        self.knn_after_select = _os.environ.get("C3D_KNN_AFTER_SELECT", "0") == "1"
         torch.cuda.synchronize(self.device)
 
     # bytes the reference dtypes move per step
@@ -145,12 +146,23 @@ class HotPathStep:
         P = self.parts
         pr = None
         sched = self.schedule
+        hold = fused and self.knn_after_select and "loss" in P
+        if hold:
+            # selection part of the loss first; its event releases the KNN + fill kernel
+            with torch.cuda.stream(st_loss):
+                self._loss_fwd(s, seed, phases=1)
+                self.ev_selected.record(st_loss)
         if fused:
             # The KNN vote (ALU bound) carries the zero fill (HBM bound): one kernel, both
             # pipes busy.  As two kernels they serialise: the fill's CTAs occupy every SM slot.
             with torch.cuda.stream(st_proj):
                 if "proj" in P:
                     pr = ops.project_batch(s.points, s.offsets, self.fov, H, W, buffers=b)
+                if hold:
+                    # The vote's 3750 CTAs keep every SM full until its grid is drained, and the
+                    # loss-rows kernel needs a whole SM (217 KB of shared memory): released
+                    # together, the high-priority rows CTAs are placed first.
+                    st_proj.wait_event(self.ev_selected)
                 self._knn(s, pr if pr is not None else self._last_proj(b), C, cofill=self.grad)
                 self.ev_proj.record(st_proj)
             st_fill.wait_event(self.ev_proj)
@@ -192,7 +204,7 @@ class HotPathStep:
             self.ev_ema.record(st_ema)
         with torch.cuda.stream(st_loss):
             if "loss" in P:
-                self._loss_fwd(s, seed)
+                self._loss_fwd(s, seed, phases=2 if hold else 3)
             st_loss.wait_event(self.ev_fill)
             if "loss" in P:
                 ops.proto_loss_backward_raw(s.feats.shape, self.cfg, C, self.M, self.loss_ws,
@@ -206,9 +218,9 @@ class HotPathStep:
         return ops.Projection(b.proj_pointcloud, b.proj_range, b.proj_idx, b.proj_mask,
                               b.uproj_x_idx, b.uproj_y_idx, b.uproj_depth, b.flags)
 
-    def _loss_fwd(self, s, seed):
+    def _loss_fwd(self, s, seed, phases=3):
         ops.proto_loss_forward_raw(s.feats, s.probs, s.labels, s.keep_mask, self.protos, self.cfg,
-                                   None, seed, self.loss_ws, self.loss)
+                                   None, seed, self.loss_ws, self.loss, phases=phases)
 
     def _ema(self, s, seed):
         distributed.prototype_update(

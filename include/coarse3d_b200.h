@@ -264,6 +264,16 @@ int c3d_proto_loss_forward(
     float* loss_out,              /* [1]                                         */
     void* stream);
 
+/* The same forward in two parts, so that a scheduler can place other work between them:
+ * phases = 1 runs the selection (label split, anchor sampling), 2 the loss / gradient rows
+ * (needs a preceding phase 1 on the same workspace), 3 both. */
+int c3d_proto_loss_forward_phase(
+    const float* feats, const float* probs, const int64_t* labels, const uint8_t* keep_mask,
+    const float* proto_queue, int batch, int dim, int proj_h, int proj_w, int n_classes,
+    int sub_protos, int ignore_label, float temperature, float base_temperature, int num_anchor,
+    const int64_t* keep, int keep_rows, uint64_t seed, int need_grad, int phases,
+    void* workspace, float* loss_out, void* stream);
+
 int c3d_proto_loss_backward(
     int batch, int dim, int proj_h, int proj_w, int n_classes, int sub_protos, int num_anchor,
     void* workspace,              /* as left by c3d_proto_loss_forward(need_grad=1) */

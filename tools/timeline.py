@@ -15,6 +15,7 @@ with ops.profile("") as prof:
     step.run(0); step.run(1)
     torch.cuda.synchronize()
     tl = prof.timeline()
-t0 = [r for r in tl if r[0] == "fill_zero_kernel"][1][1]
-for name, a, b in tl[len(tl) // 2:]:
+half = tl[len(tl) // 2:]          # second step
+t0 = min(a for _, a, _ in half)
+for name, a, b in half:
     print("%-28s %8.1f -> %8.1f  (%6.1f us)" % (name, a - t0, b - t0, b - a))
