@@ -319,10 +319,10 @@ static int launch_knn_sk(const float* proj_range, const void* proj_argmax, const
     per_cta = (per_cta + 511) / 512 * 512;  // whole 8 KB pages (and 4 KB CTA-wide store rounds)
     const char* env = getenv("C3D_KNN_COFILL_MODE");
     const int mode = (env && env[0] >= '1' && env[0] <= '3') ? env[0] - '0' : 3;
-    // C3D_KNN_FILL_CTAS=4: pad the dynamic shared memory to 48 KB so that only 4 (not 5) CTAs
+    // C3D_KNN_FILL_CTAS=4: pad the dynamic shared memory to 38 KB so that only 4 (not 5) CTAs
     // are resident per SM, leaving registers for the small kernels of the other chains.
     const char* env4 = getenv("C3D_KNN_FILL_CTAS");
-    const size_t smem_fill = (env4 && env4[0] == '4' && smem < 48 * 1024) ? 48 * 1024 : smem;
+    const size_t smem_fill = (env4 && env4[0] == '4' && smem < 38 * 1024) ? 38 * 1024 : smem;  // + 8.3 KB static
     KernelTimer timer("knn_vote_fill_kernel", stream);
     if (mode == 3)
       knn_vote_kernel<S, KT, 3><<<grid, threads, smem_fill, stream>>>(
