@@ -378,9 +378,18 @@ def run_e2e(args, step, dev, world, K):
     d_loss = [torch.zeros((), device=dev) for _ in range(NB)]
     d_knn = [torch.zeros((step.n_points,), dtype=torch.int64, device=dev) for _ in range(NB)]
 
+    use_classes = os.environ.get("C3D_E2E_API", "classes") == "classes"   # "pipeline": HotPathStep.run_inputs
+
     def compute(j):
-        """The user-level calls of one step on the device inputs of buffer j."""
+        """One step on the device inputs of buffer j."""
         di = d_in[j]
+        if not use_classes:
+            # the package's step pipeline: the same C-ABI calls, chains on streams
+            loss, lab, _ = step.run_inputs(di["points"], di["offsets"], di["weak"], step.proj_bufs[j], j)
+            d_loss[j].copy_(loss)
+            d_knn[j].copy_(lab)
+            return
+        # the reference-shaped classes called one after the other (drop-in form)
         # projection fused with label-image assembly: the weak labels travel per point
         pr = rp.doProjectionAssembleBatch(di["points"], di["offsets"], weak_label=di["weak"],
                                           buffers=step.proj_bufs[j])
@@ -423,25 +432,31 @@ def run_e2e(args, step, dev, world, K):
             torch.cuda.synchronize(dev)
             sys.stderr.write("e2e graph capture failed, running eager: %r\n" % (e,))
 
+    skip = set(os.environ.get("C3D_E2E_SKIP", "").split(","))   # diagnosis only: h2d,compute,d2h
+
     def one(i):
         h, j = host[i % len(host)], i % NB
         di, ho = d_in[j], h_out[j]
         s_in.wait_event(ev_done[j])          # buffer j free again (compute of step i-NB done)
         with torch.cuda.stream(s_in):
-            for k in ("points", "offsets", "weak"):
-                di[k].copy_(h[k], non_blocking=True)
+            if "h2d" not in skip:
+                for k in ("points", "offsets", "weak"):
+                    di[k].copy_(h[k], non_blocking=True)
             ev_in[j].record(s_in)
         main.wait_event(ev_in[j])
         main.wait_event(ev_out[j])           # outputs of step i-NB have left the device
-        if graphs is not None:
+        if "compute" in skip:
+            pass
+        elif graphs is not None:
             graphs[j].replay()
         else:
             compute(j)
         ev_done[j].record(main)
         s_out.wait_event(ev_done[j])
         with torch.cuda.stream(s_out):
-            ho["loss"].copy_(d_loss[j], non_blocking=True)
-            ho["knn"].copy_(d_knn[j], non_blocking=True)
+            if "d2h" not in skip:
+                ho["loss"].copy_(d_loss[j], non_blocking=True)
+                ho["knn"].copy_(d_knn[j], non_blocking=True)
             ev_out[j].record(s_out)
 
     for i in range(3):
@@ -464,8 +479,10 @@ def run_e2e(args, step, dev, world, K):
     return {"value": world * B * K / (float(ms.item()) * 1e-3), "unit": "scans/s",
             "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": K,
             "ms_per_step": float(ms.item()) / K,
-            "api": "RangeProjection.doProjectionAssembleBatch + ContrastMEMLoss()(..).backward() + "
-                   "PrototypeBank.update + KNN.forward_batch",
+            "api": ("RangeProjection.doProjectionAssembleBatch + ContrastMEMLoss()(..).backward() + "
+                    "PrototypeBank.update + KNN.forward_batch (classes called in sequence)") if use_classes
+                   else "coarse3d_b200.pipeline.HotPathStep.run_inputs: c3d_project_assemble_batch -> "
+                        "c3d_knn_batch(+fill) || c3d_proto_loss_forward/backward || c3d_proto_ema_* on streams",
             "host_inputs": "points, offsets, per-point weak labels int32 (pinned); "
                            "CNN activations resident on device as in the reference",
             "pipelining": "double-buffered: H2D / compute / D2H of consecutive steps on three streams",

@@ -432,6 +432,7 @@ class _ProtoLossFn(torch.autograd.Function):
         grad_out = grad_out.contiguous().float()
         if ctx.prefill is not None:
             grad, ev = ctx.prefill
+            ctx.prefill = None   # sole owner: autograd can adopt the 0.5 GB buffer instead of cloning it
             torch.cuda.current_stream(grad.device).wait_event(ev)
             proto_loss_backward_raw(ctx.shape, ctx.cfg, C, M, ctx.workspace, grad_out, grad,
                                     grad_is_zeroed=True)

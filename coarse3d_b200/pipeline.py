@@ -214,6 +214,47 @@ class HotPathStep:
             cur.wait_event(ev)
         return pr
 
+    def run_inputs(self, points, offsets, weak, bufs, set_index=0, seed=0):
+        """One step on externally supplied device inputs -- raw points (sum N, 4), CSR offsets and
+        per-point weak labels (int32), e.g. just copied from the host: the projection is the
+        fused f-1 call, whose weak-label image feeds the loss and the EMA (so those chains start
+        after the projection), then the same chains and schedule as `run`.  Returns
+        (loss 0-dim, per-point KNN labels int64, Assembled); both tensors are reused by the
+        next call."""
+        s = self.sets[set_index % len(self.sets)]
+        H, W, C = self.shape.proj_h, self.shape.proj_w, self.shape.n_classes
+        cur = torch.cuda.current_stream(self.device)
+        _, st_proj, st_ema, st_loss = self.side
+        self.ev_fork.record(cur)
+        for st in (st_proj, st_ema, st_loss):
+            st.wait_event(self.ev_fork)
+        with torch.cuda.stream(st_proj):
+            asm = ops.project_assemble_batch(points, offsets, self.fov, H, W, weak_label=weak, buffers=bufs)
+            self.ev_resolved.record(st_proj)
+            ops.knn_batch(asm.proj_range, s.argmax, asm.uproj_depth, asm.uproj_x_idx, asm.uproj_y_idx,
+                          offsets, self.knn_k, self.knn_s, self.knn_sigma, self.knn_cutoff, C,
+                          inv_gauss=self.inv_gauss, out=self.knn_out, cofill=self.grad)
+            self.ev_proj.record(st_proj)
+        labels = asm.train_label
+        with torch.cuda.stream(st_ema):
+            st_ema.wait_event(self.ev_resolved)
+            distributed.prototype_update(
+                s.feats, labels, self.protos, *self.ln_d, *self.ln_c, self.momentum,
+                assign_mode=ops.ASSIGN_GUMBEL_DEVICE, seed=seed, max_rows=self.max_rows, group=self.group,
+                workspace=self.ema_ws, packed=self.packed, out=self.protos_next)
+            self.ev_ema.record(st_ema)
+        with torch.cuda.stream(st_loss):
+            st_loss.wait_event(self.ev_resolved)
+            ops.proto_loss_forward_raw(s.feats, s.probs, labels, None, self.protos, self.cfg, None, seed,
+                                       self.loss_ws, self.loss)
+            st_loss.wait_event(self.ev_proj)          # the vote has zero-filled self.grad
+            ops.proto_loss_backward_raw(s.feats.shape, self.cfg, C, self.M, self.loss_ws, self.grad_out,
+                                        self.grad, grad_is_zeroed=True)
+            self.ev_loss.record(st_loss)
+        for ev in (self.ev_proj, self.ev_ema, self.ev_loss):
+            cur.wait_event(ev)
+        return self.loss, self.knn_out, asm
+
     def _last_proj(self, b):
         return ops.Projection(b.proj_pointcloud, b.proj_range, b.proj_idx, b.proj_mask,
                               b.uproj_x_idx, b.uproj_y_idx, b.uproj_depth, b.flags)
