@@ -351,16 +351,19 @@ def run_e2e(args, step, dev, world, K):
     crit = ContrastMEMLoss(ignore_label=0, temperature=0.07, num_anchor=512)
     bank = PrototypeBank(C, step.M, step.dim, proto_mom=0.999).to(dev)
     knn = KNN(dict(knn=5, search=5, sigma=1.0, cutoff=1.0), C)
+    # per-point labels travel as uint8 class ids (C <= 255), a quarter of the loaders' int32
+    label_np = np.int32 if os.environ.get("C3D_E2E_LABELS", "u8") == "i32" else np.uint8
+    label_t = torch.int32 if label_np is np.int32 else torch.uint8
     host = []
     for s in step.sets:
         host.append(dict(points=torch.from_numpy(s.host_points).pin_memory(),
                          offsets=torch.from_numpy(s.host_offsets).pin_memory(),
-                         weak=torch.from_numpy(s.host_weak.astype(np.int32)).pin_memory()))
+                         weak=torch.from_numpy(s.host_weak.astype(label_np)).pin_memory()))
     # double-buffered device inputs / pinned outputs: the H2D copies of step i+1 (copy-in
     # stream) and the D2H of step i-1 (copy-out stream) overlap the compute of step i
-    NB = 2
+    NB = min(int(os.environ.get("C3D_E2E_BUFFERS", "3")), len(step.sets))
     d_in = [dict(points=torch.empty_like(step.sets[0].points), offsets=torch.empty_like(step.sets[0].offsets),
-                 weak=torch.empty((step.n_points,), dtype=torch.int32, device=dev))
+                 weak=torch.empty((step.n_points,), dtype=label_t, device=dev))
             for _ in range(NB)]
     h_out = [dict(loss=torch.zeros((), dtype=torch.float32).pin_memory(),
                   knn=torch.zeros((step.n_points,), dtype=torch.int64).pin_memory()) for _ in range(NB)]
@@ -483,9 +486,9 @@ def run_e2e(args, step, dev, world, K):
                     "PrototypeBank.update + KNN.forward_batch (classes called in sequence)") if use_classes
                    else "coarse3d_b200.pipeline.HotPathStep.run_inputs: c3d_project_assemble_batch -> "
                         "c3d_knn_batch(+fill) || c3d_proto_loss_forward/backward || c3d_proto_ema_* on streams",
-            "host_inputs": "points, offsets, per-point weak labels int32 (pinned); "
+            "host_inputs": "points f32 (N,4), offsets, per-point weak labels %s (pinned); " % label_t +
                            "CNN activations resident on device as in the reference",
-            "pipelining": "double-buffered: H2D / compute / D2H of consecutive steps on three streams",
+            "pipelining": "%d-deep buffered: H2D / compute / D2H of consecutive steps on three streams" % NB,
             "compute_graph": graphs is not None}
 
 

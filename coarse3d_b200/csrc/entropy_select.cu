@@ -11,8 +11,8 @@
 // topk(w / q) (aten/native/Distributions.cpp).  Every pixel belongs to at most one class
 // (its arg-max), so it has ONE key w / q and the whole selection is:
 //   S1 select_prepare    per pixel: entropy, arg-max, key; per-(scan, class) counts
-//   S2 select_threshold  per (scan, class): the k-th largest key by a 3-pass radix
-//                        select (11 + 11 + 10 bits) over the scan's pixels
+//   S2 select_threshold  per (scan, class): the class's keys compacted into shared memory,
+//                        then the k-th largest by a 3-pass radix select (11 + 11 + 10 bits)
 //   S3 select_apply      per pixel: selected = key >= threshold; pseudo label, ground
 //                        truth kept where the weak mask is set (:512-516)
 // Noise: injected (`noise[b][c][pixel]`, the reference's per-iteration draws) for exact
@@ -154,6 +154,11 @@ __device__ __forceinline__ void find_bin_from_top(const int* s_hist, int k, int*
   __syncthreads();
 }
 
+// One CTA per (scan, class).  The class's keys are first compacted into shared memory
+// (one vectorised pass over the scan's arg-max bytes; a class holds ~HW/C of the pixels), and
+// the three radix passes then run from shared memory.  A class with more candidates than the
+// buffer holds (kSelSmemKeys) falls back to re-reading global memory in every pass.
+constexpr int kSelSmemKeys = 9984;    // 39 KB of keys + 8 KB histogram < 48 KB: 4 CTAs per SM
 __global__ void __launch_bounds__(512)
 select_threshold_kernel(const uint8_t* __restrict__ pseudo, const float* __restrict__ key,
                         const int32_t* __restrict__ count, const int32_t* __restrict__ present,
@@ -162,6 +167,8 @@ select_threshold_kernel(const uint8_t* __restrict__ pseudo, const float* __restr
   __shared__ int s_hist[2048];
   __shared__ int s_scan[16];
   __shared__ int s_out[2];
+  __shared__ int s_n;
+  extern __shared__ uint32_t s_keys[];
   const int b = blockIdx.x / C, c = blockIdx.x % C;
   const int cnt = count[blockIdx.x];
   // select_num = int(cls_mask.sum() * select_ratio): int64 0-dim tensor times a Python
@@ -173,6 +180,35 @@ select_threshold_kernel(const uint8_t* __restrict__ pseudo, const float* __restr
   }
   const uint8_t* ps = pseudo + (size_t)b * HW;
   const uint32_t* kb = reinterpret_cast<const uint32_t*>(key) + (size_t)b * HW;
+  const bool in_smem = cnt <= kSelSmemKeys;
+  if (in_smem) {
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    // 16 arg-max bytes per load (HW % 16 == 0 and a 16 B aligned scan base, else bytewise)
+    const bool vec = (HW % 16 == 0) && ((reinterpret_cast<uintptr_t>(ps) & 15) == 0);
+    if (vec) {
+      const uint4* ps4 = reinterpret_cast<const uint4*>(ps);
+      const uint32_t pat = 0x01010101u * (uint32_t)c;
+      for (int i = threadIdx.x; i < HW / 16; i += blockDim.x) {
+        const uint4 v = __ldg(ps4 + i);
+        const uint32_t w[4] = {v.x ^ pat, v.y ^ pat, v.z ^ pat, v.w ^ pat};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          // any zero byte in w[q]?  (exact test)
+          if (((w[q] - 0x01010101u) & ~w[q] & 0x80808080u) != 0u) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (((w[q] >> (8 * e)) & 0xFFu) == 0u) s_keys[atomicAdd(&s_n, 1)] = kb[i * 16 + q * 4 + e];
+          }
+        }
+      }
+    } else {
+      for (int i = threadIdx.x; i < HW; i += blockDim.x)
+        if (ps[i] == (uint8_t)c) s_keys[atomicAdd(&s_n, 1)] = kb[i];
+    }
+    __syncthreads();
+  }
+  const int n_keys = in_smem ? s_n : HW;
   int k = k0;
   uint32_t prefix = 0, prefix_mask = 0;
   // keys are positive floats: their bit patterns order like unsigned integers
@@ -183,10 +219,17 @@ select_threshold_kernel(const uint8_t* __restrict__ pseudo, const float* __restr
     __syncthreads();
     const int sh = shifts[pass];
     const uint32_t bmask = nbins[pass] - 1;
-    for (int i = threadIdx.x; i < HW; i += blockDim.x) {
-      if (ps[i] == (uint8_t)c) {
-        const uint32_t v = kb[i];
+    if (in_smem) {
+      for (int i = threadIdx.x; i < n_keys; i += blockDim.x) {
+        const uint32_t v = s_keys[i];
         if ((v & prefix_mask) == prefix) atomicAdd(&s_hist[(v >> sh) & bmask], 1);
+      }
+    } else {
+      for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+        if (ps[i] == (uint8_t)c) {
+          const uint32_t v = kb[i];
+          if ((v & prefix_mask) == prefix) atomicAdd(&s_hist[(v >> sh) & bmask], 1);
+        }
       }
     }
     __syncthreads();
@@ -259,8 +302,9 @@ extern "C" int c3d_entropy_select_batch(
   if ((rc = check_launch("select_prepare_kernel"))) return rc;
   {
     KernelTimer kt__("select_threshold_kernel", stream);
-    select_threshold_kernel<<<B * C, 512, 0, stream>>>(w.pseudo, w.key, w.count, w.present, HW, C,
-                                                       ignore_cls, select_ratio, w.thr);
+    const size_t smem = (size_t)kSelSmemKeys * sizeof(uint32_t);   // 39 KB: no opt-in needed
+    select_threshold_kernel<<<B * C, 512, smem, stream>>>(w.pseudo, w.key, w.count, w.present, HW, C,
+                                                          ignore_cls, select_ratio, w.thr);
   }
   if ((rc = check_launch("select_threshold_kernel"))) return rc;
   {

@@ -171,7 +171,8 @@ resolve_pixels_kernel(const float* __restrict__ points, int c_in,
 __global__ void __launch_bounds__(256)
 resolve_assemble_kernel(const float* __restrict__ points, const int32_t* __restrict__ offsets,
                         int HW, long long total_px, unsigned long long* __restrict__ zbuf,
-                        const int32_t* __restrict__ sem_label, const int32_t* __restrict__ weak_label,
+                        const void* __restrict__ sem_label, const void* __restrict__ weak_label,
+                        int label_is_u8,
                         const float* __restrict__ mean, const float* __restrict__ stdv,
                         float* __restrict__ proj_range, int32_t* __restrict__ proj_idx,
                         float* __restrict__ feature, long long* __restrict__ train_label,
@@ -192,8 +193,13 @@ resolve_assemble_kernel(const float* __restrict__ points, const int32_t* __restr
       const long long q = q0 + j * 256;
       const size_t row = (size_t)__ldg(offsets + (int)(q / HW)) + (uint32_t)key[j];
       pt[j] = __ldg(reinterpret_cast<const float4*>(points) + row);
-      if (sem_label) sl[j] = __ldg(sem_label + row);
-      if (weak_label) wl[j] = __ldg(weak_label + row);
+      if (label_is_u8) {
+        if (sem_label) sl[j] = __ldg(reinterpret_cast<const uint8_t*>(sem_label) + row);
+        if (weak_label) wl[j] = __ldg(reinterpret_cast<const uint8_t*>(weak_label) + row);
+      } else {
+        if (sem_label) sl[j] = __ldg(reinterpret_cast<const int32_t*>(sem_label) + row);
+        if (weak_label) wl[j] = __ldg(reinterpret_cast<const int32_t*>(weak_label) + row);
+      }
     }
   }
 #pragma unroll
@@ -313,7 +319,7 @@ extern "C" int c3d_project_batch(
 
 extern "C" int c3d_project_assemble_batch(
     const float* points, const int32_t* offsets, int batch, int64_t total_points,
-    const float* depth_override, const int32_t* sem_label, const int32_t* weak_label,
+    const float* depth_override, const void* sem_label, const void* weak_label, int label_is_u8,
     const float* img_mean, const float* img_std, double abs_fov_left, double fov_hori,
     double abs_fov_down, double fov_vert, int proj_h, int proj_w, float* feature,
     int64_t* train_label, int64_t* eval_label, float* proj_range, int32_t* proj_idx,
@@ -372,7 +378,7 @@ extern "C" int c3d_project_assemble_batch(
     int grid = (int)((total_px + 2 * threads - 1) / (2 * threads));
     KernelTimer kt__("resolve_assemble_kernel", stream);
     resolve_assemble_kernel<<<grid, threads, 0, stream>>>(
-        points, offsets, proj_h * proj_w, total_px, zbuf, sem_label, weak_label, img_mean, img_std,
+        points, offsets, proj_h * proj_w, total_px, zbuf, sem_label, weak_label, label_is_u8, img_mean, img_std,
         proj_range, proj_idx, feature, (long long*)train_label, (long long*)eval_label);
     return check_launch("resolve_assemble_kernel");
   }

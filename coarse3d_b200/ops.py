@@ -132,15 +132,21 @@ def project_assemble_batch(points, offsets, fov: Fov, proj_h, proj_w, sem_label=
     """Projection fused with its caller (loader :124-172, trainer :600-608): label images
     and the 5-channel network input straight from the z-buffer winners.
 
-    points (sum N, 4) f32; sem_label / weak_label (sum N,) int32; img_mean / img_std (5,) f32.
+    points (sum N, 4) f32; sem_label / weak_label (sum N,) int32 (the loaders' dtype) or uint8
+    (both the same); img_mean / img_std (5,) f32.
     """
     _need_cuda(points=points, offsets=offsets, depth=depth, sem_label=sem_label,
                weak_label=weak_label, img_mean=img_mean, img_std=img_std)
     if points.dtype != torch.float32 or points.dim() != 2 or points.shape[1] != 4:
         raise ValueError("points must be (N, 4) float32")
+    ldt = None
     for name, t in (("sem_label", sem_label), ("weak_label", weak_label)):
-        if t is not None and (t.dtype != torch.int32 or t.numel() != points.shape[0]):
-            raise ValueError("%s must be (N,) int32" % name)
+        if t is None:
+            continue
+        if t.dtype not in (torch.int32, torch.uint8) or t.numel() != points.shape[0] or \
+                (ldt is not None and t.dtype != ldt):
+            raise ValueError("%s must be (N,) int32 or uint8 (both labels the same dtype)" % name)
+        ldt = t.dtype
     batch, total = offsets.numel() - 1, points.shape[0]
     b = buffers
     if b is None:
@@ -151,7 +157,7 @@ def project_assemble_batch(points, offsets, fov: Fov, proj_h, proj_w, sem_label=
     evall = torch.empty((batch, proj_h, proj_w), dtype=torch.int64, device=dev) if sem_label is not None else None
     check(lib.c3d_project_assemble_batch(
         _p(points), _p(offsets), batch, total, _p(depth), _p(sem_label), _p(weak_label),
-        _p(img_mean), _p(img_std), fov.abs_fov_left, fov.fov_hori, fov.abs_fov_down, fov.fov_vert,
+        1 if ldt == torch.uint8 else 0, _p(img_mean), _p(img_std), fov.abs_fov_left, fov.fov_hori, fov.abs_fov_down, fov.fov_vert,
         proj_h, proj_w, _p(feature), _p(train), _p(evall), _p(b.proj_range), _p(b.proj_idx),
         _p(b.uproj_x_idx), _p(b.uproj_y_idx), _p(b.uproj_depth), _p(b.workspace),
         1 if b.clean else 0, _p(b.flags), _stream()))

@@ -104,8 +104,10 @@ int c3d_project_batch(
 int c3d_project_assemble_batch(
     const float* points, const int32_t* offsets, int batch, int64_t total_points,
     const float* depth_override,
-    const int32_t* sem_label,     /* [total_points] full labels (mapped to [0, C))        */
-    const int32_t* weak_label,    /* [total_points] weak labels, 0 = unlabelled            */
+    const void* sem_label,        /* [total_points] full labels (mapped to [0, C))        */
+    const void* weak_label,       /* [total_points] weak labels, 0 = unlabelled            */
+    int label_is_u8,              /* 0: labels are int32 (the loaders' dtype); 1: uint8 --
+                                     a quarter of the host->device bytes                   */
     const float* img_mean, const float* img_std,   /* [5] each (config sensor.img_mean)   */
     double abs_fov_left, double fov_hori, double abs_fov_down, double fov_vert,
     int proj_h, int proj_w,

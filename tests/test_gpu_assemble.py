@@ -38,8 +38,9 @@ def test_matches_reference_golden(cuda_device, case):
     assert np.array_equal(_bits(out.feature[0].cpu().numpy()), _bits(g["feature"]))
 
 
+@pytest.mark.parametrize("ldt", [np.int32, np.uint8])
 @pytest.mark.parametrize("normalise", [False, True])
-def test_batched_matches_oracle(cuda_device, normalise):
+def test_batched_matches_oracle(cuda_device, normalise, ldt):
     from coarse3d_b200 import ops, synth
     shp, B = synth.KITTI, 3
     pts, offs, full, weak = synth.make_batch(shp, B, seed0=700, ragged=True)
@@ -51,8 +52,8 @@ def test_batched_matches_oracle(cuda_device, normalise):
     for rep in range(2):  # second call runs on the z-buffer the first one left clean
         out = ops.project_assemble_batch(
             torch.from_numpy(pts).cuda(), torch.from_numpy(offs).cuda(), fov, shp.proj_h, shp.proj_w,
-            sem_label=torch.from_numpy(full.astype(np.int32)).cuda(),
-            weak_label=torch.from_numpy(weak.astype(np.int32)).cuda(),
+            sem_label=torch.from_numpy(full.astype(ldt)).cuda(),
+            weak_label=torch.from_numpy(weak.astype(ldt)).cuda(),
             img_mean=torch.from_numpy(mean).cuda() if normalise else None,
             img_std=torch.from_numpy(std).cuda() if normalise else None, buffers=bufs)
         ofov = oproj.Fov(fov_up=shp.fov_up, fov_down=shp.fov_down, proj_h=shp.proj_h, proj_w=shp.proj_w)

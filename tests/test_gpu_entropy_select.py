@@ -62,7 +62,8 @@ def _make(B, C, H, W, seed, weak=0.01, sharp=2.0):
 
 @pytest.mark.parametrize("B,C,H,W,ratio,ign", [(3, 20, 64, 2048, 0.5, 0), (2, 17, 32, 1024, 0.1, 0),
                                                 (4, 14, 40, 1800, 0.93, 0), (1, 5, 7, 33, 0.5, 0),
-                                                (2, 20, 16, 512, 1.0, 0), (2, 8, 16, 256, 0.001, 0)])
+                                                (2, 20, 16, 512, 1.0, 0), (2, 8, 16, 256, 0.001, 0),
+                                                (2, 3, 64, 2048, 0.4, 0)])     # > 9984 keys per class: global path
 def test_matches_oracle(cuda_device, B, C, H, W, ratio, ign):
     from coarse3d_b200 import ops
     output, wss, ev, tl, noise = _make(B, C, H, W, 500 + B * C)
