@@ -115,6 +115,8 @@ loss_sample_kernel(const int32_t* __restrict__ seg_cnt, const int32_t* __restric
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int kCdfSmem = 2048;
   __shared__ float s_cdf[kCdfSmem];
+  __shared__ int s_hit[kCdfSmem];   // multiplicities of a small segment (512 draws land on a
+                                    // handful of slots: shared, not same-address global atomics)
   __shared__ float s_warp[8];
   __shared__ float s_carry;
   __shared__ int s_iw[8];
@@ -141,8 +143,9 @@ loss_sample_kernel(const int32_t* __restrict__ seg_cnt, const int32_t* __restric
       // inclusive scan of the weights -> CDF, 256 elements per step; small segments
       // (the weak-label regime) keep the CDF in shared memory for the binary searches
       float* cdf = w_list + start;
-      if (n <= kCdfSmem) {
-        for (int i = threadIdx.x; i < n; i += 256) s_cdf[i] = w_list[start + i];
+      const bool small = n <= kCdfSmem;
+      if (small) {
+        for (int i = threadIdx.x; i < n; i += 256) { s_cdf[i] = w_list[start + i]; s_hit[i] = 0; }
         cdf = s_cdf;
       }
       if (threadIdx.x == 0) s_carry = 0.f;
@@ -175,7 +178,11 @@ loss_sample_kernel(const int32_t* __restrict__ seg_cnt, const int32_t* __restric
           const int mid = (lo + hi) >> 1;
           if (cdf[mid] > x) hi = mid; else lo = mid + 1;
         }
-        atomicAdd(&cnt_list[start + lo], 1);
+        if (small) atomicAdd(&s_hit[lo], 1); else atomicAdd(&cnt_list[start + lo], 1);
+      }
+      if (small) {   // cnt_list was zeroed by split_scatter
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += 256) cnt_list[start + i] = s_hit[i];
       }
     }
     // ---- compact the distinct sampled slots of this segment, in slot order,
