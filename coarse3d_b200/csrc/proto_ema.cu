@@ -289,6 +289,38 @@ ema_sinkhorn_kernel(const int32_t* __restrict__ seg_cnt, const int32_t* __restri
   }
 
   // Q *= B; argmax; assignment (sinkhorn.py:26-31)
+  if (fits && 2 * ne + n <= kSinkSmemFloats) {
+    // element-parallel noise (Philox + two logs per element is the expensive part; one thread
+    // per ROW left all but n threads idle), then one thread per row takes the two arg-maxes
+    float* Y = s_dyn + ne + n;
+    for (int e = threadIdx.x; e < ne; e += blockDim.x) {
+      const float q = Q[e] * fn;
+      Q[e] = q;
+      float g = 0.f;
+      const unsigned long long ctr = (unsigned long long)start * M + e;   // slot * M + m
+      if (mode == 1) g = gumbel[ctr];
+      else if (mode == 2) {
+        const uint4 r = philox_e(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), 1u, 0u),
+                                 make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+        const float u = ((float)(r.x >> 8) + 0.5f) * (1.0f / 16777216.0f);
+        g = -logf(-logf(u));
+      }
+      Y[e] = (q + g) / 0.5f;  // F.gumbel_softmax(tau=0.5); softmax is monotone
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const int slot = start + i;
+      float best = -CUDART_INF_F, bestg = -CUDART_INF_F; int idx = 0, hard = 0;
+      for (int m = 0; m < M; ++m) {
+        const float q = Q[(size_t)i * M + m], y = Y[(size_t)i * M + m];
+        if (q > best) { best = q; idx = m; }
+        if (y > bestg) { bestg = y; hard = m; }
+      }
+      sub[slot] = (mode == 0) ? idx : hard;
+      if (proto_target) proto_target[pix_list[slot]] = (float)idx + (float)(M * c);  // :390-392
+    }
+    return;
+  }
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const int slot = start + i;
     float best = -CUDART_INF_F, bestg = -CUDART_INF_F; int idx = 0, hard = 0;
