@@ -219,30 +219,32 @@ __device__ __forceinline__ uint4 philox_e(uint4 ctr, uint2 key) {
 // mode: 0 = one_hot(argmax) (sinkhorn.py:30), 1 = injected Gumbel noise, 2 = device noise
 constexpr int kSinkSmemFloats = 24 * 1024;  // 96 KB of dynamic shared memory
 
+constexpr int kSinkWarps = 32;  // 1024 threads per class: the kernel is a chain of short
+                                // element-parallel passes separated by barriers (latency bound)
 __device__ __forceinline__ void sink_row_sums(const float* Q, int n, int M, float* s_part, float* s_R) {
-  // s_R[m] = sum_i Q[i*M + m]; thread (p = warp, m = lane) sums rows p, p+8, ...
+  // s_R[m] = sum_i Q[i*M + m]; thread (p = warp, m = lane) sums rows p, p+kSinkWarps, ...
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float a = 0.f;
-  if (lane < M) for (int i = warp; i < n; i += 8) a += Q[(size_t)i * M + lane];
+  if (lane < M) for (int i = warp; i < n; i += kSinkWarps) a += Q[(size_t)i * M + lane];
   s_part[warp * 32 + lane] = a;
   __syncthreads();
   if ((int)threadIdx.x < M) {
     float t = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) t += s_part[w * 32 + threadIdx.x];
+    for (int w = 0; w < kSinkWarps; ++w) t += s_part[w * 32 + threadIdx.x];
     s_R[threadIdx.x] = t;
   }
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kSinkWarps * 32)
 ema_sinkhorn_kernel(const int32_t* __restrict__ seg_cnt, const int32_t* __restrict__ seg_start,
                     const int32_t* __restrict__ pix_list, int32_t* __restrict__ info, int B, int M,
                     int ignore_label, int max_rows, float* __restrict__ simq,
                     int32_t* __restrict__ sub, const float* __restrict__ gumbel, int mode,
                     unsigned long long seed, float* __restrict__ proto_target) {
   extern __shared__ float s_dyn[];
-  __shared__ float s_part[8 * 32];
+  __shared__ float s_part[kSinkWarps * 32];
   __shared__ float s_R[32];
   __shared__ float s_tot;
   const int c = blockIdx.x;
@@ -499,7 +501,7 @@ extern "C" int c3d_proto_ema_accumulate(
   if ((rc = check_launch("ema_rows_kernel"))) return rc;
   C3D_CUDA(cudaFuncSetAttribute(ema_sinkhorn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 kSinkSmemFloats * 4));
-  { KernelTimer kt__("ema_sinkhorn_kernel", stream); ema_sinkhorn_kernel<<<C, 256, kSinkSmemFloats * 4, stream>>>(w.seg_cnt, w.seg_start, w.pix_list, w.info, B, M,
+  { KernelTimer kt__("ema_sinkhorn_kernel", stream); ema_sinkhorn_kernel<<<C, kSinkWarps * 32, kSinkSmemFloats * 4, stream>>>(w.seg_cnt, w.seg_start, w.pix_list, w.info, B, M,
                                              ignore_label, (int)max_rows, w.simq, w.sub, gumbel,
                                              assign_mode, seed, proto_target); }
   if ((rc = check_launch("ema_sinkhorn_kernel"))) return rc;
