@@ -41,7 +41,7 @@ __device__ __forceinline__ int masked_class(const long long* __restrict__ labels
 // class, and the last scan's CTA turns the B*C totals into the segment table.
 // `info` is [8 + B] ints: info[8 + b] is scan b's ticket counter (zeroed by the caller).
 template <bool kClassMajor>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 8)
 split_count_scan_kernel(const long long* __restrict__ labels, const uint8_t* __restrict__ keep,
                         int HW, int nbps, int B, int C, int ignore_label,
                         int32_t* __restrict__ blk_cnt, int32_t* __restrict__ seg_cnt,
@@ -75,6 +75,43 @@ split_count_scan_kernel(const long long* __restrict__ labels, const uint8_t* __r
   __syncthreads();
   if (!s_flag) return;
   __threadfence();
+  // All tile counts of up to four of this warp's classes are loaded before any is scanned:
+  // one global round trip instead of one per (class, 32-tile chunk) -- this tail is latency.
+  const int nch = (nbps + 31) >> 5;
+  if (nch <= 4) {
+    for (int c0 = warp; c0 < C; c0 += 32) {
+      int v[4][4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int c = c0 + 8 * k;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int i = q * 32 + lane;
+          v[k][q] = (c < C && i < nbps) ? __ldcg(blk_cnt + ((size_t)(b * nbps + i)) * C + c) : 0;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int c = c0 + 8 * k;
+        if (c >= C) break;
+        int carry = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (q >= nch) break;
+          const int i = q * 32 + lane;
+          int incl = v[k][q];
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+          }
+          if (i < nbps) blk_cnt[((size_t)(b * nbps + i)) * C + c] = carry + incl - v[k][q];
+          carry += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (lane == 0) seg_cnt[seg_index<kClassMajor>(b, c, B, C)] = carry;
+      }
+    }
+  } else {
   for (int c = warp; c < C; c += 8) {
     int carry = 0;
     for (int base = 0; base < nbps; base += 32) {
@@ -92,6 +129,7 @@ split_count_scan_kernel(const long long* __restrict__ labels, const uint8_t* __r
     }
     if (lane == 0) seg_cnt[seg_index<kClassMajor>(b, c, B, C)] = carry;
   }
+  }
   // ---- last scan: segment table over the B*C totals
   __threadfence();
   __syncthreads();
@@ -102,23 +140,34 @@ split_count_scan_kernel(const long long* __restrict__ labels, const uint8_t* __r
   if (warp == 0) {
     int carry = 0, tcarry = 0;
     const int n = B * C;
-    for (int base = 0; base < n; base += 32) {
-      const int i = base + lane;
-      const int v = (i < n) ? __ldcg(seg_cnt + i) : 0;
-      const int ne = v > 0;
-      int incl = v, tincl = ne;
+    for (int base0 = 0; base0 < n; base0 += 32 * 8) {   // eight chunks' loads in flight
+      int vv[8];
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        int t = __shfl_up_sync(0xffffffffu, incl, o);
-        int u = __shfl_up_sync(0xffffffffu, tincl, o);
-        if (lane >= o) { incl += t; tincl += u; }
+      for (int q = 0; q < 8; ++q) {
+        const int i = base0 + q * 32 + lane;
+        vv[q] = (i < n) ? __ldcg(seg_cnt + i) : 0;
       }
-      if (i < n) {
-        seg_start[i] = carry + incl - v;
-        seg_tidx[i] = ne ? (tcarry + tincl - 1) : -1;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int base = base0 + q * 32;
+        if (base >= n) break;
+        const int i = base + lane;
+        const int v = vv[q];
+        const int ne = v > 0;
+        int incl = v, tincl = ne;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          int t = __shfl_up_sync(0xffffffffu, incl, o);
+          int u = __shfl_up_sync(0xffffffffu, tincl, o);
+          if (lane >= o) { incl += t; tincl += u; }
+        }
+        if (i < n) {
+          seg_start[i] = carry + incl - v;
+          seg_tidx[i] = ne ? (tcarry + tincl - 1) : -1;
+        }
+        carry += __shfl_sync(0xffffffffu, incl, 31);
+        tcarry += __shfl_sync(0xffffffffu, tincl, 31);
       }
-      carry += __shfl_sync(0xffffffffu, incl, 31);
-      tcarry += __shfl_sync(0xffffffffu, tincl, 31);
     }
     if (lane == 0) {
       info[kInfoT] = tcarry;
