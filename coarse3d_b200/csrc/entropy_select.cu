@@ -61,6 +61,9 @@ __device__ __forceinline__ uint4 philox_s(uint4 ctr, uint2 key) {
 }
 
 // ---------------------------------------------------------------- S1 -------
+// kPx pixels per thread (adjacent, one 64-bit load per class when kPx == 2): twice the bytes
+// in flight per thread and half the address arithmetic of the one-pixel form.
+template <int kPx>
 __global__ void __launch_bounds__(256)
 select_prepare_kernel(const float* __restrict__ probs, const long long* __restrict__ train_label,
                       const uint8_t* __restrict__ eval_mask, int HW, int C, int ignore_cls,
@@ -72,44 +75,65 @@ select_prepare_kernel(const float* __restrict__ probs, const long long* __restri
   const int b = blockIdx.y;
   if (threadIdx.x < C) { s_cnt[threadIdx.x] = 0; s_pre[threadIdx.x] = 0; }
   __syncthreads();
-  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
-  if (pix < HW) {
-    const float* p = probs + (size_t)b * C * HW + pix;
-    float ent = 0.f, best = -CUDART_INF_F;
-    int arg = 0;
-    for (int c0 = 0; c0 < C; c0 += 8) {  // 8 coalesced loads in flight
-      float v[8];
+  const int pix0 = (blockIdx.x * blockDim.x + threadIdx.x) * kPx;
+  if (pix0 < HW) {
+    const float* p = probs + (size_t)b * C * HW + pix0;
+    float ent[kPx], best[kPx];
+    int arg[kPx];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = (c0 + j < C) ? __ldg(p + (size_t)(c0 + j) * HW) : 0.f;
+    for (int e = 0; e < kPx; ++e) { ent[e] = 0.f; best[e] = -CUDART_INF_F; arg[e] = 0; }
+    for (int c0 = 0; c0 < C; c0 += 8) {  // 8 coalesced loads in flight
+      float v[8][kPx];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         if (c0 + j < C) {
-          ent += v[j] * logf(v[j] + 1e-10f);                // trainer.py:459-461
-          if (v[j] > best) { best = v[j]; arg = c0 + j; }   // torch.max: first maximum (:463)
+          if (kPx == 2) {
+            const float2 t = __ldg(reinterpret_cast<const float2*>(p + (size_t)(c0 + j) * HW));
+            v[j][0] = t.x; v[j][kPx - 1] = t.y;
+          } else {
+            v[j][0] = __ldg(p + (size_t)(c0 + j) * HW);
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < kPx; ++e) v[j][e] = 0.f;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (c0 + j < C) {
+#pragma unroll
+          for (int e = 0; e < kPx; ++e) {
+            ent[e] += v[j][e] * logf(v[j][e] + 1e-10f);                  // trainer.py:459-461
+            if (v[j][e] > best[e]) { best[e] = v[j][e]; arg[e] = c0 + j; }  // torch.max: first maximum (:463)
+          }
         }
       }
     }
-    const float w = expf(-1.0f * (-ent));                    // :466
-    const size_t gi = (size_t)b * HW + pix;
-    const bool ev = eval_mask[gi] != 0;
-    const bool cand = ev && arg != ignore_cls;               // :469, :477-480
-    float k = 0.f;
-    if (cand) {
-      float q;
-      if (noise) q = noise[((size_t)b * C + arg) * HW + pix];
-      else {
-        const unsigned long long ctr = gi;
-        const uint4 r = philox_s(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), 2u, 0u),
-                                 make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
-        q = -logf(((float)(r.x >> 8) + 0.5f) * (1.0f / 16777216.0f));  // Exp(1)
+#pragma unroll
+    for (int e = 0; e < kPx; ++e) {
+      const int pix = pix0 + e;
+      const float w = expf(-1.0f * (-ent[e]));                   // :466
+      const size_t gi = (size_t)b * HW + pix;
+      const bool ev = eval_mask[gi] != 0;
+      const bool cand = ev && arg[e] != ignore_cls;              // :469, :477-480
+      float k = 0.f;
+      if (cand) {
+        float q;
+        if (noise) q = noise[((size_t)b * C + arg[e]) * HW + pix];
+        else {
+          const unsigned long long ctr = gi;
+          const uint4 r = philox_s(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), 2u, 0u),
+                                   make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+          q = -logf(((float)(r.x >> 8) + 0.5f) * (1.0f / 16777216.0f));  // Exp(1)
+        }
+        k = w / q;                                               // multinomial: topk(w / q)
+        atomicAdd(&s_cnt[arg[e]], 1);
       }
-      k = w / q;                                             // multinomial: topk(w / q)
-      atomicAdd(&s_cnt[arg], 1);
+      pseudo[gi] = cand ? (uint8_t)arg[e] : (uint8_t)255;
+      key[gi] = k;
+      const long long tl = train_label[gi];
+      if (tl >= 0 && tl < C) s_pre[(int)tl] = 1;                 // unique(train_label[b]) (:474)
     }
-    pseudo[gi] = cand ? (uint8_t)arg : (uint8_t)255;
-    key[gi] = k;
-    const long long tl = train_label[gi];
-    if (tl >= 0 && tl < C) s_pre[(int)tl] = 1;               // unique(train_label[b]) (:474)
   }
   __syncthreads();
   if (threadIdx.x < C) {
@@ -293,11 +317,18 @@ extern "C" int c3d_entropy_select_batch(
   C3D_CUDA(cudaMemsetAsync(w.count, 0, (size_t)((char*)w.thr - (char*)w.count), stream));  // count + present
   int rc;
   {
-    dim3 grid((HW + 255) / 256, B);
     KernelTimer kt__("select_prepare_kernel", stream);
-    select_prepare_kernel<<<grid, 256, 0, stream>>>(probs, (const long long*)train_label, eval_mask,
-                                                    HW, C, ignore_cls, noise, seed, w.pseudo, w.key,
-                                                    w.count, w.present);
+    if (HW % 2 == 0 && (reinterpret_cast<uintptr_t>(probs) & 7) == 0) {
+      dim3 grid((HW / 2 + 255) / 256, B);
+      select_prepare_kernel<2><<<grid, 256, 0, stream>>>(probs, (const long long*)train_label, eval_mask,
+                                                         HW, C, ignore_cls, noise, seed, w.pseudo, w.key,
+                                                         w.count, w.present);
+    } else {
+      dim3 grid((HW + 255) / 256, B);
+      select_prepare_kernel<1><<<grid, 256, 0, stream>>>(probs, (const long long*)train_label, eval_mask,
+                                                         HW, C, ignore_cls, noise, seed, w.pseudo, w.key,
+                                                         w.count, w.present);
+    }
   }
   if ((rc = check_launch("select_prepare_kernel"))) return rc;
   {
