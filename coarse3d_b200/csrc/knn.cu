@@ -66,7 +66,7 @@ knn_vote_kernel(const float* __restrict__ proj_range, const void* __restrict__ p
                 int total, int H, int W, int knn, float cutoff, int nclasses,
                 const float* __restrict__ inv_gauss, void* __restrict__ out, int pxy64, int lab64,
                 int vec_ok, float4* __restrict__ cofill, unsigned long long cofill_n4,
-                unsigned long long cofill_per_cta) {
+                unsigned long long cofill_per_cta, int fill_early) {
   constexpr int S2 = S * S;
   constexpr int PAD = (S - 1) / 2;
   extern __shared__ int32_t s_off[];
@@ -152,7 +152,7 @@ knn_vote_kernel(const float* __restrict__ proj_range, const void* __restrict__ p
         if (rowok && xq >= 0 && xq < W) v = __ldg(reinterpret_cast<const float4*>(rowp + 4 * q));
         w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
       }
-      fill_part(dy, S);
+      if (fill_early == 1) { if (dy == 0) fill_part(0, 1); } else fill_part(dy, fill_early == 2 ? S + 3 : S);
 #pragma unroll
       for (int i = NQ * 4; i < NQ * 4 + 4; ++i) w[i] = 0.f;
       // v[dx] = w[o + dx], o in 0..3: two-level select
@@ -176,7 +176,7 @@ knn_vote_kernel(const float* __restrict__ proj_range, const void* __restrict__ p
       const int y = y0 + dy - PAD;
       const bool rowok = (y >= 0) && (y < H);
       const float* rowp = img + y * W + (x0 - PAD);
-      fill_part(dy, S);
+      if (fill_early == 1) { if (dy == 0) fill_part(0, 1); } else fill_part(dy, fill_early == 2 ? S + 3 : S);
 #pragma unroll
       for (int dx = 0; dx < S; ++dx) {
         float v = 0.0f;  // F.unfold zero padding (knn.py:79-81)
@@ -202,6 +202,7 @@ knn_vote_kernel(const float* __restrict__ proj_range, const void* __restrict__ p
       top[i] = lo;
     }
   }
+  if (fill_early == 2) fill_part(S, S + 3);      // spread: three more parts in the later phases
   float t = top[KT - 1];
   if (KT > 8) {  // generic capacity: pick entry knn-1
 #pragma unroll
@@ -246,6 +247,7 @@ knn_vote_kernel(const float* __restrict__ proj_range, const void* __restrict__ p
     }
   }
 
+  if (fill_early == 2) fill_part(S + 1, S + 3);
   // class of each voter (zero padding => class 0, which can never win)
   int cls[KT];
   const char* cbase = reinterpret_cast<const char*>(proj_argmax);
@@ -285,6 +287,7 @@ knn_vote_kernel(const float* __restrict__ proj_range, const void* __restrict__ p
     }
   }
 
+  if (fill_early == 2) fill_part(S + 2, S + 3);
   // vote over classes 1..C-1, first maximum wins (knn.py:131-137)
   int best_c = 1, best_n = 0;
 #pragma unroll
@@ -323,25 +326,28 @@ static int launch_knn_sk(const float* proj_range, const void* proj_argmax, const
     // are resident per SM, leaving registers for the small kernels of the other chains.
     const char* env4 = getenv("C3D_KNN_FILL_CTAS");
     const size_t smem_fill = (env4 && env4[0] == '4' && smem < 38 * 1024) ? 38 * 1024 : smem;  // + 8.3 KB static
+    const char* envp = getenv("C3D_KNN_FILL_EARLY");   // how a CTA spreads its share of the fill
+    const int fill_early = (envp && envp[0] >= '0' && envp[0] <= '2') ? envp[0] - '0' : 2;  // 0: S parts while the window
+    // loads, 1: whole share up front (measured worst), 2 (default): S + 3 parts down to the vote
     KernelTimer timer("knn_vote_fill_kernel", stream);
     if (mode == 3)
       knn_vote_kernel<S, KT, 3><<<grid, threads, smem_fill, stream>>>(
           proj_range, proj_argmax, unproj_range, px, py, offsets, batch, total, H, W, knn, cutoff,
-          nclasses, inv_gauss, out, pxy64, lab64, vec_ok, reinterpret_cast<float4*>(cofill), n4, per_cta);
+          nclasses, inv_gauss, out, pxy64, lab64, vec_ok, reinterpret_cast<float4*>(cofill), n4, per_cta, fill_early);
     else if (mode == 2)
       knn_vote_kernel<S, KT, 2><<<grid, threads, smem_fill, stream>>>(
           proj_range, proj_argmax, unproj_range, px, py, offsets, batch, total, H, W, knn, cutoff,
-          nclasses, inv_gauss, out, pxy64, lab64, vec_ok, reinterpret_cast<float4*>(cofill), n4, per_cta);
+          nclasses, inv_gauss, out, pxy64, lab64, vec_ok, reinterpret_cast<float4*>(cofill), n4, per_cta, fill_early);
     else
       knn_vote_kernel<S, KT, 1><<<grid, threads, smem_fill, stream>>>(
           proj_range, proj_argmax, unproj_range, px, py, offsets, batch, total, H, W, knn, cutoff,
-          nclasses, inv_gauss, out, pxy64, lab64, vec_ok, reinterpret_cast<float4*>(cofill), n4, per_cta);
+          nclasses, inv_gauss, out, pxy64, lab64, vec_ok, reinterpret_cast<float4*>(cofill), n4, per_cta, fill_early);
     return check_launch("knn_vote_fill_kernel");
   }
   KernelTimer timer("knn_vote_kernel", stream);
   knn_vote_kernel<S, KT, 0><<<grid, threads, smem, stream>>>(
       proj_range, proj_argmax, unproj_range, px, py, offsets, batch, total, H, W, knn, cutoff,
-      nclasses, inv_gauss, out, pxy64, lab64, vec_ok, nullptr, 0, 0);
+      nclasses, inv_gauss, out, pxy64, lab64, vec_ok, nullptr, 0, 0, 0);
   return check_launch("knn_vote_kernel");
 }
 
