@@ -43,6 +43,7 @@ def _load():
         "c3d_lovasz_forward": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int64, P, P, P]),
         "c3d_lovasz_backward": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int64, P, P, P, c_int, P]),
         "c3d_lovasz_info": (c_int, [P, P, P]),
+        "c3d_set_concurrent_hint": (c_int, [c_int]),
         "c3d_knn_batch": (c_int, [P, P, P, P, P, P, c_int, c_int64, c_int, c_int, c_int, c_int,
                                   c_float, c_int, P, c_int, c_int, P, P, c_size_t, P]),
         "c3d_profile_enable": (c_int, [c_char_p]),

@@ -15,6 +15,7 @@ constexpr int kMaxBatch = 4096;
 
 void set_error(const char* fmt, ...);
 extern std::atomic<long long> g_launches;
+extern std::atomic<int> g_concurrent_hint;  // c3d_set_concurrent_hint
 
 // RAII device timer around one kernel launch; a no-op unless c3d_profile_enable.
 class KernelTimer {

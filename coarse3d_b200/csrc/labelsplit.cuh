@@ -14,6 +14,8 @@
 // `label == id_c` row order, salsanext_proto.py:350-365].
 // No atomics decide positions: the order is deterministic.
 #pragma once
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace c3d {
@@ -22,6 +24,22 @@ constexpr int kTile = 1024;  // pixels per count/scatter CTA (4 rounds x 256 thr
 constexpr int kMaxClasses = 64;
 constexpr int kFlagBadLabel = 8;
 enum SplitInfo { kInfoT = 0, kInfoPl = 1, kInfoFlags = 2, kInfoDone = 3, kInfoDone2 = 4 };
+
+// Tile CTAs of the two split kernels.  Default: one CTA per tile.  With the concurrent hint
+// (c3d_set_concurrent_hint, set by the step pipeline) and up to 2048 tiles (16 KITTI scans), a
+// persistent grid of C3D_SPLIT_CTAS_PER_SM (default 2) CTAs per SM walks the tiles: alone it
+// is slower (39 vs 18 us at batch 8), but next to the KNN vote, whose CTAs hold every SM slot
+// for tens of microseconds, it is resident almost at once instead of being placed as slots
+// trickle free (step 211 -> 203 us).  Larger batches keep one CTA per tile (the per-CTA tile
+// loop costs more than the placement delay: 1436 vs 1252 us at batch 64).
+inline int split_grid(int nblk) {
+  if (!g_concurrent_hint.load(std::memory_order_relaxed) || nblk > 2048) return nblk;
+  const char* env = getenv("C3D_SPLIT_CTAS_PER_SM");
+  const int per_sm = env ? atoi(env) : 2;
+  if (per_sm <= 0) return nblk;
+  const int g = kNumSMs * per_sm;
+  return nblk < g ? nblk : g;
+}
 
 template <bool kClassMajor>
 __device__ __forceinline__ int seg_index(int b, int c, int B, int C) {
@@ -49,10 +67,15 @@ split_count_scan_kernel(const long long* __restrict__ labels, const uint8_t* __r
                         int32_t* __restrict__ info) {
   __shared__ int s_cnt[kMaxClasses];
   __shared__ int s_flag;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // Tiles are dealt to a small persistent grid: next to a kernel whose CTAs hold every SM
+  // slot for tens of microseconds (the KNN vote), a grid of one CTA per tile is only placed as
+  // slots trickle free, a grid of two CTAs per SM is resident almost at once.
+  for (int blk = blockIdx.x; blk < B * nbps; blk += gridDim.x) {
+  __syncthreads();
   if (threadIdx.x < C) s_cnt[threadIdx.x] = 0;
   __syncthreads();
-  const int b = blockIdx.x / nbps, tile = blockIdx.x % nbps;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blk / nbps, tile = blk % nbps;
   bool bad = false;
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
@@ -65,7 +88,7 @@ split_count_scan_kernel(const long long* __restrict__ labels, const uint8_t* __r
     }
   }
   __syncthreads();
-  if (threadIdx.x < C) blk_cnt[(size_t)blockIdx.x * C + threadIdx.x] = s_cnt[threadIdx.x];
+  if (threadIdx.x < C) blk_cnt[(size_t)blk * C + threadIdx.x] = s_cnt[threadIdx.x];
   if (bad) atomicOr(&info[kInfoFlags], kFlagBadLabel);
 
   // ---- last CTA of scan b: exclusive prefix of the tile counts, per class
@@ -73,7 +96,7 @@ split_count_scan_kernel(const long long* __restrict__ labels, const uint8_t* __r
   __syncthreads();
   if (threadIdx.x == 0) s_flag = (atomicAdd(&info[8 + b], 1) == nbps - 1);
   __syncthreads();
-  if (!s_flag) return;
+  if (!s_flag) continue;
   __threadfence();
   // All tile counts of up to four of this warp's classes are loaded before any is scanned:
   // one global round trip instead of one per (class, 32-tile chunk) -- this tail is latency.
@@ -135,7 +158,7 @@ split_count_scan_kernel(const long long* __restrict__ labels, const uint8_t* __r
   __syncthreads();
   if (threadIdx.x == 0) { info[8 + b] = 0; s_flag = (atomicAdd(&info[kInfoDone], 1) == B - 1); }
   __syncthreads();
-  if (!s_flag) return;
+  if (!s_flag) continue;
   __threadfence();
   if (warp == 0) {
     int carry = 0, tcarry = 0;
@@ -176,6 +199,7 @@ split_count_scan_kernel(const long long* __restrict__ labels, const uint8_t* __r
       info[kInfoDone] = 0;
     }
   }
+  }  // tile loop
 }
 
 template <bool kClassMajor, bool kEntropy>
@@ -186,12 +210,12 @@ split_scatter_kernel(const long long* __restrict__ labels, const uint8_t* __rest
                      const int32_t* __restrict__ seg_start, int32_t* __restrict__ pix_list,
                      int32_t* __restrict__ cls_list, float* __restrict__ w_list,
                      int32_t* __restrict__ cnt_list, const float* __restrict__ bank_src,
-                     int bank_rows, int D, float* __restrict__ bank_n) {
-  if ((int)blockIdx.x >= nblk) {
+                     int bank_rows, int D, float* __restrict__ bank_n, int tile_ctas) {
+  if ((int)blockIdx.x >= tile_ctas) {
     // bank rows: F.normalize(x, p=2, dim=-1), eps 1e-12
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rows = bank_rows;
-    for (int k = (blockIdx.x - nblk) * 8 + warp; k < rows; k += (gridDim.x - nblk) * 8) {
+    for (int k = (blockIdx.x - tile_ctas) * 8 + warp; k < rows; k += (gridDim.x - tile_ctas) * 8) {
       const float* src = bank_src + (size_t)k * D;
       float s = 0.f;
       for (int d = lane; d < D; d += 32) { float v = src[d]; s += v * v; }
@@ -202,8 +226,10 @@ split_scatter_kernel(const long long* __restrict__ labels, const uint8_t* __rest
     return;
   }
   __shared__ int s_cnt[4][8][kMaxClasses];  // [round][warp][class] -> exclusive prefix
-  const int b = blockIdx.x / nbps, tile = blockIdx.x % nbps;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int blk = blockIdx.x; blk < nblk; blk += tile_ctas) {   // persistent grid, see split_count_scan
+  const int b = blk / nbps, tile = blk % nbps;
+  __syncthreads();
   for (int i = threadIdx.x; i < 4 * 8 * kMaxClasses; i += 256) (&s_cnt[0][0][0])[i] = 0;
   __syncthreads();
   int cls[4], rank[4];
@@ -235,7 +261,7 @@ split_scatter_kernel(const long long* __restrict__ labels, const uint8_t* __rest
     if (c < 0) continue;
     const int pix = tile * kTile + r * 256 + threadIdx.x;
     const int slot = seg_start[seg_index<kClassMajor>(b, c, B, C)] +
-                     blk_prefix[(size_t)blockIdx.x * C + c] + s_cnt[r][warp][c] + rank[r];
+                     blk_prefix[(size_t)blk * C + c] + s_cnt[r][warp][c] + rank[r];
     pix_list[slot] = b * HW + pix;
     cls_list[slot] = c;
     if (kEntropy) {
@@ -254,6 +280,7 @@ split_scatter_kernel(const long long* __restrict__ labels, const uint8_t* __rest
       cnt_list[slot] = 0;
     }
   }
+  }  // tile loop
 }
 
 

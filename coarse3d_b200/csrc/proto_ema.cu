@@ -480,13 +480,13 @@ extern "C" int c3d_proto_ema_accumulate(
   if (proto_target) C3D_CUDA(cudaMemsetAsync(proto_target, 0, (size_t)B * HW * 4, stream));
   int rc;
   { KernelTimer kt__("split_count_scan_kernel", stream);
-    split_count_scan_kernel<true><<<nblk, 256, 0, stream>>>(
+    split_count_scan_kernel<true><<<split_grid(nblk), 256, 0, stream>>>(
         (const long long*)label, nullptr, HW, nbps, B, C, ignore_label, w.blk_cnt, w.seg_cnt, w.seg_start,
         w.seg_tidx, w.info); }
   if ((rc = check_launch("split_count_scan_kernel"))) return rc;
-  { KernelTimer kt__("split_scatter_kernel", stream); split_scatter_kernel<true, false><<<nblk + 16, 256, 0, stream>>>(
+  { KernelTimer kt__("split_scatter_kernel", stream); split_scatter_kernel<true, false><<<split_grid(nblk) + 16, 256, 0, stream>>>(
       (const long long*)label, nullptr, nullptr, HW, nbps, nblk, B, C, ignore_label, w.blk_cnt,
-      w.seg_start, w.pix_list, w.cls_list, nullptr, nullptr, prototypes, K, D, w.bank_n); }
+      w.seg_start, w.pix_list, w.cls_list, nullptr, nullptr, prototypes, K, D, w.bank_n, split_grid(nblk)); }
   if ((rc = check_launch("split_scatter_kernel"))) return rc;
 
   EmaRowsParams p{};

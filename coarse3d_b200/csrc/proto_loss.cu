@@ -926,16 +926,16 @@ static int proto_loss_forward_impl(
   if (phases & 1) {
   C3D_CUDA(cudaMemsetAsync(w.info, 0, (size_t)(8 + B) * 4, stream));
   { KernelTimer kt__("split_count_scan_kernel", stream);
-    split_count_scan_kernel<false><<<nblk, 256, 0, stream>>>(
+    split_count_scan_kernel<false><<<split_grid(nblk), 256, 0, stream>>>(
         (const long long*)labels, keep_mask, HW, nbps, B, C, ignore_label, w.blk_cnt, w.seg_cnt, w.seg_start,
         w.seg_tidx, w.info); }
   if ((rc = check_launch("split_count_scan_kernel"))) return rc;
   const int bank_blocks = 16;
   { KernelTimer kt__("split_scatter_kernel", stream);
-    split_scatter_kernel<false, true><<<nblk + bank_blocks, 256, 0, stream>>>(
+    split_scatter_kernel<false, true><<<split_grid(nblk) + bank_blocks, 256, 0, stream>>>(
         (const long long*)labels, keep_mask, probs, HW, nbps, nblk, B, C, ignore_label, w.blk_cnt,
         w.seg_start, w.pix_list, w.cls_list, w.w_list, w.cnt_list, proto_queue + (size_t)M * D,
-        (C - 1) * M, D, w.bank_n); }
+        (C - 1) * M, D, w.bank_n, split_grid(nblk)); }
   if ((rc = check_launch("split_scatter_kernel"))) return rc;
   { KernelTimer kt__("loss_sample_kernel", stream);
     loss_sample_kernel<<<B * C, 256, 0, stream>>>(w.seg_cnt, w.seg_start, w.seg_tidx, w.pix_list,

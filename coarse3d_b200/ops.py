@@ -561,6 +561,18 @@ def proto_ema_apply(prototypes, packed, momentum, ignore_label=0, out=None):
     return out
 
 
+class concurrent_hint:
+    """Context manager around multi-stream use of the library (c3d_set_concurrent_hint)."""
+
+    def __enter__(self):
+        self.prev = lib.c3d_set_concurrent_hint(1)
+        return self
+
+    def __exit__(self, *exc):
+        lib.c3d_set_concurrent_hint(self.prev)
+        return False
+
+
 def launch_count():
     """Kernel launches enqueued by the library since load."""
     return _lib.launch_count()

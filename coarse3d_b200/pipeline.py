@@ -139,6 +139,11 @@ class HotPathStep:
             if not fused:
                 self._knn(s, pr, C)
             return pr
+        with ops.concurrent_hint():
+            return self._run_concurrent(s, b, seed, fused, cur)
+
+    def _run_concurrent(self, s, b, seed, fused, cur):
+        H, W, C = self.shape.proj_h, self.shape.proj_w, self.shape.n_classes
         st_fill, st_proj, st_ema, st_loss = self.side
         self.ev_fork.record(cur)
         for st in self.side:
@@ -221,6 +226,10 @@ class HotPathStep:
         after the projection), then the same chains and schedule as `run`.  Returns
         (loss 0-dim, per-point KNN labels int64, Assembled); both tensors are reused by the
         next call."""
+        with ops.concurrent_hint():
+            return self._run_inputs(points, offsets, weak, bufs, set_index, seed)
+
+    def _run_inputs(self, points, offsets, weak, bufs, set_index, seed):
         s = self.sets[set_index % len(self.sets)]
         H, W, C = self.shape.proj_h, self.shape.proj_w, self.shape.n_classes
         cur = torch.cuda.current_stream(self.device)

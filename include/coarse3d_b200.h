@@ -39,6 +39,13 @@ const char* c3d_last_error(void);
 /* Number of kernel launches enqueued by this library since load (all threads). */
 long long c3d_launch_count(void);
 
+/* Scheduling hint (process-wide, returns the previous value).  on = 1: the caller runs this
+ * library's calls on several streams next to long-running kernels (the step pipeline), so
+ * the small latency-bound kernels should use small persistent grids, which are resident at
+ * once instead of being placed as SM slots trickle free.  on = 0 (default): calls run one
+ * after the other; grids sized for an idle GPU.  Results are identical either way. */
+int c3d_set_concurrent_hint(int on);
+
 /* Optional per-kernel device timing: CUDA events recorded on the launching
  * stream right before and after each kernel launch.  kernel_name "" = every
  * kernel, a kernel's name = only that kernel, NULL = off (default).  Not

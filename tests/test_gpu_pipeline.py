@@ -35,6 +35,21 @@ def test_schedules_agree(cuda_device, monkeypatch):
             assert torch.equal(a, b), (schedule, concurrent)
 
 
+def test_two_phase_loss_forward_and_held_knn(cuda_device, monkeypatch):
+    """c3d_proto_loss_forward_phase: selection and rows as two calls (with the KNN + fill kernel
+    released in between, C3D_KNN_AFTER_SELECT=1) give the one-call results."""
+    step = _step(monkeypatch, "fill_in_knn")
+    step.run(0, seed=5)
+    want = _outputs(step)
+    monkeypatch.setenv("C3D_KNN_AFTER_SELECT", "1")
+    held = _step(monkeypatch, "fill_in_knn")
+    assert held.knn_after_select
+    held.grad.fill_(2.0)
+    held.run(0, seed=5)
+    for a, b in zip(_outputs(held), want):
+        assert torch.equal(a, b)
+
+
 def test_graph_replay_matches_eager(cuda_device, monkeypatch):
     step = _step(monkeypatch, "fill_in_knn")
     step.run(1, seed=0)
