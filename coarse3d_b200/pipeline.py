@@ -105,6 +105,7 @@ class HotPathStep:
         (self.ev_fork, self.ev_fill, self.ev_proj, self.ev_ema, self.ev_loss,
          self.ev_resolved, self.ev_selected) = (torch.cuda.Event() for _ in range(7))
         self.knn_after_select = _os.environ.get("C3D_KNN_AFTER_SELECT", "0") == "1"
+        self.knn_split = int(_os.environ.get("C3D_KNN_SPLIT", "0"))   # scans in the first of two KNN launches
         torch.cuda.synchronize(self.device)
 
     # bytes the reference dtypes move per step
@@ -279,9 +280,25 @@ class HotPathStep:
             workspace=self.ema_ws, packed=self.packed, out=self.protos_next)
 
     def _knn(self, s, pr, C, cofill=None):
-        ops.knn_batch(pr.proj_range, s.argmax, pr.uproj_depth, pr.uproj_x_idx, pr.uproj_y_idx,
-                      s.offsets, self.knn_k, self.knn_s, self.knn_sigma, self.knn_cutoff, C,
-                      inv_gauss=self.inv_gauss, out=self.knn_out, cofill=cofill)
+        b1 = self.knn_split
+        if cofill is None or b1 <= 0 or b1 >= self.batch:
+            ops.knn_batch(pr.proj_range, s.argmax, pr.uproj_depth, pr.uproj_x_idx, pr.uproj_y_idx,
+                          s.offsets, self.knn_k, self.knn_s, self.knn_sigma, self.knn_cutoff, C,
+                          inv_gauss=self.inv_gauss, out=self.knn_out, cofill=cofill)
+            return
+        # Two launches (scans [0, b1) and [b1, B), each carrying its share of the fill): while
+        # the first drains, the whole-SM kernels of the other chains (217 / 205 KB of shared
+        # memory) are placed, instead of waiting for the end of a single 3750-CTA grid.
+        n1 = int(s.host_offsets[b1])
+        if not hasattr(s, "offsets_tail") or s.offsets_tail_b1 != b1:
+            s.offsets_tail = (s.offsets[b1:] - n1).contiguous()
+            s.offsets_tail_b1 = b1
+        ops.knn_batch(pr.proj_range[:b1], s.argmax[:b1], pr.uproj_depth[:n1], pr.uproj_x_idx[:n1],
+                      pr.uproj_y_idx[:n1], s.offsets[:b1 + 1], self.knn_k, self.knn_s, self.knn_sigma,
+                      self.knn_cutoff, C, inv_gauss=self.inv_gauss, out=self.knn_out[:n1], cofill=cofill[:b1])
+        ops.knn_batch(pr.proj_range[b1:], s.argmax[b1:], pr.uproj_depth[n1:], pr.uproj_x_idx[n1:],
+                      pr.uproj_y_idx[n1:], s.offsets_tail, self.knn_k, self.knn_s, self.knn_sigma,
+                      self.knn_cutoff, C, inv_gauss=self.inv_gauss, out=self.knn_out[n1:], cofill=cofill[b1:])
 
     def capture(self):
         """Capture one CUDA graph per input set.  Returns False if capture fails

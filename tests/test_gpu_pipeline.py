@@ -50,6 +50,21 @@ def test_two_phase_loss_forward_and_held_knn(cuda_device, monkeypatch):
         assert torch.equal(a, b)
 
 
+def test_two_launch_knn_matches(cuda_device, monkeypatch):
+    """C3D_KNN_SPLIT: the vote (+ fill) as two launches over scans [0, b1) and [b1, B)."""
+    step = _step(monkeypatch, "fill_in_knn")
+    step.run(0, seed=5)
+    want = _outputs(step)
+    monkeypatch.setenv("C3D_KNN_SPLIT", "1")
+    split = _step(monkeypatch, "fill_in_knn")
+    assert split.knn_split == 1
+    split.grad.fill_(2.0)
+    split.knn_out.fill_(-1)
+    split.run(0, seed=5)
+    for a, b in zip(_outputs(split), want):
+        assert torch.equal(a, b)
+
+
 def test_graph_replay_matches_eager(cuda_device, monkeypatch):
     step = _step(monkeypatch, "fill_in_knn")
     step.run(1, seed=0)
