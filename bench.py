@@ -10,6 +10,7 @@ packed prototype sums when N > 1) -> KNN vote.  Prints ONE JSON line on rank 0.
 """
 import argparse
 import json
+import math
 import os
 import sys
 import threading
@@ -23,36 +24,72 @@ sys.path.insert(0, ROOT)
 
 METRIC = "scans/s (project+proto-loss fwd/bwd+KNN)"
 
+# BASELINE.json configs[0..4] -> --config 1..5.  Every config is the full step of the metric
+# (projection -> EMA prototype update -> prototype loss fwd+bwd -> KNN 5x5) on its shape/batch.
+# Default = configs[4], the batch-64-per-GPU sweep the metric ("at 1/2/4/8 B200") is quoted on;
+# it fits one GPU, so it is also the N=1 workload.
+CONFIGS = {
+    1: dict(shape="kitti", batch=1, dim=256, what="single KITTI-shaped scan, D=256 (the reference's CPU-runnable case)"),
+    2: dict(shape="kitti", batch=8, dim=128, what="batch 8 KITTI-shaped scans, D=128"),
+    3: dict(shape="nuscenes", batch=32, dim=128, what="batch 32 nuScenes-shaped scans at 0.01% labels, D=128"),
+    4: dict(shape="poss", batch=16, dim=128, what="batch 16 SemanticPOSS-shaped scans, KNN 5x5, D=128"),
+    5: dict(shape="kitti", batch=64, dim=128, what="scan-sharded sweep, batch 64 KITTI-shaped scans per GPU, D=128"),
+}
+DEFAULT_CONFIG = 5
+
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=10)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--shape", default="kitti")
-    ap.add_argument("--batch-per-gpu", type=int, default=8)   # BASELINE config 2; config 5 uses 64
-    ap.add_argument("--dim", type=int, default=128)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "torch_eager"])
+    ap.add_argument("--config", type=int, default=DEFAULT_CONFIG, choices=sorted(CONFIGS))
+    ap.add_argument("--shape", default=None, help="override the config's scan shape")
+    ap.add_argument("--batch-per-gpu", type=int, default=None, help="override the config's batch")
+    ap.add_argument("--dim", type=int, default=None, help="override the config's feature dim")
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--serial", action="store_true", help="one stream, no overlap of the four chains")
+    ap.add_argument("--serial", action="store_true", help="one stream, no overlap of the chains")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-scans", type=int, default=8)
-    return ap.parse_args()
+    ap.add_argument("--min-seconds", type=float, default=1.5,
+                    help="the K-step block is repeated until the timed region is this long; "
+                         "the median block is reported")
+    args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    args.shape = args.shape or cfg["shape"]
+    args.batch_per_gpu = args.batch_per_gpu or cfg["batch"]
+    args.dim = args.dim or cfg["dim"]
+    return args
 
 
-def workload_config(args, world):
-    from coarse3d_b200 import synth
+def load_synth():
+    """The synthetic scan generator by file path: importing the `coarse3d_b200` package would
+    map libcoarse3d_b200.so, which the reference arm must not do."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import baselines
+    return baselines.load_synth()
+
+
+def workload_config(args, world, synth):
+    """Identical in both arms (the driver compares it)."""
     shp = synth.SHAPES[args.shape]
+    HW = shp.proj_h * shp.proj_w
+    inputs_mb = args.batch_per_gpu * (shp.n_points * 16 + HW * (4 * args.dim + 4 * shp.n_classes + 17)) >> 20
     return {
-        "workload": "BASELINE.json configs[1]: batch %d %s-shaped scans per GPU (%d points, %dx%d, "
-                    "%d classes, %.2g%% weak labels), D=%d, M=20, A=512; project + proto-loss fwd/bwd "
-                    "+ EMA update + KNN 5x5 k=5" % (args.batch_per_gpu, shp.name, shp.n_points,
-                                                    shp.proj_h, shp.proj_w, shp.n_classes,
-                                                    100 * shp.label_ratio, args.dim),
-        "batch_per_gpu": args.batch_per_gpu, "global_batch": args.batch_per_gpu * world,
-        "points_per_scan": shp.n_points, "proj": [shp.proj_h, shp.proj_w], "feature_dim": args.dim,
+        "workload": "BASELINE.json configs[%d]: %s; %d %s-shaped scans per GPU (%d points, %dx%d, "
+                    "%d classes, %.2g%% weak labels), D=%d, M=20, A=512; project + EMA prototype update "
+                    "+ proto-loss fwd/bwd + KNN 5x5 k=5" % (
+                        args.config - 1, CONFIGS[args.config]["what"], args.batch_per_gpu, shp.name,
+                        shp.n_points, shp.proj_h, shp.proj_w, shp.n_classes, 100 * shp.label_ratio, args.dim),
+        "config_id": args.config, "batch_per_gpu": args.batch_per_gpu,
+        "global_batch": args.batch_per_gpu * world, "points_per_scan": shp.n_points,
+        "proj": [shp.proj_h, shp.proj_w], "feature_dim": args.dim,
         "parallelism": "scan-sharded x%d, one all-reduce of [K*D|K] prototype sums" % world,
+        "l2": "no flush: 3 rotating input sets of ~%d MB re-read inputs each and a %d MB gradient "
+              "written per step, both larger than the 126 MB L2" % (
+                  inputs_mb, args.batch_per_gpu * HW * args.dim * 4 >> 20),
     }
 
 
@@ -115,10 +152,9 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------ CPU baseline --
-def cpu_reference_step(n_scans, shape_name, dim, seed0=1000):
-    """The oracle (CPU restatement of the reference) over `n_scans` scans of the
-    workload: projection, loss fwd+bwd, EMA update, KNN.  Returns seconds."""
-    from coarse3d_b200 import synth
+def cpu_port_step(synth, n_scans, shape_name, dim, seed0=1000):
+    """The oracle (CPU restatement of the reference) over `n_scans` scans of the workload:
+    projection, EMA prototype update, loss fwd+bwd on the updated bank, KNN.  Returns seconds."""
     from oracle import knn as oknn, projection as oproj, proto_ema as oema, proto_loss as oloss
     shp = synth.SHAPES[shape_name]
     H, W, C, M = shp.proj_h, shp.proj_w, shp.n_classes, 20
@@ -128,7 +164,7 @@ def cpu_reference_step(n_scans, shape_name, dim, seed0=1000):
     feats = torch.randn(n_scans, dim, H, W, generator=g)
     probs = torch.softmax(torch.randn(n_scans, C, H, W, generator=g), 1)
     argmax = torch.randint(0, C, (n_scans, H, W), generator=g).numpy()
-    queue = torch.nn.functional.normalize(torch.randn(1, C, M, dim, generator=g), dim=-1)
+    queue = torch.nn.functional.normalize(torch.randn(C, M, dim, generator=g), dim=-1)
     ln = [torch.ones(dim), torch.zeros(dim), torch.ones(C), torch.zeros(C)]
     t0 = time.perf_counter()
     projs, labels = [], []
@@ -139,54 +175,128 @@ def cpu_reference_step(n_scans, shape_name, dim, seed0=1000):
         lab[v] = weak[o["proj_idx"][v]]
         projs.append(o), labels.append(lab)
     labels = torch.from_numpy(np.stack(labels))
+    new_q, _, _, _ = oema.prototype_learning(feats, labels, queue, *ln, C, 0, 0.999, gumbel=None,
+                                             labelled_only=True)
     f = feats.clone().requires_grad_(True)
-    loss, _, _ = oloss.contrast_mem_loss(f, probs, labels, labels > 0, queue, temperature=0.07,
+    loss, _, _ = oloss.contrast_mem_loss(f, probs, labels, labels > 0, new_q[None], temperature=0.07,
                                          num_anchor=512)
     loss.backward()
-    oema.prototype_learning(feats, labels, queue[0], *ln, C, 0, 0.999, gumbel=None, labelled_only=True)
     for o, am in zip(projs, argmax):
         oknn.knn_vote(o["proj_range"], o["uproj_depth"], am, o["uproj_x_idx"], o["uproj_y_idx"],
                       5, 5, 1.0, 1.0, C)
     return time.perf_counter() - t0
 
 
-def cpu_baseline(args):
-    torch.set_num_threads(os.cpu_count() or 1)
-    cpu_reference_step(1, args.shape, args.dim)  # warm-up (imports, allocator)
-    n = max(1, args.cpu_scans)
-    dts = [cpu_reference_step(n, args.shape, args.dim, seed0=1000 + 10 * r) for r in range(3)]
+class CpuArm:
+    """The reference's CPU implementation of the path: the unmodified reference modules when a
+    reference tree is present (build container), else the oracle port (GPU box)."""
+
+    def __init__(self, args, synth):
+        import baselines
+        self.args, self.synth = args, synth
+        self.kind, self.real = "port", None
+        root = baselines.find_reference_root()
+        if root is not None and os.environ.get("C3D_BENCH_PORT_ONLY", "0") != "1":
+            try:
+                self.real = baselines.RealReference(root)
+                self.kind = "reference"
+            except Exception as e:  # noqa: BLE001
+                sys.stderr.write("reference tree at %s not usable (%r): timing the oracle port\n" % (root, e))
+        torch.set_num_threads(os.cpu_count() or 1)
+
+    def step(self, n_scans, seed0=1000):
+        if self.real is not None:
+            return self.real.step(self.synth, self.synth.SHAPES[self.args.shape], n_scans, self.args.dim, seed0)
+        return cpu_port_step(self.synth, n_scans, self.args.shape, self.args.dim, seed0)
+
+    def describe(self):
+        return ("unmodified reference modules (RangeProjection, prototype block of SalsaNextProto, "
+                "ContrastMEMLoss, KNN)" if self.real is not None else
+                "oracle/ port (numpy projection 1 thread, torch-CPU EMA / loss fwd+bwd / KNN)")
+
+
+def cpu_baseline(args, synth):
+    arm = CpuArm(args, synth)
+    arm.step(1)  # warm-up (imports, allocator)
+    n = max(1, min(args.cpu_scans, args.batch_per_gpu))
+    dts = [arm.step(n, seed0=1000 + 10 * r) for r in range(3)]
     dt = float(np.median(dts))
-    return {"value": n / dt, "unit": "scans/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": "median of 3 passes over %d scans (one batch of the workload) through oracle/ "
-                      "(numpy projection 1 thread, torch-CPU loss fwd+bwd / EMA / KNN); %.2f s per pass, "
-                      "%.1f s of CPU work" % (n, dt, sum(dts))}
+    return {"value": n / dt, "unit": "scans/s", "cores": torch.get_num_threads(), "kind": arm.kind,
+            "sample": "median of 3 passes over %d scans of the workload through the %s; %.2f s per pass, "
+                      "%.1f s of CPU work" % (n, arm.describe(), dt, sum(dts))}
 
 
 def run_reference_arm(args, rank, world):
+    """`--impl reference`: the reference's own CPU implementation of the path on the host
+    cores, W warm-up + exactly K timed steps, each a bounded sample of the workload's batch
+    (sized so that the run ends within a few minutes).  Rank 0 only."""
     if rank != 0:
         return
-    torch.set_num_threads(os.cpu_count() or 1)
-    n = 1 if args.steps > 20 else 2
-    for _ in range(min(args.warmup, 1)):
-        cpu_reference_step(1, args.shape, args.dim)
-    t_all, done, t_start = 0.0, 0, time.perf_counter()
-    for _ in range(args.steps):
-        t_all += cpu_reference_step(n, args.shape, args.dim)
-        done += 1
-        if time.perf_counter() - t_start > 150:
-            break
-    val = done * n / t_all
+    synth = load_synth()
+    arm = CpuArm(args, synth)
+    K, Wu = args.steps, max(args.warmup, 1)
+    t1 = arm.step(1)                                     # calibration = first warm-up step
+    budget = float(os.environ.get("C3D_REF_BUDGET_S", "120"))
+    n = int(max(1, min(args.batch_per_gpu, budget / ((K + Wu) * max(t1, 1e-3)))))
+    for _ in range(Wu - 1):
+        arm.step(n)
+    t_all = 0.0
+    for i in range(K):
+        t_all += arm.step(n, seed0=1000 + 10 * i)
+    val = K * n / t_all
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": "scans/s", "n_gpus": args.gpus,
-        "steps": done, "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * t_all / done,
+        "steps": K, "warmup": Wu, "ms_per_step": 1e3 * t_all / K,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": workload_config(args, world),
-        "cpu_baseline": {"value": val, "unit": "scans/s", "cores": torch.get_num_threads(), "kind": "port",
-                         "sample": "%d scan(s) per step through oracle/ on the host cores" % n},
+        "data": "synthetic", "config": workload_config(args, world, synth),
+        "cpu_baseline": {"value": val, "unit": "scans/s", "cores": torch.get_num_threads(), "kind": arm.kind,
+                         "sample": "each step = %d of the batch's %d scans through the %s" % (
+                             n, args.batch_per_gpu, arm.describe())},
         "e2e": {"value": val, "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def run_torch_eager(args, rank, world):
+    """`--impl torch_eager`: the reference's algorithm with stock torch ops on the same B200
+    (tools/baselines.py), the "existing Blackwell path" of SURVEY.md 2b / 8d.  A bounded sample
+    of the workload's batch per step (the dense prototype similarity needs 1.6 KB per pixel)."""
+    if rank != 0:
+        return
+    import baselines
+    synth = load_synth()
+    shp = synth.SHAPES[args.shape]
+    dev = torch.device("cuda", 0)
+    H, W, C, M, D = shp.proj_h, shp.proj_w, shp.n_classes, 20, args.dim
+    n = max(1, min(args.batch_per_gpu, args.cpu_scans))
+    g = torch.Generator(device=dev).manual_seed(1000)
+    state = dict(feats=torch.randn((n, D, H, W), device=dev, generator=g),
+                 probs=torch.softmax(torch.randn((n, C, H, W), device=dev, generator=g), 1),
+                 argmax=torch.randint(0, C, (n, H, W), device=dev, generator=g),
+                 protos=torch.nn.functional.normalize(torch.randn((C, M, D), device=dev, generator=g), dim=-1),
+                 ln_d=torch.nn.LayerNorm(D).to(dev), ln_c=torch.nn.LayerNorm(C).to(dev))
+    scans = [synth.make_scan(shp, 1000 + i) for i in range(n)]
+    K, Wu = args.steps, max(args.warmup, 1)
+    for _ in range(Wu):
+        baselines.torch_eager_step(synth, shp, scans, dev, D, state)
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for _ in range(K):
+        baselines.torch_eager_step(synth, shp, scans, dev, D, state)
+    torch.cuda.synchronize(dev)
+    dt = time.perf_counter() - t0
+    val = K * n / dt
+    print(json.dumps({
+        "impl": "torch_eager", "metric": METRIC, "value": val, "unit": "scans/s", "n_gpus": 1, "steps": K,
+        "warmup": Wu, "ms_per_step": 1e3 * dt / K, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, world, synth),
+        "sample": "each step = %d of the batch's %d scans: numpy projection on the host (as in the "
+                  "reference loaders) + H2D, then the reference's torch statements on cuda:0 (dense "
+                  "LayerNorm + prototype similarity, per-(scan, class) multinomial loop, autograd "
+                  "backward, two unfolds + topk per scan for KNN); wall clock incl. the host part" % (
+                      n, args.batch_per_gpu),
+        "torch": torch.__version__, "gpu_launches": 0}), flush=True)
 
 
 # ------------------------------------------------------------------- main --
@@ -197,6 +307,9 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference_arm(args, rank, world)
+        return
+    if args.impl == "torch_eager":
+        run_torch_eager(args, rank, world)
         return
 
     import torch.distributed as dist
@@ -230,32 +343,53 @@ def main():
         step.step(i)
     barrier()
 
-    # ---- timed region: exactly K steps, CUDA events, max over ranks
+    # ---- timed region: blocks of exactly K steps (CUDA events, barrier + synchronize on both
+    # sides of every block, max over ranks per block); blocks are repeated until the region is
+    # >= --min-seconds long so that the clock sampler sees it, and the MEDIAN block is reported.
     l0 = ops.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    t0 = time.perf_counter()
-    e0.record()
-    for i in range(K):
-        step.step(i)
-    e1.record()
-    barrier()
-    t1 = time.perf_counter()
-    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_total = float(ms.item())
+    block_ms = []
+    t_region0 = time.perf_counter()
+    n_blocks = 1
+    while True:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for i in range(K):
+            step.step(i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        block_ms.append(float(ms.item()))
+        if len(block_ms) == 1:   # every rank derives the same block count from the reduced time
+            n_blocks = int(min(200, max(1, math.ceil(args.min_seconds * 1e3 / max(block_ms[0], 1e-3)))))
+        if len(block_ms) >= n_blocks:
+            break
+    t_region1 = time.perf_counter()
+    ms_total = float(np.median(block_ms))
     eager_launches_per_step = None
     if graphed:
         la = ops.launch_count(); step.run(0); torch.cuda.synchronize(dev)
         eager_launches_per_step = ops.launch_count() - la
-        launches = eager_launches_per_step * K  # kernels inside the replayed graphs
+        launches = eager_launches_per_step * K  # kernels inside the replayed graphs, per block
     else:
-        launches = ops.launch_count() - l0
-    clocks = sampler.summary(t0, t1)
+        launches = (ops.launch_count() - l0) // len(block_ms)
+    clocks = sampler.summary(t_region0, t_region1)
+
+    # ---- N > 1: every rank must hold the bit-identical prototype bank
+    banks_identical = None
+    if world > 1:
+        mine = step.protos.detach().clone()
+        ref = mine.clone()
+        dist.broadcast(ref, src=0)
+        same = torch.tensor([1 if torch.equal(mine, ref) else 0], device=dev)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        banks_identical = bool(same.item())
+        assert banks_identical, "prototype banks diverged across ranks"
 
     # ---- per-kernel device times (eager, events inside the library around each launch)
-    n_prof = min(max(K, 20), 100)
+    n_prof = 20
     step.concurrent = False  # one stream, so each kernel's events bracket only itself
     with ops.profile("") as prof:
         for i in range(n_prof):
@@ -263,6 +397,16 @@ def main():
         torch.cuda.synchronize(dev)
         per_kernel = {k: {"us": 1e3 * v[0] / max(v[1], 1), "launches_per_step": v[1] / n_prof}
                       for k, v in prof.all().items()}
+    # the dominant kernel in its concurrent setting (the fill daemon runs under the other chains)
+    dom_concurrent_us = None
+    if not args.serial and step.schedule == "fill_daemon":
+        step.concurrent = True
+        with ops.profile("fill_daemon_kernel") as prof:
+            for i in range(n_prof):
+                step.run(i, seed=i)
+            torch.cuda.synchronize(dev)
+            v = prof.read("fill_daemon_kernel")
+            dom_concurrent_us = 1e3 * v[0] / max(v[1], 1)
     sampler.stop()
 
     alg = step.algorithmic_bytes()
@@ -272,9 +416,11 @@ def main():
     except Exception:  # noqa: BLE001
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    # Dominant kernel = the one that writes the dense gradient (84 % of the step's bytes):
-    # the stand-alone fill, or the KNN vote carrying it (schedule "fill_in_knn").
-    if "knn_vote_fill_kernel" in per_kernel:
+    # Dominant kernel = the one that writes the dense gradient (84 % of the step's bytes): the
+    # fill daemon, the stand-alone fill, or the KNN vote carrying the fill.
+    if "fill_daemon_kernel" in per_kernel:
+        dom, dom_bytes = "fill_daemon_kernel", alg["loss_grad_fill"]
+    elif "knn_vote_fill_kernel" in per_kernel:
         dom, dom_bytes = "knn_vote_fill_kernel", alg["loss_grad_fill"] + alg["knn"]
     else:
         dom, dom_bytes = "fill_zero_kernel", alg["loss_grad_fill"]
@@ -284,19 +430,20 @@ def main():
     tpath = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
     if os.path.exists(tpath):
         try:
-            tj = json.load(open(tpath))
-            if (tj.get("kernel") == dom and tj.get("batch") == B and tj.get("dim") == args.dim
-                    and tj.get("shape") == args.shape):
-                traffic = tj.get("dram_bytes_per_launch")
+            for tj in json.load(open(tpath)).get("entries", []):
+                if (tj.get("kernel") == dom and tj.get("batch") == B and tj.get("dim") == args.dim
+                        and tj.get("shape") == args.shape):
+                    traffic = tj.get("dram_bytes_per_launch")
         except Exception:  # noqa: BLE001
             pass
+    step_bytes = alg["project"] + alg["knn"] + alg["loss"]
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                 "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650",
                 "algorithmic_bytes_per_launch": dom_bytes,
-                "step_algorithmic_bytes": alg["project"] + alg["knn"] + alg["loss"],
-                "step_frac_of_peak": (alg["project"] + alg["knn"] + alg["loss"]) /
-                                     (ms_total / K * 1e-3) / 1e9 / peak}
+                "kernel_us_alone": dom_us, "kernel_us_under_the_step": dom_concurrent_us,
+                "step_algorithmic_bytes": step_bytes,
+                "step_frac_of_peak": step_bytes / (ms_total / K * 1e-3) / 1e9 / peak}
 
     # ---- end to end through the public, reference-shaped API with host buffers
     e2e = None
@@ -307,17 +454,17 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": "scans/s", "n_gpus": world, "steps": K, "warmup": Wu,
         "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic", "config": dict(
-            workload_config(args, world), cuda_graph=bool(graphed), concurrent_chains=not args.serial,
-            schedule=step.schedule,
-            l2="3 rotating input sets (~120 MB re-read inputs each) + a %d MB gradient streamed per "
-               "step; both exceed the 126 MB L2" % (alg["loss_grad_fill"] >> 20)),
+        "dtype": "f32", "data": "synthetic", "config": workload_config(args, world, synth),
+        "run": {"cuda_graph": bool(graphed), "concurrent_chains": not args.serial, "schedule": step.schedule,
+                "blocks": len(block_ms), "block_ms_min_median_max": [min(block_ms), ms_total, max(block_ms)],
+                "timed_region_s": t_region1 - t_region0, "banks_identical_across_ranks": banks_identical,
+                "kernels_per_step": eager_launches_per_step},
         "roofline": roofline, "clocks": clocks, "gpu_launches": int(launches),
         "kernels_us": {k: round(v["us"], 2) for k, v in sorted(per_kernel.items())},
         "e2e": e2e,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(args)
+        line["cpu_baseline"] = cpu_baseline(args, load_synth())
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -397,12 +544,12 @@ def run_e2e(args, step, dev, world, K):
         pr = rp.doProjectionAssembleBatch(di["points"], di["offsets"], weak_label=di["weak"],
                                           buffers=step.proj_bufs[j])
         labels = pr.train_label
+        bank.update(s0.feats.detach(), labels)           # model.forward's prototype block comes first
         feats = s0.feats.requires_grad_(True)
         feats.grad = None
         loss = crit(feats=feats, output=s0.probs, labels=labels, keep_mask=None,
                     proto_queue=bank.prototypes.detach().unsqueeze(0))
         loss.backward()
-        bank.update(s0.feats.detach(), labels)
         lab = knn.forward_batch(pr.proj_range, pr.uproj_depth, s0.argmax, pr.uproj_x_idx,
                                 pr.uproj_y_idx, di["offsets"])
         d_loss[j].copy_(loss.detach())
@@ -482,8 +629,8 @@ def run_e2e(args, step, dev, world, K):
     return {"value": world * B * K / (float(ms.item()) * 1e-3), "unit": "scans/s",
             "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": K,
             "ms_per_step": float(ms.item()) / K,
-            "api": ("RangeProjection.doProjectionAssembleBatch + ContrastMEMLoss()(..).backward() + "
-                    "PrototypeBank.update + KNN.forward_batch (classes called in sequence)") if use_classes
+            "api": ("RangeProjection.doProjectionAssembleBatch + PrototypeBank.update + "
+                    "ContrastMEMLoss()(..).backward() + KNN.forward_batch (classes called in sequence)") if use_classes
                    else "coarse3d_b200.pipeline.HotPathStep.run_inputs: c3d_project_assemble_batch -> "
                         "c3d_knn_batch(+fill) || c3d_proto_loss_forward/backward || c3d_proto_ema_* on streams",
             "host_inputs": "points f32 (N,4), offsets, per-point weak labels %s (pinned); " % label_t +

@@ -61,11 +61,14 @@ def _load():
         "c3d_proto_loss_backward": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P,
                                             c_int, P]),
         "c3d_zero_fill": (c_int, [P, c_size_t, P]),
+        "c3d_zero_fill_background": (c_int, [P, c_size_t, c_int, c_int, c_int, c_int, P]),
         "c3d_proto_loss_info": (c_int, [P, P, P]),
         "c3d_proto_loss_rows": (c_int, [P, c_int, c_int, c_int, c_int, c_int, c_int, c_int64, P, P, P, P]),
         "c3d_proto_ema_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int64]),
         "c3d_proto_ema_accumulate": (c_int, [P, P, P, P, P, P, P, c_float, c_int, c_int, c_int, c_int,
                                              c_int, c_int, c_int, c_int64, P, c_int, c_uint64, P, P, P, P]),
+        "c3d_proto_ema_accumulate_dense": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                                   c_int64, P, c_int, c_uint64, P, P, P, P]),
         "c3d_proto_ema_apply": (c_int, [P, P, c_int, c_int, c_int, c_int, c_double, P, P]),
         "c3d_proto_ema_info": (c_int, [P, P, P]),
     }

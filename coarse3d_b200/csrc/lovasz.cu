@@ -213,7 +213,11 @@ __global__ void lovasz_finalize_kernel(int C, int cap, int classes_all, const in
   }
   if (P == 0) atomicOr(&info[kLovFlags], kLovEmpty);
   info[kLovPresent] = n;
-  *loss_out = (n > 1) ? acc / (float)n : acc;                      // :46-48
+  // More valid pixels than the workspace holds: an arbitrary subset was kept, so the value
+  // would be wrong and non-deterministic.  Fail loudly without a host round trip: the loss is
+  // NaN (the module's own NaN assertion, lovasz_softmax.py:178, then fires).
+  const bool overflow = (info[kLovFlags] & kLovOverflow) != 0;
+  *loss_out = overflow ? __int_as_float(0x7fc00000) : ((n > 1) ? acc / (float)n : acc);  // :46-48
 }
 
 // ------------------------------------------------------ fallback: keys ----
@@ -353,12 +357,9 @@ extern "C" int c3d_lovasz_forward(const float* probs, const int64_t* labels, int
     int n = 1024;
     while (n < cap && n < kLovSortMax) n <<= 1;
     const size_t smem = (size_t)n * sizeof(unsigned long long);
-    static bool attr_set = false;
-    if (!attr_set) {
-      C3D_CUDA(cudaFuncSetAttribute(lovasz_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    kLovSortMax * (int)sizeof(unsigned long long)));
-      attr_set = true;
-    }
+    // per call: the attribute is per device, and a process may drive several devices
+    C3D_CUDA(cudaFuncSetAttribute(lovasz_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  kLovSortMax * (int)sizeof(unsigned long long)));
     KernelTimer kt__("lovasz_sort_kernel", stream);
     lovasz_sort_kernel<<<C, 1024, smem, stream>>>(probs, HW, C, cap, classes_all, w.pix, w.lab, w.hist,
                                                   w.info, w.gval, w.gpix, w.cls_loss);

@@ -199,6 +199,44 @@ ema_rows_kernel(EmaRowsParams p) {
   }
 }
 
+// ---------------------------------------------------------------- E2d ------
+// Rows from the DENSE tensors the reference's forward has already built
+// (salsanext_proto.py:497-510), for the drop-in `prototype_learning` (:337-402): out_feat
+// (n, D) LayerNorm+L2-normalised rows, nearest (B, C, H, W), sim (n, M, C).  Only the
+// labelled rows are read: feature row copy, pred = argmax_C nearest (:340), mask (:341) and the
+// row's M similarities to its own class (:352-353).
+__global__ void __launch_bounds__(256)
+ema_rows_dense_kernel(const float* __restrict__ out_feat, const float* __restrict__ nearest,
+                      const float* __restrict__ sim, const int32_t* __restrict__ pix_list,
+                      const int32_t* __restrict__ cls_list, int32_t* __restrict__ info,
+                      float* __restrict__ feat, float* __restrict__ simq, int32_t* __restrict__ maskv,
+                      int HW, int D, int M, int C, int max_rows) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_rows = info[kInfoPl];
+  if (n_rows > max_rows) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&info[kInfoFlags], kEmaOverflow);
+    return;
+  }
+  for (int slot = blockIdx.x * 8 + warp; slot < n_rows; slot += gridDim.x * 8) {
+    const int gpix = pix_list[slot], cls = cls_list[slot];
+    const int b = gpix / HW, pix = gpix - b * HW;
+    for (int d = lane; d < D; d += 32) feat[(size_t)slot * D + d] = __ldg(out_feat + (size_t)gpix * D + d);
+    float best = -CUDART_INF_F; int best_c = 0x7fffffff;
+    for (int c = lane; c < C; c += 32) {   // ascending c keeps the first maximum per lane
+      const float y = __ldg(nearest + ((size_t)b * C + c) * HW + pix);
+      if (y > best) { best = y; best_c = c; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oc = __shfl_xor_sync(0xffffffffu, best_c, o);
+      if (ob > best || (ob == best && oc < best_c)) { best = ob; best_c = oc; }
+    }
+    if (lane == 0) maskv[slot] = (best_c == cls);
+    if (lane < M) simq[(size_t)slot * M + lane] = __ldg(sim + ((size_t)gpix * M + lane) * C + cls);
+  }
+}
+
 // ---------------------------------------------------------------- E3 -------
 __device__ __forceinline__ uint4 philox_e(uint4 ctr, uint2 key) {
 #pragma unroll
@@ -389,9 +427,9 @@ ema_segsum_kernel(const int32_t* __restrict__ seg_cnt, const int32_t* __restrict
 
 // ---------------------------------------------------------------- E5 -------
 __global__ void __launch_bounds__(256)
-ema_apply_kernel(const float* __restrict__ protos_in, const float* __restrict__ packed, int C, int M,
+ema_apply_kernel(const float* protos_in, const float* __restrict__ packed, int C, int M,
                  int D, int ignore_label, float mom, float one_minus_mom,
-                 float* __restrict__ protos_out) {
+                 float* protos_out) {   // protos_out may alias protos_in (row-local read-then-write)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int K = C * M;
   const int k = blockIdx.x * 8 + warp;
@@ -445,12 +483,14 @@ extern "C" size_t c3d_proto_ema_workspace_bytes(int batch, int n_classes, int hw
   return carve_ema(nullptr, batch, n_classes, hw, dim, sub_protos, max_rows).bytes;
 }
 
-extern "C" int c3d_proto_ema_accumulate(
-    const float* embedding, const int64_t* label, const float* prototypes, const float* ln_d_w,
-    const float* ln_d_b, const float* ln_c_w, const float* ln_c_b, float ln_eps, int batch, int dim,
-    int proj_h, int proj_w, int n_classes, int sub_protos, int ignore_label, int64_t max_rows,
-    const float* gumbel, int assign_mode, uint64_t seed, void* workspace, float* packed,
-    float* proto_target, void* stream_) {
+struct DenseRows { const float* out_feat; const float* nearest; const float* sim; };
+
+static int proto_ema_accumulate_impl(
+    const float* embedding, const DenseRows* dense, const int64_t* label, const float* prototypes,
+    const float* ln_d_w, const float* ln_d_b, const float* ln_c_w, const float* ln_c_b, float ln_eps,
+    int batch, int dim, int proj_h, int proj_w, int n_classes, int sub_protos, int ignore_label,
+    int64_t max_rows, const float* gumbel, int assign_mode, uint64_t seed, void* workspace,
+    float* packed, float* proto_target, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   const int B = batch, D = dim, C = n_classes, M = sub_protos;
   const long long HWll = (long long)proj_h * proj_w;
@@ -462,14 +502,19 @@ extern "C" int c3d_proto_ema_accumulate(
   C3D_REQUIRE(max_rows > 0 && max_rows <= B * HWll, "max_rows must be in [1, B*H*W]");
   C3D_REQUIRE(assign_mode >= 0 && assign_mode <= 2, "assign_mode must be 0, 1 or 2");
   C3D_REQUIRE(assign_mode != 1 || gumbel, "assign_mode 1 needs the gumbel noise");
-  C3D_REQUIRE(embedding && label && prototypes && ln_d_w && ln_d_b && ln_c_w && ln_c_b &&
-              workspace && packed, "null pointer argument");
+  if (dense) {
+    C3D_REQUIRE(dense->out_feat && dense->nearest && dense->sim && label && workspace && packed,
+                "null pointer argument");
+  } else {
+    C3D_REQUIRE(embedding && label && prototypes && ln_d_w && ln_d_b && ln_c_w && ln_c_b &&
+                workspace && packed, "null pointer argument");
+  }
   C3D_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "workspace must be 256 B aligned");
   const int HW = (int)HWll, K = C * M;
   EmaWs w = carve_ema(workspace, B, C, HW, D, M, max_rows);
   const int nbps = (HW + kTile - 1) / kTile, nblk = B * nbps;
-  int tile_rows, n_tiles; size_t smem;
-  C3D_REQUIRE(ema_rows_config(D, K, &tile_rows, &n_tiles, &smem) == 0,
+  int tile_rows = 0, n_tiles = 0; size_t smem = 0;
+  C3D_REQUIRE(dense || ema_rows_config(D, K, &tile_rows, &n_tiles, &smem) == 0,
               "bank does not fit shared memory tiling (D=%d, K=%d)", D, K);
   int seg_split = 8;
   while (seg_split > 1 && (size_t)seg_split * ((size_t)M * D + M) * sizeof(float) > 200 * 1024) seg_split >>= 1;
@@ -484,21 +529,30 @@ extern "C" int c3d_proto_ema_accumulate(
         (const long long*)label, nullptr, HW, nbps, B, C, ignore_label, w.blk_cnt, w.seg_cnt, w.seg_start,
         w.seg_tidx, w.info); }
   if ((rc = check_launch("split_count_scan_kernel"))) return rc;
-  { KernelTimer kt__("split_scatter_kernel", stream); split_scatter_kernel<true, false><<<split_grid(nblk) + 16, 256, 0, stream>>>(
+  const int bank_ctas = dense ? 0 : 16;   // extra CTAs L2-normalise the bank rows (:502)
+  { KernelTimer kt__("split_scatter_kernel", stream); split_scatter_kernel<true, false><<<split_grid(nblk) + bank_ctas, 256, 0, stream>>>(
       (const long long*)label, nullptr, nullptr, HW, nbps, nblk, B, C, ignore_label, w.blk_cnt,
-      w.seg_start, w.pix_list, w.cls_list, nullptr, nullptr, prototypes, K, D, w.bank_n, split_grid(nblk)); }
+      w.seg_start, w.pix_list, w.cls_list, nullptr, nullptr, prototypes, dense ? 0 : K, D, w.bank_n, split_grid(nblk)); }
   if ((rc = check_launch("split_scatter_kernel"))) return rc;
 
-  EmaRowsParams p{};
-  p.emb = embedding; p.bank_n = w.bank_n; p.ln_d_w = ln_d_w; p.ln_d_b = ln_d_b;
-  p.ln_c_w = ln_c_w; p.ln_c_b = ln_c_b; p.pix_list = w.pix_list; p.cls_list = w.cls_list;
-  p.info = w.info; p.feat = w.feat; p.simq = w.simq; p.maskv = w.maskv;
-  p.HW = HW; p.D = D; p.M = M; p.C = C; p.K = K; p.tile_rows = tile_rows; p.n_tiles = n_tiles;
-  p.max_rows = (int)max_rows; p.eps = ln_eps;
-  C3D_CUDA(cudaFuncSetAttribute(ema_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)smem));
-  { KernelTimer kt__("ema_rows_kernel", stream); ema_rows_kernel<<<kNumSMs, kEmaWarps * 32, smem, stream>>>(p); }
-  if ((rc = check_launch("ema_rows_kernel"))) return rc;
+  if (dense) {
+    KernelTimer kt__("ema_rows_dense_kernel", stream);
+    ema_rows_dense_kernel<<<kNumSMs * 2, 256, 0, stream>>>(dense->out_feat, dense->nearest, dense->sim,
+                                                           w.pix_list, w.cls_list, w.info, w.feat, w.simq,
+                                                           w.maskv, HW, D, M, C, (int)max_rows);
+    if ((rc = check_launch("ema_rows_dense_kernel"))) return rc;
+  } else {
+    EmaRowsParams p{};
+    p.emb = embedding; p.bank_n = w.bank_n; p.ln_d_w = ln_d_w; p.ln_d_b = ln_d_b;
+    p.ln_c_w = ln_c_w; p.ln_c_b = ln_c_b; p.pix_list = w.pix_list; p.cls_list = w.cls_list;
+    p.info = w.info; p.feat = w.feat; p.simq = w.simq; p.maskv = w.maskv;
+    p.HW = HW; p.D = D; p.M = M; p.C = C; p.K = K; p.tile_rows = tile_rows; p.n_tiles = n_tiles;
+    p.max_rows = (int)max_rows; p.eps = ln_eps;
+    C3D_CUDA(cudaFuncSetAttribute(ema_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem));
+    { KernelTimer kt__("ema_rows_kernel", stream); ema_rows_kernel<<<kNumSMs, kEmaWarps * 32, smem, stream>>>(p); }
+    if ((rc = check_launch("ema_rows_kernel"))) return rc;
+  }
   C3D_CUDA(cudaFuncSetAttribute(ema_sinkhorn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 kSinkSmemFloats * 4));
   { KernelTimer kt__("ema_sinkhorn_kernel", stream); ema_sinkhorn_kernel<<<C, kSinkWarps * 32, kSinkSmemFloats * 4, stream>>>(w.seg_cnt, w.seg_start, w.pix_list, w.info, B, M,
@@ -512,6 +566,30 @@ extern "C" int c3d_proto_ema_accumulate(
                                                   ignore_label, (int)max_rows, seg_split, w.feat, w.maskv,
                                                   w.sub, packed); }
   return check_launch("ema_segsum_kernel");
+}
+
+extern "C" int c3d_proto_ema_accumulate(
+    const float* embedding, const int64_t* label, const float* prototypes, const float* ln_d_w,
+    const float* ln_d_b, const float* ln_c_w, const float* ln_c_b, float ln_eps, int batch, int dim,
+    int proj_h, int proj_w, int n_classes, int sub_protos, int ignore_label, int64_t max_rows,
+    const float* gumbel, int assign_mode, uint64_t seed, void* workspace, float* packed,
+    float* proto_target, void* stream) {
+  return proto_ema_accumulate_impl(embedding, nullptr, label, prototypes, ln_d_w, ln_d_b, ln_c_w, ln_c_b,
+                                   ln_eps, batch, dim, proj_h, proj_w, n_classes, sub_protos,
+                                   ignore_label, max_rows, gumbel, assign_mode, seed, workspace, packed,
+                                   proto_target, stream);
+}
+
+extern "C" int c3d_proto_ema_accumulate_dense(
+    const float* out_feat, const float* nearest, const int64_t* label, const float* feat_proto_sim,
+    int batch, int dim, int proj_h, int proj_w, int n_classes, int sub_protos, int ignore_label,
+    int64_t max_rows, const float* gumbel, int assign_mode, uint64_t seed, void* workspace,
+    float* packed, float* proto_target, void* stream) {
+  DenseRows d{out_feat, nearest, feat_proto_sim};
+  return proto_ema_accumulate_impl(nullptr, &d, label, nullptr, nullptr, nullptr, nullptr, nullptr, 0.f,
+                                   batch, dim, proj_h, proj_w, n_classes, sub_protos, ignore_label,
+                                   max_rows, gumbel, assign_mode, seed, workspace, packed, proto_target,
+                                   stream);
 }
 
 extern "C" int c3d_proto_ema_apply(const float* prototypes_in, const float* packed, int n_classes,

@@ -91,6 +91,20 @@ static LossWs carve(void* base, int B, int C, int HW, int D, int M, int A) {
   return w;
 }
 
+// bank rows: F.normalize(x, p=2, dim=-1), eps 1e-12; one warp per row
+__global__ void __launch_bounds__(256)
+bank_normalise_kernel(const float* __restrict__ src_rows, int rows, int D, float* __restrict__ dst_rows) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k = blockIdx.x * 8 + warp;
+  if (k >= rows) return;
+  const float* src = src_rows + (size_t)k * D;
+  float s = 0.f;
+  for (int d = lane; d < D; d += 32) { float v = src[d]; s += v * v; }
+  s = warp_sum(s);
+  const float inv = 1.0f / fmaxf(sqrtf(s), 1e-12f);
+  for (int d = lane; d < D; d += 32) dst_rows[(size_t)k * D + d] = src[d] * inv;
+}
+
 // ---------------------------------------------------------------- K4 -------
 __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
 #pragma unroll
@@ -930,12 +944,11 @@ static int proto_loss_forward_impl(
         (const long long*)labels, keep_mask, HW, nbps, B, C, ignore_label, w.blk_cnt, w.seg_cnt, w.seg_start,
         w.seg_tidx, w.info); }
   if ((rc = check_launch("split_count_scan_kernel"))) return rc;
-  const int bank_blocks = 16;
   { KernelTimer kt__("split_scatter_kernel", stream);
-    split_scatter_kernel<false, true><<<split_grid(nblk) + bank_blocks, 256, 0, stream>>>(
+    split_scatter_kernel<false, true><<<split_grid(nblk), 256, 0, stream>>>(
         (const long long*)labels, keep_mask, probs, HW, nbps, nblk, B, C, ignore_label, w.blk_cnt,
-        w.seg_start, w.pix_list, w.cls_list, w.w_list, w.cnt_list, proto_queue + (size_t)M * D,
-        (C - 1) * M, D, w.bank_n, split_grid(nblk)); }
+        w.seg_start, w.pix_list, w.cls_list, w.w_list, w.cnt_list, nullptr, 0, D, nullptr,
+        split_grid(nblk)); }
   if ((rc = check_launch("split_scatter_kernel"))) return rc;
   { KernelTimer kt__("loss_sample_kernel", stream);
     loss_sample_kernel<<<B * C, 256, 0, stream>>>(w.seg_cnt, w.seg_start, w.seg_tidx, w.pix_list,
@@ -945,6 +958,13 @@ static int proto_loss_forward_impl(
   if ((rc = check_launch("loss_sample_kernel"))) return rc;
   }
   if (!(phases & 2)) return C3D_OK;
+
+  // F.normalize of the bank rows of classes 1..C-1 (:167).  Part of phase 2: the bank may be
+  // written between the phases (the EMA update precedes the loss in a training step,
+  // salsanext_proto.py:520-527 -> trainer.py:675-686).
+  { KernelTimer kt__("bank_normalise_kernel", stream);
+    bank_normalise_kernel<<<(Kc + 7) / 8, 256, 0, stream>>>(proto_queue + (size_t)M * D, Kc, D, w.bank_n); }
+  if ((rc = check_launch("bank_normalise_kernel"))) return rc;
 
   RowsParams p{};
   p.feats = feats; p.bank_n = w.bank_n; p.pix_list = w.pix_list; p.cls_list = w.cls_list;

@@ -1,11 +1,21 @@
 """Multi-GPU plumbing of the hot path: scans shard across ranks, and the only
 exchange is one all-reduce of the packed prototype sums and counts.
 
-The reference's only hot-path collective is `dist.all_reduce(protos / world)`
-after per-rank EMAs (salsanext_proto.py:397-400).  Here ranks sum the
-[K*D sums | K counts] payload BEFORE the EMA, so every rank applies the identical
-update and the result equals a single-process run on the concatenated batch.
-Works with any torch.distributed backend (NCCL on the GPUs, gloo in CPU tests).
+Two synchronisation rules (`sync`):
+
+* "sum" (default, BASELINE.json north_star): ranks sum the [K*D sums | K counts] payload
+  BEFORE the EMA, so every rank applies one identical update and the banks stay bit-identical.
+  Guarantee, exactly: the result equals `apply(sum_r accumulate(shard_r))`, i.e. one EMA from
+  the summed per-rank sums.  The per-rank sums themselves are rank-local: the Sinkhorn
+  assignment normalises over the rows of a class ON THAT RANK (the reference's
+  `distributed_sinkhorn` communicates nothing either, sinkhorn.py:5-33), so the result is NOT
+  that of a single process running the concatenated batch.
+* "average" (the reference's rule, salsanext_proto.py:397-400): every rank applies its own EMA
+  from its local sums, then the banks are averaged, `all_reduce(protos / world)`, and not
+  re-normalised.
+
+On one rank both coincide with the reference.  Works with any torch.distributed backend
+(NCCL on the GPUs, gloo in CPU tests).
 """
 import torch
 import torch.distributed as dist
@@ -37,13 +47,28 @@ def allreduce_packed(packed: torch.Tensor, group=None, async_op=False):
 
 def prototype_update(embedding, label, prototypes, ln_d_w, ln_d_b, ln_c_w, ln_c_b, momentum,
                      ignore_label=0, gumbel=None, assign_mode=None, seed=None, max_rows=None,
-                     want_target=False, group=None, workspace=None, packed=None, out=None):
-    """accumulate -> all-reduce -> apply.  Returns (new prototypes, EmaAccum)."""
+                     want_target=False, group=None, workspace=None, packed=None, out=None, sync="sum"):
+    """accumulate -> all-reduce -> apply ("sum"), or accumulate -> apply -> average ("average").
+    Returns (new prototypes, EmaAccum)."""
     from . import ops
     acc = ops.proto_ema_accumulate(embedding, label, prototypes, ln_d_w, ln_d_b, ln_c_w, ln_c_b,
                                    ignore_label=ignore_label, gumbel=gumbel, assign_mode=assign_mode,
                                    seed=seed, max_rows=max_rows, want_target=want_target,
                                    workspace=workspace, packed=packed)
-    allreduce_packed(acc.packed, group)
+    return finish_update(prototypes, acc, momentum, ignore_label, group, out, sync), acc
+
+
+def finish_update(prototypes, acc, momentum, ignore_label=0, group=None, out=None, sync="sum"):
+    """The part of the update after the local accumulation (see the module docstring)."""
+    from . import ops
+    if sync == "sum":
+        allreduce_packed(acc.packed, group)
+        return ops.proto_ema_apply(prototypes, acc.packed, momentum, ignore_label, out=out)
+    if sync != "average":
+        raise ValueError("sync must be 'sum' or 'average'")
     new = ops.proto_ema_apply(prototypes, acc.packed, momentum, ignore_label, out=out)
-    return new, acc
+    n = world(group)[1]
+    if n > 1:                                   # salsanext_proto.py:397-400
+        new.div_(n)
+        dist.all_reduce(new, op=dist.ReduceOp.SUM, group=group)
+    return new

@@ -13,7 +13,9 @@ def install(pc_processor=None, trainer_cls=None):
         import pc_processor, coarse3d_b200
         coarse3d_b200.install(pc_processor)
 
-    Everything else in `pc_processor` is left untouched.  Pass the task's `Trainer` class
+    Rebound: `RangeProjection`, `KNN`, `ContrastMEMLoss`, `Lovasz_softmax`, and the
+    `prototype_learning` method + `momentum_update` helper of SalsaNextProto / RangeNetProto /
+    SqueezeSegV3Proto.  Everything else in `pc_processor` is left untouched.  Pass the task's `Trainer` class
     (tasks/weak_segmentation/trainer.py:17) as `trainer_cls` to also replace its
     `entropy_based_selection` method (trainer.py:447-518) with the batched kernel.
     """
@@ -34,6 +36,19 @@ def install(pc_processor=None, trainer_cls=None):
         pc_processor.loss.lovasz_softmax.Lovasz_softmax = Lovasz_softmax
         pc_processor.loss.lovasz_softmax.lovasz_softmax = lovasz_softmax
     pc_processor.loss.Lovasz_softmax = Lovasz_softmax
+    # a3: the EMA prototype update is a METHOD of the three *Proto models and a module-level
+    # helper of their files (salsanext_proto.py:19-31,337-402; rangenet_proto.py:460-567;
+    # squeezesegv3_Proto.py:253-351): rebind both, on every model file that is present.
+    from .pc_processor.models.prototype import momentum_update, prototype_learning
+    models = getattr(pc_processor, "models", None)
+    for mod_name, cls_name in (("salsanext_proto", "SalsaNextProto"), ("rangenet_proto", "RangeNetProto"),
+                               ("squeezesegv3_Proto", "SqueezeSegV3Proto")):
+        mod = getattr(models, mod_name, None) if models is not None else None
+        cls = getattr(mod, cls_name, None) if mod is not None else None
+        if cls is None:
+            continue
+        cls.prototype_learning = prototype_learning
+        mod.momentum_update = momentum_update
     if trainer_cls is not None:
         from .trainer_ops import entropy_based_selection
         trainer_cls.entropy_based_selection = entropy_based_selection

@@ -75,7 +75,8 @@ class ProjectionBuffers:
         self.uproj_x_idx = torch.empty((total_points,), dtype=i32, device=device)
         self.uproj_y_idx = torch.empty((total_points,), dtype=i32, device=device)
         self.uproj_depth = torch.empty((total_points,), dtype=f32, device=device)
-        self.flags = torch.zeros((1,), dtype=i32, device=device)
+        self.flags = torch.zeros((1,), dtype=i32, device=device)   # sticky: bit 0 stays set once a
+        # call saw a NaN pixel coordinate (depth == 0); `flags.zero_()` re-arms it
         nbytes = lib.c3d_project_workspace_bytes(batch, proj_h, proj_w)
         self.workspace = torch.empty((nbytes,), dtype=torch.uint8, device=device)
         self.clean = False  # True once a call has left the z-buffer reset
@@ -102,12 +103,13 @@ def project_batch(points, offsets, fov: Fov, proj_h, proj_w, depth=None,
         b = ProjectionBuffers(batch, total, c_in, proj_h, proj_w, points.device)
     elif (b.batch, b.total, b.c_in, b.H, b.W) != (batch, total, c_in, proj_h, proj_w):
         raise ValueError("ProjectionBuffers shape mismatch")
+    was_clean, b.clean = b.clean, False   # a failed call may leave a dirty z-buffer
     check(lib.c3d_project_batch(
         _p(points), c_in, _p(offsets), batch, total, _p(depth),
         fov.abs_fov_left, fov.fov_hori, fov.abs_fov_down, fov.fov_vert, proj_h, proj_w,
         _p(b.proj_range), _p(b.proj_pointcloud), _p(b.proj_idx), _p(b.proj_mask),
         _p(b.uproj_x_idx), _p(b.uproj_y_idx), _p(b.uproj_depth), _p(b.workspace),
-        1 if b.clean else 0, _p(b.flags), _stream()))
+        1 if was_clean else 0, _p(b.flags), _stream()))
     b.clean = True
     return Projection(b.proj_pointcloud, b.proj_range, b.proj_idx, b.proj_mask,
                       b.uproj_x_idx, b.uproj_y_idx, b.uproj_depth, b.flags)
@@ -151,16 +153,19 @@ def project_assemble_batch(points, offsets, fov: Fov, proj_h, proj_w, sem_label=
     b = buffers
     if b is None:
         b = ProjectionBuffers(batch, total, 4, proj_h, proj_w, points.device)
+    elif (b.batch, b.total, b.c_in, b.H, b.W) != (batch, total, 4, proj_h, proj_w):
+        raise ValueError("ProjectionBuffers shape mismatch")
     dev = points.device
     feature = torch.empty((batch, 5, proj_h, proj_w), dtype=torch.float32, device=dev)
     train = torch.empty((batch, proj_h, proj_w), dtype=torch.int64, device=dev) if weak_label is not None else None
     evall = torch.empty((batch, proj_h, proj_w), dtype=torch.int64, device=dev) if sem_label is not None else None
+    was_clean, b.clean = b.clean, False
     check(lib.c3d_project_assemble_batch(
         _p(points), _p(offsets), batch, total, _p(depth), _p(sem_label), _p(weak_label),
         1 if ldt == torch.uint8 else 0, _p(img_mean), _p(img_std), fov.abs_fov_left, fov.fov_hori, fov.abs_fov_down, fov.fov_vert,
         proj_h, proj_w, _p(feature), _p(train), _p(evall), _p(b.proj_range), _p(b.proj_idx),
         _p(b.uproj_x_idx), _p(b.uproj_y_idx), _p(b.uproj_depth), _p(b.workspace),
-        1 if b.clean else 0, _p(b.flags), _stream()))
+        1 if was_clean else 0, _p(b.flags), _stream()))
     b.clean = True
     return Assembled(feature, train, evall, b.proj_range, b.proj_idx, b.uproj_x_idx, b.uproj_y_idx,
                      b.uproj_depth, b.flags)
@@ -398,6 +403,16 @@ def zero_fill(t):
     return t
 
 
+def zero_fill_background(t, mode=0, ctas_per_sm=1, page_bytes=8192, inflight=4):
+    """Zero a contiguous CUDA tensor with the minimal-footprint persistent fill kernel
+    (c3d_zero_fill_background): meant to be launched first, on its own stream, and to run under
+    the other kernels of a step."""
+    _need_cuda(t=t)
+    check(lib.c3d_zero_fill_background(_p(t), t.numel() * t.element_size(), int(mode), int(ctas_per_sm),
+                                       int(page_bytes), int(inflight), _stream()))
+    return t
+
+
 def proto_loss_backward_raw(shape, cfg, n_classes, sub_protos, workspace, grad_out, grad_feats,
                             grad_is_zeroed=False):
     """c3d_proto_loss_backward: writes the dense (B,D,H,W) gradient into grad_feats.
@@ -545,6 +560,46 @@ def proto_ema_accumulate(embedding, label, prototypes, ln_d_w, ln_d_b, ln_c_w, l
         _p(embedding), _p(label), _p(prototypes), _p(ln_d_w), _p(ln_d_b), _p(ln_c_w), _p(ln_c_b),
         float(ln_eps), B, D, H, W, C, M, int(ignore_label), int(max_rows), _p(gumbel),
         int(assign_mode), int(seed), _p(workspace), _p(packed), _p(target), _stream()))
+    return EmaAccum(packed, target, workspace)
+
+
+def proto_ema_accumulate_dense(out_feat, nearest, label, feat_proto_sim, ignore_label=0, gumbel=None,
+                               assign_mode=None, seed=None, max_rows=None, want_target=True,
+                               workspace=None, packed=None) -> EmaAccum:
+    """The accumulation with `prototype_learning`'s own arguments (salsanext_proto.py:337-339):
+    out_feat (n, D), nearest (B, C, H, W), label (n,) or (B, H, W), feat_proto_sim (n, M, C)."""
+    _need_cuda(out_feat=out_feat, nearest=nearest, label=label, feat_proto_sim=feat_proto_sim, gumbel=gumbel)
+    if out_feat.dtype != torch.float32 or nearest.dtype != torch.float32 or feat_proto_sim.dtype != torch.float32:
+        raise ValueError("out_feat / nearest_proto_distance / feat_proto_sim must be float32")
+    if label.dtype != torch.int64:
+        raise ValueError("label must be int64")
+    if nearest.dim() != 4 or out_feat.dim() != 2 or feat_proto_sim.dim() != 3:
+        raise ValueError("expected out_feat (n, D), nearest (B, C, H, W), feat_proto_sim (n, M, C)")
+    B, C, H, W = nearest.shape
+    n, D = out_feat.shape
+    M = feat_proto_sim.shape[1]
+    if n != B * H * W or feat_proto_sim.shape != (n, M, C) or label.numel() != n:
+        raise ValueError("shape mismatch between out_feat / nearest / label / feat_proto_sim")
+    if assign_mode is None:
+        assign_mode = ASSIGN_GUMBEL_INJECTED if gumbel is not None else ASSIGN_GUMBEL_DEVICE
+    if max_rows is None:
+        max_rows = min(n, 1 << 17)
+    if gumbel is not None and (gumbel.dtype != torch.float32 or gumbel.dim() != 2 or gumbel.shape[1] != M):
+        raise ValueError("gumbel must be (rows, M) float32 in (class, pixel) row order")
+    if workspace is None:
+        nb = lib.c3d_proto_ema_workspace_bytes(B, C, H * W, D, M, max_rows)
+        if nb == 0:
+            raise ValueError("bad EMA shape")
+        workspace = torch.empty((nb,), dtype=torch.uint8, device=out_feat.device)
+    if packed is None:
+        packed = torch.empty((C * M * D + C * M,), dtype=torch.float32, device=out_feat.device)
+    target = torch.empty((n,), dtype=torch.float32, device=out_feat.device) if want_target else None
+    if seed is None:
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if assign_mode == ASSIGN_GUMBEL_DEVICE else 0
+    check(lib.c3d_proto_ema_accumulate_dense(
+        _p(out_feat), _p(nearest), _p(label), _p(feat_proto_sim), B, D, H, W, C, M, int(ignore_label),
+        int(max_rows), _p(gumbel), int(assign_mode), int(seed), _p(workspace), _p(packed), _p(target),
+        _stream()))
     return EmaAccum(packed, target, workspace)
 
 

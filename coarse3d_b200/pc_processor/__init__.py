@@ -6,9 +6,11 @@ the same names, signatures and error behaviour as the reference:
     pc_processor.dataset.preprocess.projection.RangeProjection
     pc_processor.postproc.knn.KNN
     pc_processor.loss.contrast_pixel_loss.ContrastMEMLoss
-    pc_processor.models.prototype.{momentum_update, PrototypeBank.prototype_learning}
+    pc_processor.models.prototype.{momentum_update, prototype_learning, PrototypeBank}
+        (`prototype_learning` is the method `install()` binds onto SalsaNextProto /
+        RangeNetProto / SqueezeSegV3Proto; `PrototypeBank` carries it too)
 
 `coarse3d_b200.install()` swaps them into the real `pc_processor` package so
 that tasks/weak_segmentation runs unchanged.
 """
-from . import dataset, loss, postproc  # noqa: F401
+from . import dataset, loss, models, postproc  # noqa: F401

@@ -7,8 +7,10 @@ loss with autograd to `probas`, the same NaN assertion.  The arithmetic runs in
 
 Differences a caller can observe:
   * ties between equal errors rank by ascending pixel index (torch.sort is unstable);
-  * the rank pass is quadratic in the number of valid pixels, so at most 32768 pixels may
-    carry a label (weak labels: ~1e3 per batch) -- more raises ValueError in strict mode;
+  * at most 32768 pixels may carry a label (weak labels: ~1e3 per batch).  More is never
+    silently wrong: the loss comes back NaN, so the NaN assertion below (the reference's own,
+    :178) fires; `strict=True` raises a ValueError with the pixel count instead (one extra
+    host read);
   * with no valid pixel the reference returns an empty tensor (and the trainer skips such
     batches, trainer.py:586-589); here the loss is 0 with zero gradient;
   * `classes` may be "present" (default) or "all", not a list.

@@ -1,1 +1,1 @@
-from .prototype import PrototypeBank, l2_normalize, momentum_update  # noqa: F401
+from .prototype import PrototypeBank, l2_normalize, momentum_update, prototype_learning  # noqa: F401

@@ -74,7 +74,6 @@ class HotPathStep:
         g = torch.Generator(device=self.device).manual_seed(seed0 + 7)
         self.protos = torch.nn.functional.normalize(
             torch.randn((C, sub_protos, dim), device=self.device, generator=g), dim=-1)
-        self.protos_next = torch.empty_like(self.protos)
         self.ln_d = (torch.ones(dim, device=self.device), torch.zeros(dim, device=self.device))
         self.ln_c = (torch.ones(C, device=self.device), torch.zeros(C, device=self.device))
         self.loss_ws = ops.proto_loss_workspace(batch, C, H * W, dim, sub_protos, num_anchor, self.device)
@@ -92,12 +91,14 @@ class HotPathStep:
         self.concurrent = concurrent
         import os as _os
         self.schedule = _os.environ.get("C3D_SCHEDULE", "fill_in_knn")
+        # fill daemon (schedule "fill_daemon"): mode, CTAs per SM, zero-page bytes, copies in flight
+        self.daemon = tuple(int(v) for v in _os.environ.get("C3D_DAEMON", "0,1,8192,4").split(","))
         # ablation switch for tools/ablate.py: which chains run (default: all)
         self.parts = set(parts) if parts else {"proj", "knn", "fill", "loss", "ema"}
         # Priorities: the latency-bound chains (loss, EMA) high, so their small CTAs
         # are placed first whenever the short CTAs of the fill / KNN retire.
         lo, hi = 0, -1
-        fill_prio = hi if _os.environ.get("C3D_FILL_PRIO", "0") == "1" else lo
+        fill_prio = hi if (_os.environ.get("C3D_FILL_PRIO", "0") == "1" or self.schedule == "fill_daemon") else lo
         self.side = [torch.cuda.Stream(self.device, priority=fill_prio),   # fill
                      torch.cuda.Stream(self.device, priority=lo),   # projection -> KNN
                      torch.cuda.Stream(self.device, priority=hi),   # EMA chain
@@ -131,12 +132,12 @@ class HotPathStep:
         fused = self.schedule == "fill_in_knn" and {"knn", "fill"} <= self.parts
         if not self.concurrent:
             pr = ops.project_batch(s.points, s.offsets, self.fov, H, W, buffers=b)
+            self._ema(s, seed)            # the bank is updated in the model forward, before the loss
             self._loss_fwd(s, seed)
             if fused:
                 self._knn(s, pr, C, cofill=self.grad)
             ops.proto_loss_backward_raw(s.feats.shape, self.cfg, C, self.M, self.loss_ws, self.grad_out,
                                         self.grad, grad_is_zeroed=fused)
-            self._ema(s, seed)
             if not fused:
                 self._knn(s, pr, C)
             return pr
@@ -173,6 +174,19 @@ class HotPathStep:
                 self.ev_proj.record(st_proj)
             st_fill.wait_event(self.ev_proj)
             self.ev_fill.record(st_fill)
+        elif sched == "fill_daemon":
+            # The fill as a minimal-footprint persistent kernel (one warp per SM), launched first
+            # and running UNDER everything else of the step.
+            with torch.cuda.stream(st_fill):
+                if "fill" in P:
+                    ops.zero_fill_background(self.grad, *self.daemon)
+                self.ev_fill.record(st_fill)
+            with torch.cuda.stream(st_proj):
+                if "proj" in P:
+                    pr = ops.project_batch(s.points, s.offsets, self.fov, H, W, buffers=b)
+                if "knn" in P:
+                    self._knn(s, pr if pr is not None else self._last_proj(b), C)
+                self.ev_proj.record(st_proj)
         elif sched == "fill_first":
             # fill (optionally throttled, C3D_FILL_PERSISTENT) together with the latency-bound
             # loss / EMA chains from t = 0; projection -> KNN afterwards
@@ -209,8 +223,14 @@ class HotPathStep:
                 self._ema(s, seed)
             self.ev_ema.record(st_ema)
         with torch.cuda.stream(st_loss):
+            # The selection phase (label split, anchor sampling) does not read the bank and runs
+            # next to the EMA chain; the rows phase reads the bank the EMA has just updated
+            # (salsanext_proto.py:520-527 runs inside model.forward, trainer.py:675-686 after it).
+            if "loss" in P and not hold:
+                self._loss_fwd(s, seed, phases=1)
+            st_loss.wait_event(self.ev_ema)
             if "loss" in P:
-                self._loss_fwd(s, seed, phases=2 if hold else 3)
+                self._loss_fwd(s, seed, phases=2)
             st_loss.wait_event(self.ev_fill)
             if "loss" in P:
                 ops.proto_loss_backward_raw(s.feats.shape, self.cfg, C, self.M, self.loss_ws,
@@ -251,12 +271,15 @@ class HotPathStep:
             distributed.prototype_update(
                 s.feats, labels, self.protos, *self.ln_d, *self.ln_c, self.momentum,
                 assign_mode=ops.ASSIGN_GUMBEL_DEVICE, seed=seed, max_rows=self.max_rows, group=self.group,
-                workspace=self.ema_ws, packed=self.packed, out=self.protos_next)
+                workspace=self.ema_ws, packed=self.packed, out=self.protos)
             self.ev_ema.record(st_ema)
         with torch.cuda.stream(st_loss):
             st_loss.wait_event(self.ev_resolved)
             ops.proto_loss_forward_raw(s.feats, s.probs, labels, None, self.protos, self.cfg, None, seed,
-                                       self.loss_ws, self.loss)
+                                       self.loss_ws, self.loss, phases=1)
+            st_loss.wait_event(self.ev_ema)           # the rows phase reads the updated bank
+            ops.proto_loss_forward_raw(s.feats, s.probs, labels, None, self.protos, self.cfg, None, seed,
+                                       self.loss_ws, self.loss, phases=2)
             st_loss.wait_event(self.ev_proj)          # the vote has zero-filled self.grad
             ops.proto_loss_backward_raw(s.feats.shape, self.cfg, C, self.M, self.loss_ws, self.grad_out,
                                         self.grad, grad_is_zeroed=True)
@@ -277,7 +300,7 @@ class HotPathStep:
         distributed.prototype_update(
             s.feats, s.labels, self.protos, *self.ln_d, *self.ln_c, self.momentum,
             assign_mode=ops.ASSIGN_GUMBEL_DEVICE, seed=seed, max_rows=self.max_rows, group=self.group,
-            workspace=self.ema_ws, packed=self.packed, out=self.protos_next)
+            workspace=self.ema_ws, packed=self.packed, out=self.protos)
 
     def _knn(self, s, pr, C, cofill=None):
         b1 = self.knn_split

@@ -295,6 +295,16 @@ int c3d_proto_loss_backward(
 /* The dense-gradient zero fill (128-bit streaming stores) as its own entry point. */
 int c3d_zero_fill(void* dst, size_t nbytes, void* stream);
 
+/* The same fill as a background ("daemon") kernel: one warp per CTA, ctas_per_sm CTAs per
+ * SM, resident for as long as the fill takes, so that it can run UNDER the other kernels of
+ * a step (launch it first, on its own stream) instead of holding every SM slot.
+ * mode 0: one thread per CTA issues cp.async.bulk shared->global copies of a zero page of
+ * page_bytes (multiple of 1024, <= 65536), at most `inflight` (1, 2, 4, 8, 16) copies in
+ * flight per CTA; mode 1: the warp issues 128-bit streaming stores (page_bytes / inflight
+ * ignored).  nbytes must be a multiple of 16. */
+int c3d_zero_fill_background(void* dst, size_t nbytes, int mode, int ctas_per_sm, int page_bytes,
+                             int inflight, void* stream);
+
 /* Synchronous: copies {T, labelled pixels, flags, 0} to host_info4 (host). */
 int c3d_proto_loss_info(const void* workspace, int32_t* host_info4, void* stream);
 
@@ -346,6 +356,18 @@ int c3d_proto_ema_accumulate(
     float* packed,                /* [C*M*D + C*M]                               */
     float* proto_target,          /* [B*H*W] or NULL (:346,390-392)              */
     void* stream);
+
+/* The same accumulation from the DENSE tensors the reference's forward has already built
+ * (salsanext_proto.py:497-510), i.e. with the exact arguments of
+ * `prototype_learning(out_feat, nearest_proto_distance, label, eval_mask, feat_proto_sim)`
+ * (:337-339; eval_mask is unused by the reference): out_feat [n, D] LayerNorm+L2-normalised
+ * rows (n = B*H*W, pixel-major), nearest [B, C, H, W], feat_proto_sim [n, M, C].  Only the
+ * labelled rows are read.  Workspace, packed, proto_target, assign_mode as above. */
+int c3d_proto_ema_accumulate_dense(
+    const float* out_feat, const float* nearest, const int64_t* label, const float* feat_proto_sim,
+    int batch, int dim, int proj_h, int proj_w, int n_classes, int sub_protos, int ignore_label,
+    int64_t max_rows, const float* gumbel, int assign_mode, uint64_t seed, void* workspace,
+    float* packed, float* proto_target, void* stream);
 
 int c3d_proto_ema_apply(
     const float* prototypes_in,   /* [C, M, D]                                   */

@@ -98,6 +98,12 @@ def test_no_valid_pixel_and_overflow(cuda_device):
     big_p, big_l = _make(1, 3, 256, 256, 1.0, 2)
     with pytest.raises(ValueError):
         Lovasz_softmax(ignore=0, strict=True)(big_p.cuda(), (big_l * 0 + 1).cuda())
+    # ... and never silently wrong in the default mode: the loss is NaN, so the module's own
+    # NaN assertion (lovasz_softmax.py:178) fires
+    with pytest.raises(AssertionError):
+        Lovasz_softmax(ignore=0)(big_p.cuda(), (big_l * 0 + 1).cuda())
+    raw, _ = ops.lovasz_softmax(big_p.cuda(), (big_l * 0 + 1).cuda(), ignore=0)
+    assert torch.isnan(raw)
     with pytest.raises(ValueError):
         ops.lovasz_softmax(big_p.cuda(), big_l.cuda(), ignore=0, max_valid=1 << 20)
 

@@ -17,13 +17,20 @@ def _step(monkeypatch, schedule, concurrent=True, **kw):
 
 def _outputs(step):
     torch.cuda.synchronize()
-    return (step.loss.clone(), step.grad.clone(), step.protos_next.clone(), step.knn_out.clone())
+    return (step.loss.clone(), step.grad.clone(), step.protos.clone(), step.knn_out.clone())
 
 
 def test_schedules_agree(cuda_device, monkeypatch):
     ref = None
     for schedule, concurrent in [("fill_after_projection", False), ("fill_after_projection", True),
-                                 ("fill_in_knn", False), ("fill_in_knn", True), ("fill_first", True)]:
+                                 ("fill_in_knn", False), ("fill_in_knn", True), ("fill_first", True),
+                                 ("fill_daemon", True), ("fill_daemon:1,2,0,0", True),
+                                 ("fill_daemon:0,1,4096,1", True)]:
+        schedule, _, daemon = schedule.partition(":")
+        if daemon:
+            monkeypatch.setenv("C3D_DAEMON", daemon)
+        else:
+            monkeypatch.delenv("C3D_DAEMON", raising=False)
         step = _step(monkeypatch, schedule, concurrent)
         step.grad.fill_(7.0)                       # the step must overwrite every element
         step.run(0, seed=5)
@@ -67,10 +74,12 @@ def test_two_launch_knn_matches(cuda_device, monkeypatch):
 
 def test_graph_replay_matches_eager(cuda_device, monkeypatch):
     step = _step(monkeypatch, "fill_in_knn")
+    bank0 = step.protos.clone()
     step.run(1, seed=0)
     want = _outputs(step)
     assert step.capture(), getattr(step, "capture_error", "")
     step.grad.fill_(3.0)
+    step.protos.copy_(bank0)                      # the bank evolves in place, step after step
     step.step(1)
     for a, b in zip(_outputs(step), want):
         assert torch.equal(a, b)
@@ -92,3 +101,22 @@ def test_run_inputs_equals_resident_step(cuda_device, monkeypatch):
     assert torch.equal(asm.train_label, s.labels)
     for a, b in zip(got, want):
         assert torch.equal(a, b)
+
+
+def test_loss_reads_the_updated_bank(cuda_device, monkeypatch):
+    """The EMA update precedes the loss (salsanext_proto.py:520-527 inside model.forward,
+    trainer.py:675-686 after it): the step's loss must equal the loss of the UPDATED bank."""
+    from coarse3d_b200 import ops
+    step = _step(monkeypatch, "fill_in_knn")
+    bank0 = step.protos.clone()
+    step.run(0, seed=5)
+    loss, _, bank1, _ = _outputs(step)
+    assert not torch.equal(bank0, bank1)
+    s = step.sets[0]
+    ws = ops.proto_loss_workspace(step.batch, step.shape.n_classes, step.shape.proj_h * step.shape.proj_w,
+                                  step.dim, step.M, step.cfg.num_anchor, "cuda")
+    out = torch.zeros((), device="cuda")
+    ops.proto_loss_forward_raw(s.feats, s.probs, s.labels, s.keep_mask, bank1, step.cfg, None, 5, ws, out)
+    assert torch.equal(out, loss)
+    ops.proto_loss_forward_raw(s.feats, s.probs, s.labels, s.keep_mask, bank0, step.cfg, None, 5, ws, out)
+    assert not torch.equal(out, loss)

@@ -160,3 +160,17 @@ def test_full_size_config2(cuda_device):
     assert torch.equal(acc.packed[K * D:].cpu().view(C, M), counts) and counts.sum() > 100
     assert (got.cpu() - want).abs().max() <= ATOL
     assert torch.allclose(got.norm(dim=-1), torch.ones(C, M, device="cuda"), atol=1e-5)
+
+
+def test_bank_surfaces_overflow_without_a_stall(cuda_device):
+    """More labelled pixels than max_rows: the update is skipped (flag 16); the bank examines the
+    flags of an update asynchronously and raises at the next call / on check_flags()."""
+    from coarse3d_b200.pc_processor.models import PrototypeBank
+    emb, label, protos0, ln = _problem(2, 32, 8, 64, 6, 4, 0.5, 9)
+    bank = PrototypeBank(6, 4, 32, max_rows=4).cuda()
+    bank.update(emb.cuda(), label.cuda())
+    with pytest.raises(RuntimeError):
+        bank.check_flags()
+    ok = PrototypeBank(6, 4, 32).cuda()
+    ok.update(emb.cuda(), label.cuda())
+    ok.check_flags()

@@ -1,8 +1,9 @@
 """GPU parity: c3d_proto_loss_forward/backward (through the reference-shaped
 ContrastMEMLoss module) against the CPU oracle and the reference golden vectors.
 
-Tolerances (BASELINE.json north_star): loss <= 1e-5 relative; gradients <= 1e-4
-relative, measured as max|diff| / max|ref|."""
+Tolerances (BASELINE.json north_star): loss <= 1e-5 relative; gradients <= 1e-4 relative,
+ELEMENT-WISE: |diff| <= 1e-4 * |ref| + 5e-6 * max|ref| (the absolute term covers elements that
+are small only through cancellation of much larger terms)."""
 import numpy as np
 import pytest
 import torch
@@ -17,7 +18,10 @@ LOSS_RTOL, GRAD_RTOL = 1e-5, 1e-4
 
 
 def _rel(a, b):
-    return float((a - b).abs().max() / b.abs().max())
+    """Largest element-wise violation of |a-b| <= GRAD_RTOL*|b| + 5e-6*max|b|, scaled so that
+    a value <= GRAD_RTOL passes (keeps the call sites' `_rel(..) <= GRAD_RTOL` form)."""
+    bound = GRAD_RTOL * b.abs() + 5e-6 * b.abs().max()
+    return float(((a - b).abs() / bound).max()) * GRAD_RTOL
 
 
 def _module(A, temperature=0.07, **kw):
