@@ -363,7 +363,7 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         block_ms.append(float(ms.item()))
         if len(block_ms) == 1:   # every rank derives the same block count from the reduced time
-            n_blocks = int(min(200, max(1, math.ceil(args.min_seconds * 1e3 / max(block_ms[0], 1e-3)))))
+            n_blocks = int(min(5000, max(1, math.ceil(args.min_seconds * 1e3 / max(block_ms[0], 1e-3)))))
         if len(block_ms) >= n_blocks:
             break
     t_region1 = time.perf_counter()

@@ -61,6 +61,8 @@ def _load():
         "c3d_proto_loss_backward": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P,
                                             c_int, P]),
         "c3d_zero_fill": (c_int, [P, c_size_t, P]),
+        "c3d_zero_fill_daemon": (c_int, [P, c_size_t, c_int, c_int, c_int, c_int, P, P, P]),
+        "c3d_delay": (c_int, [c_uint64, P]),
         "c3d_zero_fill_background": (c_int, [P, c_size_t, c_int, c_int, c_int, c_int, P]),
         "c3d_proto_loss_info": (c_int, [P, P, P]),
         "c3d_proto_loss_rows": (c_int, [P, c_int, c_int, c_int, c_int, c_int, c_int, c_int64, P, P, P, P]),

@@ -120,5 +120,5 @@ extern "C" int c3d_version(void) { return 100; }
 extern "C" const char* c3d_last_error(void) { return c3d::t_error; }
 extern "C" long long c3d_launch_count(void) { return c3d::g_launches.load(); }
 extern "C" int c3d_set_concurrent_hint(int on) {
-  return c3d::g_concurrent_hint.exchange(on ? 1 : 0);
+  return c3d::g_concurrent_hint.exchange(on < 0 ? 0 : on);
 }

@@ -7,7 +7,7 @@
 // in Python; only labelled pixels influence the update, so everything here runs
 // on the labelled rows only:
 //
-//   E1 split_count/scan/scatter (labelsplit.cuh, class-major): labelled pixels ->
+//   E1 split_count / split_place (labelsplit.cuh): labelled pixels ->
 //      rows sorted by (class, global pixel) = the reference's `label == id_c` order
 //   E2 ema_rows      one warp per row: strided NCHW gather, LayerNorm_D, L2 norm,
 //                    similarity against all C*M normalised prototypes (bank in
@@ -31,13 +31,7 @@ constexpr int kMaxSub = 32;  // sub-prototypes per class handled in registers
 enum EmaFlag { kEmaNoRows = 1, kEmaBadLabel = 8, kEmaOverflow = 16 };
 
 struct EmaWs {
-  int32_t* info;
-  int32_t* blk_cnt;
-  int32_t* seg_cnt;
-  int32_t* seg_start;
-  int32_t* seg_tidx;
-  int32_t* pix_list;   // [B*HW]
-  int32_t* cls_list;   // [B*HW]
+  SplitWs s;           // labelled-pixel slots, class-major (labelsplit.cuh)
   float* bank_n;       // [C*M*D]
   float* feat;         // [max_rows * D]
   float* simq;         // [max_rows * M]
@@ -46,21 +40,11 @@ struct EmaWs {
   size_t bytes;
 };
 
-static size_t align_up_e(size_t x) { return (x + 255) & ~(size_t)255; }
-
 static EmaWs carve_ema(void* base, int B, int C, int HW, int D, int M, long long max_rows) {
   EmaWs w;
-  const size_t cap = (size_t)B * HW;
-  const size_t nblk = (size_t)B * ((HW + kTile - 1) / kTile);
   size_t off = 0;
-  auto take = [&](size_t n) { size_t o = off; off += align_up_e(n); return (char*)base + o; };
-  w.info = (int32_t*)take((size_t)(8 + B) * 4);  // [8 + B]: counters/flags + per-scan tickets
-  w.blk_cnt = (int32_t*)take(nblk * C * 4);
-  w.seg_cnt = (int32_t*)take((size_t)B * C * 4);
-  w.seg_start = (int32_t*)take((size_t)B * C * 4);
-  w.seg_tidx = (int32_t*)take((size_t)B * C * 4);
-  w.pix_list = (int32_t*)take(cap * 4);
-  w.cls_list = (int32_t*)take(cap * 4);
+  w.s = carve_split(base, &off, B, C, HW);
+  auto take = [&](size_t n) { size_t o = off; off += split_align(n); return (char*)base + o; };
   w.bank_n = (float*)take((size_t)C * M * D * 4);
   w.feat = (float*)take((size_t)max_rows * D * 4);
   w.simq = (float*)take((size_t)max_rows * M * 4);
@@ -68,6 +52,20 @@ static EmaWs carve_ema(void* base, int B, int C, int HW, int D, int M, long long
   w.sub = (int32_t*)take((size_t)max_rows * 4);
   w.bytes = off;
   return w;
+}
+
+// bank rows: l2_normalize (salsanext_proto.py:502), one warp per row
+__global__ void __launch_bounds__(256)
+ema_bank_normalise_kernel(const float* __restrict__ src_rows, int rows, int D, float* __restrict__ dst_rows) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k = blockIdx.x * 8 + warp;
+  if (k >= rows) return;
+  const float* src = src_rows + (size_t)k * D;
+  float s = 0.f;
+  for (int d = lane; d < D; d += 32) { float v = src[d]; s += v * v; }
+  s = warp_sum(s);
+  const float inv = 1.0f / fmaxf(sqrtf(s), 1e-12f);
+  for (int d = lane; d < D; d += 32) dst_rows[(size_t)k * D + d] = src[d] * inv;
 }
 
 // ---------------------------------------------------------------- E2 -------
@@ -461,7 +459,7 @@ ema_apply_kernel(const float* protos_in, const float* __restrict__ packed, int C
 }
 
 static int ema_rows_config(int D, int K, int* tile_rows, int* n_tiles, size_t* smem) {
-  const size_t budget = 227 * 1024;
+  const size_t budget = 227 * 1024 - smem_reserve();
   const size_t fixed = ((size_t)kEmaWarps * D + (size_t)kEmaWarps * ((K + 31) & ~31)) * 4;
   const size_t row = (size_t)(D + 4) * 4;
   if (fixed + 32 * row > budget) return -1;
@@ -512,7 +510,6 @@ static int proto_ema_accumulate_impl(
   C3D_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "workspace must be 256 B aligned");
   const int HW = (int)HWll, K = C * M;
   EmaWs w = carve_ema(workspace, B, C, HW, D, M, max_rows);
-  const int nbps = (HW + kTile - 1) / kTile, nblk = B * nbps;
   int tile_rows = 0, n_tiles = 0; size_t smem = 0;
   C3D_REQUIRE(dense || ema_rows_config(D, K, &tile_rows, &n_tiles, &smem) == 0,
               "bank does not fit shared memory tiling (D=%d, K=%d)", D, K);
@@ -521,31 +518,28 @@ static int proto_ema_accumulate_impl(
   const size_t seg_smem = (size_t)seg_split * ((size_t)M * D + M) * sizeof(float);
   C3D_REQUIRE(seg_smem <= 227 * 1024, "M*D too large for the segmented-sum kernel");
 
-  C3D_CUDA(cudaMemsetAsync(w.info, 0, (size_t)(8 + B) * 4, stream));
+  C3D_CUDA(cudaMemsetAsync(w.s.info, 0, (size_t)(8 + B) * 4, stream));
   if (proto_target) C3D_CUDA(cudaMemsetAsync(proto_target, 0, (size_t)B * HW * 4, stream));
   int rc;
-  { KernelTimer kt__("split_count_scan_kernel", stream);
-    split_count_scan_kernel<true><<<split_grid(nblk), 256, 0, stream>>>(
-        (const long long*)label, nullptr, HW, nbps, B, C, ignore_label, w.blk_cnt, w.seg_cnt, w.seg_start,
-        w.seg_tidx, w.info); }
-  if ((rc = check_launch("split_count_scan_kernel"))) return rc;
-  const int bank_ctas = dense ? 0 : 16;   // extra CTAs L2-normalise the bank rows (:502)
-  { KernelTimer kt__("split_scatter_kernel", stream); split_scatter_kernel<true, false><<<split_grid(nblk) + bank_ctas, 256, 0, stream>>>(
-      (const long long*)label, nullptr, nullptr, HW, nbps, nblk, B, C, ignore_label, w.blk_cnt,
-      w.seg_start, w.pix_list, w.cls_list, nullptr, nullptr, prototypes, dense ? 0 : K, D, w.bank_n, split_grid(nblk)); }
-  if ((rc = check_launch("split_scatter_kernel"))) return rc;
+  if ((rc = launch_split((const long long*)label, nullptr, nullptr, B, C, HW, ignore_label, w.s, nullptr,
+                         nullptr, nullptr, 0, stream))) return rc;
+  if (!dense) {
+    KernelTimer kt__("bank_normalise_kernel", stream);
+    ema_bank_normalise_kernel<<<(K + 7) / 8, 256, 0, stream>>>(prototypes, K, D, w.bank_n);
+    if ((rc = check_launch("bank_normalise_kernel"))) return rc;
+  }
 
   if (dense) {
     KernelTimer kt__("ema_rows_dense_kernel", stream);
     ema_rows_dense_kernel<<<kNumSMs * 2, 256, 0, stream>>>(dense->out_feat, dense->nearest, dense->sim,
-                                                           w.pix_list, w.cls_list, w.info, w.feat, w.simq,
+                                                           w.s.pix_list, w.s.cls_list, w.s.info, w.feat, w.simq,
                                                            w.maskv, HW, D, M, C, (int)max_rows);
     if ((rc = check_launch("ema_rows_dense_kernel"))) return rc;
   } else {
     EmaRowsParams p{};
     p.emb = embedding; p.bank_n = w.bank_n; p.ln_d_w = ln_d_w; p.ln_d_b = ln_d_b;
-    p.ln_c_w = ln_c_w; p.ln_c_b = ln_c_b; p.pix_list = w.pix_list; p.cls_list = w.cls_list;
-    p.info = w.info; p.feat = w.feat; p.simq = w.simq; p.maskv = w.maskv;
+    p.ln_c_w = ln_c_w; p.ln_c_b = ln_c_b; p.pix_list = w.s.pix_list; p.cls_list = w.s.cls_list;
+    p.info = w.s.info; p.feat = w.feat; p.simq = w.simq; p.maskv = w.maskv;
     p.HW = HW; p.D = D; p.M = M; p.C = C; p.K = K; p.tile_rows = tile_rows; p.n_tiles = n_tiles;
     p.max_rows = (int)max_rows; p.eps = ln_eps;
     C3D_CUDA(cudaFuncSetAttribute(ema_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -555,14 +549,14 @@ static int proto_ema_accumulate_impl(
   }
   C3D_CUDA(cudaFuncSetAttribute(ema_sinkhorn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 kSinkSmemFloats * 4));
-  { KernelTimer kt__("ema_sinkhorn_kernel", stream); ema_sinkhorn_kernel<<<C, kSinkWarps * 32, kSinkSmemFloats * 4, stream>>>(w.seg_cnt, w.seg_start, w.pix_list, w.info, B, M,
+  { KernelTimer kt__("ema_sinkhorn_kernel", stream); ema_sinkhorn_kernel<<<C, kSinkWarps * 32, kSinkSmemFloats * 4, stream>>>(w.s.seg_cnt, w.s.seg_start, w.s.pix_list, w.s.info, B, M,
                                              ignore_label, (int)max_rows, w.simq, w.sub, gumbel,
                                              assign_mode, seed, proto_target); }
   if ((rc = check_launch("ema_sinkhorn_kernel"))) return rc;
   if (seg_smem > 48 * 1024)
     C3D_CUDA(cudaFuncSetAttribute(ema_segsum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)seg_smem));
-  { KernelTimer kt__("ema_segsum_kernel", stream); ema_segsum_kernel<<<C, 256, seg_smem, stream>>>(w.seg_cnt, w.seg_start, w.info, B, M, D, K,
+  { KernelTimer kt__("ema_segsum_kernel", stream); ema_segsum_kernel<<<C, 256, seg_smem, stream>>>(w.s.seg_cnt, w.s.seg_start, w.s.info, B, M, D, K,
                                                   ignore_label, (int)max_rows, seg_split, w.feat, w.maskv,
                                                   w.sub, packed); }
   return check_launch("ema_segsum_kernel");

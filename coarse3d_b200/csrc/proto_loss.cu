@@ -5,9 +5,8 @@
 // loop of unique / multinomial / gather launches, a 380 x D GEMM over A*T
 // duplicated rows and an index_put backward is restated as:
 //
-//   K1-K3 split_count / split_scan / split_scatter  (labelsplit.cuh) labelled pixels
-//         -> slots sorted by (scan, class, pixel) + entropy weight exp(-H^2) per slot
-//         (:46-49); extra CTAs L2-normalise the bank rows (:167)
+//   K1-K2 split_count / split_place  (labelsplit.cuh) labelled pixels
+//         -> slots sorted by (class, scan, pixel) + entropy weight exp(-H^2) per slot (:46-49)
 //   K4 loss_sample   one CTA per (scan, class) segment: CDF, A draws with replacement
 //         (Philox) or the injected `keep` indices -> multiplicity per slot; the
 //         distinct sampled slots are compacted into ROWS (<= A per segment)
@@ -40,16 +39,10 @@ enum LossFlag { kFlagNoAnchor = 1, kFlagBadKeep = 2, kFlagKeepRows = 4, kFlagNoG
 enum LossInfo { kInfoU = 5, kInfoDone3 = 6, kInfoHasGrad = 7 };
 
 struct LossWs {
-  int32_t* info;       // [8]
-  int32_t* blk_cnt;    // [nblk * C] counts, then exclusive prefix inside (scan, class)
-  int32_t* seg_cnt;    // [B * C]
-  int32_t* seg_start;  // [B * C]
-  int32_t* seg_tidx;   // [B * C] index among non-empty segments, or -1
-  int32_t* seg_nd;     // [B * C] distinct sampled slots of the segment
-  int32_t* row_base;   // [B * C + 1] exclusive prefix of seg_nd over non-empty segments
-  int32_t* seg_of_t;   // [B * C] segment index of the t-th non-empty segment
-  int32_t* pix_list;   // [cap] b*HW + pixel
-  int32_t* cls_list;   // [cap]
+  SplitWs s;           // labelled-pixel slots, class-major (labelsplit.cuh)
+  int32_t* seg_nd;     // [C * B] distinct sampled slots of the segment (class-major index)
+  int32_t* row_base;   // [B * C + 1] exclusive prefix of seg_nd over non-empty segments, t order
+  int32_t* seg_of_t;   // [B * C] class-major segment index of the t-th non-empty segment
   float* w_list;       // [cap] weights -> in-place CDF -> (int) distinct-slot list
   int32_t* cnt_list;   // [cap] sampling multiplicity
   float* loss_part;    // [max_rows]
@@ -65,21 +58,14 @@ static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 static LossWs carve(void* base, int B, int C, int HW, int D, int M, int A) {
   LossWs w;
   const size_t cap = (size_t)B * HW;
-  const size_t nblk = (size_t)B * ((HW + kTile - 1) / kTile);
   size_t max_rows = (size_t)A * B * (C - 1);  // <= A distinct rows per segment
   if (max_rows > cap) max_rows = cap;
   size_t off = 0;
+  w.s = carve_split(base, &off, B, C, HW);
   auto take = [&](size_t n) { size_t o = off; off += align_up(n); return (char*)base + o; };
-  w.info = (int32_t*)take((size_t)(8 + B) * 4);  // [8 + B]: counters/flags + per-scan tickets
-  w.blk_cnt = (int32_t*)take(nblk * C * 4);
-  w.seg_cnt = (int32_t*)take((size_t)B * C * 4);
-  w.seg_start = (int32_t*)take((size_t)B * C * 4);
-  w.seg_tidx = (int32_t*)take((size_t)B * C * 4);
   w.seg_nd = (int32_t*)take((size_t)B * C * 4);
   w.row_base = (int32_t*)take(((size_t)B * C + 1) * 4);
   w.seg_of_t = (int32_t*)take((size_t)B * C * 4);
-  w.pix_list = (int32_t*)take(cap * 4);
-  w.cls_list = (int32_t*)take(cap * 4);
   w.w_list = (float*)take(cap * 4);
   w.cnt_list = (int32_t*)take(cap * 4);
   w.loss_part = (float*)take(max_rows * 4);
@@ -120,10 +106,12 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
 __global__ void __launch_bounds__(256)
 loss_sample_kernel(const int32_t* __restrict__ seg_cnt, const int32_t* __restrict__ seg_start,
                    const int32_t* __restrict__ seg_tidx, const int32_t* __restrict__ pix_list,
-                   float* __restrict__ w_list, int32_t* __restrict__ cnt_list, int HW, int C, int A,
+                   float* __restrict__ w_list, int32_t* __restrict__ cnt_list, int HW, int B, int C, int A,
                    const long long* __restrict__ keep, int keep_rows, unsigned long long seed,
                    int32_t* __restrict__ seg_nd, int32_t* __restrict__ row_base,
                    int32_t* __restrict__ seg_of_t, int32_t* __restrict__ info) {
+  // one CTA per (class, scan) segment; seg = c*B + b (class-major storage), its rank among the
+  // non-empty segments in the reference's (scan, class) order is seg_tidx[b*C + c]
   const int seg = blockIdx.x, nseg = gridDim.x;
   const int n = seg_cnt[seg];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -138,7 +126,7 @@ loss_sample_kernel(const int32_t* __restrict__ seg_cnt, const int32_t* __restric
   if (keep && seg == 0 && threadIdx.x == 0 && info[kInfoT] != keep_rows)
     atomicOr(&info[kInfoFlags], kFlagKeepRows);
   if (n > 0) {
-    const int start = seg_start[seg], t = seg_tidx[seg], b = seg / C;
+    const int b = seg % B, start = seg_start[seg], t = seg_tidx[b * C + seg / B];
     if (keep) {
       bool bad = false;
       for (int a = threadIdx.x; a < A && t < keep_rows; a += 256) {
@@ -230,16 +218,17 @@ loss_sample_kernel(const int32_t* __restrict__ seg_cnt, const int32_t* __restric
   if (warp == 0) {
     int carry = 0;
     for (int base = 0; base < nseg; base += 32) {
-      const int i = base + lane;
+      const int i = base + lane;                           // i = b*C + c, the reference's order
       const int t = (i < nseg) ? seg_tidx[i] : -1;
-      const int v = (t >= 0) ? __ldcg(seg_nd + i) : 0;
+      const int sg = (i % C) * B + i / C;                  // class-major segment index
+      const int v = (t >= 0) ? __ldcg(seg_nd + sg) : 0;
       int incl = v;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
         int u = __shfl_up_sync(0xffffffffu, incl, o);
         if (lane >= o) incl += u;
       }
-      if (t >= 0) { row_base[t] = carry + incl - v; seg_of_t[t] = i; }
+      if (t >= 0) { row_base[t] = carry + incl - v; seg_of_t[t] = sg; }
       carry += __shfl_sync(0xffffffffu, incl, 31);
     }
     if (lane == 0) {
@@ -877,7 +866,7 @@ loss_grad_scatter_kernel(const float* __restrict__ grad_rows, const int32_t* __r
 }
 
 static int rows_config(int D, int Kc, int* tile_rows, int* n_tiles, size_t* smem) {
-  const size_t budget = 227 * 1024;
+  const size_t budget = 227 * 1024 - smem_reserve();
   const size_t fixed = ((size_t)kRowWarps * D + (size_t)kRowWarps * ((Kc + 31) & ~31)) * 4;
   const size_t row = (size_t)(D + 4) * 4;
   if (fixed + 32 * row > budget) return -1;
@@ -930,7 +919,6 @@ static int proto_loss_forward_impl(
   C3D_REQUIRE(temperature > 0 && base_temperature > 0, "temperatures must be positive");
   const int HW = (int)HWll;
   LossWs w = carve(workspace, B, C, HW, D, M, num_anchor);
-  const int nbps = (HW + kTile - 1) / kTile, nblk = B * nbps;
   const int Kc = (C - 1) * M;
   int tile_rows, n_tiles; size_t smem;
   C3D_REQUIRE(rows_config(D, Kc, &tile_rows, &n_tiles, &smem) == 0,
@@ -938,23 +926,14 @@ static int proto_loss_forward_impl(
 
   int rc;
   if (phases & 1) {
-  C3D_CUDA(cudaMemsetAsync(w.info, 0, (size_t)(8 + B) * 4, stream));
-  { KernelTimer kt__("split_count_scan_kernel", stream);
-    split_count_scan_kernel<false><<<split_grid(nblk), 256, 0, stream>>>(
-        (const long long*)labels, keep_mask, HW, nbps, B, C, ignore_label, w.blk_cnt, w.seg_cnt, w.seg_start,
-        w.seg_tidx, w.info); }
-  if ((rc = check_launch("split_count_scan_kernel"))) return rc;
-  { KernelTimer kt__("split_scatter_kernel", stream);
-    split_scatter_kernel<false, true><<<split_grid(nblk), 256, 0, stream>>>(
-        (const long long*)labels, keep_mask, probs, HW, nbps, nblk, B, C, ignore_label, w.blk_cnt,
-        w.seg_start, w.pix_list, w.cls_list, w.w_list, w.cnt_list, nullptr, 0, D, nullptr,
-        split_grid(nblk)); }
-  if ((rc = check_launch("split_scatter_kernel"))) return rc;
+  C3D_CUDA(cudaMemsetAsync(w.s.info, 0, (size_t)(8 + B) * 4, stream));
+  if ((rc = launch_split((const long long*)labels, keep_mask, probs, B, C, HW, ignore_label, w.s, w.w_list,
+                         w.cnt_list, nullptr, 0, stream))) return rc;
   { KernelTimer kt__("loss_sample_kernel", stream);
-    loss_sample_kernel<<<B * C, 256, 0, stream>>>(w.seg_cnt, w.seg_start, w.seg_tidx, w.pix_list,
-                                                  w.w_list, w.cnt_list, HW, C, num_anchor,
+    loss_sample_kernel<<<B * C, 256, 0, stream>>>(w.s.seg_cnt, w.s.seg_start, w.s.seg_tidx, w.s.pix_list,
+                                                  w.w_list, w.cnt_list, HW, B, C, num_anchor,
                                                   (const long long*)keep, keep_rows, seed, w.seg_nd,
-                                                  w.row_base, w.seg_of_t, w.info); }
+                                                  w.row_base, w.seg_of_t, w.s.info); }
   if ((rc = check_launch("loss_sample_kernel"))) return rc;
   }
   if (!(phases & 2)) return C3D_OK;
@@ -967,9 +946,9 @@ static int proto_loss_forward_impl(
   if ((rc = check_launch("bank_normalise_kernel"))) return rc;
 
   RowsParams p{};
-  p.feats = feats; p.bank_n = w.bank_n; p.pix_list = w.pix_list; p.cls_list = w.cls_list;
+  p.feats = feats; p.bank_n = w.bank_n; p.pix_list = w.s.pix_list; p.cls_list = w.s.cls_list;
   p.cnt_list = w.cnt_list; p.dist_list = reinterpret_cast<const int32_t*>(w.w_list);
-  p.seg_start = w.seg_start; p.row_base = w.row_base; p.seg_of_t = w.seg_of_t; p.info = w.info;
+  p.seg_start = w.s.seg_start; p.row_base = w.row_base; p.seg_of_t = w.seg_of_t; p.info = w.s.info;
   p.loss_part = w.loss_part; p.row_pix = w.row_pix; p.grad_rows = w.grad_rows; p.loss_out = loss_out;
   p.HW = HW; p.D = D; p.M = M; p.Kc = Kc; p.A = num_anchor; p.tile_rows = tile_rows;
   p.n_tiles = n_tiles; p.temperature = temperature; p.base_temperature = base_temperature;
@@ -1040,7 +1019,7 @@ extern "C" int c3d_proto_loss_backward(int batch, int dim, int proj_h, int proj_
   if (!grad_is_zeroed && (rc = launch_fill(grad_feats, (size_t)B * D * HW * 4, stream))) return rc;
   { KernelTimer kt__("loss_grad_scatter_kernel", stream);
     loss_grad_scatter_kernel<<<kNumSMs * 2, 256, 0, stream>>>(
-        w.grad_rows, w.row_pix, w.info, grad_out, HW, D, grad_feats); }
+        w.grad_rows, w.row_pix, w.s.info, grad_out, HW, D, grad_feats); }
   return check_launch("loss_grad_scatter_kernel");
 }
 
@@ -1072,8 +1051,8 @@ extern "C" int c3d_proto_loss_rows(const void* workspace, int batch, int dim, in
   C3D_REQUIRE(capacity > 0 && capacity <= (int64_t)batch * hw, "bad capacity");
   LossWs w = carve(const_cast<void*>(workspace), batch, n_classes, hw, dim, sub_protos, num_anchor);
   const size_t n = (size_t)capacity * 4;
-  C3D_CUDA(cudaMemcpyAsync(pix, w.pix_list, n, cudaMemcpyDeviceToDevice, stream));
-  C3D_CUDA(cudaMemcpyAsync(cls, w.cls_list, n, cudaMemcpyDeviceToDevice, stream));
+  C3D_CUDA(cudaMemcpyAsync(pix, w.s.pix_list, n, cudaMemcpyDeviceToDevice, stream));
+  C3D_CUDA(cudaMemcpyAsync(cls, w.s.cls_list, n, cudaMemcpyDeviceToDevice, stream));
   C3D_CUDA(cudaMemcpyAsync(cnt, w.cnt_list, n, cudaMemcpyDeviceToDevice, stream));
   return C3D_OK;
 }

@@ -372,7 +372,7 @@ def proto_loss_info(workspace):
 
 def proto_loss_rows(workspace, batch, dim, hw, n_classes, sub_protos, num_anchor):
     """Labelled-pixel slots of the last forward: (pix, cls, cnt) int32 tensors,
-    sorted by (scan, class, pixel).  Synchronises (reads the slot count)."""
+    sorted by (class, scan, pixel).  Synchronises (reads the slot count)."""
     _, n_lab, _ = proto_loss_info(workspace)
     dev = workspace.device
     pix, cls, cnt = (torch.empty((max(n_lab, 1),), dtype=torch.int32, device=dev) for _ in range(3))
@@ -411,6 +411,19 @@ def zero_fill_background(t, mode=0, ctas_per_sm=1, page_bytes=8192, inflight=4):
     check(lib.c3d_zero_fill_background(_p(t), t.numel() * t.element_size(), int(mode), int(ctas_per_sm),
                                        int(page_bytes), int(inflight), _stream()))
     return t
+
+
+def zero_fill_daemon(t, ctrl, max_per_sm=1, launch_per_sm=4, page_bytes=8192, chunk_pages=4, debug=None):
+    """c3d_zero_fill_daemon: the placement-proof background fill.  ctrl: >= 1 KB uint8/int32
+    CUDA scratch; debug: optional int64 (launch_per_sm*148, 4) tensor."""
+    _need_cuda(t=t, ctrl=ctrl, debug=debug)
+    check(lib.c3d_zero_fill_daemon(_p(t), t.numel() * t.element_size(), int(max_per_sm), int(launch_per_sm),
+                                   int(page_bytes), int(chunk_pages), _p(ctrl), _p(debug), _stream()))
+    return t
+
+
+def delay(ns):
+    check(lib.c3d_delay(int(ns), _stream()))
 
 
 def proto_loss_backward_raw(shape, cfg, n_classes, sub_protos, workspace, grad_out, grad_feats,
@@ -619,8 +632,11 @@ def proto_ema_apply(prototypes, packed, momentum, ignore_label=0, out=None):
 class concurrent_hint:
     """Context manager around multi-stream use of the library (c3d_set_concurrent_hint)."""
 
+    def __init__(self, level=1):
+        self.level = level   # 2: also leave shared memory for the fill daemon next to the rows kernels
+
     def __enter__(self):
-        self.prev = lib.c3d_set_concurrent_hint(1)
+        self.prev = lib.c3d_set_concurrent_hint(self.level)
         return self
 
     def __exit__(self, *exc):

@@ -109,7 +109,7 @@ class PrototypeBank(nn.Module):
     def check_flags(self, wait=True):
         """Raise if the last examined update overflowed `max_rows` (it was then skipped
         entirely) or saw labels outside [0, C).  wait=False only looks at a finished copy."""
-        if not self._flag_pending or self._flag_event is None:
+        if not self._flag_pending or self._flag_event is None or torch.cuda.is_current_stream_capturing():
             return
         if wait:
             self._flag_event.synchronize()

@@ -7,6 +7,8 @@ The range-image CNN between projection and loss is out of scope (SURVEY.md 2,
 row 9), so its outputs (features, softmax probabilities, argmax image) are
 synthetic resident tensors, exactly as BASELINE.json's configs prescribe.
 """
+import os as _os
+
 import numpy as np
 import torch
 
@@ -87,9 +89,12 @@ class HotPathStep:
         self.packed = torch.empty((K * dim + K,), device=self.device)
         self.knn_out = torch.empty((n,), dtype=torch.int64, device=self.device)
         self.inv_gauss = (1 - ops.gaussian_kernel(self.knn_s, self.knn_sigma)).reshape(-1).to(self.device)
+        self.daemon_ctrl = torch.zeros(256, dtype=torch.int32, device=self.device)
+        self.daemon_dbg = None
+        self.daemon_lead_ns = int(_os.environ.get("C3D_DAEMON_LEAD_NS", "0"))
+        self.ev_fork0 = torch.cuda.Event()
         self.graphs = None
         self.concurrent = concurrent
-        import os as _os
         self.schedule = _os.environ.get("C3D_SCHEDULE", "fill_in_knn")
         # fill daemon (schedule "fill_daemon"): mode, CTAs per SM, zero-page bytes, copies in flight
         self.daemon = tuple(int(v) for v in _os.environ.get("C3D_DAEMON", "0,1,8192,4").split(","))
@@ -141,18 +146,28 @@ class HotPathStep:
             if not fused:
                 self._knn(s, pr, C)
             return pr
-        with ops.concurrent_hint():
+        with ops.concurrent_hint(2 if self.schedule == "fill_daemon" else 1):
             return self._run_concurrent(s, b, seed, fused, cur)
 
     def _run_concurrent(self, s, b, seed, fused, cur):
         H, W, C = self.shape.proj_h, self.shape.proj_w, self.shape.n_classes
         st_fill, st_proj, st_ema, st_loss = self.side
-        self.ev_fork.record(cur)
-        for st in self.side:
-            st.wait_event(self.ev_fork)
         P = self.parts
         pr = None
         sched = self.schedule
+        if sched == "fill_daemon" and self.daemon_lead_ns > 0 and "fill" in P:
+            # The daemon first, alone: launched next to other grids its one-warp CTAs are packed
+            # onto a handful of SMs (measured: 148 CTAs on 6-13 SMs) and the fill crawls at the
+            # per-SM copy-engine rate.  A short hold lets it become resident on every SM.
+            self.ev_fork0.record(cur)
+            st_fill.wait_event(self.ev_fork0)
+            with torch.cuda.stream(st_fill):
+                self._daemon()
+                self.ev_fill.record(st_fill)
+            ops.delay(self.daemon_lead_ns)
+        self.ev_fork.record(cur)
+        for st in self.side:
+            st.wait_event(self.ev_fork)
         hold = fused and self.knn_after_select and "loss" in P
         if hold:
             # selection part of the loss first; its event releases the KNN + fill kernel
@@ -177,10 +192,11 @@ class HotPathStep:
         elif sched == "fill_daemon":
             # The fill as a minimal-footprint persistent kernel (one warp per SM), launched first
             # and running UNDER everything else of the step.
-            with torch.cuda.stream(st_fill):
-                if "fill" in P:
-                    ops.zero_fill_background(self.grad, *self.daemon)
-                self.ev_fill.record(st_fill)
+            if not (self.daemon_lead_ns > 0 and "fill" in P):
+                with torch.cuda.stream(st_fill):
+                    if "fill" in P:
+                        self._daemon()
+                    self.ev_fill.record(st_fill)
             with torch.cuda.stream(st_proj):
                 if "proj" in P:
                     pr = ops.project_batch(s.points, s.offsets, self.fov, H, W, buffers=b)
@@ -287,6 +303,24 @@ class HotPathStep:
         for ev in (self.ev_proj, self.ev_ema, self.ev_loss):
             cur.wait_event(ev)
         return self.loss, self.knn_out, asm
+
+    def _daemon(self):
+        if self.daemon[0] == 2:     # (2, max_per_sm, launch_per_sm, page, chunk): claim form
+            ops.zero_fill_daemon(self.grad, self.daemon_ctrl, *self.daemon[1:], debug=self.daemon_dbg)
+        else:
+            ops.zero_fill_background(self.grad, *self.daemon)
+
+    def set_schedule(self, schedule, daemon=None, parts=None, fill_priority=None):
+        """Switch the schedule of an existing step (drops captured graphs)."""
+        self.schedule = schedule
+        if daemon is not None:
+            self.daemon = tuple(daemon)
+        if parts is not None:
+            self.parts = set(parts)
+        self.graphs = None
+        if fill_priority is None:
+            fill_priority = -1 if schedule == "fill_daemon" else 0
+        self.side[0] = torch.cuda.Stream(self.device, priority=fill_priority)
 
     def _last_proj(self, b):
         return ops.Projection(b.proj_pointcloud, b.proj_range, b.proj_idx, b.proj_mask,

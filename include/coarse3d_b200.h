@@ -305,11 +305,22 @@ int c3d_zero_fill(void* dst, size_t nbytes, void* stream);
 int c3d_zero_fill_background(void* dst, size_t nbytes, int mode, int ctas_per_sm, int page_bytes,
                              int inflight, void* stream);
 
+/* Placement-proof daemon: launch_per_sm * 148 one-warp CTAs are launched, each claims the SM
+ * it lands on and retires at once if that SM already runs max_per_sm of them; pages (TMA
+ * bulk stores of a zero page of page_bytes) are handed out chunk_pages at a time by a global
+ * counter.  ctrl_ws: 1 KB of device scratch (zeroed here); debug: NULL, or
+ * [launch_per_sm * 148][4] int64 {smid, first ns, last ns, pages} per CTA that worked. */
+int c3d_zero_fill_daemon(void* dst, size_t nbytes, int max_per_sm, int launch_per_sm, int page_bytes,
+                         int chunk_pages, void* ctrl_ws, void* debug, void* stream);
+
+/* Holds `stream` for ns nanoseconds (one spinning thread). */
+int c3d_delay(unsigned long long ns, void* stream);
+
 /* Synchronous: copies {T, labelled pixels, flags, 0} to host_info4 (host). */
 int c3d_proto_loss_info(const void* workspace, int32_t* host_info4, void* stream);
 
 /* Exports the first `capacity` labelled-pixel slots of the last forward, sorted
- * by (scan, class, pixel): pix = scan*H*W + pixel, cls = class, cnt = number of
+ * by (class, scan, pixel): pix = scan*H*W + pixel, cls = class, cnt = number of
  * anchors that hit the slot (sums to num_anchor per segment). */
 int c3d_proto_loss_rows(const void* workspace, int batch, int dim, int hw, int n_classes,
                         int sub_protos, int num_anchor, int64_t capacity, int32_t* pix,

@@ -106,12 +106,17 @@ def test_run_inputs_equals_resident_step(cuda_device, monkeypatch):
 def test_loss_reads_the_updated_bank(cuda_device, monkeypatch):
     """The EMA update precedes the loss (salsanext_proto.py:520-527 inside model.forward,
     trainer.py:675-686 after it): the step's loss must equal the loss of the UPDATED bank."""
-    from coarse3d_b200 import ops
-    step = _step(monkeypatch, "fill_in_knn")
+    import dataclasses
+    from coarse3d_b200 import ops, synth
+    from coarse3d_b200.pipeline import HotPathStep
+    monkeypatch.setenv("C3D_SCHEDULE", "fill_in_knn")
+    # enough labels and a fast momentum, so that the bank visibly moves within one step
+    shape = dataclasses.replace(synth.NUSCENES, label_ratio=2e-2)
+    step = HotPathStep(shape, 3, dim=32, sub_protos=4, num_anchor=16, n_sets=2, seed0=77, momentum=0.5)
     bank0 = step.protos.clone()
     step.run(0, seed=5)
     loss, _, bank1, _ = _outputs(step)
-    assert not torch.equal(bank0, bank1)
+    assert float((bank0 - bank1).abs().max()) > 1e-3
     s = step.sets[0]
     ws = ops.proto_loss_workspace(step.batch, step.shape.n_classes, step.shape.proj_h * step.shape.proj_w,
                                   step.dim, step.M, step.cfg.num_anchor, "cuda")
