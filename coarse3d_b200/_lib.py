@@ -73,6 +73,10 @@ def _load():
                                                    c_int64, P, c_int, c_uint64, P, P, P, P]),
         "c3d_proto_ema_apply": (c_int, [P, P, c_int, c_int, c_int, c_int, c_double, P, P]),
         "c3d_proto_ema_info": (c_int, [P, P, P]),
+        "c3d_proto_step_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int, c_int64]),
+        "c3d_proto_step": (c_int, [P, P, P, P, P, P, P, P, P, c_float, c_int, c_int, c_int, c_int, c_int, c_int,
+                                   c_int, c_float, c_float, c_int, P, c_int, P, c_int, c_uint64, c_int64, c_int,
+                                   c_int, P, P, P, P, P]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported

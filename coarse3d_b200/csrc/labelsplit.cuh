@@ -73,10 +73,12 @@ __device__ __forceinline__ int masked_class(const long long* __restrict__ labels
   return (int)l;
 }
 
-// Count + stage + scan in one launch.
+// Count + stage + scan in one launch.  A CTA handles `tpc` consecutive tiles of ONE scan (tpc
+// divides the tiles per scan): the per-tile work is a handful of instructions when nothing is
+// labelled, and the expensive part -- fence, ticket, barriers -- is paid once per CTA.
 static __global__ void __launch_bounds__(256)
 split_count_kernel(const long long* __restrict__ labels, const uint8_t* __restrict__ keep, int HW,
-                   int nbps, int B, int C, int ignore_label, SplitWs w,
+                   int nbps, int tpc, int B, int C, int ignore_label, SplitWs w,
                    float* __restrict__ zero_buf, int zero_n) {
   __shared__ int s_cnt[kTileRounds][8][kMaxClasses];  // [round][warp][class] -> exclusive prefix
   __shared__ int s_cpre[kMaxClasses + 1];             // exclusive prefix over classes (tile)
@@ -85,24 +87,36 @@ split_count_kernel(const long long* __restrict__ labels, const uint8_t* __restri
   const unsigned lt = (1u << lane) - 1;
   // a small caller buffer zeroed on the side (the packed prototype sums of the fused step)
   for (int i = blockIdx.x * 256 + threadIdx.x; i < zero_n; i += gridDim.x * 256) zero_buf[i] = 0.f;
-  for (int blk = blockIdx.x; blk < B * nbps; blk += gridDim.x) {
-    const int b = blk / nbps, tile = blk % nbps;
+  const int cps = nbps / tpc;                         // CTA work items per scan
+  for (int item = blockIdx.x; item < B * cps; item += gridDim.x) {
+    const int b = item / cps;
+    // the labels of tile t + 1 are requested before tile t is processed, so that the memory
+    // system stays busy across the barriers of the per-tile work
+    int nxt[kTileRounds];
+    auto fetch = [&](int tile) {
+#pragma unroll
+      for (int r = 0; r < kTileRounds; ++r) {
+        const int pix = tile * kTile + r * 256 + threadIdx.x;
+        nxt[r] = (pix < HW) ? masked_class(labels, keep, (size_t)b * HW + pix, ignore_label) : ignore_label;
+      }
+    };
+    fetch((item % cps) * tpc);
+    for (int tt = 0; tt < tpc; ++tt) {
+    const int tile = (item % cps) * tpc + tt, blk = b * nbps + tile;
     int cls[kTileRounds], rank[kTileRounds];
     bool bad = false;
     unsigned any_round = 0;
-    // pass 1: classes of this thread's pixels; which rounds have any labelled pixel (per warp)
 #pragma unroll
     for (int r = 0; r < kTileRounds; ++r) {
-      const int pix = tile * kTile + r * 256 + threadIdx.x;
-      int c = -1;
-      if (pix < HW) {
-        c = masked_class(labels, keep, (size_t)b * HW + pix, ignore_label);
-        if (c == ignore_label) c = -1;
-        else if (c < 0 || c >= C) { bad = true; c = -1; }
-      }
+      int c = nxt[r];
+      if (c == ignore_label) c = -1;
+      else if (c < 0 || c >= C) { bad = true; c = -1; }
       cls[r] = c;
-      if (__ballot_sync(0xffffffffu, c >= 0)) any_round |= 1u << r;
     }
+    if (tt + 1 < tpc) fetch(tile + 1);
+#pragma unroll
+    for (int r = 0; r < kTileRounds; ++r)
+      if (__ballot_sync(0xffffffffu, cls[r] >= 0)) any_round |= 1u << r;
     const int tile_any = __syncthreads_or(any_round != 0);
     if (bad) atomicOr(&w.info[kInfoFlags], kFlagBadLabel);
     if (!tile_any) {
@@ -148,11 +162,11 @@ split_count_kernel(const long long* __restrict__ labels, const uint8_t* __restri
         w.stage[(size_t)b * HW + (size_t)tile * kTile + s_cpre[c] + rk] = (r * 256 + (int)threadIdx.x) | (c << 11) | (rk << 17);
       }
     }
+    }  // tiles of this CTA
 
     // ---- last CTA of scan b: exclusive prefix of the tile counts, per class
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) s_flag = (atomicAdd(&w.info[8 + b], 1) == nbps - 1);
+    __syncthreads();   // this CTA's counts are written; one thread publishes them (cumulative fence)
+    if (threadIdx.x == 0) { __threadfence(); s_flag = (atomicAdd(&w.info[8 + b], 1) == cps - 1); }
     __syncthreads();
     if (!s_flag) continue;
     __threadfence();
@@ -182,9 +196,8 @@ split_count_kernel(const long long* __restrict__ labels, const uint8_t* __restri
       if (lane == 0) w.seg_cnt[c * B + b] = carry;
     }
     // ---- last scan: segment tables over the B*C totals
-    __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) { w.info[8 + b] = 0; s_flag = (atomicAdd(&w.info[kInfoDone], 1) == B - 1); }
+    if (threadIdx.x == 0) { __threadfence(); w.info[8 + b] = 0; s_flag = (atomicAdd(&w.info[kInfoDone], 1) == B - 1); }
     __syncthreads();
     if (!s_flag) continue;
     __threadfence();
@@ -244,40 +257,65 @@ split_count_kernel(const long long* __restrict__ labels, const uint8_t* __restri
         w.info[kInfoDone] = 0;
       }
     }
-  }  // tile loop
+  }  // work-item loop
 }
 
-// Staged pixels -> sorted slots (+ entropy weight, contrast_pixel_loss.py:46-49).
+// Staged pixels -> sorted slots (+ entropy weight, contrast_pixel_loss.py:46-49).  One WARP per
+// tile (under weak labels a tile holds a couple of labelled pixels and the work is one dependent
+// chain of loads); the records beyond the first 128 of a crowded tile are shared by the CTA.
+template <bool kEntropy>
+__device__ __forceinline__ void place_record(int rec, int b, int tile, int blk, const float* __restrict__ probs,
+                                             int HW, int B, int C, const SplitWs& w,
+                                             float* __restrict__ w_list, int32_t* __restrict__ cnt_list) {
+  const int pl = rec & 2047, c = (rec >> 11) & 63, rk = rec >> 17;
+  const int pix = tile * kTile + pl;
+  const int slot = w.seg_start[c * B + b] + w.blk_cnt[(size_t)blk * C + c] + rk;
+  w.pix_list[slot] = b * HW + pix;
+  w.cls_list[slot] = c;
+  if (kEntropy) {
+    const float* p = probs + (size_t)b * C * HW + pix;
+    float ent = 0.f;
+    for (int k0 = 0; k0 < C; k0 += 8) {  // 8 strided loads in flight per pass
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = (k0 + j < C) ? __ldg(p + (size_t)(k0 + j) * HW) : 1.0f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) if (k0 + j < C) ent += v[j] * logf(v[j] + 1e-10f);
+    }
+    ent = -ent;
+    w_list[slot] = expf(-(ent * ent));
+    cnt_list[slot] = 0;
+  }
+}
+
 template <bool kEntropy>
 __global__ void __launch_bounds__(256)
 split_place_kernel(const float* __restrict__ probs, int HW, int nbps, int nblk, int B, int C,
                    SplitWs w, float* __restrict__ w_list, int32_t* __restrict__ cnt_list) {
-  for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
-    const int n = w.tile_tot[blk];
-    if (n == 0) continue;
-    const int b = blk / nbps, tile = blk % nbps;
-    for (int i = threadIdx.x; i < n; i += 256) {
-      const int rec = w.stage[(size_t)b * HW + (size_t)tile * kTile + i];
-      const int pl = rec & 2047, c = (rec >> 11) & 63, rk = rec >> 17;
-      const int pix = tile * kTile + pl;
-      const int slot = w.seg_start[c * B + b] + w.blk_cnt[(size_t)blk * C + c] + rk;
-      w.pix_list[slot] = b * HW + pix;
-      w.cls_list[slot] = c;
-      if (kEntropy) {
-        const float* p = probs + (size_t)b * C * HW + pix;
-        float ent = 0.f;
-        for (int k0 = 0; k0 < C; k0 += 8) {  // 8 strided loads in flight per pass
-          float v[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = (k0 + j < C) ? __ldg(p + (size_t)(k0 + j) * HW) : 1.0f;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) if (k0 + j < C) ent += v[j] * logf(v[j] + 1e-10f);
-        }
-        ent = -ent;
-        w_list[slot] = expf(-(ent * ent));
-        cnt_list[slot] = 0;
-      }
+  constexpr int kWarpShare = 128;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __shared__ int s_n[8];
+  for (int blk0 = blockIdx.x * 8; blk0 < nblk; blk0 += gridDim.x * 8) {
+    const int blk = blk0 + warp;
+    int n = 0;
+    if (blk < nblk) n = w.tile_tot[blk];
+    if (lane == 0) s_n[warp] = n;
+    if (n > 0) {
+      const int b = blk / nbps, tile = blk % nbps;
+      const size_t base = (size_t)b * HW + (size_t)tile * kTile;
+      for (int i = lane; i < min(n, kWarpShare); i += 32)
+        place_record<kEntropy>(w.stage[base + i], b, tile, blk, probs, HW, B, C, w, w_list, cnt_list);
     }
+    __syncthreads();
+    for (int t = 0; t < 8; ++t) {           // crowded tiles (dense labels): the CTA shares the rest
+      const int nt = s_n[t];
+      if (nt <= kWarpShare) continue;
+      const int bk = blk0 + t, b = bk / nbps, tile = bk % nbps;
+      const size_t base = (size_t)b * HW + (size_t)tile * kTile;
+      for (int i = kWarpShare + threadIdx.x; i < nt; i += 256)
+        place_record<kEntropy>(w.stage[base + i], b, tile, bk, probs, HW, B, C, w, w_list, cnt_list);
+    }
+    __syncthreads();
   }
 }
 
@@ -286,16 +324,20 @@ inline int launch_split(const long long* labels, const uint8_t* keep, const floa
                         int HW, int ignore_label, const SplitWs& w, float* w_list, int32_t* cnt_list,
                         float* zero_buf, int zero_n, cudaStream_t stream) {
   const int nbps = split_tiles_per_scan(HW), nblk = B * nbps;
+  // tiles per count CTA: enough CTAs for ~4 per SM, a power of two that divides the tiles per scan
+  int tpc = 1;
+  while (tpc < 8 && nbps % (tpc * 2) == 0 && nblk / (tpc * 2) >= kNumSMs * 4) tpc *= 2;
   int rc;
   { KernelTimer kt__("split_count_kernel", stream);
-    split_count_kernel<<<split_grid(nblk), 256, 0, stream>>>(labels, keep, HW, nbps, B, C, ignore_label, w,
-                                                             zero_buf, zero_n); }
+    split_count_kernel<<<split_grid(nblk / tpc), 256, 0, stream>>>(labels, keep, HW, nbps, tpc, B, C,
+                                                                   ignore_label, w, zero_buf, zero_n); }
   if ((rc = check_launch("split_count_kernel"))) return rc;
+  const int place_ctas = (nblk + 7) / 8;
   { KernelTimer kt__("split_place_kernel", stream);
     if (probs)
-      split_place_kernel<true><<<split_grid(nblk), 256, 0, stream>>>(probs, HW, nbps, nblk, B, C, w, w_list, cnt_list);
+      split_place_kernel<true><<<place_ctas, 256, 0, stream>>>(probs, HW, nbps, nblk, B, C, w, w_list, cnt_list);
     else
-      split_place_kernel<false><<<split_grid(nblk), 256, 0, stream>>>(nullptr, HW, nbps, nblk, B, C, w, nullptr, nullptr); }
+      split_place_kernel<false><<<place_ctas, 256, 0, stream>>>(nullptr, HW, nbps, nblk, B, C, w, nullptr, nullptr); }
   return check_launch("split_place_kernel");
 }
 

@@ -23,6 +23,8 @@
 
 #include "common.cuh"
 #include "labelsplit.cuh"
+#include "proto_internal.cuh"
+#include "rowgemm.cuh"
 
 namespace c3d {
 
@@ -40,10 +42,11 @@ struct EmaWs {
   size_t bytes;
 };
 
-static EmaWs carve_ema(void* base, int B, int C, int HW, int D, int M, long long max_rows) {
+static EmaWs carve_ema(void* base, int B, int C, int HW, int D, int M, long long max_rows,
+                       const SplitWs* shared = nullptr) {
   EmaWs w;
   size_t off = 0;
-  w.s = carve_split(base, &off, B, C, HW);
+  if (shared) w.s = *shared; else w.s = carve_split(base, &off, B, C, HW);
   auto take = [&](size_t n) { size_t o = off; off += split_align(n); return (char*)base + o; };
   w.bank_n = (float*)take((size_t)C * M * D * 4);
   w.feat = (float*)take((size_t)max_rows * D * 4);
@@ -197,6 +200,205 @@ ema_rows_kernel(EmaRowsParams p) {
   }
 }
 
+// ---------------------------------------------------------------- E2t ------
+// The same rows computation, register-tiled (rowgemm.cuh): a CTA takes a batch of up to kEmaGroups
+// groups of 16 rows, gathers + normalises them once, and then walks the bank tile by tile (tiles
+// end on class boundaries), multiplying every staged tile with all groups of the batch: each
+// bank element read from shared memory is reused for 4 rows, each staged tile for up to 64 rows.
+// Per (row, class) only the maximum over the M sub-prototypes is kept, plus the row's M
+// similarities to its own class -- the logits themselves live in a [16][tile] scratch.  Dot
+// products accumulate in the same order as ema_rows_kernel (bitwise equal similarities).
+constexpr int kEmaGroups = 4;
+constexpr int kEmaCPT = 4;            // tile_logits columns per thread -> tiles of <= 256 bank rows
+constexpr int kNvPad = kMaxClasses;   // per-row stride of the class-maximum scratch
+
+struct EmaTiledPlan { int tile_classes, n_tiles, ldl; size_t smem; };
+static int plan_ema_tiled(int D, int C, int M, EmaTiledPlan* out) {
+  const size_t budget = 227 * 1024 - 2048 - smem_reserve();
+  const BankLayout L = BankLayout::make(D);
+  const size_t fixed = (size_t)kEmaGroups * kGroupRows * ((size_t)D + kNvPad + kMaxSub) * 4;
+  for (int n_tiles = 1; n_tiles <= C; ++n_tiles) {
+    const int tc = (C + n_tiles - 1) / n_tiles;          // classes per tile
+    const int rows = tc * M;
+    if (rows > 64 * kEmaCPT) continue;
+    const int ldl = (rows + 3) & ~3;
+    const size_t need = fixed + (size_t)rows * L.ld * 4 + (size_t)kGroupRows * ldl * 4;
+    if (need <= budget) { out->tile_classes = tc; out->n_tiles = (C + tc - 1) / tc; out->ldl = ldl; out->smem = need; return 0; }
+  }
+  return -1;
+}
+
+template <int kDJ>
+__global__ void __launch_bounds__(256, 1)
+ema_rows_tiled_kernel(EmaRowsParams p, int tile_classes, int ldl, float* __restrict__ raw_rows) {
+  extern __shared__ __align__(16) float smem[];
+  const int D = p.D, M = p.M, C = p.C;
+  const BankLayout BL = BankLayout::make(D);
+  const int tile_cap = tile_classes * M;
+  float* s_bank = smem;                                        // [tile_cap] rows, layout BL
+  float* s_A = s_bank + (size_t)tile_cap * BL.ld;              // [G*16][D]
+  float* s_L = s_A + (size_t)kEmaGroups * kGroupRows * D;      // [16][ldl]
+  float* s_nv = s_L + (size_t)kGroupRows * ldl;                // [G*16][kNvPad] max over M per class
+  float* s_own = s_nv + (size_t)kEmaGroups * kGroupRows * kNvPad;   // [G*16][kMaxSub]
+  __shared__ int s_cls[kEmaGroups * kGroupRows];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_rows = p.info[kInfoPl];
+  if (n_rows > p.max_rows) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&p.info[kInfoFlags], kEmaOverflow);
+    return;
+  }
+  const int n_groups = (n_rows + kGroupRows - 1) / kGroupRows;
+  // groups per batch: as few as keeps every CTA busy once, at most kEmaGroups
+  int G = (n_groups + (int)gridDim.x - 1) / (int)gridDim.x;
+  G = G < 1 ? 1 : (G > kEmaGroups ? kEmaGroups : G);
+  const int n_batches = (n_groups + G - 1) / G;
+  const int n_tiles = (C + tile_classes - 1) / tile_classes;
+
+  for (int batch = blockIdx.x; batch < n_batches; batch += gridDim.x) {
+    const int row0 = batch * G * kGroupRows;
+    // first bank tile on its way while the rows are gathered
+    {
+      const int rows0 = min(tile_classes, C) * M;
+      stage_bank_tile_issue(s_bank, p.bank_n, 0, rows0, BL);
+    }
+    // ---- P0: gather, LayerNorm over D (salsanext_proto.py:498), L2 normalise (:501); two rows
+    //      per warp at a time, their load chains interleaved
+    for (int it = 0; it < G; ++it) {
+      float areg[2][kDJ];
+      int cls2[2]; bool act[2]; int rl2[2];
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+        rl2[rr] = it * kGroupRows + warp * 2 + rr;                // row within the batch
+        const int slot = row0 + rl2[rr];
+        act[rr] = slot < n_rows;
+        int gpix = 0; cls2[rr] = 0;
+        if (act[rr]) { gpix = p.pix_list[slot]; cls2[rr] = p.cls_list[slot]; }
+        const int b = gpix / p.HW, pix = gpix - b * p.HW;
+        const float* src = p.emb + (size_t)b * D * p.HW + pix;
+#pragma unroll
+        for (int j = 0; j < kDJ; ++j) {
+          const int d = lane + 32 * j;
+          areg[rr][j] = (act[rr] && d < D) ? __ldg(src + (size_t)d * p.HW) : 0.f;
+        }
+      }
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+        const int slot = row0 + rl2[rr];
+        if (raw_rows && act[rr]) {
+#pragma unroll
+          for (int j = 0; j < kDJ; ++j) { const int d = lane + 32 * j; if (d < D) raw_rows[(size_t)slot * D + d] = areg[rr][j]; }
+        }
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < kDJ; ++j) sum += areg[rr][j];          // d >= D lanes hold 0
+        const float mean = warp_sum(sum) / (float)D;
+        float v2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < kDJ; ++j) { const int d = lane + 32 * j; if (d < D) { const float t = areg[rr][j] - mean; v2 += t * t; } }
+        const float rstd = 1.0f / sqrtf(warp_sum(v2) / (float)D + p.eps);
+        float n2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < kDJ; ++j) {
+          const int d = lane + 32 * j;
+          if (d < D) { const float y = (areg[rr][j] - mean) * rstd * p.ln_d_w[d] + p.ln_d_b[d]; areg[rr][j] = y; n2 += y * y; }
+        }
+        const float inv = 1.0f / fmaxf(sqrtf(warp_sum(n2)), 1e-12f);
+#pragma unroll
+        for (int j = 0; j < kDJ; ++j) {
+          const int d = lane + 32 * j;
+          if (d < D) {
+            const float y = act[rr] ? areg[rr][j] * inv : 0.f;
+            s_A[(size_t)rl2[rr] * D + d] = y;
+            if (act[rr]) p.feat[(size_t)slot * D + d] = y;
+          }
+        }
+        if (lane == 0) s_cls[rl2[rr]] = act[rr] ? cls2[rr] : -1;
+      }
+    }
+    // ---- tiles of the bank x groups of the batch
+    for (int tile = 0; tile < n_tiles; ++tile) {
+      const int c0 = tile * tile_classes, tc = min(tile_classes, C - c0), rows = tc * M;
+      if (tile > 0) { __syncthreads(); stage_bank_tile_issue(s_bank, p.bank_n, c0 * M, rows, BL); }
+      cp_async_wait_all();
+      __syncthreads();
+      for (int g = 0; g < G; ++g) {
+        float acc[4][kEmaCPT];
+        tile_logits<kEmaCPT>(s_A + (size_t)g * kGroupRows * D, s_bank, rows, BL, acc);
+        const int cg = threadIdx.x & 63, rg = threadIdx.x >> 6;
+#pragma unroll
+        for (int i = 0; i < kEmaCPT; ++i) {
+          const int c = cg + 64 * i;
+          if (c < rows) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) s_L[(rg * 4 + r) * ldl + c] = acc[r][i];
+          }
+        }
+        __syncthreads();
+        // (row, class of the tile): maximum over the M sub-prototypes (:506)
+        for (int q = threadIdx.x; q < kGroupRows * tc; q += 256) {
+          const int r = q / tc, cc = q - r * tc;
+          const float* l = s_L + r * ldl + cc * M;
+          float m = -CUDART_INF_F;
+          for (int j = 0; j < M; ++j) m = fmaxf(m, l[j]);
+          s_nv[(size_t)(g * kGroupRows + r) * kNvPad + c0 + cc] = m;
+        }
+        // the row's similarities to its own class (sim[..., id_c], :352)
+        for (int q = threadIdx.x; q < kGroupRows * M; q += 256) {
+          const int r = q / M, j = q - r * M;
+          const int cls = s_cls[g * kGroupRows + r];
+          if (cls >= c0 && cls < c0 + tc) s_own[(size_t)(g * kGroupRows + r) * kMaxSub + j] = s_L[r * ldl + (cls - c0) * M + j];
+        }
+        __syncthreads();
+      }
+    }
+    // ---- per row: LayerNorm over C (:507), argmax (:340), mask (:341)
+    for (int rl = warp; rl < G * kGroupRows; rl += 8) {
+      const int slot = row0 + rl;
+      if (slot >= n_rows) continue;      // warp-uniform
+      const int cls = s_cls[rl];
+      float nv[2]; float sum = 0.f;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int c = lane + 32 * h;
+        nv[h] = (c < C) ? s_nv[(size_t)rl * kNvPad + c] : 0.f;
+        if (c < C) sum += nv[h];
+      }
+      const float mean = warp_sum(sum) / (float)C;
+      float v2 = 0.f;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) if (lane + 32 * h < C) { const float t = nv[h] - mean; v2 += t * t; }
+      const float rstd = 1.0f / sqrtf(warp_sum(v2) / (float)C + p.eps);
+      float best = -CUDART_INF_F; int best_c = 0x7fffffff;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int c = lane + 32 * h;
+        if (c < C) {
+          const float y = (nv[h] - mean) * rstd * p.ln_c_w[c] + p.ln_c_b[c];
+          if (y > best) { best = y; best_c = c; }
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oc = __shfl_xor_sync(0xffffffffu, best_c, o);
+        if (ob > best || (ob == best && oc < best_c)) { best = ob; best_c = oc; }
+      }
+      if (lane == 0) p.maskv[slot] = (best_c == cls);
+      if (lane < M) p.simq[(size_t)slot * M + lane] = s_own[(size_t)rl * kMaxSub + lane];
+    }
+    __syncthreads();   // the batch's scratch is reused
+  }
+}
+
+template <int kDJ>
+static int launch_ema_tiled(const EmaRowsParams& p, const EmaTiledPlan& plan, float* raw_rows, cudaStream_t stream) {
+  C3D_CUDA(cudaFuncSetAttribute(ema_rows_tiled_kernel<kDJ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)plan.smem));
+  KernelTimer kt__("ema_rows_kernel", stream);
+  ema_rows_tiled_kernel<kDJ><<<kNumSMs, 256, plan.smem, stream>>>(p, plan.tile_classes, plan.ldl, raw_rows);
+  return check_launch("ema_rows_tiled_kernel");
+}
+
 // ---------------------------------------------------------------- E2d ------
 // Rows from the DENSE tensors the reference's forward has already built
 // (salsanext_proto.py:497-510), for the drop-in `prototype_learning` (:337-402): out_feat
@@ -273,22 +475,12 @@ __device__ __forceinline__ void sink_row_sums(const float* Q, int n, int M, floa
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(kSinkWarps * 32)
-ema_sinkhorn_kernel(const int32_t* __restrict__ seg_cnt, const int32_t* __restrict__ seg_start,
-                    const int32_t* __restrict__ pix_list, int32_t* __restrict__ info, int B, int M,
-                    int ignore_label, int max_rows, float* __restrict__ simq,
-                    int32_t* __restrict__ sub, const float* __restrict__ gumbel, int mode,
-                    unsigned long long seed, float* __restrict__ proto_target) {
-  extern __shared__ float s_dyn[];
-  __shared__ float s_part[kSinkWarps * 32];
-  __shared__ float s_R[32];
-  __shared__ float s_tot;
-  const int c = blockIdx.x;
-  if (c == ignore_label || info[kInfoPl] > max_rows) return;
-  const int start = seg_start[c * B];
-  int n = 0;
-  for (int b = 0; b < B; ++b) n += seg_cnt[c * B + b];
-  if (n == 0) return;  // no such class (:356-357)
+// General path of the per-class assignment (any n): called by all kSinkWarps*32 threads of the CTA.
+__device__ void sinkhorn_general(float* s_dyn, float* s_part, float* s_R, float* s_tot_p, int c, int start, int n,
+                                 const int32_t* __restrict__ pix_list, int M, float* __restrict__ simq,
+                                 int32_t* __restrict__ sub, const float* __restrict__ gumbel, int mode,
+                                 unsigned long long seed, float* __restrict__ proto_target) {
+  float& s_tot = *s_tot_p;
   const int ne = n * M;
   const bool fits = ne + n <= kSinkSmemFloats;
   float* G = simq + (size_t)start * M;
@@ -383,35 +575,32 @@ ema_sinkhorn_kernel(const int32_t* __restrict__ seg_cnt, const int32_t* __restri
 }
 
 // ---------------------------------------------------------------- E4 -------
-// packed = [K*D sums | K counts]; one CTA per class.  The class's rows are dealt
-// round-robin to `nsplit` warps, each accumulating its rows in order into a private
-// shared-memory copy (lane owns feature columns); the copies are then added in warp
-// order.  Fixed assignment + fixed order => atomics-free and bitwise reproducible.
-__global__ void __launch_bounds__(256)
-ema_segsum_kernel(const int32_t* __restrict__ seg_cnt, const int32_t* __restrict__ seg_start,
-                  const int32_t* __restrict__ info, int B, int M, int D, int K, int ignore_label,
-                  int max_rows, int nsplit, const float* __restrict__ feat,
-                  const int32_t* __restrict__ maskv, const int32_t* __restrict__ sub,
-                  float* __restrict__ packed) {
-  extern __shared__ float s_sum[];  // [nsplit][M*D + M]
+// packed = [K*D sums | K counts] of one class.  The class's rows are dealt round-robin to
+// `nsplit` warps, each accumulating its rows in order into a private shared-memory copy (lane
+// owns feature columns); the copies are then added in warp order.  Fixed assignment + fixed
+// order => atomics-free and bitwise reproducible.  Called by all threads of the CTA.
+__device__ void segsum_class(float* s_sum, int c, int start, int n, int M, int D, int K, int nsplit,
+                             const float* __restrict__ feat, const int32_t* __restrict__ maskv,
+                             const int32_t* __restrict__ sub, float* __restrict__ packed) {
   const int stride = M * D + M;
-  const int c = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < nsplit * stride; i += blockDim.x) s_sum[i] = 0.f;
   __syncthreads();
-  int n = 0, start = 0;
-  if (c != ignore_label && info[kInfoPl] <= max_rows) {
-    start = seg_start[c * B];
-    for (int b = 0; b < B; ++b) n += seg_cnt[c * B + b];
-  }
   if (warp < nsplit) {
     float* acc = s_sum + (size_t)warp * stride;
-    for (int i = warp; i < n; i += nsplit) {
-      const int slot = start + i;
-      if (!maskv[slot]) continue;  // m_q = q * mask, c_q = feat * mask (:363-375)
-      const int m = sub[slot];
-      for (int d = lane; d < D; d += 32) acc[m * D + d] += feat[(size_t)slot * D + d];
-      if (lane == 0) acc[M * D + m] += 1.0f;
+    // rows warp, warp + nsplit, ... in order; 32 rows at a time: lane j fetches the (mask, sub)
+    // of the chunk's j-th row, so the feature loads below have no dependent address chain
+    for (int i0 = warp; i0 < n; i0 += nsplit * 32) {
+      const int mine = i0 + lane * nsplit;
+      int code = -1;                                   // -1: masked out / beyond n
+      if (mine < n && maskv[start + mine]) code = sub[start + mine];
+      for (int j = 0; j < 32; ++j) {
+        const int m = __shfl_sync(0xffffffffu, code, j);
+        if (m < 0) continue;                           // m_q = q * mask, c_q = feat * mask (:363-375)
+        const int slot = start + i0 + j * nsplit;
+        for (int d = lane; d < D; d += 32) acc[m * D + d] += feat[(size_t)slot * D + d];
+        if (lane == 0) acc[M * D + m] += 1.0f;
+      }
     }
   }
   __syncthreads();
@@ -421,6 +610,32 @@ ema_segsum_kernel(const int32_t* __restrict__ seg_cnt, const int32_t* __restrict
     if (i < M * D) packed[(size_t)c * M * D + i] = t;
     else packed[(size_t)K * D + c * M + (i - M * D)] = t;
   }
+}
+
+// One CTA per class: assignment (E3) and segmented sums (E4) in one launch.
+__global__ void __launch_bounds__(kSinkWarps * 32)
+ema_assign_sum_kernel(const int32_t* __restrict__ seg_cnt, const int32_t* __restrict__ seg_start,
+                      const int32_t* __restrict__ pix_list, int32_t* __restrict__ info, int B, int M,
+                      int D, int K, int ignore_label, int max_rows, int nsplit, float* __restrict__ simq,
+                      int32_t* __restrict__ sub, const float* __restrict__ gumbel, int mode,
+                      unsigned long long seed, const float* __restrict__ feat,
+                      const int32_t* __restrict__ maskv, float* __restrict__ packed,
+                      float* __restrict__ proto_target) {
+  extern __shared__ float s_dyn[];
+  __shared__ float s_part[kSinkWarps * 32];
+  __shared__ float s_R[32];
+  __shared__ float s_tot;
+  const int c = blockIdx.x;
+  int n = 0, start = 0;
+  if (c != ignore_label && info[kInfoPl] <= max_rows) {
+    start = seg_start[c * B];
+    for (int b = 0; b < B; ++b) n += seg_cnt[c * B + b];
+  }
+  if (n > 0)  // else: no such class (:356-357), its sums and counts are zero
+    sinkhorn_general(s_dyn, s_part, s_R, &s_tot, c, start, n, pix_list, M, simq, sub, gumbel, mode, seed,
+                     proto_target);
+  __syncthreads();   // sub[] of this class written (same CTA reads it below)
+  segsum_class(s_dyn, c, start, n, M, D, K, nsplit, feat, maskv, sub, packed);
 }
 
 // ---------------------------------------------------------------- E5 -------
@@ -481,14 +696,18 @@ extern "C" size_t c3d_proto_ema_workspace_bytes(int batch, int n_classes, int hw
   return carve_ema(nullptr, batch, n_classes, hw, dim, sub_protos, max_rows).bytes;
 }
 
-struct DenseRows { const float* out_feat; const float* nearest; const float* sim; };
+size_t c3d::ema_extra_bytes(int C, int D, int M, long long max_rows) {
+  SplitWs none{};
+  return carve_ema(nullptr, 1, C, 1, D, M, max_rows, &none).bytes;
+}
 
-static int proto_ema_accumulate_impl(
+int c3d::proto_ema_accumulate_impl(
     const float* embedding, const DenseRows* dense, const int64_t* label, const float* prototypes,
     const float* ln_d_w, const float* ln_d_b, const float* ln_c_w, const float* ln_c_b, float ln_eps,
     int batch, int dim, int proj_h, int proj_w, int n_classes, int sub_protos, int ignore_label,
     int64_t max_rows, const float* gumbel, int assign_mode, uint64_t seed, void* workspace,
-    float* packed, float* proto_target, void* stream_) {
+    const SplitWs* shared_split, float* packed, float* proto_target, void* stream_, float* raw_rows,
+    int rows_v1) {
   cudaStream_t stream = (cudaStream_t)stream_;
   const int B = batch, D = dim, C = n_classes, M = sub_protos;
   const long long HWll = (long long)proj_h * proj_w;
@@ -504,12 +723,12 @@ static int proto_ema_accumulate_impl(
     C3D_REQUIRE(dense->out_feat && dense->nearest && dense->sim && label && workspace && packed,
                 "null pointer argument");
   } else {
-    C3D_REQUIRE(embedding && label && prototypes && ln_d_w && ln_d_b && ln_c_w && ln_c_b &&
-                workspace && packed, "null pointer argument");
+    C3D_REQUIRE(embedding && (label || shared_split) && prototypes && ln_d_w && ln_d_b && ln_c_w &&
+                ln_c_b && workspace && packed, "null pointer argument");
   }
   C3D_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "workspace must be 256 B aligned");
   const int HW = (int)HWll, K = C * M;
-  EmaWs w = carve_ema(workspace, B, C, HW, D, M, max_rows);
+  EmaWs w = carve_ema(workspace, B, C, HW, D, M, max_rows, shared_split);
   int tile_rows = 0, n_tiles = 0; size_t smem = 0;
   C3D_REQUIRE(dense || ema_rows_config(D, K, &tile_rows, &n_tiles, &smem) == 0,
               "bank does not fit shared memory tiling (D=%d, K=%d)", D, K);
@@ -518,11 +737,13 @@ static int proto_ema_accumulate_impl(
   const size_t seg_smem = (size_t)seg_split * ((size_t)M * D + M) * sizeof(float);
   C3D_REQUIRE(seg_smem <= 227 * 1024, "M*D too large for the segmented-sum kernel");
 
-  C3D_CUDA(cudaMemsetAsync(w.s.info, 0, (size_t)(8 + B) * 4, stream));
   if (proto_target) C3D_CUDA(cudaMemsetAsync(proto_target, 0, (size_t)B * HW * 4, stream));
   int rc;
-  if ((rc = launch_split((const long long*)label, nullptr, nullptr, B, C, HW, ignore_label, w.s, nullptr,
-                         nullptr, nullptr, 0, stream))) return rc;
+  if (!shared_split) {
+    C3D_CUDA(cudaMemsetAsync(w.s.info, 0, (size_t)(8 + B) * 4, stream));
+    if ((rc = launch_split((const long long*)label, nullptr, nullptr, B, C, HW, ignore_label, w.s, nullptr,
+                           nullptr, nullptr, 0, stream))) return rc;
+  }
   if (!dense) {
     KernelTimer kt__("bank_normalise_kernel", stream);
     ema_bank_normalise_kernel<<<(K + 7) / 8, 256, 0, stream>>>(prototypes, K, D, w.bank_n);
@@ -542,24 +763,29 @@ static int proto_ema_accumulate_impl(
     p.info = w.s.info; p.feat = w.feat; p.simq = w.simq; p.maskv = w.maskv;
     p.HW = HW; p.D = D; p.M = M; p.C = C; p.K = K; p.tile_rows = tile_rows; p.n_tiles = n_tiles;
     p.max_rows = (int)max_rows; p.eps = ln_eps;
-    C3D_CUDA(cudaFuncSetAttribute(ema_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)smem));
-    { KernelTimer kt__("ema_rows_kernel", stream); ema_rows_kernel<<<kNumSMs, kEmaWarps * 32, smem, stream>>>(p); }
-    if ((rc = check_launch("ema_rows_kernel"))) return rc;
+    EmaTiledPlan plan;
+    if (!rows_v1 && D % 32 == 0 && D <= 256 && plan_ema_tiled(D, C, M, &plan) == 0) {
+      if (D <= 32) rc = launch_ema_tiled<1>(p, plan, raw_rows, stream);
+      else if (D <= 64) rc = launch_ema_tiled<2>(p, plan, raw_rows, stream);
+      else if (D <= 128) rc = launch_ema_tiled<4>(p, plan, raw_rows, stream);
+      else rc = launch_ema_tiled<8>(p, plan, raw_rows, stream);
+      if (rc) return rc;
+    } else {
+      C3D_REQUIRE(raw_rows == nullptr, "raw rows need the tiled EMA rows kernel (D %% 32 == 0, D <= 256)");
+      C3D_CUDA(cudaFuncSetAttribute(ema_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)smem));
+      { KernelTimer kt__("ema_rows_kernel", stream); ema_rows_kernel<<<kNumSMs, kEmaWarps * 32, smem, stream>>>(p); }
+      if ((rc = check_launch("ema_rows_kernel"))) return rc;
+    }
   }
-  C3D_CUDA(cudaFuncSetAttribute(ema_sinkhorn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                kSinkSmemFloats * 4));
-  { KernelTimer kt__("ema_sinkhorn_kernel", stream); ema_sinkhorn_kernel<<<C, kSinkWarps * 32, kSinkSmemFloats * 4, stream>>>(w.s.seg_cnt, w.s.seg_start, w.s.pix_list, w.s.info, B, M,
-                                             ignore_label, (int)max_rows, w.simq, w.sub, gumbel,
-                                             assign_mode, seed, proto_target); }
-  if ((rc = check_launch("ema_sinkhorn_kernel"))) return rc;
-  if (seg_smem > 48 * 1024)
-    C3D_CUDA(cudaFuncSetAttribute(ema_segsum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)seg_smem));
-  { KernelTimer kt__("ema_segsum_kernel", stream); ema_segsum_kernel<<<C, 256, seg_smem, stream>>>(w.s.seg_cnt, w.s.seg_start, w.s.info, B, M, D, K,
-                                                  ignore_label, (int)max_rows, seg_split, w.feat, w.maskv,
-                                                  w.sub, packed); }
-  return check_launch("ema_segsum_kernel");
+  size_t dyn = (size_t)kSinkSmemFloats * 4;
+  if (seg_smem > dyn) dyn = seg_smem;
+  C3D_CUDA(cudaFuncSetAttribute(ema_assign_sum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+  { KernelTimer kt__("ema_assign_sum_kernel", stream);
+    ema_assign_sum_kernel<<<C, kSinkWarps * 32, dyn, stream>>>(
+        w.s.seg_cnt, w.s.seg_start, w.s.pix_list, w.s.info, B, M, D, K, ignore_label, (int)max_rows, seg_split,
+        w.simq, w.sub, gumbel, assign_mode, seed, w.feat, w.maskv, packed, proto_target); }
+  return check_launch("ema_assign_sum_kernel");
 }
 
 extern "C" int c3d_proto_ema_accumulate(
@@ -570,8 +796,8 @@ extern "C" int c3d_proto_ema_accumulate(
     float* proto_target, void* stream) {
   return proto_ema_accumulate_impl(embedding, nullptr, label, prototypes, ln_d_w, ln_d_b, ln_c_w, ln_c_b,
                                    ln_eps, batch, dim, proj_h, proj_w, n_classes, sub_protos,
-                                   ignore_label, max_rows, gumbel, assign_mode, seed, workspace, packed,
-                                   proto_target, stream);
+                                   ignore_label, max_rows, gumbel, assign_mode, seed, workspace, nullptr,
+                                   packed, proto_target, stream, nullptr, 0);
 }
 
 extern "C" int c3d_proto_ema_accumulate_dense(
@@ -582,8 +808,8 @@ extern "C" int c3d_proto_ema_accumulate_dense(
   DenseRows d{out_feat, nearest, feat_proto_sim};
   return proto_ema_accumulate_impl(nullptr, &d, label, nullptr, nullptr, nullptr, nullptr, nullptr, 0.f,
                                    batch, dim, proj_h, proj_w, n_classes, sub_protos, ignore_label,
-                                   max_rows, gumbel, assign_mode, seed, workspace, packed, proto_target,
-                                   stream);
+                                   max_rows, gumbel, assign_mode, seed, workspace, nullptr, packed,
+                                   proto_target, stream, nullptr, 0);
 }
 
 extern "C" int c3d_proto_ema_apply(const float* prototypes_in, const float* packed, int n_classes,

@@ -29,6 +29,7 @@
 #include "common.cuh"
 #include "labelsplit.cuh"
 #include "rowgemm.cuh"
+#include "proto_internal.cuh"
 
 namespace c3d {
 
@@ -242,6 +243,8 @@ loss_sample_kernel(const int32_t* __restrict__ seg_cnt, const int32_t* __restric
 // ---------------------------------------------------------------- K5 -------
 struct RowsParams {
   const float* feats;      // (B, D, HW)
+  const float* raw_rows;   // [slots, D] un-normalised feature rows gathered by the EMA kernel, or null
+  int raw_cap;             // rows the EMA kernel had room for (more labelled pixels: it wrote none)
   const float* bank_n;     // (Kc, D)
   const int32_t* pix_list;
   const int32_t* cls_list;
@@ -517,6 +520,7 @@ loss_rows16_kernel(RowsParams p) {
   const int n_groups = (n_rows + kGroupRows - 1) / kGroupRows;
   const float scale_row = p.temperature / p.base_temperature;
   const float inv_R = 1.0f / ((float)p.A * (float)T);  // mean over R = A*T rows (:193)
+  const bool use_raw = p.raw_rows != nullptr && p.info[kInfoPl] <= p.raw_cap;
 
   DBG_STAMP(0);
   // single-tile case: start the bank copies now, complete them after the first gather
@@ -544,12 +548,21 @@ loss_rows16_kernel(RowsParams p) {
     }
 #pragma unroll
     for (int rr = 0; rr < 2; ++rr) {
-      const int b = gpix2[rr] / p.HW, pix = gpix2[rr] - b * p.HW;
-      const float* src = p.feats + (size_t)b * D * p.HW + pix;
+      if (use_raw) {      // fused step: the EMA kernel has left the row contiguous (512 B, coalesced)
+        const float* src = p.raw_rows + (size_t)slot[rr] * D;
 #pragma unroll
-      for (int j = 0; j < kDJ; ++j) {
-        const int d = lane + 32 * j;
-        areg[rr][j] = (act[rr] && d < D) ? __ldg(src + (size_t)d * p.HW) : 0.f;
+        for (int j = 0; j < kDJ; ++j) {
+          const int d = lane + 32 * j;
+          areg[rr][j] = (act[rr] && d < D) ? __ldcg(src + d) : 0.f;
+        }
+      } else {
+        const int b = gpix2[rr] / p.HW, pix = gpix2[rr] - b * p.HW;
+        const float* src = p.feats + (size_t)b * D * p.HW + pix;
+#pragma unroll
+        for (int j = 0; j < kDJ; ++j) {
+          const int d = lane + 32 * j;
+          areg[rr][j] = (act[rr] && d < D) ? __ldg(src + (size_t)d * p.HW) : 0.f;
+        }
       }
     }
 #pragma unroll
@@ -898,13 +911,21 @@ extern "C" size_t c3d_proto_loss_workspace_bytes(int batch, int n_classes, int h
   return carve(nullptr, batch, n_classes, hw, dim, sub_protos, num_anchor).bytes;
 }
 
-// phases: 1 = select (label split + anchor sampling), 2 = rows (loss and gradient rows).
-static int proto_loss_forward_impl(
+namespace c3d {
+size_t loss_ws_bytes(int B, int C, int HW, int D, int M, int A) { return carve(nullptr, B, C, HW, D, M, A).bytes; }
+SplitWs loss_ws_split(void* base, int B, int C, int HW, int D, int M, int A) { return carve(base, B, C, HW, D, M, A).s; }
+}  // namespace c3d
+using namespace c3d;
+
+// phases (internal bit mask): kPhaseSplit = label split, kPhaseSample = anchor sampling,
+// kPhaseRows = loss and gradient rows.  zero_buf / zero_n: a small buffer the split zeroes
+// on the side (the fused step's packed prototype sums).
+int c3d::proto_loss_forward_impl(
     const float* feats, const float* probs, const int64_t* labels, const uint8_t* keep_mask,
     const float* proto_queue, int batch, int dim, int proj_h, int proj_w, int n_classes,
     int sub_protos, int ignore_label, float temperature, float base_temperature, int num_anchor,
     const int64_t* keep, int keep_rows, uint64_t seed, int need_grad, int phases, void* workspace,
-    float* loss_out, void* stream_) {
+    float* loss_out, float* zero_buf, int zero_n, void* stream_, const float* raw_rows, int raw_cap) {
   cudaStream_t stream = (cudaStream_t)stream_;
   const int B = batch, D = dim, C = n_classes, M = sub_protos;
   const long long HWll = (long long)proj_h * proj_w;
@@ -913,8 +934,10 @@ static int proto_loss_forward_impl(
   C3D_REQUIRE(D > 0 && D % 4 == 0 && D <= 1024, "feature dim must be a multiple of 4, <= 1024");
   C3D_REQUIRE(M > 0 && num_anchor > 0, "sub_protos and num_anchor must be positive");
   C3D_REQUIRE(HWll > 0 && B * HWll < (1ll << 31), "batch*H*W must be < 2^31");
-  C3D_REQUIRE(feats && probs && labels && proto_queue && workspace && loss_out,
-              "null pointer argument");
+  C3D_REQUIRE(workspace, "null workspace");
+  C3D_REQUIRE(!(phases & kPhaseSplit) || (probs && labels), "null pointer argument (probs / labels)");
+  C3D_REQUIRE(!(phases & kPhaseRows) || (feats && proto_queue && loss_out),
+              "null pointer argument (feats / proto_queue / loss_out)");
   C3D_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "workspace must be 256 B aligned");
   C3D_REQUIRE(temperature > 0 && base_temperature > 0, "temperatures must be positive");
   const int HW = (int)HWll;
@@ -925,10 +948,12 @@ static int proto_loss_forward_impl(
               "bank does not fit shared memory tiling (D=%d, Kc=%d)", D, Kc);
 
   int rc;
-  if (phases & 1) {
+  if (phases & kPhaseSplit) {
   C3D_CUDA(cudaMemsetAsync(w.s.info, 0, (size_t)(8 + B) * 4, stream));
   if ((rc = launch_split((const long long*)labels, keep_mask, probs, B, C, HW, ignore_label, w.s, w.w_list,
-                         w.cnt_list, nullptr, 0, stream))) return rc;
+                         w.cnt_list, zero_buf, zero_n, stream))) return rc;
+  }
+  if (phases & kPhaseSample) {
   { KernelTimer kt__("loss_sample_kernel", stream);
     loss_sample_kernel<<<B * C, 256, 0, stream>>>(w.s.seg_cnt, w.s.seg_start, w.s.seg_tidx, w.s.pix_list,
                                                   w.w_list, w.cnt_list, HW, B, C, num_anchor,
@@ -936,7 +961,7 @@ static int proto_loss_forward_impl(
                                                   w.row_base, w.seg_of_t, w.s.info); }
   if ((rc = check_launch("loss_sample_kernel"))) return rc;
   }
-  if (!(phases & 2)) return C3D_OK;
+  if (!(phases & kPhaseRows)) return C3D_OK;
 
   // F.normalize of the bank rows of classes 1..C-1 (:167).  Part of phase 2: the bank may be
   // written between the phases (the EMA update precedes the loss in a training step,
@@ -946,7 +971,7 @@ static int proto_loss_forward_impl(
   if ((rc = check_launch("bank_normalise_kernel"))) return rc;
 
   RowsParams p{};
-  p.feats = feats; p.bank_n = w.bank_n; p.pix_list = w.s.pix_list; p.cls_list = w.s.cls_list;
+  p.feats = feats; p.raw_rows = raw_rows; p.raw_cap = raw_cap; p.bank_n = w.bank_n; p.pix_list = w.s.pix_list; p.cls_list = w.s.cls_list;
   p.cnt_list = w.cnt_list; p.dist_list = reinterpret_cast<const int32_t*>(w.w_list);
   p.seg_start = w.s.seg_start; p.row_base = w.row_base; p.seg_of_t = w.seg_of_t; p.info = w.s.info;
   p.loss_part = w.loss_part; p.row_pix = w.row_pix; p.grad_rows = w.grad_rows; p.loss_out = loss_out;
@@ -969,6 +994,7 @@ static int proto_loss_forward_impl(
     if (D <= 256) return launch_rows16<false, 1, 4, 1, 8>(p, plan.smem, stream);
     return launch_rows16<false, 1, 4, 4, 32>(p, plan.smem, stream);
   }
+  C3D_REQUIRE(raw_rows == nullptr, "raw rows need the tiled loss rows kernel");
   if (!need_grad) return launch_rows<false, 1>(p, smem, stream);
   if (D <= 128) return launch_rows<true, 1>(p, smem, stream);
   if (D <= 256) return launch_rows<true, 2>(p, smem, stream);
@@ -984,8 +1010,9 @@ extern "C" int c3d_proto_loss_forward(
     float* loss_out, void* stream) {
   return proto_loss_forward_impl(feats, probs, labels, keep_mask, proto_queue, batch, dim, proj_h, proj_w,
                                  n_classes, sub_protos, ignore_label, temperature, base_temperature,
-                                 num_anchor, keep, keep_rows, seed, need_grad, 3, workspace, loss_out,
-                                 stream);
+                                 num_anchor, keep, keep_rows, seed, need_grad,
+                                 kPhaseSplit | kPhaseSample | kPhaseRows, workspace, loss_out, nullptr, 0,
+                                 stream, nullptr, 0);
 }
 
 extern "C" int c3d_proto_loss_forward_phase(
@@ -995,10 +1022,11 @@ extern "C" int c3d_proto_loss_forward_phase(
     const int64_t* keep, int keep_rows, uint64_t seed, int need_grad, int phases, void* workspace,
     float* loss_out, void* stream) {
   C3D_REQUIRE(phases >= 1 && phases <= 3, "phases must be 1 (select), 2 (rows) or 3 (both)");
+  const int internal = ((phases & 1) ? (kPhaseSplit | kPhaseSample) : 0) | ((phases & 2) ? kPhaseRows : 0);
   return proto_loss_forward_impl(feats, probs, labels, keep_mask, proto_queue, batch, dim, proj_h, proj_w,
                                  n_classes, sub_protos, ignore_label, temperature, base_temperature,
-                                 num_anchor, keep, keep_rows, seed, need_grad, phases, workspace, loss_out,
-                                 stream);
+                                 num_anchor, keep, keep_rows, seed, need_grad, internal, workspace, loss_out,
+                                 nullptr, 0, stream, nullptr, 0);
 }
 
 extern "C" int c3d_proto_loss_backward(int batch, int dim, int proj_h, int proj_w, int n_classes,

@@ -67,12 +67,13 @@ __device__ __forceinline__ void stage_bank_tile(float* s_bank, const float* __re
 // computed on a clamped (valid) row and must be discarded by the caller: keeping the
 // inner loop branch-free lets the compiler batch the ten 128-bit loads of an iteration
 // (with per-column guards it serialised load -> use, 4x slower).
+template <int kCPT = kColsPerThread>
 __device__ __forceinline__ void tile_logits(const float* s_A, const float* s_bank, int rows,
-                                            const BankLayout& L, float (&acc)[4][kColsPerThread]) {
+                                            const BankLayout& L, float (&acc)[4][kCPT]) {
   const int cg = threadIdx.x & 63, rg = threadIdx.x >> 6;
-  int rowoff[kColsPerThread], sw[kColsPerThread];
+  int rowoff[kCPT], sw[kCPT];
 #pragma unroll
-  for (int i = 0; i < kColsPerThread; ++i) {
+  for (int i = 0; i < kCPT; ++i) {
     const int c = min(cg + 64 * i, rows - 1);
     rowoff[i] = c * L.ld;
     sw[i] = L.swz ? (c & 7) : 0;
@@ -80,19 +81,19 @@ __device__ __forceinline__ void tile_logits(const float* s_A, const float* s_ban
 #pragma unroll
   for (int r = 0; r < 4; ++r)
 #pragma unroll
-    for (int i = 0; i < kColsPerThread; ++i) acc[r][i] = 0.f;
+    for (int i = 0; i < kCPT; ++i) acc[r][i] = 0.f;
   const int d4 = L.D >> 2;
   const float4* a_base = reinterpret_cast<const float4*>(s_A) + (size_t)(rg * 4) * d4;
 #pragma unroll 2
   for (int j = 0; j < d4; ++j) {
-    float4 a[4], b[kColsPerThread];
+    float4 a[4], b[kCPT];
 #pragma unroll
     for (int r = 0; r < 4; ++r) a[r] = a_base[r * d4 + j];  // warp-wide broadcast
 #pragma unroll
-    for (int i = 0; i < kColsPerThread; ++i)
+    for (int i = 0; i < kCPT; ++i)
       b[i] = *reinterpret_cast<const float4*>(s_bank + rowoff[i] + ((j ^ sw[i]) << 2));
 #pragma unroll
-    for (int i = 0; i < kColsPerThread; ++i) {
+    for (int i = 0; i < kCPT; ++i) {
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
         acc[r][i] += a[r].x * b[i].x; acc[r][i] += a[r].y * b[i].y;

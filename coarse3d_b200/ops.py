@@ -629,6 +629,31 @@ def proto_ema_apply(prototypes, packed, momentum, ignore_label=0, out=None):
     return out
 
 
+STEP_SPLIT, STEP_SAMPLE, STEP_ACCUMULATE, STEP_LOSS_ROWS = 1, 2, 4, 8
+
+
+def proto_step_workspace(batch, n_classes, hw, dim, sub_protos, num_anchor, max_rows, device):
+    n = lib.c3d_proto_step_workspace_bytes(batch, n_classes, hw, dim, sub_protos, num_anchor, int(max_rows))
+    if n == 0:
+        raise ValueError("bad prototype-step shape")
+    return torch.empty((n,), dtype=torch.uint8, device=device)
+
+
+def proto_step_raw(phases, feats, probs, labels, keep_mask, prototypes, ln_d_w, ln_d_b, ln_c_w, ln_c_b,
+                   cfg, workspace, packed, loss_out, max_rows, ln_eps=1e-5, keep=None,
+                   gumbel=None, assign_mode=ASSIGN_GUMBEL_DEVICE, seed=0, need_grad=True, proto_target=None):
+    """c3d_proto_step on pre-validated device tensors (no autograd, no allocation): the phases of
+    the fused EMA-update + loss step (STEP_* bit mask) on one shared label split."""
+    B, D, H, W = feats.shape
+    C, M, _ = prototypes.shape
+    check(lib.c3d_proto_step(
+        _p(feats), _p(probs), _p(labels), _p(keep_mask), _p(prototypes), _p(ln_d_w), _p(ln_d_b), _p(ln_c_w),
+        _p(ln_c_b), float(ln_eps), B, D, H, W, C, M, int(cfg.ignore_label), float(cfg.temperature),
+        float(cfg.base_temperature), int(cfg.num_anchor), _p(keep), 0 if keep is None else keep.shape[0],
+        _p(gumbel), int(assign_mode), int(seed), int(max_rows), 1 if need_grad else 0, int(phases),
+        _p(workspace), _p(packed), _p(proto_target), _p(loss_out), _stream()))
+
+
 class concurrent_hint:
     """Context manager around multi-stream use of the library (c3d_set_concurrent_hint)."""
 

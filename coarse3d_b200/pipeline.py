@@ -78,11 +78,15 @@ class HotPathStep:
             torch.randn((C, sub_protos, dim), device=self.device, generator=g), dim=-1)
         self.ln_d = (torch.ones(dim, device=self.device), torch.zeros(dim, device=self.device))
         self.ln_c = (torch.ones(C, device=self.device), torch.zeros(C, device=self.device))
-        self.loss_ws = ops.proto_loss_workspace(batch, C, H * W, dim, sub_protos, num_anchor, self.device)
+        self.max_rows = min(batch * H * W, 1 << 17)
+        # fused prototype step (one label split for the EMA update and the loss); its workspace
+        # begins with a loss workspace, so the unfused calls can run on it too
+        self.fused_step = _os.environ.get("C3D_FUSED_STEP", "1") == "1"
+        self.loss_ws = ops.proto_step_workspace(batch, C, H * W, dim, sub_protos, num_anchor, self.max_rows,
+                                                self.device)
         self.loss = torch.zeros((), device=self.device)
         self.grad_out = torch.ones((), device=self.device)
         self.grad = torch.empty((batch, dim, H, W), device=self.device)
-        self.max_rows = min(batch * H * W, 1 << 17)
         nws = ops.lib.c3d_proto_ema_workspace_bytes(batch, C, H * W, dim, sub_protos, self.max_rows)
         self.ema_ws = torch.empty((nws,), dtype=torch.uint8, device=self.device)
         K = C * sub_protos
@@ -110,6 +114,7 @@ class HotPathStep:
                      torch.cuda.Stream(self.device, priority=hi)]   # loss chain
         (self.ev_fork, self.ev_fill, self.ev_proj, self.ev_ema, self.ev_loss,
          self.ev_resolved, self.ev_selected) = (torch.cuda.Event() for _ in range(7))
+        self.ev_split = torch.cuda.Event()
         self.knn_after_select = _os.environ.get("C3D_KNN_AFTER_SELECT", "0") == "1"
         self.knn_split = int(_os.environ.get("C3D_KNN_SPLIT", "0"))   # scans in the first of two KNN launches
         torch.cuda.synchronize(self.device)
@@ -137,8 +142,13 @@ class HotPathStep:
         fused = self.schedule == "fill_in_knn" and {"knn", "fill"} <= self.parts
         if not self.concurrent:
             pr = ops.project_batch(s.points, s.offsets, self.fov, H, W, buffers=b)
-            self._ema(s, seed)            # the bank is updated in the model forward, before the loss
-            self._loss_fwd(s, seed)
+            if self.fused_step:
+                self._step(ops.STEP_SPLIT | ops.STEP_SAMPLE | ops.STEP_ACCUMULATE, s.labels, s, seed)
+                self._ema_finish()
+                self._step(ops.STEP_LOSS_ROWS, s.labels, s, seed)
+            else:
+                self._ema(s, seed)            # the bank is updated in the model forward, before the loss
+                self._loss_fwd(s, seed)
             if fused:
                 self._knn(s, pr, C, cofill=self.grad)
             ops.proto_loss_backward_raw(s.feats.shape, self.cfg, C, self.M, self.loss_ws, self.grad_out,
@@ -234,18 +244,33 @@ class HotPathStep:
                 if "fill" in P:
                     ops.zero_fill(self.grad)
                 self.ev_fill.record(st_fill)
-        with torch.cuda.stream(st_ema):
-            if "ema" in P:
-                self._ema(s, seed)
-            self.ev_ema.record(st_ema)
+        fused_step = self.fused_step and {"loss", "ema"} <= P and not hold
+        if fused_step:
+            # one label split for both operators, then the sampler next to the EMA chain
+            with torch.cuda.stream(st_loss):
+                self._step(ops.STEP_SPLIT, s.labels, s, seed)
+                self.ev_split.record(st_loss)
+                self._step(ops.STEP_SAMPLE, s.labels, s, seed)
+            with torch.cuda.stream(st_ema):
+                st_ema.wait_event(self.ev_split)
+                self._step(ops.STEP_ACCUMULATE, s.labels, s, seed)
+                self._ema_finish()
+                self.ev_ema.record(st_ema)
+        else:
+            with torch.cuda.stream(st_ema):
+                if "ema" in P:
+                    self._ema(s, seed)
+                self.ev_ema.record(st_ema)
         with torch.cuda.stream(st_loss):
             # The selection phase (label split, anchor sampling) does not read the bank and runs
             # next to the EMA chain; the rows phase reads the bank the EMA has just updated
             # (salsanext_proto.py:520-527 runs inside model.forward, trainer.py:675-686 after it).
-            if "loss" in P and not hold:
+            if "loss" in P and not hold and not fused_step:
                 self._loss_fwd(s, seed, phases=1)
             st_loss.wait_event(self.ev_ema)
-            if "loss" in P:
+            if fused_step:
+                self._step(ops.STEP_LOSS_ROWS, s.labels, s, seed)
+            elif "loss" in P:
                 self._loss_fwd(s, seed, phases=2)
             st_loss.wait_event(self.ev_fill)
             if "loss" in P:
@@ -282,20 +307,19 @@ class HotPathStep:
                           inv_gauss=self.inv_gauss, out=self.knn_out, cofill=self.grad)
             self.ev_proj.record(st_proj)
         labels = asm.train_label
-        with torch.cuda.stream(st_ema):
-            st_ema.wait_event(self.ev_resolved)
-            distributed.prototype_update(
-                s.feats, labels, self.protos, *self.ln_d, *self.ln_c, self.momentum,
-                assign_mode=ops.ASSIGN_GUMBEL_DEVICE, seed=seed, max_rows=self.max_rows, group=self.group,
-                workspace=self.ema_ws, packed=self.packed, out=self.protos)
-            self.ev_ema.record(st_ema)
         with torch.cuda.stream(st_loss):
             st_loss.wait_event(self.ev_resolved)
-            ops.proto_loss_forward_raw(s.feats, s.probs, labels, None, self.protos, self.cfg, None, seed,
-                                       self.loss_ws, self.loss, phases=1)
+            self._step(ops.STEP_SPLIT, labels, s, seed)
+            self.ev_split.record(st_loss)
+            self._step(ops.STEP_SAMPLE, labels, s, seed)
+        with torch.cuda.stream(st_ema):
+            st_ema.wait_event(self.ev_split)
+            self._step(ops.STEP_ACCUMULATE, labels, s, seed)
+            self._ema_finish()
+            self.ev_ema.record(st_ema)
+        with torch.cuda.stream(st_loss):
             st_loss.wait_event(self.ev_ema)           # the rows phase reads the updated bank
-            ops.proto_loss_forward_raw(s.feats, s.probs, labels, None, self.protos, self.cfg, None, seed,
-                                       self.loss_ws, self.loss, phases=2)
+            self._step(ops.STEP_LOSS_ROWS, labels, s, seed)
             st_loss.wait_event(self.ev_proj)          # the vote has zero-filled self.grad
             ops.proto_loss_backward_raw(s.feats.shape, self.cfg, C, self.M, self.loss_ws, self.grad_out,
                                         self.grad, grad_is_zeroed=True)
@@ -325,6 +349,16 @@ class HotPathStep:
     def _last_proj(self, b):
         return ops.Projection(b.proj_pointcloud, b.proj_range, b.proj_idx, b.proj_mask,
                               b.uproj_x_idx, b.uproj_y_idx, b.uproj_depth, b.flags)
+
+    def _step(self, phases, labels, s, seed):
+        ops.proto_step_raw(phases, s.feats, s.probs, labels, None, self.protos, *self.ln_d, *self.ln_c,
+                           self.cfg, self.loss_ws, self.packed, self.loss, self.max_rows,
+                           assign_mode=ops.ASSIGN_GUMBEL_DEVICE, seed=seed)
+
+    def _ema_finish(self):
+        """all-reduce of the packed sums (N > 1) + the EMA itself, in place on the bank"""
+        distributed.allreduce_packed(self.packed, self.group)
+        ops.proto_ema_apply(self.protos, self.packed, self.momentum, 0, out=self.protos)
 
     def _loss_fwd(self, s, seed, phases=3):
         ops.proto_loss_forward_raw(s.feats, s.probs, s.labels, s.keep_mask, self.protos, self.cfg,

@@ -387,6 +387,31 @@ int c3d_proto_ema_apply(
     float* prototypes_out,        /* [C, M, D] (may alias prototypes_in)         */
     void* stream);
 
+/* -------------------------------------------------------- a2 + a3 fused ----
+ * The prototype step of a training iteration: the EMA update inside model.forward
+ * (salsanext_proto.py:520-527) followed by ContrastMEMLoss on the UPDATED bank
+ * (tasks/weak_segmentation/trainer.py:675-686), for callers whose two operators see the same
+ * label image (weak labels; `entropy_selection` off).  Everything derived from the labels is
+ * shared: one label split feeds the loss's anchor sampler and the EMA's row kernels.
+ * phases (bit mask, each phase needs the earlier ones on the same workspace):
+ *   1 split, 2 anchor sampling, 4 EMA accumulation -> packed, 8 loss + gradient rows.
+ * Between 4 and 8 the caller all-reduces `packed` (multi-GPU) and calls c3d_proto_ema_apply
+ * (in place on `prototypes`); after 8, c3d_proto_loss_backward / _info / _rows take the same
+ * workspace (it begins with a loss workspace of the same shape).  Arguments as in
+ * c3d_proto_loss_forward and c3d_proto_ema_accumulate; pointers a phase does not use may be NULL.
+ * With keep_mask the masked labels are what BOTH operators see. */
+size_t c3d_proto_step_workspace_bytes(int batch, int n_classes, int hw, int dim, int sub_protos,
+                                      int num_anchor, int64_t max_rows);
+
+int c3d_proto_step(
+    const float* feats, const float* probs, const int64_t* labels, const uint8_t* keep_mask,
+    const float* prototypes, const float* ln_d_w, const float* ln_d_b, const float* ln_c_w,
+    const float* ln_c_b, float ln_eps, int batch, int dim, int proj_h, int proj_w, int n_classes,
+    int sub_protos, int ignore_label, float temperature, float base_temperature, int num_anchor,
+    const int64_t* keep, int keep_rows, const float* gumbel, int assign_mode, uint64_t seed,
+    int64_t max_rows, int need_grad, int phases, void* workspace, float* packed, float* proto_target,
+    float* loss_out, void* stream);
+
 /* Synchronous: copies {segments, labelled rows, flags, 0} to host_info4 (host). */
 int c3d_proto_ema_info(const void* workspace, int32_t* host_info4, void* stream);
 

@@ -125,3 +125,58 @@ def test_loss_reads_the_updated_bank(cuda_device, monkeypatch):
     assert torch.equal(out, loss)
     ops.proto_loss_forward_raw(s.feats, s.probs, s.labels, s.keep_mask, bank0, step.cfg, None, 5, ws, out)
     assert not torch.equal(out, loss)
+
+
+def test_fused_step_equals_separate_operators(cuda_device, monkeypatch):
+    """c3d_proto_step (one label split shared by the EMA update and the loss) must reproduce the
+    two operators called one after the other, bit for bit."""
+    outs = []
+    for fused in ("0", "1"):
+        monkeypatch.setenv("C3D_FUSED_STEP", fused)
+        for concurrent in (False, True):
+            step = _step(monkeypatch, "fill_in_knn", concurrent)
+            assert step.fused_step == (fused == "1")
+            step.grad.fill_(5.0)
+            step.run(0, seed=3)
+            step.run(1, seed=4)          # second step: the bank of the first one is the input
+            outs.append(_outputs(step))
+    for o in outs[1:]:
+        for a, b in zip(o, outs[0]):
+            assert torch.equal(a, b)
+
+
+def test_proto_step_phases_against_the_two_entry_points(cuda_device):
+    from coarse3d_b200 import ops
+    B, D, H, W, C, M, A = 2, 32, 16, 128, 7, 4, 64
+    g = torch.Generator().manual_seed(21)
+    feats = torch.randn(B, D, H, W, generator=g).cuda()
+    probs = torch.softmax(torch.randn(B, C, H, W, generator=g), 1).cuda()
+    labels = (torch.randint(1, C, (B, H, W), generator=g) * (torch.rand(B, H, W, generator=g) < 0.05)).cuda()
+    protos = torch.nn.functional.normalize(torch.randn(C, M, D, generator=g), dim=-1).cuda()
+    ln = [torch.ones(D).cuda(), torch.zeros(D).cuda(), torch.ones(C).cuda(), torch.zeros(C).cuda()]
+    cfg = ops.ProtoLossConfig(0, 0.07, 0.07, A)
+    # separate operators: EMA (argmax assignment), then the loss on the updated bank
+    acc = ops.proto_ema_accumulate(feats, labels, protos, *ln, assign_mode=ops.ASSIGN_ARGMAX)
+    bank1 = ops.proto_ema_apply(protos, acc.packed, 0.9)
+    f1 = feats.clone().requires_grad_(True)
+    want, _ = ops.proto_loss(f1, probs, labels, None, bank1, cfg, seed=17)
+    want.backward()
+    # fused
+    max_rows = B * H * W
+    ws = ops.proto_step_workspace(B, C, H * W, D, M, A, max_rows, "cuda")
+    packed = torch.empty(C * M * D + C * M, device="cuda")
+    loss = torch.zeros((), device="cuda")
+    bank = protos.clone()
+    common = dict(assign_mode=ops.ASSIGN_ARGMAX, seed=17)
+    ops.proto_step_raw(ops.STEP_SPLIT | ops.STEP_SAMPLE | ops.STEP_ACCUMULATE, feats, probs, labels, None, bank,
+                       *ln, cfg, ws, packed, loss, max_rows, **common)
+    assert torch.equal(packed, acc.packed)
+    ops.proto_ema_apply(bank, packed, 0.9, out=bank)
+    assert torch.equal(bank, bank1)
+    ops.proto_step_raw(ops.STEP_LOSS_ROWS, feats, probs, labels, None, bank, *ln, cfg, ws, packed, loss,
+                       max_rows, **common)
+    assert torch.equal(loss, want.detach())
+    grad = torch.empty_like(feats)
+    ops.proto_loss_backward_raw(feats.shape, cfg, C, M, ws, torch.ones((), device="cuda"), grad)
+    assert torch.equal(grad, f1.grad)
+    assert ops.proto_loss_info(ws)[1] == int((labels > 0).sum())
