@@ -43,7 +43,6 @@ def _load():
         "c3d_lovasz_forward": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int64, P, P, P]),
         "c3d_lovasz_backward": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int64, P, P, P, c_int, P]),
         "c3d_lovasz_info": (c_int, [P, P, P]),
-        "c3d_set_concurrent_hint": (c_int, [c_int]),
         "c3d_knn_batch": (c_int, [P, P, P, P, P, P, c_int, c_int64, c_int, c_int, c_int, c_int,
                                   c_float, c_int, P, c_int, c_int, P, P, c_size_t, P]),
         "c3d_profile_enable": (c_int, [c_char_p]),
@@ -71,12 +70,13 @@ def _load():
                                              c_int, c_int, c_int, c_int64, P, c_int, c_uint64, P, P, P, P]),
         "c3d_proto_ema_accumulate_dense": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                                    c_int64, P, c_int, c_uint64, P, P, P, P]),
-        "c3d_proto_ema_apply": (c_int, [P, P, c_int, c_int, c_int, c_int, c_double, P, P]),
+        "c3d_proto_ema_apply": (c_int, [P, P, c_int, c_int, c_int, c_int, c_double, P, P, P, P]),
         "c3d_proto_ema_info": (c_int, [P, P, P]),
+        "c3d_proto_bank_normalise": (c_int, [P, c_int, c_int, P, P]),
         "c3d_proto_step_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int, c_int64]),
         "c3d_proto_step": (c_int, [P, P, P, P, P, P, P, P, P, c_float, c_int, c_int, c_int, c_int, c_int, c_int,
                                    c_int, c_float, c_float, c_int, P, c_int, P, c_int, c_uint64, c_int64, c_int,
-                                   c_int, P, P, P, P, P]),
+                                   c_int, P, P, P, P, P, P, P]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported

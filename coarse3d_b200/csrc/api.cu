@@ -12,7 +12,6 @@ namespace c3d {
 
 static thread_local char t_error[512] = "";
 std::atomic<long long> g_launches{0};
-std::atomic<int> g_concurrent_hint{0};
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -119,6 +118,3 @@ extern "C" int c3d_profile_reset(void) {
 extern "C" int c3d_version(void) { return 100; }
 extern "C" const char* c3d_last_error(void) { return c3d::t_error; }
 extern "C" long long c3d_launch_count(void) { return c3d::g_launches.load(); }
-extern "C" int c3d_set_concurrent_hint(int on) {
-  return c3d::g_concurrent_hint.exchange(on < 0 ? 0 : on);
-}

@@ -15,12 +15,6 @@ constexpr int kMaxBatch = 4096;
 
 void set_error(const char* fmt, ...);
 extern std::atomic<long long> g_launches;
-extern std::atomic<int> g_concurrent_hint;  // c3d_set_concurrent_hint
-
-// Shared memory (bytes) the whole-SM kernels leave free when the caller runs the library on
-// several streams (c3d_set_concurrent_hint): room for the fill daemon's CTA (zero page + the
-// per-CTA reservation) next to a rows kernel on the same SM.
-inline size_t smem_reserve() { return g_concurrent_hint.load(std::memory_order_relaxed) >= 2 ? 12 * 1024 : 0; }
 
 // RAII device timer around one kernel launch; a no-op unless c3d_profile_enable.
 class KernelTimer {

@@ -32,7 +32,6 @@
 //   3  (default) the same with an L2 evict-first policy on the copies, so the zero lines do
 //      not displace the range / class images the vote gathers from (113 us; step -2 %).
 #include <math_constants.h>
-#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -320,28 +319,14 @@ static int launch_knn_sk(const float* proj_range, const void* proj_argmax, const
     const unsigned long long n4 = cofill_bytes / 16;
     unsigned long long per_cta = (n4 + grid - 1) / grid;
     per_cta = (per_cta + 511) / 512 * 512;  // whole 8 KB pages (and 4 KB CTA-wide store rounds)
-    const char* env = getenv("C3D_KNN_COFILL_MODE");
-    const int mode = (env && env[0] >= '1' && env[0] <= '3') ? env[0] - '0' : 3;
-    // C3D_KNN_FILL_CTAS=4: pad the dynamic shared memory to 38 KB so that only 4 (not 5) CTAs
-    // are resident per SM, leaving registers for the small kernels of the other chains.
-    const char* env4 = getenv("C3D_KNN_FILL_CTAS");
-    const size_t smem_fill = (env4 && env4[0] == '4' && smem < 38 * 1024) ? 38 * 1024 : smem;  // + 8.3 KB static
-    const char* envp = getenv("C3D_KNN_FILL_EARLY");   // how a CTA spreads its share of the fill
-    const int fill_early = (envp && envp[0] >= '0' && envp[0] <= '2') ? envp[0] - '0' : 2;  // 0: S parts while the window
-    // loads, 1: whole share up front (measured worst), 2 (default): S + 3 parts down to the vote
+    // Co-fill form: TMA bulk stores of a zero page with an L2 evict-first policy, spread over
+    // S + 3 instalments from the window loads down to the vote (the measured best of the
+    // variants described at the top of this file).
+    const int fill_early = 2;
     KernelTimer timer("knn_vote_fill_kernel", stream);
-    if (mode == 3)
-      knn_vote_kernel<S, KT, 3><<<grid, threads, smem_fill, stream>>>(
-          proj_range, proj_argmax, unproj_range, px, py, offsets, batch, total, H, W, knn, cutoff,
-          nclasses, inv_gauss, out, pxy64, lab64, vec_ok, reinterpret_cast<float4*>(cofill), n4, per_cta, fill_early);
-    else if (mode == 2)
-      knn_vote_kernel<S, KT, 2><<<grid, threads, smem_fill, stream>>>(
-          proj_range, proj_argmax, unproj_range, px, py, offsets, batch, total, H, W, knn, cutoff,
-          nclasses, inv_gauss, out, pxy64, lab64, vec_ok, reinterpret_cast<float4*>(cofill), n4, per_cta, fill_early);
-    else
-      knn_vote_kernel<S, KT, 1><<<grid, threads, smem_fill, stream>>>(
-          proj_range, proj_argmax, unproj_range, px, py, offsets, batch, total, H, W, knn, cutoff,
-          nclasses, inv_gauss, out, pxy64, lab64, vec_ok, reinterpret_cast<float4*>(cofill), n4, per_cta, fill_early);
+    knn_vote_kernel<S, KT, 3><<<grid, threads, smem, stream>>>(
+        proj_range, proj_argmax, unproj_range, px, py, offsets, batch, total, H, W, knn, cutoff,
+        nclasses, inv_gauss, out, pxy64, lab64, vec_ok, reinterpret_cast<float4*>(cofill), n4, per_cta, fill_early);
     return check_launch("knn_vote_fill_kernel");
   }
   KernelTimer timer("knn_vote_kernel", stream);

@@ -57,13 +57,8 @@ inline SplitWs carve_split(void* base, size_t* off, int B, int C, int HW) {
   return w;
 }
 
-// Grid of the two tile kernels: one CTA per tile, or (concurrent hint, small batches) a
-// persistent grid of two CTAs per SM that is resident at once next to long-running kernels.
-inline int split_grid(int nblk) {
-  if (!g_concurrent_hint.load(std::memory_order_relaxed) || nblk > 2048) return nblk;
-  const int g = kNumSMs * 2;
-  return nblk < g ? nblk : g;
-}
+// Grid of the count kernel: one CTA per work item.
+inline int split_grid(int nitems) { return nitems; }
 
 __device__ __forceinline__ int masked_class(const long long* __restrict__ labels,
                                             const uint8_t* __restrict__ keep, size_t i,

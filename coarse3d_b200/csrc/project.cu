@@ -20,7 +20,6 @@
 // in fp64 when the scaled coordinate lies within a proven error bound of a
 // pixel boundary (the only case where the floor could differ): ~0.5 % of
 // points.  C3D_PROJECT_F64_ONLY=1 forces the fp64 path for every point.
-#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -244,7 +243,7 @@ extern "C" int c3d_project_batch(
     const float* depth_override, double abs_fov_left, double fov_hori, double abs_fov_down,
     double fov_vert, int proj_h, int proj_w, float* proj_range, float* proj_pointcloud,
     int32_t* proj_idx, int32_t* proj_mask, int32_t* uproj_x_idx, int32_t* uproj_y_idx,
-    float* uproj_depth, void* workspace, int workspace_is_clean, int32_t* status_flags,
+    float* uproj_depth, void* workspace, int workspace_flags, int32_t* status_flags,
     void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   C3D_REQUIRE(batch > 0 && batch <= kMaxBatch, "batch must be in [1, %d], got %d", kMaxBatch, batch);
@@ -274,15 +273,14 @@ extern "C" int c3d_project_batch(
 
   const long long total_px = (long long)batch * proj_h * proj_w;
   auto* zbuf = reinterpret_cast<unsigned long long*>(workspace);
-  if (!workspace_is_clean) {
+  if (!(workspace_flags & 1)) {
     KernelTimer kt__("zbuf_memset", stream);
     C3D_CUDA(cudaMemsetAsync(zbuf, 0xFF, (size_t)total_px * sizeof(unsigned long long), stream));
   }
 
   const bool c4 = (c_in == 4) && ((reinterpret_cast<uintptr_t>(points) & 15) == 0) &&
                   ((reinterpret_cast<uintptr_t>(proj_pointcloud) & 15) == 0);
-  const char* env = getenv("C3D_PROJECT_F64_ONLY");
-  const bool hybrid = !(env && env[0] == '1');
+  const bool hybrid = !(workspace_flags & 2);
   const int threads = 256;
   if (total_points > 0) {
     int grid = (int)((total_points + threads - 1) / threads);  // short CTAs (overlap)
@@ -324,7 +322,7 @@ extern "C" int c3d_project_assemble_batch(
     double abs_fov_down, double fov_vert, int proj_h, int proj_w, float* feature,
     int64_t* train_label, int64_t* eval_label, float* proj_range, int32_t* proj_idx,
     int32_t* uproj_x_idx, int32_t* uproj_y_idx, float* uproj_depth, void* workspace,
-    int workspace_is_clean, int32_t* status_flags, void* stream_) {
+    int workspace_flags, int32_t* status_flags, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   C3D_REQUIRE(batch > 0 && batch <= kMaxBatch, "batch must be in [1, %d], got %d", kMaxBatch, batch);
   C3D_REQUIRE(proj_h > 0 && proj_w > 0, "bad image size %dx%d", proj_h, proj_w);
@@ -352,12 +350,11 @@ extern "C" int c3d_project_assemble_batch(
   p.sy = p.hf / p.fov_vert;
   const long long total_px = (long long)batch * proj_h * proj_w;
   auto* zbuf = reinterpret_cast<unsigned long long*>(workspace);
-  if (!workspace_is_clean) {
+  if (!(workspace_flags & 1)) {
     KernelTimer kt__("zbuf_memset", stream);
     C3D_CUDA(cudaMemsetAsync(zbuf, 0xFF, (size_t)total_px * sizeof(unsigned long long), stream));
   }
-  const char* env = getenv("C3D_PROJECT_F64_ONLY");
-  const bool hybrid = !(env && env[0] == '1');
+  const bool hybrid = !(workspace_flags & 2);
   const int threads = 256;
   if (total_points > 0) {
     int grid = (int)((total_points + threads - 1) / threads);

@@ -214,7 +214,7 @@ constexpr int kNvPad = kMaxClasses;   // per-row stride of the class-maximum scr
 
 struct EmaTiledPlan { int tile_classes, n_tiles, ldl; size_t smem; };
 static int plan_ema_tiled(int D, int C, int M, EmaTiledPlan* out) {
-  const size_t budget = 227 * 1024 - 2048 - smem_reserve();
+  const size_t budget = 227 * 1024 - 2048;
   const BankLayout L = BankLayout::make(D);
   const size_t fixed = (size_t)kEmaGroups * kGroupRows * ((size_t)D + kNvPad + kMaxSub) * 4;
   for (int n_tiles = 1; n_tiles <= C; ++n_tiles) {
@@ -618,7 +618,8 @@ ema_assign_sum_kernel(const int32_t* __restrict__ seg_cnt, const int32_t* __rest
                       const int32_t* __restrict__ pix_list, int32_t* __restrict__ info, int B, int M,
                       int D, int K, int ignore_label, int max_rows, int nsplit, float* __restrict__ simq,
                       int32_t* __restrict__ sub, const float* __restrict__ gumbel, int mode,
-                      unsigned long long seed, const float* __restrict__ feat,
+                      unsigned long long seed, const unsigned long long* __restrict__ seed_dev,
+                      const float* __restrict__ feat,
                       const int32_t* __restrict__ maskv, float* __restrict__ packed,
                       float* __restrict__ proto_target) {
   extern __shared__ float s_dyn[];
@@ -626,6 +627,7 @@ ema_assign_sum_kernel(const int32_t* __restrict__ seg_cnt, const int32_t* __rest
   __shared__ float s_R[32];
   __shared__ float s_tot;
   const int c = blockIdx.x;
+  if (seed_dev) seed += seed_dev[1];   // device-side step counter: fresh noise in every graph replay
   int n = 0, start = 0;
   if (c != ignore_label && info[kInfoPl] <= max_rows) {
     start = seg_start[c * B];
@@ -642,9 +644,11 @@ ema_assign_sum_kernel(const int32_t* __restrict__ seg_cnt, const int32_t* __rest
 __global__ void __launch_bounds__(256)
 ema_apply_kernel(const float* protos_in, const float* __restrict__ packed, int C, int M,
                  int D, int ignore_label, float mom, float one_minus_mom,
-                 float* protos_out) {   // protos_out may alias protos_in (row-local read-then-write)
+                 float* protos_out,   // may alias protos_in (row-local read-then-write)
+                 float* __restrict__ normalised_out, unsigned long long* __restrict__ seed_counter) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int K = C * M;
+  if (seed_counter && blockIdx.x == 0 && threadIdx.x == 0) seed_counter[1] += 1;   // next step: new noise
   const int k = blockIdx.x * 8 + warp;
   if (k >= K) return;
   const int c = k / M;
@@ -666,15 +670,26 @@ ema_apply_kernel(const float* protos_in, const float* __restrict__ packed, int C
     n2 += v * v;
   }
   const float ninv = 1.0f / fmaxf(sqrtf(warp_sum(n2)), 1e-12f);    // l2_normalize(protos) (:394)
+  float m2 = 0.f;
   for (int d = lane; d < D; d += 32) {
     float v = old[d] * oinv;
     if (update) v = mom * v + one_minus_mom * (f[d] * finv);
-    protos_out[(size_t)k * D + d] = v * ninv;
+    const float o = v * ninv;
+    protos_out[(size_t)k * D + d] = o;
+    m2 += o * o;
+  }
+  if (normalised_out) {
+    // F.normalize / l2_normalize of the stored bank, as its readers apply it: the loss on this
+    // bank (contrast_pixel_loss.py:167) and the next step's similarity pre-step
+    // (salsanext_proto.py:502) -- the same arithmetic as the stand-alone normalise kernels
+    const float inv2 = 1.0f / fmaxf(sqrtf(warp_sum(m2)), 1e-12f);
+    for (int d = lane; d < D; d += 32)   // this lane stored the element just above (in-place safe)
+      normalised_out[(size_t)k * D + d] = protos_out[(size_t)k * D + d] * inv2;
   }
 }
 
 static int ema_rows_config(int D, int K, int* tile_rows, int* n_tiles, size_t* smem) {
-  const size_t budget = 227 * 1024 - smem_reserve();
+  const size_t budget = 227 * 1024;
   const size_t fixed = ((size_t)kEmaWarps * D + (size_t)kEmaWarps * ((K + 31) & ~31)) * 4;
   const size_t row = (size_t)(D + 4) * 4;
   if (fixed + 32 * row > budget) return -1;
@@ -707,7 +722,7 @@ int c3d::proto_ema_accumulate_impl(
     int batch, int dim, int proj_h, int proj_w, int n_classes, int sub_protos, int ignore_label,
     int64_t max_rows, const float* gumbel, int assign_mode, uint64_t seed, void* workspace,
     const SplitWs* shared_split, float* packed, float* proto_target, void* stream_, float* raw_rows,
-    int rows_v1) {
+    int rows_v1, const float* bank_n_in, const uint64_t* seed_dev) {
   cudaStream_t stream = (cudaStream_t)stream_;
   const int B = batch, D = dim, C = n_classes, M = sub_protos;
   const long long HWll = (long long)proj_h * proj_w;
@@ -744,7 +759,7 @@ int c3d::proto_ema_accumulate_impl(
     if ((rc = launch_split((const long long*)label, nullptr, nullptr, B, C, HW, ignore_label, w.s, nullptr,
                            nullptr, nullptr, 0, stream))) return rc;
   }
-  if (!dense) {
+  if (!dense && !bank_n_in) {
     KernelTimer kt__("bank_normalise_kernel", stream);
     ema_bank_normalise_kernel<<<(K + 7) / 8, 256, 0, stream>>>(prototypes, K, D, w.bank_n);
     if ((rc = check_launch("bank_normalise_kernel"))) return rc;
@@ -758,7 +773,7 @@ int c3d::proto_ema_accumulate_impl(
     if ((rc = check_launch("ema_rows_dense_kernel"))) return rc;
   } else {
     EmaRowsParams p{};
-    p.emb = embedding; p.bank_n = w.bank_n; p.ln_d_w = ln_d_w; p.ln_d_b = ln_d_b;
+    p.emb = embedding; p.bank_n = bank_n_in ? bank_n_in : w.bank_n; p.ln_d_w = ln_d_w; p.ln_d_b = ln_d_b;
     p.ln_c_w = ln_c_w; p.ln_c_b = ln_c_b; p.pix_list = w.s.pix_list; p.cls_list = w.s.cls_list;
     p.info = w.s.info; p.feat = w.feat; p.simq = w.simq; p.maskv = w.maskv;
     p.HW = HW; p.D = D; p.M = M; p.C = C; p.K = K; p.tile_rows = tile_rows; p.n_tiles = n_tiles;
@@ -784,7 +799,8 @@ int c3d::proto_ema_accumulate_impl(
   { KernelTimer kt__("ema_assign_sum_kernel", stream);
     ema_assign_sum_kernel<<<C, kSinkWarps * 32, dyn, stream>>>(
         w.s.seg_cnt, w.s.seg_start, w.s.pix_list, w.s.info, B, M, D, K, ignore_label, (int)max_rows, seg_split,
-        w.simq, w.sub, gumbel, assign_mode, seed, w.feat, w.maskv, packed, proto_target); }
+        w.simq, w.sub, gumbel, assign_mode, seed, reinterpret_cast<const unsigned long long*>(seed_dev),
+        w.feat, w.maskv, packed, proto_target); }
   return check_launch("ema_assign_sum_kernel");
 }
 
@@ -797,7 +813,7 @@ extern "C" int c3d_proto_ema_accumulate(
   return proto_ema_accumulate_impl(embedding, nullptr, label, prototypes, ln_d_w, ln_d_b, ln_c_w, ln_c_b,
                                    ln_eps, batch, dim, proj_h, proj_w, n_classes, sub_protos,
                                    ignore_label, max_rows, gumbel, assign_mode, seed, workspace, nullptr,
-                                   packed, proto_target, stream, nullptr, 0);
+                                   packed, proto_target, stream, nullptr, 0, nullptr, nullptr);
 }
 
 extern "C" int c3d_proto_ema_accumulate_dense(
@@ -809,12 +825,13 @@ extern "C" int c3d_proto_ema_accumulate_dense(
   return proto_ema_accumulate_impl(nullptr, &d, label, nullptr, nullptr, nullptr, nullptr, nullptr, 0.f,
                                    batch, dim, proj_h, proj_w, n_classes, sub_protos, ignore_label,
                                    max_rows, gumbel, assign_mode, seed, workspace, nullptr, packed,
-                                   proto_target, stream, nullptr, 0);
+                                   proto_target, stream, nullptr, 0, nullptr, nullptr);
 }
 
 extern "C" int c3d_proto_ema_apply(const float* prototypes_in, const float* packed, int n_classes,
                                    int sub_protos, int dim, int ignore_label, double momentum,
-                                   float* prototypes_out, void* stream_) {
+                                   float* prototypes_out, float* normalised_out, uint64_t* seed_counter,
+                                   void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   C3D_REQUIRE(prototypes_in && packed && prototypes_out, "null pointer argument");
   C3D_REQUIRE(n_classes >= 2 && sub_protos > 0 && dim > 0, "bad prototype shape");
@@ -823,8 +840,18 @@ extern "C" int c3d_proto_ema_apply(const float* prototypes_in, const float* pack
   // floats multiplied into float32 tensors (salsanext_proto.py:20)
   { KernelTimer kt__("ema_apply_kernel", stream); ema_apply_kernel<<<(K + 7) / 8, 256, 0, stream>>>(prototypes_in, packed, n_classes, sub_protos,
                                                     dim, ignore_label, (float)momentum,
-                                                    (float)(1.0 - momentum), prototypes_out); }
+                                                    (float)(1.0 - momentum), prototypes_out, normalised_out,
+                                                    reinterpret_cast<unsigned long long*>(seed_counter)); }
   return check_launch("ema_apply_kernel");
+}
+
+extern "C" int c3d_proto_bank_normalise(const float* prototypes, int rows, int dim, float* normalised_out,
+                                        void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  C3D_REQUIRE(prototypes && normalised_out && rows > 0 && dim > 0, "bad argument");
+  { KernelTimer kt__("bank_normalise_kernel", stream);
+    ema_bank_normalise_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(prototypes, rows, dim, normalised_out); }
+  return check_launch("bank_normalise_kernel");
 }
 
 extern "C" int c3d_proto_ema_info(const void* workspace, int32_t* host_info4, void* stream_) {

@@ -16,7 +16,9 @@ int proto_loss_forward_impl(
     int sub_protos, int ignore_label, float temperature, float base_temperature, int num_anchor,
     const int64_t* keep, int keep_rows, uint64_t seed, int need_grad, int phases, void* workspace,
     float* loss_out, float* zero_buf, int zero_n, void* stream,
-    const float* raw_rows /* [slots, D] rows left by the EMA kernel (fused step), or null */, int raw_cap);
+    const float* raw_rows /* [slots, D] rows left by the EMA kernel (fused step), or null */, int raw_cap,
+    const float* bank_n /* [C, M, D] F.normalize'd bank, or null: normalised here */,
+    uint64_t* seed_dev /* [2] device step counters; [0] is added to `seed` and advanced by the sampler */);
 
 // proto_ema.cu
 struct DenseRows { const float* out_feat; const float* nearest; const float* sim; };
@@ -29,6 +31,8 @@ int proto_ema_accumulate_impl(
     int batch, int dim, int proj_h, int proj_w, int n_classes, int sub_protos, int ignore_label,
     int64_t max_rows, const float* gumbel, int assign_mode, uint64_t seed, void* workspace,
     const SplitWs* shared_split, float* packed, float* proto_target, void* stream,
-    float* raw_rows /* [max_rows, D] un-normalised gathered rows, or null */, int rows_v1 /* A/B: warp-per-row kernel */);
+    float* raw_rows /* [max_rows, D] un-normalised gathered rows, or null */, int rows_v1 /* A/B: warp-per-row kernel */,
+    const float* bank_n /* [C, M, D] l2-normalised bank, or null: normalised here */,
+    const uint64_t* seed_dev /* [2] device step counters added to `seed` ([1] is this operator's), or null */);
 
 }  // namespace c3d

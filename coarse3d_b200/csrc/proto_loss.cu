@@ -24,7 +24,6 @@
 //
 // All reductions are order-deterministic (no float atomics).
 #include <math_constants.h>
-#include <stdlib.h>
 
 #include "common.cuh"
 #include "labelsplit.cuh"
@@ -109,11 +108,12 @@ loss_sample_kernel(const int32_t* __restrict__ seg_cnt, const int32_t* __restric
                    const int32_t* __restrict__ seg_tidx, const int32_t* __restrict__ pix_list,
                    float* __restrict__ w_list, int32_t* __restrict__ cnt_list, int HW, int B, int C, int A,
                    const long long* __restrict__ keep, int keep_rows, unsigned long long seed,
-                   int32_t* __restrict__ seg_nd, int32_t* __restrict__ row_base,
+                   unsigned long long* __restrict__ seed_dev, int32_t* __restrict__ seg_nd, int32_t* __restrict__ row_base,
                    int32_t* __restrict__ seg_of_t, int32_t* __restrict__ info) {
   // one CTA per (class, scan) segment; seg = c*B + b (class-major storage), its rank among the
   // non-empty segments in the reference's (scan, class) order is seg_tidx[b*C + c]
   const int seg = blockIdx.x, nseg = gridDim.x;
+  if (seed_dev) seed += seed_dev[0];   // device-side step counter (advanced by the last CTA below)
   const int n = seg_cnt[seg];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int kCdfSmem = 2048;
@@ -236,6 +236,7 @@ loss_sample_kernel(const int32_t* __restrict__ seg_cnt, const int32_t* __restric
       row_base[info[kInfoT]] = carry;
       info[kInfoU] = carry;
       info[kInfoDone3] = 0;
+      if (seed_dev) seed_dev[0] += 1;   // every CTA has read it (they all passed the ticket)
     }
   }
 }
@@ -845,11 +846,6 @@ int launch_fill(void* dst, size_t nbytes, cudaStream_t stream) {
   size_t grid = (n4 + per_cta - 1) / per_cta;
   if (grid == 0) grid = 1;
   if (grid > 0x7fffffffull) { set_error("fill too large"); return C3D_INVALID_ARGUMENT; }
-  const char* env = getenv("C3D_FILL_PERSISTENT");
-  if (env && env[0] != '0') {
-    const size_t cap = (size_t)kNumSMs * (size_t)(env[0] - '0');
-    if (grid > cap) grid = cap;
-  }
   KernelTimer kt__("fill_zero_kernel", stream);
   fill_zero_kernel<<<(unsigned)grid, 256, 0, stream>>>(reinterpret_cast<float4*>(dst), n4,
                                                        reinterpret_cast<float*>(dst) + n4 * 4,
@@ -879,7 +875,7 @@ loss_grad_scatter_kernel(const float* __restrict__ grad_rows, const int32_t* __r
 }
 
 static int rows_config(int D, int Kc, int* tile_rows, int* n_tiles, size_t* smem) {
-  const size_t budget = 227 * 1024 - smem_reserve();
+  const size_t budget = 227 * 1024;
   const size_t fixed = ((size_t)kRowWarps * D + (size_t)kRowWarps * ((Kc + 31) & ~31)) * 4;
   const size_t row = (size_t)(D + 4) * 4;
   if (fixed + 32 * row > budget) return -1;
@@ -925,7 +921,8 @@ int c3d::proto_loss_forward_impl(
     const float* proto_queue, int batch, int dim, int proj_h, int proj_w, int n_classes,
     int sub_protos, int ignore_label, float temperature, float base_temperature, int num_anchor,
     const int64_t* keep, int keep_rows, uint64_t seed, int need_grad, int phases, void* workspace,
-    float* loss_out, float* zero_buf, int zero_n, void* stream_, const float* raw_rows, int raw_cap) {
+    float* loss_out, float* zero_buf, int zero_n, void* stream_, const float* raw_rows, int raw_cap,
+    const float* bank_n_in, uint64_t* seed_dev) {
   cudaStream_t stream = (cudaStream_t)stream_;
   const int B = batch, D = dim, C = n_classes, M = sub_protos;
   const long long HWll = (long long)proj_h * proj_w;
@@ -936,7 +933,7 @@ int c3d::proto_loss_forward_impl(
   C3D_REQUIRE(HWll > 0 && B * HWll < (1ll << 31), "batch*H*W must be < 2^31");
   C3D_REQUIRE(workspace, "null workspace");
   C3D_REQUIRE(!(phases & kPhaseSplit) || (probs && labels), "null pointer argument (probs / labels)");
-  C3D_REQUIRE(!(phases & kPhaseRows) || (feats && proto_queue && loss_out),
+  C3D_REQUIRE(!(phases & kPhaseRows) || (feats && (proto_queue || bank_n_in) && loss_out),
               "null pointer argument (feats / proto_queue / loss_out)");
   C3D_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "workspace must be 256 B aligned");
   C3D_REQUIRE(temperature > 0 && base_temperature > 0, "temperatures must be positive");
@@ -957,7 +954,8 @@ int c3d::proto_loss_forward_impl(
   { KernelTimer kt__("loss_sample_kernel", stream);
     loss_sample_kernel<<<B * C, 256, 0, stream>>>(w.s.seg_cnt, w.s.seg_start, w.s.seg_tidx, w.s.pix_list,
                                                   w.w_list, w.cnt_list, HW, B, C, num_anchor,
-                                                  (const long long*)keep, keep_rows, seed, w.seg_nd,
+                                                  (const long long*)keep, keep_rows, seed,
+                                                  reinterpret_cast<unsigned long long*>(seed_dev), w.seg_nd,
                                                   w.row_base, w.seg_of_t, w.s.info); }
   if ((rc = check_launch("loss_sample_kernel"))) return rc;
   }
@@ -966,20 +964,21 @@ int c3d::proto_loss_forward_impl(
   // F.normalize of the bank rows of classes 1..C-1 (:167).  Part of phase 2: the bank may be
   // written between the phases (the EMA update precedes the loss in a training step,
   // salsanext_proto.py:520-527 -> trainer.py:675-686).
-  { KernelTimer kt__("bank_normalise_kernel", stream);
-    bank_normalise_kernel<<<(Kc + 7) / 8, 256, 0, stream>>>(proto_queue + (size_t)M * D, Kc, D, w.bank_n); }
-  if ((rc = check_launch("bank_normalise_kernel"))) return rc;
+  if (!bank_n_in) {
+    { KernelTimer kt__("bank_normalise_kernel", stream);
+      bank_normalise_kernel<<<(Kc + 7) / 8, 256, 0, stream>>>(proto_queue + (size_t)M * D, Kc, D, w.bank_n); }
+    if ((rc = check_launch("bank_normalise_kernel"))) return rc;
+  }
 
   RowsParams p{};
-  p.feats = feats; p.raw_rows = raw_rows; p.raw_cap = raw_cap; p.bank_n = w.bank_n; p.pix_list = w.s.pix_list; p.cls_list = w.s.cls_list;
+  p.feats = feats; p.raw_rows = raw_rows; p.raw_cap = raw_cap; p.bank_n = bank_n_in ? bank_n_in + (size_t)M * D : w.bank_n; p.pix_list = w.s.pix_list; p.cls_list = w.s.cls_list;
   p.cnt_list = w.cnt_list; p.dist_list = reinterpret_cast<const int32_t*>(w.w_list);
   p.seg_start = w.s.seg_start; p.row_base = w.row_base; p.seg_of_t = w.seg_of_t; p.info = w.s.info;
   p.loss_part = w.loss_part; p.row_pix = w.row_pix; p.grad_rows = w.grad_rows; p.loss_out = loss_out;
   p.HW = HW; p.D = D; p.M = M; p.Kc = Kc; p.A = num_anchor; p.tile_rows = tile_rows;
   p.n_tiles = n_tiles; p.temperature = temperature; p.base_temperature = base_temperature;
-  const char* v1 = getenv("C3D_LOSS_ROWS_V1");
   RowsPlan plan;
-  if (!(v1 && v1[0] == '1') && plan_rows16(D, Kc, &plan) == 0) {
+  if (plan_rows16(D, Kc, &plan) == 0) {
     p.tile_rows = plan.tile_rows; p.n_tiles = plan.n_tiles; p.ldl = plan.ldl;
     // <grad, k-splits, rows per thread in P3, chunks per thread, D/32>; chunk-threads
     // CT = 256 / (kKS * 16 / kRP) must cover D/4 chunks (times kDch)
@@ -1012,7 +1011,7 @@ extern "C" int c3d_proto_loss_forward(
                                  n_classes, sub_protos, ignore_label, temperature, base_temperature,
                                  num_anchor, keep, keep_rows, seed, need_grad,
                                  kPhaseSplit | kPhaseSample | kPhaseRows, workspace, loss_out, nullptr, 0,
-                                 stream, nullptr, 0);
+                                 stream, nullptr, 0, nullptr, nullptr);
 }
 
 extern "C" int c3d_proto_loss_forward_phase(
@@ -1026,7 +1025,7 @@ extern "C" int c3d_proto_loss_forward_phase(
   return proto_loss_forward_impl(feats, probs, labels, keep_mask, proto_queue, batch, dim, proj_h, proj_w,
                                  n_classes, sub_protos, ignore_label, temperature, base_temperature,
                                  num_anchor, keep, keep_rows, seed, need_grad, internal, workspace, loss_out,
-                                 nullptr, 0, stream, nullptr, 0);
+                                 nullptr, 0, stream, nullptr, 0, nullptr, nullptr);
 }
 
 extern "C" int c3d_proto_loss_backward(int batch, int dim, int proj_h, int proj_w, int n_classes,

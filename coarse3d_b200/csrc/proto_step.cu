@@ -38,8 +38,8 @@ extern "C" int c3d_proto_step(
     const float* ln_c_b, float ln_eps, int batch, int dim, int proj_h, int proj_w, int n_classes,
     int sub_protos, int ignore_label, float temperature, float base_temperature, int num_anchor,
     const int64_t* keep, int keep_rows, const float* gumbel, int assign_mode, uint64_t seed,
-    int64_t max_rows, int need_grad, int phases, void* workspace, float* packed, float* proto_target,
-    float* loss_out, void* stream) {
+    int64_t max_rows, int need_grad, int phases, const float* bank_n, uint64_t* seed_counters,
+    void* workspace, float* packed, float* proto_target, float* loss_out, void* stream) {
   C3D_REQUIRE(workspace && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "workspace must be 256 B aligned");
   C3D_REQUIRE(phases > 0 && phases < 16, "phases: bit mask of 1 split, 2 sample, 4 accumulate, 8 loss rows");
   C3D_REQUIRE(batch > 0 && n_classes >= 2 && dim > 0 && sub_protos > 0 && num_anchor > 0 && max_rows > 0 &&
@@ -56,21 +56,23 @@ extern "C" int c3d_proto_step(
     rc = proto_loss_forward_impl(nullptr, probs, labels, keep_mask, nullptr, batch, dim, proj_h, proj_w,
                                  n_classes, sub_protos, ignore_label, temperature, base_temperature,
                                  num_anchor, keep, keep_rows, seed, need_grad, loss_phases, workspace, nullptr,
-                                 nullptr, 0, stream, nullptr, 0);
+                                 nullptr, 0, stream, nullptr, 0, nullptr, seed_counters);
     if (rc) return rc;
   }
   if (phases & 4) {
     const SplitWs s = loss_ws_split(workspace, batch, n_classes, HW, dim, sub_protos, num_anchor);
     rc = proto_ema_accumulate_impl(feats, nullptr, nullptr, prototypes, ln_d_w, ln_d_b, ln_c_w, ln_c_b, ln_eps,
                                    batch, dim, proj_h, proj_w, n_classes, sub_protos, ignore_label, max_rows,
-                                   gumbel, assign_mode, seed, extra, &s, packed, proto_target, stream, raw_rows, 0);
+                                   gumbel, assign_mode, seed, extra, &s, packed, proto_target, stream, raw_rows, 0, bank_n,
+                                   seed_counters);
     if (rc) return rc;
   }
   if (phases & 8) {
     rc = proto_loss_forward_impl(feats, nullptr, nullptr, nullptr, prototypes, batch, dim, proj_h, proj_w,
                                  n_classes, sub_protos, ignore_label, temperature, base_temperature,
                                  num_anchor, nullptr, 0, seed, need_grad, kPhaseRows, workspace, loss_out,
-                                 nullptr, 0, stream, raw_rows, (int)(max_rows > 0x7fffffff ? 0x7fffffff : max_rows));
+                                 nullptr, 0, stream, raw_rows, (int)(max_rows > 0x7fffffff ? 0x7fffffff : max_rows), bank_n,
+                                 nullptr);
     if (rc) return rc;
   }
   return C3D_OK;

@@ -166,7 +166,7 @@ __device__ __forceinline__ void tile_gradT(const float* s_G, int ldg, int k0, co
 // 64-row tile does not fit.
 struct RowsPlan { int tile_rows, n_tiles, ldl; size_t smem; };
 inline int plan_rows16(int D, int K, RowsPlan* out) {
-  const size_t budget = 227 * 1024 - 1024 - smem_reserve();  // 1 KB for the kernel's static shared memory
+  const size_t budget = 227 * 1024 - 1024;  // 1 KB for the kernel's static shared memory
   const BankLayout L = BankLayout::make(D);
   const int ldl = (K + 3) & ~3;
   // the L region also holds the k-split partial sums of the gradient product

@@ -83,11 +83,13 @@ class ProjectionBuffers:
 
 
 def project_batch(points, offsets, fov: Fov, proj_h, proj_w, depth=None,
-                  buffers: ProjectionBuffers = None) -> Projection:
+                  buffers: ProjectionBuffers = None, exact_f64=False) -> Projection:
     """RangeProjection.doProjection for a CSR batch (projection.py:43-115).
 
     points (sum N, C>=3) f32, offsets (B+1,) i32, optional depth (sum N,) f32;
-    all CUDA.  proj_idx holds indices local to each scan.
+    all CUDA.  proj_idx holds indices local to each scan.  exact_f64=True evaluates the angles
+    of EVERY point in fp64 (the default does so only inside the guard band of a pixel boundary;
+    both give the same pixels, the flag exists to prove that).
     """
     _need_cuda(points=points, offsets=offsets, depth=depth)
     if points.dtype != torch.float32 or points.dim() != 2:
@@ -109,7 +111,7 @@ def project_batch(points, offsets, fov: Fov, proj_h, proj_w, depth=None,
         fov.abs_fov_left, fov.fov_hori, fov.abs_fov_down, fov.fov_vert, proj_h, proj_w,
         _p(b.proj_range), _p(b.proj_pointcloud), _p(b.proj_idx), _p(b.proj_mask),
         _p(b.uproj_x_idx), _p(b.uproj_y_idx), _p(b.uproj_depth), _p(b.workspace),
-        1 if was_clean else 0, _p(b.flags), _stream()))
+        (1 if was_clean else 0) | (2 if exact_f64 else 0), _p(b.flags), _stream()))
     b.clean = True
     return Projection(b.proj_pointcloud, b.proj_range, b.proj_idx, b.proj_mask,
                       b.uproj_x_idx, b.uproj_y_idx, b.uproj_depth, b.flags)
@@ -616,8 +618,11 @@ def proto_ema_accumulate_dense(out_feat, nearest, label, feat_proto_sim, ignore_
     return EmaAccum(packed, target, workspace)
 
 
-def proto_ema_apply(prototypes, packed, momentum, ignore_label=0, out=None):
-    """normalise sums -> EMA where count != 0 -> renormalise (salsanext_proto.py:379-394)."""
+def proto_ema_apply(prototypes, packed, momentum, ignore_label=0, out=None, normalised_out=None,
+                    seed_counters=None):
+    """normalise sums -> EMA where count != 0 -> renormalise (salsanext_proto.py:379-394).
+    normalised_out (C,M,D): also receives F.normalize(out), the form the bank's readers use;
+    seed_counters (2,) int64: device step counters of the fused step ([1] is advanced here)."""
     _need_cuda(prototypes=prototypes, packed=packed)
     C, M, D = prototypes.shape
     if packed.numel() != C * M * D + C * M or packed.dtype != torch.float32:
@@ -625,7 +630,18 @@ def proto_ema_apply(prototypes, packed, momentum, ignore_label=0, out=None):
     if out is None:
         out = torch.empty_like(prototypes)
     check(lib.c3d_proto_ema_apply(_p(prototypes), _p(packed), C, M, D, int(ignore_label),
-                                  float(momentum), _p(out), _stream()))
+                                  float(momentum), _p(out), _p(normalised_out), _p(seed_counters), _stream()))
+    return out
+
+
+def bank_normalise(prototypes, out=None):
+    """F.normalize(prototypes, dim=-1) with the library's own kernel (bitwise what
+    c3d_proto_ema_apply's `normalised_out` and the operators' internal normalisation produce)."""
+    _need_cuda(prototypes=prototypes, out=out)
+    if out is None:
+        out = torch.empty_like(prototypes)
+    D = prototypes.shape[-1]
+    check(lib.c3d_proto_bank_normalise(_p(prototypes), prototypes.numel() // D, D, _p(out), _stream()))
     return out
 
 
@@ -641,7 +657,8 @@ def proto_step_workspace(batch, n_classes, hw, dim, sub_protos, num_anchor, max_
 
 def proto_step_raw(phases, feats, probs, labels, keep_mask, prototypes, ln_d_w, ln_d_b, ln_c_w, ln_c_b,
                    cfg, workspace, packed, loss_out, max_rows, ln_eps=1e-5, keep=None,
-                   gumbel=None, assign_mode=ASSIGN_GUMBEL_DEVICE, seed=0, need_grad=True, proto_target=None):
+                   gumbel=None, assign_mode=ASSIGN_GUMBEL_DEVICE, seed=0, need_grad=True, proto_target=None,
+                   bank_n=None, seed_counters=None):
     """c3d_proto_step on pre-validated device tensors (no autograd, no allocation): the phases of
     the fused EMA-update + loss step (STEP_* bit mask) on one shared label split."""
     B, D, H, W = feats.shape
@@ -651,22 +668,7 @@ def proto_step_raw(phases, feats, probs, labels, keep_mask, prototypes, ln_d_w, 
         _p(ln_c_b), float(ln_eps), B, D, H, W, C, M, int(cfg.ignore_label), float(cfg.temperature),
         float(cfg.base_temperature), int(cfg.num_anchor), _p(keep), 0 if keep is None else keep.shape[0],
         _p(gumbel), int(assign_mode), int(seed), int(max_rows), 1 if need_grad else 0, int(phases),
-        _p(workspace), _p(packed), _p(proto_target), _p(loss_out), _stream()))
-
-
-class concurrent_hint:
-    """Context manager around multi-stream use of the library (c3d_set_concurrent_hint)."""
-
-    def __init__(self, level=1):
-        self.level = level   # 2: also leave shared memory for the fill daemon next to the rows kernels
-
-    def __enter__(self):
-        self.prev = lib.c3d_set_concurrent_hint(self.level)
-        return self
-
-    def __exit__(self, *exc):
-        lib.c3d_set_concurrent_hint(self.prev)
-        return False
+        _p(bank_n), _p(seed_counters), _p(workspace), _p(packed), _p(proto_target), _p(loss_out), _stream()))
 
 
 def launch_count():

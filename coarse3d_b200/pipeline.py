@@ -91,6 +91,11 @@ class HotPathStep:
         self.ema_ws = torch.empty((nws,), dtype=torch.uint8, device=self.device)
         K = C * sub_protos
         self.packed = torch.empty((K * dim + K,), device=self.device)
+        # F.normalize(bank): written by every EMA apply, read by the loss (this step) and by the
+        # similarity pre-step of the EMA (next step); device step counters feed the Philox streams
+        self.bank_n = ops.bank_normalise(self.protos)
+        self.seed_counters = torch.zeros(2, dtype=torch.int64, device=self.device)
+        self.device_seeds = _os.environ.get("C3D_DEVICE_SEEDS", "1") == "1"   # 0: `seed` alone decides the draws
         self.knn_out = torch.empty((n,), dtype=torch.int64, device=self.device)
         self.inv_gauss = (1 - ops.gaussian_kernel(self.knn_s, self.knn_sigma)).reshape(-1).to(self.device)
         self.daemon_ctrl = torch.zeros(256, dtype=torch.int32, device=self.device)
@@ -156,8 +161,7 @@ class HotPathStep:
             if not fused:
                 self._knn(s, pr, C)
             return pr
-        with ops.concurrent_hint(2 if self.schedule == "fill_daemon" else 1):
-            return self._run_concurrent(s, b, seed, fused, cur)
+        return self._run_concurrent(s, b, seed, fused, cur)
 
     def _run_concurrent(self, s, b, seed, fused, cur):
         H, W, C = self.shape.proj_h, self.shape.proj_w, self.shape.n_classes
@@ -288,8 +292,7 @@ class HotPathStep:
         after the projection), then the same chains and schedule as `run`.  Returns
         (loss 0-dim, per-point KNN labels int64, Assembled); both tensors are reused by the
         next call."""
-        with ops.concurrent_hint():
-            return self._run_inputs(points, offsets, weak, bufs, set_index, seed)
+        return self._run_inputs(points, offsets, weak, bufs, set_index, seed)
 
     def _run_inputs(self, points, offsets, weak, bufs, set_index, seed):
         s = self.sets[set_index % len(self.sets)]
@@ -353,12 +356,15 @@ class HotPathStep:
     def _step(self, phases, labels, s, seed):
         ops.proto_step_raw(phases, s.feats, s.probs, labels, None, self.protos, *self.ln_d, *self.ln_c,
                            self.cfg, self.loss_ws, self.packed, self.loss, self.max_rows,
-                           assign_mode=ops.ASSIGN_GUMBEL_DEVICE, seed=seed)
+                           assign_mode=ops.ASSIGN_GUMBEL_DEVICE, seed=seed, bank_n=self.bank_n,
+                           seed_counters=self.seed_counters if self.device_seeds else None)
 
     def _ema_finish(self):
         """all-reduce of the packed sums (N > 1) + the EMA itself, in place on the bank"""
         distributed.allreduce_packed(self.packed, self.group)
-        ops.proto_ema_apply(self.protos, self.packed, self.momentum, 0, out=self.protos)
+        ops.proto_ema_apply(self.protos, self.packed, self.momentum, 0, out=self.protos,
+                            normalised_out=self.bank_n,
+                            seed_counters=self.seed_counters if self.device_seeds else None)
 
     def _loss_fwd(self, s, seed, phases=3):
         ops.proto_loss_forward_raw(s.feats, s.probs, s.labels, s.keep_mask, self.protos, self.cfg,

@@ -11,6 +11,9 @@
  *   - no hidden allocation: scratch is passed in, sized by *_workspace_bytes;
  *   - `stream` is a cudaStream_t (CUstream) passed as void*; all work is
  *     enqueued on it and nothing synchronises;
+ *   - no process-global state decides what a call does: no environment variables are read,
+ *     every option is an argument (the only globals are the launch counter and the optional
+ *     profiler below, both diagnostics); calls on different streams are independent;
  *   - every function returns a c3d_status; on failure c3d_last_error() gives a
  *     thread-local message; nothing throws across the ABI;
  *   - a scan batch is CSR: `offsets[b] .. offsets[b+1]` are scan b's points.
@@ -38,13 +41,6 @@ int c3d_version(void);
 const char* c3d_last_error(void);
 /* Number of kernel launches enqueued by this library since load (all threads). */
 long long c3d_launch_count(void);
-
-/* Scheduling hint (process-wide, returns the previous value).  on = 1: the caller runs this
- * library's calls on several streams next to long-running kernels (the step pipeline), so
- * the small latency-bound kernels should use small persistent grids, which are resident at
- * once instead of being placed as SM slots trickle free.  on = 0 (default): calls run one
- * after the other; grids sized for an idle GPU.  Results are identical either way. */
-int c3d_set_concurrent_hint(int on);
 
 /* Optional per-kernel device timing: CUDA events recorded on the launching
  * stream right before and after each kernel launch.  kernel_name "" = every
@@ -91,9 +87,12 @@ int c3d_project_batch(
     int32_t* uproj_y_idx,         /* [total_points]                              */
     float* uproj_depth,           /* [total_points]                              */
     void* workspace,              /* c3d_project_workspace_bytes                 */
-    int workspace_is_clean,       /* 1: workspace is as a previous call left it
+    int workspace_flags,          /* bit 0: workspace is as a previous call left it
                                      (all 0xFF), so the 8 B/pixel memset is
-                                     skipped; 0: fresh memory                    */
+                                     skipped (0: fresh memory); bit 1: evaluate the
+                                     angles of every point in fp64 (default: only
+                                     inside the guard band of a pixel boundary --
+                                     same pixels)                 */
     int32_t* status_flags,        /* [1], caller-zeroed                          */
     void* stream);
 
@@ -124,7 +123,7 @@ int c3d_project_assemble_batch(
     float* proj_range,            /* [batch, H, W]                                         */
     int32_t* proj_idx,            /* [batch, H, W]                                         */
     int32_t* uproj_x_idx, int32_t* uproj_y_idx, float* uproj_depth,   /* [total_points]   */
-    void* workspace, int workspace_is_clean, int32_t* status_flags, void* stream);
+    void* workspace, int workspace_flags, int32_t* status_flags, void* stream);
 
 /* ---------------------------------------------------------------- a4 ----
  * KNN.forward, pc_processor/postproc/knn.py:54-142, for a CSR batch of scans.
@@ -385,6 +384,12 @@ int c3d_proto_ema_apply(
     const float* packed,          /* [C*M*D + C*M], summed over ranks            */
     int n_classes, int sub_protos, int dim, int ignore_label, double momentum,
     float* prototypes_out,        /* [C, M, D] (may alias prototypes_in)         */
+    float* normalised_out,        /* [C, M, D] or NULL: F.normalize(prototypes_out), the form
+                                     the bank's readers use (contrast_pixel_loss.py:167;
+                                     salsanext_proto.py:502) -- pass it as `bank_n` to
+                                     c3d_proto_step and no normalise kernel is launched   */
+    uint64_t* seed_counters,      /* [2] or NULL: device step counters of c3d_proto_step;
+                                     [1] (the EMA's noise stream) is advanced here        */
     void* stream);
 
 /* -------------------------------------------------------- a2 + a3 fused ----
@@ -409,8 +414,18 @@ int c3d_proto_step(
     const float* ln_c_b, float ln_eps, int batch, int dim, int proj_h, int proj_w, int n_classes,
     int sub_protos, int ignore_label, float temperature, float base_temperature, int num_anchor,
     const int64_t* keep, int keep_rows, const float* gumbel, int assign_mode, uint64_t seed,
-    int64_t max_rows, int need_grad, int phases, void* workspace, float* packed, float* proto_target,
-    float* loss_out, void* stream);
+    int64_t max_rows, int need_grad, int phases,
+    const float* bank_n,          /* [C, M, D] or NULL: F.normalize(prototypes) as left by
+                                     c3d_proto_ema_apply(normalised_out); NULL = normalised here */
+    uint64_t* seed_counters,      /* [2] or NULL: device-side step counters added to `seed`
+                                     ([0] anchor sampling, advanced by phase 2; [1] Gumbel noise,
+                                     advanced by c3d_proto_ema_apply), so that replays of a
+                                     captured CUDA graph draw fresh randomness              */
+    void* workspace, float* packed, float* proto_target, float* loss_out, void* stream);
+
+/* F.normalize(x, p=2, dim=-1) of `rows` bank rows (eps 1e-12): the `bank_n` of c3d_proto_step for a
+ * bank that did not come out of c3d_proto_ema_apply (e.g. the initial one). */
+int c3d_proto_bank_normalise(const float* prototypes, int rows, int dim, float* normalised_out, void* stream);
 
 /* Synchronous: copies {segments, labelled rows, flags, 0} to host_info4 (host). */
 int c3d_proto_ema_info(const void* workspace, int32_t* host_info4, void* stream);

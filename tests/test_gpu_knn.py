@@ -119,14 +119,12 @@ def test_random_images_any_width(cuda_device, W, k, s):
         assert np.array_equal(out.cpu().numpy(), want), int((out.cpu().numpy() != want).sum())
 
 
-@pytest.mark.parametrize("mode", ["2", "1"])     # TMA bulk stores (default) / per-thread stores
 @pytest.mark.parametrize("nfill,W", [(16, 64), (4096 * 7 + 16, 64), (1 << 22, 101), (999 * 16, 7),
                                      (8192 * 10, 64), (8192 * 10 + 48, 64)])
-def test_co_scheduled_fill_zeroes_exactly_its_buffer(cuda_device, monkeypatch, nfill, W, mode):
+def test_co_scheduled_fill_zeroes_exactly_its_buffer(cuda_device, nfill, W):
     """The vote kernel can carry a zero fill (the loss's dense gradient in the step
     pipeline): labels are unchanged, every byte of the buffer is zero, guards untouched."""
     from coarse3d_b200 import ops
-    monkeypatch.setenv("C3D_KNN_COFILL_MODE", mode)
     rng = np.random.default_rng(nfill % 1000 + W)
     H, P, C = 9, 2500, 11
     proj_range = rng.uniform(1, 30, (H, W)).astype(np.float32)

@@ -73,6 +73,7 @@ def test_two_launch_knn_matches(cuda_device, monkeypatch):
 
 
 def test_graph_replay_matches_eager(cuda_device, monkeypatch):
+    from coarse3d_b200 import ops
     step = _step(monkeypatch, "fill_in_knn")
     bank0 = step.protos.clone()
     step.run(1, seed=0)
@@ -80,6 +81,8 @@ def test_graph_replay_matches_eager(cuda_device, monkeypatch):
     assert step.capture(), getattr(step, "capture_error", "")
     step.grad.fill_(3.0)
     step.protos.copy_(bank0)                      # the bank evolves in place, step after step
+    ops.bank_normalise(bank0, out=step.bank_n)
+    step.seed_counters.zero_()                    # ... and so do the device-side step counters
     step.step(1)
     for a, b in zip(_outputs(step), want):
         assert torch.equal(a, b)
@@ -131,6 +134,7 @@ def test_fused_step_equals_separate_operators(cuda_device, monkeypatch):
     """c3d_proto_step (one label split shared by the EMA update and the loss) must reproduce the
     two operators called one after the other, bit for bit."""
     outs = []
+    monkeypatch.setenv("C3D_DEVICE_SEEDS", "0")     # the separate operators take `seed` alone
     for fused in ("0", "1"):
         monkeypatch.setenv("C3D_FUSED_STEP", fused)
         for concurrent in (False, True):
@@ -180,3 +184,33 @@ def test_proto_step_phases_against_the_two_entry_points(cuda_device):
     ops.proto_loss_backward_raw(feats.shape, cfg, C, M, ws, torch.ones((), device="cuda"), grad)
     assert torch.equal(grad, f1.grad)
     assert ops.proto_loss_info(ws)[1] == int((labels > 0).sum())
+
+
+def test_device_step_counters_vary_the_draws_in_graph_replays(cuda_device, monkeypatch):
+    """A captured graph bakes `seed` in; the device-side counters (advanced by the sampler and by
+    the EMA apply) make every replay draw new anchors and new Gumbel noise."""
+    import dataclasses
+    from coarse3d_b200 import ops, synth
+    from coarse3d_b200.pipeline import HotPathStep
+    monkeypatch.setenv("C3D_SCHEDULE", "fill_in_knn")
+    shape = dataclasses.replace(synth.NUSCENES, label_ratio=2e-2)   # many pixels per segment to draw from
+    step = HotPathStep(shape, 3, dim=32, sub_protos=4, num_anchor=16, n_sets=2, seed0=77, momentum=0.5)
+    assert step.capture(), getattr(step, "capture_error", "")
+    step.seed_counters.zero_()
+    bank0 = step.protos.clone()
+    losses = []
+    for _ in range(3):
+        step.protos.copy_(bank0)
+        ops.bank_normalise(bank0, out=step.bank_n)
+        step.step(0)
+        torch.cuda.synchronize()
+        losses.append(float(step.loss))
+    assert step.seed_counters.tolist() == [3, 3]
+    assert len(set(losses)) == 3
+    # same counters, same draws
+    step.seed_counters.zero_()
+    step.protos.copy_(bank0)
+    ops.bank_normalise(bank0, out=step.bank_n)
+    step.step(0)
+    torch.cuda.synchronize()
+    assert float(step.loss) == losses[0]

@@ -51,16 +51,15 @@ def test_dropin_matches_oracle_and_golden(cuda_device, case):
             assert np.array_equal(_bits(out[k]), _bits(g[k])), k
 
 
-@pytest.mark.parametrize("f64_only", ["0", "1"])
+@pytest.mark.parametrize("f64_only", [False, True])
 @pytest.mark.parametrize("shape_name,batch", [("kitti", 3), ("nuscenes", 5), ("poss", 2)])
-def test_batched_ragged_matches_oracle(cuda_device, shape_name, batch, f64_only, monkeypatch):
+def test_batched_ragged_matches_oracle(cuda_device, shape_name, batch, f64_only):
     from coarse3d_b200 import ops, synth
-    monkeypatch.setenv("C3D_PROJECT_F64_ONLY", f64_only)
     shp = synth.SHAPES[shape_name]
     pts, offs, _, _ = synth.make_batch(shp, batch, seed0=100, ragged=True)
     fov = ops.Fov.from_degrees(shp.fov_up, shp.fov_down)
     out = ops.project_batch(torch.from_numpy(pts).cuda(), torch.from_numpy(offs).cuda(), fov,
-                            shp.proj_h, shp.proj_w)
+                            shp.proj_h, shp.proj_w, exact_f64=f64_only)
     torch.cuda.synchronize()
     assert int(out.flags.item()) == 0
     ofov = oproj.Fov(fov_up=shp.fov_up, fov_down=shp.fov_down, proj_h=shp.proj_h, proj_w=shp.proj_w)
@@ -131,9 +130,7 @@ def test_full_size_properties_and_hybrid_equals_f64(cuda_device, monkeypatch):
     pts, offs, _, _ = synth.make_batch(shp, 8, seed0=1000)
     P, O = torch.from_numpy(pts).cuda(), torch.from_numpy(offs).cuda()
     fov = ops.Fov.from_degrees(shp.fov_up, shp.fov_down)
-    monkeypatch.setenv("C3D_PROJECT_F64_ONLY", "1")
-    ref = ops.project_batch(P, O, fov, shp.proj_h, shp.proj_w)
-    monkeypatch.setenv("C3D_PROJECT_F64_ONLY", "0")
+    ref = ops.project_batch(P, O, fov, shp.proj_h, shp.proj_w, exact_f64=True)
     out = ops.project_batch(P, O, fov, shp.proj_h, shp.proj_w)
     torch.cuda.synchronize()
     for a, b in zip(out[:7], ref[:7]):
@@ -159,7 +156,7 @@ def test_full_size_properties_and_hybrid_equals_f64(cuda_device, monkeypatch):
 def test_estimate_guard_band_on_adversarial_points(cuda_device, monkeypatch):
     """Points constructed to sit on / next to pixel boundaries, on the axes, at extreme
     magnitudes and outside the vertical field of view: the fast-transcendental + guard band
-    path must give exactly the exact-chain pixels (C3D_PROJECT_F64_ONLY=1) and the oracle's."""
+    path must give exactly the exact-chain pixels (exact_f64=True) and the oracle's."""
     from coarse3d_b200 import ops
     rng = np.random.default_rng(11)
     H, W, up, down = 64, 2048, 3.0, -25.0
@@ -188,9 +185,7 @@ def test_estimate_guard_band_on_adversarial_points(cuda_device, monkeypatch):
     P = torch.from_numpy(pts).cuda()
     O = torch.tensor([0, pts.shape[0]], dtype=torch.int32, device="cuda")
     fov = ops.Fov.from_degrees(up, down)
-    monkeypatch.setenv("C3D_PROJECT_F64_ONLY", "1")
-    ref = [t.clone() for t in ops.project_batch(P, O, fov, H, W)]
-    monkeypatch.setenv("C3D_PROJECT_F64_ONLY", "0")
+    ref = [t.clone() for t in ops.project_batch(P, O, fov, H, W, exact_f64=True)]
     out = ops.project_batch(P, O, fov, H, W)
     for a, b in zip(out, ref):
         assert torch.equal(a, b)

@@ -60,17 +60,16 @@ def main():
     bufs = ops.ProjectionBuffers(B, N, 4, shp.proj_h, shp.proj_w, "cuda")
     if "project" in args.ops:
         for mode in ("0", "1"):
-            os.environ["C3D_PROJECT_F64_ONLY"] = mode
+            f64 = mode == "1"
             kern = None
             if os.environ.get("C3D_MB_PROFILE"):   # per-kernel events perturb the total
                 with ops.profile("") as prof:
-                    timeit(lambda: ops.project_batch(P, O, fov, shp.proj_h, shp.proj_w, buffers=bufs), flush=flush)
+                    timeit(lambda: ops.project_batch(P, O, fov, shp.proj_h, shp.proj_w, buffers=bufs, exact_f64=f64), flush=flush)
                     kern = {n: round(1e3 * v[0] / (ITERS[0] + WARMUP[0]), 1) for n, v in prof.all().items()}
-            med, mn = timeit(lambda: ops.project_batch(P, O, fov, shp.proj_h, shp.proj_w, buffers=bufs), flush=flush)
+            med, mn = timeit(lambda: ops.project_batch(P, O, fov, shp.proj_h, shp.proj_w, buffers=bufs, exact_f64=f64), flush=flush)
             by = 28 * N + 28 * B * HW
             res["project_f64only=" + mode] = dict(ms=med, ms_min=mn, GBs=by / med / 1e6, scans_s=B / med * 1e3,
                                                   kernels_us_per_call=kern)
-        os.environ["C3D_PROJECT_F64_ONLY"] = "0"
     pr = ops.project_batch(P, O, fov, shp.proj_h, shp.proj_w, buffers=bufs)
     if "knn" in args.ops:
         for idt, name in ((torch.int64, "i64"), (torch.int32, "i32")):
