@@ -264,8 +264,8 @@ def run_torch_eager(args, rank, world):
     of the workload's batch per step (the dense prototype similarity needs 1.6 KB per pixel)."""
     if rank != 0:
         return
-    import baselines
     synth = load_synth()
+    import baselines
     shp = synth.SHAPES[args.shape]
     dev = torch.device("cuda", 0)
     H, W, C, M, D = shp.proj_h, shp.proj_w, shp.n_classes, 20, args.dim
@@ -497,6 +497,8 @@ def run_e2e(args, step, dev, world, K):
     rp = RangeProjection(fov_up=shp.fov_up, fov_down=shp.fov_down, proj_h=H, proj_w=W, device=dev)
     crit = ContrastMEMLoss(ignore_label=0, temperature=0.07, num_anchor=512)
     bank = PrototypeBank(C, step.M, step.dim, proto_mom=0.999).to(dev)
+    with torch.no_grad():
+        bank.prototypes.copy_(step.protos)     # one bank value on every rank (a replicated parameter)
     knn = KNN(dict(knn=5, search=5, sigma=1.0, cutoff=1.0), C)
     # per-point labels travel as uint8 class ids (C <= 255), a quarter of the loaders' int32
     label_np = np.int32 if os.environ.get("C3D_E2E_LABELS", "u8") == "i32" else np.uint8

@@ -56,7 +56,7 @@ class HotPathStep:
 
     def __init__(self, shape, batch, dim=128, sub_protos=20, num_anchor=512, temperature=0.07,
                  momentum=0.999, n_sets=3, seed0=1000, device="cuda", group=None,
-                 knn=(5, 5, 1.0, 1.0), concurrent=True, parts=None):
+                 knn=(5, 5, 1.0, 1.0), concurrent=True, parts=None, bank_seed=7):
         self.shape, self.batch, self.dim, self.M = shape, batch, dim, sub_protos
         self.device, self.group = torch.device(device), group
         self.knn_k, self.knn_s, self.knn_sigma, self.knn_cutoff = knn
@@ -73,7 +73,9 @@ class HotPathStep:
         self.proj_bufs = [ops.ProjectionBuffers(batch, n, 4, H, W, self.device) for _ in self.sets]
         for s, b in zip(self.sets, self.proj_bufs):
             s.derive_labels(ops.project_batch(s.points, s.offsets, self.fov, H, W, buffers=b))
-        g = torch.Generator(device=self.device).manual_seed(seed0 + 7)
+        # the bank is a model parameter: the SAME initial value on every rank (seed0 differs per
+        # rank, it seeds the scans), kept identical afterwards by the summed update
+        g = torch.Generator(device=self.device).manual_seed(bank_seed)
         self.protos = torch.nn.functional.normalize(
             torch.randn((C, sub_protos, dim), device=self.device, generator=g), dim=-1)
         self.ln_d = (torch.ones(dim, device=self.device), torch.zeros(dim, device=self.device))
