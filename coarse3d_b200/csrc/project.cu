@@ -74,6 +74,19 @@ __device__ __forceinline__ void pixel_of(float x, float y, float q, const ProjPa
   py = (int)fmaxf(fminf(p.hmax, floorf(fy)), 0.0f);
 }
 
+// L2 residency hints of the two-kernel form.  The z-buffer (8 B per pixel, 67 MB at batch 64) is
+// written by the point pass and consumed by the resolve pass right after: its lines are marked
+// evict-last so that the streamed per-point traffic does not push them out to DRAM and back.
+__device__ __forceinline__ unsigned long long policy_evict_last() {
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;\n" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void red_min_u64_hint(unsigned long long* addr, unsigned long long v,
+                                                 unsigned long long pol) {
+  asm volatile("red.global.min.L2::cache_hint.u64 [%0], %1, %2;\n" :: "l"(addr), "l"(v), "l"(pol) : "memory");
+}
+
 template <bool kHybrid, bool kC4>
 __global__ void __launch_bounds__(256)
 project_points_kernel(const float* __restrict__ points, int c_in,
@@ -105,10 +118,10 @@ project_points_kernel(const float* __restrict__ points, int c_in,
   float q = z / depth;
   int px, py; bool nan;
   pixel_of<kHybrid>(x, y, q, p, px, py, nan);
-  upx[g] = px; upy[g] = py; udepth[g] = depth;
+  __stcs(upx + g, px); __stcs(upy + g, py); __stcs(udepth + g, depth);   // written once, streamed
   unsigned long long key =
       ((unsigned long long)depth_key(depth) << 32) | (uint32_t)(g - s_off[b]);
-  atomicMin(zbuf + (size_t)b * HW + py * p.W + px, key);
+  red_min_u64_hint(zbuf + (size_t)b * HW + py * p.W + px, key, policy_evict_last());
   if (nan) atomicOr(flags, 1);
 }
 
@@ -229,13 +242,230 @@ resolve_assemble_kernel(const float* __restrict__ points, const int32_t* __restr
   }
 }
 
+
+// ------------------------------------------------------------ fused, persistent --
+// One launch for both passes, z-buffer resident in L2.
+//
+// The two-kernel form moves ~1.7x the algorithmic bytes through DRAM at batch 64: every scan's
+// 1 MB of z-buffer keys is written back after the point pass, re-read by the resolve pass and
+// written back again after its reset (24 B per pixel), and the winners' points are re-fetched.
+// Here a persistent grid pulls work items from one queue in which the resolve items of scan s
+// follow the point items of scan s + 2:
+//     P(0) P(1) | R(0) P(2) | R(1) P(3) | ... | R(B-2) | R(B-1)
+// and the z-buffer is a ring of kRing scan-sized regions (8 MB for KITTI) that never leaves L2.
+// R(s) waits (spin on a counter) until every P(s) item has retired, P(s) until R(s - kRing) has
+// reset the region it reuses; both are earlier in the queue, hence already running: no deadlock,
+// no grid-wide barrier.  DRAM traffic ~= the algorithmic 28 N + 28 HW bytes.
+constexpr int kRing = 8;            // z-buffer regions (scans in flight)
+constexpr int kPtItem = 1024;       // points per P item (4 per thread)
+constexpr int kPxItem = 1024;       // pixels per R item (4 per thread)
+
+struct FusedCtl {                   // device control block (zeroed per call), after the ring
+  unsigned int head;                // next queue item
+  unsigned int pad[15];
+  // followed by pdone[B], rdone[B]
+};
+
+__device__ __forceinline__ void wait_count(unsigned int* ctr, unsigned int need) {
+  if (threadIdx.x == 0) {
+    while (atomicAdd(ctr, 0u) < need) __nanosleep(64);
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+template <bool kHybrid, bool kAssemble>
+__global__ void __launch_bounds__(256)
+project_fused_kernel(const float4* __restrict__ points, const int32_t* __restrict__ offsets, int batch,
+                     const float* __restrict__ depth_override, ProjParams p,
+                     int32_t* __restrict__ upx, int32_t* __restrict__ upy, float* __restrict__ udepth,
+                     unsigned long long* __restrict__ ring, unsigned int* __restrict__ ctl,
+                     int32_t* __restrict__ flags,
+                     // plain outputs
+                     float* __restrict__ proj_range, float4* __restrict__ proj_pc,
+                     int32_t* __restrict__ proj_idx, int32_t* __restrict__ proj_mask,
+                     // assemble outputs (f-1)
+                     const void* __restrict__ sem_label, const void* __restrict__ weak_label, int label_is_u8,
+                     const float* __restrict__ mean, const float* __restrict__ stdv,
+                     float* __restrict__ feature, long long* __restrict__ train_label,
+                     long long* __restrict__ eval_label) {
+  extern __shared__ int32_t s_tab[];            // [batch + 1] offsets, [batch + 3] block bases
+  int32_t* s_off = s_tab;
+  int32_t* s_base = s_tab + batch + 1;
+  __shared__ unsigned int s_item;
+  const int HW = p.H * p.W;
+  const int nR = (HW + kPxItem - 1) / kPxItem;
+  for (int i = threadIdx.x; i <= batch; i += blockDim.x) s_off[i] = offsets[i];
+  __syncthreads();
+  // queue block j = R items of scan j - 2, then P items of scan j; exclusive prefix of the sizes
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int j = 0; j < batch + 2; ++j) {
+      s_base[j] = run;
+      if (j >= 2) run += nR;
+      if (j < batch) run += (s_off[j + 1] - s_off[j] + kPtItem - 1) / kPtItem;
+    }
+    s_base[batch + 2] = run;
+  }
+  __syncthreads();
+  const unsigned int n_items = (unsigned int)s_base[batch + 2];
+  unsigned int* pdone = ctl + 16;
+  unsigned int* rdone = pdone + batch;
+
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) s_item = atomicAdd(&ctl[0], 1u);
+    __syncthreads();
+    const unsigned int item = s_item;
+    if (item >= n_items) break;
+    int lo = 0, hi = batch + 2;                 // s_base[lo] <= item < s_base[hi]
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if ((unsigned)s_base[mid] <= item) lo = mid; else hi = mid; }
+    const int j = lo;
+    int k = (int)item - s_base[j];
+    const bool is_r = (j >= 2) && (k < nR);
+    if (!is_r) {
+      // ---------------- P item: kPtItem points of scan j
+      if (j >= 2) k -= nR;
+      const int s = j;
+      if (s >= kRing) wait_count(&rdone[s - kRing], (unsigned)nR);   // the region it reuses is reset
+      unsigned long long* zb = ring + (size_t)(s % kRing) * HW;
+      const int g0 = s_off[s] + k * kPtItem, g_end = s_off[s + 1];
+      bool nan_any = false;
+#pragma unroll
+      for (int u = 0; u < kPtItem / 256; ++u) {
+        const int g = g0 + u * 256 + threadIdx.x;
+        if (g < g_end) {
+          const float4 v = __ldg(points + g);
+          const float depth = depth_override ? depth_override[g] : sqrtf((v.x * v.x + v.y * v.y) + v.z * v.z);
+          const float q = v.z / depth;
+          int px, py; bool nan;
+          pixel_of<kHybrid>(v.x, v.y, q, p, px, py, nan);
+          upx[g] = px; upy[g] = py; udepth[g] = depth;
+          const unsigned long long key = ((unsigned long long)depth_key(depth) << 32) | (uint32_t)(g - s_off[s]);
+          atomicMin(zb + py * p.W + px, key);
+          nan_any |= nan;
+        }
+      }
+      if (nan_any) atomicOr(flags, 1);
+      __threadfence();
+      __syncthreads();
+      if (threadIdx.x == 0) atomicAdd(&pdone[s], 1u);
+    } else {
+      // ---------------- R item: kPxItem pixels of scan j - 2
+      const int s = j - 2;
+      const unsigned int nP = (unsigned)((s_off[s + 1] - s_off[s] + kPtItem - 1) / kPtItem);
+      wait_count(&pdone[s], nP);
+      unsigned long long* zb = ring + (size_t)(s % kRing) * HW;
+      const int off = s_off[s];
+      constexpr int U = kPxItem / 256;
+      unsigned long long key[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int pix = k * kPxItem + u * 256 + threadIdx.x;
+        key[u] = (pix < HW) ? __ldcg(zb + pix) : ~0ull;       // L2: the keys were written by other SMs
+      }
+      float4 pt[U]; int sl[U], wl[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        pt[u] = make_float4(-1.f, -1.f, -1.f, -1.f); sl[u] = 0; wl[u] = 0;
+        if (key[u] != ~0ull) {
+          const size_t row = (size_t)off + (uint32_t)key[u];
+          pt[u] = __ldg(points + row);
+          if (kAssemble) {
+            if (label_is_u8) {
+              if (sem_label) sl[u] = __ldg(reinterpret_cast<const uint8_t*>(sem_label) + row);
+              if (weak_label) wl[u] = __ldg(reinterpret_cast<const uint8_t*>(weak_label) + row);
+            } else {
+              if (sem_label) sl[u] = __ldg(reinterpret_cast<const int32_t*>(sem_label) + row);
+              if (weak_label) wl[u] = __ldg(reinterpret_cast<const int32_t*>(weak_label) + row);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int pix = k * kPxItem + u * 256 + threadIdx.x;
+        if (pix >= HW) continue;
+        const size_t q = (size_t)s * HW + pix;
+        const bool valid = key[u] != ~0ull;
+        const int idx = valid ? (int)(uint32_t)key[u] : -1;
+        const float rng = valid ? key_depth((uint32_t)(key[u] >> 32)) : -1.0f;
+        if (!kAssemble) {
+          proj_range[q] = rng;
+          proj_idx[q] = idx;
+          proj_mask[q] = idx > 0;  // projection.py:113
+          st_stream(proj_pc + q, pt[u]);
+        } else {
+          if (proj_range) proj_range[q] = rng;
+          if (proj_idx) proj_idx[q] = idx;
+          // loader :124-132 builds float32 label images, trainer :600-601 casts them to int64
+          if (eval_label) eval_label[q] = (long long)(float)sl[u];
+          if (train_label) train_label[q] = (long long)(float)wl[u];
+          float f[5];
+          f[0] = rng; f[1] = pt[u].x; f[2] = pt[u].y; f[3] = pt[u].z;
+          f[4] = ((pt[u].w != -1.0f) ? 1.0f : 0.0f) * pt[u].w;          // loader :161-164
+          float* dst = feature + (size_t)s * 5 * HW + pix;
+          if (mean) {
+            const float m = (sl[u] > 0) ? 1.0f : 0.0f;                   // eval_mask, trainer :603
+#pragma unroll
+            for (int c = 0; c < 5; ++c) f[c] = (f[c] - mean[c]) / stdv[c] * m;  // trainer :604-608
+          }
+#pragma unroll
+          for (int c = 0; c < 5; ++c) dst[(size_t)c * HW] = f[c];
+        }
+        if (valid) zb[pix] = ~0ull;     // the ring region is left clean for scan s + kRing / the next call
+      }
+      __threadfence();
+      __syncthreads();
+      if (threadIdx.x == 0) atomicAdd(&rdone[s], 1u);
+    }
+  }
+}
+
+static size_t fused_ctl_bytes(int batch) { return (size_t)(16 + 2 * (size_t)batch) * 4; }
+static size_t fused_ring_bytes(int batch, int HW) {
+  return (size_t)(batch < kRing ? batch : kRing) * HW * sizeof(unsigned long long);
+}
+
+
+// Launches the fused persistent kernel (points must be [N, 4], 16 B aligned).
+template <bool kAssemble>
+static int launch_fused(const float* points, const int32_t* offsets, int batch, long long total_points,
+                        const float* depth_override, const ProjParams& p, bool hybrid, int32_t* upx,
+                        int32_t* upy, float* udepth, void* workspace, int32_t* status_flags,
+                        float* proj_range, float* proj_pc, int32_t* proj_idx, int32_t* proj_mask,
+                        const void* sem_label, const void* weak_label, int label_is_u8, const float* mean,
+                        const float* stdv, float* feature, long long* train_label, long long* eval_label,
+                        cudaStream_t stream) {
+  const int HW = p.H * p.W;
+  auto* ring = reinterpret_cast<unsigned long long*>(workspace);
+  auto* ctl = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(workspace) +
+                                              (size_t)batch * HW * sizeof(unsigned long long));
+  C3D_CUDA(cudaMemsetAsync(ctl, 0, fused_ctl_bytes(batch), stream));
+  const long long items = (long long)batch * ((HW + kPxItem - 1) / kPxItem) +
+                          (total_points + kPtItem - 1) / kPtItem + batch;
+  long long grid = (long long)kNumSMs * 4;   // 64 registers x 256 threads: four CTAs per SM
+  if (grid > items) grid = items;
+  const size_t smem = (size_t)(2 * batch + 4) * sizeof(int32_t);
+  KernelTimer kt__("project_fused_kernel", stream);
+#define C3D_FUSED(HY)                                                                               \
+  project_fused_kernel<HY, kAssemble><<<(unsigned)grid, 256, smem, stream>>>(                        \
+      reinterpret_cast<const float4*>(points), offsets, batch, depth_override, p, upx, upy, udepth,  \
+      ring, ctl, status_flags, proj_range, reinterpret_cast<float4*>(proj_pc), proj_idx, proj_mask,  \
+      sem_label, weak_label, label_is_u8, mean, stdv, feature, train_label, eval_label)
+  if (hybrid) C3D_FUSED(true); else C3D_FUSED(false);
+#undef C3D_FUSED
+  return check_launch("project_fused_kernel");
+}
+
 }  // namespace c3d
 
 using namespace c3d;
 
 extern "C" size_t c3d_project_workspace_bytes(int batch, int proj_h, int proj_w) {
   if (batch <= 0 || proj_h <= 0 || proj_w <= 0) return 0;
-  return (size_t)batch * proj_h * proj_w * sizeof(unsigned long long);
+  // two-kernel form: one key per pixel; fused form: a ring of kRing scans + the control block
+  return (size_t)batch * proj_h * proj_w * sizeof(unsigned long long) + fused_ctl_bytes(batch);
 }
 
 extern "C" int c3d_project_batch(
@@ -273,14 +503,20 @@ extern "C" int c3d_project_batch(
 
   const long long total_px = (long long)batch * proj_h * proj_w;
   auto* zbuf = reinterpret_cast<unsigned long long*>(workspace);
-  if (!(workspace_flags & 1)) {
-    KernelTimer kt__("zbuf_memset", stream);
-    C3D_CUDA(cudaMemsetAsync(zbuf, 0xFF, (size_t)total_px * sizeof(unsigned long long), stream));
-  }
-
   const bool c4 = (c_in == 4) && ((reinterpret_cast<uintptr_t>(points) & 15) == 0) &&
                   ((reinterpret_cast<uintptr_t>(proj_pointcloud) & 15) == 0);
   const bool hybrid = !(workspace_flags & 2);
+  const bool fused = c4 && (workspace_flags & 4);    // bit 2: the fused persistent kernel (A/B; measured slower)
+  if (!(workspace_flags & 1)) {
+    KernelTimer kt__("zbuf_memset", stream);
+    const size_t nb = fused ? fused_ring_bytes(batch, proj_h * proj_w) : (size_t)total_px * sizeof(unsigned long long);
+    C3D_CUDA(cudaMemsetAsync(zbuf, 0xFF, nb, stream));
+  }
+  if (fused)
+    return launch_fused<false>(points, offsets, batch, total_points, depth_override, p, hybrid, uproj_x_idx,
+                               uproj_y_idx, uproj_depth, workspace, status_flags, proj_range, proj_pointcloud,
+                               proj_idx, proj_mask, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr,
+                               nullptr, stream);
   const int threads = 256;
   if (total_points > 0) {
     int grid = (int)((total_points + threads - 1) / threads);  // short CTAs (overlap)
@@ -350,11 +586,18 @@ extern "C" int c3d_project_assemble_batch(
   p.sy = p.hf / p.fov_vert;
   const long long total_px = (long long)batch * proj_h * proj_w;
   auto* zbuf = reinterpret_cast<unsigned long long*>(workspace);
+  const bool hybrid = !(workspace_flags & 2);
+  const bool fused = (workspace_flags & 4) != 0;
   if (!(workspace_flags & 1)) {
     KernelTimer kt__("zbuf_memset", stream);
-    C3D_CUDA(cudaMemsetAsync(zbuf, 0xFF, (size_t)total_px * sizeof(unsigned long long), stream));
+    const size_t nb = fused ? fused_ring_bytes(batch, proj_h * proj_w) : (size_t)total_px * sizeof(unsigned long long);
+    C3D_CUDA(cudaMemsetAsync(zbuf, 0xFF, nb, stream));
   }
-  const bool hybrid = !(workspace_flags & 2);
+  if (fused)
+    return launch_fused<true>(points, offsets, batch, total_points, depth_override, p, hybrid, uproj_x_idx,
+                              uproj_y_idx, uproj_depth, workspace, status_flags, proj_range, nullptr, proj_idx,
+                              nullptr, sem_label, weak_label, label_is_u8, img_mean, img_std, feature,
+                              (long long*)train_label, (long long*)eval_label, stream);
   const int threads = 256;
   if (total_points > 0) {
     int grid = (int)((total_points + threads - 1) / threads);

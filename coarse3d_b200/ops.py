@@ -79,11 +79,11 @@ class ProjectionBuffers:
         # call saw a NaN pixel coordinate (depth == 0); `flags.zero_()` re-arms it
         nbytes = lib.c3d_project_workspace_bytes(batch, proj_h, proj_w)
         self.workspace = torch.empty((nbytes,), dtype=torch.uint8, device=device)
-        self.clean = False  # True once a call has left the z-buffer reset
+        self.clean = False  # "two" / "fused": the form whose call has left the z-buffer reset
 
 
 def project_batch(points, offsets, fov: Fov, proj_h, proj_w, depth=None,
-                  buffers: ProjectionBuffers = None, exact_f64=False) -> Projection:
+                  buffers: ProjectionBuffers = None, exact_f64=False, fused_kernel=False) -> Projection:
     """RangeProjection.doProjection for a CSR batch (projection.py:43-115).
 
     points (sum N, C>=3) f32, offsets (B+1,) i32, optional depth (sum N,) f32;
@@ -105,14 +105,17 @@ def project_batch(points, offsets, fov: Fov, proj_h, proj_w, depth=None,
         b = ProjectionBuffers(batch, total, c_in, proj_h, proj_w, points.device)
     elif (b.batch, b.total, b.c_in, b.H, b.W) != (batch, total, c_in, proj_h, proj_w):
         raise ValueError("ProjectionBuffers shape mismatch")
-    was_clean, b.clean = b.clean, False   # a failed call may leave a dirty z-buffer
+    form = "fused" if fused_kernel else "two"
+    was_clean, b.clean = (b.clean == form), False   # a failed call may leave a dirty z-buffer; the two
+    # forms initialise different parts of the workspace, so "clean" holds per form
     check(lib.c3d_project_batch(
         _p(points), c_in, _p(offsets), batch, total, _p(depth),
         fov.abs_fov_left, fov.fov_hori, fov.abs_fov_down, fov.fov_vert, proj_h, proj_w,
         _p(b.proj_range), _p(b.proj_pointcloud), _p(b.proj_idx), _p(b.proj_mask),
         _p(b.uproj_x_idx), _p(b.uproj_y_idx), _p(b.uproj_depth), _p(b.workspace),
-        (1 if was_clean else 0) | (2 if exact_f64 else 0), _p(b.flags), _stream()))
-    b.clean = True
+        (1 if was_clean else 0) | (2 if exact_f64 else 0) | (4 if fused_kernel else 0), _p(b.flags),
+        _stream()))
+    b.clean = form
     return Projection(b.proj_pointcloud, b.proj_range, b.proj_idx, b.proj_mask,
                       b.uproj_x_idx, b.uproj_y_idx, b.uproj_depth, b.flags)
 
@@ -132,7 +135,7 @@ class Assembled(NamedTuple):
 
 def project_assemble_batch(points, offsets, fov: Fov, proj_h, proj_w, sem_label=None,
                            weak_label=None, img_mean=None, img_std=None, depth=None,
-                           buffers: ProjectionBuffers = None) -> Assembled:
+                           buffers: ProjectionBuffers = None, fused_kernel=False) -> Assembled:
     """Projection fused with its caller (loader :124-172, trainer :600-608): label images
     and the 5-channel network input straight from the z-buffer winners.
 
@@ -161,14 +164,15 @@ def project_assemble_batch(points, offsets, fov: Fov, proj_h, proj_w, sem_label=
     feature = torch.empty((batch, 5, proj_h, proj_w), dtype=torch.float32, device=dev)
     train = torch.empty((batch, proj_h, proj_w), dtype=torch.int64, device=dev) if weak_label is not None else None
     evall = torch.empty((batch, proj_h, proj_w), dtype=torch.int64, device=dev) if sem_label is not None else None
-    was_clean, b.clean = b.clean, False
+    form = "fused" if fused_kernel else "two"
+    was_clean, b.clean = (b.clean == form), False
     check(lib.c3d_project_assemble_batch(
         _p(points), _p(offsets), batch, total, _p(depth), _p(sem_label), _p(weak_label),
         1 if ldt == torch.uint8 else 0, _p(img_mean), _p(img_std), fov.abs_fov_left, fov.fov_hori, fov.abs_fov_down, fov.fov_vert,
         proj_h, proj_w, _p(feature), _p(train), _p(evall), _p(b.proj_range), _p(b.proj_idx),
         _p(b.uproj_x_idx), _p(b.uproj_y_idx), _p(b.uproj_depth), _p(b.workspace),
-        1 if was_clean else 0, _p(b.flags), _stream()))
-    b.clean = True
+        (1 if was_clean else 0) | (4 if fused_kernel else 0), _p(b.flags), _stream()))
+    b.clean = form
     return Assembled(feature, train, evall, b.proj_range, b.proj_idx, b.uproj_x_idx, b.uproj_y_idx,
                      b.uproj_depth, b.flags)
 

@@ -87,12 +87,15 @@ int c3d_project_batch(
     int32_t* uproj_y_idx,         /* [total_points]                              */
     float* uproj_depth,           /* [total_points]                              */
     void* workspace,              /* c3d_project_workspace_bytes                 */
-    int workspace_flags,          /* bit 0: workspace is as a previous call left it
+    int workspace_flags,          /* bit 0: workspace is as a previous call OF THE SAME
+                                     FORM (bit 2) left it
                                      (all 0xFF), so the 8 B/pixel memset is
                                      skipped (0: fresh memory); bit 1: evaluate the
                                      angles of every point in fp64 (default: only
                                      inside the guard band of a pixel boundary --
-                                     same pixels)                 */
+                                     same pixels); bit 2: the fused
+                                     persistent kernel instead of the two-kernel form
+                                     (same results; kept for A/B timing, slower) */
     int32_t* status_flags,        /* [1], caller-zeroed                          */
     void* stream);
 

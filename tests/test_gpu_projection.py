@@ -193,3 +193,23 @@ def test_estimate_guard_band_on_adversarial_points(cuda_device, monkeypatch):
     assert np.array_equal(out.uproj_x_idx.cpu().numpy(), o["uproj_x_idx"])
     assert np.array_equal(out.uproj_y_idx.cpu().numpy(), o["uproj_y_idx"])
     assert np.array_equal(out.proj_idx[0].cpu().numpy(), o["proj_idx"])
+
+
+def test_fused_persistent_kernel_equals_two_kernel_form(cuda_device):
+    """c3d_project_batch flag bit 2: one persistent launch with a ring z-buffer (work queue,
+    per-scan counters) must give the two-kernel form's outputs bit for bit, ragged batches and
+    more scans than ring slots included, and leave the workspace reusable."""
+    from coarse3d_b200 import ops, synth
+    shp = synth.NUSCENES
+    pts, offs, _, _ = synth.make_batch(shp, 11, seed0=300, ragged=True)
+    P, O = torch.from_numpy(pts).cuda(), torch.from_numpy(offs).cuda()
+    fov = ops.Fov.from_degrees(shp.fov_up, shp.fov_down)
+    ref = [t.clone() for t in ops.project_batch(P, O, fov, shp.proj_h, shp.proj_w)]
+    bufs = ops.ProjectionBuffers(11, pts.shape[0], 4, shp.proj_h, shp.proj_w, "cuda")
+    for _ in range(3):     # repeated calls reuse the ring left clean by the previous one
+        out = ops.project_batch(P, O, fov, shp.proj_h, shp.proj_w, buffers=bufs, fused_kernel=True)
+        for a, b in zip(out[:7], ref[:7]):
+            assert torch.equal(a, b)
+    out = ops.project_batch(P, O, fov, shp.proj_h, shp.proj_w, buffers=bufs)   # and back
+    for a, b in zip(out[:7], ref[:7]):
+        assert torch.equal(a, b)
