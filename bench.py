@@ -514,8 +514,11 @@ def run_e2e(args, step, dev, world, K):
     d_in = [dict(points=torch.empty_like(step.sets[0].points), offsets=torch.empty_like(step.sets[0].offsets),
                  weak=torch.empty((step.n_points,), dtype=label_t, device=dev))
             for _ in range(NB)]
+    # KNN labels go back as the reference's int64 by default; C3D_E2E_KNN=u8 takes the opt-in uint8
+    knn_u8 = os.environ.get("C3D_E2E_KNN", "i64") == "u8"
+    knn_t = torch.uint8 if knn_u8 else torch.int64
     h_out = [dict(loss=torch.zeros((), dtype=torch.float32).pin_memory(),
-                  knn=torch.zeros((step.n_points,), dtype=torch.int64).pin_memory()) for _ in range(NB)]
+                  knn=torch.zeros((step.n_points,), dtype=knn_t).pin_memory()) for _ in range(NB)]
     s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
     ev_in = [torch.cuda.Event() for _ in range(NB)]
     ev_done = [torch.cuda.Event() for _ in range(NB)]
@@ -524,11 +527,11 @@ def run_e2e(args, step, dev, world, K):
     for e in ev_done + ev_out:
         e.record(main)
     h2d = sum(host[0][k].numel() * host[0][k].element_size() for k in host[0])
-    d2h = 4 + step.n_points * 8
+    d2h = 4 + step.n_points * (1 if knn_u8 else 8)
 
     s0 = step.sets[0]
     d_loss = [torch.zeros((), device=dev) for _ in range(NB)]
-    d_knn = [torch.zeros((step.n_points,), dtype=torch.int64, device=dev) for _ in range(NB)]
+    d_knn = [torch.zeros((step.n_points,), dtype=knn_t, device=dev) for _ in range(NB)]
 
     use_classes = os.environ.get("C3D_E2E_API", "classes") == "classes"   # "pipeline": HotPathStep.run_inputs
 
@@ -553,7 +556,7 @@ def run_e2e(args, step, dev, world, K):
                     proto_queue=bank.prototypes.detach().unsqueeze(0))
         loss.backward()
         lab = knn.forward_batch(pr.proj_range, pr.uproj_depth, s0.argmax, pr.uproj_x_idx,
-                                pr.uproj_y_idx, di["offsets"])
+                                pr.uproj_y_idx, di["offsets"], out_uint8=knn_u8)
         d_loss[j].copy_(loss.detach())
         d_knn[j].copy_(lab)
 
@@ -638,6 +641,9 @@ def run_e2e(args, step, dev, world, K):
             "host_inputs": "points f32 (N,4), offsets, per-point weak labels %s (pinned); " % label_t +
                            "CNN activations resident on device as in the reference",
             "pipelining": "%d-deep buffered: H2D / compute / D2H of consecutive steps on three streams" % NB,
+            "knn_labels_to_host": str(knn_t), "h2d_gbs": h2d * K / (float(ms.item()) * 1e-3) / 1e9,
+            "bound": "host->device link: %.1f MB per step at the PCIe Gen5 x16 rate (~52 GB/s measured, "
+                     "tools/pcie_probe.py) is %.2f ms" % (h2d / 1e6, h2d / 52e9 * 1e3),
             "compute_graph": graphs is not None}
 
 

@@ -260,7 +260,7 @@ knn_vote_kernel(const float* __restrict__ proj_range, const void* __restrict__ p
         const int y = y0 + s / S - PAD, x = x0 + s % S - PAD;
         if (y >= 0 && y < H && x >= 0 && x < W) {
           const size_t o = (size_t)b * HW + y * W + x;
-          cls[j] = lab64 ? (int)__ldg(reinterpret_cast<const long long*>(cbase) + o)
+          cls[j] = (lab64 & 1) ? (int)__ldg(reinterpret_cast<const long long*>(cbase) + o)
                          : __ldg(reinterpret_cast<const int*>(cbase) + o);
         }
       }
@@ -276,7 +276,7 @@ knn_vote_kernel(const float* __restrict__ proj_range, const void* __restrict__ p
         int c = 0;
         if (y >= 0 && y < H && x >= 0 && x < W) {
           const size_t o = (size_t)b * HW + y * W + x;
-          c = lab64 ? (int)__ldg(reinterpret_cast<const long long*>(cbase) + o)
+          c = (lab64 & 1) ? (int)__ldg(reinterpret_cast<const long long*>(cbase) + o)
                     : __ldg(reinterpret_cast<const int*>(cbase) + o);
         }
 #pragma unroll
@@ -299,7 +299,8 @@ knn_vote_kernel(const float* __restrict__ proj_range, const void* __restrict__ p
       if (n > best_n || (n == best_n && c < best_c)) { best_n = n; best_c = c; }
     }
   }
-  if (lab64) reinterpret_cast<long long*>(out)[g] = best_c;
+  if (lab64 & 2) reinterpret_cast<uint8_t*>(out)[g] = (uint8_t)best_c;   // opt-in compact output
+  else if (lab64) reinterpret_cast<long long*>(out)[g] = best_c;
   else reinterpret_cast<int*>(out)[g] = best_c;
   // the zero page must outlive the copies that read it (thread 0 is always a valid point)
   if (kFill >= 2 && threadIdx.x == 0) bulk_wait_read_all();
@@ -381,6 +382,7 @@ extern "C" int c3d_knn_batch(const float* proj_range, const void* proj_argmax,
   C3D_REQUIRE(batch > 0 && batch <= kMaxBatch, "batch must be in [1, %d]", kMaxBatch);
   C3D_REQUIRE(knn >= 1 && knn <= search * search && knn <= 32, "knn must be in [1, min(search^2, 32)]");
   C3D_REQUIRE(nclasses >= 2, "nclasses must be >= 2");
+  C3D_REQUIRE(!(label_is_i64 & 2) || nclasses <= 256, "uint8 output needs nclasses <= 256");
   C3D_REQUIRE(total_points >= 0 && total_points < (1ll << 31), "total_points out of range");
   C3D_REQUIRE(proj_h > 0 && proj_w > 0, "bad image size");
   C3D_REQUIRE(proj_range && proj_argmax && offsets && inv_gauss, "null pointer argument");

@@ -18,7 +18,8 @@ int proto_loss_forward_impl(
     float* loss_out, float* zero_buf, int zero_n, void* stream,
     const float* raw_rows /* [slots, D] rows left by the EMA kernel (fused step), or null */, int raw_cap,
     const float* bank_n /* [C, M, D] F.normalize'd bank, or null: normalised here */,
-    uint64_t* seed_dev /* [2] device step counters; [0] is added to `seed` and advanced by the sampler */);
+    uint64_t* seed_dev /* [2] device step counters; [0] is added to `seed` and advanced by the sampler */,
+    int rows_mode /* 0: register-tiled FFMA products, 1: tensor cores (mma.sync, 3xTF32) */);
 
 // proto_ema.cu
 struct DenseRows { const float* out_feat; const float* nearest; const float* sim; };

@@ -497,15 +497,18 @@ __device__ long long g_rows_dbg[16];
 // loss_rows16: the same math as loss_rows_kernel, organised as register-tiled products
 // over groups of 16 rows (rowgemm.cuh).  Default; C3D_LOSS_ROWS_V1=1 selects the
 // warp-per-row kernel above (kept for A/B measurements).
-template <bool kWithGrad, int kKS, int kRP, int kDch, int kDJ>
+// kMma: the two products on the tensor cores (mma.sync m16n8k8, 3xTF32; rowgemm.cuh) instead of
+// the register-tiled FFMA form.
+template <bool kWithGrad, int kKS, int kRP, int kDch, int kDJ, bool kMma>
 __global__ void __launch_bounds__(256, 1)
 loss_rows16_kernel(RowsParams p) {
   extern __shared__ __align__(16) float smem[];
   const int D = p.D, Kc = p.Kc, ldl = p.ldl;
   const BankLayout BL = BankLayout::make(D);
   float* s_bank = smem;                                   // [tile_rows] rows, layout BL
-  float* s_A = s_bank + (size_t)p.tile_rows * BL.ld;      // [16][D]   a_hat, later d a_hat
-  float* s_L = s_A + kGroupRows * D;                      // [16][ldl] logits, later dL/dlogit
+  const int lda = D + (kMma ? kMmaPadA : 0);
+  float* s_A = s_bank + (size_t)p.tile_rows * BL.ld;      // [16][lda] a_hat, later d a_hat
+  float* s_L = s_A + kGroupRows * lda;                    // [16][ldl] logits, later dL/dlogit
   __shared__ int s_cnt[kGroupRows], s_cls[kGroupRows];
   __shared__ float s_inv[kGroupRows];
   __shared__ int s_last;
@@ -578,7 +581,7 @@ loss_rows16_kernel(RowsParams p) {
       for (int j = 0; j < kDJ; ++j) {
         areg[rr][j] *= inv_norm;
         const int d = lane + 32 * j;
-        if (d < D) s_A[rl * D + d] = areg[rr][j];
+        if (d < D) s_A[rl * lda + d] = areg[rr][j];
       }
       if (lane == 0) {
         s_cnt[rl] = cnt2[rr]; s_cls[rl] = cls2[rr]; s_inv[rl] = inv_norm;
@@ -594,14 +597,18 @@ loss_rows16_kernel(RowsParams p) {
     for (int tile = 0; tile < p.n_tiles; ++tile) {
       const int r0 = tile * p.tile_rows, rows = min(p.tile_rows, Kc - r0);
       if (p.n_tiles > 1) { __syncthreads(); stage_bank_tile(s_bank, p.bank_n, r0, rows, BL); __syncthreads(); }
-      float acc[4][kColsPerThread];
-      tile_logits(s_A, s_bank, rows, BL, acc);
+      if (kMma) {
+        mma_tile_logits<kColsPerThread>(s_A, lda, s_bank, rows, BL, s_L, ldl, r0, p.temperature);
+      } else {
+        float acc[4][kColsPerThread];
+        tile_logits(s_A, s_bank, rows, BL, acc);
 #pragma unroll
-      for (int i = 0; i < kColsPerThread; ++i) {
-        const int c = cg + 64 * i;
-        if (c < rows) {
+        for (int i = 0; i < kColsPerThread; ++i) {
+          const int c = cg + 64 * i;
+          if (c < rows) {
 #pragma unroll
-          for (int r = 0; r < 4; ++r) s_L[(rg * 4 + r) * ldl + r0 + c] = acc[r][i] / p.temperature;
+            for (int r = 0; r < 4; ++r) s_L[(rg * 4 + r) * ldl + r0 + c] = acc[r][i] / p.temperature;
+          }
         }
       }
     }
@@ -695,7 +702,31 @@ loss_rows16_kernel(RowsParams p) {
     __syncthreads();
 
     DBG_STAMP(4);
-    if (kWithGrad) {
+    if (kWithGrad && kMma) {
+      // ---- P3 (tensor cores): d a_hat = G . bank; warp w owns the feature slices 8 (w + 8 j)
+      constexpr int kNTG = (kDJ + 1) / 2;
+      float accm[kNTG][4];
+#pragma unroll
+      for (int j = 0; j < kNTG; ++j) accm[j][0] = accm[j][1] = accm[j][2] = accm[j][3] = 0.f;
+      for (int tile = 0; tile < p.n_tiles; ++tile) {
+        const int r0 = tile * p.tile_rows, rows = min(p.tile_rows, Kc - r0);
+        if (p.n_tiles > 1) { __syncthreads(); stage_bank_tile(s_bank, p.bank_n, r0, rows, BL); __syncthreads(); }
+        mma_tile_gradT<kNTG>(s_L, ldl, r0, s_bank, rows, BL, accm);
+      }
+      {
+        const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+        for (int j = 0; j < kNTG; ++j) {
+          const int d0 = 8 * (warp + 8 * j) + 2 * t;
+          if (d0 < D) {
+            s_A[g * lda + d0] = accm[j][0]; s_A[g * lda + d0 + 1] = accm[j][1];
+            s_A[(g + 8) * lda + d0] = accm[j][2]; s_A[(g + 8) * lda + d0 + 1] = accm[j][3];
+          }
+        }
+      }
+      __syncthreads();
+    }
+    if (kWithGrad && !kMma) {
       // ---- P3: d a_hat = G . bank
       float4 acc4[kRP][kDch];
 #pragma unroll
@@ -757,6 +788,8 @@ loss_rows16_kernel(RowsParams p) {
         }
       }
       __syncthreads();
+    }
+    if (kWithGrad) {
       // ---- P4: normalize backward, weighted gradient row
 #pragma unroll
       for (int rr = 0; rr < 2; ++rr) {
@@ -766,7 +799,7 @@ loss_rows16_kernel(RowsParams p) {
 #pragma unroll
           for (int j = 0; j < kDJ; ++j) {
             const int d = lane + 32 * j;
-            if (d < D) dot += areg[rr][j] * s_A[rl * D + d];
+            if (d < D) dot += areg[rr][j] * s_A[rl * lda + d];
           }
           dot = warp_sum(dot);
           const float inv_norm = s_inv[rl];
@@ -775,7 +808,7 @@ loss_rows16_kernel(RowsParams p) {
 #pragma unroll
           for (int j = 0; j < kDJ; ++j) {
             const int d = lane + 32 * j;
-            if (d < D) p.grad_rows[(size_t)row * D + d] = (s_A[rl * D + d] - areg[rr][j] * sub) * w;
+            if (d < D) p.grad_rows[(size_t)row * D + d] = (s_A[rl * lda + d] - areg[rr][j] * sub) * w;
           }
         }
       }
@@ -806,12 +839,12 @@ loss_rows16_kernel(RowsParams p) {
   }
 }
 
-template <bool kWithGrad, int kKS, int kRP, int kDch, int kDJ>
+template <bool kWithGrad, int kKS, int kRP, int kDch, int kDJ, bool kMma = false>
 static int launch_rows16(const RowsParams& p, size_t smem, cudaStream_t stream) {
-  C3D_CUDA(cudaFuncSetAttribute(loss_rows16_kernel<kWithGrad, kKS, kRP, kDch, kDJ>,
+  C3D_CUDA(cudaFuncSetAttribute(loss_rows16_kernel<kWithGrad, kKS, kRP, kDch, kDJ, kMma>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   KernelTimer kt__("loss_rows_kernel", stream);
-  loss_rows16_kernel<kWithGrad, kKS, kRP, kDch, kDJ><<<kNumSMs, 256, smem, stream>>>(p);
+  loss_rows16_kernel<kWithGrad, kKS, kRP, kDch, kDJ, kMma><<<kNumSMs, 256, smem, stream>>>(p);
   return check_launch("loss_rows16_kernel");
 }
 
@@ -922,8 +955,9 @@ int c3d::proto_loss_forward_impl(
     int sub_protos, int ignore_label, float temperature, float base_temperature, int num_anchor,
     const int64_t* keep, int keep_rows, uint64_t seed, int need_grad, int phases, void* workspace,
     float* loss_out, float* zero_buf, int zero_n, void* stream_, const float* raw_rows, int raw_cap,
-    const float* bank_n_in, uint64_t* seed_dev) {
+    const float* bank_n_in, uint64_t* seed_dev, int rows_mode) {
   cudaStream_t stream = (cudaStream_t)stream_;
+  need_grad &= 1;   // bit 1 of the public argument selects rows_mode (passed separately here)
   const int B = batch, D = dim, C = n_classes, M = sub_protos;
   const long long HWll = (long long)proj_h * proj_w;
   C3D_REQUIRE(B > 0 && B <= kMaxBatch, "batch must be in [1, %d]", kMaxBatch);
@@ -978,6 +1012,20 @@ int c3d::proto_loss_forward_impl(
   p.HW = HW; p.D = D; p.M = M; p.Kc = Kc; p.A = num_anchor; p.tile_rows = tile_rows;
   p.n_tiles = n_tiles; p.temperature = temperature; p.base_temperature = base_temperature;
   RowsPlan plan;
+  // rows_mode 1: tensor cores (mma.sync 3xTF32) for the two products, D a multiple of 32
+  if (rows_mode == 1 && D % 32 == 0 && D <= 256 && plan_rows16(D, Kc, &plan, kMmaPadA) == 0) {
+    p.tile_rows = plan.tile_rows; p.n_tiles = plan.n_tiles; p.ldl = plan.ldl;
+    if (need_grad) {
+      if (D <= 32) return launch_rows16<true, 1, 4, 1, 1, true>(p, plan.smem, stream);
+      if (D <= 64) return launch_rows16<true, 1, 4, 1, 2, true>(p, plan.smem, stream);
+      if (D <= 128) return launch_rows16<true, 1, 4, 1, 4, true>(p, plan.smem, stream);
+      return launch_rows16<true, 1, 4, 1, 8, true>(p, plan.smem, stream);
+    }
+    if (D <= 32) return launch_rows16<false, 1, 4, 1, 1, true>(p, plan.smem, stream);
+    if (D <= 64) return launch_rows16<false, 1, 4, 1, 2, true>(p, plan.smem, stream);
+    if (D <= 128) return launch_rows16<false, 1, 4, 1, 4, true>(p, plan.smem, stream);
+    return launch_rows16<false, 1, 4, 1, 8, true>(p, plan.smem, stream);
+  }
   if (plan_rows16(D, Kc, &plan) == 0) {
     p.tile_rows = plan.tile_rows; p.n_tiles = plan.n_tiles; p.ldl = plan.ldl;
     // <grad, k-splits, rows per thread in P3, chunks per thread, D/32>; chunk-threads
@@ -1011,7 +1059,7 @@ extern "C" int c3d_proto_loss_forward(
                                  n_classes, sub_protos, ignore_label, temperature, base_temperature,
                                  num_anchor, keep, keep_rows, seed, need_grad,
                                  kPhaseSplit | kPhaseSample | kPhaseRows, workspace, loss_out, nullptr, 0,
-                                 stream, nullptr, 0, nullptr, nullptr);
+                                 stream, nullptr, 0, nullptr, nullptr, need_grad >> 1);
 }
 
 extern "C" int c3d_proto_loss_forward_phase(
@@ -1025,7 +1073,7 @@ extern "C" int c3d_proto_loss_forward_phase(
   return proto_loss_forward_impl(feats, probs, labels, keep_mask, proto_queue, batch, dim, proj_h, proj_w,
                                  n_classes, sub_protos, ignore_label, temperature, base_temperature,
                                  num_anchor, keep, keep_rows, seed, need_grad, internal, workspace, loss_out,
-                                 nullptr, 0, stream, nullptr, 0, nullptr, nullptr);
+                                 nullptr, 0, stream, nullptr, 0, nullptr, nullptr, need_grad >> 1);
 }
 
 extern "C" int c3d_proto_loss_backward(int batch, int dim, int proj_h, int proj_w, int n_classes,

@@ -56,7 +56,7 @@ extern "C" int c3d_proto_step(
     rc = proto_loss_forward_impl(nullptr, probs, labels, keep_mask, nullptr, batch, dim, proj_h, proj_w,
                                  n_classes, sub_protos, ignore_label, temperature, base_temperature,
                                  num_anchor, keep, keep_rows, seed, need_grad, loss_phases, workspace, nullptr,
-                                 nullptr, 0, stream, nullptr, 0, nullptr, seed_counters);
+                                 nullptr, 0, stream, nullptr, 0, nullptr, seed_counters, 0);
     if (rc) return rc;
   }
   if (phases & 4) {
@@ -72,7 +72,7 @@ extern "C" int c3d_proto_step(
                                  n_classes, sub_protos, ignore_label, temperature, base_temperature,
                                  num_anchor, nullptr, 0, seed, need_grad, kPhaseRows, workspace, loss_out,
                                  nullptr, 0, stream, raw_rows, (int)(max_rows > 0x7fffffff ? 0x7fffffff : max_rows), bank_n,
-                                 nullptr);
+                                 nullptr, need_grad >> 1);
     if (rc) return rc;
   }
   return C3D_OK;

@@ -162,10 +162,102 @@ __device__ __forceinline__ void tile_gradT(const float* s_G, int ldg, int k0, co
   }
 }
 
+// ---------------------------------------------------------------- tensor cores ----
+// The same two products on the tensor cores: mma.sync m16n8k8 TF32 with the 3xTF32 split
+// (x = hi + lo, both TF32; a.b ~= a_lo.b_hi + a_hi.b_lo + a_hi.b_hi, fp32 accumulate), which keeps
+// the products at fp32 accuracy (the dropped lo.lo term is ~2^-22 relative), as the loss's 1e-5
+// bar needs.  A 16-row group is exactly one M tile.  Operand fragments come straight from the
+// shared-memory tiles: the XOR-swizzled bank layout is conflict-free for the B fragments of the
+// logits product (8 rows x 4 consecutive floats) and 2-way for the gradient product; A rows are
+// padded to D + 4 floats (kMmaPadA) so that the 8 rows of a fragment hit 8 different bank groups.
+constexpr int kMmaPadA = 4;
+
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+  const float r = x - __uint_as_float(hi);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ void mma_3x(float (&c)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4],
+                                       const uint32_t (&bh)[2], const uint32_t (&bl)[2]) {
+  mma_tf32(c, al, bh);
+  mma_tf32(c, ah, bl);
+  mma_tf32(c, ah, bh);
+}
+
+// s_L[16][r0 .. r0 + rows) = (A[16][D] . bank_tile^T) * out_scale.  Warp w owns the 8-column tiles
+// w, w + 8, ...; kNT = tiles per warp (8 * 8 * kNT >= tile rows).
+template <int kNT>
+__device__ __forceinline__ void mma_tile_logits(const float* s_A, int lda, const float* s_bank, int rows,
+                                                const BankLayout& L, float* s_L, int ldl, int r0,
+                                                float temperature) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  float acc[kNT][4];
+  int brow[kNT];
+#pragma unroll
+  for (int j = 0; j < kNT; ++j) {
+    acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+    brow[j] = min(8 * (warp + 8 * j) + g, rows - 1);     // clamped: out-of-range columns are discarded
+  }
+  for (int k0 = 0; k0 < L.D; k0 += 8) {
+    uint32_t ah[4], al[4];
+    split_tf32(s_A[g * lda + k0 + t], ah[0], al[0]);
+    split_tf32(s_A[(g + 8) * lda + k0 + t], ah[1], al[1]);
+    split_tf32(s_A[g * lda + k0 + t + 4], ah[2], al[2]);
+    split_tf32(s_A[(g + 8) * lda + k0 + t + 4], ah[3], al[3]);
+    const int c0 = k0 >> 2;
+#pragma unroll
+    for (int j = 0; j < kNT; ++j) {
+      if (8 * (warp + 8 * j) >= rows) continue;          // warp-uniform
+      uint32_t bh[2], bl[2];
+      split_tf32(s_bank[L.off(brow[j], c0) + t], bh[0], bl[0]);
+      split_tf32(s_bank[L.off(brow[j], c0 + 1) + t], bh[1], bl[1]);
+      mma_3x(acc[j], ah, al, bh, bl);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < kNT; ++j) {
+    const int n0 = 8 * (warp + 8 * j) + 2 * t;
+    if (n0 < rows) { s_L[g * ldl + r0 + n0] = acc[j][0] / temperature; s_L[(g + 8) * ldl + r0 + n0] = acc[j][2] / temperature; }
+    if (n0 + 1 < rows) { s_L[g * ldl + r0 + n0 + 1] = acc[j][1] / temperature; s_L[(g + 8) * ldl + r0 + n0 + 1] = acc[j][3] / temperature; }
+  }
+}
+
+// acc (this warp's 8-wide slices of dA[16][D]) += G[16][r0 .. r0 + rows) . bank_tile.  Warp w owns the
+// feature slices d0 = 8 (w + 8 j), j < kNT.
+template <int kNT>
+__device__ __forceinline__ void mma_tile_gradT(const float* s_G, int ldg, int r0, const float* s_bank, int rows,
+                                               const BankLayout& L, float (&acc)[kNT][4]) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  for (int k0 = 0; k0 < rows; k0 += 8) {
+    const bool v0 = k0 + t < rows, v1 = k0 + t + 4 < rows;   // the last step of a tile may be partial
+    uint32_t ah[4], al[4];
+    split_tf32(v0 ? s_G[g * ldg + r0 + k0 + t] : 0.f, ah[0], al[0]);
+    split_tf32(v0 ? s_G[(g + 8) * ldg + r0 + k0 + t] : 0.f, ah[1], al[1]);
+    split_tf32(v1 ? s_G[g * ldg + r0 + k0 + t + 4] : 0.f, ah[2], al[2]);
+    split_tf32(v1 ? s_G[(g + 8) * ldg + r0 + k0 + t + 4] : 0.f, ah[3], al[3]);
+    const int ra = min(k0 + t, rows - 1), rb = min(k0 + t + 4, rows - 1);
+#pragma unroll
+    for (int j = 0; j < kNT; ++j) {
+      const int d0 = 8 * (warp + 8 * j);
+      if (d0 >= L.D) continue;                             // warp-uniform
+      const int d = d0 + g;
+      uint32_t bh[2], bl[2];
+      split_tf32(v0 ? s_bank[L.off(ra, d >> 2) + (d & 3)] : 0.f, bh[0], bl[0]);
+      split_tf32(v1 ? s_bank[L.off(rb, d >> 2) + (d & 3)] : 0.f, bh[1], bl[1]);
+      mma_3x(acc[j], ah, al, bh, bl);
+    }
+  }
+}
+
 // Shared-memory plan: [bank tile][A / dA : 16 x D][L : 16 x ldl]; returns -1 if even a
 // 64-row tile does not fit.
 struct RowsPlan { int tile_rows, n_tiles, ldl; size_t smem; };
-inline int plan_rows16(int D, int K, RowsPlan* out) {
+inline int plan_rows16(int D, int K, RowsPlan* out, int pad_a = 0) {
   const size_t budget = 227 * 1024 - 1024;  // 1 KB for the kernel's static shared memory
   const BankLayout L = BankLayout::make(D);
   const int ldl = (K + 3) & ~3;
@@ -174,7 +266,7 @@ inline int plan_rows16(int D, int K, RowsPlan* out) {
   const size_t part = (D <= 64) ? (size_t)3 * kGroupRows * D : (D <= 128 ? (size_t)kGroupRows * D : 0);
   size_t lfloats = (size_t)kGroupRows * ldl;
   if (lfloats < part) lfloats = part;
-  const size_t fixed = ((size_t)kGroupRows * D + lfloats) * 4;
+  const size_t fixed = ((size_t)kGroupRows * (D + pad_a) + lfloats) * 4;
   const size_t row = (size_t)L.ld * 4;
   if (fixed + 64 * row > budget) return -1;
   long long tr = (long long)((budget - fixed) / row);

@@ -193,12 +193,13 @@ def gaussian_kernel(kernel_size=3, sigma=2):
 
 
 def knn_batch(proj_range, proj_argmax, unproj_range, px, py, offsets, knn, search, sigma,
-              cutoff, nclasses, inv_gauss=None, out=None, cofill=None):
+              cutoff, nclasses, inv_gauss=None, out=None, cofill=None, out_uint8=False):
     """KNN.forward for a CSR batch (knn.py:54-142).
 
     proj_range (B,H,W) f32; px, py (sum N,) int64 (the reference's dtype) or
     int32 (project_batch's output); proj_argmax (B,H,W) int64 or int32; offsets
-    (B+1,) i32.  Returns (sum N,) labels with proj_argmax's dtype.
+    (B+1,) i32.  Returns (sum N,) labels with proj_argmax's dtype, or uint8 with out_uint8=True
+    (opt-in: class ids < 256, an eighth of the reference's int64 bytes on the way to the host).
     `cofill`: a contiguous CUDA tensor zeroed by the same kernel (TMA bulk stores from a
     shared-memory zero page while the vote keeps the ALU busy; the step pipeline passes the
     loss's dense gradient buffer).
@@ -223,7 +224,9 @@ def knn_batch(proj_range, proj_argmax, unproj_range, px, py, offsets, knn, searc
     if inv_gauss is None:
         inv_gauss = (1 - gaussian_kernel(search, sigma)).reshape(-1).to(proj_range.device)
     if out is None:
-        out = torch.empty((total,), dtype=ldt, device=proj_range.device)
+        out = torch.empty((total,), dtype=torch.uint8 if out_uint8 else ldt, device=proj_range.device)
+    elif out.dtype != (torch.uint8 if out_uint8 else ldt) or out.numel() != total:
+        raise ValueError("out must be (sum N,) %s" % (torch.uint8 if out_uint8 else ldt))
     nfill = 0
     if cofill is not None:
         _need_cuda(cofill=cofill)
@@ -233,7 +236,7 @@ def knn_batch(proj_range, proj_argmax, unproj_range, px, py, offsets, knn, searc
     check(lib.c3d_knn_batch(
         _p(proj_range), _p(proj_argmax), _p(unproj_range), _p(px), _p(py), _p(offsets), B, total,
         H, W, int(knn), int(search), float(cutoff), int(nclasses), _p(inv_gauss),
-        1 if idt == torch.int64 else 0, 1 if ldt == torch.int64 else 0, _p(out),
+        1 if idt == torch.int64 else 0, (1 if ldt == torch.int64 else 0) | (2 if out_uint8 else 0), _p(out),
         _p(cofill) if nfill else None, nfill, _stream()))
     return out
 
@@ -389,7 +392,7 @@ def proto_loss_rows(workspace, batch, dim, hw, n_classes, sub_protos, num_anchor
 
 
 def proto_loss_forward_raw(feats, probs, labels, keep_mask, queue, cfg, keep, seed, workspace, loss_out,
-                           need_grad=True, phases=3):
+                           need_grad=True, phases=3, tensor_cores=False):
     """c3d_proto_loss_forward on pre-validated device tensors (no autograd, no allocation).
     phases: 1 = selection only, 2 = rows only (after a phase 1), 3 = both."""
     B, D, H, W = feats.shape
@@ -398,7 +401,8 @@ def proto_loss_forward_raw(feats, probs, labels, keep_mask, queue, cfg, keep, se
         _p(feats), _p(probs), _p(labels), _p(keep_mask), _p(queue), B, D, H, W, C, M,
         int(cfg.ignore_label), float(cfg.temperature), float(cfg.base_temperature),
         int(cfg.num_anchor), _p(keep), 0 if keep is None else keep.shape[0], int(seed),
-        1 if need_grad else 0, int(phases), _p(workspace), _p(loss_out), _stream()))
+        (1 if need_grad else 0) | (2 if tensor_cores else 0), int(phases), _p(workspace), _p(loss_out),
+        _stream()))
     return loss_out
 
 
@@ -662,7 +666,7 @@ def proto_step_workspace(batch, n_classes, hw, dim, sub_protos, num_anchor, max_
 def proto_step_raw(phases, feats, probs, labels, keep_mask, prototypes, ln_d_w, ln_d_b, ln_c_w, ln_c_b,
                    cfg, workspace, packed, loss_out, max_rows, ln_eps=1e-5, keep=None,
                    gumbel=None, assign_mode=ASSIGN_GUMBEL_DEVICE, seed=0, need_grad=True, proto_target=None,
-                   bank_n=None, seed_counters=None):
+                   bank_n=None, seed_counters=None, tensor_cores=False):
     """c3d_proto_step on pre-validated device tensors (no autograd, no allocation): the phases of
     the fused EMA-update + loss step (STEP_* bit mask) on one shared label split."""
     B, D, H, W = feats.shape
@@ -671,7 +675,8 @@ def proto_step_raw(phases, feats, probs, labels, keep_mask, prototypes, ln_d_w, 
         _p(feats), _p(probs), _p(labels), _p(keep_mask), _p(prototypes), _p(ln_d_w), _p(ln_d_b), _p(ln_c_w),
         _p(ln_c_b), float(ln_eps), B, D, H, W, C, M, int(cfg.ignore_label), float(cfg.temperature),
         float(cfg.base_temperature), int(cfg.num_anchor), _p(keep), 0 if keep is None else keep.shape[0],
-        _p(gumbel), int(assign_mode), int(seed), int(max_rows), 1 if need_grad else 0, int(phases),
+        _p(gumbel), int(assign_mode), int(seed), int(max_rows),
+        (1 if need_grad else 0) | (2 if tensor_cores else 0), int(phases),
         _p(bank_n), _p(seed_counters), _p(workspace), _p(packed), _p(proto_target), _p(loss_out), _stream()))
 
 

@@ -38,12 +38,14 @@ class KNN(nn.Module):
             self._inv_gauss[key] = (1 - ops.gaussian_kernel(self.search, self.sigma)).reshape(-1).to(device)
         return self._inv_gauss[key]
 
-    def forward_batch(self, proj_range, unproj_range, proj_argmax, px, py, offsets):
+    def forward_batch(self, proj_range, unproj_range, proj_argmax, px, py, offsets, out_uint8=False):
+        """CSR batch of scans in one launch.  out_uint8=True returns uint8 class ids instead of
+        the reference's int64 (opt-in: an eighth of the bytes when the labels go to the host)."""
         if self.search % 2 == 0:
             raise ValueError("Nearest neighbor kernel must be odd number")
         return ops.knn_batch(proj_range, proj_argmax, unproj_range, px, py, offsets, self.knn,
                              self.search, self.sigma, self.cutoff, self.nclasses,
-                             inv_gauss=self._weights(proj_range.device))
+                             inv_gauss=self._weights(proj_range.device), out_uint8=out_uint8)
 
     def forward(self, proj_range, unproj_range, proj_argmax, px, py):
         ''' Un-batched, like the reference (knn.py:55-58). '''

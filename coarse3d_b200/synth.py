@@ -29,9 +29,11 @@ POSS = ScanShape("poss", 72_000, 40, 1800, 15.0, -25.0, 14, 1e-3)
 SHAPES = {s.name: s for s in (KITTI, NUSCENES, POSS)}
 
 
-def make_scan(shape: ScanShape, seed: int, n_points: int = None):
+def make_scan(shape: ScanShape, seed: int, n_points: int = None, sensor_order: bool = False):
     """One scan: points (N,4) f32 [x,y,z,intensity], full labels (N,) i64 in
-    [1, C-1], weak labels (N,) i64 (0 = unlabelled)."""
+    [1, C-1], weak labels (N,) i64 (0 = unlabelled).  Points come in random order (BASELINE's
+    synthetic spec); sensor_order=True sorts them by (beam, azimuth) the way a
+    spinning LiDAR emits them (what the .bin files of the real datasets hold)."""
     rng = np.random.default_rng(seed)
     n = shape.n_points if n_points is None else n_points
     beams = shape.proj_h
@@ -53,17 +55,20 @@ def make_scan(shape: ScanShape, seed: int, n_points: int = None):
     k = max(1, int(round(shape.label_ratio * n)))
     pick = rng.choice(n, k, replace=False)
     weak[pick] = full[pick]
+    if sensor_order:
+        order = np.lexsort((yaw, beam))
+        points, full, weak = points[order], full[order], weak[order]
     return points, full.astype(np.int64), weak
 
 
-def make_batch(shape: ScanShape, batch: int, seed0: int, ragged: bool = False):
+def make_batch(shape: ScanShape, batch: int, seed0: int, ragged: bool = False, sensor_order: bool = False):
     """CSR batch: points (sum N, 4) f32, offsets (B+1,) i32, full / weak labels."""
     pts, fulls, weaks, offs = [], [], [], [0]
     for i in range(batch):
         n = shape.n_points
         if ragged:
             n = int(n * (0.7 + 0.3 * ((seed0 + i) % 7) / 6.0))
-        p, f, w = make_scan(shape, seed0 + i, n)
+        p, f, w = make_scan(shape, seed0 + i, n, sensor_order)
         pts.append(p), fulls.append(f), weaks.append(w)
         offs.append(offs[-1] + n)
     return (np.concatenate(pts, 0), np.asarray(offs, dtype=np.int32),

@@ -134,9 +134,10 @@ int c3d_project_assemble_batch(
  * inv_gauss is (1 - get_gaussian_kernel(search, sigma)) flattened row-major
  * (knn.py:11-33,102-104), computed by the host with the reference's formula.
  * Tie rule: k smallest by (distance, window slot); vote argmax = first maximum.
- * pxy_is_i64 selects the dtype of px / py, label_is_i64 that of proj_argmax /
+ * pxy_is_i64 selects the dtype of px / py, label_is_i64 (bit 0) that of proj_argmax /
  * out_labels (int64 = the reference's dtypes, int32 = this library's
- * projection outputs).
+ * projection outputs).  label_is_i64 bit 1: out_labels is uint8 whatever proj_argmax is
+ * (class ids < 256: an eighth of the device->host bytes of the reference's int64).
  *
  * Co-scheduled fill: the vote is ALU bound and leaves HBM idle, so the caller may hand it
  * an unrelated zero fill -- in the hot-path step the dense gradient buffer of
@@ -270,7 +271,10 @@ int c3d_proto_loss_forward(
     int ignore_label, float temperature, float base_temperature, int num_anchor,
     const int64_t* keep,          /* [keep_rows, num_anchor] or NULL             */
     int keep_rows, uint64_t seed,
-    int need_grad,                /* 1: also evaluate the gradient rows (training) */
+    int need_grad,                /* bit 0: also evaluate the gradient rows (training);
+                                     bit 1: run the two row x bank products on the tensor
+                                     cores (mma.sync m16n8k8, 3xTF32 split: fp32-level
+                                     accuracy) instead of the FFMA form -- see DESIGN.md  */
     void* workspace,              /* c3d_proto_loss_workspace_bytes, 256 B aligned */
     float* loss_out,              /* [1]                                         */
     void* stream);

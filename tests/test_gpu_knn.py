@@ -154,3 +154,25 @@ def test_co_scheduled_fill_without_points(cuda_device):
     ops.knn_batch(z, z.long(), e, e.long(), e.long(), torch.zeros(2, dtype=torch.int32, device="cuda"),
                   5, 5, 1.0, 1.0, 5, cofill=buf)
     assert float(buf.abs().max()) == 0.0
+
+
+def test_uint8_output_option(cuda_device):
+    """label_is_i64 bit 1: uint8 labels out, whatever the dtype of proj_argmax; same values."""
+    from coarse3d_b200 import ops
+    rng = np.random.default_rng(5)
+    H, W, P, C = 16, 128, 3000, 20
+    proj_range = rng.uniform(1, 30, (2, H, W)).astype(np.float32)
+    proj_range[rng.random((2, H, W)) < 0.3] = -1.0
+    argmax = rng.integers(0, C, (2, H, W))
+    px, py = rng.integers(0, W, 2 * P), rng.integers(0, H, 2 * P)
+    ur = rng.uniform(1, 30, 2 * P).astype(np.float32)
+    offs = torch.tensor([0, P, 2 * P], dtype=torch.int32).cuda()
+    for adt in (torch.int64, torch.int32):
+        args = (torch.from_numpy(proj_range).cuda(), torch.from_numpy(argmax).to(adt).cuda(),
+                torch.from_numpy(ur).cuda(), torch.from_numpy(px).cuda(), torch.from_numpy(py).cuda(), offs,
+                5, 5, 1.0, 1.0, C)
+        want = ops.knn_batch(*args)
+        got = ops.knn_batch(*args, out_uint8=True)
+        assert got.dtype == torch.uint8 and torch.equal(got.long(), want.long())
+    with pytest.raises(ValueError):
+        ops.knn_batch(*args[:-1], 300, out_uint8=True)

@@ -210,3 +210,36 @@ def test_full_size_config2_properties(cuda_device):
     got.backward()
     assert abs(got.item() - want.item()) <= LOSS_RTOL * abs(want.item())
     assert _rel(f0.grad.cpu(), f_cpu.grad) <= GRAD_RTOL
+
+
+@pytest.mark.parametrize("B,D,H,W,C,M,A,frac", [
+    (2, 128, 16, 512, 20, 20, 512, 0.002),    # KITTI-like weak labels
+    (2, 128, 16, 256, 20, 20, 64, 0.3),       # dense labels: many distinct rows per segment
+    (1, 64, 8, 128, 7, 5, 32, 0.1),           # tile rows not a multiple of 8 (30 bank rows)
+    (1, 256, 8, 128, 20, 20, 64, 0.05),       # D = 256: two bank tiles
+    (2, 32, 8, 64, 5, 3, 16, 0.2),
+])
+def test_tensor_core_rows_match_oracle(cuda_device, B, D, H, W, C, M, A, frac):
+    """need_grad bit 1: the two row x bank products on the tensor cores (mma.sync m16n8k8,
+    3xTF32).  Same bars as the FFMA form: loss 1e-5 relative, gradients 1e-4 element-wise."""
+    from coarse3d_b200 import ops
+    feats, output, labels, keep_mask, queue = _random_problem(B, D, H, W, C, M, frac, 31)
+    cfg = ops.ProtoLossConfig(0, 0.07, 0.07, A)
+    f_cpu = feats.clone().requires_grad_(True)
+    want, keep, _ = oloss.contrast_mem_loss(f_cpu, output, labels, keep_mask, queue, temperature=0.07,
+                                            num_anchor=A, generator=torch.Generator().manual_seed(3))
+    want.backward()
+    ws = ops.proto_loss_workspace(B, C, H * W, D, M, A, "cuda")
+    dev = [t.cuda() for t in (feats, output, labels, keep_mask, queue[0])]
+    outs = []
+    for tc in (False, True):
+        loss = torch.zeros((), device="cuda")
+        ops.proto_loss_forward_raw(*dev, cfg, keep.cuda(), 0, ws, loss, tensor_cores=tc)
+        grad = torch.empty_like(dev[0])
+        ops.proto_loss_backward_raw(dev[0].shape, cfg, C, M, ws, torch.ones((), device="cuda"), grad)
+        assert abs(loss.item() - want.item()) <= LOSS_RTOL * abs(want.item()), tc
+        assert _rel(grad.cpu(), f_cpu.grad) <= GRAD_RTOL, tc
+        assert torch.equal(grad.cpu() != 0, f_cpu.grad != 0)
+        outs.append((loss.item(), grad))
+    # the two forms agree far inside the bar
+    assert abs(outs[0][0] - outs[1][0]) <= 2e-6 * abs(outs[0][0])

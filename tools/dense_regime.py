@@ -18,17 +18,20 @@ for frac in (1e-3, 0.05, 0.3):
     keep = torch.rand(B, H, W, device="cuda", generator=g) < frac
     ws = ops.proto_loss_workspace(B, C, H * W, D, M, A, "cuda")
     loss = torch.zeros((), device="cuda"); go = torch.ones((), device="cuda"); grad = torch.empty_like(feats)
-    def run():
-        ops.proto_loss_forward_raw(feats, probs, labels, keep, queue, cfg, None, 1, ws, loss)
-        ops.proto_loss_backward_raw(feats.shape, cfg, C, M, ws, go, grad)
-    for _ in range(3): run()
-    torch.cuda.synchronize()
-    with ops.profile("") as prof:
-        for _ in range(5): run()
+    for tc in (False, True):
+        def run():
+            ops.proto_loss_forward_raw(feats, probs, labels, keep, queue, cfg, None, 1, ws, loss, tensor_cores=tc)
+            ops.proto_loss_backward_raw(feats.shape, cfg, C, M, ws, go, grad)
+        for _ in range(3): run()
         torch.cuda.synchronize()
-        k = {n: round(1e3 * v[0] / v[1], 1) for n, v in prof.all().items()}
-    T, nlab, flags = ops.proto_loss_info(ws)
-    print("loss  frac=%g labelled=%d segments=%d flags=%d  us: %s" % (frac, nlab, T, flags, k))
+        with ops.profile("") as prof:
+            for _ in range(5): run()
+            torch.cuda.synchronize()
+            k = {n: round(1e3 * v[0] / v[1], 1) for n, v in prof.all().items()}
+        T, nlab, flags = ops.proto_loss_info(ws)
+        rows = int(ws[20:24].view(torch.int32).item())      # info[5]: distinct sampled rows
+        print("loss  frac=%g tensor_cores=%s labelled=%d segments=%d rows=%d flags=%d loss=%.7f  us: %s" % (
+            frac, tc, nlab, T, rows, flags, float(loss), k))
     lab_ema = (labels * keep).contiguous()
     mr = min(B * H * W, int(nlab * 1.1) + 1024)
     def run2():

@@ -42,11 +42,12 @@ def main():
     ap.add_argument("--ops", default="project,knn,assemble,unproject,select,lovasz")
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--sensor-order", action="store_true", help="points sorted by (beam, azimuth)")
     args = ap.parse_args()
     shp = synth.SHAPES[args.shape]
     ITERS[0], WARMUP[0] = args.iters, args.warmup
     B = args.batch
-    one, offs1, _, _ = synth.make_batch(shp, min(B, 8), seed0=1000)
+    one, offs1, _, _ = synth.make_batch(shp, min(B, 8), seed0=1000, sensor_order=args.sensor_order)
     reps = (B + 7) // 8
     pts = np.concatenate([one] * reps, 0)
     sizes = np.tile(np.diff(offs1), reps)[:B]
