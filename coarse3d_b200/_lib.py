@@ -40,8 +40,8 @@ def _load():
         "c3d_entropy_select_batch": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_float, P,
                                              c_uint64, P, P, P, P]),
         "c3d_lovasz_workspace_bytes": (c_size_t, [c_int, c_int64]),
-        "c3d_lovasz_forward": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int64, P, P, P]),
-        "c3d_lovasz_backward": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int64, P, P, P, c_int, P]),
+        "c3d_lovasz_forward": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_uint64, c_int64, P, P, P]),
+        "c3d_lovasz_backward": (c_int, [c_int, c_int, c_int, c_int, c_int, c_uint64, c_int64, P, P, P, c_int, P]),
         "c3d_lovasz_info": (c_int, [P, P, P]),
         "c3d_knn_batch": (c_int, [P, P, P, P, P, P, c_int, c_int64, c_int, c_int, c_int, c_int,
                                   c_float, c_int, P, c_int, c_int, P, P, c_size_t, P]),

@@ -33,6 +33,11 @@ constexpr long long kLovMaxValid = 32768;
 constexpr int kLovSortMax = 16384;        // keys of one class that fit shared memory (128 KB)
 enum LovInfo { kLovP = 0, kLovPresent = 1, kLovFlags = 2 };
 enum LovFlag { kLovOverflow = 1, kLovEmpty = 2 };
+// classes = 'present' (mode 0: classes with a foreground pixel), 'all' (1), or a list (2: the
+// classes of `mask`, absent ones included -- lovasz_softmax.py:117-122)
+__device__ __forceinline__ bool lov_included(int mode, unsigned long long mask, int hist_c, int c) {
+  return mode == 1 || (mode == 0 && hist_c > 0) || (mode == 2 && ((mask >> c) & 1ull));
+}
 
 struct LovWs {
   int32_t* info;      // [4] P, n_present, flags
@@ -123,7 +128,7 @@ __device__ __forceinline__ float lovasz_grad_at(float gts, int r, int F, int fg)
 // ---------------------------------------------------------------- L2 -------
 // One CTA (1024 threads) per class.  n = next power of two >= P keys in dynamic shared memory.
 __global__ void __launch_bounds__(1024)
-lovasz_sort_kernel(const float* __restrict__ probs, int HW, int C, int cap, int classes_all,
+lovasz_sort_kernel(const float* __restrict__ probs, int HW, int C, int cap, int classes_all, unsigned long long cls_mask,
                    const int32_t* __restrict__ pix, const int32_t* __restrict__ lab,
                    const int32_t* __restrict__ hist, const int32_t* __restrict__ info,
                    float* __restrict__ gval, int32_t* __restrict__ gpix,
@@ -135,7 +140,7 @@ lovasz_sort_kernel(const float* __restrict__ probs, int HW, int C, int cap, int 
   const int P = min(info[kLovP], cap);
   if (P > kLovSortMax) return;                                     // fallback path runs instead
   if (threadIdx.x == 0) cls_loss[c] = 0.0f;
-  if ((!classes_all && hist[c] == 0) || P == 0) return;           // :121-122
+  if (!lov_included(classes_all, cls_mask, hist[c], c) || P == 0) return;   // :121-122
   int n = 1;
   while (n < P) n <<= 1;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -199,7 +204,7 @@ lovasz_sort_kernel(const float* __restrict__ probs, int HW, int C, int cap, int 
 }
 
 // ---------------------------------------------------------------- L3 -------
-__global__ void lovasz_finalize_kernel(int C, int cap, int classes_all, const int32_t* __restrict__ hist,
+__global__ void lovasz_finalize_kernel(int C, int cap, int classes_all, unsigned long long cls_mask, const int32_t* __restrict__ hist,
                                        int32_t* __restrict__ info, const float* __restrict__ cls_loss,
                                        float* __restrict__ loss_out) {
   if (threadIdx.x != 0) return;
@@ -207,7 +212,7 @@ __global__ void lovasz_finalize_kernel(int C, int cap, int classes_all, const in
   int n = 0;
   float acc = 0.0f;
   for (int c = 0; c < C; ++c) {
-    if (P == 0 || (!classes_all && hist[c] == 0)) continue;
+    if (P == 0 || !lov_included(classes_all, cls_mask, hist[c], c)) continue;
     acc += cls_loss[c];                                            // mean(): acc = acc + v (:44-45)
     ++n;
   }
@@ -222,14 +227,14 @@ __global__ void lovasz_finalize_kernel(int C, int cap, int classes_all, const in
 
 // ------------------------------------------------------ fallback: keys ----
 __global__ void __launch_bounds__(256)
-lovasz_keys_kernel(const float* __restrict__ probs, int HW, int C, int cap, int classes_all,
+lovasz_keys_kernel(const float* __restrict__ probs, int HW, int C, int cap, int classes_all, unsigned long long cls_mask,
                    const int32_t* __restrict__ pix, const int32_t* __restrict__ lab,
                    const int32_t* __restrict__ hist, const int32_t* __restrict__ info,
                    unsigned long long* __restrict__ keys) {
   const int c = blockIdx.y;
   const int P = min(info[kLovP], cap);
   if (P <= kLovSortMax) return;                                   // the sort path handled it
-  if (!classes_all && hist[c] == 0) return;                       // lovasz_softmax.py:121-122
+  if (!lov_included(classes_all, cls_mask, hist[c], c)) return;   // lovasz_softmax.py:121-122
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= P) return;
   const int g = pix[i];
@@ -240,14 +245,14 @@ lovasz_keys_kernel(const float* __restrict__ probs, int HW, int C, int cap, int 
 // ------------------------------------------------------ fallback: rank ----
 constexpr int kLovTile = 1024;
 __global__ void __launch_bounds__(256)
-lovasz_rank_kernel(int C, int cap, int classes_all, const int32_t* __restrict__ hist,
+lovasz_rank_kernel(int C, int cap, int classes_all, unsigned long long cls_mask, const int32_t* __restrict__ hist,
                    const int32_t* __restrict__ info, const unsigned long long* __restrict__ keys,
                    float* __restrict__ term, float* __restrict__ gval, int32_t* __restrict__ gpix) {
   __shared__ unsigned long long s_key[kLovTile];
   const int c = blockIdx.y;
   const int P = min(info[kLovP], cap);
   if (P <= kLovSortMax) return;
-  if (!classes_all && hist[c] == 0) return;
+  if (!lov_included(classes_all, cls_mask, hist[c], c)) return;
   if (blockIdx.x * blockDim.x >= P) return;
   const unsigned long long* kc = keys + (size_t)c * cap;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -277,7 +282,7 @@ lovasz_rank_kernel(int C, int cap, int classes_all, const int32_t* __restrict__ 
 
 // ---------------------------------------------------- fallback: reduce ----
 __global__ void __launch_bounds__(1024)
-lovasz_reduce_kernel(int C, int cap, int classes_all, const int32_t* __restrict__ hist,
+lovasz_reduce_kernel(int C, int cap, int classes_all, unsigned long long cls_mask, const int32_t* __restrict__ hist,
                      const int32_t* __restrict__ info, const float* __restrict__ term,
                      float* __restrict__ cls_loss) {
   __shared__ float s_part[32];
@@ -286,7 +291,7 @@ lovasz_reduce_kernel(int C, int cap, int classes_all, const int32_t* __restrict_
   if (P <= kLovSortMax) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float v = 0.0f;
-  if (classes_all || hist[c] > 0)
+  if (lov_included(classes_all, cls_mask, hist[c], c))
     for (int r = threadIdx.x; r < P; r += blockDim.x) v += term[(size_t)c * cap + r];
   v = warp_sum(v);
   if (lane == 0) s_part[warp] = v;
@@ -300,13 +305,13 @@ lovasz_reduce_kernel(int C, int cap, int classes_all, const int32_t* __restrict_
 
 // ------------------------------------------------------------- backward ----
 __global__ void __launch_bounds__(256)
-lovasz_scatter_kernel(int HW, int C, int cap, int classes_all, const int32_t* __restrict__ hist,
+lovasz_scatter_kernel(int HW, int C, int cap, int classes_all, unsigned long long cls_mask, const int32_t* __restrict__ hist,
                       const int32_t* __restrict__ info, const float* __restrict__ gval,
                       const int32_t* __restrict__ gpix, const float* __restrict__ grad_out,
                       float* __restrict__ grad_probs) {
   const int c = blockIdx.y;
   const int P = min(info[kLovP], cap);
-  if (!classes_all && hist[c] == 0) return;
+  if (!lov_included(classes_all, cls_mask, hist[c], c)) return;
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= P) return;
   const int n_present = info[kLovPresent];
@@ -326,10 +331,12 @@ extern "C" size_t c3d_lovasz_workspace_bytes(int n_classes, int64_t max_valid) {
 }
 
 extern "C" int c3d_lovasz_forward(const float* probs, const int64_t* labels, int batch, int n_classes,
-                                  int proj_h, int proj_w, int ignore, int classes_all,
+                                  int proj_h, int proj_w, int ignore, int classes_all, uint64_t class_mask,
                                   int64_t max_valid, void* workspace, float* loss_out,
                                   void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
+  const unsigned long long cls_mask = class_mask;
+  C3D_REQUIRE(classes_all >= 0 && classes_all <= 2, "classes: 0 present, 1 all, 2 the classes of class_mask");
   const long long HWll = (long long)proj_h * proj_w;
   C3D_REQUIRE(batch > 0 && batch <= kMaxBatch, "batch must be in [1, %d]", kMaxBatch);
   C3D_REQUIRE(n_classes >= 1 && n_classes <= kLovMaxClasses, "n_classes must be in [1, %d]", kLovMaxClasses);
@@ -361,7 +368,7 @@ extern "C" int c3d_lovasz_forward(const float* probs, const int64_t* labels, int
     C3D_CUDA(cudaFuncSetAttribute(lovasz_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   kLovSortMax * (int)sizeof(unsigned long long)));
     KernelTimer kt__("lovasz_sort_kernel", stream);
-    lovasz_sort_kernel<<<C, 1024, smem, stream>>>(probs, HW, C, cap, classes_all, w.pix, w.lab, w.hist,
+    lovasz_sort_kernel<<<C, 1024, smem, stream>>>(probs, HW, C, cap, classes_all, cls_mask, w.pix, w.lab, w.hist,
                                                   w.info, w.gval, w.gpix, w.cls_loss);
   }
   if ((rc = check_launch("lovasz_sort_kernel"))) return rc;
@@ -369,33 +376,34 @@ extern "C" int c3d_lovasz_forward(const float* probs, const int64_t* labels, int
     const dim3 grid((cap + 255) / 256, C);
     {
       KernelTimer kt__("lovasz_keys_kernel", stream);
-      lovasz_keys_kernel<<<grid, 256, 0, stream>>>(probs, HW, C, cap, classes_all, w.pix, w.lab, w.hist,
+      lovasz_keys_kernel<<<grid, 256, 0, stream>>>(probs, HW, C, cap, classes_all, cls_mask, w.pix, w.lab, w.hist,
                                                    w.info, w.keys);
     }
     if ((rc = check_launch("lovasz_keys_kernel"))) return rc;
     {
       KernelTimer kt__("lovasz_rank_kernel", stream);
-      lovasz_rank_kernel<<<grid, 256, 0, stream>>>(C, cap, classes_all, w.hist, w.info, w.keys, w.term,
+      lovasz_rank_kernel<<<grid, 256, 0, stream>>>(C, cap, classes_all, cls_mask, w.hist, w.info, w.keys, w.term,
                                                    w.gval, w.gpix);
     }
     if ((rc = check_launch("lovasz_rank_kernel"))) return rc;
     {
       KernelTimer kt__("lovasz_reduce_kernel", stream);
-      lovasz_reduce_kernel<<<C, 1024, 0, stream>>>(C, cap, classes_all, w.hist, w.info, w.term, w.cls_loss);
+      lovasz_reduce_kernel<<<C, 1024, 0, stream>>>(C, cap, classes_all, cls_mask, w.hist, w.info, w.term, w.cls_loss);
     }
     if ((rc = check_launch("lovasz_reduce_kernel"))) return rc;
   }
   {
     KernelTimer kt__("lovasz_finalize_kernel", stream);
-    lovasz_finalize_kernel<<<1, 32, 0, stream>>>(C, cap, classes_all, w.hist, w.info, w.cls_loss, loss_out);
+    lovasz_finalize_kernel<<<1, 32, 0, stream>>>(C, cap, classes_all, cls_mask, w.hist, w.info, w.cls_loss, loss_out);
   }
   return check_launch("lovasz_finalize_kernel");
 }
 
 extern "C" int c3d_lovasz_backward(int batch, int n_classes, int proj_h, int proj_w, int classes_all,
-                                   int64_t max_valid, void* workspace, const float* grad_out,
+                                   uint64_t class_mask, int64_t max_valid, void* workspace, const float* grad_out,
                                    float* grad_probs, int grad_is_zeroed, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
+  const unsigned long long cls_mask = class_mask;
   const long long HWll = (long long)proj_h * proj_w;
   C3D_REQUIRE(batch > 0 && batch <= kMaxBatch && n_classes >= 1 && n_classes <= kLovMaxClasses,
               "bad batch / n_classes");
@@ -409,7 +417,7 @@ extern "C" int c3d_lovasz_backward(int batch, int n_classes, int proj_h, int pro
   if (!grad_is_zeroed && (rc = launch_fill(grad_probs, (size_t)batch * C * HW * 4, stream))) return rc;
   const dim3 grid((cap + 255) / 256, C);
   KernelTimer kt__("lovasz_scatter_kernel", stream);
-  lovasz_scatter_kernel<<<grid, 256, 0, stream>>>(HW, C, cap, classes_all, w.hist, w.info, w.gval, w.gpix,
+  lovasz_scatter_kernel<<<grid, 256, 0, stream>>>(HW, C, cap, classes_all, cls_mask, w.hist, w.info, w.gval, w.gpix,
                                                   grad_out, grad_probs);
   return check_launch("lovasz_scatter_kernel");
 }

@@ -314,43 +314,53 @@ def lovasz_info(workspace):
 
 class _LovaszFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, probs, labels, ignore, classes_all, max_valid, workspace):
+    def forward(ctx, probs, labels, ignore, classes_all, class_mask, max_valid, workspace):
         B, C, H, W = probs.shape
         loss = torch.empty((), dtype=torch.float32, device=probs.device)
         check(lib.c3d_lovasz_forward(_p(probs), _p(labels), B, C, H, W, int(ignore), int(classes_all),
-                                     int(max_valid), _p(workspace), _p(loss), _stream()))
-        ctx.args = (B, C, H, W, int(classes_all), int(max_valid), workspace)
+                                     int(class_mask), int(max_valid), _p(workspace), _p(loss), _stream()))
+        ctx.args = (B, C, H, W, int(classes_all), int(class_mask), int(max_valid), workspace)
         return loss
 
     @staticmethod
     def backward(ctx, grad_out):
-        B, C, H, W, classes_all, max_valid, workspace = ctx.args
+        B, C, H, W, classes_all, class_mask, max_valid, workspace = ctx.args
         grad = torch.empty((B, C, H, W), dtype=torch.float32, device=grad_out.device)
-        check(lib.c3d_lovasz_backward(B, C, H, W, classes_all, max_valid, _p(workspace),
+        check(lib.c3d_lovasz_backward(B, C, H, W, classes_all, class_mask, max_valid, _p(workspace),
                                       _p(grad_out.contiguous().float()), _p(grad), 0, _stream()))
-        return grad, None, None, None, None, None
+        return grad, None, None, None, None, None, None
 
 
 def lovasz_softmax(probs, labels, ignore=None, classes="present", max_valid=LOVASZ_MAX_VALID,
                    workspace=None):
     """lovasz_softmax(per_image=False) of lovasz_softmax.py:67-98 on (B,C,H,W) probabilities and
-    (B,H,W) int64 labels; returns (0-dim loss with autograd to `probs`, workspace).
+    (B,H,W) int64 labels; `classes`: 'present', 'all' or a list of class ids (:117).  Returns
+    (0-dim loss with autograd to `probs`, workspace).
     More than `max_valid` (<= 32768) valid pixels is an error reported by `lovasz_info`."""
     _need_cuda(probs=probs, labels=labels)
     if probs.dtype != torch.float32 or probs.dim() != 4:
         raise ValueError("probas must be (B, C, H, W) float32")
     if labels.dtype != torch.int64 or labels.shape != (probs.shape[0],) + probs.shape[2:]:
         raise ValueError("labels must be (B, H, W) int64")
-    if classes not in ("present", "all"):
-        raise ValueError("classes must be 'present' or 'all'")
     C = probs.shape[1]
+    class_mask = 0
+    if isinstance(classes, (list, tuple)):          # an explicit class list (lovasz_softmax.py:117)
+        for c in classes:
+            if not 0 <= int(c) < C:
+                raise ValueError("class %r outside [0, %d)" % (c, C))
+            class_mask |= 1 << int(c)
+        mode = 2
+    elif classes in ("present", "all"):
+        mode = 1 if classes == "all" else 0
+    else:
+        raise ValueError("classes must be 'present', 'all' or a list of class ids")
     if workspace is None:
         n = lib.c3d_lovasz_workspace_bytes(C, int(max_valid))
         if n == 0:
             raise ValueError("Lovasz: max_valid must be in [1, %d] and n_classes <= 64" % LOVASZ_MAX_VALID)
         workspace = torch.empty((n,), dtype=torch.uint8, device=probs.device)
     loss = _LovaszFn.apply(probs.contiguous(), labels.contiguous(), -1 if ignore is None else int(ignore),
-                           1 if classes == "all" else 0, int(max_valid), workspace)
+                           mode, class_mask, int(max_valid), workspace)
     return loss, workspace
 
 

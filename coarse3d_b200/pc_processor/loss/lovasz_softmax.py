@@ -13,7 +13,7 @@ Differences a caller can observe:
     host read);
   * with no valid pixel the reference returns an empty tensor (and the trainer skips such
     batches, trainer.py:586-589); here the loss is 0 with zero gradient;
-  * `classes` may be "present" (default) or "all", not a list.
+  * labels >= C are ignored pixels here (the reference counts them as background of every class).
 """
 import torch
 import torch.nn as nn

@@ -205,7 +205,7 @@ int c3d_entropy_select_batch(
  * Lovasz-softmax loss, pc_processor/loss/lovasz_softmax.py:51-157 (lovasz_grad,
  * lovasz_softmax_flat, flatten_probas), as the trainer calls it
  * (tasks/weak_segmentation/trainer.py:362-364,650): class probabilities, weak labels,
- * `ignore`, classes = "present" (classes_all = 0) or "all" (1), per_image = False.
+ * `ignore`, classes = "present" (classes_all = 0), "all" (1) or a list (2), per_image = False.
  * Forward keeps per-element gradient entries in the workspace; backward zero-fills the
  * dense (B,C,H,W) gradient (unless grad_is_zeroed) and scatters P x C entries scaled by
  * grad_out.  The rank pass is quadratic in the number of valid pixels P, so max_valid is
@@ -218,14 +218,17 @@ size_t c3d_lovasz_workspace_bytes(int n_classes, int64_t max_valid);
 int c3d_lovasz_forward(
     const float* probs,           /* [B, C, H, W] class probabilities            */
     const int64_t* labels,        /* [B, H, W]                                   */
-    int batch, int n_classes, int proj_h, int proj_w, int ignore, int classes_all,
+    int batch, int n_classes, int proj_h, int proj_w, int ignore,
+    int classes_all,              /* 0: classes = 'present', 1: 'all', 2: the list in class_mask */
+    uint64_t class_mask,          /* bit c set: class c is in the list (:117-122)        */
     int64_t max_valid,
     void* workspace,              /* c3d_lovasz_workspace_bytes, 256 B aligned   */
     float* loss_out,              /* [1]                                         */
     void* stream);
 
 int c3d_lovasz_backward(
-    int batch, int n_classes, int proj_h, int proj_w, int classes_all, int64_t max_valid,
+    int batch, int n_classes, int proj_h, int proj_w, int classes_all, uint64_t class_mask,
+    int64_t max_valid,
     void* workspace,              /* as left by c3d_lovasz_forward               */
     const float* grad_out,        /* [1] upstream gradient                       */
     float* grad_probs,            /* [B, C, H, W], 16 B aligned                  */

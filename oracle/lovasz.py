@@ -32,7 +32,8 @@ def lovasz_softmax(probas, labels, ignore=None, classes="present"):
     if pred.numel() == 0:
         return probas.sum() * 0.0
     losses = []
-    for c in range(C):                                             # :117-133
+    class_to_sum = list(range(C)) if classes in ("all", "present") else list(classes)   # :117
+    for c in class_to_sum:                                         # :119-133
         fg = (lab == c).float()
         if classes == "present" and fg.sum() == 0:
             continue

@@ -141,3 +141,22 @@ def test_full_size_is_deterministic(cuda_device):
     for l, g in outs[1:]:
         assert torch.equal(l, outs[0][0]) and torch.equal(g, outs[0][1])
     assert int((outs[0][1] != 0).sum()) > 0
+
+
+def test_class_list_form(cuda_device):
+    """classes = [ids] (lovasz_softmax.py:117-122): the listed classes are averaged, absent ones
+    included (unlike 'present'); checked against the oracle."""
+    from coarse3d_b200 import ops
+    from oracle import lovasz as olov
+    probs, labels = _make(2, 6, 8, 64, 0.3, 4)
+    labels[labels == 5] = 1                       # class 5 is absent but listed
+    for classes in ([1, 3, 5], [2], list(range(6))):
+        p_ref = probs.clone().requires_grad_(True)
+        want = olov.lovasz_softmax(p_ref, labels, classes=classes, ignore=0)
+        want.backward()
+        p = probs.cuda().requires_grad_(True)
+        loss, _ = ops.lovasz_softmax(p, labels.cuda(), ignore=0, classes=classes)
+        loss.backward()
+        _check(loss.detach().cpu(), p.grad.cpu(), want.detach(), p_ref.grad)
+    with pytest.raises(ValueError):
+        ops.lovasz_softmax(probs.cuda(), labels.cuda(), ignore=0, classes=[7])
