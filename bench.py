@@ -421,7 +421,8 @@ def main():
     if "fill_daemon_kernel" in per_kernel:
         dom, dom_bytes = "fill_daemon_kernel", alg["loss_grad_fill"]
     elif "knn_vote_fill_kernel" in per_kernel:
-        dom, dom_bytes = "knn_vote_fill_kernel", alg["loss_grad_fill"] + alg["knn"]
+        # the vote writes the share of the zero fill the schedule leaves with it
+        dom, dom_bytes = "knn_vote_fill_kernel", step.fill_bytes_by_carrier()["knn_vote"] + alg["knn"]
     else:
         dom, dom_bytes = "fill_zero_kernel", alg["loss_grad_fill"]
     dom_us = per_kernel.get(dom, {}).get("us")
@@ -456,6 +457,7 @@ def main():
         "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": workload_config(args, world, synth),
         "run": {"cuda_graph": bool(graphed), "concurrent_chains": not args.serial, "schedule": step.schedule,
+                "fill_bytes_by_carrier": step.fill_bytes_by_carrier(), "vote_after_loss_rows": step.knn_after_rows,
                 "blocks": len(block_ms), "block_ms_min_median_max": [min(block_ms), ms_total, max(block_ms)],
                 "timed_region_s": t_region1 - t_region0, "banks_identical_across_ranks": banks_identical,
                 "kernels_per_step": eager_launches_per_step},

@@ -30,10 +30,10 @@ def _load():
         "c3d_launch_count": (c_longlong, []),
         "c3d_project_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
         "c3d_project_batch": (c_int, [P, c_int, P, c_int, c_int64, P, c_double, c_double, c_double,
-                                      c_double, c_int, c_int, P, P, P, P, P, P, P, P, c_int, P, P]),
+                                      c_double, c_int, c_int, P, P, P, P, P, P, P, P, c_int, P, P, c_size_t, P]),
         "c3d_project_assemble_batch": (c_int, [P, P, c_int, c_int64, P, P, P, c_int, P, P, c_double, c_double,
                                                c_double, c_double, c_int, c_int, P, P, P, P, P, P, P, P,
-                                               P, c_int, P, P]),
+                                               P, c_int, P, P, c_size_t, P]),
         "c3d_unproject_confusion_batch": (c_int, [P, P, P, P, P, c_int, c_int64, c_int, c_int, c_int, c_int,
                                                   c_int, c_int, P, P, P, P]),
         "c3d_entropy_select_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
@@ -76,7 +76,7 @@ def _load():
         "c3d_proto_step_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int, c_int64]),
         "c3d_proto_step": (c_int, [P, P, P, P, P, P, P, P, P, c_float, c_int, c_int, c_int, c_int, c_int, c_int,
                                    c_int, c_float, c_float, c_int, P, c_int, P, c_int, c_uint64, c_int64, c_int,
-                                   c_int, P, P, P, P, P, P, P]),
+                                   c_int, P, P, P, P, P, P, P, c_size_t, P]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported

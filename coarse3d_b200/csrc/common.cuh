@@ -95,6 +95,75 @@ __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
 }
 
+// ------------------------------------------------------------------ carried fill ----
+// The dense-gradient zero fill of the loss backward (84 % of a step's bytes, pure HBM writes)
+// has no dependence on anything but "done before the gradient rows are scattered", while every
+// other kernel of the step is latency-, ALU- or L1-bound and leaves HBM mostly idle.  Any kernel
+// can therefore CARRY a share of the fill: each CTA keeps a small zero page in shared memory and
+// ONE thread issues cp.async.bulk shared->global copies of it (UBLKCP: no LSU wavefronts, a few
+// issue slots) over the CTA's slice of the share, in instalments between its own phases.
+struct FillShare {
+  char* ptr;                    // this launch's byte range of the buffer to zero (16 B aligned), or null
+  unsigned long long bytes;     // multiple of 16
+};
+
+__device__ __forceinline__ void bulk_store_evict_first(void* gdst, const void* ssrc, unsigned bytes) {
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(pol));
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;\n"
+               :: "l"(gdst), "r"((unsigned)__cvta_generic_to_shared(ssrc)), "r"(bytes), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_all() {
+  asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+}
+
+// All threads of the CTA: zero the page and make it visible to the copy engine.  The caller's
+// next __syncthreads() (before the first carrier_issue) completes the hand-over.
+__device__ __forceinline__ void carrier_init(void* s_page, int page_bytes) {
+  for (int i = threadIdx.x; i < page_bytes / 16; i += blockDim.x)
+    reinterpret_cast<float4*>(s_page)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+}
+
+// One thread: the pages j = part, part + nparts, ... of CTA `cta`'s slice (of `nctas` equal,
+// page-aligned slices of the share).
+__device__ __forceinline__ void carrier_issue(const FillShare& f, const void* s_page, unsigned page_bytes,
+                                              unsigned cta, unsigned nctas, int part, int nparts) {
+  if (f.ptr == nullptr || f.bytes == 0) return;
+  const unsigned long long pages = (f.bytes + page_bytes - 1) / page_bytes;
+  const unsigned long long per = (pages + nctas - 1) / nctas;
+  const unsigned long long lo = (unsigned long long)cta * per;
+  const unsigned long long hi = lo + per < pages ? lo + per : pages;
+  bool any = false;
+  for (unsigned long long j = lo + part; j < hi; j += nparts) {
+    const unsigned long long off = j * page_bytes;
+    const unsigned long long left = f.bytes - off;
+    bulk_store_evict_first(f.ptr + off, s_page, left < page_bytes ? (unsigned)left : page_bytes);
+    any = true;
+  }
+  if (any) bulk_commit();
+}
+
+// A carrier WARP: the rows kernels (one 256-thread CTA per SM, phases separated by barriers) give
+// the fill a ninth warp of its own instead of thread 0 -- a thread that issues hundreds of bulk
+// copies blocks whenever the copy queue is full, and the whole CTA would wait for it at the next
+// barrier.  The compute warps synchronise among themselves on named barrier 1 (rows_sync).
+constexpr int kRowsThreads = 256;
+__device__ __forceinline__ void rows_sync() { asm volatile("bar.sync 1, 256;\n" ::: "memory"); }
+__device__ __forceinline__ void carrier_warp_run(const FillShare& f, void* s_page, int page_bytes,
+                                                 unsigned cta, unsigned nctas) {
+  const int lane = threadIdx.x & 31;
+  for (int i = lane; i < page_bytes / 16; i += 32)
+    reinterpret_cast<float4*>(s_page)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+  __syncwarp();
+  if (lane == 0) {
+    carrier_issue(f, s_page, page_bytes, cta, nctas, 0, 1);
+    bulk_wait_read_all();
+  }
+}
+
 // Streaming 128-bit store (data written once, never re-read by this kernel).
 __device__ __forceinline__ void st_stream(float4* p, float4 v) { __stcs(p, v); }
 

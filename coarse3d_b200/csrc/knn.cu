@@ -43,18 +43,6 @@ __device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, unsigne
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n"
                :: "l"(gdst), "r"((unsigned)__cvta_generic_to_shared(ssrc)), "r"(bytes) : "memory");
 }
-// Same copy with an L2 evict-first policy: the zero lines should not displace the range /
-// class images the vote gathers from.
-__device__ __forceinline__ void bulk_store_evict_first(void* gdst, const void* ssrc, unsigned bytes) {
-  unsigned long long pol;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(pol));
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;\n"
-               :: "l"(gdst), "r"((unsigned)__cvta_generic_to_shared(ssrc)), "r"(bytes), "l"(pol) : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read_all() {
-  asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
-}
 
 // KT >= knn is the compile-time capacity of the top-k network (KT == knn for knn <= 8).
 template <int S, int KT, int kFill>

@@ -71,15 +71,23 @@ __device__ __forceinline__ int masked_class(const long long* __restrict__ labels
 // Count + stage + scan in one launch.  A CTA handles `tpc` consecutive tiles of ONE scan (tpc
 // divides the tiles per scan): the per-tile work is a handful of instructions when nothing is
 // labelled, and the expensive part -- fence, ticket, barriers -- is paid once per CTA.
+constexpr int kSplitZeroPage = 8192;
+template <bool kFill>
 static __global__ void __launch_bounds__(256)
 split_count_kernel(const long long* __restrict__ labels, const uint8_t* __restrict__ keep, int HW,
                    int nbps, int tpc, int B, int C, int ignore_label, SplitWs w,
-                   float* __restrict__ zero_buf, int zero_n) {
+                   float* __restrict__ zero_buf, int zero_n, FillShare fill) {
   __shared__ int s_cnt[kTileRounds][8][kMaxClasses];  // [round][warp][class] -> exclusive prefix
   __shared__ int s_cpre[kMaxClasses + 1];             // exclusive prefix over classes (tile)
   __shared__ int s_flag;
+  __shared__ __align__(128) float4 s_zero[kFill ? kSplitZeroPage / 16 : 1];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const unsigned lt = (1u << lane) - 1;
+  if (kFill) {   // this CTA's slice of the carried fill (common.cuh), issued while the labels stream in
+    carrier_init(s_zero, kSplitZeroPage);
+    __syncthreads();
+    if (threadIdx.x == 0) carrier_issue(fill, s_zero, kSplitZeroPage, blockIdx.x, gridDim.x, 0, 1);
+  }
   // a small caller buffer zeroed on the side (the packed prototype sums of the fused step)
   for (int i = blockIdx.x * 256 + threadIdx.x; i < zero_n; i += gridDim.x * 256) zero_buf[i] = 0.f;
   const int cps = nbps / tpc;                         // CTA work items per scan
@@ -253,6 +261,7 @@ split_count_kernel(const long long* __restrict__ labels, const uint8_t* __restri
       }
     }
   }  // work-item loop
+  if (kFill && threadIdx.x == 0) bulk_wait_read_all();
 }
 
 // Staged pixels -> sorted slots (+ entropy weight, contrast_pixel_loss.py:46-49).  One WARP per
@@ -317,15 +326,19 @@ split_place_kernel(const float* __restrict__ probs, int HW, int nbps, int nblk, 
 // Launches both kernels on `stream` (info must have been zeroed).  Returns a c3d status.
 inline int launch_split(const long long* labels, const uint8_t* keep, const float* probs, int B, int C,
                         int HW, int ignore_label, const SplitWs& w, float* w_list, int32_t* cnt_list,
-                        float* zero_buf, int zero_n, cudaStream_t stream) {
+                        float* zero_buf, int zero_n, cudaStream_t stream, FillShare fill = FillShare{nullptr, 0}) {
   const int nbps = split_tiles_per_scan(HW), nblk = B * nbps;
   // tiles per count CTA: enough CTAs for ~4 per SM, a power of two that divides the tiles per scan
   int tpc = 1;
   while (tpc < 8 && nbps % (tpc * 2) == 0 && nblk / (tpc * 2) >= kNumSMs * 4) tpc *= 2;
   int rc;
   { KernelTimer kt__("split_count_kernel", stream);
-    split_count_kernel<<<split_grid(nblk / tpc), 256, 0, stream>>>(labels, keep, HW, nbps, tpc, B, C,
-                                                                   ignore_label, w, zero_buf, zero_n); }
+    if (fill.bytes)
+      split_count_kernel<true><<<split_grid(nblk / tpc), 256, 0, stream>>>(labels, keep, HW, nbps, tpc, B, C,
+                                                                           ignore_label, w, zero_buf, zero_n, fill);
+    else
+      split_count_kernel<false><<<split_grid(nblk / tpc), 256, 0, stream>>>(labels, keep, HW, nbps, tpc, B, C,
+                                                                            ignore_label, w, zero_buf, zero_n, fill); }
   if ((rc = check_launch("split_count_kernel"))) return rc;
   const int place_ctas = (nblk + 7) / 8;
   { KernelTimer kt__("split_place_kernel", stream);

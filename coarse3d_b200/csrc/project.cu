@@ -87,23 +87,31 @@ __device__ __forceinline__ void red_min_u64_hint(unsigned long long* addr, unsig
   asm volatile("red.global.min.L2::cache_hint.u64 [%0], %1, %2;\n" :: "l"(addr), "l"(v), "l"(pol) : "memory");
 }
 
-template <bool kHybrid, bool kC4>
+constexpr int kProjZeroPage = 8192;   // zero page of the carried fill (common.cuh)
+
+// kFill: the CTAs also carry a share of an unrelated zero fill (the loss's dense gradient).
+template <bool kHybrid, bool kC4, bool kFill>
 __global__ void __launch_bounds__(256)
 project_points_kernel(const float* __restrict__ points, int c_in,
                       const int32_t* __restrict__ offsets, int batch, int total,
                       const float* __restrict__ depth_override, ProjParams p,
                       int32_t* __restrict__ upx, int32_t* __restrict__ upy,
                       float* __restrict__ udepth, unsigned long long* __restrict__ zbuf,
-                      int32_t* __restrict__ flags) {
+                      int32_t* __restrict__ flags, FillShare fill) {
   extern __shared__ int32_t s_off[];
   __shared__ int s_b0;
+  __shared__ __align__(128) float4 s_zero[kFill ? kProjZeroPage / 16 : 1];
   for (int i = threadIdx.x; i <= batch; i += blockDim.x) s_off[i] = offsets[i];
+  if (kFill) carrier_init(s_zero, kProjZeroPage);
   __syncthreads();
-  if (threadIdx.x == 0) s_b0 = scan_of(s_off, batch, min((int)(blockIdx.x * blockDim.x), total - 1));
+  if (threadIdx.x == 0) {
+    s_b0 = scan_of(s_off, batch, min((int)(blockIdx.x * blockDim.x), total - 1));
+    if (kFill) carrier_issue(fill, s_zero, kProjZeroPage, blockIdx.x, gridDim.x, 0, 1);
+  }
   __syncthreads();
   const int HW = p.H * p.W;
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= total) return;
+  if (g >= total) { if (kFill && threadIdx.x == 0) bulk_wait_read_all(); return; }
   int b = s_b0;
   while (g >= s_off[b + 1]) ++b;  // a CTA spans at most a few scans
   float x, y, z;
@@ -123,18 +131,25 @@ project_points_kernel(const float* __restrict__ points, int c_in,
       ((unsigned long long)depth_key(depth) << 32) | (uint32_t)(g - s_off[b]);
   red_min_u64_hint(zbuf + (size_t)b * HW + py * p.W + px, key, policy_evict_last());
   if (nan) atomicOr(flags, 1);
+  if (kFill && threadIdx.x == 0) bulk_wait_read_all();   // the zero page must outlive the copies reading it
 }
 
 // Two pixels per thread (two independent key -> gather -> store chains in flight).
 // Every z-buffer entry is reset to "empty" after it is read, so the workspace is
 // left clean for the next call and needs no memset.
-template <bool kC4>
+template <bool kC4, bool kFill>
 __global__ void __launch_bounds__(256)
 resolve_pixels_kernel(const float* __restrict__ points, int c_in,
                       const int32_t* __restrict__ offsets, int HW, long long total_px,
                       unsigned long long* __restrict__ zbuf,
                       float* __restrict__ proj_range, float* __restrict__ proj_pc,
-                      int32_t* __restrict__ proj_idx, int32_t* __restrict__ proj_mask) {
+                      int32_t* __restrict__ proj_idx, int32_t* __restrict__ proj_mask, FillShare fill) {
+  __shared__ __align__(128) float4 s_zero[kFill ? kProjZeroPage / 16 : 1];
+  if (kFill) {
+    carrier_init(s_zero, kProjZeroPage);
+    __syncthreads();
+    if (threadIdx.x == 0) carrier_issue(fill, s_zero, kProjZeroPage, blockIdx.x, gridDim.x, 0, 1);
+  }
   const long long q0 = ((long long)blockIdx.x * blockDim.x) * 2 + threadIdx.x;
   unsigned long long key[2];
   bool in[2];
@@ -173,6 +188,7 @@ resolve_pixels_kernel(const float* __restrict__ points, int c_in,
     }
     if (valid) zbuf[q] = ~0ull;
   }
+  if (kFill && threadIdx.x == 0) bulk_wait_read_all();
 }
 
 // ---------------------------------------------------------------- f1 -------
@@ -180,6 +196,7 @@ resolve_pixels_kernel(const float* __restrict__ points, int c_in,
 // network input are written straight from the z-buffer winners
 // (wss_sem_kitti_loader.py:124-132,159-172; trainer.py:600-608), so neither the
 // (H,W,4) projected point cloud nor a CPU-side gather is needed.
+template <bool kFill>
 __global__ void __launch_bounds__(256)
 resolve_assemble_kernel(const float* __restrict__ points, const int32_t* __restrict__ offsets,
                         int HW, long long total_px, unsigned long long* __restrict__ zbuf,
@@ -188,7 +205,13 @@ resolve_assemble_kernel(const float* __restrict__ points, const int32_t* __restr
                         const float* __restrict__ mean, const float* __restrict__ stdv,
                         float* __restrict__ proj_range, int32_t* __restrict__ proj_idx,
                         float* __restrict__ feature, long long* __restrict__ train_label,
-                        long long* __restrict__ eval_label) {
+                        long long* __restrict__ eval_label, FillShare fill) {
+  __shared__ __align__(128) float4 s_zero[kFill ? kProjZeroPage / 16 : 1];
+  if (kFill) {
+    carrier_init(s_zero, kProjZeroPage);
+    __syncthreads();
+    if (threadIdx.x == 0) carrier_issue(fill, s_zero, kProjZeroPage, blockIdx.x, gridDim.x, 0, 1);
+  }
   const long long q0 = ((long long)blockIdx.x * blockDim.x) * 2 + threadIdx.x;
   unsigned long long key[2]; bool in[2];
 #pragma unroll
@@ -240,6 +263,7 @@ resolve_assemble_kernel(const float* __restrict__ points, const int32_t* __restr
     for (int c = 0; c < 5; ++c) dst[(size_t)c * HW] = f[c];
     if (valid) zbuf[q] = ~0ull;
   }
+  if (kFill && threadIdx.x == 0) bulk_wait_read_all();
 }
 
 
@@ -474,10 +498,12 @@ extern "C" int c3d_project_batch(
     double fov_vert, int proj_h, int proj_w, float* proj_range, float* proj_pointcloud,
     int32_t* proj_idx, int32_t* proj_mask, int32_t* uproj_x_idx, int32_t* uproj_y_idx,
     float* uproj_depth, void* workspace, int workspace_flags, int32_t* status_flags,
-    void* stream_) {
+    void* cofill_ptr, size_t cofill_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   C3D_REQUIRE(batch > 0 && batch <= kMaxBatch, "batch must be in [1, %d], got %d", kMaxBatch, batch);
   C3D_REQUIRE(c_in >= 3, "c_in must be >= 3, got %d", c_in);
+  C3D_REQUIRE((cofill_ptr == nullptr) == (cofill_bytes == 0) && cofill_bytes % 16 == 0 &&
+              (reinterpret_cast<uintptr_t>(cofill_ptr) & 15) == 0, "carried fill: 16 B aligned pointer and size");
   C3D_REQUIRE(proj_h > 0 && proj_w > 0, "bad image size %dx%d", proj_h, proj_w);
   C3D_REQUIRE(total_points >= 0 && total_points < (1ll << 31), "total_points out of range");
   C3D_REQUIRE((long long)batch * proj_h * proj_w < (1ll << 31), "batch*H*W must be < 2^31");
@@ -512,6 +538,18 @@ extern "C" int c3d_project_batch(
     const size_t nb = fused ? fused_ring_bytes(batch, proj_h * proj_w) : (size_t)total_px * sizeof(unsigned long long);
     C3D_CUDA(cudaMemsetAsync(zbuf, 0xFF, nb, stream));
   }
+  // the carried fill is split between the two passes; forms that cannot carry it fill up front
+  FillShare f1{nullptr, 0}, f2{nullptr, 0};
+  if (cofill_bytes) {
+    if (fused || !c4 || total_points == 0) {
+      int rc = launch_fill(cofill_ptr, cofill_bytes, stream);
+      if (rc) return rc;
+    } else {
+      const unsigned long long half = (cofill_bytes / 2) & ~(unsigned long long)(kProjZeroPage - 1);
+      f1 = FillShare{reinterpret_cast<char*>(cofill_ptr), half};
+      f2 = FillShare{reinterpret_cast<char*>(cofill_ptr) + half, cofill_bytes - half};
+    }
+  }
   if (fused)
     return launch_fused<false>(points, offsets, batch, total_points, depth_override, p, hybrid, uproj_x_idx,
                                uproj_y_idx, uproj_depth, workspace, status_flags, proj_range, proj_pointcloud,
@@ -521,14 +559,15 @@ extern "C" int c3d_project_batch(
   if (total_points > 0) {
     int grid = (int)((total_points + threads - 1) / threads);  // short CTAs (overlap)
     size_t smem = (size_t)(batch + 1) * sizeof(int32_t);
-#define LAUNCH_PP(HY, C4)                                                                   \
-  project_points_kernel<HY, C4><<<grid, threads, smem, stream>>>(                           \
+#define LAUNCH_PP(HY, C4, FL)                                                               \
+  project_points_kernel<HY, C4, FL><<<grid, threads, smem, stream>>>(                       \
       points, c_in, offsets, batch, (int)total_points, depth_override, p, uproj_x_idx,      \
-      uproj_y_idx, uproj_depth, zbuf, status_flags)
+      uproj_y_idx, uproj_depth, zbuf, status_flags, f1)
     {
       KernelTimer kt__("project_points_kernel", stream);
-      if (hybrid) { if (c4) LAUNCH_PP(true, true); else LAUNCH_PP(true, false); }
-      else        { if (c4) LAUNCH_PP(false, true); else LAUNCH_PP(false, false); }
+      if (f1.bytes) { if (hybrid) LAUNCH_PP(true, true, true); else LAUNCH_PP(false, true, true); }
+      else if (hybrid) { if (c4) LAUNCH_PP(true, true, false); else LAUNCH_PP(true, false, false); }
+      else             { if (c4) LAUNCH_PP(false, true, false); else LAUNCH_PP(false, false, false); }
     }
 #undef LAUNCH_PP
     int rc = check_launch("project_points_kernel");
@@ -537,14 +576,18 @@ extern "C" int c3d_project_batch(
   {
     int grid = (int)((total_px + 2 * threads - 1) / (2 * threads));
     KernelTimer kt__("resolve_pixels_kernel", stream);
-    if (c4)
-      resolve_pixels_kernel<true><<<grid, threads, 0, stream>>>(
+    if (f2.bytes)
+      resolve_pixels_kernel<true, true><<<grid, threads, 0, stream>>>(
           points, c_in, offsets, proj_h * proj_w, total_px, zbuf, proj_range, proj_pointcloud,
-          proj_idx, proj_mask);
+          proj_idx, proj_mask, f2);
+    else if (c4)
+      resolve_pixels_kernel<true, false><<<grid, threads, 0, stream>>>(
+          points, c_in, offsets, proj_h * proj_w, total_px, zbuf, proj_range, proj_pointcloud,
+          proj_idx, proj_mask, f2);
     else
-      resolve_pixels_kernel<false><<<grid, threads, 0, stream>>>(
+      resolve_pixels_kernel<false, false><<<grid, threads, 0, stream>>>(
           points, c_in, offsets, proj_h * proj_w, total_px, zbuf, proj_range, proj_pointcloud,
-          proj_idx, proj_mask);
+          proj_idx, proj_mask, f2);
     int rc = check_launch("resolve_pixels_kernel");
     if (rc) return rc;
   }
@@ -558,9 +601,11 @@ extern "C" int c3d_project_assemble_batch(
     double abs_fov_down, double fov_vert, int proj_h, int proj_w, float* feature,
     int64_t* train_label, int64_t* eval_label, float* proj_range, int32_t* proj_idx,
     int32_t* uproj_x_idx, int32_t* uproj_y_idx, float* uproj_depth, void* workspace,
-    int workspace_flags, int32_t* status_flags, void* stream_) {
+    int workspace_flags, int32_t* status_flags, void* cofill_ptr, size_t cofill_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   C3D_REQUIRE(batch > 0 && batch <= kMaxBatch, "batch must be in [1, %d], got %d", kMaxBatch, batch);
+  C3D_REQUIRE((cofill_ptr == nullptr) == (cofill_bytes == 0) && cofill_bytes % 16 == 0 &&
+              (reinterpret_cast<uintptr_t>(cofill_ptr) & 15) == 0, "carried fill: 16 B aligned pointer and size");
   C3D_REQUIRE(proj_h > 0 && proj_w > 0, "bad image size %dx%d", proj_h, proj_w);
   C3D_REQUIRE(total_points >= 0 && total_points < (1ll << 31), "total_points out of range");
   C3D_REQUIRE((long long)batch * proj_h * proj_w < (1ll << 31), "batch*H*W must be < 2^31");
@@ -593,6 +638,17 @@ extern "C" int c3d_project_assemble_batch(
     const size_t nb = fused ? fused_ring_bytes(batch, proj_h * proj_w) : (size_t)total_px * sizeof(unsigned long long);
     C3D_CUDA(cudaMemsetAsync(zbuf, 0xFF, nb, stream));
   }
+  FillShare f1{nullptr, 0}, f2{nullptr, 0};
+  if (cofill_bytes) {
+    if (fused || total_points == 0) {
+      int rc = launch_fill(cofill_ptr, cofill_bytes, stream);
+      if (rc) return rc;
+    } else {
+      const unsigned long long half = (cofill_bytes / 2) & ~(unsigned long long)(kProjZeroPage - 1);
+      f1 = FillShare{reinterpret_cast<char*>(cofill_ptr), half};
+      f2 = FillShare{reinterpret_cast<char*>(cofill_ptr) + half, cofill_bytes - half};
+    }
+  }
   if (fused)
     return launch_fused<true>(points, offsets, batch, total_points, depth_override, p, hybrid, uproj_x_idx,
                               uproj_y_idx, uproj_depth, workspace, status_flags, proj_range, nullptr, proj_idx,
@@ -603,23 +659,27 @@ extern "C" int c3d_project_assemble_batch(
     int grid = (int)((total_points + threads - 1) / threads);
     size_t smem = (size_t)(batch + 1) * sizeof(int32_t);
     KernelTimer kt__("project_points_kernel", stream);
-    if (hybrid)
-      project_points_kernel<true, true><<<grid, threads, smem, stream>>>(
-          points, 4, offsets, batch, (int)total_points, depth_override, p, uproj_x_idx, uproj_y_idx,
-          uproj_depth, zbuf, status_flags);
-    else
-      project_points_kernel<false, true><<<grid, threads, smem, stream>>>(
-          points, 4, offsets, batch, (int)total_points, depth_override, p, uproj_x_idx, uproj_y_idx,
-          uproj_depth, zbuf, status_flags);
+#define LAUNCH_PA(HY, FL)                                                                              \
+  project_points_kernel<HY, true, FL><<<grid, threads, smem, stream>>>(                                \
+      points, 4, offsets, batch, (int)total_points, depth_override, p, uproj_x_idx, uproj_y_idx,       \
+      uproj_depth, zbuf, status_flags, f1)
+    if (f1.bytes) { if (hybrid) LAUNCH_PA(true, true); else LAUNCH_PA(false, true); }
+    else          { if (hybrid) LAUNCH_PA(true, false); else LAUNCH_PA(false, false); }
+#undef LAUNCH_PA
     int rc = check_launch("project_points_kernel");
     if (rc) return rc;
   }
   {
     int grid = (int)((total_px + 2 * threads - 1) / (2 * threads));
     KernelTimer kt__("resolve_assemble_kernel", stream);
-    resolve_assemble_kernel<<<grid, threads, 0, stream>>>(
-        points, offsets, proj_h * proj_w, total_px, zbuf, sem_label, weak_label, label_is_u8, img_mean, img_std,
-        proj_range, proj_idx, feature, (long long*)train_label, (long long*)eval_label);
+    if (f2.bytes)
+      resolve_assemble_kernel<true><<<grid, threads, 0, stream>>>(
+          points, offsets, proj_h * proj_w, total_px, zbuf, sem_label, weak_label, label_is_u8, img_mean, img_std,
+          proj_range, proj_idx, feature, (long long*)train_label, (long long*)eval_label, f2);
+    else
+      resolve_assemble_kernel<false><<<grid, threads, 0, stream>>>(
+          points, offsets, proj_h * proj_w, total_px, zbuf, sem_label, weak_label, label_is_u8, img_mean, img_std,
+          proj_range, proj_idx, feature, (long long*)train_label, (long long*)eval_label, f2);
     return check_launch("resolve_assemble_kernel");
   }
 }

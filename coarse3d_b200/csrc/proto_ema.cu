@@ -212,11 +212,12 @@ constexpr int kEmaGroups = 4;
 constexpr int kEmaCPT = 4;            // tile_logits columns per thread -> tiles of <= 256 bank rows
 constexpr int kNvPad = kMaxClasses;   // per-row stride of the class-maximum scratch
 
+constexpr int kEmaZeroPage = 8192;
 struct EmaTiledPlan { int tile_classes, n_tiles, ldl; size_t smem; };
 static int plan_ema_tiled(int D, int C, int M, EmaTiledPlan* out) {
   const size_t budget = 227 * 1024 - 2048;
   const BankLayout L = BankLayout::make(D);
-  const size_t fixed = (size_t)kEmaGroups * kGroupRows * ((size_t)D + kNvPad + kMaxSub) * 4;
+  const size_t fixed = (size_t)kEmaGroups * kGroupRows * ((size_t)D + kNvPad + kMaxSub) * 4 + kEmaZeroPage;
   for (int n_tiles = 1; n_tiles <= C; ++n_tiles) {
     const int tc = (C + n_tiles - 1) / n_tiles;          // classes per tile
     const int rows = tc * M;
@@ -229,8 +230,8 @@ static int plan_ema_tiled(int D, int C, int M, EmaTiledPlan* out) {
 }
 
 template <int kDJ>
-__global__ void __launch_bounds__(256, 1)
-ema_rows_tiled_kernel(EmaRowsParams p, int tile_classes, int ldl, float* __restrict__ raw_rows) {
+__global__ void __launch_bounds__(kRowsThreads + 32, 1)
+ema_rows_tiled_kernel(EmaRowsParams p, int tile_classes, int ldl, float* __restrict__ raw_rows, FillShare fill) {
   extern __shared__ __align__(16) float smem[];
   const int D = p.D, M = p.M, C = p.C;
   const BankLayout BL = BankLayout::make(D);
@@ -240,7 +241,13 @@ ema_rows_tiled_kernel(EmaRowsParams p, int tile_classes, int ldl, float* __restr
   float* s_L = s_A + (size_t)kEmaGroups * kGroupRows * D;      // [16][ldl]
   float* s_nv = s_L + (size_t)kGroupRows * ldl;                // [G*16][kNvPad] max over M per class
   float* s_own = s_nv + (size_t)kEmaGroups * kGroupRows * kNvPad;   // [G*16][kMaxSub]
+  float* s_zero = s_own + (size_t)kEmaGroups * kGroupRows * kMaxSub; // zero page of the carried fill
   __shared__ int s_cls[kEmaGroups * kGroupRows];
+  // carried fill: a ninth warp (launched only with a share) sends this CTA's slice on its own
+  if (threadIdx.x >= kRowsThreads) {
+    carrier_warp_run(fill, s_zero, kEmaZeroPage, blockIdx.x, gridDim.x);
+    return;
+  }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_rows = p.info[kInfoPl];
   if (n_rows > p.max_rows) {
@@ -318,9 +325,9 @@ ema_rows_tiled_kernel(EmaRowsParams p, int tile_classes, int ldl, float* __restr
     // ---- tiles of the bank x groups of the batch
     for (int tile = 0; tile < n_tiles; ++tile) {
       const int c0 = tile * tile_classes, tc = min(tile_classes, C - c0), rows = tc * M;
-      if (tile > 0) { __syncthreads(); stage_bank_tile_issue(s_bank, p.bank_n, c0 * M, rows, BL); }
+      if (tile > 0) { rows_sync(); stage_bank_tile_issue(s_bank, p.bank_n, c0 * M, rows, BL); }
       cp_async_wait_all();
-      __syncthreads();
+      rows_sync();
       for (int g = 0; g < G; ++g) {
         float acc[4][kEmaCPT];
         tile_logits<kEmaCPT>(s_A + (size_t)g * kGroupRows * D, s_bank, rows, BL, acc);
@@ -333,7 +340,7 @@ ema_rows_tiled_kernel(EmaRowsParams p, int tile_classes, int ldl, float* __restr
             for (int r = 0; r < 4; ++r) s_L[(rg * 4 + r) * ldl + c] = acc[r][i];
           }
         }
-        __syncthreads();
+        rows_sync();
         // (row, class of the tile): maximum over the M sub-prototypes (:506)
         for (int q = threadIdx.x; q < kGroupRows * tc; q += 256) {
           const int r = q / tc, cc = q - r * tc;
@@ -348,7 +355,7 @@ ema_rows_tiled_kernel(EmaRowsParams p, int tile_classes, int ldl, float* __restr
           const int cls = s_cls[g * kGroupRows + r];
           if (cls >= c0 && cls < c0 + tc) s_own[(size_t)(g * kGroupRows + r) * kMaxSub + j] = s_L[r * ldl + (cls - c0) * M + j];
         }
-        __syncthreads();
+        rows_sync();
       }
     }
     // ---- per row: LayerNorm over C (:507), argmax (:340), mask (:341)
@@ -386,16 +393,18 @@ ema_rows_tiled_kernel(EmaRowsParams p, int tile_classes, int ldl, float* __restr
       if (lane == 0) p.maskv[slot] = (best_c == cls);
       if (lane < M) p.simq[(size_t)slot * M + lane] = s_own[(size_t)rl * kMaxSub + lane];
     }
-    __syncthreads();   // the batch's scratch is reused
+    rows_sync();   // the batch's scratch is reused
   }
 }
 
 template <int kDJ>
-static int launch_ema_tiled(const EmaRowsParams& p, const EmaTiledPlan& plan, float* raw_rows, cudaStream_t stream) {
+static int launch_ema_tiled(const EmaRowsParams& p, const EmaTiledPlan& plan, float* raw_rows, FillShare fill,
+                            cudaStream_t stream) {
   C3D_CUDA(cudaFuncSetAttribute(ema_rows_tiled_kernel<kDJ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)plan.smem));
   KernelTimer kt__("ema_rows_kernel", stream);
-  ema_rows_tiled_kernel<kDJ><<<kNumSMs, 256, plan.smem, stream>>>(p, plan.tile_classes, plan.ldl, raw_rows);
+  ema_rows_tiled_kernel<kDJ><<<kNumSMs, kRowsThreads + (fill.bytes ? 32 : 0), plan.smem, stream>>>(
+      p, plan.tile_classes, plan.ldl, raw_rows, fill);
   return check_launch("ema_rows_tiled_kernel");
 }
 
@@ -722,7 +731,7 @@ int c3d::proto_ema_accumulate_impl(
     int batch, int dim, int proj_h, int proj_w, int n_classes, int sub_protos, int ignore_label,
     int64_t max_rows, const float* gumbel, int assign_mode, uint64_t seed, void* workspace,
     const SplitWs* shared_split, float* packed, float* proto_target, void* stream_, float* raw_rows,
-    int rows_v1, const float* bank_n_in, const uint64_t* seed_dev) {
+    int rows_v1, const float* bank_n_in, const uint64_t* seed_dev, FillShare fill) {
   cudaStream_t stream = (cudaStream_t)stream_;
   const int B = batch, D = dim, C = n_classes, M = sub_protos;
   const long long HWll = (long long)proj_h * proj_w;
@@ -766,6 +775,7 @@ int c3d::proto_ema_accumulate_impl(
   }
 
   if (dense) {
+    if (fill.bytes && (rc = launch_fill(fill.ptr, fill.bytes, stream))) return rc;
     KernelTimer kt__("ema_rows_dense_kernel", stream);
     ema_rows_dense_kernel<<<kNumSMs * 2, 256, 0, stream>>>(dense->out_feat, dense->nearest, dense->sim,
                                                            w.s.pix_list, w.s.cls_list, w.s.info, w.feat, w.simq,
@@ -780,13 +790,14 @@ int c3d::proto_ema_accumulate_impl(
     p.max_rows = (int)max_rows; p.eps = ln_eps;
     EmaTiledPlan plan;
     if (!rows_v1 && D % 32 == 0 && D <= 256 && plan_ema_tiled(D, C, M, &plan) == 0) {
-      if (D <= 32) rc = launch_ema_tiled<1>(p, plan, raw_rows, stream);
-      else if (D <= 64) rc = launch_ema_tiled<2>(p, plan, raw_rows, stream);
-      else if (D <= 128) rc = launch_ema_tiled<4>(p, plan, raw_rows, stream);
-      else rc = launch_ema_tiled<8>(p, plan, raw_rows, stream);
+      if (D <= 32) rc = launch_ema_tiled<1>(p, plan, raw_rows, fill, stream);
+      else if (D <= 64) rc = launch_ema_tiled<2>(p, plan, raw_rows, fill, stream);
+      else if (D <= 128) rc = launch_ema_tiled<4>(p, plan, raw_rows, fill, stream);
+      else rc = launch_ema_tiled<8>(p, plan, raw_rows, fill, stream);
       if (rc) return rc;
     } else {
       C3D_REQUIRE(raw_rows == nullptr, "raw rows need the tiled EMA rows kernel (D %% 32 == 0, D <= 256)");
+      if (fill.bytes && (rc = launch_fill(fill.ptr, fill.bytes, stream))) return rc;   // this form does not carry
       C3D_CUDA(cudaFuncSetAttribute(ema_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)smem));
       { KernelTimer kt__("ema_rows_kernel", stream); ema_rows_kernel<<<kNumSMs, kEmaWarps * 32, smem, stream>>>(p); }
@@ -813,7 +824,7 @@ extern "C" int c3d_proto_ema_accumulate(
   return proto_ema_accumulate_impl(embedding, nullptr, label, prototypes, ln_d_w, ln_d_b, ln_c_w, ln_c_b,
                                    ln_eps, batch, dim, proj_h, proj_w, n_classes, sub_protos,
                                    ignore_label, max_rows, gumbel, assign_mode, seed, workspace, nullptr,
-                                   packed, proto_target, stream, nullptr, 0, nullptr, nullptr);
+                                   packed, proto_target, stream, nullptr, 0, nullptr, nullptr, FillShare{nullptr, 0});
 }
 
 extern "C" int c3d_proto_ema_accumulate_dense(
@@ -825,7 +836,7 @@ extern "C" int c3d_proto_ema_accumulate_dense(
   return proto_ema_accumulate_impl(nullptr, &d, label, nullptr, nullptr, nullptr, nullptr, nullptr, 0.f,
                                    batch, dim, proj_h, proj_w, n_classes, sub_protos, ignore_label,
                                    max_rows, gumbel, assign_mode, seed, workspace, nullptr, packed,
-                                   proto_target, stream, nullptr, 0, nullptr, nullptr);
+                                   proto_target, stream, nullptr, 0, nullptr, nullptr, FillShare{nullptr, 0});
 }
 
 extern "C" int c3d_proto_ema_apply(const float* prototypes_in, const float* packed, int n_classes,

@@ -19,7 +19,8 @@ int proto_loss_forward_impl(
     const float* raw_rows /* [slots, D] rows left by the EMA kernel (fused step), or null */, int raw_cap,
     const float* bank_n /* [C, M, D] F.normalize'd bank, or null: normalised here */,
     uint64_t* seed_dev /* [2] device step counters; [0] is added to `seed` and advanced by the sampler */,
-    int rows_mode /* 0: register-tiled FFMA products, 1: tensor cores (mma.sync, 3xTF32) */);
+    int rows_mode /* 0: register-tiled FFMA products, 1: tensor cores (mma.sync, 3xTF32) */,
+    FillShare fill /* carried zero fill: given to the split (kPhaseSplit) or to the rows kernel (kPhaseRows) */);
 
 // proto_ema.cu
 struct DenseRows { const float* out_feat; const float* nearest; const float* sim; };
@@ -34,6 +35,7 @@ int proto_ema_accumulate_impl(
     const SplitWs* shared_split, float* packed, float* proto_target, void* stream,
     float* raw_rows /* [max_rows, D] un-normalised gathered rows, or null */, int rows_v1 /* A/B: warp-per-row kernel */,
     const float* bank_n /* [C, M, D] l2-normalised bank, or null: normalised here */,
-    const uint64_t* seed_dev /* [2] device step counters added to `seed` ([1] is this operator's), or null */);
+    const uint64_t* seed_dev /* [2] device step counters added to `seed` ([1] is this operator's), or null */,
+    FillShare fill /* a share of the carried zero fill for the rows kernel, or {null, 0} */);
 
 }  // namespace c3d

@@ -246,6 +246,7 @@ struct RowsParams {
   const float* feats;      // (B, D, HW)
   const float* raw_rows;   // [slots, D] un-normalised feature rows gathered by the EMA kernel, or null
   int raw_cap;             // rows the EMA kernel had room for (more labelled pixels: it wrote none)
+  FillShare fill;          // share of the carried zero fill (common.cuh), or {null, 0}
   const float* bank_n;     // (Kc, D)
   const int32_t* pix_list;
   const int32_t* cls_list;
@@ -500,7 +501,7 @@ __device__ long long g_rows_dbg[16];
 // kMma: the two products on the tensor cores (mma.sync m16n8k8, 3xTF32; rowgemm.cuh) instead of
 // the register-tiled FFMA form.
 template <bool kWithGrad, int kKS, int kRP, int kDch, int kDJ, bool kMma>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(kRowsThreads + 32, 1)
 loss_rows16_kernel(RowsParams p) {
   extern __shared__ __align__(16) float smem[];
   const int D = p.D, Kc = p.Kc, ldl = p.ldl;
@@ -515,6 +516,13 @@ loss_rows16_kernel(RowsParams p) {
   __shared__ float s_red[8];
   constexpr int kRbCap = 192;
   __shared__ int32_t s_rb[kRbCap];
+  constexpr int kLossZeroPage = 2048;        // all the shared memory the bank tile leaves free
+  __shared__ __align__(128) float4 s_zero[kLossZeroPage / 16];
+  // carried fill: a ninth warp (launched only with a share) sends this CTA's slice on its own
+  if (threadIdx.x >= kRowsThreads) {
+    carrier_warp_run(p.fill, s_zero, kLossZeroPage, blockIdx.x, gridDim.x);
+    return;
+  }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cg = threadIdx.x & 63, rg = threadIdx.x >> 6;
   const int n_rows = p.info[kInfoU];
@@ -530,7 +538,7 @@ loss_rows16_kernel(RowsParams p) {
   // single-tile case: start the bank copies now, complete them after the first gather
   bool staged = !(p.n_tiles == 1 && (int)blockIdx.x < n_groups);
   if (!staged) stage_bank_tile_issue(s_bank, p.bank_n, 0, Kc, BL);
-  __syncthreads();  // s_rb visible
+  rows_sync();  // s_rb visible
 
   for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
     // ---- P0: gather + L2-normalise two rows per warp (:166); the two rows' dependent
@@ -590,13 +598,13 @@ loss_rows16_kernel(RowsParams p) {
     }
     DBG_STAMP(1);
     if (!staged) { cp_async_wait_all(); staged = true; }
-    __syncthreads();
+    rows_sync();
     DBG_STAMP(2);
 
     // ---- P1: logits z = (a_hat . c_hat) / temperature (:168-172)
     for (int tile = 0; tile < p.n_tiles; ++tile) {
       const int r0 = tile * p.tile_rows, rows = min(p.tile_rows, Kc - r0);
-      if (p.n_tiles > 1) { __syncthreads(); stage_bank_tile(s_bank, p.bank_n, r0, rows, BL); __syncthreads(); }
+      if (p.n_tiles > 1) { rows_sync(); stage_bank_tile(s_bank, p.bank_n, r0, rows, BL); rows_sync(); }
       if (kMma) {
         mma_tile_logits<kColsPerThread>(s_A, lda, s_bank, rows, BL, s_L, ldl, r0, p.temperature);
       } else {
@@ -612,7 +620,7 @@ loss_rows16_kernel(RowsParams p) {
         }
       }
     }
-    __syncthreads();
+    rows_sync();
 
     DBG_STAMP(3);
     // ---- P2: softmax statistics, loss term, dL/dlogit (:175-193); one half-warp per
@@ -699,7 +707,7 @@ loss_rows16_kernel(RowsParams p) {
         }
       }
     }
-    __syncthreads();
+    rows_sync();
 
     DBG_STAMP(4);
     if (kWithGrad && kMma) {
@@ -710,7 +718,7 @@ loss_rows16_kernel(RowsParams p) {
       for (int j = 0; j < kNTG; ++j) accm[j][0] = accm[j][1] = accm[j][2] = accm[j][3] = 0.f;
       for (int tile = 0; tile < p.n_tiles; ++tile) {
         const int r0 = tile * p.tile_rows, rows = min(p.tile_rows, Kc - r0);
-        if (p.n_tiles > 1) { __syncthreads(); stage_bank_tile(s_bank, p.bank_n, r0, rows, BL); __syncthreads(); }
+        if (p.n_tiles > 1) { rows_sync(); stage_bank_tile(s_bank, p.bank_n, r0, rows, BL); rows_sync(); }
         mma_tile_gradT<kNTG>(s_L, ldl, r0, s_bank, rows, BL, accm);
       }
       {
@@ -724,7 +732,7 @@ loss_rows16_kernel(RowsParams p) {
           }
         }
       }
-      __syncthreads();
+      rows_sync();
     }
     if (kWithGrad && !kMma) {
       // ---- P3: d a_hat = G . bank
@@ -735,7 +743,7 @@ loss_rows16_kernel(RowsParams p) {
         for (int q = 0; q < kDch; ++q) acc4[r][q] = make_float4(0.f, 0.f, 0.f, 0.f);
       for (int tile = 0; tile < p.n_tiles; ++tile) {
         const int r0 = tile * p.tile_rows, rows = min(p.tile_rows, Kc - r0);
-        if (p.n_tiles > 1) { __syncthreads(); stage_bank_tile(s_bank, p.bank_n, r0, rows, BL); __syncthreads(); }
+        if (p.n_tiles > 1) { rows_sync(); stage_bank_tile(s_bank, p.bank_n, r0, rows, BL); rows_sync(); }
         tile_gradT<kKS, kRP, kDch>(s_L, ldl, r0, s_bank, rows, BL, acc4);
       }
       {
@@ -745,7 +753,7 @@ loss_rows16_kernel(RowsParams p) {
         const int kh = threadIdx.x / (CT * kRowGroups), d4 = D >> 2;
         if (kKS > 1) {
           // add the k-split partials through shared memory (G in s_L is dead now)
-          __syncthreads();
+          rows_sync();
           float4* s_part = reinterpret_cast<float4*>(s_L);  // [kKS-1][16 rows][d4]
           if (kh > 0) {
 #pragma unroll
@@ -758,7 +766,7 @@ loss_rows16_kernel(RowsParams p) {
               }
             }
           }
-          __syncthreads();
+          rows_sync();
           if (kh == 0) {
 #pragma unroll
             for (int q = 0; q < kDch; ++q) {
@@ -787,7 +795,7 @@ loss_rows16_kernel(RowsParams p) {
           }
         }
       }
-      __syncthreads();
+      rows_sync();
     }
     if (kWithGrad) {
       // ---- P4: normalize backward, weighted gradient row
@@ -813,23 +821,23 @@ loss_rows16_kernel(RowsParams p) {
         }
       }
     }
-    __syncthreads();
+    rows_sync();
   }
 
   DBG_STAMP(6);
   // ---- deterministic final reduction by the last CTA: loss = sum / (A*T)
   __threadfence();
-  __syncthreads();
+  rows_sync();
   if (threadIdx.x == 0) s_last = (atomicAdd(&p.info[kInfoDone2], 1) == (int)gridDim.x - 1);
-  __syncthreads();
+  rows_sync();
   DBG_STAMP(7);
   if (!s_last) return;
   __threadfence();
   float s = 0.f;
-  for (int i = threadIdx.x; i < n_rows; i += blockDim.x) s += __ldcg(p.loss_part + i);
+  for (int i = threadIdx.x; i < n_rows; i += kRowsThreads) s += __ldcg(p.loss_part + i);
   s = warp_sum(s);
   if (lane == 0) s_red[warp] = s;
-  __syncthreads();
+  rows_sync();
   if (threadIdx.x == 0) {
     float tot = 0.f;
     for (int w = 0; w < 8; ++w) tot += s_red[w];
@@ -844,7 +852,8 @@ static int launch_rows16(const RowsParams& p, size_t smem, cudaStream_t stream) 
   C3D_CUDA(cudaFuncSetAttribute(loss_rows16_kernel<kWithGrad, kKS, kRP, kDch, kDJ, kMma>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   KernelTimer kt__("loss_rows_kernel", stream);
-  loss_rows16_kernel<kWithGrad, kKS, kRP, kDch, kDJ, kMma><<<kNumSMs, 256, smem, stream>>>(p);
+  loss_rows16_kernel<kWithGrad, kKS, kRP, kDch, kDJ, kMma>
+      <<<kNumSMs, kRowsThreads + (p.fill.bytes ? 32 : 0), smem, stream>>>(p);
   return check_launch("loss_rows16_kernel");
 }
 
@@ -955,7 +964,7 @@ int c3d::proto_loss_forward_impl(
     int sub_protos, int ignore_label, float temperature, float base_temperature, int num_anchor,
     const int64_t* keep, int keep_rows, uint64_t seed, int need_grad, int phases, void* workspace,
     float* loss_out, float* zero_buf, int zero_n, void* stream_, const float* raw_rows, int raw_cap,
-    const float* bank_n_in, uint64_t* seed_dev, int rows_mode) {
+    const float* bank_n_in, uint64_t* seed_dev, int rows_mode, FillShare fill) {
   cudaStream_t stream = (cudaStream_t)stream_;
   need_grad &= 1;   // bit 1 of the public argument selects rows_mode (passed separately here)
   const int B = batch, D = dim, C = n_classes, M = sub_protos;
@@ -982,7 +991,8 @@ int c3d::proto_loss_forward_impl(
   if (phases & kPhaseSplit) {
   C3D_CUDA(cudaMemsetAsync(w.s.info, 0, (size_t)(8 + B) * 4, stream));
   if ((rc = launch_split((const long long*)labels, keep_mask, probs, B, C, HW, ignore_label, w.s, w.w_list,
-                         w.cnt_list, zero_buf, zero_n, stream))) return rc;
+                         w.cnt_list, zero_buf, zero_n, stream,
+                         (phases & kPhaseRows) ? FillShare{nullptr, 0} : fill))) return rc;
   }
   if (phases & kPhaseSample) {
   { KernelTimer kt__("loss_sample_kernel", stream);
@@ -1005,7 +1015,7 @@ int c3d::proto_loss_forward_impl(
   }
 
   RowsParams p{};
-  p.feats = feats; p.raw_rows = raw_rows; p.raw_cap = raw_cap; p.bank_n = bank_n_in ? bank_n_in + (size_t)M * D : w.bank_n; p.pix_list = w.s.pix_list; p.cls_list = w.s.cls_list;
+  p.feats = feats; p.raw_rows = raw_rows; p.raw_cap = raw_cap; p.fill = fill; p.bank_n = bank_n_in ? bank_n_in + (size_t)M * D : w.bank_n; p.pix_list = w.s.pix_list; p.cls_list = w.s.cls_list;
   p.cnt_list = w.cnt_list; p.dist_list = reinterpret_cast<const int32_t*>(w.w_list);
   p.seg_start = w.s.seg_start; p.row_base = w.row_base; p.seg_of_t = w.seg_of_t; p.info = w.s.info;
   p.loss_part = w.loss_part; p.row_pix = w.row_pix; p.grad_rows = w.grad_rows; p.loss_out = loss_out;
@@ -1041,7 +1051,7 @@ int c3d::proto_loss_forward_impl(
     if (D <= 256) return launch_rows16<false, 1, 4, 1, 8>(p, plan.smem, stream);
     return launch_rows16<false, 1, 4, 4, 32>(p, plan.smem, stream);
   }
-  C3D_REQUIRE(raw_rows == nullptr, "raw rows need the tiled loss rows kernel");
+  C3D_REQUIRE(raw_rows == nullptr && fill.bytes == 0, "raw rows / carried fill need the tiled loss rows kernel");
   if (!need_grad) return launch_rows<false, 1>(p, smem, stream);
   if (D <= 128) return launch_rows<true, 1>(p, smem, stream);
   if (D <= 256) return launch_rows<true, 2>(p, smem, stream);
@@ -1059,7 +1069,7 @@ extern "C" int c3d_proto_loss_forward(
                                  n_classes, sub_protos, ignore_label, temperature, base_temperature,
                                  num_anchor, keep, keep_rows, seed, need_grad,
                                  kPhaseSplit | kPhaseSample | kPhaseRows, workspace, loss_out, nullptr, 0,
-                                 stream, nullptr, 0, nullptr, nullptr, need_grad >> 1);
+                                 stream, nullptr, 0, nullptr, nullptr, need_grad >> 1, FillShare{nullptr, 0});
 }
 
 extern "C" int c3d_proto_loss_forward_phase(
@@ -1073,7 +1083,7 @@ extern "C" int c3d_proto_loss_forward_phase(
   return proto_loss_forward_impl(feats, probs, labels, keep_mask, proto_queue, batch, dim, proj_h, proj_w,
                                  n_classes, sub_protos, ignore_label, temperature, base_temperature,
                                  num_anchor, keep, keep_rows, seed, need_grad, internal, workspace, loss_out,
-                                 nullptr, 0, stream, nullptr, 0, nullptr, nullptr, need_grad >> 1);
+                                 nullptr, 0, stream, nullptr, 0, nullptr, nullptr, need_grad >> 1, FillShare{nullptr, 0});
 }
 
 extern "C" int c3d_proto_loss_backward(int batch, int dim, int proj_h, int proj_w, int n_classes,

@@ -39,11 +39,20 @@ extern "C" int c3d_proto_step(
     int sub_protos, int ignore_label, float temperature, float base_temperature, int num_anchor,
     const int64_t* keep, int keep_rows, const float* gumbel, int assign_mode, uint64_t seed,
     int64_t max_rows, int need_grad, int phases, const float* bank_n, uint64_t* seed_counters,
-    void* workspace, float* packed, float* proto_target, float* loss_out, void* stream) {
+    void* workspace, float* packed, float* proto_target, float* loss_out, void* cofill_ptr,
+    size_t cofill_bytes, void* stream) {
   C3D_REQUIRE(workspace && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "workspace must be 256 B aligned");
   C3D_REQUIRE(phases > 0 && phases < 16, "phases: bit mask of 1 split, 2 sample, 4 accumulate, 8 loss rows");
   C3D_REQUIRE(batch > 0 && n_classes >= 2 && dim > 0 && sub_protos > 0 && num_anchor > 0 && max_rows > 0 &&
               proj_h > 0 && proj_w > 0, "bad shape");
+  C3D_REQUIRE((cofill_ptr == nullptr) == (cofill_bytes == 0) && cofill_bytes % 16 == 0 &&
+              (reinterpret_cast<uintptr_t>(cofill_ptr) & 15) == 0, "carried fill: 16 B aligned pointer and size");
+  // The carried fill goes to ONE kernel of the call: the rows kernel of the latest phase asked
+  // for (loss rows, else EMA rows), else the label split.
+  FillShare fill{reinterpret_cast<char*>(cofill_ptr), cofill_bytes};
+  const FillShare none{nullptr, 0};
+  const int carrier = (phases & 8) ? 8 : ((phases & 4) ? 4 : ((phases & 1) ? 1 : 0));
+  if (cofill_bytes && carrier == 0) { int rcf = launch_fill(cofill_ptr, cofill_bytes, (cudaStream_t)stream); if (rcf) return rcf; }
   const int HW = proj_h * proj_w;
   int rc;
   char* extra = reinterpret_cast<char*>(workspace) +
@@ -56,7 +65,7 @@ extern "C" int c3d_proto_step(
     rc = proto_loss_forward_impl(nullptr, probs, labels, keep_mask, nullptr, batch, dim, proj_h, proj_w,
                                  n_classes, sub_protos, ignore_label, temperature, base_temperature,
                                  num_anchor, keep, keep_rows, seed, need_grad, loss_phases, workspace, nullptr,
-                                 nullptr, 0, stream, nullptr, 0, nullptr, seed_counters, 0);
+                                 nullptr, 0, stream, nullptr, 0, nullptr, seed_counters, 0, carrier == 1 ? fill : none);
     if (rc) return rc;
   }
   if (phases & 4) {
@@ -64,7 +73,7 @@ extern "C" int c3d_proto_step(
     rc = proto_ema_accumulate_impl(feats, nullptr, nullptr, prototypes, ln_d_w, ln_d_b, ln_c_w, ln_c_b, ln_eps,
                                    batch, dim, proj_h, proj_w, n_classes, sub_protos, ignore_label, max_rows,
                                    gumbel, assign_mode, seed, extra, &s, packed, proto_target, stream, raw_rows, 0, bank_n,
-                                   seed_counters);
+                                   seed_counters, carrier == 4 ? fill : none);
     if (rc) return rc;
   }
   if (phases & 8) {
@@ -72,7 +81,7 @@ extern "C" int c3d_proto_step(
                                  n_classes, sub_protos, ignore_label, temperature, base_temperature,
                                  num_anchor, nullptr, 0, seed, need_grad, kPhaseRows, workspace, loss_out,
                                  nullptr, 0, stream, raw_rows, (int)(max_rows > 0x7fffffff ? 0x7fffffff : max_rows), bank_n,
-                                 nullptr, need_grad >> 1);
+                                 nullptr, need_grad >> 1, carrier == 8 ? fill : none);
     if (rc) return rc;
   }
   return C3D_OK;

@@ -43,9 +43,9 @@ struct BankLayout {
 // `issue` only starts the copies; cp_async_wait_all() (+ a barrier) completes them, so
 // the caller can overlap the staging with its own global loads.
 __device__ __forceinline__ void stage_bank_tile_issue(float* s_bank, const float* __restrict__ bank_n,
-                                                      int r0, int rows, const BankLayout& L) {
+                                                      int r0, int rows, const BankLayout& L,
+                                                      int nt = kRowsThreads /* staging threads */) {
   const int d4 = L.D >> 2;
-  const int nt = blockDim.x;
   if (d4 <= nt && nt % d4 == 0) {  // fixed chunk per thread: no division in the loop
     const int c = threadIdx.x % d4, rstep = nt / d4;
     for (int r = threadIdx.x / d4; r < rows; r += rstep)

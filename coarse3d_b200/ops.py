@@ -33,6 +33,18 @@ def _need_cuda(**tensors):
             raise ValueError("coarse3d_b200: `%s` must be contiguous" % name)
 
 
+def _cofill_args(cofill):
+    """(pointer, bytes) of a carried fill: a contiguous CUDA tensor (or a flat slice of one)
+    that the call's kernels zero on the side while they do their own work."""
+    if cofill is None or cofill.numel() == 0:
+        return None, 0
+    _need_cuda(cofill=cofill)
+    n = cofill.numel() * cofill.element_size()
+    if n % 16 or cofill.data_ptr() % 16:
+        raise ValueError("cofill must be contiguous, 16 B aligned and a multiple of 16 B")
+    return ctypes.c_void_p(cofill.data_ptr()), n
+
+
 # --------------------------------------------------------------------- a1 --
 class Fov(NamedTuple):
     """The angles RangeProjection.__init__ stores (projection.py:29-35), radians."""
@@ -83,7 +95,8 @@ class ProjectionBuffers:
 
 
 def project_batch(points, offsets, fov: Fov, proj_h, proj_w, depth=None,
-                  buffers: ProjectionBuffers = None, exact_f64=False, fused_kernel=False) -> Projection:
+                  buffers: ProjectionBuffers = None, exact_f64=False, fused_kernel=False,
+                  cofill=None) -> Projection:
     """RangeProjection.doProjection for a CSR batch (projection.py:43-115).
 
     points (sum N, C>=3) f32, offsets (B+1,) i32, optional depth (sum N,) f32;
@@ -114,7 +127,7 @@ def project_batch(points, offsets, fov: Fov, proj_h, proj_w, depth=None,
         _p(b.proj_range), _p(b.proj_pointcloud), _p(b.proj_idx), _p(b.proj_mask),
         _p(b.uproj_x_idx), _p(b.uproj_y_idx), _p(b.uproj_depth), _p(b.workspace),
         (1 if was_clean else 0) | (2 if exact_f64 else 0) | (4 if fused_kernel else 0), _p(b.flags),
-        _stream()))
+        *_cofill_args(cofill), _stream()))
     b.clean = form
     return Projection(b.proj_pointcloud, b.proj_range, b.proj_idx, b.proj_mask,
                       b.uproj_x_idx, b.uproj_y_idx, b.uproj_depth, b.flags)
@@ -135,7 +148,7 @@ class Assembled(NamedTuple):
 
 def project_assemble_batch(points, offsets, fov: Fov, proj_h, proj_w, sem_label=None,
                            weak_label=None, img_mean=None, img_std=None, depth=None,
-                           buffers: ProjectionBuffers = None, fused_kernel=False) -> Assembled:
+                           buffers: ProjectionBuffers = None, fused_kernel=False, cofill=None) -> Assembled:
     """Projection fused with its caller (loader :124-172, trainer :600-608): label images
     and the 5-channel network input straight from the z-buffer winners.
 
@@ -171,7 +184,8 @@ def project_assemble_batch(points, offsets, fov: Fov, proj_h, proj_w, sem_label=
         1 if ldt == torch.uint8 else 0, _p(img_mean), _p(img_std), fov.abs_fov_left, fov.fov_hori, fov.abs_fov_down, fov.fov_vert,
         proj_h, proj_w, _p(feature), _p(train), _p(evall), _p(b.proj_range), _p(b.proj_idx),
         _p(b.uproj_x_idx), _p(b.uproj_y_idx), _p(b.uproj_depth), _p(b.workspace),
-        (1 if was_clean else 0) | (4 if fused_kernel else 0), _p(b.flags), _stream()))
+        (1 if was_clean else 0) | (4 if fused_kernel else 0), _p(b.flags),
+        *_cofill_args(cofill), _stream()))
     b.clean = form
     return Assembled(feature, train, evall, b.proj_range, b.proj_idx, b.uproj_x_idx, b.uproj_y_idx,
                      b.uproj_depth, b.flags)
@@ -676,7 +690,7 @@ def proto_step_workspace(batch, n_classes, hw, dim, sub_protos, num_anchor, max_
 def proto_step_raw(phases, feats, probs, labels, keep_mask, prototypes, ln_d_w, ln_d_b, ln_c_w, ln_c_b,
                    cfg, workspace, packed, loss_out, max_rows, ln_eps=1e-5, keep=None,
                    gumbel=None, assign_mode=ASSIGN_GUMBEL_DEVICE, seed=0, need_grad=True, proto_target=None,
-                   bank_n=None, seed_counters=None, tensor_cores=False):
+                   bank_n=None, seed_counters=None, tensor_cores=False, cofill=None):
     """c3d_proto_step on pre-validated device tensors (no autograd, no allocation): the phases of
     the fused EMA-update + loss step (STEP_* bit mask) on one shared label split."""
     B, D, H, W = feats.shape
@@ -687,7 +701,8 @@ def proto_step_raw(phases, feats, probs, labels, keep_mask, prototypes, ln_d_w, 
         float(cfg.base_temperature), int(cfg.num_anchor), _p(keep), 0 if keep is None else keep.shape[0],
         _p(gumbel), int(assign_mode), int(seed), int(max_rows),
         (1 if need_grad else 0) | (2 if tensor_cores else 0), int(phases),
-        _p(bank_n), _p(seed_counters), _p(workspace), _p(packed), _p(proto_target), _p(loss_out), _stream()))
+        _p(bank_n), _p(seed_counters), _p(workspace), _p(packed), _p(proto_target), _p(loss_out),
+        *_cofill_args(cofill), _stream()))
 
 
 def launch_count():

@@ -106,7 +106,7 @@ class HotPathStep:
         self.ev_fork0 = torch.cuda.Event()
         self.graphs = None
         self.concurrent = concurrent
-        self.schedule = _os.environ.get("C3D_SCHEDULE", "fill_in_knn")
+        self.schedule = _os.environ.get("C3D_SCHEDULE", "fill_spread")
         # fill daemon (schedule "fill_daemon"): mode, CTAs per SM, zero-page bytes, copies in flight
         self.daemon = tuple(int(v) for v in _os.environ.get("C3D_DAEMON", "0,1,8192,4").split(","))
         # ablation switch for tools/ablate.py: which chains run (default: all)
@@ -123,8 +123,39 @@ class HotPathStep:
          self.ev_resolved, self.ev_selected) = (torch.cuda.Event() for _ in range(7))
         self.ev_split = torch.cuda.Event()
         self.knn_after_select = _os.environ.get("C3D_KNN_AFTER_SELECT", "0") == "1"
+        # the vote (+ its share of the fill) released only when the loss rows are done: the rows
+        # kernels of both chains need whole SMs (shared memory) and, run next to the vote's
+        # 30 k CTAs, stall it for longer than they take ("auto": batches >= 48, measured)
+        kar = _os.environ.get("C3D_KNN_AFTER_ROWS", "auto")
+        self.knn_after_rows = (batch >= 20) if kar == "auto" else kar == "1"
+        self.ev_rows = torch.cuda.Event()
         self.knn_split = int(_os.environ.get("C3D_KNN_SPLIT", "0"))   # scans in the first of two KNN launches
+        # schedule "fill_spread": fractions of the dense-gradient zero fill carried by the
+        # projection's two passes, the label split, the EMA rows kernel and the loss rows kernel
+        # (the KNN vote carries the rest).  Defaults from the sweeps in profiles/r2/fill_spread_*.txt:
+        # only the loss rows kernel's carrier warp pays -- half of the fill at batch 8, where the
+        # vote is short, a fifth once the vote is held back until the rows kernels are done.
+        shares = _os.environ.get("C3D_FILL_SHARES", "auto")
+        if shares == "auto":
+            self.fill_shares = (0.0, 0.0, 0.0, 0.5 if batch <= 12 else (0.3 if batch < 20 else 0.2))
+        else:
+            self.fill_shares = tuple(float(v) for v in shares.split(","))
         torch.cuda.synchronize(self.device)
+
+    def _fill_slices(self, chains=True):
+        """The gradient buffer as five flat 8 KB-aligned slices: (proj, split, ema, loss, knn);
+        without the prototype chains their shares stay with the vote."""
+        flat = self.grad.view(-1)
+        n, page = flat.numel(), 2048          # floats per 8 KB page
+        out, lo = [], 0
+        for j, f in enumerate(self.fill_shares):
+            if j > 0 and not chains:
+                f = 0.0
+            hi = min(n, lo + int(n * max(f, 0.0)) // page * page)
+            out.append(flat[lo:hi] if hi > lo else None)
+            lo = hi
+        out.append(flat[lo:] if lo < n else None)
+        return out
 
     # bytes the reference dtypes move per step (BASELINE.md section 3)
     def algorithmic_bytes(self):
@@ -137,6 +168,17 @@ class HotPathStep:
             "loss_grad_fill": 4 * D * B * HW,
         }
 
+    def fill_bytes_by_carrier(self):
+        """Bytes of the dense-gradient zero fill each kernel of the current schedule carries."""
+        names = ("project", "label_split", "ema_rows", "loss_rows", "knn_vote")
+        total = self.grad.numel() * 4
+        if self.schedule == "fill_in_knn":
+            return dict(zip(names, (0, 0, 0, 0, total)))
+        if self.schedule != "fill_spread":
+            return {"fill_kernel": total}
+        sl = self._fill_slices(chains=self.fused_step and {"loss", "ema"} <= self.parts)
+        return {k: (0 if v is None else v.numel() * 4) for k, v in zip(names, sl)}
+
     def run(self, i, seed=0):
         """Enqueue one step (no allocation, no sync).  The four independent chains
         -- projection -> KNN, the dense-gradient zero fill, loss forward -> backward,
@@ -146,18 +188,24 @@ class HotPathStep:
         s, b = self.sets[i % len(self.sets)], self.proj_bufs[i % len(self.sets)]
         H, W, C = self.shape.proj_h, self.shape.proj_w, self.shape.n_classes
         cur = torch.cuda.current_stream(self.device)
-        fused = self.schedule == "fill_in_knn" and {"knn", "fill"} <= self.parts
+        spread = (self.schedule == "fill_spread" and {"proj", "knn", "fill"} <= self.parts and
+                  not self.knn_after_select)
+        fused = (self.schedule == "fill_in_knn" or spread) and {"knn", "fill"} <= self.parts
+        self._fs = [None, None, None, None, self.grad]
+        if spread:
+            self._fs = self._fill_slices(chains=self.fused_step and {"loss", "ema"} <= self.parts)
         if not self.concurrent:
-            pr = ops.project_batch(s.points, s.offsets, self.fov, H, W, buffers=b)
+            pr = ops.project_batch(s.points, s.offsets, self.fov, H, W, buffers=b, cofill=self._fs[0])
             if self.fused_step:
-                self._step(ops.STEP_SPLIT | ops.STEP_SAMPLE | ops.STEP_ACCUMULATE, s.labels, s, seed)
+                self._step(ops.STEP_SPLIT, s.labels, s, seed, cofill=self._fs[1])
+                self._step(ops.STEP_SAMPLE | ops.STEP_ACCUMULATE, s.labels, s, seed, cofill=self._fs[2])
                 self._ema_finish()
-                self._step(ops.STEP_LOSS_ROWS, s.labels, s, seed)
+                self._step(ops.STEP_LOSS_ROWS, s.labels, s, seed, cofill=self._fs[3])
             else:
                 self._ema(s, seed)            # the bank is updated in the model forward, before the loss
                 self._loss_fwd(s, seed)
             if fused:
-                self._knn(s, pr, C, cofill=self.grad)
+                self._knn(s, pr, C, cofill=self._fs[4])
             ops.proto_loss_backward_raw(s.feats.shape, self.cfg, C, self.M, self.loss_ws, self.grad_out,
                                         self.grad, grad_is_zeroed=fused)
             if not fused:
@@ -185,6 +233,7 @@ class HotPathStep:
         for st in self.side:
             st.wait_event(self.ev_fork)
         hold = fused and self.knn_after_select and "loss" in P
+        defer_knn = (fused and self.knn_after_rows and self.fused_step and {"loss", "ema"} <= P and not hold)
         if hold:
             # selection part of the loss first; its event releases the KNN + fill kernel
             with torch.cuda.stream(st_loss):
@@ -195,16 +244,18 @@ class HotPathStep:
             # pipes busy.  As two kernels they serialise: the fill's CTAs occupy every SM slot.
             with torch.cuda.stream(st_proj):
                 if "proj" in P:
-                    pr = ops.project_batch(s.points, s.offsets, self.fov, H, W, buffers=b)
+                    pr = ops.project_batch(s.points, s.offsets, self.fov, H, W, buffers=b, cofill=self._fs[0])
                 if hold:
                     # The vote's 3750 CTAs keep every SM full until its grid is drained, and the
                     # loss-rows kernel needs a whole SM (217 KB of shared memory): released
                     # together, the high-priority rows CTAs are placed first.
                     st_proj.wait_event(self.ev_selected)
-                self._knn(s, pr if pr is not None else self._last_proj(b), C, cofill=self.grad)
-                self.ev_proj.record(st_proj)
-            st_fill.wait_event(self.ev_proj)
-            self.ev_fill.record(st_fill)
+                if not defer_knn:
+                    self._knn(s, pr if pr is not None else self._last_proj(b), C, cofill=self._fs[4])
+                    self.ev_proj.record(st_proj)
+            if not defer_knn:
+                st_fill.wait_event(self.ev_proj)
+                self.ev_fill.record(st_fill)
         elif sched == "fill_daemon":
             # The fill as a minimal-footprint persistent kernel (one warp per SM), launched first
             # and running UNDER everything else of the step.
@@ -254,12 +305,12 @@ class HotPathStep:
         if fused_step:
             # one label split for both operators, then the sampler next to the EMA chain
             with torch.cuda.stream(st_loss):
-                self._step(ops.STEP_SPLIT, s.labels, s, seed)
+                self._step(ops.STEP_SPLIT, s.labels, s, seed, cofill=self._fs[1])
                 self.ev_split.record(st_loss)
                 self._step(ops.STEP_SAMPLE, s.labels, s, seed)
             with torch.cuda.stream(st_ema):
                 st_ema.wait_event(self.ev_split)
-                self._step(ops.STEP_ACCUMULATE, s.labels, s, seed)
+                self._step(ops.STEP_ACCUMULATE, s.labels, s, seed, cofill=self._fs[2])
                 self._ema_finish()
                 self.ev_ema.record(st_ema)
         else:
@@ -275,9 +326,17 @@ class HotPathStep:
                 self._loss_fwd(s, seed, phases=1)
             st_loss.wait_event(self.ev_ema)
             if fused_step:
-                self._step(ops.STEP_LOSS_ROWS, s.labels, s, seed)
+                self._step(ops.STEP_LOSS_ROWS, s.labels, s, seed, cofill=self._fs[3])
             elif "loss" in P:
                 self._loss_fwd(s, seed, phases=2)
+            if defer_knn:
+                self.ev_rows.record(st_loss)
+                with torch.cuda.stream(st_proj):
+                    st_proj.wait_event(self.ev_rows)
+                    self._knn(s, pr if pr is not None else self._last_proj(b), C, cofill=self._fs[4])
+                    self.ev_proj.record(st_proj)
+                st_fill.wait_event(self.ev_proj)
+                self.ev_fill.record(st_fill)
             st_loss.wait_event(self.ev_fill)
             if "loss" in P:
                 ops.proto_loss_backward_raw(s.feats.shape, self.cfg, C, self.M, self.loss_ws,
@@ -339,9 +398,14 @@ class HotPathStep:
         else:
             ops.zero_fill_background(self.grad, *self.daemon)
 
-    def set_schedule(self, schedule, daemon=None, parts=None, fill_priority=None):
+    def set_schedule(self, schedule, daemon=None, parts=None, fill_priority=None, fill_shares=None,
+                     knn_after_rows=None):
         """Switch the schedule of an existing step (drops captured graphs)."""
         self.schedule = schedule
+        if knn_after_rows is not None:
+            self.knn_after_rows = bool(knn_after_rows)
+        if fill_shares is not None:
+            self.fill_shares = tuple(fill_shares)
         if daemon is not None:
             self.daemon = tuple(daemon)
         if parts is not None:
@@ -355,11 +419,11 @@ class HotPathStep:
         return ops.Projection(b.proj_pointcloud, b.proj_range, b.proj_idx, b.proj_mask,
                               b.uproj_x_idx, b.uproj_y_idx, b.uproj_depth, b.flags)
 
-    def _step(self, phases, labels, s, seed):
+    def _step(self, phases, labels, s, seed, cofill=None):
         ops.proto_step_raw(phases, s.feats, s.probs, labels, None, self.protos, *self.ln_d, *self.ln_c,
                            self.cfg, self.loss_ws, self.packed, self.loss, self.max_rows,
                            assign_mode=ops.ASSIGN_GUMBEL_DEVICE, seed=seed, bank_n=self.bank_n,
-                           seed_counters=self.seed_counters if self.device_seeds else None)
+                           seed_counters=self.seed_counters if self.device_seeds else None, cofill=cofill)
 
     def _ema_finish(self):
         """all-reduce of the packed sums (N > 1) + the EMA itself, in place on the bank"""

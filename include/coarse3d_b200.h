@@ -97,6 +97,9 @@ int c3d_project_batch(
                                      persistent kernel instead of the two-kernel form
                                      (same results; kept for A/B timing, slower) */
     int32_t* status_flags,        /* [1], caller-zeroed                          */
+    void* cofill_ptr,             /* carried fill (see c3d_knn_batch): a 16 B aligned buffer
+                                     zeroed meanwhile by the two passes' CTAs, or NULL       */
+    size_t cofill_bytes,          /* multiple of 16                                        */
     void* stream);
 
 /* ---------------------------------------------------------------- f1 ----
@@ -126,7 +129,9 @@ int c3d_project_assemble_batch(
     float* proj_range,            /* [batch, H, W]                                         */
     int32_t* proj_idx,            /* [batch, H, W]                                         */
     int32_t* uproj_x_idx, int32_t* uproj_y_idx, float* uproj_depth,   /* [total_points]   */
-    void* workspace, int workspace_flags, int32_t* status_flags, void* stream);
+    void* workspace, int workspace_flags, int32_t* status_flags,
+    void* cofill_ptr, size_t cofill_bytes,   /* carried fill, as in c3d_project_batch */
+    void* stream);
 
 /* ---------------------------------------------------------------- a4 ----
  * KNN.forward, pc_processor/postproc/knn.py:54-142, for a CSR batch of scans.
@@ -431,7 +436,11 @@ int c3d_proto_step(
                                      ([0] anchor sampling, advanced by phase 2; [1] Gumbel noise,
                                      advanced by c3d_proto_ema_apply), so that replays of a
                                      captured CUDA graph draw fresh randomness              */
-    void* workspace, float* packed, float* proto_target, float* loss_out, void* stream);
+    void* workspace, float* packed, float* proto_target, float* loss_out,
+    void* cofill_ptr, size_t cofill_bytes,   /* carried fill (see c3d_knn_batch) for ONE kernel of the
+                                                call: the rows kernel of the latest phase asked for,
+                                                else the label split; NULL / 0 for none          */
+    void* stream);
 
 /* F.normalize(x, p=2, dim=-1) of `rows` bank rows (eps 1e-12): the `bank_n` of c3d_proto_step for a
  * bank that did not come out of c3d_proto_ema_apply (e.g. the initial one). */

@@ -25,7 +25,14 @@ def test_schedules_agree(cuda_device, monkeypatch):
     for schedule, concurrent in [("fill_after_projection", False), ("fill_after_projection", True),
                                  ("fill_in_knn", False), ("fill_in_knn", True), ("fill_first", True),
                                  ("fill_daemon", True), ("fill_daemon:1,2,0,0", True),
-                                 ("fill_daemon:0,1,4096,1", True)]:
+                                 ("fill_daemon:0,1,4096,1", True), ("fill_spread", False),
+                                 ("fill_spread", True), ("fill_spread=0.3,0.2,0.25,0.25", True),
+                                 ("fill_spread=0,0,0,1", True), ("fill_spread=0.001,0.5,0,0", False)]:
+        schedule, _, shares = schedule.partition("=")
+        if shares:
+            monkeypatch.setenv("C3D_FILL_SHARES", shares)
+        else:
+            monkeypatch.delenv("C3D_FILL_SHARES", raising=False)
         schedule, _, daemon = schedule.partition(":")
         if daemon:
             monkeypatch.setenv("C3D_DAEMON", daemon)
@@ -40,6 +47,28 @@ def test_schedules_agree(cuda_device, monkeypatch):
             assert torch.isfinite(out[0]) and int((out[1] != 0).sum()) > 0
         for a, b in zip(out, ref):
             assert torch.equal(a, b), (schedule, concurrent)
+
+
+def test_vote_released_after_the_loss_rows(cuda_device, monkeypatch):
+    """C3D_KNN_AFTER_ROWS=1 (the large-batch default): the vote and its share of the fill wait for
+    the rows kernels of both chains -- an ordering only, same results."""
+    monkeypatch.setenv("C3D_KNN_AFTER_ROWS", "0")
+    step = _step(monkeypatch, "fill_in_knn")
+    step.run(0, seed=5)
+    want = _outputs(step)
+    monkeypatch.setenv("C3D_KNN_AFTER_ROWS", "1")
+    for schedule, shares in [("fill_in_knn", None), ("fill_spread", "0.2,0,0.15,0.15")]:
+        if shares:
+            monkeypatch.setenv("C3D_FILL_SHARES", shares)
+        held = _step(monkeypatch, schedule)
+        assert held.knn_after_rows
+        held.grad.fill_(2.0)
+        held.knn_out.fill_(-1)
+        held.run(0, seed=5)
+        for a, b in zip(_outputs(held), want):
+            assert torch.equal(a, b), schedule
+        assert held.capture()
+        held.protos.copy_(step.protos); held.bank_n.copy_(step.bank_n)
 
 
 def test_two_phase_loss_forward_and_held_knn(cuda_device, monkeypatch):

@@ -11,6 +11,8 @@ ALL = ["proj", "knn", "fill", "loss", "ema"]
 SETS = [ALL, ["proj"], ["proj", "knn"], ["fill"], ["proj", "knn", "fill"], ["loss"], ["ema"],
         ["loss", "fill"], ["loss", "ema"], ["proj", "knn", "loss", "ema"], ["proj", "fill", "loss", "ema"]]
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+if len(sys.argv) > 2:      # e.g. "proj+knn+fill,loss+ema"
+    SETS = [t.split("+") for t in sys.argv[2].split(",")]
 for parts in SETS:
     step = HotPathStep(synth.KITTI, B, parts=parts, n_sets=2)
     for i in range(4):

@@ -14,6 +14,10 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from coarse3d_b200 import synth  # noqa: E402
 from coarse3d_b200.pipeline import HotPathStep  # noqa: E402
 
+# fill_spread: shares of the zero fill carried by (projection, label split, EMA rows, loss rows)
+SPREAD = [(0.15, 0.05, 0.1, 0.1), (0.1, 0, 0, 0), (0.2, 0, 0, 0), (0.3, 0, 0, 0), (0, 0.05, 0, 0), (0, 0.1, 0, 0),
+          (0, 0, 0.1, 0), (0, 0, 0.2, 0), (0, 0, 0, 0.1), (0, 0, 0, 0.2), (0.2, 0.05, 0.1, 0.1),
+          (0.2, 0.1, 0.15, 0.15), (0.25, 0.1, 0.2, 0.2), (0.1, 0.05, 0.05, 0.05), (0.3, 0.1, 0.2, 0.3)]
 VARIANTS = [
     ("fill_in_knn", None),
     ("fill_after_projection", None),
@@ -51,12 +55,20 @@ def main():
     global VARIANTS
     if os.environ.get("C3D_SCHED_QUICK"):
         VARIANTS = VARIANTS[:2]
+    if os.environ.get("C3D_SCHED_SPREAD"):
+        spread = SPREAD
+        if os.environ["C3D_SCHED_SPREAD"] != "1":     # "a,b,c,d;a,b,c,d;..."
+            spread = [tuple(float(v) for v in t.split(",")) for t in os.environ["C3D_SCHED_SPREAD"].split(";")]
+        VARIANTS = VARIANTS[:1] + [("fill_spread", sh) for sh in spread] + VARIANTS[:1]
     batches = [int(a) for a in sys.argv[1:]] or [8, 64]
     out = []
     for B in batches:
         step = HotPathStep(synth.KITTI, B, n_sets=3)
         for sched, daemon in VARIANTS:
-            step.set_schedule(sched, daemon)
+            if sched == "fill_spread":     # shares, optionally a 5th value: 1 = vote after the loss rows
+                step.set_schedule(sched, fill_shares=daemon[:4], knn_after_rows=len(daemon) > 4 and daemon[4] > 0)
+            else:
+                step.set_schedule(sched, daemon, knn_after_rows=False)
             for i in range(3):
                 step.run(i, seed=i)
             torch.cuda.synchronize()
@@ -67,7 +79,7 @@ def main():
             out.append(rec)
         # where the daemon's own time goes, alone on the GPU
         from coarse3d_b200 import ops
-        for daemon in [] if os.environ.get("C3D_SCHED_QUICK") else [(0, 1, 8192, 4), (0, 1, 4096, 16), (0, 2, 4096, 8), (1, 1, 0, 0), (1, 2, 0, 0)]:
+        for daemon in [] if (os.environ.get("C3D_SCHED_QUICK") or os.environ.get("C3D_SCHED_SPREAD")) else [(0, 1, 8192, 4), (0, 1, 4096, 16), (0, 2, 4096, 8), (1, 1, 0, 0), (1, 2, 0, 0)]:
             for _ in range(2):
                 ops.zero_fill_background(step.grad, *daemon)
             torch.cuda.synchronize()
