@@ -33,6 +33,7 @@ struct SelWs {
   int32_t* count;     // [B*C] candidates per (scan, class)
   int32_t* present;   // [B*C] class occurs in train_label[b]
   uint32_t* thr;      // [B*C] key bits of the k-th largest, kNoThreshold = select nothing
+  int32_t* flags;     // [1] bit 0: a guard band overflowed (fast threshold kept for that class)
   size_t bytes;
 };
 
@@ -43,6 +44,7 @@ static SelWs carve_sel(void* base, int B, int C, int HW) {
   w.count = (int32_t*)take((size_t)B * C * 4);
   w.present = (int32_t*)take((size_t)B * C * 4);
   w.thr = (uint32_t*)take((size_t)B * C * 4);
+  w.flags = (int32_t*)take(4);
   w.key = (float*)take((size_t)B * HW * 4);
   w.pseudo = (uint8_t*)take((size_t)B * HW);
   w.bytes = off;
@@ -58,6 +60,31 @@ __device__ __forceinline__ uint4 philox_s(uint4 ctr, uint2 key) {
     key.x += 0x9E3779B9u; key.y += 0xBB67AE85u;
   }
   return ctr;
+}
+
+// The Exp(1) draw of pixel `gi` on the device sampler's Philox stream.
+__device__ __forceinline__ float philox_exp1(unsigned long long gi, unsigned long long seed) {
+  const uint4 r = philox_s(make_uint4((uint32_t)gi, (uint32_t)(gi >> 32), 2u, 0u),
+                           make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  return -logf(((float)(r.x >> 8) + 0.5f) * (1.0f / 16777216.0f));
+}
+
+// The key of one pixel under the oracle's rule (oracle/entropy_select.py, "rounded"): every
+// float32 operation of trainer.py:459-466 correctly rounded, in the reference's order -- log and
+// exp evaluated in float64 and rounded once, products and the class sum as separate float32
+// operations (no contraction), IEEE division.  Only the few pixels whose fast key lies in the
+// guard band around a (scan, class) threshold are evaluated this way (select_threshold).
+__device__ __forceinline__ float rounded_rule_key(const float* __restrict__ probs_b, int pix, int HW, int C,
+                                                  float q) {
+  float ent = 0.f;
+  for (int c = 0; c < C; ++c) {
+    const float p = __ldg(probs_b + (size_t)c * HW + pix);
+    const float x = __fadd_rn(p, 1e-10f);
+    const float l = (float)log((double)x);
+    ent = __fadd_rn(ent, __fmul_rn(p, l));
+  }
+  const float w = (float)exp((double)ent);       // exp(-1 * entropy), entropy = -sum
+  return __fdiv_rn(w, q);
 }
 
 // ---------------------------------------------------------------- S1 -------
@@ -120,12 +147,7 @@ select_prepare_kernel(const float* __restrict__ probs, const long long* __restri
       if (cand) {
         float q;
         if (noise) q = noise[((size_t)b * C + arg[e]) * HW + pix];
-        else {
-          const unsigned long long ctr = gi;
-          const uint4 r = philox_s(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), 2u, 0u),
-                                   make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
-          q = -logf(((float)(r.x >> 8) + 0.5f) * (1.0f / 16777216.0f));  // Exp(1)
-        }
+        else q = philox_exp1(gi, seed);                          // Exp(1)
         k = w / q;                                               // multinomial: topk(w / q)
         atomicAdd(&s_cnt[arg[e]], 1);
       }
@@ -182,17 +204,32 @@ __device__ __forceinline__ void find_bin_from_top(const int* s_hist, int k, int*
 // (one vectorised pass over the scan's arg-max bytes; a class holds ~HW/C of the pixels), and
 // the three radix passes then run from shared memory.  A class with more candidates than the
 // buffer holds (kSelSmemKeys) falls back to re-reading global memory in every pass.
-constexpr int kSelSmemKeys = 9984;    // 39 KB of keys + 8 KB histogram < 48 KB: 4 CTAs per SM
+//
+// Exactness.  The fast keys of S1 carry the device's logf / expf errors (a few 1e-7 relative), so
+// a key next to the k-th one could land on the other side of it than under the oracle's
+// correctly rounded rule.  After the radix select, every candidate whose fast key lies within
+// kSelGuard (relative) of the fast threshold -- the threshold's own pixel and, rarely, a
+// neighbour -- is re-evaluated under that rule (rounded_rule_key), its stored key is replaced,
+// and the threshold becomes the r-th largest exact key of the band, r = k - #{keys above the
+// band}.  Keys outside the band are more than 100 error bounds away from the threshold, so the
+// selection of S3 is the oracle's, bit for bit.
+constexpr int kSelSmemKeys = 6144;    // 24 KB keys + 24 KB pixel ids + 8 KB histogram: 4 CTAs per SM
+constexpr int kSelBandCap = 256;      // band candidates re-evaluated per (scan, class)
+constexpr float kSelGuard = 6.1035156e-05f;   // 2^-14 >> the fast keys' error (<= ~1e-5 worst case)
 __global__ void __launch_bounds__(512)
-select_threshold_kernel(const uint8_t* __restrict__ pseudo, const float* __restrict__ key,
+select_threshold_kernel(const uint8_t* __restrict__ pseudo, float* __restrict__ key,
                         const int32_t* __restrict__ count, const int32_t* __restrict__ present,
                         int HW, int C, int ignore_cls, float select_ratio,
-                        uint32_t* __restrict__ thr) {
+                        const float* __restrict__ probs, const float* __restrict__ noise,
+                        unsigned long long seed, uint32_t* __restrict__ thr, int32_t* __restrict__ flags) {
   __shared__ int s_hist[2048];
   __shared__ int s_scan[16];
   __shared__ int s_out[2];
-  __shared__ int s_n;
+  __shared__ int s_n, s_above, s_nb;
+  __shared__ int s_bpix[kSelBandCap];
+  __shared__ float s_bkey[kSelBandCap];
   extern __shared__ uint32_t s_keys[];
+  uint32_t* s_pix = s_keys + kSelSmemKeys;
   const int b = blockIdx.x / C, c = blockIdx.x % C;
   const int cnt = count[blockIdx.x];
   // select_num = int(cls_mask.sum() * select_ratio): int64 0-dim tensor times a Python
@@ -222,13 +259,16 @@ select_threshold_kernel(const uint8_t* __restrict__ pseudo, const float* __restr
           if (((w[q] - 0x01010101u) & ~w[q] & 0x80808080u) != 0u) {
 #pragma unroll
             for (int e = 0; e < 4; ++e)
-              if (((w[q] >> (8 * e)) & 0xFFu) == 0u) s_keys[atomicAdd(&s_n, 1)] = kb[i * 16 + q * 4 + e];
+              if (((w[q] >> (8 * e)) & 0xFFu) == 0u) {
+                const int at = atomicAdd(&s_n, 1), pix = i * 16 + q * 4 + e;
+                s_keys[at] = kb[pix]; s_pix[at] = pix;
+              }
           }
         }
       }
     } else {
       for (int i = threadIdx.x; i < HW; i += blockDim.x)
-        if (ps[i] == (uint8_t)c) s_keys[atomicAdd(&s_n, 1)] = kb[i];
+        if (ps[i] == (uint8_t)c) { const int at = atomicAdd(&s_n, 1); s_keys[at] = kb[i]; s_pix[at] = i; }
     }
     __syncthreads();
   }
@@ -265,7 +305,45 @@ select_threshold_kernel(const uint8_t* __restrict__ pseudo, const float* __restr
     prefix_mask |= bmask << sh;
     __syncthreads();
   }
-  if (threadIdx.x == 0) thr[blockIdx.x] = prefix;  // bits of the k0-th largest key
+  // ---- guard band around the fast threshold `prefix` (bits of the k0-th largest fast key)
+  const float t_fast = __uint_as_float(prefix);
+  const float lo = t_fast * (1.0f - kSelGuard), hi = t_fast * (1.0f + kSelGuard);
+  if (threadIdx.x == 0) { s_above = 0; s_nb = 0; }
+  __syncthreads();
+  int above = 0;
+  auto visit = [&](uint32_t bits, int pix) {
+    const float v = __uint_as_float(bits);
+    if (v > hi) ++above;
+    else if (v >= lo) { const int at = atomicAdd(&s_nb, 1); if (at < kSelBandCap) s_bpix[at] = pix; }
+  };
+  if (in_smem) {
+    for (int i = threadIdx.x; i < n_keys; i += blockDim.x) visit(s_keys[i], (int)s_pix[i]);
+  } else {
+    for (int i = threadIdx.x; i < HW; i += blockDim.x) if (ps[i] == (uint8_t)c) visit(kb[i], i);
+  }
+  above = __reduce_add_sync(0xffffffffu, above);
+  if ((threadIdx.x & 31) == 0 && above) atomicAdd(&s_above, above);
+  __syncthreads();
+  const int nb = s_nb, r = k0 - s_above;      // 1 <= r <= nb: the fast threshold is in the band
+  if (nb > kSelBandCap) {                     // a pile-up of (near-)equal keys: keep the fast threshold
+    if (threadIdx.x == 0) { thr[blockIdx.x] = prefix; atomicOr(flags, 1); }
+    return;
+  }
+  if ((int)threadIdx.x < nb) {
+    const int pix = s_bpix[threadIdx.x];
+    const size_t gi = (size_t)b * HW + pix;
+    const float q = noise ? noise[((size_t)b * C + c) * HW + pix] : philox_exp1(gi, seed);
+    const float kx = rounded_rule_key(probs + (size_t)b * C * HW, pix, HW, C, q);
+    s_bkey[threadIdx.x] = kx;
+    key[gi] = kx;
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < nb) {
+    const float mine = s_bkey[threadIdx.x];
+    int gt = 0, ge = 0;
+    for (int j = 0; j < nb; ++j) { gt += s_bkey[j] > mine; ge += s_bkey[j] >= mine; }
+    if (gt < r && r <= ge) thr[blockIdx.x] = __float_as_uint(mine);   // ties write the same bits
+  }
 }
 
 // ---------------------------------------------------------------- S3 -------
@@ -315,6 +393,7 @@ extern "C" int c3d_entropy_select_batch(
   const int HW = (int)HWll, B = batch, C = n_classes;
   SelWs w = carve_sel(workspace, B, C, HW);
   C3D_CUDA(cudaMemsetAsync(w.count, 0, (size_t)((char*)w.thr - (char*)w.count), stream));  // count + present
+  C3D_CUDA(cudaMemsetAsync(w.flags, 0, 4, stream));
   int rc;
   {
     KernelTimer kt__("select_prepare_kernel", stream);
@@ -333,9 +412,11 @@ extern "C" int c3d_entropy_select_batch(
   if ((rc = check_launch("select_prepare_kernel"))) return rc;
   {
     KernelTimer kt__("select_threshold_kernel", stream);
-    const size_t smem = (size_t)kSelSmemKeys * sizeof(uint32_t);   // 39 KB: no opt-in needed
+    const size_t smem = (size_t)kSelSmemKeys * 2 * sizeof(uint32_t);   // 48 KB + 11 KB static: opt-in
+    C3D_CUDA(cudaFuncSetAttribute(select_threshold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     select_threshold_kernel<<<B * C, 512, smem, stream>>>(w.pseudo, w.key, w.count, w.present, HW, C,
-                                                          ignore_cls, select_ratio, w.thr);
+                                                          ignore_cls, select_ratio, probs, noise, seed, w.thr,
+                                                          w.flags);
   }
   if ((rc = check_launch("select_threshold_kernel"))) return rc;
   {

@@ -7,12 +7,36 @@ tests/golden/make_golden.py), so the oracle takes the draws as input: `noise[b, 
 (H*W,) vector the reference would draw in iteration (b, cls).  Rule fixed where the
 reference is undefined: among keys equal to the k-th largest all are selected (torch.topk
 picks arbitrarily); with continuous noise ties do not occur.
+
+Transcendentals.  torch's CPU `log` / `exp` are vectorised routines that are not correctly
+rounded and differ between machines and builds, so a key that lies within a few ulp of the
+(scan, class) threshold can fall on either side of it depending on where the reference runs.
+`rule="rounded"` (the default, and the rule the device implements bit for bit) therefore fixes
+every float32 operation of :459-466 as the correctly rounded one, in the reference's order:
+x = p + 1e-10, l = log(x), t = p * l, sum over classes c = 0..C-1 sequentially, w = exp(sum),
+key = w / q.  `rule="torch"` evaluates the reference's literal torch statements; the golden
+vectors pin it exactly, and pin `rounded` everywhere except at pixels whose key is within
+1e-5 (relative) of the threshold, which is where the reference itself is machine dependent.
 """
+import numpy as np
 import torch
 
 
+def entropy_weights_rounded(output):
+    """exp(-entropy) of (B,C,H,W) probabilities with every float32 operation correctly rounded
+    (float64 log / exp rounded once to float32; sequential float32 sum over the classes)."""
+    p = output.numpy().astype(np.float32)
+    x = (p + np.float32(1e-10)).astype(np.float32)
+    l = np.log(x.astype(np.float64)).astype(np.float32)
+    t = (p * l).astype(np.float32)
+    acc = np.zeros((p.shape[0],) + p.shape[2:], dtype=np.float32)
+    for c in range(p.shape[1]):
+        acc = (acc + t[:, c]).astype(np.float32)
+    return torch.from_numpy(np.exp(acc.astype(np.float64)).astype(np.float32))
+
+
 def entropy_based_selection(output, wss_mask, eval_mask, train_label, select_ratio, ignore_cls,
-                            noise):
+                            noise, rule="rounded"):
     """output (B,C,H,W) probs; wss_mask / eval_mask (B,H,W) bool; train_label (B,H,W) int64;
     noise (B,C,H*W) Exp(1) draws.  Returns (pseudo_label int64, new_wss_mask bool, keys, thr):
     keys (B,H*W) and thr {(b,cls): k-th largest key} let a checker identify near-threshold pixels."""
@@ -20,6 +44,10 @@ def entropy_based_selection(output, wss_mask, eval_mask, train_label, select_rat
     entropy = -torch.sum(output * torch.log(output + 1e-10), dim=1)          # :459-461
     _, pseudo_label = torch.max(output, dim=1)                                # :463
     entropy_weights = torch.exp(-1 * entropy)                                 # :466
+    if rule == "rounded":
+        entropy_weights = entropy_weights_rounded(output)
+    else:
+        assert rule == "torch"
     pseudo_label = pseudo_label.clone()
     pseudo_label[eval_mask == False] = ignore_cls                             # noqa: E712  :469
     low_entropy_mask = torch.zeros(bs, C, h, w).bool()
