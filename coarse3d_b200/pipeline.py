@@ -19,9 +19,9 @@ class StepInputs:
     """One set of resident inputs for a batch of `batch` scans of `shape`."""
 
     def __init__(self, shape: synth.ScanShape, batch, dim, sub_protos, seed0, device,
-                 feats=None, share_probs=None):
+                 feats=None, share_probs=None, sensor_order=False):
         self.shape, self.batch, self.dim = shape, batch, dim
-        pts, offs, _full, weak = synth.make_batch(shape, batch, seed0)
+        pts, offs, _full, weak = synth.make_batch(shape, batch, seed0, sensor_order=sensor_order)
         H, W, C = shape.proj_h, shape.proj_w, shape.n_classes
         self.host_points, self.host_offsets, self.host_weak = pts, offs, weak
         self.points = torch.from_numpy(pts).to(device)
@@ -56,7 +56,7 @@ class HotPathStep:
 
     def __init__(self, shape, batch, dim=128, sub_protos=20, num_anchor=512, temperature=0.07,
                  momentum=0.999, n_sets=3, seed0=1000, device="cuda", group=None,
-                 knn=(5, 5, 1.0, 1.0), concurrent=True, parts=None, bank_seed=7):
+                 knn=(5, 5, 1.0, 1.0), concurrent=True, parts=None, bank_seed=7, sensor_order=False):
         self.shape, self.batch, self.dim, self.M = shape, batch, dim, sub_protos
         self.device, self.group = torch.device(device), group
         self.knn_k, self.knn_s, self.knn_sigma, self.knn_cutoff = knn
@@ -66,7 +66,8 @@ class HotPathStep:
         self.momentum = momentum
         self.sets = []
         for i in range(n_sets):
-            self.sets.append(StepInputs(shape, batch, dim, sub_protos, seed0 + 100 * i, self.device))
+            self.sets.append(StepInputs(shape, batch, dim, sub_protos, seed0 + 100 * i, self.device,
+                                        sensor_order=sensor_order))
         n = self.sets[0].n_points
         assert all(s.n_points == n for s in self.sets)
         self.n_points = n
