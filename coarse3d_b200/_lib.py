@@ -73,6 +73,15 @@ def _load():
         "c3d_proto_ema_apply": (c_int, [P, P, c_int, c_int, c_int, c_int, c_double, P, P, P, P]),
         "c3d_proto_ema_info": (c_int, [P, P, P]),
         "c3d_proto_bank_normalise": (c_int, [P, c_int, c_int, P, P]),
+        "c3d_peer_exchange_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+        "c3d_peer_state_bytes": (c_size_t, [c_int, c_int]),
+        "c3d_peer_alloc": (c_int, [c_size_t, P]),
+        "c3d_peer_free": (c_int, [P]),
+        "c3d_peer_export": (c_int, [P, P]),
+        "c3d_peer_import": (c_int, [P, P]),
+        "c3d_peer_close": (c_int, [P]),
+        "c3d_proto_ema_apply_peers": (c_int, [P, P, P, c_int, c_int, P, c_int, c_int, c_int, c_int, c_double,
+                                              P, P, P, c_double, P]),
         "c3d_proto_step_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int, c_int64]),
         "c3d_proto_step": (c_int, [P, P, P, P, P, P, P, P, P, c_float, c_int, c_int, c_int, c_int, c_int, c_int,
                                    c_int, c_float, c_float, c_int, P, c_int, P, c_int, c_uint64, c_int64, c_int,

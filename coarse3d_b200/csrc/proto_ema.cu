@@ -20,6 +20,7 @@
 //                    [K*D sums | K counts] buffer, the all-reduce payload
 //   E5 ema_apply     normalise sums, EMA where count != 0, renormalise (:379-394)
 #include <math_constants.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "labelsplit.cuh"
@@ -650,6 +651,59 @@ ema_assign_sum_kernel(const int32_t* __restrict__ seg_cnt, const int32_t* __rest
 }
 
 // ---------------------------------------------------------------- E5 -------
+// One bank row (warp): normalise the summed features, EMA where the sub-prototype received rows,
+// renormalise; `f` holds the row's summed features, lane-strided (f[j] = element lane + 32 j).
+constexpr int kApplyDJ = 16;   // D <= 512
+__device__ __forceinline__ void ema_apply_row(const float* protos_in, const float (&f)[kApplyDJ], bool update,
+                                              int k, int D, float mom, float one_minus_mom, float* protos_out,
+                                              float* __restrict__ normalised_out) {
+  const int lane = threadIdx.x & 31;
+  const float* old = protos_in + (size_t)k * D;
+  float o2 = 0.f, f2 = 0.f;
+#pragma unroll
+  for (int j = 0; j < kApplyDJ; ++j) {
+    const int d = lane + 32 * j;
+    if (d < D) { o2 += old[d] * old[d]; f2 += f[j] * f[j]; }
+  }
+  const float oinv = 1.0f / fmaxf(sqrtf(warp_sum(o2)), 1e-12f);  // prototypes <- l2norm (:502)
+  const float finv = 1.0f / fmaxf(sqrtf(warp_sum(f2)), 1e-12f);  // f = normalize(f) (:380)
+  float v[kApplyDJ];
+  float n2 = 0.f;
+#pragma unroll
+  for (int j = 0; j < kApplyDJ; ++j) {
+    const int d = lane + 32 * j;
+    v[j] = 0.f;
+    if (d < D) {
+      float t = old[d] * oinv;
+      if (update) t = mom * t + one_minus_mom * (f[j] * finv);     // momentum_update (:19-31)
+      v[j] = t;
+      n2 += t * t;
+    }
+  }
+  const float ninv = 1.0f / fmaxf(sqrtf(warp_sum(n2)), 1e-12f);    // l2_normalize(protos) (:394)
+  float m2 = 0.f;
+#pragma unroll
+  for (int j = 0; j < kApplyDJ; ++j) {
+    const int d = lane + 32 * j;
+    if (d < D) {
+      v[j] = v[j] * ninv;
+      protos_out[(size_t)k * D + d] = v[j];
+      m2 += v[j] * v[j];
+    }
+  }
+  if (normalised_out) {
+    // F.normalize / l2_normalize of the stored bank, as its readers apply it: the loss on this
+    // bank (contrast_pixel_loss.py:167) and the next step's similarity pre-step
+    // (salsanext_proto.py:502) -- the same arithmetic as the stand-alone normalise kernels
+    const float inv2 = 1.0f / fmaxf(sqrtf(warp_sum(m2)), 1e-12f);
+#pragma unroll
+    for (int j = 0; j < kApplyDJ; ++j) {
+      const int d = lane + 32 * j;
+      if (d < D) normalised_out[(size_t)k * D + d] = v[j] * inv2;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256)
 ema_apply_kernel(const float* protos_in, const float* __restrict__ packed, int C, int M,
                  int D, int ignore_label, float mom, float one_minus_mom,
@@ -666,34 +720,147 @@ ema_apply_kernel(const float* protos_in, const float* __restrict__ packed, int C
   for (int m = lane; m < M; m += 32) csum += cnt[c * M + m];
   csum = warp_sum(csum);
   const bool update = (c != ignore_label) && (csum > 0.f) && (cnt[k] != 0.f);  // :379,383
-  const float* old = protos_in + (size_t)k * D;
-  const float* f = packed + (size_t)k * D;
-  float o2 = 0.f, f2 = 0.f;
-  for (int d = lane; d < D; d += 32) { o2 += old[d] * old[d]; f2 += f[d] * f[d]; }
-  const float oinv = 1.0f / fmaxf(sqrtf(warp_sum(o2)), 1e-12f);  // prototypes <- l2norm (:502)
-  const float finv = 1.0f / fmaxf(sqrtf(warp_sum(f2)), 1e-12f);  // f = normalize(f) (:380)
-  float n2 = 0.f;
-  for (int d = lane; d < D; d += 32) {
-    float v = old[d] * oinv;
-    if (update) v = mom * v + one_minus_mom * (f[d] * finv);       // momentum_update (:19-31)
-    n2 += v * v;
+  float f[kApplyDJ];
+#pragma unroll
+  for (int j = 0; j < kApplyDJ; ++j) {
+    const int d = lane + 32 * j;
+    f[j] = d < D ? packed[(size_t)k * D + d] : 0.f;
   }
-  const float ninv = 1.0f / fmaxf(sqrtf(warp_sum(n2)), 1e-12f);    // l2_normalize(protos) (:394)
-  float m2 = 0.f;
-  for (int d = lane; d < D; d += 32) {
-    float v = old[d] * oinv;
-    if (update) v = mom * v + one_minus_mom * (f[d] * finv);
-    const float o = v * ninv;
-    protos_out[(size_t)k * D + d] = o;
-    m2 += o * o;
+  ema_apply_row(protos_in, f, update, k, D, mom, one_minus_mom, protos_out, normalised_out);
+}
+
+// ------------------------------------------------------- E5 over peer memory -------
+// The multi-GPU form of E5 WITHOUT a collective call: the all-reduce of the 206 kB payload and
+// the EMA are one kernel, in the style of a low-latency ("LL") collective protocol.  Every rank
+// owns a peer-visible exchange buffer of 2 (parities) x world slots x payload x {value, flag}
+// pairs (c3d_peer_alloc, opened by the other ranks through CUDA IPC).  Per step s (a device
+// counter, so captured graphs replay correctly), parity p = s & 1, flag value s + 1:
+//   A  PUSH: all CTAs store their slice of the local payload as 8-byte {value, s + 1} pairs into
+//      slot [p][rank] of EVERY rank's buffer (posted remote stores over NVLink: no round trip,
+//      no fence, no separate flag -- an aligned 8-byte store arrives whole);
+//   D  each warp polls, in its OWN buffer, the pairs of its bank row in all `world` slots until
+//      their flags read s + 1 (bounded: a missing peer sets an error word instead of hanging the
+//      GPU), sums the values in rank order 0..W-1 -- the same order on every rank, so the banks
+//      stay bit-identical -- writes the sum back to the local payload and applies the EMA;
+//   E  the last CTA to finish advances s.
+// Slot [p][r] is rewritten by rank r at step s + 2, which r reaches only after its step s + 1
+// consumed THIS rank's step s + 1 push, issued after this rank finished reading step s.
+constexpr int kMaxPeers = 8;
+struct PeerPtrs { float2* buf[kMaxPeers]; };
+
+__device__ __forceinline__ float2 ld_pair(const float2* p) {
+  float2 v;
+  asm volatile("ld.volatile.global.v2.f32 {%0, %1}, [%2];\n" : "=f"(v.x), "=f"(v.y) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_pair(float2* p, float v, unsigned flag) {
+  asm volatile("st.volatile.global.v2.f32 [%0], {%1, %2};\n" :: "l"(p), "f"(v), "f"(__uint_as_float(flag)) : "memory");
+}
+
+// values of payload element `i` from all ranks, summed in rank order (polls until every flag is there)
+__device__ __forceinline__ float peer_sum(const float2* mine_par, size_t slot_pairs, size_t i, int world,
+                                          unsigned flagv, long long t0, long long spin_limit, int32_t* err) {
+  float2 v[kMaxPeers];
+  unsigned pending = 0;
+#pragma unroll
+  for (int r = 0; r < kMaxPeers; ++r)
+    if (r < world) { v[r] = ld_pair(mine_par + r * slot_pairs + i); if (__float_as_uint(v[r].y) != flagv) pending |= 1u << r; }
+  while (pending) {
+    if (clock64() - t0 > spin_limit) { atomicOr(err, (int)pending); break; }
+#pragma unroll
+    for (int r = 0; r < kMaxPeers; ++r)
+      if (pending & (1u << r)) {
+        v[r] = ld_pair(mine_par + r * slot_pairs + i);
+        if (__float_as_uint(v[r].y) == flagv) pending &= ~(1u << r);
+      }
   }
-  if (normalised_out) {
-    // F.normalize / l2_normalize of the stored bank, as its readers apply it: the loss on this
-    // bank (contrast_pixel_loss.py:167) and the next step's similarity pre-step
-    // (salsanext_proto.py:502) -- the same arithmetic as the stand-alone normalise kernels
-    const float inv2 = 1.0f / fmaxf(sqrtf(warp_sum(m2)), 1e-12f);
-    for (int d = lane; d < D; d += 32)   // this lane stored the element just above (in-place safe)
-      normalised_out[(size_t)k * D + d] = protos_out[(size_t)k * D + d] * inv2;
+  float t = 0.f;
+#pragma unroll
+  for (int r = 0; r < kMaxPeers; ++r) if (r < world) t += v[r].x;
+  return t;
+}
+
+__global__ void __launch_bounds__(256)
+ema_apply_peers_kernel(const float* protos_in, float* __restrict__ packed, PeerPtrs peers, int rank, int world,
+                       size_t slot_pairs /* pairs per (parity, rank) slot, padded */, int32_t* __restrict__ state,
+                       int C, int M, int D, int ignore_label, float mom, float one_minus_mom,
+                       float* protos_out, float* __restrict__ normalised_out,
+                       unsigned long long* __restrict__ seed_counter, long long spin_limit) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int K = C * M;
+  const size_t n_payload = (size_t)K * D + K;
+  const unsigned step = *reinterpret_cast<volatile unsigned*>(&state[0]);
+  const unsigned par = step & 1u, flagv = step + 1u;
+  if (seed_counter && blockIdx.x == 0 && threadIdx.x == 0) seed_counter[1] += 1;
+  const long long t0 = clock64();
+  // A: push this CTA's rows (the ones it will reduce itself first, so that every rank's early
+  //    CTAs feed every rank's early CTAs) and the counts
+  const size_t slot_off = ((size_t)par * world + rank) * slot_pairs;
+  {
+    const size_t lo = (size_t)blockIdx.x * 8 * D, hi = min((size_t)(blockIdx.x + 1) * 8 * D, (size_t)K * D);
+    for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+      const float v = packed[i];
+      for (int r = 0; r < world; ++r) st_pair(peers.buf[r] + slot_off + i, v, flagv);
+    }
+    if (blockIdx.x == 0)
+      for (size_t i = (size_t)K * D + threadIdx.x; i < n_payload; i += blockDim.x) {
+        const float v = packed[i];
+        for (int r = 0; r < world; ++r) st_pair(peers.buf[r] + slot_off + i, v, flagv);
+      }
+  }
+  // the local payload is overwritten with the sums below: every thread of this CTA must have
+  // read its part first (rows are CTA-private; the counts are read by CTA 0 only, written by all)
+  __syncthreads();
+  // D: sum over the ranks in rank order, write the sum back, apply the EMA
+  const float2* mine_par = peers.buf[rank] + (size_t)par * world * slot_pairs;
+  const int k = blockIdx.x * 8 + warp;
+  if (k < K) {
+    const int c = k / M;
+    float csum = 0.f, cnt_k = 0.f;
+    for (int m = lane; m < M; m += 32) {
+      const float t = peer_sum(mine_par, slot_pairs, (size_t)K * D + c * M + m, world, flagv, t0, spin_limit, &state[3]);
+      csum += t;
+      if (c * M + m == k) cnt_k = t;
+    }
+    csum = warp_sum(csum);
+    cnt_k = warp_sum(cnt_k);     // exactly one lane holds it, the others add zeros
+    float f[kApplyDJ];
+#pragma unroll
+    for (int j = 0; j < kApplyDJ; ++j) {
+      const int d = lane + 32 * j;
+      f[j] = 0.f;
+      if (d < D) f[j] = peer_sum(mine_par, slot_pairs, (size_t)k * D + d, world, flagv, t0, spin_limit, &state[3]);
+    }
+    const bool update = (c != ignore_label) && (csum > 0.f) && (cnt_k != 0.f);  // :379,383
+    ema_apply_row(protos_in, f, update, k, D, mom, one_minus_mom, protos_out, normalised_out);
+    // the summed payload back into `packed` (what an all-reduce would have left there); the counts
+    // are written after EVERY CTA has pushed them (ticket below), the rows are CTA-private
+#pragma unroll
+    for (int j = 0; j < kApplyDJ; ++j) {
+      const int d = lane + 32 * j;
+      if (d < D) packed[(size_t)k * D + d] = f[j];
+    }
+    if (lane == 0) state[4 + k] = __float_as_int(cnt_k);
+  }
+  // E: the last CTA to finish (every CTA has pushed and reduced by then) writes the summed counts,
+  //    re-arms the ticket and advances the step
+  __shared__ int s_last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_last = atomicAdd(&state[1], 1) == (int)gridDim.x - 1;
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    for (int i = threadIdx.x; i < K; i += blockDim.x)
+      packed[(size_t)K * D + i] = __int_as_float(*reinterpret_cast<volatile int*>(&state[4 + i]));
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      state[1] = 0;
+      __threadfence();
+      *reinterpret_cast<volatile unsigned*>(&state[0]) = step + 1u;
+    }
   }
 }
 
@@ -845,7 +1012,7 @@ extern "C" int c3d_proto_ema_apply(const float* prototypes_in, const float* pack
                                    void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   C3D_REQUIRE(prototypes_in && packed && prototypes_out, "null pointer argument");
-  C3D_REQUIRE(n_classes >= 2 && sub_protos > 0 && dim > 0, "bad prototype shape");
+  C3D_REQUIRE(n_classes >= 2 && sub_protos > 0 && dim > 0 && dim <= 32 * kApplyDJ, "bad prototype shape (dim <= %d)", 32 * kApplyDJ);
   const int K = n_classes * sub_protos;
   // weak-scalar rounding of the reference: momentum and (1 - momentum) are Python
   // floats multiplied into float32 tensors (salsanext_proto.py:20)
@@ -854,6 +1021,68 @@ extern "C" int c3d_proto_ema_apply(const float* prototypes_in, const float* pack
                                                     (float)(1.0 - momentum), prototypes_out, normalised_out,
                                                     reinterpret_cast<unsigned long long*>(seed_counter)); }
   return check_launch("ema_apply_kernel");
+}
+
+// ---- peer exchange: buffer management (explicit, outside the hot path) and the fused kernel
+static size_t peer_slot_pairs(int K, int D) { return (((size_t)K * D + K) + 63) & ~(size_t)63; }
+
+extern "C" size_t c3d_peer_exchange_bytes(int n_classes, int sub_protos, int dim, int world) {
+  if (n_classes < 2 || sub_protos <= 0 || dim <= 0 || world < 1 || world > kMaxPeers) return 0;
+  return 2 * (size_t)world * peer_slot_pairs(n_classes * sub_protos, dim) * sizeof(float2);
+}
+
+extern "C" size_t c3d_peer_state_bytes(int n_classes, int sub_protos) {
+  if (n_classes < 2 || sub_protos <= 0) return 0;
+  return (size_t)(4 + n_classes * sub_protos) * sizeof(int32_t);
+}
+
+extern "C" int c3d_peer_alloc(size_t bytes, void** ptr) {
+  C3D_REQUIRE(ptr && bytes > 0, "bad argument");
+  C3D_CUDA(cudaMalloc(ptr, bytes));           // a dedicated allocation: IPC handles export whole allocations
+  C3D_CUDA(cudaMemset(*ptr, 0, bytes));
+  C3D_CUDA(cudaDeviceSynchronize());
+  return C3D_OK;
+}
+extern "C" int c3d_peer_free(void* ptr) { C3D_CUDA(cudaFree(ptr)); return C3D_OK; }
+extern "C" int c3d_peer_export(void* ptr, unsigned char* handle64) {
+  C3D_REQUIRE(ptr && handle64, "null pointer argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  cudaIpcMemHandle_t h;
+  C3D_CUDA(cudaIpcGetMemHandle(&h, ptr));
+  memcpy(handle64, &h, 64);
+  return C3D_OK;
+}
+extern "C" int c3d_peer_import(const unsigned char* handle64, void** ptr) {
+  C3D_REQUIRE(ptr && handle64, "null pointer argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  C3D_CUDA(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return C3D_OK;
+}
+extern "C" int c3d_peer_close(void* ptr) { C3D_CUDA(cudaIpcCloseMemHandle(ptr)); return C3D_OK; }
+
+extern "C" int c3d_proto_ema_apply_peers(const float* prototypes_in, float* packed, void* const* peer_bufs,
+                                         int rank, int world, int32_t* state, int n_classes, int sub_protos,
+                                         int dim, int ignore_label, double momentum, float* prototypes_out,
+                                         float* normalised_out, uint64_t* seed_counter, double timeout_s,
+                                         void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  C3D_REQUIRE(prototypes_in && packed && prototypes_out && peer_bufs && state, "null pointer argument");
+  C3D_REQUIRE(n_classes >= 2 && sub_protos > 0 && dim > 0 && dim <= 32 * kApplyDJ, "bad prototype shape (dim <= %d)", 32 * kApplyDJ);
+  C3D_REQUIRE(world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world, "rank / world out of range (<= %d ranks)", kMaxPeers);
+  const int K = n_classes * sub_protos;
+  PeerPtrs pp{};
+  for (int r = 0; r < world; ++r) {
+    C3D_REQUIRE(peer_bufs[r] != nullptr, "peer buffer %d is null", r);
+    pp.buf[r] = reinterpret_cast<float2*>(peer_bufs[r]);
+  }
+  const long long spin = (long long)((timeout_s > 0 ? timeout_s : 2.0) * 1.9e9);   // SM clocks
+  { KernelTimer kt__("ema_apply_peers_kernel", stream);
+    ema_apply_peers_kernel<<<(K + 7) / 8, 256, 0, stream>>>(
+        prototypes_in, packed, pp, rank, world, peer_slot_pairs(K, dim), state, n_classes, sub_protos, dim,
+        ignore_label, (float)momentum, (float)(1.0 - momentum), prototypes_out, normalised_out,
+        reinterpret_cast<unsigned long long*>(seed_counter), spin); }
+  return check_launch("ema_apply_peers_kernel");
 }
 
 extern "C" int c3d_proto_bank_normalise(const float* prototypes, int rows, int dim, float* normalised_out,

@@ -45,6 +45,86 @@ def allreduce_packed(packed: torch.Tensor, group=None, async_op=False):
     return dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
 
 
+class PeerExchange:
+    """The all-reduce of the packed prototype sums fused with the EMA into ONE kernel over peer
+    memory (c3d_proto_ema_apply_peers; NVLink / NVSwitch P2P loads and stores, no collective call
+    on the step's critical path).  Set-up (once, collective over `group`): every rank allocates
+    an exchange buffer, the CUDA IPC handles travel through torch.distributed, every rank maps
+    the others' buffers.  Afterwards `apply()` is device-side only and can be captured in a CUDA
+    graph.  Ranks must live on one node; all ranks must call `apply` the same number of times."""
+
+    def __init__(self, n_classes, sub_protos, dim, device, group=None, timeout_s=2.0):
+        import ctypes
+        from ._lib import check, lib
+        self.lib, self.check, self.group = lib, check, group
+        self.rank, self.world = world(group)
+        self.shape = (n_classes, sub_protos, dim)
+        self.timeout_s = float(timeout_s)
+        self.device = torch.device(device)
+        with torch.cuda.device(self.device):
+            nbytes = lib.c3d_peer_exchange_bytes(n_classes, sub_protos, dim, self.world)
+            if nbytes == 0:
+                raise ValueError("peer exchange: bad shape or more than 8 ranks")
+            own = ctypes.c_void_p()
+            check(lib.c3d_peer_alloc(nbytes, ctypes.byref(own)))
+            self._own = own
+            handle = ctypes.create_string_buffer(64)
+            check(lib.c3d_peer_export(own, handle))
+            handles = [None] * self.world
+            if self.world > 1:
+                dist.all_gather_object(handles, handle.raw, group=group)
+            else:
+                handles[0] = handle.raw
+            self._mapped = []
+            ptrs = (ctypes.c_void_p * self.world)()
+            for r, h in enumerate(handles):
+                if r == self.rank:
+                    ptrs[r] = own.value
+                    continue
+                q = ctypes.c_void_p()
+                check(lib.c3d_peer_import(ctypes.create_string_buffer(h, 64), ctypes.byref(q)))
+                self._mapped.append(q)
+                ptrs[r] = q.value
+            self._ptrs = ptrs
+            self.state = torch.zeros(lib.c3d_peer_state_bytes(n_classes, sub_protos) // 4, dtype=torch.int32,
+                                     device=self.device)
+        if self.world > 1:
+            dist.barrier(group=group)      # every buffer is mapped everywhere before the first use
+
+    def apply(self, prototypes, packed, momentum, ignore_label=0, out=None, normalised_out=None,
+              seed_counters=None):
+        """sum `packed` over the ranks (left in `packed`) and apply the EMA: the multi-GPU
+        c3d_proto_ema_apply.  Bit-identical banks on every rank."""
+        from .ops import _need_cuda, _p, _stream
+        _need_cuda(prototypes=prototypes, packed=packed)
+        C, M, D = prototypes.shape
+        if (C, M, D) != self.shape or packed.numel() != C * M * D + C * M or packed.dtype != torch.float32:
+            raise ValueError("bank / payload shape differs from the exchange buffer's")
+        if out is None:
+            out = torch.empty_like(prototypes)
+        self.check(self.lib.c3d_proto_ema_apply_peers(
+            _p(prototypes), _p(packed), self._ptrs, self.rank, self.world, _p(self.state), C, M, D,
+            int(ignore_label), float(momentum), _p(out), _p(normalised_out), _p(seed_counters),
+            self.timeout_s, _stream()))
+        return out
+
+    def errors(self):
+        """Bit r set: rank r's payload did not arrive within the timeout in some call (host sync)."""
+        return int(self.state[3].item())
+
+    def close(self):
+        if getattr(self, "_own", None) is None:
+            return
+        torch.cuda.synchronize(self.device)
+        if self.world > 1:
+            dist.barrier(group=self.group)   # nobody still reads a buffer that is about to go away
+        with torch.cuda.device(self.device):
+            for q in self._mapped:
+                self.lib.c3d_peer_close(q)
+            self.lib.c3d_peer_free(self._own)
+        self._own, self._mapped = None, []
+
+
 def prototype_update(embedding, label, prototypes, ln_d_w, ln_d_b, ln_c_w, ln_c_b, momentum,
                      ignore_label=0, gumbel=None, assign_mode=None, seed=None, max_rows=None,
                      want_target=False, group=None, workspace=None, packed=None, out=None, sync="sum"):

@@ -130,6 +130,11 @@ class HotPathStep:
         kar = _os.environ.get("C3D_KNN_AFTER_ROWS", "auto")
         self.knn_after_rows = (batch >= 20) if kar == "auto" else kar == "1"
         self.ev_rows = torch.cuda.Event()
+        # N > 1: the all-reduce of the packed sums fused with the EMA over peer memory (default),
+        # or ncclAllReduce + c3d_proto_ema_apply (C3D_PEER_EXCHANGE=0)
+        self.peer = None
+        if distributed.world(group)[1] > 1 and _os.environ.get("C3D_PEER_EXCHANGE", "1") == "1":
+            self.peer = distributed.PeerExchange(C, sub_protos, dim, self.device, group)
         self.knn_split = int(_os.environ.get("C3D_KNN_SPLIT", "0"))   # scans in the first of two KNN launches
         # schedule "fill_spread": fractions of the dense-gradient zero fill carried by the
         # projection's two passes, the label split, the EMA rows kernel and the loss rows kernel
@@ -428,10 +433,14 @@ class HotPathStep:
 
     def _ema_finish(self):
         """all-reduce of the packed sums (N > 1) + the EMA itself, in place on the bank"""
+        sc = self.seed_counters if self.device_seeds else None
+        if self.peer is not None:
+            self.peer.apply(self.protos, self.packed, self.momentum, 0, out=self.protos,
+                            normalised_out=self.bank_n, seed_counters=sc)
+            return
         distributed.allreduce_packed(self.packed, self.group)
         ops.proto_ema_apply(self.protos, self.packed, self.momentum, 0, out=self.protos,
-                            normalised_out=self.bank_n,
-                            seed_counters=self.seed_counters if self.device_seeds else None)
+                            normalised_out=self.bank_n, seed_counters=sc)
 
     def _loss_fwd(self, s, seed, phases=3):
         ops.proto_loss_forward_raw(s.feats, s.probs, s.labels, s.keep_mask, self.protos, self.cfg,

@@ -407,6 +407,41 @@ int c3d_proto_ema_apply(
                                      [1] (the EMA's noise stream) is advanced here        */
     void* stream);
 
+/* Multi-GPU form of c3d_proto_ema_apply WITHOUT a collective call ("only the K x D
+ * prototype sums and counts combined ... so every rank applies an identical EMA update"): the
+ * all-reduce of `packed` and the EMA are ONE kernel over peer memory.  It replaces, for ranks of
+ * one NVLink / NVSwitch box, `dist.all_reduce(...)` of salsanext_proto.py:397-400 plus the EMA.
+ * Every rank owns an exchange buffer of c3d_peer_exchange_bytes() allocated by c3d_peer_alloc
+ * (a dedicated cudaMalloc, zeroed), exports it (c3d_peer_export -> 64-byte CUDA IPC handle, sent
+ * to the other processes by any means, e.g. torch.distributed.all_gather_object) and opens the
+ * others' (c3d_peer_import).  Per call each rank PUSHES its payload as 8-byte {value, step flag}
+ * pairs into its slot of every rank's buffer (posted NVLink stores: no fence, no round trip),
+ * then polls its own buffer until every rank's pairs carry this step's flag (bounded by
+ * timeout_s; a missing peer sets bit r of state[3] instead of hanging), sums the values in rank
+ * order 0..world-1 -- identical order, hence bit-identical banks, on every rank -- writes the
+ * sum back to `packed` and applies the EMA.  `state` = c3d_peer_state_bytes() of zero-initialised
+ * device memory ([0] step counter advanced by the kernel, so a captured CUDA graph replays
+ * correctly; [1] ticket; [3] error bits; then scratch).  All ranks must make the same sequence of
+ * calls; world <= 8 (one NVSwitch box). */
+size_t c3d_peer_exchange_bytes(int n_classes, int sub_protos, int dim, int world);
+size_t c3d_peer_state_bytes(int n_classes, int sub_protos);
+int c3d_peer_alloc(size_t bytes, void** ptr);
+int c3d_peer_free(void* ptr);
+int c3d_peer_export(void* ptr, unsigned char* handle64);
+int c3d_peer_import(const unsigned char* handle64, void** ptr);
+int c3d_peer_close(void* ptr);
+int c3d_proto_ema_apply_peers(
+    const float* prototypes_in,   /* [C, M, D]                                               */
+    float* packed,                /* [C*M*D + C*M] this rank's sums and counts; holds the sum
+                                     over ranks afterwards                                    */
+    void* const* peer_bufs,       /* HOST array [world]: every rank's exchange buffer as mapped
+                                     in this process (own buffer at index `rank`)             */
+    int rank, int world, int32_t* state,
+    int n_classes, int sub_protos, int dim, int ignore_label, double momentum,
+    float* prototypes_out, float* normalised_out, uint64_t* seed_counters,
+    double timeout_s,             /* spin bound per call (<= 0: 2 s)                         */
+    void* stream);
+
 /* -------------------------------------------------------- a2 + a3 fused ----
  * The prototype step of a training iteration: the EMA update inside model.forward
  * (salsanext_proto.py:520-527) followed by ContrastMEMLoss on the UPDATED bank

@@ -72,7 +72,27 @@ def _worker(rank, world, port, result):
             else:
                 want = sum(ops.proto_ema_apply(p0, a.packed, 0.9) / world for a in accs)
                 assert (new - want).abs().max() <= 1e-7, "average mode != mean of per-rank post-EMA banks"
-        # the step pipeline, all-reduce inside the captured graph
+        # the fused form: all-reduce + EMA as ONE kernel over peer memory (CUDA IPC, NVLink P2P)
+        px = distributed.PeerExchange(C, M, D, dev)
+        cur = p0.clone()
+        bank_n = torch.empty_like(cur)
+        want = p0.clone()
+        for it in range(5):                       # both buffer halves, several times
+            acc = ops.proto_ema_accumulate(emb, label, cur, *ln, assign_mode=ops.ASSIGN_ARGMAX)
+            mine = acc.packed.clone()
+            px.apply(cur, acc.packed, 0.9, out=cur, normalised_out=bank_n)
+            # reference: NCCL all-reduce of the same payload (2 ranks: a + b in either order) + apply
+            dist.all_reduce(mine)
+            assert torch.equal(acc.packed, mine), "peer sum != all-reduce sum (step %d)" % it
+            want = ops.proto_ema_apply(want, mine, 0.9)
+            assert torch.equal(cur, want), "peer-memory EMA != all-reduce + apply (step %d)" % it
+            assert torch.equal(bank_n, ops.bank_normalise(cur))
+        assert px.errors() == 0
+        banks = [torch.empty_like(cur) for _ in range(world)]
+        dist.all_gather(banks, cur)
+        assert all(torch.equal(b, banks[0]) for b in banks), "peer-memory banks differ across ranks"
+        px.close()
+        # the step pipeline, exchange inside the captured graph (peer memory by default)
         step = HotPathStep(synth.NUSCENES, 2, dim=32, sub_protos=4, num_anchor=16, n_sets=2,
                            seed0=500 + 10000 * rank, device=dev)
         for i in range(2):
@@ -87,10 +107,12 @@ def _worker(rank, world, port, result):
         losses = [torch.zeros((), device=dev) for _ in range(world)]
         dist.all_gather(losses, step.loss)
         assert not torch.equal(losses[0], losses[1])          # ranks really saw different scans
+        assert step.peer is not None and step.peer.errors() == 0
         if rank == 0:
             result["ok"] = True
             result["graphed"] = bool(graphed)
         step.graphs = None
+        step.peer.close()
         dist.barrier()
         torch.cuda.synchronize(dev)
     finally:
