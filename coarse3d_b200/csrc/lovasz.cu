@@ -19,17 +19,25 @@
 // per element, the larger keys of its class by all pairs (tiles broadcast from shared memory;
 // quadratic, 0.75 ms at P = 8.4k, so only the fallback) and lovasz_reduce sums the classes.
 // Keys are unique (they embed the pixel), so both paths give identical ranks, no atomics are
-// needed, and the result does not depend on the order of the compacted list.  More valid
-// pixels need a multi-CTA segmented radix sort, which is not built (overflow flag /
-// C3D_UNSUPPORTED).  Tie rule (torch.sort is unstable): equal errors rank by pixel index.
+// needed, and the result does not depend on the order of the compacted list.
+// Dense / pseudo-label regime (max_valid > 32768, up to 2^24 pixels in the batch): the keys of
+// ALL classes go through ONE device-wide radix sort -- class id in the top 6 key bits, so each
+// class comes out as a contiguous descending run (cub::DeviceRadixSort, the CUDA toolkit's
+// library sort: the one library call of this repository, used where the reference calls
+// torch.sort) -- and lovasz_sorted walks each run once: blocked prefix count of the foreground
+// bits with a running carry, closed-form gradient entry and e * g term per rank.
+// Tie rule (torch.sort is unstable): equal errors rank by pixel index.
 #include <math_constants.h>
+
+#include <cub/device/device_radix_sort.cuh>
 
 #include "common.cuh"
 
 namespace c3d {
 
 constexpr int kLovMaxClasses = 64;
-constexpr long long kLovMaxValid = 32768;
+constexpr long long kLovMaxPairs = 32768;          // all-pairs rank path (quadratic) up to here
+constexpr long long kLovMaxValid = 1ll << 24;      // radix path: 24 pixel bits in the key
 constexpr int kLovSortMax = 16384;        // keys of one class that fit shared memory (128 KB)
 enum LovInfo { kLovP = 0, kLovPresent = 1, kLovFlags = 2 };
 enum LovFlag { kLovOverflow = 1, kLovEmpty = 2 };
@@ -45,7 +53,10 @@ struct LovWs {
   int32_t* pix;       // [cap] b*HW + pixel
   int32_t* lab;       // [cap]
   float* cls_loss;    // [C] loss_c
-  unsigned long long* keys;  // [C * cap] fallback path only
+  unsigned long long* keys;  // [C * cap] fallback / radix paths only
+  unsigned long long* keys2; // [C * cap] radix path: sorted keys
+  void* sort_tmp;     // radix path: cub temporary storage
+  size_t sort_tmp_bytes;
   float* term;        // [C * cap] e * g at slot rank (fallback path)
   float* gval;        // [C * cap] d loss_c / d p of the element at slot rank
   int32_t* gpix;      // [C * cap] its pixel
@@ -63,9 +74,16 @@ static LovWs carve_lov(void* base, int C, long long cap) {
   w.cls_loss = (float*)take((size_t)C * 4);
   w.gval = (float*)take((size_t)C * cap * 4);
   w.gpix = (int32_t*)take((size_t)C * cap * 4);
-  const bool fallback = cap > kLovSortMax;
+  const bool fallback = cap > kLovSortMax, radix = cap > kLovMaxPairs;
   w.keys = (unsigned long long*)take(fallback ? (size_t)C * cap * 8 : 0);
-  w.term = (float*)take(fallback ? (size_t)C * cap * 4 : 0);
+  w.term = (float*)take(fallback && !radix ? (size_t)C * cap * 4 : 0);
+  w.keys2 = (unsigned long long*)take(radix ? (size_t)C * cap * 8 : 0);
+  w.sort_tmp_bytes = 0;
+  if (radix) {   // size query only: no launch, no allocation
+    const unsigned long long* kin = nullptr; unsigned long long* kout = nullptr;
+    cub::DeviceRadixSort::SortKeysDescending(nullptr, w.sort_tmp_bytes, kin, kout, C * cap, 0, 64);
+  }
+  w.sort_tmp = take(w.sort_tmp_bytes);
   w.bytes = off;
   return w;
 }
@@ -303,6 +321,118 @@ lovasz_reduce_kernel(int C, int cap, int classes_all, unsigned long long cls_mas
   }
 }
 
+// ------------------------------------------------------ radix path: keys ----
+// Key of (class c, element): [63:58] class, [57:26] error bits, [25:2] 0xFFFFFF - pixel,
+// [1] sign of d|fg - p|/dp, [0] foreground.  One descending sort of all C * cap keys leaves every
+// included class as a contiguous run (classes descending), padding and excluded classes (key 0)
+// at the very end.
+__device__ __forceinline__ unsigned long long lovasz_key_big(int c, float p, bool fg, int gpix) {
+  const float fgf = fg ? 1.0f : 0.0f;
+  const float e = fabsf(fgf - p);
+  return ((unsigned long long)c << 58) | ((unsigned long long)__float_as_uint(e) << 26) |
+         ((unsigned long long)(0xFFFFFFu - (unsigned)gpix) << 2) | (p < fgf ? 2ull : 0ull) | (fg ? 1ull : 0ull);
+}
+
+__global__ void __launch_bounds__(256)
+lovasz_keys_big_kernel(const float* __restrict__ probs, int HW, int C, int cap, int classes_all,
+                       unsigned long long cls_mask, const int32_t* __restrict__ pix,
+                       const int32_t* __restrict__ lab, const int32_t* __restrict__ hist,
+                       const int32_t* __restrict__ info, unsigned long long* __restrict__ keys) {
+  const int c = blockIdx.y;
+  const int P = min(info[kLovP], cap);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= cap) return;
+  unsigned long long k = 0ull;
+  if (i < P && lov_included(classes_all, cls_mask, hist[c], c)) {
+    const int g = pix[i];
+    const int b = g / HW, hw = g - b * HW;
+    // c + 1 in the class field: a real key is never 0 (error 0, pixel 0xFFFFFF, class 0 would be)
+    k = lovasz_key_big(c + 1, __ldg(probs + ((size_t)b * C + c) * HW + hw), lab[i] == c, g);
+  }
+  keys[(size_t)c * cap + i] = k;
+}
+
+// ------------------------------------------------------ radix path: runs ----
+// One CTA (1024 threads) per class walks the class's sorted run: 8 consecutive ranks per thread,
+// a block-wide exclusive scan of the per-thread foreground counts plus a running carry gives
+// F_r; the e * g terms are summed per thread, then over the block in a fixed order.
+constexpr int kLovItems = 8;
+__global__ void __launch_bounds__(1024)
+lovasz_sorted_kernel(int C, int cap, int classes_all, unsigned long long cls_mask, const int32_t* __restrict__ hist,
+                     const int32_t* __restrict__ info, const unsigned long long* __restrict__ sorted,
+                     float* __restrict__ gval, int32_t* __restrict__ gpix, float* __restrict__ cls_loss) {
+  __shared__ int s_warp[32];
+  __shared__ int s_carry;
+  __shared__ float s_part[32];
+  const int c = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int P = min(info[kLovP], cap);
+  if (!lov_included(classes_all, cls_mask, hist[c], c) || P == 0) {
+    if (threadIdx.x == 0) cls_loss[c] = 0.0f;
+    return;
+  }
+  // the run of class c starts after the runs of the included classes with a larger id
+  int later = 0;
+  for (int cc = c + 1; cc < C; ++cc) later += lov_included(classes_all, cls_mask, hist[cc], cc) ? 1 : 0;
+  const unsigned long long* run = sorted + (size_t)later * P;
+  const float gts = (float)hist[c];
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  float acc = 0.0f;
+  const int chunk = 1024 * kLovItems;
+  for (int r0 = 0; r0 < P; r0 += chunk) {
+    const int base = r0 + threadIdx.x * kLovItems;
+    unsigned long long k[kLovItems];
+    int cnt = 0;
+#pragma unroll
+    for (int j = 0; j < kLovItems; ++j) {
+      k[j] = (base + j < P) ? run[base + j] : 0ull;
+      cnt += (int)(k[j] & 1ull);
+    }
+    // exclusive scan of cnt over the block
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      int w = s_warp[lane], wi = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += v; }
+      s_warp[lane] = wi - w;                    // exclusive prefix over warps
+      if (lane == 31) s_part[0] = __int_as_float(wi);   // block total (bits)
+    }
+    __syncthreads();
+    int F = s_carry + s_warp[warp] + incl - cnt;   // foreground among the ranks before this thread's
+    const int block_total = __float_as_int(s_part[0]);
+#pragma unroll
+    for (int j = 0; j < kLovItems; ++j) {
+      const int r = base + j;
+      if (r < P) {
+        const int fg = (int)(k[j] & 1ull);
+        F += fg;
+        const float g = lovasz_grad_at(gts, r, F, fg);
+        const unsigned ebits = (unsigned)((k[j] >> 26) & 0xFFFFFFFFull);
+        acc += __uint_as_float(ebits) * g;
+        const float sign = (ebits == 0u) ? 0.0f : ((k[j] & 2ull) ? -1.0f : 1.0f);
+        gval[(size_t)c * cap + r] = g * sign;
+        gpix[(size_t)c * cap + r] = (int)(0xFFFFFFu - (unsigned)((k[j] >> 2) & 0xFFFFFFull));
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_carry += block_total;
+    __syncthreads();
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) s_part[warp] = acc;
+  __syncthreads();
+  if (warp == 0) {
+    float t = s_part[lane];
+    t = warp_sum(t);
+    if (lane == 0) cls_loss[c] = t;
+  }
+}
+
 // ------------------------------------------------------------- backward ----
 __global__ void __launch_bounds__(256)
 lovasz_scatter_kernel(int HW, int C, int cap, int classes_all, unsigned long long cls_mask, const int32_t* __restrict__ hist,
@@ -343,10 +473,10 @@ extern "C" int c3d_lovasz_forward(const float* probs, const int64_t* labels, int
   C3D_REQUIRE(HWll > 0 && batch * HWll <= (1ll << 30), "batch*H*W must be <= 2^30");
   C3D_REQUIRE(probs && labels && workspace && loss_out, "null pointer argument");
   C3D_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "workspace must be 256 B aligned");
-  if (max_valid <= 0 || max_valid > kLovMaxValid) {
-    set_error("Lovasz: max_valid=%lld outside [1, %lld]: the rank pass is quadratic in the number of "
-              "labelled pixels; dense labels need the radix-sort path, which is not built",
-              (long long)max_valid, kLovMaxValid);
+  if (max_valid <= 0 || max_valid > kLovMaxValid ||
+      (max_valid > kLovMaxPairs && (batch * HWll > kLovMaxValid || n_classes > 63))) {
+    set_error("Lovasz: max_valid=%lld outside [1, %lld] (the radix path keeps 24 pixel bits in its keys: "
+              "batch*H*W <= 2^24, n_classes <= 63)", (long long)max_valid, kLovMaxValid);
     return C3D_UNSUPPORTED;
   }
   const int HW = (int)HWll, C = n_classes, cap = (int)max_valid;
@@ -360,6 +490,31 @@ extern "C" int c3d_lovasz_forward(const float* probs, const int64_t* labels, int
         (const long long*)labels, total, C, ignore, cap, w.pix, w.lab, w.hist, w.info);
   }
   if ((rc = check_launch("lovasz_compact_kernel"))) return rc;
+  if (cap > kLovMaxPairs) {   // dense / pseudo-label regime: one device-wide radix sort
+    const dim3 grid((cap + 255) / 256, C);
+    {
+      KernelTimer kt__("lovasz_keys_big_kernel", stream);
+      lovasz_keys_big_kernel<<<grid, 256, 0, stream>>>(probs, HW, C, cap, classes_all, cls_mask, w.pix, w.lab,
+                                                       w.hist, w.info, w.keys);
+    }
+    if ((rc = check_launch("lovasz_keys_big_kernel"))) return rc;
+    {
+      KernelTimer kt__("lovasz_radix_sort(cub)", stream);
+      size_t tmp = w.sort_tmp_bytes;
+      const unsigned long long* kin = w.keys;
+      C3D_CUDA(cub::DeviceRadixSort::SortKeysDescending(w.sort_tmp, tmp, kin, w.keys2, C * cap, 0, 64,
+                                                        stream));
+    }
+    {
+      KernelTimer kt__("lovasz_sorted_kernel", stream);
+      lovasz_sorted_kernel<<<C, 1024, 0, stream>>>(C, cap, classes_all, cls_mask, w.hist, w.info, w.keys2, w.gval,
+                                                   w.gpix, w.cls_loss);
+    }
+    if ((rc = check_launch("lovasz_sorted_kernel"))) return rc;
+    KernelTimer kt__("lovasz_finalize_kernel", stream);
+    lovasz_finalize_kernel<<<1, 32, 0, stream>>>(C, cap, classes_all, cls_mask, w.hist, w.info, w.cls_loss, loss_out);
+    return check_launch("lovasz_finalize_kernel");
+  }
   {
     int n = 1024;
     while (n < cap && n < kLovSortMax) n <<= 1;

@@ -316,7 +316,7 @@ def entropy_select_batch(output, wss_mask, eval_mask, train_label, select_ratio,
 
 
 # --------------------------------------------------------------------- f4 --
-LOVASZ_MAX_VALID = 32768
+LOVASZ_MAX_VALID = 1 << 24      # radix path (24 pixel bits in the sort keys); <= 32768 stays in shared memory / all-pairs
 
 
 def lovasz_info(workspace):
@@ -345,12 +345,16 @@ class _LovaszFn(torch.autograd.Function):
         return grad, None, None, None, None, None, None
 
 
-def lovasz_softmax(probs, labels, ignore=None, classes="present", max_valid=LOVASZ_MAX_VALID,
+def lovasz_softmax(probs, labels, ignore=None, classes="present", max_valid=None,
                    workspace=None):
     """lovasz_softmax(per_image=False) of lovasz_softmax.py:67-98 on (B,C,H,W) probabilities and
     (B,H,W) int64 labels; `classes`: 'present', 'all' or a list of class ids (:117).  Returns
     (0-dim loss with autograd to `probs`, workspace).
-    More than `max_valid` (<= 32768) valid pixels is an error reported by `lovasz_info`."""
+    `max_valid` = capacity in valid (labelled) pixels; it selects the sort path (<= 16384: one CTA
+    per class in shared memory; <= 32768: all-pairs ranks; more, up to 2^24: device-wide radix
+    sort) and sizes the workspace.  None: the valid pixels are counted first (one host read, as
+    the reference's own `.sum() == 0` checks do) and the next power of two is taken.  More valid
+    pixels than an explicit `max_valid`: NaN loss + flag (`lovasz_info`)."""
     _need_cuda(probs=probs, labels=labels)
     if probs.dtype != torch.float32 or probs.dim() != 4:
         raise ValueError("probas must be (B, C, H, W) float32")
@@ -368,6 +372,16 @@ def lovasz_softmax(probs, labels, ignore=None, classes="present", max_valid=LOVA
         mode = 1 if classes == "all" else 0
     else:
         raise ValueError("classes must be 'present', 'all' or a list of class ids")
+    if max_valid is None:
+        lab_ok = (labels >= 0) & (labels < C)
+        if ignore is not None:
+            lab_ok &= labels != int(ignore)
+        n_valid = int(lab_ok.sum())
+        max_valid = 1024
+        while max_valid < n_valid:
+            max_valid *= 2
+        max_valid = min(max_valid, max(labels.numel(), 1))
+        workspace = None
     if workspace is None:
         n = lib.c3d_lovasz_workspace_bytes(C, int(max_valid))
         if n == 0:

@@ -48,6 +48,10 @@ def _make(B, C, H, W, frac, seed, sharp=1.5):
     (1, 3, 128, 128, 1.0, 0, "present"),       # 16384 valid pixels: largest in-smem sort
     (1, 5, 9, 33, 0.5, 0, "present"),
     (1, 4, 8, 32, 1.0, None, "present"),       # no ignored label: every pixel valid
+    (1, 5, 256, 256, 1.0, 0, "present"),       # 65536 valid pixels: device-wide radix sort path
+    (2, 20, 64, 2048, 0.3, 0, "present"),      # pseudo-label regime: ~79k valid pixels, 20 classes
+    (1, 20, 64, 2048, 1.0, None, "all"),       # dense labels, every pixel valid, all classes
+    (3, 7, 40, 1800, 0.6, 0, [1, 3, 6]),       # class list on the radix path
 ])
 def test_matches_oracle(cuda_device, B, C, H, W, frac, ignore, classes):
     from coarse3d_b200 import ops
@@ -94,18 +98,22 @@ def test_no_valid_pixel_and_overflow(cuda_device):
     loss.backward()
     assert float(loss) == 0.0 and float(p.grad.abs().max()) == 0.0
     assert ops.lovasz_info(ws)[2] & 2
-    # more labelled pixels than the quadratic rank pass supports: loud in strict mode
+    # more labelled pixels than a caller-fixed capacity: loud in strict mode
     big_p, big_l = _make(1, 3, 256, 256, 1.0, 2)
     with pytest.raises(ValueError):
-        Lovasz_softmax(ignore=0, strict=True)(big_p.cuda(), (big_l * 0 + 1).cuda())
-    # ... and never silently wrong in the default mode: the loss is NaN, so the module's own
-    # NaN assertion (lovasz_softmax.py:178) fires
+        Lovasz_softmax(ignore=0, strict=True, max_valid=32768)(big_p.cuda(), (big_l * 0 + 1).cuda())
+    # ... and never silently wrong otherwise: the loss is NaN, so the module's own NaN assertion
+    # (lovasz_softmax.py:178) fires
     with pytest.raises(AssertionError):
-        Lovasz_softmax(ignore=0)(big_p.cuda(), (big_l * 0 + 1).cuda())
-    raw, _ = ops.lovasz_softmax(big_p.cuda(), (big_l * 0 + 1).cuda(), ignore=0)
-    assert torch.isnan(raw)
+        Lovasz_softmax(ignore=0, max_valid=32768)(big_p.cuda(), (big_l * 0 + 1).cuda())
+    for cap in (32768, 40000):                                   # all-pairs path / radix path
+        raw, _ = ops.lovasz_softmax(big_p.cuda(), (big_l * 0 + 1).cuda(), ignore=0, max_valid=cap)
+        assert torch.isnan(raw)
     with pytest.raises(ValueError):
-        ops.lovasz_softmax(big_p.cuda(), big_l.cuda(), ignore=0, max_valid=1 << 20)
+        ops.lovasz_softmax(big_p.cuda(), big_l.cuda(), ignore=0, max_valid=(1 << 24) + 1)
+    # the default capacity adapts to the labels: the same input is simply computed
+    loss = Lovasz_softmax(ignore=0)(big_p.cuda(), (big_l * 0 + 1).cuda())
+    assert torch.isfinite(loss)
 
 
 def test_per_image_and_softmax_options(cuda_device):
