@@ -135,7 +135,12 @@ class HotPathStep:
         self.peer = None
         if distributed.world(group)[1] > 1 and _os.environ.get("C3D_PEER_EXCHANGE", "1") == "1":
             self.peer = distributed.PeerExchange(C, sub_protos, dim, self.device, group)
-        self.knn_split = int(_os.environ.get("C3D_KNN_SPLIT", "0"))   # scans in the first of two KNN launches
+        # scans in the first of two KNN launches.  With the vote held back until the rows kernels
+        # are done (below), the first launch is NOT held: a few scans' votes fit between the
+        # projection and the loss rows (-26 us per step for 4 scans at batch 20..40, nothing from
+        # batch 48 on: profiles/r2/fill_spread_early*.txt)
+        ks = _os.environ.get("C3D_KNN_SPLIT", "auto")
+        self.knn_split = (4 if 20 <= batch < 48 else 0) if ks == "auto" else int(ks)
         # schedule "fill_spread": fractions of the dense-gradient zero fill carried by the
         # projection's two passes, the label split, the EMA rows kernel and the loss rows kernel
         # (the KNN vote carries the rest).  Defaults from the sweeps in profiles/r2/fill_spread_*.txt:
@@ -259,6 +264,8 @@ class HotPathStep:
                 if not defer_knn:
                     self._knn(s, pr if pr is not None else self._last_proj(b), C, cofill=self._fs[4])
                     self.ev_proj.record(st_proj)
+                else:   # the first knn_split scans are voted while the chains are between rows kernels
+                    self._knn(s, pr if pr is not None else self._last_proj(b), C, cofill=self._fs[4], part="early")
             if not defer_knn:
                 st_fill.wait_event(self.ev_proj)
                 self.ev_fill.record(st_fill)
@@ -339,7 +346,7 @@ class HotPathStep:
                 self.ev_rows.record(st_loss)
                 with torch.cuda.stream(st_proj):
                     st_proj.wait_event(self.ev_rows)
-                    self._knn(s, pr if pr is not None else self._last_proj(b), C, cofill=self._fs[4])
+                    self._knn(s, pr if pr is not None else self._last_proj(b), C, cofill=self._fs[4], part="late")
                     self.ev_proj.record(st_proj)
                 st_fill.wait_event(self.ev_proj)
                 self.ev_fill.record(st_fill)
@@ -405,9 +412,11 @@ class HotPathStep:
             ops.zero_fill_background(self.grad, *self.daemon)
 
     def set_schedule(self, schedule, daemon=None, parts=None, fill_priority=None, fill_shares=None,
-                     knn_after_rows=None):
+                     knn_after_rows=None, knn_split=None):
         """Switch the schedule of an existing step (drops captured graphs)."""
         self.schedule = schedule
+        if knn_split is not None:
+            self.knn_split = int(knn_split)
         if knn_after_rows is not None:
             self.knn_after_rows = bool(knn_after_rows)
         if fill_shares is not None:
@@ -452,26 +461,34 @@ class HotPathStep:
             assign_mode=ops.ASSIGN_GUMBEL_DEVICE, seed=seed, max_rows=self.max_rows, group=self.group,
             workspace=self.ema_ws, packed=self.packed, out=self.protos)
 
-    def _knn(self, s, pr, C, cofill=None):
+    def _knn(self, s, pr, C, cofill=None, part=None):
+        """The vote (carrying `cofill`).  With knn_split = b1 scans it is two launches over scans
+        [0, b1) and [b1, B), each with its proportional share of the fill; `part` = "early" /
+        "late" issues only one of them (the pipeline releases them at different points)."""
         b1 = self.knn_split
-        if cofill is None or b1 <= 0 or b1 >= self.batch:
-            ops.knn_batch(pr.proj_range, s.argmax, pr.uproj_depth, pr.uproj_x_idx, pr.uproj_y_idx,
-                          s.offsets, self.knn_k, self.knn_s, self.knn_sigma, self.knn_cutoff, C,
-                          inv_gauss=self.inv_gauss, out=self.knn_out, cofill=cofill)
+        if b1 <= 0 or b1 >= self.batch:
+            if part != "early":
+                ops.knn_batch(pr.proj_range, s.argmax, pr.uproj_depth, pr.uproj_x_idx, pr.uproj_y_idx,
+                              s.offsets, self.knn_k, self.knn_s, self.knn_sigma, self.knn_cutoff, C,
+                              inv_gauss=self.inv_gauss, out=self.knn_out, cofill=cofill)
             return
-        # Two launches (scans [0, b1) and [b1, B), each carrying its share of the fill): while
-        # the first drains, the whole-SM kernels of the other chains (217 / 205 KB of shared
-        # memory) are placed, instead of waiting for the end of a single 3750-CTA grid.
         n1 = int(s.host_offsets[b1])
         if not hasattr(s, "offsets_tail") or s.offsets_tail_b1 != b1:
             s.offsets_tail = (s.offsets[b1:] - n1).contiguous()
             s.offsets_tail_b1 = b1
-        ops.knn_batch(pr.proj_range[:b1], s.argmax[:b1], pr.uproj_depth[:n1], pr.uproj_x_idx[:n1],
-                      pr.uproj_y_idx[:n1], s.offsets[:b1 + 1], self.knn_k, self.knn_s, self.knn_sigma,
-                      self.knn_cutoff, C, inv_gauss=self.inv_gauss, out=self.knn_out[:n1], cofill=cofill[:b1])
-        ops.knn_batch(pr.proj_range[b1:], s.argmax[b1:], pr.uproj_depth[n1:], pr.uproj_x_idx[n1:],
-                      pr.uproj_y_idx[n1:], s.offsets_tail, self.knn_k, self.knn_s, self.knn_sigma,
-                      self.knn_cutoff, C, inv_gauss=self.inv_gauss, out=self.knn_out[n1:], cofill=cofill[b1:])
+        f1 = f2 = None
+        if cofill is not None:
+            flat = cofill.view(-1)
+            cut = flat.numel() * b1 // self.batch // 2048 * 2048      # 8 KB pages
+            f1, f2 = (flat[:cut] if cut else None), flat[cut:]
+        if part != "late":
+            ops.knn_batch(pr.proj_range[:b1], s.argmax[:b1], pr.uproj_depth[:n1], pr.uproj_x_idx[:n1],
+                          pr.uproj_y_idx[:n1], s.offsets[:b1 + 1], self.knn_k, self.knn_s, self.knn_sigma,
+                          self.knn_cutoff, C, inv_gauss=self.inv_gauss, out=self.knn_out[:n1], cofill=f1)
+        if part != "early":
+            ops.knn_batch(pr.proj_range[b1:], s.argmax[b1:], pr.uproj_depth[n1:], pr.uproj_x_idx[n1:],
+                          pr.uproj_y_idx[n1:], s.offsets_tail, self.knn_k, self.knn_s, self.knn_sigma,
+                          self.knn_cutoff, C, inv_gauss=self.inv_gauss, out=self.knn_out[n1:], cofill=f2)
 
     def capture(self):
         """Capture one CUDA graph per input set.  Returns False if capture fails

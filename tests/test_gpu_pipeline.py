@@ -57,11 +57,13 @@ def test_vote_released_after_the_loss_rows(cuda_device, monkeypatch):
     step.run(0, seed=5)
     want = _outputs(step)
     monkeypatch.setenv("C3D_KNN_AFTER_ROWS", "1")
-    for schedule, shares in [("fill_in_knn", None), ("fill_spread", "0.2,0,0.15,0.15")]:
+    for schedule, shares, early in [("fill_in_knn", None, 0), ("fill_spread", "0.2,0,0.15,0.15", 0),
+                                    ("fill_spread", "0,0,0,0.2", 1), ("fill_in_knn", None, 2)]:
         if shares:
             monkeypatch.setenv("C3D_FILL_SHARES", shares)
+        monkeypatch.setenv("C3D_KNN_SPLIT", str(early))      # scans voted right after the projection
         held = _step(monkeypatch, schedule)
-        assert held.knn_after_rows
+        assert held.knn_after_rows and held.knn_split == early
         held.grad.fill_(2.0)
         held.knn_out.fill_(-1)
         held.run(0, seed=5)

@@ -65,10 +65,11 @@ def main():
     for B in batches:
         step = HotPathStep(synth.KITTI, B, n_sets=3)
         for sched, daemon in VARIANTS:
-            if sched == "fill_spread":     # shares, optionally a 5th value: 1 = vote after the loss rows
-                step.set_schedule(sched, fill_shares=daemon[:4], knn_after_rows=len(daemon) > 4 and daemon[4] > 0)
+            if sched == "fill_spread":     # shares; 5th value: 1 = vote after the loss rows; 6th: scans voted early
+                step.set_schedule(sched, fill_shares=daemon[:4], knn_after_rows=len(daemon) > 4 and daemon[4] > 0,
+                                  knn_split=int(daemon[5]) if len(daemon) > 5 else 0)
             else:
-                step.set_schedule(sched, daemon, knn_after_rows=False)
+                step.set_schedule(sched, daemon, knn_after_rows=False, knn_split=0)
             for i in range(3):
                 step.run(i, seed=i)
             torch.cuda.synchronize()
