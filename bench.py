@@ -392,6 +392,8 @@ def main():
         dist.all_reduce(same, op=dist.ReduceOp.MIN)
         banks_identical = bool(same.item())
         assert banks_identical, "prototype banks diverged across ranks"
+        if step.peer is not None:
+            assert step.peer.errors() == 0, "peer exchange: a rank's payload timed out (bits %x)" % step.peer.errors()
 
     # ---- per-kernel device times (eager, events inside the library around each launch)
     n_prof = 20
@@ -463,6 +465,9 @@ def main():
         "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": workload_config(args, world, synth),
         "run": {"cuda_graph": bool(graphed), "concurrent_chains": not args.serial, "schedule": step.schedule,
+                "prototype_exchange": (None if world == 1 else
+                                       "fused all-reduce + EMA kernel over NVLink peer memory (c3d_proto_ema_apply_peers)"
+                                       if step.peer is not None else "ncclAllReduce + c3d_proto_ema_apply"),
                 "fill_bytes_by_carrier": step.fill_bytes_by_carrier(), "vote_after_loss_rows": step.knn_after_rows,
                 "blocks": len(block_ms), "block_ms_min_median_max": [min(block_ms), ms_total, max(block_ms)],
                 "timed_region_s": t_region1 - t_region0, "banks_identical_across_ranks": banks_identical,

@@ -53,7 +53,7 @@ class PeerExchange:
     the others' buffers.  Afterwards `apply()` is device-side only and can be captured in a CUDA
     graph.  Ranks must live on one node; all ranks must call `apply` the same number of times."""
 
-    def __init__(self, n_classes, sub_protos, dim, device, group=None, timeout_s=2.0):
+    def __init__(self, n_classes, sub_protos, dim, device, group=None, timeout_s=20.0):
         import ctypes
         from ._lib import check, lib
         self.lib, self.check, self.group = lib, check, group
@@ -61,41 +61,60 @@ class PeerExchange:
         self.shape = (n_classes, sub_protos, dim)
         self.timeout_s = float(timeout_s)
         self.device = torch.device(device)
+        self._own, self._mapped = None, []
+        ok, why = 1, ""
         with torch.cuda.device(self.device):
             nbytes = lib.c3d_peer_exchange_bytes(n_classes, sub_protos, dim, self.world)
             if nbytes == 0:
                 raise ValueError("peer exchange: bad shape or more than 8 ranks")
-            own = ctypes.c_void_p()
-            check(lib.c3d_peer_alloc(nbytes, ctypes.byref(own)))
-            self._own = own
             handle = ctypes.create_string_buffer(64)
-            check(lib.c3d_peer_export(own, handle))
+            try:
+                own = ctypes.c_void_p()
+                check(lib.c3d_peer_alloc(nbytes, ctypes.byref(own)))
+                self._own = own
+                check(lib.c3d_peer_export(own, handle))
+            except Exception as e:  # noqa: BLE001  (e.g. CUDA IPC unavailable in this container)
+                ok, why = 0, repr(e)
+            # every rank takes part in every collective below, whatever happened locally
             handles = [None] * self.world
             if self.world > 1:
-                dist.all_gather_object(handles, handle.raw, group=group)
+                dist.all_gather_object(handles, (ok, handle.raw), group=group)
             else:
-                handles[0] = handle.raw
-            self._mapped = []
+                handles[0] = (ok, handle.raw)
             ptrs = (ctypes.c_void_p * self.world)()
-            for r, h in enumerate(handles):
-                if r == self.rank:
-                    ptrs[r] = own.value
-                    continue
-                q = ctypes.c_void_p()
-                check(lib.c3d_peer_import(ctypes.create_string_buffer(h, 64), ctypes.byref(q)))
-                self._mapped.append(q)
-                ptrs[r] = q.value
+            if ok and all(h[0] for h in handles):
+                try:
+                    for r, (_, h) in enumerate(handles):
+                        if r == self.rank:
+                            ptrs[r] = self._own.value
+                            continue
+                        q = ctypes.c_void_p()
+                        check(lib.c3d_peer_import(ctypes.create_string_buffer(h, 64), ctypes.byref(q)))
+                        self._mapped.append(q)
+                        ptrs[r] = q.value
+                except Exception as e:  # noqa: BLE001
+                    ok, why = 0, repr(e)
+            else:
+                ok = 0
             self._ptrs = ptrs
             self.state = torch.zeros(lib.c3d_peer_state_bytes(n_classes, sub_protos) // 4, dtype=torch.int32,
                                      device=self.device)
         if self.world > 1:
-            dist.barrier(group=group)      # every buffer is mapped everywhere before the first use
+            # one decision for all ranks; also: every buffer is mapped everywhere before the first use
+            flag = torch.tensor([ok], dtype=torch.int32, device=self.device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+            ok = int(flag.item())
+        self.available, self.why_not = bool(ok), why
+        if not ok:
+            self._release()
 
     def apply(self, prototypes, packed, momentum, ignore_label=0, out=None, normalised_out=None,
               seed_counters=None):
         """sum `packed` over the ranks (left in `packed`) and apply the EMA: the multi-GPU
         c3d_proto_ema_apply.  Bit-identical banks on every rank."""
         from .ops import _need_cuda, _p, _stream
+        if not self.available:
+            raise RuntimeError("peer exchange unavailable on this machine: %s" % self.why_not)
         _need_cuda(prototypes=prototypes, packed=packed)
         C, M, D = prototypes.shape
         if (C, M, D) != self.shape or packed.numel() != C * M * D + C * M or packed.dtype != torch.float32:
@@ -112,17 +131,21 @@ class PeerExchange:
         """Bit r set: rank r's payload did not arrive within the timeout in some call (host sync)."""
         return int(self.state[3].item())
 
+    def _release(self):
+        with torch.cuda.device(self.device):
+            for q in self._mapped:
+                self.lib.c3d_peer_close(q)
+            if self._own is not None:
+                self.lib.c3d_peer_free(self._own)
+        self._own, self._mapped = None, []
+
     def close(self):
         if getattr(self, "_own", None) is None:
             return
         torch.cuda.synchronize(self.device)
         if self.world > 1:
             dist.barrier(group=self.group)   # nobody still reads a buffer that is about to go away
-        with torch.cuda.device(self.device):
-            for q in self._mapped:
-                self.lib.c3d_peer_close(q)
-            self.lib.c3d_peer_free(self._own)
-        self._own, self._mapped = None, []
+        self._release()
 
 
 def prototype_update(embedding, label, prototypes, ln_d_w, ln_d_b, ln_c_w, ln_c_b, momentum,

@@ -135,6 +135,8 @@ class HotPathStep:
         self.peer = None
         if distributed.world(group)[1] > 1 and _os.environ.get("C3D_PEER_EXCHANGE", "1") == "1":
             self.peer = distributed.PeerExchange(C, sub_protos, dim, self.device, group)
+            if not self.peer.available:     # e.g. no CUDA IPC in this container: all ranks fall back together
+                self.peer = None
         # scans in the first of two KNN launches.  With the vote held back until the rows kernels
         # are done (below), the first launch is NOT held: a few scans' votes fit between the
         # projection and the loss rows (-26 us per step for 4 scans at batch 20..40, nothing from

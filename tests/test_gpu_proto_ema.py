@@ -174,3 +174,50 @@ def test_bank_surfaces_overflow_without_a_stall(cuda_device):
     ok = PrototypeBank(6, 4, 32).cuda()
     ok.update(emb.cuda(), label.cuda())
     ok.check_flags()
+
+
+@pytest.mark.parametrize("C,M,D", [(20, 20, 128), (7, 4, 32), (14, 20, 256)])
+def test_peer_exchange_kernel_on_one_rank(cuda_device, C, M, D):
+    """c3d_proto_ema_apply_peers with world = 1 (the rank exchanges with itself through its own
+    CUDA-IPC-exportable buffer): the fused all-reduce + EMA kernel must reproduce
+    c3d_proto_ema_apply bit for bit, over several steps (both slot parities, the device step
+    counter) and inside a captured CUDA graph.  The two-rank form is tests/test_gpu_multi.py."""
+    from coarse3d_b200 import distributed, ops
+    g = torch.Generator().manual_seed(C * 100 + D)
+    bank = torch.nn.functional.normalize(torch.randn(C, M, D, generator=g), dim=-1).cuda()
+    px = distributed.PeerExchange(C, M, D, "cuda")
+    assert px.available, px.why_not
+    want, cur = bank.clone(), bank.clone()
+    bank_n = torch.empty_like(cur)
+    K = C * M
+    payloads = []
+    for it in range(4):
+        packed = torch.randn(K * D + K, generator=g)
+        packed[K * D:] = torch.randint(0, 3, (K,), generator=g).float()        # counts, some zero
+        packed[K * D + M:K * D + 2 * M] = 0                                     # a class without rows
+        payloads.append(packed.cuda())
+    for it, packed in enumerate(payloads):
+        mine = packed.clone()
+        px.apply(cur, mine, 0.9, out=cur, normalised_out=bank_n)
+        want = ops.proto_ema_apply(want, packed, 0.9)
+        assert torch.equal(mine, packed), "summed payload of a single rank must be the payload"
+        assert torch.equal(cur, want), "step %d" % it
+        assert torch.equal(bank_n, ops.bank_normalise(cur))
+    # graph replay: the step counter lives on the device
+    buf = payloads[0].clone()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        px.apply(cur, buf, 0.9, out=cur)
+    torch.cuda.current_stream().wait_stream(side)
+    want = ops.proto_ema_apply(want, payloads[0], 0.9)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        px.apply(cur, buf, 0.9, out=cur)
+    for it in range(3):
+        buf.copy_(payloads[it + 1])
+        graph.replay()
+        want = ops.proto_ema_apply(want, payloads[it + 1], 0.9)
+        assert torch.equal(cur, want), "graph replay %d" % it
+    assert px.errors() == 0
+    px.close()
