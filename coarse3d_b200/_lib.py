@@ -29,6 +29,7 @@ def _load():
         "c3d_last_error": (c_char_p, []),
         "c3d_launch_count": (c_longlong, []),
         "c3d_project_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+        "c3d_project_cluster_supported": (c_int, [c_int, c_int, c_int]),
         "c3d_project_batch": (c_int, [P, c_int, P, c_int, c_int64, P, c_double, c_double, c_double,
                                       c_double, c_int, c_int, P, P, P, P, P, P, P, P, c_int, P, P, c_size_t, P]),
         "c3d_project_assemble_batch": (c_int, [P, P, c_int, c_int64, P, P, P, c_int, P, P, c_double, c_double,

@@ -21,7 +21,11 @@
 // pixel boundary (the only case where the floor could differ): ~0.5 % of
 // points.  C3D_PROJECT_F64_ONLY=1 forces the fp64 path for every point.
 
+#include <cooperative_groups.h>
+
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace c3d {
 
@@ -446,6 +450,191 @@ project_fused_kernel(const float4* __restrict__ points, const int32_t* __restric
   }
 }
 
+// ---------------------------------------------------- cluster / DSMEM form ----
+// The two-kernel form moves 1.7x its algorithmic bytes at batch 64: the z-buffer (1 MB per scan)
+// does not stay in L2, so its lines are fetched by the atomics, read back by the resolve pass and
+// written back reset.  Here a scan's z-buffer never leaves the chip: a thread-block CLUSTER of 8
+// CTAs owns one scan at a time and keeps the scan's H x W keys in its distributed shared memory
+// (8 x 128 KB for 64 x 2048 pixels).  Shared-memory atomics are native for 32 bits only (a
+// 64-bit atomicMin through a generic pointer into a peer's shared memory LOSES updates --
+// measured: 0.5 % of the pixels kept a farther point), so the 64-bit (depth, index) minimum is
+// taken in two native 32-bit steps.  Per scan:
+//   reset    every CTA resets its slice of depth keys and indices;               cluster barrier
+//   depth    the cluster's 8192 threads stream the scan's points (4 per thread in flight), write
+//            the per-point outputs and send one red.min.u32 of the depth key to the CTA that owns
+//            the pixel (DSMEM);                                                  cluster barrier
+//   index    the same threads re-read their per-point outputs (L2 hits), read the pixel's final
+//            depth key from its owner and, where it is their own, red.min.u32 their point index
+//            (equal depths: the smallest index wins, the z-buffer's tie rule);   cluster barrier
+//   resolve  every CTA resolves its own slice (the winners' points were read a moment ago by this
+//            cluster: L2 hits).
+// Clusters walk the scans persistently.  DRAM traffic = algorithmic bytes + the sector waste of
+// the winner gather; no global z-buffer, no memset, no reset pass.  Results are bit-identical to
+// the two-kernel form (same keys, same minimum, same per-point arithmetic).
+constexpr int kClusterCtas = 8;
+constexpr int kClusterThreads = 1024;
+constexpr int kClusterPts = 4;           // points / pixels per thread in flight
+constexpr size_t kClusterSmemMax = 200 * 1024;
+
+__device__ __forceinline__ unsigned dsmem_addr(const void* local_smem, int owner) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(local_smem);
+  unsigned r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(a), "r"(owner));
+  return r;
+}
+__device__ __forceinline__ void dsmem_red_min(unsigned addr, unsigned v) {
+  asm volatile("red.relaxed.cluster.shared::cluster.min.u32 [%0], %1;\n" :: "r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned dsmem_ld(unsigned addr) {
+  unsigned v;
+  asm volatile("ld.relaxed.cluster.shared::cluster.u32 %0, [%1];\n" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+
+template <bool kHybrid>
+__global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kClusterThreads, 1)
+project_cluster_kernel(const float4* __restrict__ points, const int32_t* __restrict__ offsets, int batch,
+                       const float* __restrict__ depth_override, ProjParams p, int slice,
+                       int32_t* upx, int32_t* upy, float* udepth,
+                       int32_t* __restrict__ flags, float* __restrict__ proj_range,
+                       float4* __restrict__ proj_pc, int32_t* __restrict__ proj_idx,
+                       int32_t* __restrict__ proj_mask) {
+  extern __shared__ __align__(16) unsigned s_zd[];   // [slice] depth keys, then [slice] point indices
+  unsigned* s_zi = s_zd + slice;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int n_clusters = gridDim.x / kClusterCtas, cid = blockIdx.x / kClusterCtas;
+  const int HW = p.H * p.W;
+  const int tid = threadIdx.x;
+  constexpr int kStride = kClusterCtas * kClusterThreads;
+  bool any_nan = false;
+  for (int b = cid; b < batch; b += n_clusters) {
+    for (int i = tid; i < 2 * slice; i += kClusterThreads) s_zd[i] = 0xFFFFFFFFu;
+    cluster.sync();            // every slice is reset before the first atomic lands
+    const int n0 = __ldg(offsets + b), n = __ldg(offsets + b + 1) - n0;
+    // ---- depth: per-point outputs + minimum depth key per pixel
+    for (int i0 = rank * kClusterThreads + tid; i0 < n; i0 += kClusterPts * kStride) {
+      float4 v[kClusterPts];
+      float dov[kClusterPts];
+#pragma unroll
+      for (int j = 0; j < kClusterPts; ++j) {
+        const int i = i0 + j * kStride;
+        v[j] = make_float4(1.f, 0.f, 0.f, 0.f);
+        dov[j] = 1.f;
+        if (i < n) {
+          v[j] = __ldg(points + n0 + i);
+          if (depth_override) dov[j] = __ldg(depth_override + n0 + i);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < kClusterPts; ++j) {
+        const int i = i0 + j * kStride;
+        if (i >= n) continue;
+        const float x = v[j].x, y = v[j].y, z = v[j].z;
+        const float depth = depth_override ? dov[j] : sqrtf((x * x + y * y) + z * z);
+        const float q = z / depth;
+        int px, py; bool nan;
+        pixel_of<kHybrid>(x, y, q, p, px, py, nan);
+        any_nan |= nan;
+        const int g = n0 + i;
+        upx[g] = px; upy[g] = py; udepth[g] = depth;        // re-read below: plain stores (L2)
+        const int pix = py * p.W + px;
+        const int owner = pix / slice, off = pix - owner * slice;
+        dsmem_red_min(dsmem_addr(s_zd + off, owner), depth_key(depth));
+      }
+    }
+    cluster.sync();            // the pixels' minimum depths are final
+    // ---- index: among the points at a pixel's minimum depth, the smallest index
+    for (int i0 = rank * kClusterThreads + tid; i0 < n; i0 += kClusterPts * kStride) {
+      int pix[kClusterPts]; unsigned dk[kClusterPts], zmin[kClusterPts];
+#pragma unroll
+      for (int j = 0; j < kClusterPts; ++j) {
+        const int i = i0 + j * kStride;
+        pix[j] = -1;
+        if (i < n) {
+          const int g = n0 + i;
+          pix[j] = upy[g] * p.W + upx[g];
+          dk[j] = depth_key(udepth[g]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < kClusterPts; ++j) {
+        zmin[j] = 0;
+        if (pix[j] >= 0) { const int owner = pix[j] / slice; zmin[j] = dsmem_ld(dsmem_addr(s_zd + (pix[j] - owner * slice), owner)); }
+      }
+#pragma unroll
+      for (int j = 0; j < kClusterPts; ++j) {
+        if (pix[j] >= 0 && zmin[j] == dk[j]) {
+          const int owner = pix[j] / slice;
+          dsmem_red_min(dsmem_addr(s_zi + (pix[j] - owner * slice), owner), (unsigned)(i0 + j * kStride));
+        }
+      }
+    }
+    cluster.sync();            // winners are final
+    // ---- resolve this CTA's slice
+    const int pix0 = rank * slice;
+    for (int l0 = tid; l0 < slice; l0 += kClusterPts * kClusterThreads) {
+      unsigned kd[kClusterPts], ki[kClusterPts];
+      float4 pt[kClusterPts];
+#pragma unroll
+      for (int j = 0; j < kClusterPts; ++j) {
+        const int l = l0 + j * kClusterThreads;
+        const bool in = l < slice && pix0 + l < HW;
+        kd[j] = in ? s_zd[l] : 0xFFFFFFFFu;
+        ki[j] = in ? s_zi[l] : 0xFFFFFFFFu;
+        pt[j] = make_float4(-1.f, -1.f, -1.f, -1.f);
+        if (ki[j] != 0xFFFFFFFFu) pt[j] = __ldg(points + n0 + ki[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < kClusterPts; ++j) {
+        const int l = l0 + j * kClusterThreads;
+        if (l >= slice || pix0 + l >= HW) continue;
+        const size_t qd = (size_t)b * HW + pix0 + l;
+        const bool valid = ki[j] != 0xFFFFFFFFu;
+        const int idx = valid ? (int)ki[j] : -1;
+        __stcs(proj_range + qd, valid ? key_depth(kd[j]) : -1.0f);
+        __stcs(proj_idx + qd, idx);
+        __stcs(proj_mask + qd, (int)(idx > 0));   // projection.py:113
+        st_stream(proj_pc + qd, pt[j]);
+      }
+    }
+    // the reset at the top of the next scan touches only this CTA's own slice; the barrier after
+    // it keeps the other CTAs' next atomics behind it
+  }
+  if (any_nan) atomicOr(flags, 1);
+  cluster.sync();              // no CTA exits while a peer may still address its shared memory
+}
+
+static int cluster_slice(int HW) { return (HW + kClusterCtas - 1) / kClusterCtas; }
+static bool cluster_form_fits(int HW) { return (size_t)cluster_slice(HW) * 8 <= kClusterSmemMax; }
+
+static int launch_cluster(const float* points, const int32_t* offsets, int batch, const float* depth_override,
+                          const ProjParams& p, bool hybrid, int32_t* upx, int32_t* upy, float* udepth,
+                          int32_t* status_flags, float* proj_range, float* proj_pc, int32_t* proj_idx,
+                          int32_t* proj_mask, cudaStream_t stream) {
+  const int HW = p.H * p.W, slice = cluster_slice(HW);
+  const size_t smem = (size_t)slice * sizeof(unsigned long long);
+  auto kern = hybrid ? project_cluster_kernel<true> : project_cluster_kernel<false>;
+  C3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // as many clusters as can be resident at once (a cluster lives inside one GPC), at most one per scan
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(kClusterCtas, 1, 1); cfg.blockDim = dim3(kClusterThreads, 1, 1);
+  cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr{};
+  attr.id = cudaLaunchAttributeClusterDimension;
+  attr.val.clusterDim.x = kClusterCtas; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+  cfg.attrs = &attr; cfg.numAttrs = 1;
+  int max_clusters = 0;
+  C3D_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg));
+  if (max_clusters < 1) { set_error("cluster projection: no 8-CTA cluster fits on this device"); return C3D_UNSUPPORTED; }
+  const int n_clusters = batch < max_clusters ? batch : max_clusters;
+  KernelTimer kt__("project_cluster_kernel", stream);
+  kern<<<n_clusters * kClusterCtas, kClusterThreads, smem, stream>>>(
+      reinterpret_cast<const float4*>(points), offsets, batch, depth_override, p, slice, upx, upy, udepth,
+      status_flags, proj_range, reinterpret_cast<float4*>(proj_pc), proj_idx, proj_mask);
+  return check_launch("project_cluster_kernel");
+}
+
 static size_t fused_ctl_bytes(int batch) { return (size_t)(16 + 2 * (size_t)batch) * 4; }
 static size_t fused_ring_bytes(int batch, int HW) {
   return (size_t)(batch < kRing ? batch : kRing) * HW * sizeof(unsigned long long);
@@ -485,6 +674,11 @@ static int launch_fused(const float* points, const int32_t* offsets, int batch, 
 }  // namespace c3d
 
 using namespace c3d;
+
+extern "C" int c3d_project_cluster_supported(int c_in, int proj_h, int proj_w) {
+  // 1 if workspace_flags bit 3 of c3d_project_batch takes the cluster form for this shape
+  return c_in == 4 && proj_h > 0 && proj_w > 0 && cluster_form_fits(proj_h * proj_w);
+}
 
 extern "C" size_t c3d_project_workspace_bytes(int batch, int proj_h, int proj_w) {
   if (batch <= 0 || proj_h <= 0 || proj_w <= 0) return 0;
@@ -533,6 +727,13 @@ extern "C" int c3d_project_batch(
                   ((reinterpret_cast<uintptr_t>(proj_pointcloud) & 15) == 0);
   const bool hybrid = !(workspace_flags & 2);
   const bool fused = c4 && (workspace_flags & 4);    // bit 2: the fused persistent kernel (A/B; measured slower)
+  // bit 3: the cluster / DSMEM form (z-buffer in distributed shared memory; workspace untouched)
+  if ((workspace_flags & 8) && c4 && !fused && total_points > 0 && cluster_form_fits(proj_h * proj_w) &&
+      ((reinterpret_cast<uintptr_t>(proj_pointcloud) & 15) == 0)) {
+    if (cofill_bytes) { int rc = launch_fill(cofill_ptr, cofill_bytes, stream); if (rc) return rc; }
+    return launch_cluster(points, offsets, batch, depth_override, p, hybrid, uproj_x_idx, uproj_y_idx, uproj_depth,
+                          status_flags, proj_range, proj_pointcloud, proj_idx, proj_mask, stream);
+  }
   if (!(workspace_flags & 1)) {
     KernelTimer kt__("zbuf_memset", stream);
     const size_t nb = fused ? fused_ring_bytes(batch, proj_h * proj_w) : (size_t)total_px * sizeof(unsigned long long);

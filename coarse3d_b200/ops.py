@@ -94,15 +94,20 @@ class ProjectionBuffers:
         self.clean = False  # "two" / "fused": the form whose call has left the z-buffer reset
 
 
+PROJECT_CLUSTER_DEFAULT = False   # set by the measurements in DESIGN.md 3.1
+
+
 def project_batch(points, offsets, fov: Fov, proj_h, proj_w, depth=None,
                   buffers: ProjectionBuffers = None, exact_f64=False, fused_kernel=False,
-                  cofill=None) -> Projection:
+                  cofill=None, cluster_kernel=None) -> Projection:
     """RangeProjection.doProjection for a CSR batch (projection.py:43-115).
 
     points (sum N, C>=3) f32, offsets (B+1,) i32, optional depth (sum N,) f32;
     all CUDA.  proj_idx holds indices local to each scan.  exact_f64=True evaluates the angles
     of EVERY point in fp64 (the default does so only inside the guard band of a pixel boundary;
-    both give the same pixels, the flag exists to prove that).
+    both give the same pixels, the flag exists to prove that).  cluster_kernel: the form that keeps
+    each scan's z-buffer in the distributed shared memory of a thread-block cluster (None = where
+    it applies: C == 4 and H*W*8 <= 8 x 200 KB; bit-identical results).
     """
     _need_cuda(points=points, offsets=offsets, depth=depth)
     if points.dtype != torch.float32 or points.dim() != 2:
@@ -118,7 +123,11 @@ def project_batch(points, offsets, fov: Fov, proj_h, proj_w, depth=None,
         b = ProjectionBuffers(batch, total, c_in, proj_h, proj_w, points.device)
     elif (b.batch, b.total, b.c_in, b.H, b.W) != (batch, total, c_in, proj_h, proj_w):
         raise ValueError("ProjectionBuffers shape mismatch")
+    want_cluster = PROJECT_CLUSTER_DEFAULT if cluster_kernel is None else bool(cluster_kernel)
+    cluster = (want_cluster and not fused_kernel and total > 0 and points.data_ptr() % 16 == 0 and
+               bool(lib.c3d_project_cluster_supported(c_in, proj_h, proj_w)))
     form = "fused" if fused_kernel else "two"
+    keep_clean = b.clean                            # the cluster form does not touch the workspace
     was_clean, b.clean = (b.clean == form), False   # a failed call may leave a dirty z-buffer; the two
     # forms initialise different parts of the workspace, so "clean" holds per form
     check(lib.c3d_project_batch(
@@ -126,9 +135,9 @@ def project_batch(points, offsets, fov: Fov, proj_h, proj_w, depth=None,
         fov.abs_fov_left, fov.fov_hori, fov.abs_fov_down, fov.fov_vert, proj_h, proj_w,
         _p(b.proj_range), _p(b.proj_pointcloud), _p(b.proj_idx), _p(b.proj_mask),
         _p(b.uproj_x_idx), _p(b.uproj_y_idx), _p(b.uproj_depth), _p(b.workspace),
-        (1 if was_clean else 0) | (2 if exact_f64 else 0) | (4 if fused_kernel else 0), _p(b.flags),
-        *_cofill_args(cofill), _stream()))
-    b.clean = form
+        (1 if was_clean else 0) | (2 if exact_f64 else 0) | (4 if fused_kernel else 0) | (8 if cluster else 0),
+        _p(b.flags), *_cofill_args(cofill), _stream()))
+    b.clean = keep_clean if cluster else form
     return Projection(b.proj_pointcloud, b.proj_range, b.proj_idx, b.proj_mask,
                       b.uproj_x_idx, b.uproj_y_idx, b.uproj_depth, b.flags)
 

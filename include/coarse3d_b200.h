@@ -69,6 +69,9 @@ int c3d_profile_reset(void);
  * case in which the reference crashes.
  */
 size_t c3d_project_workspace_bytes(int batch, int proj_h, int proj_w);
+/* 1 if workspace_flags bit 3 (cluster form: the scan's z-buffer in the distributed shared memory
+ * of an 8-CTA thread-block cluster, workspace untouched) applies to this shape. */
+int c3d_project_cluster_supported(int c_in, int proj_h, int proj_w);
 
 int c3d_project_batch(
     const float* points,          /* [total_points, c_in] x,y,z,(intensity,...)  */
@@ -95,7 +98,11 @@ int c3d_project_batch(
                                      inside the guard band of a pixel boundary --
                                      same pixels); bit 2: the fused
                                      persistent kernel instead of the two-kernel form
-                                     (same results; kept for A/B timing, slower) */
+                                     (same results; kept for A/B timing, slower); bit 3: the
+                                     cluster form where c3d_project_cluster_supported(): the
+                                     scan's z-buffer in the distributed shared memory of an
+                                     8-CTA thread-block cluster, workspace untouched (same
+                                     results; kept for A/B timing, slower) */
     int32_t* status_flags,        /* [1], caller-zeroed                          */
     void* cofill_ptr,             /* carried fill (see c3d_knn_batch): a 16 B aligned buffer
                                      zeroed meanwhile by the two passes' CTAs, or NULL       */

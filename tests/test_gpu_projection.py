@@ -213,3 +213,32 @@ def test_fused_persistent_kernel_equals_two_kernel_form(cuda_device):
     out = ops.project_batch(P, O, fov, shp.proj_h, shp.proj_w, buffers=bufs)   # and back
     for a, b in zip(out[:7], ref[:7]):
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("shape,batch,ragged", [("kitti", 5, True), ("nuscenes", 37, True), ("poss", 3, False)])
+def test_cluster_dsmem_form_equals_two_kernel_form(cuda_device, shape, batch, ragged):
+    """c3d_project_batch flag bit 3: the scan's z-buffer lives in the distributed shared memory of
+    an 8-CTA thread-block cluster (no global z-buffer traffic).  Must give the two-kernel form's
+    outputs bit for bit: ragged batches, more scans than resident clusters, depth override, both
+    transcendental modes, an empty scan, and leave the global workspace as it was."""
+    from coarse3d_b200 import ops, synth
+    shp = synth.SHAPES[shape]
+    pts, offs, _, _ = synth.make_batch(shp, batch, seed0=900, ragged=ragged)
+    offs = offs.copy()
+    if batch > 2:                      # scan 1 becomes empty: its points go to scan 2
+        offs[2] = offs[1]
+    P, O = torch.from_numpy(pts).cuda(), torch.from_numpy(offs).cuda()
+    fov = ops.Fov.from_degrees(shp.fov_up, shp.fov_down)
+    g = torch.Generator().manual_seed(3)
+    depth = (torch.from_numpy(np.linalg.norm(pts[:, :3], axis=1)) * (0.5 + torch.rand(pts.shape[0], generator=g))).float().cuda()
+    assert ops.lib.c3d_project_cluster_supported(4, shp.proj_h, shp.proj_w) == 1
+    for kw in ({}, {"depth": depth}, {"exact_f64": True}):
+        ref = [t.clone() for t in ops.project_batch(P, O, fov, shp.proj_h, shp.proj_w, cluster_kernel=False, **kw)]
+        bufs = ops.ProjectionBuffers(batch, pts.shape[0], 4, shp.proj_h, shp.proj_w, "cuda")
+        for rep in range(2):
+            out = ops.project_batch(P, O, fov, shp.proj_h, shp.proj_w, buffers=bufs, cluster_kernel=True, **kw)
+            for a, b in zip(out[:7], ref[:7]):
+                assert a.dtype == b.dtype and torch.equal(a, b), (kw.keys(), rep)
+        out = ops.project_batch(P, O, fov, shp.proj_h, shp.proj_w, buffers=bufs, cluster_kernel=False, **kw)
+        for a, b in zip(out[:7], ref[:7]):
+            assert torch.equal(a, b)

@@ -60,15 +60,16 @@ def main():
     res = {}
     bufs = ops.ProjectionBuffers(B, N, 4, shp.proj_h, shp.proj_w, "cuda")
     if "project" in args.ops:
-        for mode in ("0", "1", "fused_kernel"):
+        for mode in ("0", "1", "fused_kernel", "cluster_kernel"):
             f64 = mode == "1"
             two = mode == "fused_kernel"
+            clu = mode == "cluster_kernel"
             kern = None
             if os.environ.get("C3D_MB_PROFILE"):   # per-kernel events perturb the total
                 with ops.profile("") as prof:
-                    timeit(lambda: ops.project_batch(P, O, fov, shp.proj_h, shp.proj_w, buffers=bufs, exact_f64=f64, fused_kernel=two), flush=flush)
+                    timeit(lambda: ops.project_batch(P, O, fov, shp.proj_h, shp.proj_w, buffers=bufs, exact_f64=f64, fused_kernel=two, cluster_kernel=clu), flush=flush)
                     kern = {n: round(1e3 * v[0] / (ITERS[0] + WARMUP[0]), 1) for n, v in prof.all().items()}
-            med, mn = timeit(lambda: ops.project_batch(P, O, fov, shp.proj_h, shp.proj_w, buffers=bufs, exact_f64=f64, fused_kernel=two), flush=flush)
+            med, mn = timeit(lambda: ops.project_batch(P, O, fov, shp.proj_h, shp.proj_w, buffers=bufs, exact_f64=f64, fused_kernel=two, cluster_kernel=clu), flush=flush)
             by = 28 * N + 28 * B * HW
             res["project_f64only=" + mode] = dict(ms=med, ms_min=mn, GBs=by / med / 1e6, scans_s=B / med * 1e3,
                                                   kernels_us_per_call=kern)
