@@ -74,6 +74,8 @@ def _load():
         "c3d_proto_ema_apply": (c_int, [P, P, c_int, c_int, c_int, c_int, c_double, P, P, P, P]),
         "c3d_proto_ema_info": (c_int, [P, P, P]),
         "c3d_proto_bank_normalise": (c_int, [P, c_int, c_int, P, P]),
+        "c3d_knn_sort_workspace_bytes": (c_size_t, [c_int, c_int64, c_int, c_int]),
+        "c3d_knn_sort_points": (c_int, [P, P, P, P, c_int, c_int64, c_int, c_int, c_int, P, P, P]),
         "c3d_peer_exchange_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
         "c3d_peer_state_bytes": (c_size_t, [c_int, c_int]),
         "c3d_peer_alloc": (c_int, [c_size_t, P]),

@@ -105,12 +105,21 @@ knn_vote_kernel(const float* __restrict__ proj_range, const void* __restrict__ p
   int b = s_b0;
   while (g >= s_off[b + 1]) ++b;
   const int HW = H * W;
-  const float r = __ldcs(unproj_range + g);
-  int x0, y0;
-  if (pxy64) {
+  float r;
+  int x0, y0, gout = g;
+  if (pxy64 == 2) {
+    // binned order (c3d_knn_sort_points): one 16-byte record {range, x, y, original index} per
+    // point, points of a 32-pixel row segment adjacent, so a warp's window and class loads share
+    // cache lines
+    const float4 rec = __ldcs(reinterpret_cast<const float4*>(px_) + g);
+    r = rec.x; x0 = __float_as_int(rec.y); y0 = __float_as_int(rec.z); gout = __float_as_int(rec.w);
+    b = scan_of(s_off, batch, gout);     // records may come in any order: the scan follows the point
+  } else if (pxy64) {
+    r = __ldcs(unproj_range + g);
     x0 = (int)__ldcs(reinterpret_cast<const long long*>(px_) + g);
     y0 = (int)__ldcs(reinterpret_cast<const long long*>(py_) + g);
   } else {
+    r = __ldcs(unproj_range + g);
     x0 = __ldcs(reinterpret_cast<const int*>(px_) + g);
     y0 = __ldcs(reinterpret_cast<const int*>(py_) + g);
   }
@@ -287,9 +296,9 @@ knn_vote_kernel(const float* __restrict__ proj_range, const void* __restrict__ p
       if (n > best_n || (n == best_n && c < best_c)) { best_n = n; best_c = c; }
     }
   }
-  if (lab64 & 2) reinterpret_cast<uint8_t*>(out)[g] = (uint8_t)best_c;   // opt-in compact output
-  else if (lab64) reinterpret_cast<long long*>(out)[g] = best_c;
-  else reinterpret_cast<int*>(out)[g] = best_c;
+  if (lab64 & 2) reinterpret_cast<uint8_t*>(out)[gout] = (uint8_t)best_c;   // opt-in compact output
+  else if (lab64) reinterpret_cast<long long*>(out)[gout] = best_c;
+  else reinterpret_cast<int*>(out)[gout] = best_c;
   // the zero page must outlive the copies that read it (thread 0 is always a valid point)
   if (kFill >= 2 && threadIdx.x == 0) bulk_wait_read_all();
 }
@@ -354,9 +363,130 @@ static int launch_knn_s(int knn, const float* proj_range, const void* proj_argma
   return C3D_UNSUPPORTED;
 }
 
+// ------------------------------------------------------------ binning ----
+// The vote reads a 5 x 5 window and up to k classes per point through the L1: with the points of
+// a scan in arbitrary order every lane of a warp touches its own cache lines, and the kernel is
+// bound by the L1's tag stage (one line per cycle: 15 gather instructions x 32 lines per warp).
+// Binning the points by (row, 32-pixel column segment) first makes the lanes of a warp share
+// lines.  Counting sort, three small kernels, per-scan (the order stays scan-major, so the CSR
+// offsets still describe it): count + rank (one atomicAdd per point), per-scan exclusive scan of
+// the bin counts, scatter of 16-byte records {range, x, y, original index}.  The order inside a
+// bin is whatever the atomics gave: it only affects locality, the vote of a point does not
+// depend on its position.
+__device__ __forceinline__ int knn_bin_of(int x, int y, int nbx) { return y * nbx + (x >> 5); }
+
+template <bool kI64>
+__global__ void __launch_bounds__(256)
+knn_bin_count_kernel(const void* __restrict__ px_, const void* __restrict__ py_,
+                     const int32_t* __restrict__ offsets, int batch, int total, int nbx, int nb,
+                     int32_t* __restrict__ cnt, int32_t* __restrict__ rank) {
+  extern __shared__ int32_t s_off[];
+  for (int i = threadIdx.x; i <= batch; i += blockDim.x) s_off[i] = offsets[i];
+  __syncthreads();
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= total) return;
+  int b = scan_of(s_off, batch, g);
+  int x, y;
+  if (kI64) { x = (int)reinterpret_cast<const long long*>(px_)[g]; y = (int)reinterpret_cast<const long long*>(py_)[g]; }
+  else { x = reinterpret_cast<const int*>(px_)[g]; y = reinterpret_cast<const int*>(py_)[g]; }
+  rank[g] = atomicAdd(&cnt[(size_t)b * nb + knn_bin_of(x, y, nbx)], 1);
+}
+
+// one CTA per scan: cnt[b*nb + bin] -> first sorted position of the bin (offsets[b] + exclusive prefix)
+__global__ void __launch_bounds__(1024)
+knn_bin_scan_kernel(const int32_t* __restrict__ offsets, int nb, int32_t* __restrict__ cnt) {
+  __shared__ int s_warp[32];
+  __shared__ int s_carry;
+  const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int32_t* c = cnt + (size_t)b * nb;
+  if (threadIdx.x == 0) s_carry = offsets[b];
+  __syncthreads();
+  for (int base = 0; base < nb; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int v = i < nb ? c[i] : 0;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      const int w = s_warp[lane];
+      int wi = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += t; }
+      s_warp[lane] = wi - w;
+    }
+    __syncthreads();
+    const int excl = s_carry + s_warp[warp] + incl - v;
+    if (i < nb) c[i] = excl;
+    __syncthreads();
+    if (threadIdx.x == 1023) s_carry = excl + v;
+    __syncthreads();
+  }
+}
+
+template <bool kI64>
+__global__ void __launch_bounds__(256)
+knn_bin_scatter_kernel(const float* __restrict__ unproj_range, const void* __restrict__ px_,
+                       const void* __restrict__ py_, const int32_t* __restrict__ offsets, int batch,
+                       int total, int nbx, int nb, const int32_t* __restrict__ start,
+                       const int32_t* __restrict__ rank, float4* __restrict__ rec) {
+  extern __shared__ int32_t s_off[];
+  for (int i = threadIdx.x; i <= batch; i += blockDim.x) s_off[i] = offsets[i];
+  __syncthreads();
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= total) return;
+  const int b = scan_of(s_off, batch, g);
+  int x, y;
+  if (kI64) { x = (int)reinterpret_cast<const long long*>(px_)[g]; y = (int)reinterpret_cast<const long long*>(py_)[g]; }
+  else { x = reinterpret_cast<const int*>(px_)[g]; y = reinterpret_cast<const int*>(py_)[g]; }
+  const int pos = start[(size_t)b * nb + knn_bin_of(x, y, nbx)] + rank[g];
+  rec[pos] = make_float4(__ldcs(unproj_range + g), __int_as_float(x), __int_as_float(y), __int_as_float(g));
+}
+
 }  // namespace c3d
 
 using namespace c3d;
+
+extern "C" size_t c3d_knn_sort_workspace_bytes(int batch, int64_t total_points, int proj_h, int proj_w) {
+  if (batch <= 0 || total_points < 0 || proj_h <= 0 || proj_w <= 0) return 0;
+  const size_t nb = (size_t)proj_h * ((proj_w + 31) / 32);
+  return (((size_t)batch * nb * 4 + 255) & ~(size_t)255) + (size_t)total_points * 4 + 256;
+}
+
+extern "C" int c3d_knn_sort_points(const float* unproj_range, const void* px, const void* py,
+                                   const int32_t* offsets, int batch, int64_t total_points, int proj_h,
+                                   int proj_w, int pxy_is_i64, void* workspace, void* sorted_records,
+                                   void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  C3D_REQUIRE(batch > 0 && batch <= kMaxBatch, "batch must be in [1, %d]", kMaxBatch);
+  C3D_REQUIRE(total_points >= 0 && total_points < (1ll << 31), "total_points out of range");
+  C3D_REQUIRE(proj_h > 0 && proj_w > 0, "bad image size");
+  C3D_REQUIRE(offsets && workspace && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0,
+              "workspace must be 256 B aligned");
+  if (total_points == 0) return C3D_OK;
+  C3D_REQUIRE(unproj_range && px && py && sorted_records &&
+              (reinterpret_cast<uintptr_t>(sorted_records) & 15) == 0, "null / misaligned per-point pointer");
+  const int total = (int)total_points, nbx = (proj_w + 31) / 32, nb = proj_h * nbx;
+  int32_t* cnt = reinterpret_cast<int32_t*>(workspace);
+  const size_t cnt_bytes = ((size_t)batch * nb * 4 + 255) & ~(size_t)255;
+  int32_t* rank = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(workspace) + cnt_bytes);
+  C3D_CUDA(cudaMemsetAsync(cnt, 0, (size_t)batch * nb * 4, stream));
+  const int grid = (total + 255) / 256;
+  const size_t smem = (size_t)(batch + 1) * sizeof(int32_t);
+  int rc;
+  { KernelTimer kt__("knn_bin_count_kernel", stream);
+    if (pxy_is_i64) knn_bin_count_kernel<true><<<grid, 256, smem, stream>>>(px, py, offsets, batch, total, nbx, nb, cnt, rank);
+    else knn_bin_count_kernel<false><<<grid, 256, smem, stream>>>(px, py, offsets, batch, total, nbx, nb, cnt, rank); }
+  if ((rc = check_launch("knn_bin_count_kernel"))) return rc;
+  { KernelTimer kt__("knn_bin_scan_kernel", stream);
+    knn_bin_scan_kernel<<<batch, 1024, 0, stream>>>(offsets, nb, cnt); }
+  if ((rc = check_launch("knn_bin_scan_kernel"))) return rc;
+  { KernelTimer kt__("knn_bin_scatter_kernel", stream);
+    if (pxy_is_i64) knn_bin_scatter_kernel<true><<<grid, 256, smem, stream>>>(unproj_range, px, py, offsets, batch, total, nbx, nb, cnt, rank, reinterpret_cast<float4*>(sorted_records));
+    else knn_bin_scatter_kernel<false><<<grid, 256, smem, stream>>>(unproj_range, px, py, offsets, batch, total, nbx, nb, cnt, rank, reinterpret_cast<float4*>(sorted_records)); }
+  return check_launch("knn_bin_scatter_kernel");
+}
 
 extern "C" int c3d_knn_batch(const float* proj_range, const void* proj_argmax,
                              const float* unproj_range, const void* px, const void* py,
@@ -378,7 +508,11 @@ extern "C" int c3d_knn_batch(const float* proj_range, const void* proj_argmax,
   C3D_REQUIRE((reinterpret_cast<uintptr_t>(cofill_ptr) & 15) == 0 && cofill_bytes % 16 == 0,
               "co-scheduled fill must be 16 B aligned and a multiple of 16 B");
   if (total_points == 0) return cofill_ptr ? launch_fill(cofill_ptr, cofill_bytes, stream) : C3D_OK;
-  C3D_REQUIRE(unproj_range && px && py && out_labels, "null per-point pointer");
+  if (pxy_is_i64 == 2) {   // px = the 16-byte records of c3d_knn_sort_points; unproj_range / py unused
+    C3D_REQUIRE(px && out_labels && (reinterpret_cast<uintptr_t>(px) & 15) == 0, "null / misaligned records");
+  } else {
+    C3D_REQUIRE(unproj_range && px && py && out_labels, "null per-point pointer");
+  }
 #define KNN_ARGS knn, proj_range, proj_argmax, unproj_range, px, py, offsets, batch,            \
                  (int)total_points, proj_h, proj_w, cutoff, nclasses, inv_gauss, out_labels,     \
                  pxy_is_i64, label_is_i64, cofill_ptr, cofill_bytes, stream

@@ -216,7 +216,7 @@ def gaussian_kernel(kernel_size=3, sigma=2):
 
 
 def knn_batch(proj_range, proj_argmax, unproj_range, px, py, offsets, knn, search, sigma,
-              cutoff, nclasses, inv_gauss=None, out=None, cofill=None, out_uint8=False):
+              cutoff, nclasses, inv_gauss=None, out=None, cofill=None, out_uint8=False, records=None):
     """KNN.forward for a CSR batch (knn.py:54-142).
 
     proj_range (B,H,W) f32; px, py (sum N,) int64 (the reference's dtype) or
@@ -226,6 +226,8 @@ def knn_batch(proj_range, proj_argmax, unproj_range, px, py, offsets, knn, searc
     `cofill`: a contiguous CUDA tensor zeroed by the same kernel (TMA bulk stores from a
     shared-memory zero page while the vote keeps the ALU busy; the step pipeline passes the
     loss's dense gradient buffer).
+    `records`: the binned per-point records of `knn_sort_points` (same points, same results): the
+    vote then reads them instead of unproj_range / px / py, and a warp's gathers share cache lines.
     """
     if search % 2 == 0:
         raise ValueError("Nearest neighbor kernel must be odd number")  # knn.py:72-73
@@ -248,7 +250,10 @@ def knn_batch(proj_range, proj_argmax, unproj_range, px, py, offsets, knn, searc
         inv_gauss = (1 - gaussian_kernel(search, sigma)).reshape(-1).to(proj_range.device)
     if out is None:
         out = torch.empty((total,), dtype=torch.uint8 if out_uint8 else ldt, device=proj_range.device)
-    elif out.dtype != (torch.uint8 if out_uint8 else ldt) or out.numel() != total:
+    elif out.dtype != (torch.uint8 if out_uint8 else ldt) or \
+            (out.numel() != total and not (records is not None and out.numel() > total)):
+        # with records the labels go to the ORIGINAL point indices, which may belong to a larger
+        # batch than the scans of this call (two-launch vote): `out` is then the whole batch's
         raise ValueError("out must be (sum N,) %s" % (torch.uint8 if out_uint8 else ldt))
     nfill = 0
     if cofill is not None:
@@ -256,11 +261,42 @@ def knn_batch(proj_range, proj_argmax, unproj_range, px, py, offsets, knn, searc
         nfill = cofill.numel() * cofill.element_size()
         if not cofill.is_contiguous() or nfill % 16 or cofill.data_ptr() % 16:
             raise ValueError("cofill must be contiguous, 16 B aligned and a multiple of 16 B")
+    if records is not None:
+        _need_cuda(records=records)
+        if records.dtype != torch.float32 or records.shape != (total, 4):
+            raise ValueError("records must be the (sum N, 4) float32 tensor of knn_sort_points")
     check(lib.c3d_knn_batch(
-        _p(proj_range), _p(proj_argmax), _p(unproj_range), _p(px), _p(py), _p(offsets), B, total,
+        _p(proj_range), _p(proj_argmax), _p(unproj_range), _p(px if records is None else records), _p(py),
+        _p(offsets), B, total,
         H, W, int(knn), int(search), float(cutoff), int(nclasses), _p(inv_gauss),
-        1 if idt == torch.int64 else 0, (1 if ldt == torch.int64 else 0) | (2 if out_uint8 else 0), _p(out),
+        2 if records is not None else (1 if idt == torch.int64 else 0),
+        (1 if ldt == torch.int64 else 0) | (2 if out_uint8 else 0), _p(out),
         _p(cofill) if nfill else None, nfill, _stream()))
+    return out
+
+
+def knn_sort_workspace(batch, total, proj_h, proj_w, device):
+    n = lib.c3d_knn_sort_workspace_bytes(int(batch), int(total), int(proj_h), int(proj_w))
+    return torch.empty((max(n, 256),), dtype=torch.uint8, device=device)
+
+
+def knn_sort_points(unproj_range, px, py, offsets, proj_h, proj_w, workspace=None, out=None):
+    """Bin the points of every scan by (row, 32-pixel column segment) for `knn_batch(records=)`:
+    returns (sum N, 4) float32 records {range, x, y, original index} (ints bit-cast), scan-major,
+    so that the vote's warps touch shared cache lines.  Three small kernels, no sync."""
+    _need_cuda(unproj_range=unproj_range, px=px, py=py, offsets=offsets)
+    if px.dtype not in (torch.int64, torch.int32) or py.dtype != px.dtype:
+        raise ValueError("px, py must share dtype int64 or int32")
+    if unproj_range.dtype != torch.float32 or offsets.dtype != torch.int32:
+        raise ValueError("unproj_range must be float32, offsets int32")
+    total, batch = unproj_range.numel(), offsets.numel() - 1
+    if workspace is None:
+        workspace = knn_sort_workspace(batch, total, proj_h, proj_w, px.device)
+    if out is None:
+        out = torch.empty((total, 4), dtype=torch.float32, device=px.device)
+    check(lib.c3d_knn_sort_points(_p(unproj_range), _p(px), _p(py), _p(offsets), batch, total, int(proj_h),
+                                  int(proj_w), 1 if px.dtype == torch.int64 else 0, _p(workspace), _p(out),
+                                  _stream()))
     return out
 
 

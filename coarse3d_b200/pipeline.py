@@ -130,6 +130,11 @@ class HotPathStep:
         kar = _os.environ.get("C3D_KNN_AFTER_ROWS", "auto")
         self.knn_after_rows = (batch >= 20) if kar == "auto" else kar == "1"
         self.ev_rows = torch.cuda.Event()
+        # the vote on points binned by (row, 32-pixel segment) (c3d_knn_sort_points): measured a net
+        # loss inside the step (vote + fill 673 -> 612 us at batch 64, binning 201 us), off by default
+        self.knn_binned = _os.environ.get("C3D_KNN_BINNED", "0") == "1"
+        self.knn_sort_ws = ops.knn_sort_workspace(batch, n, H, W, self.device)
+        self.knn_records = torch.empty((n, 4), dtype=torch.float32, device=self.device)
         # N > 1: the all-reduce of the packed sums fused with the EMA over peer memory (default),
         # or ncclAllReduce + c3d_proto_ema_apply (C3D_PEER_EXCHANGE=0)
         self.peer = None
@@ -209,6 +214,7 @@ class HotPathStep:
             self._fs = self._fill_slices(chains=self.fused_step and {"loss", "ema"} <= self.parts)
         if not self.concurrent:
             pr = ops.project_batch(s.points, s.offsets, self.fov, H, W, buffers=b, cofill=self._fs[0])
+            self._bin(pr, s)
             if self.fused_step:
                 self._step(ops.STEP_SPLIT, s.labels, s, seed, cofill=self._fs[1])
                 self._step(ops.STEP_SAMPLE | ops.STEP_ACCUMULATE, s.labels, s, seed, cofill=self._fs[2])
@@ -258,6 +264,7 @@ class HotPathStep:
             with torch.cuda.stream(st_proj):
                 if "proj" in P:
                     pr = ops.project_batch(s.points, s.offsets, self.fov, H, W, buffers=b, cofill=self._fs[0])
+                self._bin(pr if pr is not None else self._last_proj(b), s)
                 if hold:
                     # The vote's 3750 CTAs keep every SM full until its grid is drained, and the
                     # loss-rows kernel needs a whole SM (217 KB of shared memory): released
@@ -282,6 +289,7 @@ class HotPathStep:
             with torch.cuda.stream(st_proj):
                 if "proj" in P:
                     pr = ops.project_batch(s.points, s.offsets, self.fov, H, W, buffers=b)
+                self._bin(pr if pr is not None else self._last_proj(b), s)
                 if "knn" in P:
                     self._knn(s, pr if pr is not None else self._last_proj(b), C)
                 self.ev_proj.record(st_proj)
@@ -296,6 +304,7 @@ class HotPathStep:
                 st_proj.wait_event(self.ev_fill)
                 if "proj" in P:
                     pr = ops.project_batch(s.points, s.offsets, self.fov, H, W, buffers=b)
+                self._bin(pr if pr is not None else self._last_proj(b), s)
                 if "knn" in P:
                     self._knn(s, pr if pr is not None else self._last_proj(b), C)
                 self.ev_proj.record(st_proj)
@@ -303,6 +312,7 @@ class HotPathStep:
             with torch.cuda.stream(st_proj):
                 if "proj" in P:
                     pr = ops.project_batch(s.points, s.offsets, self.fov, H, W, buffers=b)
+                self._bin(pr if pr is not None else self._last_proj(b), s)
                 self.ev_resolved.record(st_proj)
                 if "knn" in P:
                     self._knn(s, pr if pr is not None else self._last_proj(b), C)  # ALU-bound
@@ -463,16 +473,24 @@ class HotPathStep:
             assign_mode=ops.ASSIGN_GUMBEL_DEVICE, seed=seed, max_rows=self.max_rows, group=self.group,
             workspace=self.ema_ws, packed=self.packed, out=self.protos)
 
+    def _bin(self, pr, s):
+        """Binning pre-pass of the vote (right after the projection, on its stream)."""
+        if self.knn_binned and "knn" in self.parts:
+            ops.knn_sort_points(pr.uproj_depth, pr.uproj_x_idx, pr.uproj_y_idx, s.offsets,
+                                self.shape.proj_h, self.shape.proj_w, workspace=self.knn_sort_ws,
+                                out=self.knn_records)
+
     def _knn(self, s, pr, C, cofill=None, part=None):
         """The vote (carrying `cofill`).  With knn_split = b1 scans it is two launches over scans
         [0, b1) and [b1, B), each with its proportional share of the fill; `part` = "early" /
         "late" issues only one of them (the pipeline releases them at different points)."""
-        b1 = self.knn_split
+        rec = self.knn_records if self.knn_binned else None
+        b1 = self.knn_split if rec is None else 0      # records are not sliced by scan: one launch
         if b1 <= 0 or b1 >= self.batch:
             if part != "early":
                 ops.knn_batch(pr.proj_range, s.argmax, pr.uproj_depth, pr.uproj_x_idx, pr.uproj_y_idx,
                               s.offsets, self.knn_k, self.knn_s, self.knn_sigma, self.knn_cutoff, C,
-                              inv_gauss=self.inv_gauss, out=self.knn_out, cofill=cofill)
+                              inv_gauss=self.inv_gauss, out=self.knn_out, cofill=cofill, records=rec)
             return
         n1 = int(s.host_offsets[b1])
         if not hasattr(s, "offsets_tail") or s.offsets_tail_b1 != b1:
@@ -483,14 +501,19 @@ class HotPathStep:
             flat = cofill.view(-1)
             cut = flat.numel() * b1 // self.batch // 2048 * 2048      # 8 KB pages
             f1, f2 = (flat[:cut] if cut else None), flat[cut:]
+        # binned records carry ORIGINAL (whole-batch) point indices: both launches write into knn_out
         if part != "late":
             ops.knn_batch(pr.proj_range[:b1], s.argmax[:b1], pr.uproj_depth[:n1], pr.uproj_x_idx[:n1],
                           pr.uproj_y_idx[:n1], s.offsets[:b1 + 1], self.knn_k, self.knn_s, self.knn_sigma,
-                          self.knn_cutoff, C, inv_gauss=self.inv_gauss, out=self.knn_out[:n1], cofill=f1)
+                          self.knn_cutoff, C, inv_gauss=self.inv_gauss,
+                          out=self.knn_out if rec is not None else self.knn_out[:n1], cofill=f1,
+                          records=None if rec is None else rec[:n1])
         if part != "early":
             ops.knn_batch(pr.proj_range[b1:], s.argmax[b1:], pr.uproj_depth[n1:], pr.uproj_x_idx[n1:],
                           pr.uproj_y_idx[n1:], s.offsets_tail, self.knn_k, self.knn_s, self.knn_sigma,
-                          self.knn_cutoff, C, inv_gauss=self.inv_gauss, out=self.knn_out[n1:], cofill=f2)
+                          self.knn_cutoff, C, inv_gauss=self.inv_gauss,
+                          out=self.knn_out if rec is not None else self.knn_out[n1:], cofill=f2,
+                          records=None if rec is None else rec[n1:])
 
     def capture(self):
         """Capture one CUDA graph per input set.  Returns False if capture fails

@@ -72,6 +72,25 @@ def test_batched_matches_oracle(cuda_device, shape_name, batch, k, s, sigma, cut
                         cat("uproj_x_idx", npdt), cat("uproj_y_idx", npdt),
                         torch.from_numpy(offs).cuda(), k, s, sigma, cutoff, shp.n_classes)
     assert out.dtype == idt
+    # the binned form (c3d_knn_sort_points + records): same labels at the original point indices,
+    # also with a co-scheduled fill and the uint8 output
+    px, py, ur = cat("uproj_x_idx", npdt), cat("uproj_y_idx", npdt), cat("uproj_depth", np.float32)
+    O = torch.from_numpy(offs).cuda()
+    rec = ops.knn_sort_points(ur, px, py, O, shp.proj_h, shp.proj_w)
+    assert sorted(rec[:, 3].view(torch.int32).tolist()) == list(range(px.numel()))     # a permutation
+    seg = rec[:, 2].view(torch.int32).long() * ((shp.proj_w + 31) // 32) + (rec[:, 1].view(torch.int32).long() >> 5)
+    for b in range(batch):                      # scan-major, bins ascending inside a scan
+        sb = seg[offs[b]:offs[b + 1]]
+        assert bool((sb[1:] >= sb[:-1]).all())
+        idx = rec[offs[b]:offs[b + 1], 3].view(torch.int32)
+        assert int(idx.min()) >= offs[b] and int(idx.max()) < offs[b + 1]
+    fillbuf = torch.ones(3001 * 4, device="cuda")
+    out2 = ops.knn_batch(proj_range, proj_argmax, ur, px, py, O, k, s, sigma, cutoff, shp.n_classes,
+                         records=rec, cofill=fillbuf)
+    assert torch.equal(out2, out) and float(fillbuf.abs().max()) == 0.0
+    out3 = ops.knn_batch(proj_range, proj_argmax, ur, px, py, O, k, s, sigma, cutoff, shp.n_classes,
+                         records=rec, out_uint8=True)
+    assert torch.equal(out3.to(idt), out)
     out = out.cpu().numpy()
     for b, (o, argmax) in enumerate(per):
         want = oknn.knn_vote(o["proj_range"], o["uproj_depth"], argmax, o["uproj_x_idx"],

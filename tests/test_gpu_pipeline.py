@@ -62,6 +62,7 @@ def test_vote_released_after_the_loss_rows(cuda_device, monkeypatch):
         if shares:
             monkeypatch.setenv("C3D_FILL_SHARES", shares)
         monkeypatch.setenv("C3D_KNN_SPLIT", str(early))      # scans voted right after the projection
+        monkeypatch.setenv("C3D_KNN_BINNED", "1" if early == 0 else "0")   # binned vote in two of the cases
         held = _step(monkeypatch, schedule)
         assert held.knn_after_rows and held.knn_split == early
         held.grad.fill_(2.0)
