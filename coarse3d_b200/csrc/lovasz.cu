@@ -24,8 +24,9 @@
 // ALL classes go through ONE device-wide radix sort -- class id in the top 6 key bits, so each
 // class comes out as a contiguous descending run (cub::DeviceRadixSort, the CUDA toolkit's
 // library sort: the one library call of this repository, used where the reference calls
-// torch.sort) -- and lovasz_sorted walks each run once: blocked prefix count of the foreground
-// bits with a running carry, closed-form gradient entry and e * g term per rank.
+// torch.sort) -- and the runs are walked in 8192-rank chunks by the whole GPU: foreground count
+// per chunk, then per chunk the blocked prefix count of the foreground bits, the closed-form
+// gradient entry and the e * g term per rank.
 // Tie rule (torch.sort is unstable): equal errors rank by pixel index.
 #include <math_constants.h>
 
@@ -57,6 +58,8 @@ struct LovWs {
   unsigned long long* keys2; // [C * cap] radix path: sorted keys
   void* sort_tmp;     // radix path: cub temporary storage
   size_t sort_tmp_bytes;
+  int32_t* chunk_fg;  // [C * n_chunks] radix path: foreground keys per 8192-rank chunk
+  float* chunk_loss;  // [C * n_chunks] radix path: partial losses
   float* term;        // [C * cap] e * g at slot rank (fallback path)
   float* gval;        // [C * cap] d loss_c / d p of the element at slot rank
   int32_t* gpix;      // [C * cap] its pixel
@@ -84,6 +87,9 @@ static LovWs carve_lov(void* base, int C, long long cap) {
     cub::DeviceRadixSort::SortKeysDescending(nullptr, w.sort_tmp_bytes, kin, kout, C * cap, 0, 64);
   }
   w.sort_tmp = take(w.sort_tmp_bytes);
+  const size_t n_chunks = radix ? (size_t)((cap + 8191) / 8192) : 0;
+  w.chunk_fg = (int32_t*)take((size_t)C * n_chunks * 4);
+  w.chunk_loss = (float*)take((size_t)C * n_chunks * 4);
   w.bytes = off;
   return w;
 }
@@ -93,6 +99,11 @@ __global__ void __launch_bounds__(256)
 lovasz_compact_kernel(const long long* __restrict__ labels, long long total, int C, int ignore,
                       int cap, int32_t* __restrict__ pix, int32_t* __restrict__ lab,
                       int32_t* __restrict__ hist, int32_t* __restrict__ info) {
+  // class histogram per CTA in shared memory, flushed once (dense labels: one global atomic per
+  // valid pixel on ~20 addresses was most of this kernel's time)
+  __shared__ int s_hist[kLovMaxClasses];
+  if (threadIdx.x < kLovMaxClasses) s_hist[threadIdx.x] = 0;
+  __syncthreads();
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long q0 = (long long)blockIdx.x * blockDim.x; q0 < total; q0 += stride) {
     const long long q = q0 + threadIdx.x;
@@ -107,11 +118,13 @@ lovasz_compact_kernel(const long long* __restrict__ labels, long long total, int
       base = __shfl_sync(0xffffffffu, base, 0);
       if (valid) {
         const int pos = base + __popc(m & ((1u << lane) - 1));
-        if (pos < cap) { pix[pos] = (int)q; lab[pos] = (int)l; atomicAdd(&hist[(int)l], 1); }
+        if (pos < cap) { pix[pos] = (int)q; lab[pos] = (int)l; atomicAdd(&s_hist[(int)l], 1); }
         else atomicOr(&info[kLovFlags], kLovOverflow);
       }
     }
   }
+  __syncthreads();
+  if (threadIdx.x < C && s_hist[threadIdx.x]) atomicAdd(&hist[threadIdx.x], s_hist[threadIdx.x]);
 }
 
 // Key of (class c, element): descending error, then ascending pixel -- a larger key sorts
@@ -353,75 +366,108 @@ lovasz_keys_big_kernel(const float* __restrict__ probs, int HW, int C, int cap, 
 }
 
 // ------------------------------------------------------ radix path: runs ----
-// One CTA (1024 threads) per class walks the class's sorted run: 8 consecutive ranks per thread,
-// a block-wide exclusive scan of the per-thread foreground counts plus a running carry gives
-// F_r; the e * g terms are summed per thread, then over the block in a fixed order.
+// The class's sorted run is cut into chunks of 8192 ranks, one CTA (1024 threads, 8 consecutive
+// ranks per thread) per (chunk, class), so the whole GPU works on it:
+//   lovasz_chunk_count  foreground keys per chunk;
+//   lovasz_chunk_apply  F_r = (foreground in the earlier chunks) + a block-wide exclusive scan of
+//                       the per-thread counts; closed-form gradient entry and e * g term per
+//                       rank; the chunk's partial loss;
+//   lovasz_chunk_reduce the class's partial losses summed in chunk order (fixed order).
 constexpr int kLovItems = 8;
+constexpr int kLovChunk = 1024 * kLovItems;
+
+// first key of class c's run and its length P (0 if the class is not averaged)
+__device__ __forceinline__ const unsigned long long* lov_run(const unsigned long long* sorted, int C, int c, int P,
+                                                              int classes_all, unsigned long long cls_mask,
+                                                              const int32_t* __restrict__ hist) {
+  int later = 0;   // the runs of the included classes with a larger id come first
+  for (int cc = c + 1; cc < C; ++cc) later += lov_included(classes_all, cls_mask, hist[cc], cc) ? 1 : 0;
+  return sorted + (size_t)later * P;
+}
+
 __global__ void __launch_bounds__(1024)
-lovasz_sorted_kernel(int C, int cap, int classes_all, unsigned long long cls_mask, const int32_t* __restrict__ hist,
-                     const int32_t* __restrict__ info, const unsigned long long* __restrict__ sorted,
-                     float* __restrict__ gval, int32_t* __restrict__ gpix, float* __restrict__ cls_loss) {
+lovasz_chunk_count_kernel(int C, int cap, int n_chunks, int classes_all, unsigned long long cls_mask,
+                          const int32_t* __restrict__ hist, const int32_t* __restrict__ info,
+                          const unsigned long long* __restrict__ sorted, int32_t* __restrict__ chunk_fg) {
+  __shared__ int s_warp[32];
+  const int c = blockIdx.y, chunk = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int P = min(info[kLovP], cap);
+  int cnt = 0;
+  if (lov_included(classes_all, cls_mask, hist[c], c) && chunk * kLovChunk < P) {
+    const unsigned long long* run = lov_run(sorted, C, c, P, classes_all, cls_mask, hist);
+    const int base = chunk * kLovChunk + threadIdx.x * kLovItems;
+#pragma unroll
+    for (int j = 0; j < kLovItems; ++j) cnt += (base + j < P) ? (int)(run[base + j] & 1ull) : 0;
+  }
+  cnt = __reduce_add_sync(0xffffffffu, cnt);
+  if (lane == 0) s_warp[warp] = cnt;
+  __syncthreads();
+  if (warp == 0) {
+    const int t = __reduce_add_sync(0xffffffffu, s_warp[lane]);
+    if (lane == 0) chunk_fg[c * n_chunks + chunk] = t;
+  }
+}
+
+__global__ void __launch_bounds__(1024)
+lovasz_chunk_apply_kernel(int C, int cap, int n_chunks, int classes_all, unsigned long long cls_mask,
+                          const int32_t* __restrict__ hist, const int32_t* __restrict__ info,
+                          const unsigned long long* __restrict__ sorted, const int32_t* __restrict__ chunk_fg,
+                          float* __restrict__ gval, int32_t* __restrict__ gpix, float* __restrict__ chunk_loss) {
   __shared__ int s_warp[32];
   __shared__ int s_carry;
   __shared__ float s_part[32];
-  const int c = blockIdx.x;
+  const int c = blockIdx.y, chunk = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int P = min(info[kLovP], cap);
-  if (!lov_included(classes_all, cls_mask, hist[c], c) || P == 0) {
-    if (threadIdx.x == 0) cls_loss[c] = 0.0f;
+  if (!lov_included(classes_all, cls_mask, hist[c], c) || chunk * kLovChunk >= P) {
+    if (threadIdx.x == 0) chunk_loss[c * n_chunks + chunk] = 0.0f;
     return;
   }
-  // the run of class c starts after the runs of the included classes with a larger id
-  int later = 0;
-  for (int cc = c + 1; cc < C; ++cc) later += lov_included(classes_all, cls_mask, hist[cc], cc) ? 1 : 0;
-  const unsigned long long* run = sorted + (size_t)later * P;
+  const unsigned long long* run = lov_run(sorted, C, c, P, classes_all, cls_mask, hist);
   const float gts = (float)hist[c];
-  if (threadIdx.x == 0) s_carry = 0;
+  if (warp == 0) {            // foreground keys in the earlier chunks of this class
+    int t = 0;
+    for (int j = lane; j < chunk; j += 32) t += chunk_fg[c * n_chunks + j];
+    t = __reduce_add_sync(0xffffffffu, t);
+    if (lane == 0) s_carry = t;
+  }
+  const int base = chunk * kLovChunk + threadIdx.x * kLovItems;
+  unsigned long long k[kLovItems];
+  int cnt = 0;
+#pragma unroll
+  for (int j = 0; j < kLovItems; ++j) {
+    k[j] = (base + j < P) ? run[base + j] : 0ull;
+    cnt += (int)(k[j] & 1ull);
+  }
+  int incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+  if (lane == 31) s_warp[warp] = incl;
   __syncthreads();
+  if (warp == 0) {
+    const int w = s_warp[lane];
+    int wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += v; }
+    s_warp[lane] = wi - w;                    // exclusive prefix over warps
+  }
+  __syncthreads();
+  int F = s_carry + s_warp[warp] + incl - cnt;   // foreground among the ranks before this thread's
   float acc = 0.0f;
-  const int chunk = 1024 * kLovItems;
-  for (int r0 = 0; r0 < P; r0 += chunk) {
-    const int base = r0 + threadIdx.x * kLovItems;
-    unsigned long long k[kLovItems];
-    int cnt = 0;
 #pragma unroll
-    for (int j = 0; j < kLovItems; ++j) {
-      k[j] = (base + j < P) ? run[base + j] : 0ull;
-      cnt += (int)(k[j] & 1ull);
+  for (int j = 0; j < kLovItems; ++j) {
+    const int r = base + j;
+    if (r < P) {
+      const int fg = (int)(k[j] & 1ull);
+      F += fg;
+      const float g = lovasz_grad_at(gts, r, F, fg);
+      const unsigned ebits = (unsigned)((k[j] >> 26) & 0xFFFFFFFFull);
+      acc += __uint_as_float(ebits) * g;
+      const float sign = (ebits == 0u) ? 0.0f : ((k[j] & 2ull) ? -1.0f : 1.0f);
+      gval[(size_t)c * cap + r] = g * sign;
+      gpix[(size_t)c * cap + r] = (int)(0xFFFFFFu - (unsigned)((k[j] >> 2) & 0xFFFFFFull));
     }
-    // exclusive scan of cnt over the block
-    int incl = cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-    if (lane == 31) s_warp[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-      int w = s_warp[lane], wi = w;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += v; }
-      s_warp[lane] = wi - w;                    // exclusive prefix over warps
-      if (lane == 31) s_part[0] = __int_as_float(wi);   // block total (bits)
-    }
-    __syncthreads();
-    int F = s_carry + s_warp[warp] + incl - cnt;   // foreground among the ranks before this thread's
-    const int block_total = __float_as_int(s_part[0]);
-#pragma unroll
-    for (int j = 0; j < kLovItems; ++j) {
-      const int r = base + j;
-      if (r < P) {
-        const int fg = (int)(k[j] & 1ull);
-        F += fg;
-        const float g = lovasz_grad_at(gts, r, F, fg);
-        const unsigned ebits = (unsigned)((k[j] >> 26) & 0xFFFFFFFFull);
-        acc += __uint_as_float(ebits) * g;
-        const float sign = (ebits == 0u) ? 0.0f : ((k[j] & 2ull) ? -1.0f : 1.0f);
-        gval[(size_t)c * cap + r] = g * sign;
-        gpix[(size_t)c * cap + r] = (int)(0xFFFFFFu - (unsigned)((k[j] >> 2) & 0xFFFFFFull));
-      }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) s_carry += block_total;
-    __syncthreads();
   }
   acc = warp_sum(acc);
   if (lane == 0) s_part[warp] = acc;
@@ -429,8 +475,17 @@ lovasz_sorted_kernel(int C, int cap, int classes_all, unsigned long long cls_mas
   if (warp == 0) {
     float t = s_part[lane];
     t = warp_sum(t);
-    if (lane == 0) cls_loss[c] = t;
+    if (lane == 0) chunk_loss[c * n_chunks + chunk] = t;
   }
+}
+
+__global__ void __launch_bounds__(32)
+lovasz_chunk_reduce_kernel(int n_chunks, const float* __restrict__ chunk_loss, float* __restrict__ cls_loss) {
+  const int c = blockIdx.x, lane = threadIdx.x;
+  float t = 0.0f;
+  for (int j = lane; j < n_chunks; j += 32) t += chunk_loss[c * n_chunks + j];   // lane-strided, then a tree:
+  t = warp_sum(t);                                                               // one fixed order
+  if (lane == 0) cls_loss[c] = t;
 }
 
 // ------------------------------------------------------------- backward ----
@@ -506,11 +561,20 @@ extern "C" int c3d_lovasz_forward(const float* probs, const int64_t* labels, int
                                                         stream));
     }
     {
-      KernelTimer kt__("lovasz_sorted_kernel", stream);
-      lovasz_sorted_kernel<<<C, 1024, 0, stream>>>(C, cap, classes_all, cls_mask, w.hist, w.info, w.keys2, w.gval,
-                                                   w.gpix, w.cls_loss);
+      const int n_chunks = (cap + kLovChunk - 1) / kLovChunk;
+      const dim3 cgrid(n_chunks, C);
+      { KernelTimer kt__("lovasz_chunk_count_kernel", stream);
+        lovasz_chunk_count_kernel<<<cgrid, 1024, 0, stream>>>(C, cap, n_chunks, classes_all, cls_mask, w.hist, w.info,
+                                                              w.keys2, w.chunk_fg); }
+      if ((rc = check_launch("lovasz_chunk_count_kernel"))) return rc;
+      { KernelTimer kt__("lovasz_chunk_apply_kernel", stream);
+        lovasz_chunk_apply_kernel<<<cgrid, 1024, 0, stream>>>(C, cap, n_chunks, classes_all, cls_mask, w.hist, w.info,
+                                                              w.keys2, w.chunk_fg, w.gval, w.gpix, w.chunk_loss); }
+      if ((rc = check_launch("lovasz_chunk_apply_kernel"))) return rc;
+      { KernelTimer kt__("lovasz_chunk_reduce_kernel", stream);
+        lovasz_chunk_reduce_kernel<<<C, 32, 0, stream>>>(n_chunks, w.chunk_loss, w.cls_loss); }
+      if ((rc = check_launch("lovasz_chunk_reduce_kernel"))) return rc;
     }
-    if ((rc = check_launch("lovasz_sorted_kernel"))) return rc;
     KernelTimer kt__("lovasz_finalize_kernel", stream);
     lovasz_finalize_kernel<<<1, 32, 0, stream>>>(C, cap, classes_all, cls_mask, w.hist, w.info, w.cls_loss, loss_out);
     return check_launch("lovasz_finalize_kernel");

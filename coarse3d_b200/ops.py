@@ -423,8 +423,10 @@ def lovasz_softmax(probs, labels, ignore=None, classes="present", max_valid=None
             lab_ok &= labels != int(ignore)
         n_valid = int(lab_ok.sum())
         max_valid = 1024
-        while max_valid < n_valid:
-            max_valid *= 2
+        while max_valid < min(n_valid, 32768):
+            max_valid *= 2                       # shared-memory / all-pairs paths: power-of-two capacities
+        if n_valid > 32768:                      # radix path: the sort handles C * capacity keys
+            max_valid = (n_valid + 4095) // 4096 * 4096
         max_valid = min(max_valid, max(labels.numel(), 1))
         workspace = None
     if workspace is None:

@@ -8,7 +8,7 @@ for B, frac in ((8, 0.3), (8, 1.0), (64, 0.3)):
     labels = torch.randint(1, C, (B, H, W), device="cuda", generator=g) * (torch.rand(B, H, W, device="cuda", generator=g) < frac)
     n_valid = int((labels != 0).sum()); cap = 1024
     while cap < n_valid: cap *= 2
-    cap = min(cap, labels.numel())
+    cap = min(cap, labels.numel()) if n_valid <= 32768 else (n_valid + 4095) // 4096 * 4096
     p = probs.requires_grad_(True)
     for _ in range(2):
         p.grad = None
