@@ -51,6 +51,23 @@ class StepInputs:
         self.keep_mask = (lab > 0).contiguous()
 
 
+def fill_partition(n_floats, shares, chains=True, page=2048):
+    """Split a flat buffer of `n_floats` float32 into five contiguous ranges (lo, hi) for the
+    carriers (projection, label split, EMA rows, loss rows, KNN vote): the first four take
+    `shares[j]` of the buffer rounded DOWN to whole 8 KB pages (`page` floats), the vote takes the
+    rest.  With chains=False the prototype chains' shares (indices 1..3) stay with the vote.
+    The ranges tile [0, n_floats) exactly; every boundary but the last is page-aligned."""
+    out, lo = [], 0
+    for j, f in enumerate(shares):
+        if j > 0 and not chains:
+            f = 0.0
+        hi = min(n_floats, lo + int(n_floats * max(f, 0.0)) // page * page)
+        out.append((lo, hi))
+        lo = hi
+    out.append((lo, n_floats))
+    return out
+
+
 class HotPathStep:
     """Pre-allocated, allocation-free step over rotating input sets."""
 
@@ -164,16 +181,8 @@ class HotPathStep:
         """The gradient buffer as five flat 8 KB-aligned slices: (proj, split, ema, loss, knn);
         without the prototype chains their shares stay with the vote."""
         flat = self.grad.view(-1)
-        n, page = flat.numel(), 2048          # floats per 8 KB page
-        out, lo = [], 0
-        for j, f in enumerate(self.fill_shares):
-            if j > 0 and not chains:
-                f = 0.0
-            hi = min(n, lo + int(n * max(f, 0.0)) // page * page)
-            out.append(flat[lo:hi] if hi > lo else None)
-            lo = hi
-        out.append(flat[lo:] if lo < n else None)
-        return out
+        return [flat[lo:hi] if hi > lo else None
+                for lo, hi in fill_partition(flat.numel(), self.fill_shares, chains)]
 
     # bytes the reference dtypes move per step (BASELINE.md section 3)
     def algorithmic_bytes(self):
