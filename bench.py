@@ -52,6 +52,11 @@ def parse():
                     help="order of the points inside a scan: random (BASELINE's synthetic spec, the hard "
                          "case for the z-buffer atomics and the KNN gathers) or sensor = (beam, azimuth), "
                          "what a spinning LiDAR's .bin file holds")
+    ap.add_argument("--label-frac", type=float, default=None,
+                    help="pseudo-label regime the reference trains in once entropy_selection is on "
+                         "(tasks/weak_segmentation/trainer.py:654-686): the contrastive loss sees the weak labels "
+                         "PLUS the class of this fraction of the occupied pixels (e.g. 0.3), the EMA update keeps "
+                         "the weak labels (model.forward, :625-630); a measurement variant, not a BASELINE config")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--serial", action="store_true", help="one stream, no overlap of the chains")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -91,6 +96,7 @@ def workload_config(args, world, synth):
         "global_batch": args.batch_per_gpu * world, "points_per_scan": shp.n_points,
         "proj": [shp.proj_h, shp.proj_w], "feature_dim": args.dim,
         "point_order": getattr(args, "point_order", "random"),
+        "loss_label_frac": getattr(args, "label_frac", None),
         "parallelism": "scan-sharded x%d, one all-reduce of [K*D|K] prototype sums" % world,
         "l2": "no flush: 3 rotating input sets of ~%d MB re-read inputs each and a %d MB gradient "
               "written per step, both larger than the 126 MB L2" % (
@@ -330,7 +336,8 @@ def main():
     B, K, Wu = args.batch_per_gpu, args.steps, max(args.warmup, 3)
 
     step = HotPathStep(shp, B, dim=args.dim, seed0=1000 + 10000 * rank, device=dev,
-                       concurrent=not args.serial, sensor_order=args.point_order == "sensor")
+                       concurrent=not args.serial, sensor_order=args.point_order == "sensor",
+                       loss_label_frac=args.label_frac)
     sampler = ClockSampler(local)
     sampler.start()
 

@@ -27,6 +27,8 @@ class StepInputs:
         self.points = torch.from_numpy(pts).to(device)
         self.offsets = torch.from_numpy(offs).to(device)
         self.weak = torch.from_numpy(weak).to(device)
+        self.full = torch.from_numpy(_full).to(device)
+        self.seed0 = seed0
         self.n_points = int(pts.shape[0])
         g = torch.Generator(device=device).manual_seed(seed0)
         self.feats = feats if feats is not None else \
@@ -38,8 +40,10 @@ class StepInputs:
         self.argmax = torch.randint(0, C, (batch, H, W), device=device, generator=g)  # int64
         self.labels = None      # (B,H,W) int64: weak labels of the winning points
         self.keep_mask = None   # (B,H,W) bool
+        self.labels_loss = None     # the contrastive loss's labels when they differ from the EMA's
+        self.keep_mask_loss = None  # (pseudo-label regime, trainer.py:654-686)
 
-    def derive_labels(self, proj):
+    def derive_labels(self, proj, loss_label_frac=None):
         """Projected weak-label image, like the reference's loader builds it
         (wss_sem_kitti_loader.py:124-132): label of the point that won the pixel."""
         B = self.batch
@@ -49,6 +53,16 @@ class StepInputs:
         lab[valid] = self.weak[gidx[valid]]
         self.labels = lab.contiguous()
         self.keep_mask = (lab > 0).contiguous()
+        if loss_label_frac is not None:
+            # stand-in for entropy_based_selection's output: the weak labels plus the ground-truth
+            # class on a random `loss_label_frac` of the occupied pixels
+            g = torch.Generator(device=lab.device).manual_seed(self.seed0 + 17)
+            pick = valid & (torch.rand(lab.shape, device=lab.device, generator=g) < loss_label_frac)
+            full_img = torch.zeros_like(gidx)
+            full_img[valid] = self.full[gidx[valid]]
+            ll = torch.where(pick, full_img, lab)
+            self.labels_loss = ll.contiguous()
+            self.keep_mask_loss = (ll > 0).contiguous()
 
 
 def fill_partition(n_floats, shares, chains=True, page=2048):
@@ -73,7 +87,8 @@ class HotPathStep:
 
     def __init__(self, shape, batch, dim=128, sub_protos=20, num_anchor=512, temperature=0.07,
                  momentum=0.999, n_sets=3, seed0=1000, device="cuda", group=None,
-                 knn=(5, 5, 1.0, 1.0), concurrent=True, parts=None, bank_seed=7, sensor_order=False):
+                 knn=(5, 5, 1.0, 1.0), concurrent=True, parts=None, bank_seed=7, sensor_order=False,
+                 loss_label_frac=None):
         self.shape, self.batch, self.dim, self.M = shape, batch, dim, sub_protos
         self.device, self.group = torch.device(device), group
         self.knn_k, self.knn_s, self.knn_sigma, self.knn_cutoff = knn
@@ -90,7 +105,7 @@ class HotPathStep:
         self.n_points = n
         self.proj_bufs = [ops.ProjectionBuffers(batch, n, 4, H, W, self.device) for _ in self.sets]
         for s, b in zip(self.sets, self.proj_bufs):
-            s.derive_labels(ops.project_batch(s.points, s.offsets, self.fov, H, W, buffers=b))
+            s.derive_labels(ops.project_batch(s.points, s.offsets, self.fov, H, W, buffers=b), loss_label_frac)
         # the bank is a model parameter: the SAME initial value on every rank (seed0 differs per
         # rank, it seeds the scans), kept identical afterwards by the summed update
         g = torch.Generator(device=self.device).manual_seed(bank_seed)
@@ -101,7 +116,10 @@ class HotPathStep:
         self.max_rows = min(batch * H * W, 1 << 17)
         # fused prototype step (one label split for the EMA update and the loss); its workspace
         # begins with a loss workspace, so the unfused calls can run on it too
-        self.fused_step = _os.environ.get("C3D_FUSED_STEP", "1") == "1"
+        # pseudo-label regime: the EMA sees the weak labels (model.forward, trainer.py:625-630), the
+        # loss the expanded ones (:680-686): two label splits, so not the fused step
+        self.loss_label_frac = loss_label_frac
+        self.fused_step = _os.environ.get("C3D_FUSED_STEP", "1") == "1" and loss_label_frac is None
         self.loss_ws = ops.proto_step_workspace(batch, C, H * W, dim, sub_protos, num_anchor, self.max_rows,
                                                 self.device)
         self.loss = torch.zeros((), device=self.device)
@@ -473,7 +491,9 @@ class HotPathStep:
                             normalised_out=self.bank_n, seed_counters=sc)
 
     def _loss_fwd(self, s, seed, phases=3):
-        ops.proto_loss_forward_raw(s.feats, s.probs, s.labels, s.keep_mask, self.protos, self.cfg,
+        labels = s.labels if s.labels_loss is None else s.labels_loss
+        keep = s.keep_mask if s.keep_mask_loss is None else s.keep_mask_loss
+        ops.proto_loss_forward_raw(s.feats, s.probs, labels, keep, self.protos, self.cfg,
                                    None, seed, self.loss_ws, self.loss, phases=phases)
 
     def _ema(self, s, seed):
