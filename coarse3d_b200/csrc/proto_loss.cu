@@ -527,8 +527,11 @@ loss_rows16_kernel(RowsParams p) {
   const int cg = threadIdx.x & 63, rg = threadIdx.x >> 6;
   const int n_rows = p.info[kInfoU];
   const int T = p.info[kInfoT];
-  const int32_t* rb_s = (T + 1 <= kRbCap) ? s_rb : nullptr;
-  if (rb_s && (int)threadIdx.x <= T) s_rb[threadIdx.x] = __ldg(p.row_base + threadIdx.x);
+  // row -> segment search: every `rb_stride`-th entry of row_base[0..T] lives in shared memory
+  // (binary search there), the entries in between come from ONE round of independent loads
+  const int rb_stride = (T + kRbCap) / kRbCap;          // 1 when the whole table fits
+  const int rb_n = T / rb_stride + 1;                   // coarse entries 0, stride, 2 stride, ... <= T
+  if ((int)threadIdx.x < rb_n) s_rb[threadIdx.x] = __ldg(p.row_base + threadIdx.x * rb_stride);
   const int n_groups = (n_rows + kGroupRows - 1) / kGroupRows;
   const float scale_row = p.temperature / p.base_temperature;
   const float inv_R = 1.0f / ((float)p.A * (float)T);  // mean over R = A*T rows (:193)
@@ -540,23 +543,63 @@ loss_rows16_kernel(RowsParams p) {
   if (!staged) stage_bank_tile_issue(s_bank, p.bank_n, 0, Kc, BL);
   rows_sync();  // s_rb visible
 
+  // The chain row -> segment -> distinct-slot list -> slot -> (count, pixel, class) is four
+  // dependent global round trips before the features can be fetched.  It is walked ONE GROUP
+  // AHEAD, one link per phase of the current group (each link's load is issued at a phase
+  // boundary and first used a phase later), so that a group's P0 only waits for its features.
+  bool n_act[2];
+  int n_row[2], n_seg[2], n_base[2], n_slot[2], n_cnt[2], n_pix[2], n_cls[2];
+  auto link_a = [&](int g2) {        // row -> segment index, segment id + first row of the segment
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      const int row = g2 * kGroupRows + warp * 2 + rr;
+      n_row[rr] = row;
+      n_act[rr] = g2 < n_groups && row < n_rows;
+      n_seg[rr] = 0; n_base[rr] = 0;
+      if (n_act[rr]) {
+        int lo = 0, hi = rb_n;       // s_rb[lo] <= row < s_rb[hi]
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_rb[mid] <= row) lo = mid; else hi = mid; }
+        lo *= rb_stride;
+        if (rb_stride > 1) {         // row_base is non-decreasing: count the entries <= row
+          int more = 0;
+          for (int j = 1; j < rb_stride; ++j) {
+            const int idx = lo + j;
+            more += (idx < T && __ldg(p.row_base + idx) <= row) ? 1 : 0;
+          }
+          lo += more;
+        }
+        n_seg[rr] = __ldg(p.seg_of_t + lo);
+        n_base[rr] = __ldg(p.row_base + lo);
+      }
+    }
+  };
+  auto link_b = [&]() {              // segment id -> start of its distinct-slot list
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) if (n_act[rr]) n_seg[rr] = __ldg(p.seg_start + n_seg[rr]);
+  };
+  auto link_c = [&]() {              // -> slot
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr)
+      n_slot[rr] = n_act[rr] ? __ldcg(p.dist_list + n_seg[rr] + (n_row[rr] - n_base[rr])) : 0;
+  };
+  auto link_d = [&]() {              // -> multiplicity, pixel, class
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      n_cnt[rr] = n_act[rr] ? __ldcg(p.cnt_list + n_slot[rr]) : 0;
+      n_pix[rr] = n_act[rr] ? p.pix_list[n_slot[rr]] : 0;
+      n_cls[rr] = n_act[rr] ? p.cls_list[n_slot[rr]] : 0;
+    }
+  };
+  link_a(blockIdx.x); link_b(); link_c(); link_d();     // the CTA's first group: un-overlapped
+
   for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
-    // ---- P0: gather + L2-normalise two rows per warp (:166); the two rows' dependent
-    //      load chains (row -> slot -> pixel -> features) are issued interleaved
+    // ---- P0: gather + L2-normalise two rows per warp (:166)
     float areg[2][kDJ];
     int slot[2], cnt2[2], cls2[2], gpix2[2];
     bool act[2];
 #pragma unroll
     for (int rr = 0; rr < 2; ++rr) {
-      const int row = grp * kGroupRows + warp * 2 + rr;
-      act[rr] = row < n_rows;
-      slot[rr] = act[rr] ? slot_of_row(row, T, p.row_base, p.seg_of_t, p.seg_start, p.dist_list, rb_s) : 0;
-    }
-#pragma unroll
-    for (int rr = 0; rr < 2; ++rr) {
-      cnt2[rr] = act[rr] ? __ldcg(p.cnt_list + slot[rr]) : 0;
-      gpix2[rr] = act[rr] ? p.pix_list[slot[rr]] : 0;
-      cls2[rr] = act[rr] ? p.cls_list[slot[rr]] : 0;
+      act[rr] = n_act[rr]; slot[rr] = n_slot[rr]; cnt2[rr] = n_cnt[rr]; gpix2[rr] = n_pix[rr]; cls2[rr] = n_cls[rr];
     }
 #pragma unroll
     for (int rr = 0; rr < 2; ++rr) {
@@ -600,6 +643,7 @@ loss_rows16_kernel(RowsParams p) {
     if (!staged) { cp_async_wait_all(); staged = true; }
     rows_sync();
     DBG_STAMP(2);
+    link_a(grp + gridDim.x);
 
     // ---- P1: logits z = (a_hat . c_hat) / temperature (:168-172)
     for (int tile = 0; tile < p.n_tiles; ++tile) {
@@ -623,6 +667,7 @@ loss_rows16_kernel(RowsParams p) {
     rows_sync();
 
     DBG_STAMP(3);
+    link_b();
     // ---- P2: softmax statistics, loss term, dL/dlogit (:175-193); one half-warp per
     //      row, so the two rows of a warp advance together
     {
@@ -710,6 +755,7 @@ loss_rows16_kernel(RowsParams p) {
     rows_sync();
 
     DBG_STAMP(4);
+    link_c();
     if (kWithGrad && kMma) {
       // ---- P3 (tensor cores): d a_hat = G . bank; warp w owns the feature slices 8 (w + 8 j)
       constexpr int kNTG = (kDJ + 1) / 2;
@@ -797,6 +843,7 @@ loss_rows16_kernel(RowsParams p) {
       }
       rows_sync();
     }
+    link_d();
     if (kWithGrad) {
       // ---- P4: normalize backward, weighted gradient row
 #pragma unroll
